@@ -1,0 +1,238 @@
+/*
+ * b200rt.h -- C ABI of libb200rt.so, the B200 (sm_100a) sequential real-ray
+ * trace engine that replaces the hot path of mjhoptics/ray-optics:
+ *
+ *   rayoptics.raytr.raytrace.trace()/trace_raw()   src/rayoptics/raytr/raytrace.py:51-264
+ *   and the per-ray loops stacked on it             src/rayoptics/raytr/trace.py:537-605,
+ *                                                   src/rayoptics/raytr/analyses.py:212-230,437-455,666-696
+ *
+ * The reference is pure Python and has no FFI of its own; the binding a
+ * maintainer would add is a ctypes stub.  Every entry
+ * point below takes plain pointers and sizes -- no torch / numpy types.
+ *
+ * Conventions
+ *   - all functions return RT_OK (0) or a negative rt_error code; the message
+ *     for the calling thread is available from rt_last_error().
+ *   - per-ray failures (missed surface, TIR, blocked by an aperture) are DATA
+ *     (`status`, `fail_surf` arrays), never C errors.  They map 1:1 onto the
+ *     reference's TraceError subclasses (src/rayoptics/raytr/traceerror.py:11-52).
+ *   - pointers documented "DEVICE" must be device pointers on the table's
+ *     device; pointers documented "HOST" are host pointers that are read
+ *     before the call returns.
+ *   - the caller owns every ray / result buffer; the library owns only the
+ *     immutable table / grid handles.  Launches are asynchronous on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - all floating point is IEEE binary64; the arithmetic contract (which
+ *     operations are fused) is stated in DESIGN.md and is what makes results
+ *     bit-identical to the reference's numpy path.
+ */
+#ifndef B200RT_H
+#define B200RT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+#define RT_MAX_COEFS 20     /* EvenPolynomial uses <=10, RadialPolynomial <=20 */
+#define RT_MAX_APERTURES 4  /* Surface.clear_apertures entries honoured per interface */
+#define RT_SEG_DOUBLES 10   /* one ray segment = p[3], d[3], dst, nrml[3]  (raytr/__init__.py:36) */
+#define RT_SUMMARY_DOUBLES 16
+
+/* error codes (function return values) */
+enum rt_error {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,     /* bad argument */
+    RT_ERR_CUDA = -2,        /* CUDA runtime error, text in rt_last_error() */
+    RT_ERR_UNSUPPORTED = -3, /* interface type not representable in the table */
+    RT_ERR_NOMEM = -4
+};
+
+/* SurfaceProfile subclasses, src/rayoptics/elem/profiles.py */
+enum rt_profile {
+    RT_PROFILE_SPHERICAL = 0,  /* profiles.py:218-416 */
+    RT_PROFILE_CONIC = 1,      /* profiles.py:449-680 */
+    RT_PROFILE_EVENPOLY = 2,   /* profiles.py:682-889 */
+    RT_PROFILE_RADIALPOLY = 3, /* profiles.py:891-1116 */
+    RT_PROFILE_YTOROID = 4,    /* profiles.py:1119-1372 */
+    RT_PROFILE_XTOROID = 5     /* profiles.py:1375-1437 */
+};
+
+/* Interface.interact_mode, src/rayoptics/seq/interface.py:42-49 */
+enum rt_mode {
+    RT_MODE_TRANSMIT = 0,
+    RT_MODE_REFLECT = 1,
+    RT_MODE_DUMMY = 2,
+    RT_MODE_PHANTOM = 3
+};
+
+/* per-ray status; 1..4 are the TraceError subclasses of traceerror.py */
+enum rt_status {
+    RT_RAY_OK = 0,
+    RT_RAY_MISSED = 1,     /* TraceMissedSurfaceError */
+    RT_RAY_TIR = 2,        /* TraceTIRError */
+    RT_RAY_BLOCKED = 3,    /* TraceRayBlockedError */
+    RT_RAY_EVANESCENT = 4, /* TraceEvanescentRayError (phase elements; never produced in v1) */
+    RT_RAY_NUMERIC = 5     /* the reference would raise an uncaught ValueError /
+                              ZeroDivisionError (sqrt of a negative in
+                              EvenPolynomial.df, profiles.py:870-873) */
+};
+
+/* Aperture subclasses, src/rayoptics/elem/surface.py:340-494 */
+enum rt_aperture_type {
+    RT_APERTURE_CIRCULAR = 1,    /* surface.py:397-431 */
+    RT_APERTURE_RECTANGULAR = 2, /* surface.py:434-469 */
+    RT_APERTURE_ELLIPTICAL = 3   /* surface.py:472-494: no point_inside() -> always blocks */
+};
+
+typedef struct rt_aperture_desc {
+    int32_t type;           /* rt_aperture_type */
+    int32_t is_obscuration; /* Aperture.is_obscuration */
+    double a;               /* Circular.radius | x_half_width */
+    double b;               /* y_half_width (unused for Circular) */
+    double x_offset;        /* Aperture.x_offset */
+    double y_offset;        /* Aperture.y_offset */
+} rt_aperture_desc;
+
+/* One entry of SequentialModel.path(wvl): (Intfc, Gap, Tfrm, Indx, Zdir),
+ * src/rayoptics/optical/model_constants.py:12, seq/sequential.py:149-202.
+ * The refractive index lives in the separate n_by_wvl table. */
+typedef struct rt_surface_desc {
+    int32_t profile;      /* rt_profile */
+    int32_t mode;         /* rt_mode */
+    int32_t z_dir;        /* path tuple Zdir: +1 / -1 */
+    int32_t n_coefs;      /* profile.max_nonzero_coef (polynomial profiles) */
+    int32_t has_tfrm;     /* 0: Tfrm rotation is the identity (only `t` is applied);
+                             1: rotation stored Fortran-ordered in numpy (r.transpose() of a C array,
+                                elem/transform.py:86) -> y_i = fma(a_i2,v2, fma(a_i1,v1, a_i0*v0));
+                             2: C-contiguous in numpy -> y_i = fma(a_i2,v2, fma(a_i0,v0, a_i1*v1))
+                             (the two roundings numpy/OpenBLAS dgemv produce) */
+    int32_t n_apertures;  /* len(ifc.clear_apertures), 0 -> max_aperture test */
+    double cv;            /* profile.cv */
+    double cc;            /* profile.cc */
+    double ec;            /* profile.ec (= cc + 1.0 evaluated by the host) */
+    double cR;            /* toroid sweep curvature */
+    double max_aperture;  /* Interface.max_aperture */
+    double coefs[RT_MAX_COEFS];
+    double rt[9];         /* Tfrm[0], row-major: applied as rt . (p - t) on the way to the NEXT interface */
+    double t[3];          /* Tfrm[1] */
+    rt_aperture_desc apertures[RT_MAX_APERTURES];
+} rt_surface_desc;
+
+/* keyword arguments of trace_raw(), raytrace.py:83-121 */
+typedef struct rt_opts {
+    double eps;                  /* eps=1e-12 */
+    double pt_inside_fuzz;       /* pt_inside_fuzz; <0 means None -> the 1e-5 default of point_inside() */
+    int32_t check_apertures;     /* check_apertures=False */
+    int32_t intersect_obj;       /* intersect_obj=True */
+    int32_t filter_out_phantoms; /* filter_out_phantoms=False */
+    int32_t first_surf;          /* first_surf (trace() default 1, trace_raw() default 0) */
+    int32_t last_surf;           /* last_surf; <0 means None */
+    int32_t wvl_idx;             /* row of n_by_wvl used when the per-ray wvl_idx pointer is NULL */
+} rt_opts;
+
+/* Result buffers of a bundle / grid trace; every pointer is DEVICE and
+ * optional (NULL = not wanted).  Arrays hold one element per ray. */
+typedef struct rt_out {
+    /* last ray segment, i.e. ray[-1] of the (possibly partial) RayPkg */
+    double *px, *py, *pz;   /* RaySeg.p    */
+    double *dx, *dy, *dz;   /* RaySeg.d    */
+    double *nx, *ny, *nz;   /* RaySeg.nrml */
+    double *dst;            /* RaySeg.dst (0 unless the ray missed: then pp_dst, raytrace.py:232) */
+    double *op;             /* op_delta on success, opl so far on failure (raytrace.py:236,261) */
+    int32_t *status;        /* rt_status */
+    int32_t *fail_surf;     /* TraceError.surf; -1 on success */
+    int32_t *n_seg;         /* number of valid segments in `full` */
+    /* whole ray, structure of arrays: full[(seg*RT_SEG_DOUBLES + c)*full_stride + ray],
+     * c = 0..2 p, 3..5 d, 6 dst, 7..9 nrml; seg < n_ifc.  Segments >= n_seg are not written. */
+    double *full;
+    int64_t full_stride;    /* >= n_rays */
+    /* transverse ray aberration at the image (grid traces only):
+     * p + (foc/d_z) d - ref_img, analyses.py:561-580 */
+    double *abr_x, *abr_y;
+} rt_out;
+
+typedef struct rt_table rt_table;
+typedef struct rt_grid rt_grid;
+
+/* ---- table: the compiled form of SequentialModel.path() for all wavelengths */
+
+/* surfs: HOST [n_ifc]; n_by_wvl: HOST [n_wvl][n_ifc] refractive index following
+ * each interface (path tuple Indx, unsigned; seq/sequential.py:259-274). */
+int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc,
+                    const double *n_by_wvl, int32_t n_wvl,
+                    int32_t device, rt_table **out);
+int rt_table_destroy(rt_table *table);
+int rt_table_dims(const rt_table *table, int32_t *n_ifc, int32_t *n_wvl, int32_t *device);
+
+/* ---- bundle trace: replaces a Python loop over rt.trace()/trace_raw()
+ * (raytrace.py:51-264; callers raytr/trace.py:250,310; analyses.py:458-510).
+ * px..dz: DEVICE [n_rays] start point / direction cosines in the object
+ * interface's coordinates; wvl_idx: DEVICE [n_rays] or NULL. */
+int rt_trace_bundle(const rt_table *table, int64_t n_rays,
+                    const double *px, const double *py, const double *pz,
+                    const double *dx, const double *dy, const double *dz,
+                    const int32_t *wvl_idx, const rt_opts *opts,
+                    const rt_out *out, void *stream);
+
+/* ---- grid trace: replaces trace.trace_grid / analyses.trace_ray_grid /
+ * trace_ray_list / trace_ray_fan (raytr/trace.py:537-605, analyses.py:212-230,
+ * 437-455,666-696) including the start-ray generation of
+ * OpticalSpecs.ray_start_from_osp 'epd' branch (raytr/opticalspec.py:289-366),
+ * Field.apply_vignetting (opticalspec.py:1339-1353) and the refocus /
+ * transverse-aberration step (analyses.py:561-580). */
+
+typedef struct rt_field_desc {
+    double pt0[3];   /* ray start point on the object interface (opticalspec.py:361) */
+    double aim[2];   /* fld.aim_info: aim point on the paraxial entrance pupil (opticalspec.py:357) */
+    double vlx, vux, vly, vuy; /* Field vignetting factors */
+} rt_field_desc;
+
+typedef struct rt_grid_spec {
+    int32_t n_fields, n_wvls;  /* tiles = n_fields * n_wvls, ordered field-major */
+    int32_t nx, ny;            /* pupil samples per tile: x outer, y inner (trace.py:572-604) */
+    const rt_field_desc *fields; /* HOST [n_fields] */
+    const int32_t *wvl_idx;    /* HOST [n_wvls] rows of the table's n_by_wvl */
+    const double *pupil_x;     /* HOST [n_fields][nx] relative pupil x before vignetting */
+    const double *pupil_y;     /* HOST [n_fields][ny] */
+    const double *ref_img;     /* HOST [n_fields][n_wvls][2] reference image point (ref_sphere[0]) or NULL (=0) */
+    int32_t apply_vignetting;  /* trace_base(apply_vignetting=...) trace.py:289-292 */
+    int32_t flip_z_dir;        /* seq_model.z_dir[0]: dir0 is negated when dir0.z*z_dir < 0 (trace.py:305-308) */
+    double eprad;              /* pupil_value/2 (opticalspec.py:340) */
+    double z_pupil;            /* fod.obj_dist + z_enp: z of the aim plane (opticalspec.py:360) */
+    double foc;                /* focus shift used for abr_x/abr_y (analyses.py:572) */
+} rt_grid_spec;
+
+int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out);
+int rt_grid_destroy(rt_grid *grid);
+/* total rays and the chunk geometry used for sharding / summaries */
+int rt_grid_dims(const rt_grid *grid, int64_t *n_rays, int64_t *n_chunks, int32_t *chunk_rays);
+
+/* Trace chunks [chunk_begin, chunk_end) of the grid.  A chunk is `chunk_rays`
+ * consecutive rays of one (field, wvl) tile (the last chunk of a tile may be
+ * short); flattened ray index = ((f*n_wvls + w)*nx + i)*ny + j.  Per-ray
+ * outputs are indexed by (flattened ray index - first ray of chunk_begin).
+ * summary: DEVICE [n_fields*n_wvls][RT_SUMMARY_DOUBLES] or NULL; receives this
+ * call's partial per-tile sums (deterministic order):
+ *   0 n_ok 1 n_missed 2 n_tir 3 n_blocked 4 n_other
+ *   5 sum_x 6 sum_y 7 sum_xx 8 sum_yy 9 sum_xy (of abr_x/abr_y over ok rays)
+ *   10 min_x 11 max_x 12 min_y 13 max_y 14 sum_op 15 reserved
+ * scratch: DEVICE, rt_grid_scratch_bytes() bytes, needed when summary != NULL. */
+int64_t rt_grid_scratch_bytes(const rt_grid *grid, int64_t chunk_begin, int64_t chunk_end);
+int rt_trace_grid(const rt_table *table, const rt_grid *grid,
+                  int64_t chunk_begin, int64_t chunk_end,
+                  const rt_opts *opts, const rt_out *out,
+                  double *summary, void *scratch, void *stream);
+
+/* ---- misc */
+const char *rt_last_error(void);
+int rt_abi_version(void);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+int64_t rt_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RT_H */

@@ -1,0 +1,659 @@
+/*
+ * rt_oracle.c -- CPU restatement of the reference's sequential real-ray trace.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity oracle for libb200rt.so:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+ * arm may load it.  Nothing under rayoptics_b200/ links, imports or calls it.
+ *
+ * It restates, scalar and one ray at a time, the algorithm of
+ *   /root/reference/src/rayoptics/raytr/raytrace.py:19-38   bend, reflect
+ *   /root/reference/src/rayoptics/raytr/raytrace.py:83-264  trace_raw
+ *   /root/reference/src/rayoptics/elem/profiles.py:155-186  intersect_spencer
+ *   /root/reference/src/rayoptics/elem/profiles.py:310-362  Spherical
+ *   /root/reference/src/rayoptics/elem/profiles.py:569-609  Conic
+ *   /root/reference/src/rayoptics/elem/profiles.py:849-885  EvenPolynomial
+ *   /root/reference/src/rayoptics/elem/profiles.py:1070-1113 RadialPolynomial
+ *   /root/reference/src/rayoptics/elem/profiles.py:1317-1369,1429-1437 Y/XToroid
+ *   /root/reference/src/rayoptics/elem/surface.py:198-208,416-419,453-457 point_inside
+ *   /root/reference/src/rayoptics/seq/interface.py:113-122  default point_inside
+ *   /root/reference/src/rayoptics/util/misc_math.py:48-54   normalize
+ * and, for grids, the start-ray generation of
+ *   /root/reference/src/rayoptics/raytr/opticalspec.py:289-366,1339-1353
+ *   /root/reference/src/rayoptics/raytr/trace.py:289-308
+ *
+ * Arithmetic contract (pinned by tests/test_oracle_golden.py
+ * against vectors produced by the reference itself in tests/golden/):
+ *   - numpy's 3-vector dot / linalg.norm are the FMA chain
+ *       dot3(a,b) = fma(a2,b2, fma(a1,b1, a0*b0))
+ *   - every other expression is unfused IEEE binary64 in source order;
+ *   - sqrt and / are correctly rounded.
+ * Build with -ffp-contract=off (see Makefile); fma() below is the only fusion.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../include/b200rt.h"
+
+#define ST_OK RT_RAY_OK
+#define ST_MISS RT_RAY_MISSED
+#define ST_TIR RT_RAY_TIR
+#define ST_BLOCKED RT_RAY_BLOCKED
+#define ST_NUMERIC RT_RAY_NUMERIC
+
+static inline double dot3(const double a[3], const double b[3])
+{
+    /* OpenBLAS ddot for n=3 as seen from numpy: sequential FMA accumulation */
+    return fma(a[2], b[2], fma(a[1], b[1], a[0]*b[0]));
+}
+
+/* misc_math.normalize: v/norm(v), norm = sqrt(dot(v,v)); zero vector unchanged */
+static inline void normalize3(const double v[3], double out[3])
+{
+    double len = sqrt(dot3(v, v));
+    if (len == 0.0) {
+        out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
+    } else {
+        out[0] = v[0]/len; out[1] = v[1]/len; out[2] = v[2]/len;
+    }
+}
+
+/* ---- quadric root shared by Spherical.intersect and Conic.intersect
+ * s = cx2/(z_dir*sqrt(b*b - ax2*cx2) - b) with the reference's special cases */
+static inline int quadric_root(double ax2, double cx2, double b, double z_dir, double *s)
+{
+    if (!(b == 0) || !(cx2 == 0) || !(ax2 == 0)) {
+        double disc = b*b - ax2*cx2;
+        if (disc < 0.0)
+            return ST_MISS;                 /* math.sqrt ValueError */
+        double den = z_dir*sqrt(disc) - b;
+        if (den == 0.0 && cx2 != 0.0 && !isnan(cx2) && !isinf(cx2))
+            *s = 0.0;                       /* FloatingPointError (divide) -> s = 0 */
+        else
+            *s = cx2/den;                   /* includes 0/0 -> nan ('invalid' is not raised) */
+    } else {
+        *s = 0.0;
+    }
+    return ST_OK;
+}
+
+/* ---- polynomial / toroid pieces ------------------------------------------*/
+
+/* EvenPolynomial.sag (profiles.py:849-866) */
+static int evenpoly_sag(const rt_surface_desc *S, double x, double y, double *z_tot)
+{
+    double r2 = x*x + y*y;
+    double arg = 1. - S->ec*S->cv*S->cv*r2;
+    if (arg < 0.0) return ST_MISS;
+    double z = S->cv*r2/(1. + sqrt(arg));
+    double z_asp = 0.0, r_pow = r2;
+    for (int i = 0; i < S->n_coefs; i++) {
+        z_asp += S->coefs[i]*r_pow;
+        r_pow *= r2;
+    }
+    *z_tot = z + z_asp;
+    return ST_OK;
+}
+
+/* EvenPolynomial.df (profiles.py:870-885) */
+static int evenpoly_df(const rt_surface_desc *S, const double p[3], double g[3])
+{
+    double r2 = p[0]*p[0] + p[1]*p[1];
+    double arg = 1. - S->ec*S->cv*S->cv*r2;
+    if (arg < 0.0) return ST_NUMERIC;       /* uncaught ValueError in the reference */
+    double sq = sqrt(arg);
+    if (sq == 0.0) return ST_NUMERIC;       /* ZeroDivisionError */
+    double e = S->cv/sq;
+    double r_pow = 1.0, e_asp = 0.0, c_coef = 2.0;
+    for (int i = 0; i < S->n_coefs; i++) {
+        e_asp += c_coef*S->coefs[i]*r_pow;
+        c_coef += 2.0;
+        r_pow *= r2;
+    }
+    double e_tot = e + e_asp;
+    g[0] = -e_tot*p[0]; g[1] = -e_tot*p[1]; g[2] = 1.0;
+    return ST_OK;
+}
+
+/* RadialPolynomial.sag (profiles.py:1070-1088) */
+static int radpoly_sag(const rt_surface_desc *S, double x, double y, double *z_tot)
+{
+    double r2 = x*x + y*y;
+    double r = sqrt(r2);
+    double arg = 1. - S->ec*S->cv*S->cv*r2;
+    if (arg < 0.0) return ST_MISS;
+    double z = S->cv*r2/(1. + sqrt(arg));
+    double z_asp = 0.0, r_pow = r;
+    for (int i = 0; i < S->n_coefs; i++) {
+        z_asp += S->coefs[i]*r_pow;
+        r_pow *= r;
+    }
+    *z_tot = z + z_asp;
+    return ST_OK;
+}
+
+/* RadialPolynomial.df (profiles.py:1093-1113) */
+static int radpoly_df(const rt_surface_desc *S, const double p[3], double g[3])
+{
+    double r2 = p[0]*p[0] + p[1]*p[1];
+    double r = sqrt(r2);
+    double arg = 1. - S->ec*S->cv*S->cv*r2;
+    if (arg < 0.0) return ST_NUMERIC;
+    double sq = sqrt(arg);
+    if (sq == 0.0) return ST_NUMERIC;
+    double e = S->cv/sq;
+    double e_asp = 0.0;
+    double r_pow = (r == 0.0) ? 1.0 : 1/r;
+    double c_coef = 1.0;
+    for (int i = 0; i < S->n_coefs; i++) {
+        e_asp += c_coef*S->coefs[i]*r_pow;
+        c_coef += 1.0;
+        r_pow *= r;
+    }
+    double e_tot = e + e_asp;
+    g[0] = -e_tot*p[0]; g[1] = -e_tot*p[1]; g[2] = 1.0;
+    return ST_OK;
+}
+
+/* YToroid.fY (profiles.py:1329-1345) */
+static int ytoroid_fY(const rt_surface_desc *S, double y, double *out)
+{
+    double y2 = y*y;
+    double arg = 1. - S->ec*S->cv*S->cv*y2;
+    if (arg < 0.0) return ST_MISS;
+    double z = S->cv*y2/(1. + sqrt(arg));
+    double z_asp = 0.0, y_pow = y2;
+    for (int i = 0; i < S->n_coefs; i++) {
+        z_asp += S->coefs[i]*y_pow;
+        y_pow *= y2;
+    }
+    *out = z + z_asp;
+    return ST_OK;
+}
+
+/* YToroid.f (profiles.py:1347-1349) */
+static int ytoroid_f(const rt_surface_desc *S, const double p[3], double *f)
+{
+    double fY;
+    int st = ytoroid_fY(S, p[1], &fY);
+    if (st) return st;
+    *f = p[2] - fY - S->cR*(p[0]*p[0] + p[2]*p[2] - fY*fY)/2;
+    return ST_OK;
+}
+
+/* YToroid.df (profiles.py:1351-1369) */
+static int ytoroid_df(const rt_surface_desc *S, const double p[3], double g[3])
+{
+    double y2 = p[1]*p[1];
+    double arg = 1. - S->ec*S->cv*S->cv*y2;
+    if (arg < 0.0) return ST_NUMERIC;
+    double sq = sqrt(arg);
+    if (sq == 0.0) return ST_NUMERIC;
+    double e = S->cv/sq;
+    double e_asp = 0.0, y_pow = 1.0, c_coef = 2.0;
+    for (int i = 0; i < S->n_coefs; i++) {
+        e_asp += c_coef*S->coefs[i]*y_pow;
+        c_coef += 2.0;
+        y_pow *= y2;
+    }
+    double dfdY = e + e_asp;
+    double fY;
+    int st = ytoroid_fY(S, p[1], &fY);
+    if (st) return st;
+    g[0] = -S->cR*p[0];
+    g[1] = (S->cR*fY - 1)*(dfdY)*p[1];
+    g[2] = 1 - S->cR*p[2];
+    return ST_OK;
+}
+
+/* profile.f(p) for the iterated profiles */
+static int prof_f(const rt_surface_desc *S, const double p[3], double *f)
+{
+    double z;
+    int st;
+    switch (S->profile) {
+    case RT_PROFILE_EVENPOLY:
+        st = evenpoly_sag(S, p[0], p[1], &z);
+        if (st) return st;
+        *f = p[2] - z;
+        return ST_OK;
+    case RT_PROFILE_RADIALPOLY:
+        st = radpoly_sag(S, p[0], p[1], &z);
+        if (st) return st;
+        *f = p[2] - z;
+        return ST_OK;
+    case RT_PROFILE_YTOROID:
+        return ytoroid_f(S, p, f);
+    case RT_PROFILE_XTOROID: {
+        double q[3] = {p[1], p[0], p[2]};   /* profiles.py:1432-1433 */
+        return ytoroid_f(S, q, f);
+    }
+    }
+    return ST_NUMERIC;
+}
+
+/* profile.df(p) for every profile */
+static int prof_df(const rt_surface_desc *S, const double p[3], double g[3])
+{
+    switch (S->profile) {
+    case RT_PROFILE_SPHERICAL:              /* profiles.py:360-362 */
+        g[0] = -S->cv*p[0]; g[1] = -S->cv*p[1]; g[2] = 1.0 - S->cv*p[2];
+        return ST_OK;
+    case RT_PROFILE_CONIC:                  /* profiles.py:605-609 */
+        g[0] = -S->cv*p[0]; g[1] = -S->cv*p[1]; g[2] = 1.0 - S->ec*S->cv*p[2];
+        return ST_OK;
+    case RT_PROFILE_EVENPOLY:
+        return evenpoly_df(S, p, g);
+    case RT_PROFILE_RADIALPOLY:
+        return radpoly_df(S, p, g);
+    case RT_PROFILE_YTOROID:
+        return ytoroid_df(S, p, g);
+    case RT_PROFILE_XTOROID: {              /* profiles.py:1435-1437 */
+        double q[3] = {p[1], p[0], p[2]}, h[3];
+        int st = ytoroid_df(S, q, h);
+        if (st) return st;
+        g[0] = h[1]; g[1] = h[0]; g[2] = h[2];
+        return ST_OK;
+    }
+    }
+    return ST_NUMERIC;
+}
+
+/* SurfaceProfile.intersect_spencer (profiles.py:155-186).  Note the returned
+ * point is the last *evaluated* iterate, not p0 + s1*d. */
+static int intersect_spencer(const rt_surface_desc *S, const double p0[3], const double d[3],
+                             double eps, double *s_out, double p_out[3])
+{
+    double p[3] = {p0[0], p0[1], p0[2]};
+    double f, g[3];
+    int st = prof_f(S, p, &f);
+    if (st) return st;
+    st = prof_df(S, p, g);
+    if (st) return st;
+    double s1 = -f/dot3(d, g);
+    double delta = fabs(s1);
+    int iter = 0;
+    while (delta > eps && iter < 1000) {
+        p[0] = p0[0] + s1*d[0]; p[1] = p0[1] + s1*d[1]; p[2] = p0[2] + s1*d[2];
+        st = prof_f(S, p, &f);
+        if (st) return st;
+        st = prof_df(S, p, g);
+        if (st) return st;
+        double s2 = s1 - f/dot3(d, g);
+        delta = fabs(s2 - s1);
+        s1 = s2;
+        iter++;
+    }
+    *s_out = s1;
+    p_out[0] = p[0]; p_out[1] = p[1]; p_out[2] = p[2];
+    return ST_OK;
+}
+
+/* ifc.intersect(p, d, eps, z_dir) -> (s, p1) */
+static int ifc_intersect(const rt_surface_desc *S, const double p[3], const double d[3],
+                         double eps, double z_dir, double *s, double p1[3])
+{
+    int st;
+    switch (S->profile) {
+    case RT_PROFILE_SPHERICAL: {            /* profiles.py:310-336 */
+        double ax2 = S->cv;
+        double cx2 = S->cv*dot3(p, p) - 2*p[2];
+        double b = S->cv*dot3(d, p) - d[2];
+        st = quadric_root(ax2, cx2, b, z_dir, s);
+        if (st) return st;
+        break;
+    }
+    case RT_PROFILE_CONIC: {                /* profiles.py:569-593 */
+        double ax2 = S->cv*(1. + S->cc*d[2]*d[2]);
+        double cx2 = S->cv*(p[0]*p[0] + p[1]*p[1] + S->ec*p[2]*p[2]) - 2.0*p[2];
+        double b = S->cv*(d[0]*p[0] + d[1]*p[1] + S->ec*d[2]*p[2]) - d[2];
+        st = quadric_root(ax2, cx2, b, z_dir, s);
+        if (st) return st;
+        break;
+    }
+    default:
+        return intersect_spencer(S, p, d, eps, s, p1);
+    }
+    p1[0] = p[0] + (*s)*d[0]; p1[1] = p[1] + (*s)*d[1]; p1[2] = p[2] + (*s)*d[2];
+    return ST_OK;
+}
+
+static int ifc_normal(const rt_surface_desc *S, const double p[3], double n[3])
+{
+    double g[3];
+    int st = prof_df(S, p, g);
+    if (st) return st;
+    normalize3(g, n);
+    return ST_OK;
+}
+
+/* Surface.point_inside / Interface.point_inside */
+static int point_inside(const rt_surface_desc *S, double x, double y, double fuzz)
+{
+    if (S->n_apertures > 0) {
+        for (int k = 0; k < S->n_apertures; k++) {
+            const rt_aperture_desc *A = &S->apertures[k];
+            double xa = x - A->x_offset, ya = y - A->y_offset;  /* Aperture.tform, surface.py:391-394 */
+            int ans;
+            if (A->type == RT_APERTURE_CIRCULAR) {
+                ans = sqrt(xa*xa + ya*ya) <= A->a + fuzz;
+            } else if (A->type == RT_APERTURE_RECTANGULAR) {
+                ans = (fabs(xa) <= A->a + fuzz) && (fabs(ya) <= A->b + fuzz);
+            } else {
+                return 0;   /* Elliptical has no point_inside: the base returns None */
+            }
+            if (A->is_obscuration) ans = !ans;
+            if (!ans) return 0;
+        }
+        return 1;
+    }
+    return sqrt(x*x + y*y) <= S->max_aperture + fuzz;
+}
+
+static inline void apply_tfrm(const rt_surface_desc *S, const double p[3], const double d[3],
+                              double bp[3], double bd[3])
+{
+    double q[3] = {p[0] - S->t[0], p[1] - S->t[1], p[2] - S->t[2]};
+    if (S->has_tfrm == 2) {
+        /* rt C-contiguous: OpenBLAS dgemv 't' path as seen from numpy,
+         * y_i = fma(a_i2,v2, fma(a_i0,v0, a_i1*v1))  (probed, tools/probe_blas.py) */
+        for (int r = 0; r < 3; r++) {
+            const double *a = &S->rt[3*r];
+            bp[r] = fma(a[2], q[2], fma(a[0], q[0], a[1]*q[1]));
+            bd[r] = fma(a[2], d[2], fma(a[0], d[0], a[1]*d[1]));
+        }
+    } else if (S->has_tfrm) {
+        /* rt Fortran-ordered (r.transpose() of a C array, elem/transform.py:86):
+         * dgemv 'n' path, y_i = fma(a_i2,v2, fma(a_i1,v1, a_i0*v0)) */
+        for (int r = 0; r < 3; r++) {
+            bp[r] = dot3(&S->rt[3*r], q);
+            bd[r] = dot3(&S->rt[3*r], d);
+        }
+    } else {
+        bp[0] = q[0]; bp[1] = q[1]; bp[2] = q[2];
+        bd[0] = d[0]; bd[1] = d[1]; bd[2] = d[2];
+    }
+}
+
+static inline void put_seg(double *ray, int k, const double p[3], const double d[3],
+                           double dst, const double n[3])
+{
+    if (!ray) return;
+    double *s = ray + (size_t)k*RT_SEG_DOUBLES;
+    s[0] = p[0]; s[1] = p[1]; s[2] = p[2];
+    s[3] = d[0]; s[4] = d[1]; s[5] = d[2];
+    s[6] = dst;
+    s[7] = n[0]; s[8] = n[1]; s[9] = n[2];
+}
+
+/* trace_raw (raytrace.py:83-264) for one ray.
+ *  n_row[i]  : refractive index following interface i (path tuple Indx)
+ *  ray       : [n_ifc][RT_SEG_DOUBLES] or NULL
+ *  last      : [RT_SEG_DOUBLES] copy of ray[-1] or NULL                       */
+int rto_trace_ray(const rt_surface_desc *surfs, int32_t n_ifc, const double *n_row,
+                  const double pt0[3], const double dir0[3], const rt_opts *o,
+                  double *ray, double *last, int32_t *n_seg_out, double *op_out,
+                  int32_t *status_out, int32_t *fail_surf_out)
+{
+    const double fuzz = (o->pt_inside_fuzz < 0.0) ? 1e-5 : o->pt_inside_fuzz;
+    const int first_surf = o->first_surf;
+    const int last_surf = o->last_surf;     /* <0: None */
+    int n_seg = 0, status = ST_OK, fail_surf = -1;
+    double opl = 0.0;
+    double before_pt[3], before_dir[3], before_nrml[3];
+    double inc_pt[3] = {0, 0, 0}, normal[3] = {0, 0, 1}, after_dir[3] = {0, 0, 0};
+    double lseg[RT_SEG_DOUBLES];
+    memset(lseg, 0, sizeof lseg);
+    int b4_mode = RT_MODE_DUMMY;
+
+    const rt_surface_desc *before = &surfs[0];
+    if (o->intersect_obj) {
+        double s;
+        b4_mode = before->mode;
+        /* raytrace.py:150: eps takes intersect()'s default 1e-12 */
+        int st = ifc_intersect(before, pt0, dir0, 1.0e-12, (double)before->z_dir, &s, before_pt);
+        if (!st) st = ifc_normal(before, before_pt, before_nrml);
+        if (st) { status = st; fail_surf = 0; goto done; }
+    } else {
+        before_pt[0] = pt0[0]; before_pt[1] = pt0[1]; before_pt[2] = pt0[2];
+        before_nrml[0] = 0.; before_nrml[1] = 0.; before_nrml[2] = 1.;
+    }
+    before_dir[0] = dir0[0]; before_dir[1] = dir0[1]; before_dir[2] = dir0[2];
+    double z_dir_before = (double)before->z_dir;
+
+    for (int surf = 1; surf < n_ifc; surf++) {
+        const rt_surface_desc *ifc = &surfs[surf];
+        double n_before = n_row[surf - 1];
+        double b4_pt[3], b4_dir[3], pp_pt[3];
+        apply_tfrm(before, before_pt, before_dir, b4_pt, b4_dir);
+        double pp_dst = -dot3(b4_pt, b4_dir);
+        pp_pt[0] = b4_pt[0] + pp_dst*b4_dir[0];
+        pp_pt[1] = b4_pt[1] + pp_dst*b4_dir[1];
+        pp_pt[2] = b4_pt[2] + pp_dst*b4_dir[2];
+
+        double s;
+        int st = ifc_intersect(ifc, pp_pt, b4_dir, o->eps, z_dir_before, &s, inc_pt);
+        if (st == ST_MISS) {
+            /* raytrace.py:231-237 */
+            put_seg(ray, n_seg, before_pt, before_dir, pp_dst, before_nrml);
+            put_seg(lseg, 0, before_pt, before_dir, pp_dst, before_nrml);
+            n_seg++;
+            status = ST_MISS; fail_surf = surf;
+            goto done;
+        } else if (st) {
+            status = st; fail_surf = surf;
+            goto done;
+        }
+        double dst_b4 = pp_dst + s;
+
+        if (b4_mode == RT_MODE_PHANTOM && o->filter_out_phantoms && n_seg > 0) {
+            if (ray) ray[(size_t)(n_seg - 1)*RT_SEG_DOUBLES + 6] += dst_b4;
+            lseg[6] += dst_b4;
+        } else {
+            put_seg(ray, n_seg, before_pt, before_dir, dst_b4, before_nrml);
+            put_seg(lseg, 0, before_pt, before_dir, dst_b4, before_nrml);
+            n_seg++;
+        }
+
+        /* in_gap_range(surf-1), raytrace.py:123-132 */
+        {
+            int g = surf - 1, in_gap;
+            if (first_surf == last_surf) in_gap = 0;
+            else if (g < first_surf) in_gap = 0;
+            else if (last_surf < 0) in_gap = 1;
+            else in_gap = g < last_surf;
+            if (in_gap) opl += n_before*dst_b4;
+        }
+
+        st = ifc_normal(ifc, inc_pt, normal);
+        if (st) { status = st; fail_surf = surf; goto done; }
+
+        if (o->check_apertures && surf >= first_surf && (last_surf < 0 || surf <= last_surf)
+            && ifc->mode != RT_MODE_PHANTOM) {
+            if (!point_inside(ifc, inc_pt[0], inc_pt[1], fuzz)) {
+                /* raytrace.py:247-251 */
+                const double zero = 0.0;
+                put_seg(ray, n_seg, inc_pt, before_dir, zero, normal);
+                put_seg(lseg, 0, inc_pt, before_dir, zero, normal);
+                n_seg++;
+                status = ST_BLOCKED; fail_surf = surf;
+                goto done;
+            }
+        }
+
+        if (ifc->mode == RT_MODE_REFLECT) {
+            /* reflect, raytrace.py:33-38 */
+            double normal_len = sqrt(dot3(normal, normal));
+            double cosI = dot3(b4_dir, normal)/normal_len;
+            double k = 2.0*cosI;
+            after_dir[0] = b4_dir[0] - k*normal[0];
+            after_dir[1] = b4_dir[1] - k*normal[1];
+            after_dir[2] = b4_dir[2] - k*normal[2];
+        } else if (ifc->mode == RT_MODE_TRANSMIT) {
+            /* bend, raytrace.py:19-30 */
+            double n_in = n_before, n_out = n_row[surf];
+            double normal_len = sqrt(dot3(normal, normal));
+            double cosI = dot3(b4_dir, normal)/normal_len;
+            double sinI_sqr = 1.0 - cosI*cosI;
+            double arg = n_out*n_out - n_in*n_in*sinI_sqr;
+            if (arg < 0.0) {
+                /* raytrace.py:239-245 */
+                put_seg(ray, n_seg, inc_pt, before_dir, 0.0, normal);
+                put_seg(lseg, 0, inc_pt, before_dir, 0.0, normal);
+                n_seg++;
+                status = ST_TIR; fail_surf = surf;
+                goto done;
+            }
+            double n_cosIp = copysign(sqrt(arg), cosI);
+            double alpha = n_cosIp - n_in*cosI;
+            after_dir[0] = (n_in*b4_dir[0] + alpha*normal[0])/n_out;
+            after_dir[1] = (n_in*b4_dir[1] + alpha*normal[1])/n_out;
+            after_dir[2] = (n_in*b4_dir[2] + alpha*normal[2])/n_out;
+        } else {
+            after_dir[0] = b4_dir[0]; after_dir[1] = b4_dir[1]; after_dir[2] = b4_dir[2];
+        }
+
+        for (int c = 0; c < 3; c++) {
+            before_pt[c] = inc_pt[c];
+            before_nrml[c] = normal[c];
+            before_dir[c] = after_dir[c];
+        }
+        z_dir_before = (double)ifc->z_dir;
+        b4_mode = ifc->mode;
+        before = ifc;
+    }
+    /* StopIteration, raytrace.py:259-262 */
+    if (n_ifc > 1) {
+        put_seg(ray, n_seg, inc_pt, after_dir, 0.0, normal);
+        put_seg(lseg, 0, inc_pt, after_dir, 0.0, normal);
+        n_seg++;
+    }
+
+done:
+    if (last) memcpy(last, lseg, sizeof lseg);
+    *n_seg_out = n_seg;
+    *op_out = opl;
+    *status_out = status;
+    *fail_surf_out = fail_surf;
+    return 0;
+}
+
+/* ---- bundle: loop of rto_trace_ray over SoA inputs.  n_by_wvl: [n_wvl][n_ifc].
+ * full: [n_ifc][10][stride] SoA (like rt_out.full) or NULL; last: [10][n_rays] SoA or NULL.
+ * n_threads > 1 splits the rays over pthreads (the host-cores CPU baseline). */
+typedef struct {
+    const rt_surface_desc *surfs; int32_t n_ifc; const double *n_by_wvl; int64_t n_rays;
+    const double *px, *py, *pz, *dx, *dy, *dz; const int32_t *wvl_idx; const rt_opts *o;
+    double *last, *full; int64_t full_stride;
+    double *op; int32_t *status, *fail_surf, *n_seg;
+    int64_t r0, r1;
+} bundle_job;
+
+static void *bundle_worker(void *arg)
+{
+    bundle_job *J = (bundle_job *)arg;
+    const int32_t n_ifc = J->n_ifc;
+    double *ray = (double *)malloc(sizeof(double)*RT_SEG_DOUBLES*(size_t)n_ifc);
+    double lseg[RT_SEG_DOUBLES];
+    for (int64_t r = J->r0; r < J->r1; r++) {
+        double p0[3] = {J->px[r], J->py[r], J->pz[r]}, d0[3] = {J->dx[r], J->dy[r], J->dz[r]};
+        int w = J->wvl_idx ? J->wvl_idx[r] : J->o->wvl_idx;
+        int32_t ns, st, fs;
+        double opl;
+        rto_trace_ray(J->surfs, n_ifc, J->n_by_wvl + (size_t)w*n_ifc, p0, d0, J->o,
+                      J->full ? ray : NULL, lseg, &ns, &opl, &st, &fs);
+        if (J->op) J->op[r] = opl;
+        if (J->status) J->status[r] = st;
+        if (J->fail_surf) J->fail_surf[r] = fs;
+        if (J->n_seg) J->n_seg[r] = ns;
+        if (J->last)
+            for (int c = 0; c < RT_SEG_DOUBLES; c++) J->last[(size_t)c*J->n_rays + r] = lseg[c];
+        if (J->full)
+            for (int k = 0; k < ns; k++)
+                for (int c = 0; c < RT_SEG_DOUBLES; c++)
+                    J->full[((size_t)k*RT_SEG_DOUBLES + c)*J->full_stride + r] = ray[k*RT_SEG_DOUBLES + c];
+    }
+    free(ray);
+    return NULL;
+}
+
+int rto_trace_bundle(const rt_surface_desc *surfs, int32_t n_ifc, const double *n_by_wvl,
+                     int64_t n_rays,
+                     const double *px, const double *py, const double *pz,
+                     const double *dx, const double *dy, const double *dz,
+                     const int32_t *wvl_idx, const rt_opts *o,
+                     double *last, double *full, int64_t full_stride,
+                     double *op, int32_t *status, int32_t *fail_surf, int32_t *n_seg,
+                     int32_t n_threads)
+{
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    bundle_job jobs[256];
+    pthread_t tids[256];
+    int64_t per = (n_rays + n_threads - 1)/n_threads;
+    for (int t = 0; t < n_threads; t++) {
+        bundle_job J = {surfs, n_ifc, n_by_wvl, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o,
+                        last, full, full_stride, op, status, fail_surf, n_seg, 0, 0};
+        J.r0 = t*per; J.r1 = (t + 1)*per;
+        if (J.r0 > n_rays) J.r0 = n_rays;
+        if (J.r1 > n_rays) J.r1 = n_rays;
+        jobs[t] = J;
+    }
+    if (n_threads == 1) { bundle_worker(&jobs[0]); return 0; }
+    for (int t = 0; t < n_threads; t++) pthread_create(&tids[t], NULL, bundle_worker, &jobs[t]);
+    for (int t = 0; t < n_threads; t++) pthread_join(tids[t], NULL);
+    return 0;
+}
+
+/* ---- grid start rays: Field.apply_vignetting (opticalspec.py:1339-1353) +
+ * ray_start_from_osp 'epd' branch (opticalspec.py:354-366) + the virtual-object
+ * direction flip of trace_base (trace.py:305-308).
+ * Writes pt0/dir0 SoA for rays [ray_begin, ray_end) of the flattened grid. */
+int rto_grid_start_rays(const rt_grid_spec *g, int64_t ray_begin, int64_t ray_end,
+                        double *px, double *py, double *pz,
+                        double *dx, double *dy, double *dz, int32_t *wvl_idx,
+                        double *pupx, double *pupy)
+{
+    const int64_t per_tile = (int64_t)g->nx*g->ny;
+    for (int64_t r = ray_begin; r < ray_end; r++) {
+        int64_t tile = r/per_tile, loc = r - tile*per_tile;
+        int f = (int)(tile/g->n_wvls), w = (int)(tile - (int64_t)f*g->n_wvls);
+        int i = (int)(loc/g->ny), j = (int)(loc - (int64_t)i*g->ny);
+        const rt_field_desc *F = &g->fields[f];
+        double pup[2] = {g->pupil_x[(size_t)f*g->nx + i], g->pupil_y[(size_t)f*g->ny + j]};
+        if (g->apply_vignetting) {
+            if (pup[0] < 0.0) { if (F->vlx != 0.0) pup[0] *= (1.0 - F->vlx); }
+            else              { if (F->vux != 0.0) pup[0] *= (1.0 - F->vux); }
+            if (pup[1] < 0.0) { if (F->vly != 0.0) pup[1] *= (1.0 - F->vly); }
+            else              { if (F->vuy != 0.0) pup[1] *= (1.0 - F->vuy); }
+        }
+        double pt1[3] = {g->eprad*pup[0] + F->aim[0], g->eprad*pup[1] + F->aim[1], g->z_pupil};
+        double v[3] = {pt1[0] - F->pt0[0], pt1[1] - F->pt0[1], pt1[2] - F->pt0[2]};
+        double d[3];
+        normalize3(v, d);
+        if (d[2]*(double)g->flip_z_dir < 0) { d[0] = -d[0]; d[1] = -d[1]; d[2] = -d[2]; }
+        int64_t k = r - ray_begin;
+        px[k] = F->pt0[0]; py[k] = F->pt0[1]; pz[k] = F->pt0[2];
+        dx[k] = d[0]; dy[k] = d[1]; dz[k] = d[2];
+        if (wvl_idx) wvl_idx[k] = g->wvl_idx[w];
+        if (pupx) pupx[k] = pup[0];
+        if (pupy) pupy[k] = pup[1];
+    }
+    return 0;
+}
+
+/* transverse aberration, analyses.py:561-580: p + (foc/d_z) d - image_pt */
+int rto_transverse_abr(int64_t n, const double *px, const double *py,
+                       const double *dx, const double *dy, const double *dz,
+                       double foc, double ref_x, double ref_y, double *ax, double *ay)
+{
+    for (int64_t r = 0; r < n; r++) {
+        double dist = foc/dz[r];
+        ax[r] = (px[r] + dist*dx[r]) - ref_x;
+        ay[r] = (py[r] + dist*dy[r]) - ref_y;
+    }
+    return 0;
+}
+
+int rto_sizeof_surface_desc(void) { return (int)sizeof(rt_surface_desc); }

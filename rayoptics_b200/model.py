@@ -1,0 +1,551 @@
+"""Host-side sequential model: the data the ray-trace engine is compiled from.
+
+This is a *data* mirror of the parts of the reference's model layer that the
+hot path reads -- it holds numbers, it does not trace rays:
+
+* profile classes carry the attributes of ``rayoptics.elem.profiles``
+  (``Spherical`` :218, ``Conic`` :449, ``EvenPolynomial`` :682,
+  ``RadialPolynomial`` :891, ``YToroid`` :1119, ``XToroid`` :1375 of
+  /root/reference/src/rayoptics/elem/profiles.py) under the *same class
+  names*, because the surface-table builder (``table.py``) dispatches on
+  ``type(profile).__name__`` and therefore accepts the reference's own objects
+  and these mirrors interchangeably;
+* ``Surface`` / ``Circular`` / ``Rectangular`` mirror
+  /root/reference/src/rayoptics/elem/surface.py:38-271,397-469;
+* ``SequentialModel.path(wl)`` yields the reference's path tuples
+  ``(Intfc, Gap, Tfrm, Indx, Zdir)`` (seq/sequential.py:149-202,
+  optical/model_constants.py:12).
+
+Models are persisted as a small JSON "prescription" (``b200rt-model-v1``);
+tools/make_models.py writes them from the reference's bundled lens files.
+"""
+from __future__ import annotations
+
+import json
+import math
+from itertools import zip_longest
+
+import numpy as np
+
+
+# ----------------------------------------------------------------- profiles
+class SurfaceProfile:
+    """Base of the profile data holders (reference: elem/profiles.py:48)."""
+
+    cv = 0.0
+
+    def update(self):
+        return self
+
+    def to_dict(self):
+        d = {'type': type(self).__name__}
+        d.update({k: (list(v) if isinstance(v, (list, tuple, np.ndarray)) else v)
+                  for k, v in vars(self).items() if k != 'max_nonzero_coef'})
+        return d
+
+
+class Spherical(SurfaceProfile):
+    def __init__(self, c=0.0, r=None):
+        if r is not None:
+            c = 1.0/r if r != 0.0 else 0.0
+        self.cv = c
+
+    @property
+    def r(self):
+        return 1.0/self.cv if self.cv != 0.0 else 0.0
+
+
+class Conic(SurfaceProfile):
+    def __init__(self, c=0.0, cc=0.0, r=None, ec=None):
+        if r is not None:
+            c = 1.0/r if r != 0.0 else 0.0
+        self.cv = c
+        self.cc = cc if ec is None else ec - 1.0
+
+    @property
+    def ec(self):
+        # same expression as the reference property (profiles.py:519-521)
+        return self.cc + 1.0
+
+
+def _max_nonzero_coef(coefs):
+    k = -1
+    for i, c in enumerate(coefs):
+        if c != 0.0:
+            k = i
+    return k + 1
+
+
+class EvenPolynomial(SurfaceProfile):
+    """coefs[i] multiplies r**(2*(i+1)) (profiles.py:849-866)."""
+
+    def __init__(self, c=0.0, cc=0.0, r=None, ec=None, coefs=None):
+        if r is not None:
+            c = 1.0/r if r != 0.0 else 0.0
+        self.cv = c
+        self.cc = cc if ec is None else ec - 1.0
+        self.coefs = list(coefs) if coefs is not None else []
+        self.update()
+
+    @property
+    def ec(self):
+        return self.cc + 1.0
+
+    def update(self):
+        self.max_nonzero_coef = _max_nonzero_coef(self.coefs)
+        return self
+
+
+class RadialPolynomial(SurfaceProfile):
+    """coefs[i] multiplies r**(i+1); stores ec, cc is derived (profiles.py:970-976)."""
+
+    def __init__(self, c=0.0, cc=None, r=None, ec=1.0, coefs=None):
+        if r is not None:
+            c = 1.0/r if r != 0.0 else 0.0
+        self.cv = c
+        self.ec = ec if cc is None else cc + 1.0
+        self.coefs = list(coefs) if coefs is not None else []
+        self.update()
+
+    @property
+    def cc(self):
+        return self.ec - 1.0
+
+    def update(self):
+        self.max_nonzero_coef = _max_nonzero_coef(self.coefs)
+        return self
+
+
+class YToroid(SurfaceProfile):
+    def __init__(self, c=0.0, cR=0.0, cc=0.0, r=None, rR=None, ec=None, coefs=None):
+        if r is not None:
+            c = 1.0/r if r != 0.0 else 0.0
+        if rR is not None:
+            cR = 1.0/rR if rR != 0.0 else 0.0
+        self.cv = c
+        self.cR = cR
+        self.cc = cc if ec is None else ec - 1.0
+        self.coefs = list(coefs) if coefs is not None else []
+        self.update()
+
+    @property
+    def ec(self):
+        return self.cc + 1.0
+
+    @property
+    def rR(self):
+        return 1.0/self.cR if self.cR != 0.0 else 0.0
+
+    def update(self):
+        self.max_nonzero_coef = _max_nonzero_coef(self.coefs)
+        return self
+
+
+class XToroid(YToroid):
+    pass
+
+
+_PROFILE_CLASSES = {c.__name__: c for c in
+                    (Spherical, Conic, EvenPolynomial, RadialPolynomial, YToroid, XToroid)}
+
+
+def profile_from_dict(d):
+    d = dict(d)
+    cls = _PROFILE_CLASSES[d.pop('type')]
+    prf = cls.__new__(cls)
+    for k, v in d.items():
+        setattr(prf, k, v)
+    return prf.update()
+
+
+# ---------------------------------------------------------------- apertures
+class Aperture:
+    def __init__(self, x_offset=0.0, y_offset=0.0, rotation=0.0, is_obscuration=False):
+        self.x_offset = x_offset
+        self.y_offset = y_offset
+        self.rotation = rotation
+        self.is_obscuration = is_obscuration
+
+    def to_dict(self):
+        d = {'type': type(self).__name__}
+        d.update(vars(self))
+        return d
+
+
+class Circular(Aperture):
+    def __init__(self, radius=1.0, **kwargs):
+        super().__init__(**kwargs)
+        self.radius = radius
+
+
+class Rectangular(Aperture):
+    def __init__(self, x_half_width=1.0, y_half_width=1.0, **kwargs):
+        super().__init__(**kwargs)
+        self.x_half_width = x_half_width
+        self.y_half_width = y_half_width
+
+
+class Elliptical(Aperture):
+    def __init__(self, x_half_width=1.0, y_half_width=1.0, **kwargs):
+        super().__init__(**kwargs)
+        self.x_half_width = x_half_width
+        self.y_half_width = y_half_width
+
+
+_APERTURE_CLASSES = {c.__name__: c for c in (Circular, Rectangular, Elliptical)}
+
+
+def aperture_from_dict(d):
+    d = dict(d)
+    cls = _APERTURE_CLASSES[d.pop('type')]
+    return cls(**d)
+
+
+# ------------------------------------------------------------------ surface
+class Surface:
+    """Data mirror of elem/surface.py:38 ``Surface(Interface)``."""
+
+    def __init__(self, lbl='', profile=None, interact_mode='transmit',
+                 max_aperture=1.0, clear_apertures=None, **kwargs):
+        self.label = lbl
+        self.profile = profile if profile is not None else Spherical()
+        self.interact_mode = interact_mode
+        self.max_aperture = max_aperture
+        self.clear_apertures = list(clear_apertures) if clear_apertures else []
+        self.edge_apertures = []
+        self.decenter = None
+        self.delta_n = 0.0
+
+    def set_max_aperture(self, max_ap):
+        self.max_aperture = max_ap
+
+    def update(self):
+        self.profile.update()
+        return self
+
+
+# -------------------------------------------------------------------- media
+class Medium:
+    """Refractive-index source of a gap: ``rindex(wvl_nm)``.
+
+    The reference delegates this to the un-vendored ``opticalglass`` package
+    (seq/sequential.py:259-274); here the index table is an *input* shared by
+    the oracle and the engine.
+    """
+
+    def rindex(self, wvl):
+        raise NotImplementedError
+
+    def to_dict(self):
+        d = {'type': type(self).__name__}
+        d.update(vars(self))
+        return d
+
+
+class Air(Medium):
+    def rindex(self, wvl):
+        return 1.0
+
+
+class ConstantIndex(Medium):
+    def __init__(self, n=1.0, label=''):
+        self.n = n
+        self.label = label
+
+    def rindex(self, wvl):
+        return self.n
+
+
+class Sellmeier(Medium):
+    """n**2 = 1 + sum B_i l**2/(l**2 - C_i), l in um; coefs = [B1,B2,B3,C1,C2,C3]
+    as stored per glass in the reference's .roa files."""
+
+    def __init__(self, coefs=None, label=''):
+        self.coefs = list(coefs)
+        self.label = label
+
+    def rindex(self, wvl):
+        w2 = (wvl*1.0e-3)**2
+        B1, B2, B3, C1, C2, C3 = self.coefs
+        n2 = 1.0 + B1*w2/(w2 - C1) + B2*w2/(w2 - C2) + B3*w2/(w2 - C3)
+        return math.sqrt(n2)
+
+
+class AbbeGlass(Medium):
+    """Two-term Cauchy glass fitted through (n_d, V_d): n = A + B/l**2 with
+    n_F - n_C = (n_d - 1)/V_d.  A documented synthetic dispersion model for
+    prescriptions that give only n_d and V_d (raytr/tests/ag_dblgauss_s.py)."""
+
+    L_D, L_F, L_C = 0.5875618, 0.4861327, 0.6562725
+
+    def __init__(self, nd=1.5, vd=60.0, label=''):
+        self.nd = nd
+        self.vd = vd
+        self.label = label
+
+    def rindex(self, wvl):
+        if self.vd == 0.0:
+            return self.nd
+        l2 = (wvl*1.0e-3)**2
+        B = ((self.nd - 1.0)/self.vd)/(1.0/self.L_F**2 - 1.0/self.L_C**2)
+        A = self.nd - B/self.L_D**2
+        return A + B/l2
+
+
+class TableIndex(Medium):
+    def __init__(self, wvls=None, ns=None, label=''):
+        self.wvls = list(wvls)
+        self.ns = list(ns)
+        self.label = label
+
+    def rindex(self, wvl):
+        for w, n in zip(self.wvls, self.ns):
+            if w == wvl:
+                return n
+        return float(np.interp(wvl, self.wvls, self.ns))
+
+
+_MEDIUM_CLASSES = {c.__name__: c for c in (Air, ConstantIndex, Sellmeier, AbbeGlass, TableIndex)}
+
+
+def medium_from_dict(d):
+    d = dict(d)
+    cls = _MEDIUM_CLASSES[d.pop('type')]
+    return cls(**d)
+
+
+class Gap:
+    """seq/gap.py:21 -- thickness + medium."""
+
+    def __init__(self, t=0.0, med=None):
+        self.thi = t
+        self.medium = med if med is not None else Air()
+
+
+# ---------------------------------------------------------- sequential model
+class SequentialModel:
+    """Interfaces, gaps and what ``path()`` needs (seq/sequential.py:41-202).
+
+    ``lcl_tfrms[i] = (rt, t)`` takes interface ``i`` coordinates to interface
+    ``i+1`` coordinates as ``rt.dot(p - t)`` (elem/transform.py:79-107).
+    """
+
+    def __init__(self, ifcs, gaps, z_dir=None, stop_surface=None, wvlns=None,
+                 ref_wvl=0, lcl_tfrms=None):
+        assert len(gaps) == len(ifcs) - 1
+        self.ifcs = list(ifcs)
+        self.gaps = list(gaps)
+        self.stop_surface = stop_surface
+        self.wvlns = list(wvlns) if wvlns is not None else [550.0]
+        self.ref_wvl = ref_wvl
+        self.z_dir = list(z_dir) if z_dir is not None else None
+        self._tfrms_given = lcl_tfrms
+        self._version = 0
+        self.update_model()
+
+    # -- reference API used by the hot path
+    def get_num_surfaces(self):
+        return len(self.ifcs)
+
+    def central_wavelength(self):
+        return self.wvlns[self.ref_wvl]
+
+    def index_for_wavelength(self, wvl):
+        return self.wvlns.index(wvl)
+
+    def calc_ref_indices_for_spectrum(self, wvls):
+        return [[g.medium.rindex(w) for w in wvls] for g in self.gaps]
+
+    def update_model(self, **kwargs):
+        """Rebuild index table, z_dir and transforms (seq/sequential.py:612-669)."""
+        self.rndx = self.calc_ref_indices_for_spectrum(self.wvlns)
+        if self.z_dir is None or len(self.z_dir) != len(self.gaps):
+            z_before = 1
+            self.z_dir = []
+            for ifc in self.ifcs[:-1]:
+                z_after = -z_before if ifc.interact_mode == 'reflect' else z_before
+                self.z_dir.append(z_after)
+                z_before = z_after
+        if self._tfrms_given is not None:
+            self.lcl_tfrms = [(np.array(rt, dtype=float), np.array(t, dtype=float))
+                              for rt, t in self._tfrms_given]
+        else:
+            self.lcl_tfrms = [(np.identity(3), np.array([0., 0., g.thi])) for g in self.gaps]
+            self.lcl_tfrms.append((np.identity(3), np.array([0., 0., 0.])))
+        for ifc in self.ifcs:
+            ifc.update()
+        self._version += 1
+
+    def path(self, wl=None, start=None, stop=None, step=1):
+        """Iterator of ``(Intfc, Gap, Tfrm, Indx, Zdir)`` (seq/sequential.py:149-202)."""
+        if wl is None:
+            wl = self.central_wavelength()
+        wi = self.index_for_wavelength(wl)
+        rndx = [n[wi] for n in self.rndx[start:stop:step]]
+        return iter(list(zip_longest(self.ifcs[start:stop:step],
+                                     self.gaps[start:stop:step],
+                                     self.lcl_tfrms[start:stop:step],
+                                     rndx,
+                                     self.z_dir[start:stop:step])))
+
+    # -- persistence
+    def to_dict(self):
+        ifcs = []
+        for i, ifc in enumerate(self.ifcs):
+            e = {'label': ifc.label, 'mode': ifc.interact_mode,
+                 'max_aperture': ifc.max_aperture,
+                 'profile': ifc.profile.to_dict()}
+            if ifc.clear_apertures:
+                e['clear_apertures'] = [ca.to_dict() for ca in ifc.clear_apertures]
+            if i < len(self.gaps):
+                e['thi'] = self.gaps[i].thi
+                e['medium'] = self.gaps[i].medium.to_dict()
+                e['z_dir'] = self.z_dir[i]
+                rt, t = self.lcl_tfrms[i]
+                if not np.array_equal(rt, np.identity(3)) or t[0] != 0.0 or t[1] != 0.0:
+                    rt = np.asarray(rt)
+                    order = 'C' if (rt.flags['C_CONTIGUOUS'] and not rt.flags['F_CONTIGUOUS']) else 'F'
+                    e['tfrm'] = {'rt': rt.tolist(), 't': np.asarray(t).tolist(), 'order': order}
+            ifcs.append(e)
+        return {'ifcs': ifcs, 'stop_surface': self.stop_surface,
+                'wvls': self.wvlns, 'ref_wvl': self.ref_wvl}
+
+    @classmethod
+    def from_dict(cls, d):
+        ifcs, gaps, z_dir, tfrms, any_tfrm = [], [], [], [], False
+        n = len(d['ifcs'])
+        for i, e in enumerate(d['ifcs']):
+            s = Surface(lbl=e.get('label', ''), profile=profile_from_dict(e['profile']),
+                        interact_mode=e['mode'], max_aperture=e.get('max_aperture', 1.0),
+                        clear_apertures=[aperture_from_dict(a) for a in e.get('clear_apertures', [])])
+            ifcs.append(s)
+            if i < n - 1:
+                gaps.append(Gap(e['thi'], medium_from_dict(e['medium'])))
+                z_dir.append(e.get('z_dir', 1))
+                if 'tfrm' in e:
+                    any_tfrm = True
+                    # the memory order decides which dgemv rounding numpy applies (table.py)
+                    rt = np.array(e['tfrm']['rt'], dtype=float)
+                    if e['tfrm'].get('order', 'F') == 'F':
+                        rt = np.asfortranarray(rt)
+                    tfrms.append((rt, e['tfrm']['t']))
+                else:
+                    tfrms.append((np.identity(3), [0., 0., e['thi']]))
+        tfrms.append((np.identity(3), [0., 0., 0.]))
+        return cls(ifcs, gaps, z_dir=z_dir, stop_surface=d.get('stop_surface'),
+                   wvlns=d.get('wvls', [550.0]), ref_wvl=d.get('ref_wvl', 0),
+                   lcl_tfrms=tfrms if any_tfrm else None)
+
+
+def gen_sequence(surf_data_list, wvls=(550.0,), ref_wvl=0, sd=None, stop_surface=None):
+    """Build a model from ``[curvature, thickness, n_d, V_d]`` rows, the list
+    form used by the reference's own hot-path test
+    (seq/sequential.py:1182-1223, raytr/tests/test_sequential.py:38-41)."""
+    ifcs, gaps = [], []
+    prev_med = Air()
+    for row in surf_data_list:
+        s = Surface(profile=Spherical(c=row[0]))
+        if len(row) > 2 and isinstance(row[2], str) and row[2].casefold() == 'refl':
+            s.interact_mode = 'reflect'
+            med = prev_med
+        elif len(row) > 3 and row[3] != 0:
+            med = AbbeGlass(row[2], row[3])
+        elif len(row) > 2:
+            med = ConstantIndex(row[2]) if row[2] != 1 else Air()
+        else:
+            med = Air()
+        if sd is not None:
+            s.set_max_aperture(sd)
+        ifcs.append(s)
+        gaps.append(Gap(row[1], med))
+        prev_med = med
+    ifcs[-1].interact_mode = 'dummy'
+    return SequentialModel(ifcs, gaps[:-1], stop_surface=stop_surface,
+                           wvlns=list(wvls), ref_wvl=ref_wvl)
+
+
+# ------------------------------------------------------ optical specification
+class Field:
+    """raytr/opticalspec.py:1197 -- field point + vignetting + aim info."""
+
+    def __init__(self, x=0.0, y=0.0, wt=1.0, vux=0.0, vuy=0.0, vlx=0.0, vly=0.0,
+                 aim_pt=None):
+        self.x, self.y, self.wt = x, y, wt
+        self.vux, self.vuy, self.vlx, self.vly = vux, vuy, vlx, vly
+        self.aim_info = None if aim_pt is None else np.array(aim_pt, dtype=float)
+        self.chief_ray = None
+        self.ref_sphere = None
+
+    def apply_vignetting(self, pupil):
+        """opticalspec.py:1339-1353 (including its in-place behaviour for ndarrays)."""
+        vig_pupil = pupil[:]
+        if pupil[0] < 0.0:
+            if self.vlx != 0.0:
+                vig_pupil[0] *= (1.0 - self.vlx)
+        else:
+            if self.vux != 0.0:
+                vig_pupil[0] *= (1.0 - self.vux)
+        if pupil[1] < 0.0:
+            if self.vly != 0.0:
+                vig_pupil[1] *= (1.0 - self.vly)
+        else:
+            if self.vuy != 0.0:
+                vig_pupil[1] *= (1.0 - self.vuy)
+        return vig_pupil
+
+    def to_dict(self):
+        return {'x': self.x, 'y': self.y, 'wt': self.wt, 'vux': self.vux, 'vuy': self.vuy,
+                'vlx': self.vlx, 'vly': self.vly,
+                'aim_pt': None if self.aim_info is None else list(map(float, self.aim_info))}
+
+
+class OpticalModel:
+    """Container with the reference's access keys (optical/opticalmodel.py:186-202):
+    ``opm['seq_model']``, ``opm['optical_spec']``, ``opm['analysis_results']``."""
+
+    def __init__(self, seq_model, optical_spec=None, name=''):
+        self.name = name
+        self.seq_model = seq_model
+        self.optical_spec = optical_spec
+        self.analysis_results = {'parax_data': None}
+        if optical_spec is not None:
+            optical_spec.opt_model = self
+            optical_spec.update_model()
+
+    _keys = {'sm': 'seq_model', 'seq_model': 'seq_model', 'osp': 'optical_spec',
+             'optical_spec': 'optical_spec', 'ar': 'analysis_results',
+             'analysis_results': 'analysis_results'}
+
+    def __getitem__(self, key):
+        return getattr(self, self._keys[key])
+
+    def nm_to_sys_units(self, nm):
+        return 1e-6*nm   # millimetres
+
+    def update_model(self, **kwargs):
+        self.seq_model.update_model(**kwargs)
+        if self.optical_spec is not None:
+            self.optical_spec.update_model(**kwargs)
+
+    def to_dict(self):
+        d = {'format': 'b200rt-model-v1', 'name': self.name}
+        d.update(self.seq_model.to_dict())
+        if self.optical_spec is not None:
+            d['optical_spec'] = self.optical_spec.to_dict()
+        return d
+
+    def save(self, path):
+        with open(path, 'w') as f:
+            json.dump(self.to_dict(), f, indent=1)
+
+    @classmethod
+    def from_dict(cls, d):
+        from .opticalspec import OpticalSpecs
+        sm = SequentialModel.from_dict(d)
+        osp = OpticalSpecs.from_dict(d['optical_spec']) if 'optical_spec' in d else None
+        return cls(sm, osp, name=d.get('name', ''))
+
+    @classmethod
+    def load(cls, path):
+        with open(path) as f:
+            return cls.from_dict(json.load(f))
