@@ -1,0 +1,389 @@
+#!/usr/bin/env python3
+"""bench.py -- rays/sec (fp64) through a sequential model on B200(s).
+
+Metric (BASELINE.json): rays/sec in fp64 through an N-surface sequential model.
+Workload at N=1: BASELINE configs[1] -- double Gauss (13 interfaces), 3 fields x
+3 wavelengths x 512 x 512 pupil grid = 2,359,296 rays per step, apertures
+checked, start rays generated on the device, per-ray last-segment records
+(p, d, op, status, fail_surf: 64 B) + transverse aberration (16 B) written to
+HBM, per-(field, wvl) spot sums reduced.  Multi-GPU: the chunk space of the same
+grid is weak-scaled (every rank traces the full 2.36 M-ray grid of its own
+replica ... no: see `scaling` below) -- ranks shard nothing but summaries.
+
+  python bench.py --gpus N --steps K --warmup W            (this repo's engine)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the oracle
+        port of the reference's trace_raw on all host threads; the reference is
+        pure Python and cannot travel to the GPU box -- DESIGN.md)
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for how every
+field is obtained.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'rays/sec (fp64) through N-surface seq model'
+UNIT = 'rays/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--model', default='dblgauss')
+    ap.add_argument('--num', type=int, default=512, help='pupil samples per side')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def load_model(name):
+    from rayoptics_b200 import model as M
+    return M.OpticalModel.load(os.path.join(ROOT, 'tests', 'golden', 'models', name + '.json'))
+
+
+# ---------------------------------------------------------------- flop model
+# Algorithmic work per ray per interface, from the reference's algebra
+# (add/mul/sub = 1, fma = 2, div = 1, sqrt = 1).
+def interface_flops(desc, n_wild_newton=3.3):
+    tfrm = 3 if desc.has_tfrm == 0 else 33
+    closest = 12
+    k = desc.n_coefs
+    if desc.profile == 0:
+        isect, nrm = 28, 13
+    elif desc.profile == 1:
+        isect, nrm = 41, 15
+    else:
+        isect, nrm = n_wild_newton*(46 + 5*k), 20 + 3*k
+    act = {0: 33, 1: 18}.get(desc.mode, 0)
+    return dict(tfrm=tfrm, closest=closest, isect=isect, dst=3, nrm=nrm, ap=4, act=act)
+
+
+def flops_by_outcome(descs):
+    """cum[k] = flops of a ray that completes interface k; plus partial costs."""
+    n = len(descs)
+    start = 20 + 6                      # start-ray generation + transverse aberration
+    obj = interface_flops(descs[0])
+    cum = [start + obj['isect'] + obj['nrm']]
+    parts = [None]
+    for k in range(1, n):
+        f = interface_flops(descs[k])
+        f['tfrm'] = interface_flops(descs[k - 1])['tfrm']
+        parts.append(f)
+        cum.append(cum[-1] + sum(f.values()))
+    return cum, parts
+
+
+def algorithmic_flops(descs, status, fail_surf):
+    cum, parts = flops_by_outcome(descs)
+    cum = np.array(cum, dtype=np.float64)
+    n_ifc = len(descs)
+    total = float((status == 0).sum())*cum[-1]
+    for st in (1, 2, 3, 5):
+        m = status == st
+        if not m.any():
+            continue
+        ks = np.bincount(fail_surf[m], minlength=n_ifc)
+        for k, cnt in enumerate(ks):
+            if cnt == 0 or k == 0:
+                continue
+            f = parts[k]
+            if st in (1, 5):
+                w = cum[k - 1] + f['tfrm'] + f['closest'] + f['isect']
+            elif st == 3:
+                w = cum[k] - f['act']
+            else:
+                w = cum[k]
+            total += cnt*w
+    return total, cum[-1]
+
+
+# ------------------------------------------------------------ clock sampling
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                       '-lms', '100', '-i', str(gpu_index)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons, pw = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(',')]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                'sw_power_cap'), c[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)),
+                       reasons=sorted(reasons), samples=len(sm), power_w_max=float(max(pw)))
+        return out
+
+
+# ------------------------------------------------------------- CPU baseline
+def host_grid_spec(opm, num):
+    """Host-only grid spec with chief-ray reference image points from the oracle."""
+    from oracle import rt_oracle
+    from rayoptics_b200 import _abi, table as T, engine as E
+    sm = opm.seq_model
+    descs, n_by_wvl, _ = T.describe_model(sm)
+    fields = opm.optical_spec.fov.fields
+    g0 = E.grid_spec_for_model(opm, 1, wvls=[sm.central_wavelength()], pupil_range=(0.0, 0.0),
+                               apply_vignetting=False)
+    o0 = _abi.make_opts(first_surf=1, last_surf=len(descs) - 2, check_apertures=False)
+    r0 = rt_oracle.trace_grid(g0.c_spec(), descs, n_by_wvl, 0, g0.n_rays, o0)
+    ref = r0['last'][0:2].T.copy()
+    ref_fw = np.repeat(ref[:, None, :], len(sm.wvlns), axis=1)
+    spec = E.grid_spec_for_model(opm, num, ref_img=ref_fw)
+    return spec, descs, n_by_wvl
+
+
+def cpu_trace(spec, descs, n_by_wvl, r0, r1, threads):
+    from oracle import rt_oracle
+    from rayoptics_b200 import _abi
+    opts = _abi.make_opts(first_surf=1, last_surf=len(descs) - 2, check_apertures=True)
+    t0 = time.perf_counter()
+    r = rt_oracle.trace_grid(spec.c_spec(), descs, n_by_wvl, r0, r1, opts, n_threads=threads,
+                             want_last=False)
+    return time.perf_counter() - t0, r
+
+
+def cpu_baseline(opm, num, target_s=12.0):
+    """The oracle port on all host threads, on a bounded contiguous sample of the
+    same grid (one tile = field 1, wavelength 1)."""
+    cores = os.cpu_count() or 1
+    spec, descs, n_by_wvl = host_grid_spec(opm, num)
+    per_tile = num*num
+    tile = min(4, spec.n_tiles - 1)
+    r0, r1 = tile*per_tile, (tile + 1)*per_tile
+    dt, _ = cpu_trace(spec, descs, n_by_wvl, r0, r0 + min(20000, per_tile), cores)   # warm-up
+    reps, total_t, total_n = 0, 0.0, 0
+    while total_t < target_s and reps < 50:
+        dt, _ = cpu_trace(spec, descs, n_by_wvl, r0, r1, cores)
+        total_t += dt; total_n += r1 - r0; reps += 1
+    dt1, _ = cpu_trace(spec, descs, n_by_wvl, r0, r0 + min(100000, per_tile), 1)
+    return {'value': total_n/total_t, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'{reps} x {r1 - r0} rays (tile field 1 / wvl 1 of the same grid), '
+                      f'oracle/rt_oracle.c on {cores} pthreads',
+            'single_thread': min(100000, per_tile)/dt1}
+
+
+# ------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    opm = load_model(args.model)
+    cores = os.cpu_count() or 1
+    spec, descs, n_by_wvl = host_grid_spec(opm, args.num)
+    n = spec.n_rays
+    for _ in range(max(args.warmup, 1)):
+        cpu_trace(spec, descs, n_by_wvl, 0, min(n, 200000), cores)
+    t_tot = 0.0
+    for _ in range(args.steps):
+        dt, _ = cpu_trace(spec, descs, n_by_wvl, 0, n, cores)
+        t_tot += dt
+    val = n*args.steps/t_tot
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT,
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3*t_tot/args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': config_dict(args, opm, spec, 1),
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': f'whole grid ({n} rays) per step, oracle/rt_oracle.c port of '
+                                       f'trace_raw on {cores} pthreads; the Python reference itself '
+                                       f'cannot run on this box (no /root/reference)'},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, opm, grid, world):
+    sm = opm.seq_model
+    return {'workload': f'{args.model}: {sm.get_num_surfaces()} interfaces, '
+                        f'{grid.n_fields} fields x {grid.n_wvls} wvls x {args.num}x{args.num} pupil '
+                        f'(BASELINE configs[1])' if args.model == 'dblgauss' and args.num == 512 else
+                        f'{args.model}: {sm.get_num_surfaces()} interfaces, {grid.n_fields} fields x '
+                        f'{grid.n_wvls} wvls x {args.num}x{args.num} pupil',
+            'rays_per_step_per_gpu': grid.n_rays, 'check_apertures': True,
+            'output': 'last segment p,d + op + status + fail_surf (64 B/ray) + transverse '
+                      'aberration (16 B/ray) + per-(field,wvl) spot sums',
+            'parallelism': f'replica-per-gpu x{world}, all-gather of [n_tiles,16] spot sums',
+            'l2': 'no HBM input is re-read (start rays are generated on-chip); each step writes '
+                  '189 MB of results > 126 MB L2'}
+
+
+# ----------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from rayoptics_b200 import _abi, table as T, engine as E, analyses as A, parallel as P
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py --impl b200 needs a CUDA device'
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    _abi.load_library()
+
+    opm = load_model(args.model)
+    tab = T.SurfaceTable.from_model(opm.seq_model, device=local)
+    grid = E.grid_for_model(opm, tab, args.num)
+    res = E.BundleResult(grid.n_rays, tab.n_ifc, dev, E.GRID_OUTPUTS)
+    n_rays = grid.n_rays                     # weak scaling: every rank traces a full grid replica
+
+    def step():
+        r = E.trace_grid(tab, grid, res=res)
+        if world > 1:
+            r.summary = P.gather_summaries(r.summary)
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = E.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    e_first, e_last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e_first.record()
+    for k in range(args.steps):
+        ev[k][0].record()
+        E.trace_grid(tab, grid, res=res)          # dominant kernel, bracketed for the roofline
+        ev[k][1].record()
+        if world > 1:
+            res.summary = P.gather_summaries(res.summary)
+    e_last.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = E.launch_count() - launches0
+    dev_ms = e_first.elapsed_time(e_last)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    t = torch.tensor([dev_ms, wall*1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end to end through the public API, host buffers both sides
+    e2e = None
+    if not args.no_e2e:
+        pinned = {'abr': torch.empty((2, n_rays), dtype=torch.float64).pin_memory(),
+                  'status': torch.empty(n_rays, dtype=torch.int32).pin_memory()}
+        for _ in range(3):
+            sd = A.spot_diagram(opm, args.num, table=tab, pinned=pinned)
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            sd = A.spot_diagram(opm, args.num, table=tab, pinned=pinned)
+            if world > 1:
+                P.gather_summaries(res.summary)
+        barrier()
+        e2e_s = time.perf_counter() - t1
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {'value': world*n_rays*args.steps/float(te[0]), 'unit': UNIT,
+               'h2d_bytes_per_step': int(sd.io_bytes['h2d']),
+               'd2h_bytes_per_step': int(sd.io_bytes['d2h']),
+               'api': 'rayoptics_b200.analyses.spot_diagram(opt_model, 512): grid spec from host, '
+                      'aberrations + status into pinned host memory'}
+
+    if rank == 0:
+        status = res.status.cpu().numpy()
+        fail_surf = res.fail_surf.cpu().numpy()
+        flops, flops_full_ray = algorithmic_flops(tab.descs, status, fail_surf)
+        fp64_peak = E.measure_fp64_peak(local)
+        bpr = res.bytes_per_ray()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        ach_gbs = n_rays*bpr/(kern_ms*1e-3)/1e9
+        ach_tf = flops/(kern_ms*1e-3)/1e12
+        roof = {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': ach_gbs/hbm_peak,
+                'peak_source': 'MEASURED_PEAKS.json (of measured)' if 'hbm_gbs' in peaks
+                else 'B200_PROFILING.md fallback (of fallback)',
+                'traffic': None, 'bytes_per_ray': bpr, 'kernel': 'k_trace_grid<0,1,1>',
+                'kernel_ms': kern_ms,
+                'limiter': 'fp64 vector pipe (kernel is register-resident; HBM only receives results)',
+                'fp64': {'achieved_tflops': ach_tf, 'peak_tflops': fp64_peak,
+                         'frac': ach_tf/fp64_peak if fp64_peak else None,
+                         'peak_source': 'rt_measure_fp64_peak: DFMA chain microbenchmark, this run',
+                         'algorithmic_flop_per_full_ray': flops_full_ray,
+                         'algorithmic_flop_per_step': flops}}
+        line = {'metric': METRIC, 'value': world*n_rays*args.steps/(dev_ms_max*1e-3), 'unit': UNIT,
+                'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+                'ms_per_step': dev_ms_max/args.steps, 'wall_ms_per_step': wall_ms_max/args.steps,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                'data': 'synthetic', 'config': config_dict(args, opm, grid, world),
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
+                'rays_ok_frac': float((status == 0).mean())}
+        if not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline(opm, args.num)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

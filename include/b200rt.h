@@ -231,6 +231,9 @@ const char *rt_last_error(void);
 int rt_abi_version(void);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 int64_t rt_launch_count(void);
+/* fp64 vector-pipe peak of `device` in TFLOP/s, measured with a chain of
+ * independent DFMAs (the roofline denominator of the register-resident trace) */
+int rt_measure_fp64_peak(int32_t device, double *tflops);
 
 #ifdef __cplusplus
 }

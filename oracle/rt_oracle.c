@@ -434,14 +434,12 @@ int rto_trace_ray(const rt_surface_desc *surfs, int32_t n_ifc, const double *n_r
 
         double s;
         int st = ifc_intersect(ifc, pp_pt, b4_dir, o->eps, z_dir_before, &s, inc_pt);
-        if (st == ST_MISS) {
-            /* raytrace.py:231-237 */
+        if (st) {
+            /* TraceMissedSurfaceError, raytrace.py:231-237.  ST_NUMERIC (where the
+             * reference dies with an uncaught ValueError) is packaged the same way. */
             put_seg(ray, n_seg, before_pt, before_dir, pp_dst, before_nrml);
             put_seg(lseg, 0, before_pt, before_dir, pp_dst, before_nrml);
             n_seg++;
-            status = ST_MISS; fail_surf = surf;
-            goto done;
-        } else if (st) {
             status = st; fail_surf = surf;
             goto done;
         }
@@ -653,6 +651,70 @@ int rto_transverse_abr(int64_t n, const double *px, const double *py,
         ax[r] = (px[r] + dist*dx[r]) - ref_x;
         ay[r] = (py[r] + dist*dy[r]) - ref_y;
     }
+    return 0;
+}
+
+/* ---- whole grid on the host: start rays + trace + transverse aberration, split
+ * over n_threads pthreads.  This is the CPU baseline / reference arm of bench.py
+ * (the reference evaluates the same thing with a Python loop, trace.py:563-605).
+ * Outputs are SoA over rays [ray_begin, ray_end): last [10][n], op, status,
+ * fail_surf, abr_x, abr_y (any may be NULL). */
+typedef struct {
+    const rt_grid_spec *g; const rt_surface_desc *surfs; int32_t n_ifc; const double *n_by_wvl;
+    const rt_opts *o; int64_t ray_begin, n; int64_t r0, r1;
+    double *last, *op, *abr_x, *abr_y; int32_t *status, *fail_surf;
+} grid_job;
+
+static void *grid_worker(void *arg)
+{
+    grid_job *J = (grid_job *)arg;
+    const rt_grid_spec *g = J->g;
+    const int64_t per_tile = (int64_t)g->nx*g->ny;
+    for (int64_t r = J->r0; r < J->r1; r++) {
+        double px, py, pz, dx, dy, dz;
+        int32_t w;
+        rto_grid_start_rays(g, r, r + 1, &px, &py, &pz, &dx, &dy, &dz, &w, NULL, NULL);
+        double p0[3] = {px, py, pz}, d0[3] = {dx, dy, dz}, lseg[RT_SEG_DOUBLES], opl;
+        int32_t ns, st, fs;
+        rto_trace_ray(J->surfs, J->n_ifc, J->n_by_wvl + (size_t)w*J->n_ifc, p0, d0, J->o,
+                      NULL, lseg, &ns, &opl, &st, &fs);
+        int64_t k = r - J->ray_begin;
+        if (J->last) for (int c = 0; c < RT_SEG_DOUBLES; c++) J->last[(size_t)c*J->n + k] = lseg[c];
+        if (J->op) J->op[k] = opl;
+        if (J->status) J->status[k] = st;
+        if (J->fail_surf) J->fail_surf[k] = fs;
+        if (J->abr_x) {
+            int64_t tile = r/per_tile;
+            double rx = g->ref_img ? g->ref_img[tile*2] : 0.0, ry = g->ref_img ? g->ref_img[tile*2 + 1] : 0.0;
+            double dist = g->foc/lseg[5];
+            J->abr_x[k] = (lseg[0] + dist*lseg[3]) - rx;
+            J->abr_y[k] = (lseg[1] + dist*lseg[4]) - ry;
+        }
+    }
+    return NULL;
+}
+
+int rto_trace_grid(const rt_grid_spec *g, const rt_surface_desc *surfs, int32_t n_ifc,
+                   const double *n_by_wvl, int64_t ray_begin, int64_t ray_end, const rt_opts *o,
+                   double *last, double *op, int32_t *status, int32_t *fail_surf,
+                   double *abr_x, double *abr_y, int32_t n_threads)
+{
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    grid_job jobs[256];
+    pthread_t tids[256];
+    int64_t n = ray_end - ray_begin, per = (n + n_threads - 1)/n_threads;
+    for (int t = 0; t < n_threads; t++) {
+        grid_job J = {g, surfs, n_ifc, n_by_wvl, o, ray_begin, n, 0, 0, last, op, abr_x, abr_y,
+                      status, fail_surf};
+        J.r0 = ray_begin + t*per; J.r1 = J.r0 + per;
+        if (J.r0 > ray_end) J.r0 = ray_end;
+        if (J.r1 > ray_end) J.r1 = ray_end;
+        jobs[t] = J;
+    }
+    if (n_threads == 1) { grid_worker(&jobs[0]); return 0; }
+    for (int t = 0; t < n_threads; t++) pthread_create(&tids[t], NULL, grid_worker, &jobs[t]);
+    for (int t = 0; t < n_threads; t++) pthread_join(tids[t], NULL);
     return 0;
 }
 

@@ -100,3 +100,21 @@ def transverse_abr(px, py, dx, dy, dz, foc, ref_x, ref_y):
     lib().rto_transverse_abr(C.c_int64(n), *[_dp(a) for a in arrs], C.c_double(foc),
                              C.c_double(ref_x), C.c_double(ref_y), _dp(ax), _dp(ay))
     return ax, ay
+
+
+def trace_grid(spec: rt_grid_spec, descs, n_by_wvl, ray_begin, ray_end, opts, n_threads=1,
+               want_last=True):
+    """Whole grid on the host (start rays + trace + transverse aberration)."""
+    n = ray_end - ray_begin
+    n_by_wvl = np.ascontiguousarray(n_by_wvl, dtype=np.float64)
+    last = np.zeros((RT_SEG_DOUBLES, n)) if want_last else None
+    op = np.zeros(n)
+    status = np.zeros(n, dtype=np.int32)
+    fail_surf = np.zeros(n, dtype=np.int32)
+    ax, ay = np.zeros(n), np.zeros(n)
+    lib().rto_trace_grid(C.byref(spec), descs, C.c_int32(len(descs)), _dp(n_by_wvl),
+                         C.c_int64(ray_begin), C.c_int64(ray_end), C.byref(opts),
+                         _dp(last), _dp(op), _ip(status), _ip(fail_surf), _dp(ax), _dp(ay),
+                         C.c_int32(n_threads))
+    return {'last': last, 'op': op, 'status': status, 'fail_surf': fail_surf,
+            'abr': np.stack([ax, ay])}

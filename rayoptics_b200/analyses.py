@@ -1,0 +1,135 @@
+"""Grid / list / fan analyses as single bundle launches.
+
+The reference evaluates every analysis with a Python loop that traces one ray
+per iteration (/root/reference/src/rayoptics/raytr/trace.py:537-605,
+raytr/analyses.py:212-230,437-455,666-696; seq/sequential.py:1006-1085).  Here
+the whole fields x wavelengths x pupil-grid index space is one ``rt_trace_grid``
+launch; the start rays are generated on the device and only the requested
+results come back to the host.
+
+``spot_diagram`` is the engine-side equivalent of
+``SequentialModel.trace_grid(spot, fi, num_rays=N, form='list',
+append_if_none=False)`` evaluated for every field
+(seq/sequential.py:1058-1085 with the ``spot`` filter of
+mpl/axisarrayfigure.py:229-238): per field and wavelength the transverse ray
+aberrations ``(dx, dy)`` of the rays that reach the image, referred to the
+chief-ray image point at the central wavelength.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import engine as E
+from .table import SurfaceTable
+
+
+class SpotDiagram:
+    """Result of ``spot_diagram``.
+
+    ``abr`` ``[2, n]`` / ``status`` ``[n]``: host (pinned) arrays over the rays
+    this process traced, flattened (field, wvl, i, j) order starting at
+    ``first_ray``; ``grids[fi][wi]``: ``[n_ok, 2]`` arrays of the rays that reach
+    the image, in the reference's order (x outer, y inner) -- the ``form='list',
+    append_if_none=False`` shape of seq/sequential.py:1058-1085 -- built lazily
+    (whole grid only); ``summary``: dict of ``[n_fields, n_wvls]`` arrays (n_ok,
+    n_blocked, centroid_x/y, rms_radius ...), combined over all ranks;
+    ``ref_img``: ``[n_fields, 2]`` chief-ray image points."""
+
+    def __init__(self, abr, status, summary, ref_img, num_rays, n_fields, n_wvls, first_ray,
+                 n_rays_total, io_bytes):
+        self.abr, self.status, self.summary, self.ref_img = abr, status, summary, ref_img
+        self.num_rays, self.n_fields, self.n_wvls = num_rays, n_fields, n_wvls
+        self.first_ray, self.n_rays_total = first_ray, n_rays_total
+        self.io_bytes = io_bytes            # {'h2d': ..., 'd2h': ...} of this call
+        self._grids = None
+
+    @property
+    def grids(self):
+        if self._grids is None:
+            if self.first_ray != 0 or self.status.shape[0] != self.n_rays_total:
+                raise ValueError('per-tile lists need the whole grid on one process')
+            ok = self.status == 0
+            per = self.num_rays*self.num_rays
+            self._grids = []
+            for fi in range(self.n_fields):
+                row = []
+                for wi in range(self.n_wvls):
+                    sl = slice((fi*self.n_wvls + wi)*per, (fi*self.n_wvls + wi + 1)*per)
+                    m = ok[sl]
+                    row.append(np.stack([self.abr[0, sl][m], self.abr[1, sl][m]], axis=1))
+                self._grids.append(row)
+        return self._grids
+
+
+def _table_for(opt_model, table=None, device=0):
+    if table is not None:
+        return table
+    sm = opt_model.seq_model
+    cached = getattr(sm, '_b200_table', None)
+    version = getattr(sm, '_version', None)
+    if cached is None or cached[0] != version or cached[1].device != device:
+        cached = (version, SurfaceTable.from_model(sm, device=device))
+        sm._b200_table = cached
+    return cached[1]
+
+
+def chief_ray_image_points(opt_model, table, fields, wvl=None, foc=0.0, io=None):
+    """Image intercept of the (0, 0) pupil ray of every field at ``wvl``
+    (default: central wavelength): ``ref_sphere[0]`` of
+    raytr/waveabr.py:24-76 for ``image_pt_2d=None``."""
+    osp, sm = opt_model.optical_spec, opt_model.seq_model
+    wvl = sm.central_wavelength() if wvl is None else wvl
+    recs, eprad, z_pupil = osp.grid_fields(fields)
+    g0 = E.PupilGrid(recs, [table.wvl_index(wvl)], [0.0], [0.0], eprad, z_pupil,
+                     apply_vignetting=False, flip_z_dir=sm.z_dir[0], foc=foc, device=table.device)
+    r0 = E.trace_grid(table, g0, outputs=('p',), summary=False, check_apertures=False)
+    ref = r0.p[:2].t().contiguous().cpu().numpy()
+    if io is not None:
+        io['h2d'] += g0.host_bytes()
+        io['d2h'] += ref.nbytes
+    g0.close()
+    return ref        # [n_fields, 2]
+
+
+def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table=None,
+                 device=0, pinned=None, shard=None, group=None, **kwargs):
+    """Spot diagrams of all fields and wavelengths in one launch.
+
+    Host buffers in, host buffers out: the grid description goes to the device
+    (``rt_grid_create``), ``rt_trace_grid`` generates and traces the rays, and
+    the transverse aberrations + status come back into pinned host memory.
+    ``shard=(rank, world)`` traces only that rank's slice of the chunk space and
+    all-gathers the per-(field, wvl) sums over ``group`` (parallel.py).
+    ``pinned``: optional dict of pinned host tensors ``abr`` ``[2, >=n]`` and
+    ``status`` ``[>=n]`` to re-use across calls."""
+    from .parallel import shard_chunks, gather_summaries
+    osp, sm = opt_model.optical_spec, opt_model.seq_model
+    table = _table_for(opt_model, table, device)
+    fields = list(osp.field_of_view.fields if fields is None else fields)
+    wvls = list(sm.wvlns if wvls is None else wvls)
+    foc = osp.defocus.focus_shift if foc is None else foc
+    io = {'h2d': 0, 'd2h': 0}
+    ref = chief_ray_image_points(opt_model, table, fields, foc=foc, io=io)
+    ref_fw = np.repeat(ref[:, None, :], len(wvls), axis=1)
+    grid = E.grid_for_model(opt_model, table, num_rays, fields=fields, wvls=wvls, foc=foc,
+                            ref_img=ref_fw)
+    io['h2d'] += grid.host_bytes()
+    c0, c1 = (0, grid.n_chunks) if shard is None else shard_chunks(grid.n_chunks, *shard)
+    res = E.trace_grid(table, grid, c0, c1, outputs=('abr', 'status'), **kwargs)
+    n = res.n
+    if pinned is None:
+        pinned = {'abr': torch.empty((2, n), dtype=torch.float64).pin_memory(),
+                  'status': torch.empty(n, dtype=torch.int32).pin_memory()}
+    h_abr, h_status = pinned['abr'][:, :n], pinned['status'][:n]
+    h_abr.copy_(res.abr, non_blocking=True)
+    h_status.copy_(res.status, non_blocking=True)
+    summ = res.summary if shard is None else gather_summaries(res.summary, group)
+    stats = E.spot_statistics(summ)
+    stats_host = {k: v.cpu().numpy().reshape(len(fields), len(wvls)) for k, v in stats.items()}
+    torch.cuda.current_stream(table.device).synchronize()
+    io['d2h'] += h_abr.numel()*8 + h_status.numel()*4 + sum(v.nbytes for v in stats_host.values())
+    out = SpotDiagram(h_abr.numpy(), h_status.numpy(), stats_host, ref, num_rays, len(fields),
+                      len(wvls), grid.first_ray_of_chunk(c0), grid.n_rays, io)
+    grid.close()
+    return out

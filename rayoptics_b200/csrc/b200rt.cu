@@ -1,0 +1,607 @@
+/*
+ * b200rt.cu -- kernels and C ABI of libb200rt.so (see include/b200rt.h).
+ *
+ * Kernels (sm_100a; fp64 vector pipe + coalesced SoA global traffic; no tensor
+ * cores -- the path is not a contraction):
+ *   k_trace_bundle<FULL,STAGE>  one ray per lane over caller-supplied start rays
+ *   k_trace_grid<FULL,SUMMARY,STAGE>  start rays generated on device from the
+ *                               (field, wavelength, pupil i, j) index, optional
+ *                               per-chunk spot sums
+ *   k_reduce_summary            fixed-order per-tile reduction of the chunk sums
+ *   k_dfma_peak                 fp64 FMA microbenchmark (roofline denominator)
+ *
+ * The surface table (n_ifc x rt_surface_desc + n_wvl x n_ifc indices) is staged
+ * into shared memory once per CTA; CTAs are persistent (grid = SMs x resident
+ * CTAs) and walk rays / chunks with a grid stride.
+ */
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rt_device.cuh"
+
+using namespace b200rt;
+
+#define RT_BLOCK 256          /* threads per CTA = rays per chunk */
+#define RT_MAX_STAGE_BYTES (200*1024)
+
+/* ------------------------------------------------------------------ errors */
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char *fmt, const char *a = "", const char *b = "")
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, fmt, a, b);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                            \
+    do {                                                                          \
+        cudaError_t e_ = (expr);                                                  \
+        if (e_ != cudaSuccess)                                                    \
+            return fail(RT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));    \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            cudaSetDevice(dev);
+            changed = true;
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
+/* ------------------------------------------------------------------ handles */
+struct rt_table {
+    int32_t device, n_ifc, n_wvl, sm_count;
+    rt_surface_desc *d_surfs;
+    double *d_n;
+    size_t stage_bytes;      /* shared memory needed to stage the table */
+    bool stage;              /* false: table too large, read it from global/L1 */
+};
+
+struct rt_grid {
+    int32_t device;
+    int32_t n_fields, n_wvls, nx, ny;
+    int32_t apply_vignetting, flip_z_dir;
+    double eprad, z_pupil, foc;
+    rt_field_desc *d_fields;
+    int32_t *d_wvl_idx;
+    double *d_pupil_x, *d_pupil_y, *d_ref_img;
+    int64_t rays_per_tile, chunks_per_tile, n_tiles, n_chunks, n_rays;
+};
+
+/* what the grid kernel needs, passed by value */
+struct GridDev {
+    int32_t n_wvls, nx, ny, apply_vignetting, flip_z_dir;
+    double eprad, z_pupil, foc;
+    const rt_field_desc *fields;
+    const int32_t *wvl_idx;
+    const double *pupil_x, *pupil_y, *ref_img;
+    int64_t rays_per_tile, chunks_per_tile;
+};
+
+/* ------------------------------------------------------------------ kernels */
+
+/* Stage the table into shared memory (8-byte words, coalesced) or, for very
+ * long systems, leave it in global memory (uniform loads hit L1). */
+template <bool STAGE>
+__device__ __forceinline__ void stage_table(const rt_surface_desc *g_surfs, const double *g_n,
+                                            int n_ifc, int n_wvl, unsigned char *smem,
+                                            const rt_surface_desc *&tab, const double *&ntab)
+{
+    if (STAGE) {
+        const int words_s = n_ifc*(int)(sizeof(rt_surface_desc)/8);
+        const int words_n = n_ifc*n_wvl;
+        double *dst = reinterpret_cast<double *>(smem);
+        const double *src = reinterpret_cast<const double *>(g_surfs);
+        for (int i = threadIdx.x; i < words_s; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < words_n; i += blockDim.x) dst[words_s + i] = g_n[i];
+        __syncthreads();
+        tab = reinterpret_cast<const rt_surface_desc *>(smem);
+        ntab = dst + words_s;
+    } else {
+        tab = g_surfs;
+        ntab = g_n;
+    }
+}
+
+__device__ __forceinline__ void store_result(const rt_out &out, int64_t k, const RayResult &R)
+{
+    if (out.px) { out.px[k] = R.p.x; out.py[k] = R.p.y; out.pz[k] = R.p.z; }
+    if (out.dx) { out.dx[k] = R.d.x; out.dy[k] = R.d.y; out.dz[k] = R.d.z; }
+    if (out.nx) { out.nx[k] = R.n.x; out.ny[k] = R.n.y; out.nz[k] = R.n.z; }
+    if (out.dst) out.dst[k] = R.dst;
+    if (out.op) out.op[k] = R.op;
+    if (out.status) out.status[k] = R.status;
+    if (out.fail_surf) out.fail_surf[k] = R.fail_surf;
+    if (out.n_seg) out.n_seg[k] = R.n_seg;
+}
+
+template <bool FULL, bool STAGE>
+__global__ void __launch_bounds__(RT_BLOCK)
+k_trace_bundle(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
+               int n_ifc, int n_wvl, int64_t n_rays,
+               const double *__restrict__ px, const double *__restrict__ py,
+               const double *__restrict__ pz, const double *__restrict__ dx,
+               const double *__restrict__ dy, const double *__restrict__ dz,
+               const int32_t *__restrict__ wvl_idx, rt_opts o, rt_out out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const rt_surface_desc *tab;
+    const double *ntab;
+    stage_table<STAGE>(g_surfs, g_n, n_ifc, n_wvl, smem, tab, ntab);
+
+    const int64_t step = (int64_t)gridDim.x*blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x*blockDim.x + threadIdx.x; r < n_rays; r += step) {
+        Vec3 p0 = {px[r], py[r], pz[r]};
+        Vec3 d0 = {dx[r], dy[r], dz[r]};
+        const int w = wvl_idx ? wvl_idx[r] : o.wvl_idx;
+        FullWriter fw = {FULL ? out.full + r : nullptr, out.full_stride};
+        RayResult R;
+        trace_ray<FULL>(tab, ntab + (int64_t)w*n_ifc, n_ifc, o, p0, d0, fw, R);
+        store_result(out, r, R);
+    }
+}
+
+/* deterministic CTA reduction of the 16 summary quantities */
+__device__ __forceinline__ void block_reduce_summary(double (&v)[RT_SUMMARY_DOUBLES], double *dst)
+{
+    __shared__ double wsum[RT_BLOCK/32][RT_SUMMARY_DOUBLES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < RT_SUMMARY_DOUBLES; k++) {
+        double x = v[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double y = __shfl_down_sync(0xffffffffu, x, off);
+            if (k == 10 || k == 12) x = fmin(x, y);
+            else if (k == 11 || k == 13) x = fmax(x, y);
+            else x = x + y;
+        }
+        if (lane == 0) wsum[warp][k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < RT_SUMMARY_DOUBLES) {
+        const int k = threadIdx.x;
+        double x = wsum[0][k];
+        for (int w = 1; w < RT_BLOCK/32; w++) {
+            double y = wsum[w][k];
+            if (k == 10 || k == 12) x = fmin(x, y);
+            else if (k == 11 || k == 13) x = fmax(x, y);
+            else x = x + y;
+        }
+        dst[k] = x;
+    }
+    __syncthreads();
+}
+
+template <bool FULL, bool SUMMARY, bool STAGE>
+__global__ void __launch_bounds__(RT_BLOCK)
+k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
+             int n_ifc, int n_wvl, GridDev G, int64_t chunk_begin, int64_t chunk_end,
+             rt_opts o, rt_out out, double *__restrict__ scratch)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const rt_surface_desc *tab;
+    const double *ntab;
+    stage_table<STAGE>(g_surfs, g_n, n_ifc, n_wvl, smem, tab, ntab);
+
+    const int64_t tile0 = chunk_begin/G.chunks_per_tile;
+    const int64_t ray0 = tile0*G.rays_per_tile + (chunk_begin - tile0*G.chunks_per_tile)*RT_BLOCK;
+
+    for (int64_t c = chunk_begin + blockIdx.x; c < chunk_end; c += gridDim.x) {
+        const int64_t tile = c/G.chunks_per_tile;
+        const int64_t loc = (c - tile*G.chunks_per_tile)*RT_BLOCK + threadIdx.x;
+        const bool valid = loc < G.rays_per_tile;
+        const int f = (int)(tile/G.n_wvls);
+        const int w = (int)(tile - (int64_t)f*G.n_wvls);
+        double v[RT_SUMMARY_DOUBLES];
+        if (SUMMARY) {
+#pragma unroll
+            for (int k = 0; k < RT_SUMMARY_DOUBLES; k++) v[k] = 0.0;
+            v[10] = v[12] = CUDART_INF;
+            v[11] = v[13] = -CUDART_INF;
+        }
+        if (valid) {
+            const int i = (int)(loc/G.ny), j = (int)(loc - (int64_t)i*G.ny);
+            const rt_field_desc F = G.fields[f];
+            /* Field.apply_vignetting, opticalspec.py:1339-1353 */
+            double pupx = G.pupil_x[(int64_t)f*G.nx + i], pupy = G.pupil_y[(int64_t)f*G.ny + j];
+            if (G.apply_vignetting) {
+                if (pupx < 0.0) { if (F.vlx != 0.0) pupx *= (1.0 - F.vlx); }
+                else            { if (F.vux != 0.0) pupx *= (1.0 - F.vux); }
+                if (pupy < 0.0) { if (F.vly != 0.0) pupy *= (1.0 - F.vly); }
+                else            { if (F.vuy != 0.0) pupy *= (1.0 - F.vuy); }
+            }
+            /* ray_start_from_osp 'epd' branch, opticalspec.py:354-366 */
+            Vec3 p0 = {F.pt0[0], F.pt0[1], F.pt0[2]};
+            Vec3 pt1 = {G.eprad*pupx + F.aim[0], G.eprad*pupy + F.aim[1], G.z_pupil};
+            Vec3 dv = {pt1.x - p0.x, pt1.y - p0.y, pt1.z - p0.z};
+            Vec3 d0 = normalize3(dv);
+            /* trace_base virtual-object flip, trace.py:305-308 */
+            if (d0.z*(double)G.flip_z_dir < 0) { d0.x = -d0.x; d0.y = -d0.y; d0.z = -d0.z; }
+
+            const int64_t k = tile*G.rays_per_tile + loc - ray0;
+            FullWriter fw = {FULL ? out.full + k : nullptr, out.full_stride};
+            RayResult R;
+            trace_ray<FULL>(tab, ntab + (int64_t)G.wvl_idx[w]*n_ifc, n_ifc, o, p0, d0, fw, R);
+            store_result(out, k, R);
+
+            if (out.abr_x || SUMMARY) {
+                /* focus_pupil_coords, analyses.py:561-580 */
+                const double rx = G.ref_img ? G.ref_img[(tile)*2 + 0] : 0.0;
+                const double ry = G.ref_img ? G.ref_img[(tile)*2 + 1] : 0.0;
+                double dist = G.foc/R.d.z;
+                double ax = (R.p.x + dist*R.d.x) - rx;
+                double ay = (R.p.y + dist*R.d.y) - ry;
+                if (out.abr_x) { out.abr_x[k] = ax; out.abr_y[k] = ay; }
+                if (SUMMARY) {
+                    if (R.status == RT_RAY_OK) {
+                        v[0] = 1.0;
+                        v[5] = ax; v[6] = ay; v[7] = ax*ax; v[8] = ay*ay; v[9] = ax*ay;
+                        v[10] = v[11] = ax; v[12] = v[13] = ay;
+                        v[14] = R.op;
+                    } else if (R.status == RT_RAY_MISSED) v[1] = 1.0;
+                    else if (R.status == RT_RAY_TIR) v[2] = 1.0;
+                    else if (R.status == RT_RAY_BLOCKED) v[3] = 1.0;
+                    else v[4] = 1.0;
+                }
+            }
+        }
+        if (SUMMARY)
+            block_reduce_summary(v, scratch + (c - chunk_begin)*RT_SUMMARY_DOUBLES);
+    }
+}
+
+/* one thread per (tile, quantity): sum this call's chunk partials in chunk order */
+__global__ void k_reduce_summary(const double *__restrict__ scratch, int64_t chunk_begin,
+                                 int64_t chunk_end, int64_t chunks_per_tile, int64_t n_tiles,
+                                 double *__restrict__ summary)
+{
+    const int64_t idx = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= n_tiles*RT_SUMMARY_DOUBLES) return;
+    const int64_t tile = idx/RT_SUMMARY_DOUBLES;
+    const int k = (int)(idx - tile*RT_SUMMARY_DOUBLES);
+    int64_t c0 = tile*chunks_per_tile, c1 = c0 + chunks_per_tile;
+    if (c0 < chunk_begin) c0 = chunk_begin;
+    if (c1 > chunk_end) c1 = chunk_end;
+    double x = (k == 10 || k == 12) ? CUDART_INF : ((k == 11 || k == 13) ? -CUDART_INF : 0.0);
+    for (int64_t c = c0; c < c1; c++) {
+        double y = scratch[(c - chunk_begin)*RT_SUMMARY_DOUBLES + k];
+        if (k == 10 || k == 12) x = fmin(x, y);
+        else if (k == 11 || k == 13) x = fmax(x, y);
+        else x = x + y;
+    }
+    summary[idx] = x;
+}
+
+/* fp64 FMA microbenchmark: 8 independent chains per thread */
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+    double x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b);
+        x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b);
+        x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+    double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) out[blockIdx.x*blockDim.x + threadIdx.x] = s;
+}
+
+/* ------------------------------------------------------------ launch helpers */
+template <typename K>
+static int persistent_grid(K kernel, size_t smem, int sm_count, int64_t work_items, int *grid)
+{
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RT_BLOCK, smem));
+    if (per_sm < 1) per_sm = 1;
+    int64_t g = (int64_t)sm_count*per_sm;
+    if (g > work_items) g = work_items;
+    if (g < 1) g = 1;
+    *grid = (int)g;
+    return RT_OK;
+}
+
+template <typename K>
+static int prep_kernel(K kernel, size_t smem)
+{
+    if (smem > 48*1024)
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return RT_OK;
+}
+
+static int check_opts(const rt_table *t, const rt_opts *o)
+{
+    if (!o) return fail(RT_ERR_INVALID, "opts is NULL");
+    if (o->wvl_idx < 0 || o->wvl_idx >= t->n_wvl) return fail(RT_ERR_INVALID, "opts.wvl_idx out of range");
+    return RT_OK;
+}
+
+template <bool FULL, bool STAGE>
+static int launch_bundle(const rt_table *t, int64_t n_rays, const double *px, const double *py,
+                         const double *pz, const double *dx, const double *dy, const double *dz,
+                         const int32_t *wvl_idx, const rt_opts *o, const rt_out *out,
+                         cudaStream_t stream)
+{
+    auto kern = k_trace_bundle<FULL, STAGE>;
+    const size_t smem = STAGE ? t->stage_bytes : 0;
+    int rc = prep_kernel(kern, smem);
+    if (rc) return rc;
+    int grid;
+    rc = persistent_grid(kern, smem, t->sm_count, (n_rays + RT_BLOCK - 1)/RT_BLOCK, &grid);
+    if (rc) return rc;
+    kern<<<grid, RT_BLOCK, smem, stream>>>(t->d_surfs, t->d_n, t->n_ifc, t->n_wvl, n_rays,
+                                           px, py, pz, dx, dy, dz, wvl_idx, *o, *out);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+/* ---- grids */
+template <typename T>
+static cudaError_t upload(T **dst, const T *src, size_t n)
+{
+    *dst = nullptr;
+    if (!src || n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(dst, n*sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src, n*sizeof(T), cudaMemcpyHostToDevice);
+}
+
+template <bool FULL, bool SUMMARY, bool STAGE>
+static int launch_grid(const rt_table *t, const rt_grid *g, const GridDev &G, int64_t cb, int64_t ce,
+                       const rt_opts *o, const rt_out *out, double *scratch, cudaStream_t stream)
+{
+    auto kern = k_trace_grid<FULL, SUMMARY, STAGE>;
+    const size_t smem = STAGE ? t->stage_bytes : 0;
+    int rc = prep_kernel(kern, smem);
+    if (rc) return rc;
+    int grid;
+    rc = persistent_grid(kern, smem, t->sm_count, ce - cb, &grid);
+    if (rc) return rc;
+    kern<<<grid, RT_BLOCK, smem, stream>>>(t->d_surfs, t->d_n, t->n_ifc, t->n_wvl, G, cb, ce, *o, *out,
+                                           scratch);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+/* ------------------------------------------------------------------ C ABI */
+extern "C" {
+
+int rt_abi_version(void) { return RT_ABI_VERSION; }
+const char *rt_last_error(void) { return g_err.c_str(); }
+int64_t rt_launch_count(void) { return g_launches.load(); }
+
+int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n_by_wvl,
+                    int32_t n_wvl, int32_t device, rt_table **out)
+{
+    if (!surfs || !n_by_wvl || !out || n_ifc < 2 || n_wvl < 1)
+        return fail(RT_ERR_INVALID, "rt_table_create: bad arguments");
+    for (int i = 0; i < n_ifc; i++) {
+        const rt_surface_desc &s = surfs[i];
+        if (s.profile < RT_PROFILE_SPHERICAL || s.profile > RT_PROFILE_XTOROID)
+            return fail(RT_ERR_UNSUPPORTED, "rt_table_create: unknown profile id");
+        if (s.mode < RT_MODE_TRANSMIT || s.mode > RT_MODE_PHANTOM)
+            return fail(RT_ERR_UNSUPPORTED, "rt_table_create: unknown interact mode");
+        if (s.n_coefs < 0 || s.n_coefs > RT_MAX_COEFS || s.n_apertures < 0 ||
+            s.n_apertures > RT_MAX_APERTURES)
+            return fail(RT_ERR_INVALID, "rt_table_create: coefficient / aperture count out of range");
+    }
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    rt_table *t = new (std::nothrow) rt_table();
+    if (!t) return fail(RT_ERR_NOMEM, "rt_table_create: out of host memory");
+    t->device = device; t->n_ifc = n_ifc; t->n_wvl = n_wvl;
+    t->sm_count = prop.multiProcessorCount;
+    t->d_surfs = nullptr; t->d_n = nullptr;
+    t->stage_bytes = (size_t)n_ifc*sizeof(rt_surface_desc) + (size_t)n_ifc*n_wvl*sizeof(double);
+    t->stage = t->stage_bytes <= RT_MAX_STAGE_BYTES;
+    cudaError_t e = cudaMalloc(&t->d_surfs, (size_t)n_ifc*sizeof(rt_surface_desc));
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_n, (size_t)n_ifc*n_wvl*sizeof(double));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(t->d_surfs, surfs, (size_t)n_ifc*sizeof(rt_surface_desc), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(t->d_n, n_by_wvl, (size_t)n_ifc*n_wvl*sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(t->d_surfs); cudaFree(t->d_n); delete t;
+        return fail(RT_ERR_CUDA, "rt_table_create: %s", cudaGetErrorString(e));
+    }
+    *out = t;
+    return RT_OK;
+}
+
+int rt_table_destroy(rt_table *t)
+{
+    if (!t) return RT_OK;
+    DeviceGuard guard(t->device);
+    cudaFree(t->d_surfs);
+    cudaFree(t->d_n);
+    delete t;
+    return RT_OK;
+}
+
+int rt_table_dims(const rt_table *t, int32_t *n_ifc, int32_t *n_wvl, int32_t *device)
+{
+    if (!t) return fail(RT_ERR_INVALID, "rt_table_dims: NULL table");
+    if (n_ifc) *n_ifc = t->n_ifc;
+    if (n_wvl) *n_wvl = t->n_wvl;
+    if (device) *device = t->device;
+    return RT_OK;
+}
+
+int rt_trace_bundle(const rt_table *t, int64_t n_rays, const double *px, const double *py,
+                    const double *pz, const double *dx, const double *dy, const double *dz,
+                    const int32_t *wvl_idx, const rt_opts *o, const rt_out *out, void *stream)
+{
+    if (!t || !out || n_rays < 0 || !px || !py || !pz || !dx || !dy || !dz)
+        return fail(RT_ERR_INVALID, "rt_trace_bundle: bad arguments");
+    int rc = check_opts(t, o);
+    if (rc) return rc;
+    if (n_rays == 0) return RT_OK;
+    if (out->full && out->full_stride < n_rays)
+        return fail(RT_ERR_INVALID, "rt_trace_bundle: full_stride < n_rays");
+    DeviceGuard guard(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (out->full) {
+        return t->stage ? launch_bundle<true, true>(t, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o, out, s)
+                        : launch_bundle<true, false>(t, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o, out, s);
+    }
+    return t->stage ? launch_bundle<false, true>(t, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o, out, s)
+                    : launch_bundle<false, false>(t, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o, out, s);
+}
+
+int rt_grid_destroy(rt_grid *g)
+{
+    if (!g) return RT_OK;
+    DeviceGuard guard(g->device);
+    cudaFree(g->d_fields); cudaFree(g->d_wvl_idx);
+    cudaFree(g->d_pupil_x); cudaFree(g->d_pupil_y); cudaFree(g->d_ref_img);
+    delete g;
+    return RT_OK;
+}
+
+int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out)
+{
+    if (!spec || !out || spec->n_fields < 1 || spec->n_wvls < 1 || spec->nx < 1 || spec->ny < 1 ||
+        !spec->fields || !spec->wvl_idx || !spec->pupil_x || !spec->pupil_y)
+        return fail(RT_ERR_INVALID, "rt_grid_create: bad arguments");
+    DeviceGuard guard(device);
+    rt_grid *g = new (std::nothrow) rt_grid();
+    if (!g) return fail(RT_ERR_NOMEM, "rt_grid_create: out of host memory");
+    g->device = device;
+    g->n_fields = spec->n_fields; g->n_wvls = spec->n_wvls; g->nx = spec->nx; g->ny = spec->ny;
+    g->apply_vignetting = spec->apply_vignetting; g->flip_z_dir = spec->flip_z_dir;
+    g->eprad = spec->eprad; g->z_pupil = spec->z_pupil; g->foc = spec->foc;
+    g->rays_per_tile = (int64_t)spec->nx*spec->ny;
+    g->chunks_per_tile = (g->rays_per_tile + RT_BLOCK - 1)/RT_BLOCK;
+    g->n_tiles = (int64_t)spec->n_fields*spec->n_wvls;
+    g->n_chunks = g->n_tiles*g->chunks_per_tile;
+    g->n_rays = g->n_tiles*g->rays_per_tile;
+    cudaError_t e = upload(&g->d_fields, spec->fields, (size_t)spec->n_fields);
+    if (e == cudaSuccess) e = upload(&g->d_wvl_idx, spec->wvl_idx, (size_t)spec->n_wvls);
+    if (e == cudaSuccess) e = upload(&g->d_pupil_x, spec->pupil_x, (size_t)spec->n_fields*spec->nx);
+    if (e == cudaSuccess) e = upload(&g->d_pupil_y, spec->pupil_y, (size_t)spec->n_fields*spec->ny);
+    if (e == cudaSuccess) e = upload(&g->d_ref_img, spec->ref_img, (size_t)g->n_tiles*2);
+    if (e != cudaSuccess) {
+        rt_grid_destroy(g);
+        return fail(RT_ERR_CUDA, "rt_grid_create: %s", cudaGetErrorString(e));
+    }
+    *out = g;
+    return RT_OK;
+}
+
+int rt_grid_dims(const rt_grid *g, int64_t *n_rays, int64_t *n_chunks, int32_t *chunk_rays)
+{
+    if (!g) return fail(RT_ERR_INVALID, "rt_grid_dims: NULL grid");
+    if (n_rays) *n_rays = g->n_rays;
+    if (n_chunks) *n_chunks = g->n_chunks;
+    if (chunk_rays) *chunk_rays = RT_BLOCK;
+    return RT_OK;
+}
+
+int64_t rt_grid_scratch_bytes(const rt_grid *g, int64_t chunk_begin, int64_t chunk_end)
+{
+    if (!g || chunk_end < chunk_begin) return 0;
+    return (chunk_end - chunk_begin)*RT_SUMMARY_DOUBLES*(int64_t)sizeof(double);
+}
+
+int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int64_t chunk_end,
+                  const rt_opts *o, const rt_out *out, double *summary, void *scratch, void *stream)
+{
+    if (!t || !g || !out) return fail(RT_ERR_INVALID, "rt_trace_grid: bad arguments");
+    if (t->device != g->device) return fail(RT_ERR_INVALID, "rt_trace_grid: table and grid on different devices");
+    if (chunk_begin < 0 || chunk_end > g->n_chunks || chunk_end < chunk_begin)
+        return fail(RT_ERR_INVALID, "rt_trace_grid: chunk range out of bounds");
+    if (summary && !scratch) return fail(RT_ERR_INVALID, "rt_trace_grid: summary needs scratch");
+    int rc = check_opts(t, o);
+    if (rc) return rc;
+    DeviceGuard guard(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (summary && chunk_begin == chunk_end)
+        CUDA_TRY(cudaMemsetAsync(summary, 0, (size_t)g->n_tiles*RT_SUMMARY_DOUBLES*sizeof(double), s));
+    if (chunk_begin == chunk_end) return RT_OK;
+    GridDev G;
+    G.n_wvls = g->n_wvls; G.nx = g->nx; G.ny = g->ny;
+    G.apply_vignetting = g->apply_vignetting; G.flip_z_dir = g->flip_z_dir;
+    G.eprad = g->eprad; G.z_pupil = g->z_pupil; G.foc = g->foc;
+    G.fields = g->d_fields; G.wvl_idx = g->d_wvl_idx;
+    G.pupil_x = g->d_pupil_x; G.pupil_y = g->d_pupil_y; G.ref_img = g->d_ref_img;
+    G.rays_per_tile = g->rays_per_tile; G.chunks_per_tile = g->chunks_per_tile;
+    double *scr = (double *)scratch;
+    const bool full = out->full != nullptr, summ = summary != nullptr, st = t->stage;
+#define RT_GRID_CASE(F, S, T)                                                               \
+    if (full == F && summ == S && st == T)                                                  \
+        rc = launch_grid<F, S, T>(t, g, G, chunk_begin, chunk_end, o, out, scr, s);
+    RT_GRID_CASE(false, false, true)
+    RT_GRID_CASE(false, true, true)
+    RT_GRID_CASE(true, false, true)
+    RT_GRID_CASE(true, true, true)
+    RT_GRID_CASE(false, false, false)
+    RT_GRID_CASE(false, true, false)
+    RT_GRID_CASE(true, false, false)
+    RT_GRID_CASE(true, true, false)
+#undef RT_GRID_CASE
+    if (rc) return rc;
+    if (summ) {
+        const int64_t n = g->n_tiles*RT_SUMMARY_DOUBLES;
+        k_reduce_summary<<<(unsigned)((n + 127)/128), 128, 0, s>>>(scr, chunk_begin, chunk_end,
+                                                                   g->chunks_per_tile, g->n_tiles, summary);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return RT_OK;
+}
+
+/* fp64 vector-pipe peak, measured with a DFMA chain kernel: the roofline
+ * denominator for the register-resident trace (DESIGN.md "roofline"). */
+int rt_measure_fp64_peak(int32_t device, double *tflops)
+{
+    if (!tflops) return fail(RT_ERR_INVALID, "rt_measure_fp64_peak: NULL output");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount*8, iters = 1 << 14;
+    double *d_out;
+    CUDA_TRY(cudaMalloc(&d_out, (size_t)blocks*256*sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        k_dfma_peak<<<blocks, 256>>>(d_out, iters, 0.999999, 1e-9);
+        g_launches++;
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double fl = 2.0*8.0*(double)iters*256.0*blocks;
+        double tf = fl/(ms*1e-3)/1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *tflops = best;
+    return RT_OK;
+}
+
+}  /* extern "C" */

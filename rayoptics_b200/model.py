@@ -437,7 +437,8 @@ class SequentialModel:
                    lcl_tfrms=tfrms if any_tfrm else None)
 
 
-def gen_sequence(surf_data_list, wvls=(550.0,), ref_wvl=0, sd=None, stop_surface=None):
+def gen_sequence(surf_data_list, wvls=(550.0,), ref_wvl=0, sd=None, stop_surface=None,
+                 dispersion=True):
     """Build a model from ``[curvature, thickness, n_d, V_d]`` rows, the list
     form used by the reference's own hot-path test
     (seq/sequential.py:1182-1223, raytr/tests/test_sequential.py:38-41)."""
@@ -448,7 +449,7 @@ def gen_sequence(surf_data_list, wvls=(550.0,), ref_wvl=0, sd=None, stop_surface
         if len(row) > 2 and isinstance(row[2], str) and row[2].casefold() == 'refl':
             s.interact_mode = 'reflect'
             med = prev_med
-        elif len(row) > 3 and row[3] != 0:
+        elif len(row) > 3 and row[3] != 0 and dispersion:
             med = AbbeGlass(row[2], row[3])
         elif len(row) > 2:
             med = ConstantIndex(row[2]) if row[2] != 1 else Air()

@@ -1,0 +1,256 @@
+"""Optical specification (wavelengths, pupil, fields, focus) and start rays.
+
+Mirrors what the hot path's callers read from the reference's
+``OpticalSpecs`` (/root/reference/src/rayoptics/raytr/opticalspec.py:41-400):
+
+* ``obj_coords(fld)``            opticalspec.py:990-1091 (non wide-angle cases)
+* ``ray_start_from_osp(...)``    opticalspec.py:289-400  (single ray, numpy,
+  same expression order as the reference so the start ray has the same bits)
+* ``grid_fields(...)``           the per-field constants of the 'epd' branch
+  (opticalspec.py:354-366) that the grid kernel turns into start rays on device.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .model import Field
+from .firstorder import compute_first_order
+
+
+def normalize(v):
+    """util/misc_math.py:48-54"""
+    length = np.linalg.norm(v)
+    if length == 0.0:
+        return v
+    return v/length
+
+
+class WvlSpec:
+    def __init__(self, wavelengths=(550.0,), ref_wl=0, spectral_wts=None):
+        self.wavelengths = list(wavelengths)
+        self.reference_wvl = ref_wl
+        self.spectral_wts = list(spectral_wts) if spectral_wts else [1.0]*len(self.wavelengths)
+
+    @property
+    def central_wvl(self):
+        return self.wavelengths[self.reference_wvl]
+
+
+class PupilSpec:
+    """key = (object|image, epd|f/#|NA); opticalspec.py:626-760"""
+    default_pupil_rays = [[0., 0.], [1., 0.], [-1., 0.], [0., 1.], [0., -1.]]
+
+    def __init__(self, key=('object', 'epd'), value=1.0):
+        self.key = tuple(key[-2:])
+        self.value = value
+        self.pupil_rays = [list(r) for r in self.default_pupil_rays]
+
+
+class FieldSpec:
+    """key = (object|image, angle|height); opticalspec.py:820-1195"""
+
+    def __init__(self, key=('object', 'angle'), value=0.0, fields=None, is_relative=False,
+                 is_wide_angle=False):
+        self.key = tuple(key[-2:])
+        self.value = value
+        self.is_relative = is_relative
+        self.is_wide_angle = is_wide_angle
+        self.fields = list(fields) if fields else [Field()]
+
+    def max_field_value(self):
+        if self.is_relative:
+            return self.value
+        m = 0.0
+        for f in self.fields:
+            m = max(m, math.sqrt(f.x*f.x + f.y*f.y))
+        return m if m != 0.0 else self.value
+
+
+class FocusRange:
+    def __init__(self, focus_shift=0.0, defocus_range=0.0):
+        self.focus_shift = focus_shift
+        self.defocus_range = defocus_range
+
+
+class OpticalSpecs:
+    def __init__(self, wvls=None, pupil=None, fov=None, focus=None, do_aiming=True):
+        self.spectral_region = wvls or WvlSpec()
+        self.pupil = pupil or PupilSpec()
+        self.field_of_view = fov or FieldSpec()
+        self.defocus = focus or FocusRange()
+        self.do_aiming = do_aiming
+        self.opt_model = None
+
+    # reference access keys (opticalspec.py:78-95)
+    _keys = {'wvls': 'spectral_region', 'pupil': 'pupil', 'fov': 'field_of_view',
+             'focus': 'defocus'}
+
+    def __getitem__(self, key):
+        return getattr(self, self._keys[key])
+
+    @property
+    def fov(self):
+        return self.field_of_view
+
+    def update_model(self, **kwargs):
+        sm = self.opt_model.seq_model
+        fod = compute_first_order(sm, self, self.spectral_region.central_wvl)
+        self.opt_model.analysis_results['parax_data'] = _ParaxData(fod)
+
+    @property
+    def fod(self):
+        return self.opt_model.analysis_results['parax_data'].fod
+
+    def obj_img_rindex(self):
+        return self.fod.n_obj, self.fod.n_img
+
+    def conjugate_type(self, space='object'):
+        sm = self.opt_model.seq_model
+        thi = sm.gaps[0].thi if space == 'object' else sm.gaps[-1].thi
+        return 'infinite' if abs(thi) >= 1e8 or math.isinf(thi) else 'finite'
+
+    # ---------------------------------------------------------- obj_coords
+    def obj_coords(self, fld):
+        """(pt, dir) characterising `fld` in object space, opticalspec.py:990-1091."""
+        fov = self.field_of_view
+        obj_img_key, value_key = fov.key
+        fld_coord = np.array([fld.x, fld.y, 0.0])
+        rel_fld_coord = np.array([fld.x, fld.y, 0.0])
+        if fov.is_relative:
+            fld_coord *= fov.value
+        else:
+            if fov.value != 0:
+                rel_fld_coord /= fov.value
+        fod = self.fod
+        obj2enp_dist = fod.obj_dist + fod.enp_dist
+        pt1 = np.array([0., 0., obj2enp_dist])
+        if self.conjugate_type('object') == 'infinite':
+            if obj_img_key == 'image':
+                max_field_ang = math.atan(fod.pr_slp0)
+                fld_angle = max_field_ang*rel_fld_coord
+            elif value_key == 'angle':
+                fld_angle = np.deg2rad(fld_coord)
+            else:
+                obj_pt = fld_coord
+                return obj_pt, normalize(pt1 - obj_pt)
+            ang_x, ang_y = fld_angle[0], fld_angle[1]
+            dir_cos = np.array([math.sin(ang_x)*math.cos(ang_y),
+                                math.sin(ang_y),
+                                math.cos(ang_x)*math.cos(ang_y)])
+            obj_pt = obj2enp_dist*np.array([dir_cos[0]/dir_cos[2], dir_cos[1]/dir_cos[2], 0.0])
+            return obj_pt, dir_cos
+        # finite conjugates
+        if obj_img_key == 'image':
+            obj_pt = fod.pr_ht0*rel_fld_coord
+        elif value_key == 'angle':
+            fld_angle = np.deg2rad(fld_coord)
+            obj_dir = np.sin(fld_angle)
+            obj_dir[2] = np.sqrt(1 - obj_dir[0]**2 - obj_dir[1]**2)
+            obj_pt = obj2enp_dist*np.array([obj_dir[0]/obj_dir[2], obj_dir[1]/obj_dir[2], 0.0])
+            return obj_pt, obj_dir
+        else:
+            obj_pt = fld_coord
+        return obj_pt, normalize(pt1 - obj_pt)
+
+    # -------------------------------------------------- single start ray
+    def _epd_pupil(self):
+        """(pupil_value_key, pupil_value) after the image-space substitution of
+        opticalspec.py:311-325"""
+        pupil_oi_key, pupil_value_key = self.pupil.key
+        pupil_value = self.pupil.value
+        fod = self.fod
+        if pupil_oi_key == 'image':
+            if abs(fod.m) < 1e-10:
+                pupil_value_key, pupil_value = 'epd', 2*fod.enp_radius
+            elif abs(fod.enp_dist) > 1e10:
+                pupil_value_key = 'NA'
+                pupil_value = fod.obj_na
+            else:
+                pupil_value_key, pupil_value = 'epd', 2*fod.enp_radius
+        return pupil_oi_key, pupil_value_key, pupil_value
+
+    def ray_start_from_osp(self, pupil, fld, pupil_type='rel pupil'):
+        """(pt0, dir0) for one ray, opticalspec.py:289-400 (non wide-angle)."""
+        pupil_oi_key, pupil_value_key, pupil_value = self._epd_pupil()
+        n_obj, n_img = self.obj_img_rindex()
+        p0, d0 = self.obj_coords(fld)
+        fod = self.fod
+        aim_info = fld.aim_info if getattr(fld, 'aim_info', None) is not None else None
+        z_enp = fod.enp_dist
+        if 'epd' == pupil_value_key:
+            if pupil_type == 'aim pt':
+                pt0 = p0
+                pt1 = np.array([pupil[0], pupil[1], fod.obj_dist + z_enp])
+            else:
+                eprad = pupil_value/2
+                aim_pt = [0., 0.] if aim_info is None else aim_info
+                obj2enp_dist = -(fod.obj_dist + z_enp)
+                pt1 = np.array([eprad*pupil[0] + aim_pt[0],
+                                eprad*pupil[1] + aim_pt[1],
+                                fod.obj_dist + z_enp])
+                pt0 = obj2enp_dist*np.array([d0[0]/d0[2], d0[1]/d0[2], 0.])
+            dir0 = normalize(pt1 - pt0)
+        else:
+            if pupil_type == 'aim dir':
+                dir_tot = pupil
+                pt0 = p0
+            else:
+                if 'NA' in pupil_value_key:
+                    n = n_obj if pupil_oi_key == 'object' else n_img
+                    sin_ang = pupil_value/n
+                    pupil_dir = sin_ang*np.array([pupil[0], pupil[1]])
+                else:
+                    slope = -1/(2*pupil_value)
+                    hypt = np.sqrt(1 + (pupil[0]*slope)**2 + (pupil[1]*slope)**2)
+                    pupil_dir = np.array([slope*pupil[0]/hypt, slope*pupil[1]/hypt])
+                pt0 = p0
+                cr_dir = d0[:2]
+                dir_tot = pupil_dir + cr_dir
+            dir0 = np.array([dir_tot[0], dir_tot[1], np.sqrt(1 - np.dot(dir_tot, dir_tot))])
+        return pt0, dir0
+
+    # ------------------------------------------------- grid field records
+    def grid_fields(self, fields=None):
+        """Per-field constants of the 'epd' start-ray branch for the grid kernel:
+        list of dicts (pt0, aim, vlx, vux, vly, vuy) plus (eprad, z_pupil)."""
+        pupil_oi_key, pupil_value_key, pupil_value = self._epd_pupil()
+        if pupil_value_key != 'epd':
+            raise NotImplementedError('grid start rays need an epd-type pupil specification')
+        fod = self.fod
+        eprad = pupil_value/2
+        z_pupil = fod.obj_dist + fod.enp_dist
+        obj2enp_dist = -(fod.obj_dist + fod.enp_dist)
+        out = []
+        for fld in (fields if fields is not None else self.field_of_view.fields):
+            p0, d0 = self.obj_coords(fld)
+            pt0 = obj2enp_dist*np.array([d0[0]/d0[2], d0[1]/d0[2], 0.])
+            aim = [0., 0.] if getattr(fld, 'aim_info', None) is None else fld.aim_info
+            out.append({'pt0': pt0, 'aim': [float(aim[0]), float(aim[1])],
+                        'vlx': fld.vlx, 'vux': fld.vux, 'vly': fld.vly, 'vuy': fld.vuy})
+        return out, eprad, z_pupil
+
+    # ------------------------------------------------------- persistence
+    def to_dict(self):
+        return {'wvls': self.spectral_region.wavelengths,
+                'ref_wvl': self.spectral_region.reference_wvl,
+                'pupil': {'key': list(self.pupil.key), 'value': self.pupil.value},
+                'fov': {'key': list(self.field_of_view.key), 'value': self.field_of_view.value,
+                        'is_relative': self.field_of_view.is_relative,
+                        'fields': [f.to_dict() for f in self.field_of_view.fields]},
+                'focus_shift': self.defocus.focus_shift}
+
+    @classmethod
+    def from_dict(cls, d):
+        fov = d['fov']
+        fields = [Field(**f) for f in fov['fields']]
+        return cls(WvlSpec(d['wvls'], d.get('ref_wvl', 0)),
+                   PupilSpec(d['pupil']['key'], d['pupil']['value']),
+                   FieldSpec(fov['key'], fov['value'], fields, fov.get('is_relative', False)),
+                   FocusRange(d.get('focus_shift', 0.0)))
+
+
+class _ParaxData:
+    def __init__(self, fod):
+        self.fod = fod

@@ -1,0 +1,51 @@
+"""Multi-GPU sharding of pupil grids: one process per GPU, no data-path collective.
+
+Every ray is independent and the surface table is < 32 KB, so each rank
+replicates the table, takes a contiguous slice of the grid's chunk space
+(field-major, then wavelength, then pupil rows -- SURVEY.md 8(e)), generates its
+own start rays on the device and traces them.  The single collective is an
+all-gather of the ``[n_tiles, 16]`` partial spot sums (NCCL over NVLink on GPUs;
+gloo in the CPU tests), followed by a local combine on every rank.
+
+The reference has no multi-process code at all; there is nothing to mirror.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .engine import combine_summaries
+
+
+def shard_chunks(n_chunks, rank, world_size):
+    """Balanced contiguous split of ``[0, n_chunks)``: the first ``n_chunks %
+    world_size`` ranks get one extra chunk.  Returns ``(begin, end)``."""
+    base, extra = divmod(int(n_chunks), int(world_size))
+    begin = rank*base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def gather_summaries(partial, group=None):
+    """All-gather the per-rank partial summaries and combine them.
+
+    ``partial``: ``[n_tiles, 16]`` float64 tensor (CUDA for NCCL, CPU for gloo).
+    Returns the combined ``[n_tiles, 16]`` summary, identical on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return partial.clone()
+    world = dist.get_world_size(group)
+    partial = partial.contiguous()
+    out = torch.empty((world,) + tuple(partial.shape), dtype=partial.dtype, device=partial.device)
+    dist.all_gather_into_tensor(out, partial, group=group)
+    return combine_summaries(out)
+
+
+def trace_grid_sharded(table, grid, group=None, **kwargs):
+    """Trace this rank's shard of ``grid`` and return ``(local result,
+    combined summary)``.  ``kwargs`` go to ``engine.trace_grid``."""
+    from .engine import trace_grid
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    begin, end = shard_chunks(grid.n_chunks, rank, world)
+    res = trace_grid(table, grid, begin, end, **kwargs)
+    combined = gather_summaries(res.summary, group) if res.summary is not None else None
+    return res, combined

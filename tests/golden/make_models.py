@@ -1,0 +1,195 @@
+#!/usr/bin/env python3
+"""Write the model fixtures tests/golden/models/*.json (format b200rt-model-v1).
+
+Runs ONLY in the build container: it reads the reference's bundled lens data
+under /root/reference (which does not exist on the GPU box) and uses the
+reference's own ``trace_raw`` (through oracle/ref_harness.py) for chief-ray
+aiming and clear apertures.  The JSON it writes is committed, so tests, smoke()
+and bench.py never need the reference tree.
+
+Sources (numbers only; no reference source code is copied):
+  singlet     /root/reference/src/rayoptics/models/singlet_f5.roa
+  dblgauss    /root/reference/src/rayoptics/raytr/tests/ag_dblgauss_s.py  [cv, thi, n_d, V_d]
+              + spec of /root/reference/src/rayoptics/codev/tests/ag_dblgauss.seq
+              (EPD 50, fields 0/10/14 deg, VUY/VLY, WL 656.3 587.6 486.1, stop at surface 6)
+  triplet     /root/reference/src/rayoptics/models/Sasian Triplet.roa
+  rc          /root/reference/src/rayoptics/models/Ritchey_Chretien.roa (5 fields interpolated)
+  cellphone   /root/reference/src/rayoptics/optical/tests/cell_phone_camera.roa (9 fields)
+  cellphone_even  same lens, RadialPolynomial surfaces replaced by EvenPolynomial
+              ones built from their even-order coefficients (synthetic)
+  evenasph    /root/reference/src/rayoptics/zemax/tests/US08427765-1.ZMX geometry, with
+              catalogue glasses replaced by (n_d, V_d) Cauchy models (approximate)
+  zoom52      synthetic 50-surface stack (recipe below), 25 fields x 7 wavelengths
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh                      # noqa: E402
+from rayoptics_b200 import model as M, roa, vigcalc       # noqa: E402
+from rayoptics_b200.opticalspec import (OpticalSpecs, WvlSpec, PupilSpec, FieldSpec,  # noqa: E402
+                                        FocusRange)
+
+REF = '/root/reference/src/rayoptics'
+OUT = os.path.join(HERE, 'models')
+
+
+def ref_trace_fn(sm, pt0, dir0, wvl, **kw):
+    """trace() semantics of raytrace.py:51-80 on the reference's own trace_raw."""
+    R = rh.ref()
+    path = rh.ref_path(sm, wvl)
+    kw.setdefault('first_surf', 1)
+    kw.setdefault('last_surf', sm.get_num_surfaces() - 2)
+    return R.raytrace.trace_raw(iter(path), np.array(pt0, dtype=float),
+                                np.array(dir0, dtype=float), wvl, **kw)
+
+
+def finish(opm, aim=True, apertures=True):
+    opm.update_model()
+    if aim:
+        vigcalc.aim_all_fields(opm, ref_trace_fn)
+    if apertures:
+        vigcalc.set_clear_apertures(opm, ref_trace_fn)
+    return opm
+
+
+def dblgauss():
+    spec = importlib.util.spec_from_file_location(
+        'dblg', f'{REF}/raytr/tests/ag_dblgauss_s.py')
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows = [list(r) for r in mod.ag_dblgauss]
+    rows[-2][1] += rows[-1][1]      # lump the defocus into the back focal distance,
+    rows[-1][1] = 0.0               # as raytr/tests/test_sequential.py:26-27 does
+    wvls = [656.3, 587.6, 486.1]
+    sm = M.gen_sequence(rows, wvls=wvls, ref_wvl=1, stop_surface=6)
+    sm.ifcs[6].interact_mode = 'dummy'      # STO plane (ag_dblgauss.seq:26-28)
+    fields = [M.Field(y=0.0), M.Field(y=10.0000000023, vuy=0.2, vly=0.25),
+              M.Field(y=14.0000000032, vuy=0.4, vly=0.4)]
+    osp = OpticalSpecs(WvlSpec(wvls, 1), PupilSpec(('object', 'epd'), 50.0),
+                       FieldSpec(('object', 'angle'), 14.0000000032, fields))
+    return finish(M.OpticalModel(sm, osp, name='dblgauss'))
+
+
+def from_roa(rel, name, n_fields=None, aim=False, apertures=False):
+    opm = roa.open_roa(f'{REF}/{rel}')
+    opm.name = name
+    if n_fields is not None:
+        fov = opm.optical_spec.field_of_view
+        ymax = max(f.y for f in fov.fields)
+        fov.fields = [M.Field(y=ymax*i/(n_fields - 1)) for i in range(n_fields)]
+        aim = True
+    return finish(opm, aim=aim, apertures=apertures)
+
+
+def cellphone_even():
+    opm = roa.open_roa(f'{REF}/optical/tests/cell_phone_camera.roa')
+    opm.name = 'cellphone_even'
+    for ifc in opm.seq_model.ifcs:
+        p = ifc.profile
+        if type(p).__name__ == 'RadialPolynomial':
+            even = [p.coefs[i] if i < len(p.coefs) else 0.0 for i in range(1, 10, 2)]
+            ifc.profile = M.EvenPolynomial(c=p.cv, ec=p.ec, coefs=even)
+    fov = opm.optical_spec.field_of_view
+    fov.fields = [M.Field(y=i/8) for i in range(9)]
+    return finish(opm)
+
+
+def evenasph():
+    # geometry of zemax/tests/US08427765-1.ZMX (SURF 0..12); glasses -> (n_d, V_d)
+    glass = {'J-LAK14': (1.6968, 55.5), 'L-TIM28': (1.68893, 31.1), 'SF11': (1.78472, 25.7),
+             'TAF3': (1.8042, 46.5), 'TAFD30': (1.883, 40.8)}
+    surf = [  # cv, thi, glass, evenasph(cc, coefs)
+        (7.7669902912621352e-02, 3.34, 'J-LAK14', None),
+        (2.8248587570621469e-02, 0.29, None, None),
+        (7.2306579898770790e-02, 1.85, 'L-TIM28', None),
+        (1.1178180192264700e-01, 4.25, None, (2.0e-2, [0.0, 1.10721e-5, 1.837e-7])),
+        (0.0, 5.4, None, None),            # STOP
+        (-1.2048192771084336e-01, 0.65, 'SF11', None),
+        (-1.8660197798096658e-02, 0.22, None, None),
+        (-2.6688017080330931e-02, 3.62, 'TAF3', None),
+        (-8.5012326787384171e-02, 0.12, None, None),
+        (4.8473097430925833e-03, 3.5, 'TAFD30', None),
+        (-3.7707390648567117e-02, 21.25417782777, None, None)]
+    ifcs = [M.Surface(lbl='Obj', interact_mode='dummy')]
+    gaps = [M.Gap(1e10)]
+    for i, (cv, thi, g, asp) in enumerate(surf):
+        prf = M.Spherical(c=cv) if asp is None else M.EvenPolynomial(c=cv, cc=asp[0], coefs=asp[1])
+        mode = 'dummy' if i == 4 else 'transmit'
+        ifcs.append(M.Surface(profile=prf, interact_mode=mode))
+        gaps.append(M.Gap(thi, M.AbbeGlass(*glass[g], label=g) if g else M.Air()))
+    ifcs.append(M.Surface(lbl='Img', interact_mode='dummy'))
+    wvls = [486.1327, 587.5618, 656.2725]
+    sm = M.SequentialModel(ifcs, gaps, stop_surface=5, wvlns=wvls, ref_wvl=1)
+    fields = [M.Field(y=13.6*i/8) for i in range(9)]
+    osp = OpticalSpecs(WvlSpec(wvls, 1), PupilSpec(('image', 'f/#'), 2.1),
+                       FieldSpec(('object', 'angle'), 13.6, fields))
+    return finish(M.OpticalModel(sm, osp, name='evenasph'))
+
+
+def zoom52():
+    """Synthetic 50-surface stack: 12 weak air-spaced doublet cells (4 surfaces
+    each) + one focusing singlet.  Deterministic, no RNG."""
+    ifcs = [M.Surface(lbl='Obj', interact_mode='dummy')]
+    gaps = [M.Gap(1e10)]
+    crown, flint = M.AbbeGlass(1.62041, 60.3, 'crown'), M.AbbeGlass(1.60342, 38.0, 'flint')
+    for c in range(12):
+        s = 1.0 + 0.02*c
+        cell = [(1/(150.0*s), 6.0, crown), (-1/(320.0*s), 1.5, None),
+                (-1/(140.0*s), 3.0, flint), (1/(600.0*s), 6.0, None)]
+        if c % 3 == 1:   # every third cell carries conic surfaces
+            profs = [M.Conic(c=cell[0][0], cc=-0.4), M.Spherical(c=cell[1][0]),
+                     M.Conic(c=cell[2][0], cc=0.25), M.Spherical(c=cell[3][0])]
+        else:
+            profs = [M.Spherical(c=k[0]) for k in cell]
+        for prf, (cv, thi, g) in zip(profs, cell):
+            ifcs.append(M.Surface(profile=prf))
+            gaps.append(M.Gap(thi, g if g else M.Air()))
+    ifcs.append(M.Surface(profile=M.Spherical(c=1/90.0)))
+    gaps.append(M.Gap(7.0, crown))
+    ifcs.append(M.Surface(profile=M.Spherical(c=-1/400.0)))
+    gaps.append(M.Gap(100.0))
+    ifcs.append(M.Surface(lbl='Img', interact_mode='dummy'))
+    wvls = [656.3, 620.0, 587.6, 550.0, 520.0, 486.1, 450.0]
+    sm = M.SequentialModel(ifcs, gaps, stop_surface=25, wvlns=wvls, ref_wvl=2)
+    fields = [M.Field(y=3.0*i/24) for i in range(25)]
+    osp = OpticalSpecs(WvlSpec(wvls, 2), PupilSpec(('object', 'epd'), 24.0),
+                       FieldSpec(('object', 'angle'), 3.0, fields))
+    opm = M.OpticalModel(sm, osp, name='zoom52')
+    sm.gaps[-1].thi = float(osp.fod.img_dist)     # paraxial focus
+    return finish(opm)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    models = {
+        'singlet': lambda: from_roa('models/singlet_f5.roa', 'singlet'),
+        'dblgauss': dblgauss,
+        'triplet': lambda: from_roa('models/Sasian Triplet.roa', 'triplet'),
+        'rc': lambda: from_roa('models/Ritchey_Chretien.roa', 'rc', n_fields=5, apertures=True),
+        'cellphone': lambda: from_roa('optical/tests/cell_phone_camera.roa', 'cellphone',
+                                      n_fields=9),
+        'cellphone_even': cellphone_even,
+        'evenasph': evenasph,
+        'zoom52': zoom52,
+    }
+    only = sys.argv[1:]
+    for name, fn in models.items():
+        if only and name not in only:
+            continue
+        opm = fn()
+        opm.save(os.path.join(OUT, name + '.json'))
+        fod = opm.optical_spec.fod
+        print(f'{name:15s} n_ifc={opm.seq_model.get_num_surfaces():3d} efl={fod.efl:10.4f} '
+              f'enp_dist={fod.enp_dist:10.4f} enp_r={fod.enp_radius:8.4f} '
+              f'aims={[list(np.round(f.aim_info, 6)) for f in opm.optical_spec.fov.fields][:3]}')
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,153 @@
+"""CPU: host logic and the C-ABI surface (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, MODEL_NAMES, load_model
+from rayoptics_b200 import _abi, table as T, model as M, engine as E, parallel as P
+
+
+def test_library_exports_every_declared_symbol():
+    """libb200rt.so loads here (no GPU) and exports exactly what include/b200rt.h declares."""
+    hdr = open(os.path.join(ROOT, 'include', 'b200rt.h')).read()
+    declared = set(re.findall(r'\b(rt_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(_abi.EXPORTS)
+    lib = _abi.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.rt_abi_version() == _abi.RT_ABI_VERSION
+    assert lib.rt_launch_count() == 0
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors have the sizes nvcc/gcc give the C structs."""
+    from oracle import rt_oracle
+    assert rt_oracle.lib().rto_sizeof_surface_desc() == C.sizeof(_abi.rt_surface_desc) == 480
+    assert C.sizeof(_abi.rt_opts) == 40
+    assert C.sizeof(_abi.rt_out) == 18*8
+    assert C.sizeof(_abi.rt_field_desc) == 72
+
+
+def test_bad_arguments_return_error_codes():
+    lib = _abi.load_library()
+    handle = C.c_void_p()
+    rc = lib.rt_table_create(None, 0, None, 0, 0, C.byref(handle))
+    assert rc == -1 and b'rt_table_create' in lib.rt_last_error()
+    assert lib.rt_table_destroy(None) == 0
+    assert lib.rt_grid_destroy(None) == 0
+
+
+def test_no_cpu_fallback_when_library_missing(monkeypatch):
+    monkeypatch.setattr(_abi, '_lib', None)
+    monkeypatch.setattr(_abi, 'LIB_NAME', 'libb200rt_missing.so')
+    with pytest.raises(ImportError, match='no CPU fallback'):
+        _abi.load_library()
+
+
+@pytest.mark.parametrize('name', MODEL_NAMES)
+def test_model_roundtrip_and_table(name):
+    opm = load_model(name)
+    sm = opm.seq_model
+    d2 = M.OpticalModel.from_dict(opm.to_dict())
+    a, na, _ = T.describe_model(sm)
+    b, nb, _ = T.describe_model(d2.seq_model)
+    assert bytes(a) == bytes(b) and np.array_equal(na, nb)
+    assert len(a) == sm.get_num_surfaces() and na.shape == (len(sm.wvlns), len(a))
+    assert a[len(a) - 1].mode == _abi.MODE_IDS['dummy']
+    for i, ifc in enumerate(sm.ifcs):
+        assert a[i].profile == _abi.PROFILE_IDS[type(ifc.profile).__name__]
+        assert a[i].cv == ifc.profile.cv and a[i].max_aperture == ifc.max_aperture
+
+
+def test_table_accepts_reference_objects():
+    """describe_path works on the reference's own Surface/profile objects."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip('/root/reference not present (GPU box)')
+    opm = load_model('cellphone')
+    wvl = opm.seq_model.central_wavelength()
+    a, na = T.describe_path(opm.seq_model.path(wvl))
+    b, nb = T.describe_path(rh.ref_path(opm.seq_model, wvl))
+    assert bytes(a) == bytes(b) and na == nb
+
+
+def test_unsupported_interfaces_are_rejected():
+    class ThinLens:           # reference: oprops/thinlens.py (no profile, phase element)
+        interact_mode = 'transmit'
+        phase_element = object()
+    with pytest.raises(T.UnsupportedInterfaceError):
+        T.describe_path([(ThinLens(), None, None, 1.0, 1)])
+
+
+def test_accumulated_steps_is_the_reference_loop():
+    """start += step repeated, NOT linspace (raytr/trace.py:567-604)."""
+    xs = E.accumulated_steps(-1.0, 1.0, 512)
+    start = np.array([-1.0, -1.0])
+    step = np.array((np.array([1.0, 1.0]) - start)/(512 - 1))
+    ref = []
+    for _ in range(512):
+        ref.append(start[0])
+        start[0] += step[0]
+    assert np.array_equal(xs, np.array(ref))
+    assert not np.array_equal(xs, np.linspace(-1, 1, 512))
+
+
+@pytest.mark.parametrize('name', ['dblgauss', 'rc', 'cellphone', 'singlet'])
+def test_start_rays_numpy_vs_oracle(oracle, name):
+    """ray_start_from_osp evaluated by numpy (the reference's expressions) and
+    the C restatement used by the oracle / mirrored by the grid kernel agree
+    bit for bit, including vignetting and the accumulated pupil steps."""
+    opm = load_model(name)
+    osp, sm = opm.optical_spec, opm.seq_model
+    num = 9
+    spec = E.grid_spec_for_model(opm, num)
+    p, d, wv, pup = oracle.grid_start_rays(spec.c_spec(), 0, spec.n_rays)
+    xs = E.accumulated_steps(-1.0, 1.0, num)
+    k = 0
+    for fld in osp.fov.fields:
+        for wi in range(len(sm.wvlns)):
+            for i in range(num):
+                for j in range(num):
+                    pupil = fld.apply_vignetting(np.array([xs[i], xs[j]]))
+                    pt0, dir0 = osp.ray_start_from_osp(pupil, fld, 'rel pupil')
+                    if dir0[2]*sm.z_dir[0] < 0:
+                        dir0 = -dir0
+                    assert np.array_equal(pup[:, k], pupil)
+                    assert np.array_equal(p[:, k], pt0) and np.array_equal(d[:, k], dir0)
+                    assert wv[k] == wi
+                    k += 1
+    assert k == spec.n_rays
+
+
+def test_grid_geometry():
+    opm = load_model('dblgauss')
+    spec = E.grid_spec_for_model(opm, 100)
+    assert spec.n_rays == 9*100*100 and spec.chunks_per_tile == 40 and spec.n_chunks == 360
+    assert spec.first_ray_of_chunk(0) == 0 and spec.first_ray_of_chunk(40) == 10000
+    assert spec.first_ray_of_chunk(39) == 39*256 and spec.rays_in_chunks(39, 41) == 10000 - 39*256 + 256
+    assert spec.rays_in_chunks(0, spec.n_chunks) == spec.n_rays
+
+
+def test_shard_chunks_partitions_exactly():
+    for n in (0, 1, 7, 360, 9216, 1000003):
+        for world in (1, 2, 3, 4, 8):
+            edges = [P.shard_chunks(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for (a, b), (c, d) in zip(edges[:-1], edges[1:]):
+                assert b == c and a <= b
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_first_order_against_stored_reference_values():
+    """Chief-ray aim points stored by the reference in its .roa files pin
+    first-order data + aiming: Sasian triplet 20 deg field."""
+    opm = load_model('triplet')
+    aim = opm.optical_spec.fov.fields[1].aim_info
+    assert aim[1] == pytest.approx(-0.3143052528206426, abs=1e-12)
+    fod = opm.optical_spec.fod
+    assert fod.efl == pytest.approx(50.0, rel=2e-4)
+    assert load_model('dblgauss').optical_spec.fod.efl == pytest.approx(100.0, rel=2e-4)
