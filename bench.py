@@ -354,7 +354,7 @@ def run_b200(args):
                 'frac': ach_gbs/hbm_peak,
                 'peak_source': 'MEASURED_PEAKS.json (of measured)' if 'hbm_gbs' in peaks
                 else 'B200_PROFILING.md fallback (of fallback)',
-                'traffic': None, 'bytes_per_ray': bpr, 'kernel': 'k_trace_grid<0,1,1>',
+                'traffic': None, 'bytes_per_ray': bpr, 'kernel': 'k_trace_grid_lean<0,1>',
                 'kernel_ms': kern_ms,
                 'limiter': 'fp64 vector pipe (kernel is register-resident; HBM only receives results)',
                 'fp64': {'achieved_tflops': ach_tf, 'peak_tflops': fp64_peak,

@@ -234,6 +234,11 @@ int64_t rt_launch_count(void);
 /* fp64 vector-pipe peak of `device` in TFLOP/s, measured with a chain of
  * independent DFMAs (the roofline denominator of the register-resident trace) */
 int rt_measure_fp64_peak(int32_t device, double *tflops);
+/* self-test of the shared-reciprocal division of the specialised kernels against
+ * the IEEE division (n_blocks x 256 threads x n_per_thread operand sets);
+ * *mismatches must come back 0 */
+int rt_selftest_division(int32_t device, int32_t n_blocks, int64_t n_per_thread, uint64_t seed,
+                         uint64_t *mismatches);
 
 #ifdef __cplusplus
 }

@@ -97,7 +97,8 @@ LIB_NAME = 'libb200rt.so'
 EXPORTS = ['rt_table_create', 'rt_table_destroy', 'rt_table_dims',
            'rt_trace_bundle', 'rt_grid_create', 'rt_grid_destroy', 'rt_grid_dims',
            'rt_grid_scratch_bytes', 'rt_trace_grid',
-           'rt_last_error', 'rt_abi_version', 'rt_launch_count', 'rt_measure_fp64_peak']
+           'rt_last_error', 'rt_abi_version', 'rt_launch_count', 'rt_measure_fp64_peak',
+           'rt_selftest_division']
 
 _lib = None
 
@@ -143,6 +144,8 @@ def load_library():
     lib.rt_launch_count.restype = i64
     lib.rt_measure_fp64_peak.argtypes = [i32, c_double_p]
     lib.rt_measure_fp64_peak.restype = i32
+    lib.rt_selftest_division.argtypes = [i32, i32, i64, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.rt_selftest_division.restype = i32
     for name in ('rt_table_create', 'rt_table_destroy', 'rt_table_dims', 'rt_trace_bundle',
                  'rt_grid_create', 'rt_grid_destroy', 'rt_grid_dims', 'rt_trace_grid'):
         getattr(lib, name).restype = i32

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "rt_device.cuh"
+#include "rt_lean.cuh"
 
 using namespace b200rt;
 
@@ -73,6 +74,8 @@ struct rt_table {
     double *d_n;
     size_t stage_bytes;      /* shared memory needed to stage the table */
     bool stage;              /* false: table too large, read it from global/L1 */
+    bool lean;               /* all interfaces quadric, unrotated, max_aperture clipping only */
+    size_t lean_bytes;       /* shared memory of the lean plan */
 };
 
 struct rt_grid {
@@ -159,13 +162,14 @@ k_trace_bundle(const rt_surface_desc *__restrict__ g_surfs, const double *__rest
     }
 }
 
-/* deterministic CTA reduction of the 16 summary quantities */
-__device__ __forceinline__ void block_reduce_summary(double (&v)[RT_SUMMARY_DOUBLES], double *dst)
+/* Deterministic warp reduction of the 16 summary quantities; lane 0 writes the
+ * warp's partial.  No CTA barrier: warps whose rays were clipped early do not
+ * wait for the others. */
+__device__ __forceinline__ void warp_reduce_summary(double (&v)[RT_SUMMARY_DOUBLES], double *dst)
 {
-    __shared__ double wsum[RT_BLOCK/32][RT_SUMMARY_DOUBLES];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < RT_SUMMARY_DOUBLES; k++) {
+    for (int k = 0; k < RT_SUMMARY_DOUBLES - 1; k++) {
         double x = v[k];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -174,21 +178,68 @@ __device__ __forceinline__ void block_reduce_summary(double (&v)[RT_SUMMARY_DOUB
             else if (k == 11 || k == 13) x = fmax(x, y);
             else x = x + y;
         }
-        if (lane == 0) wsum[warp][k] = x;
+        if (lane == 0) dst[k] = x;
     }
-    __syncthreads();
-    if (threadIdx.x < RT_SUMMARY_DOUBLES) {
-        const int k = threadIdx.x;
-        double x = wsum[0][k];
-        for (int w = 1; w < RT_BLOCK/32; w++) {
-            double y = wsum[w][k];
-            if (k == 10 || k == 12) x = fmin(x, y);
-            else if (k == 11 || k == 13) x = fmax(x, y);
-            else x = x + y;
+}
+
+/* start ray of grid ray (tile, loc): Field.apply_vignetting + ray_start_from_osp
+ * 'epd' branch + the virtual-object flip of trace_base */
+template <bool LEAN>
+__device__ __forceinline__ void grid_start_ray(const GridDev &G, int f, int64_t loc, Vec3 &p0, Vec3 &d0)
+{
+    const int i = (int)(loc/G.ny), j = (int)(loc - (int64_t)i*G.ny);
+    const rt_field_desc &F = G.fields[f];
+    /* Field.apply_vignetting, opticalspec.py:1339-1353 */
+    double pupx = G.pupil_x[(int64_t)f*G.nx + i], pupy = G.pupil_y[(int64_t)f*G.ny + j];
+    if (G.apply_vignetting) {
+        const double vlx = F.vlx, vux = F.vux, vly = F.vly, vuy = F.vuy;
+        if (pupx < 0.0) { if (vlx != 0.0) pupx *= (1.0 - vlx); }
+        else            { if (vux != 0.0) pupx *= (1.0 - vux); }
+        if (pupy < 0.0) { if (vly != 0.0) pupy *= (1.0 - vly); }
+        else            { if (vuy != 0.0) pupy *= (1.0 - vuy); }
+    }
+    /* ray_start_from_osp 'epd' branch, opticalspec.py:354-366 */
+    p0.x = F.pt0[0]; p0.y = F.pt0[1]; p0.z = F.pt0[2];
+    Vec3 pt1 = {G.eprad*pupx + F.aim[0], G.eprad*pupy + F.aim[1], G.z_pupil};
+    Vec3 dv = {pt1.x - p0.x, pt1.y - p0.y, pt1.z - p0.z};
+    d0 = LEAN ? normalize3_shared(dv) : normalize3(dv);
+    /* trace_base virtual-object flip, trace.py:305-308 */
+    if (d0.z*(double)G.flip_z_dir < 0) { d0.x = -d0.x; d0.y = -d0.y; d0.z = -d0.z; }
+}
+
+/* transverse aberration (focus_pupil_coords, analyses.py:561-580) + spot sums */
+template <bool SUMMARY>
+__device__ __forceinline__ void grid_epilogue(const GridDev &G, const rt_out &out, int64_t tile,
+                                              int64_t k, const RayResult &R,
+                                              double (&v)[RT_SUMMARY_DOUBLES])
+{
+    if (out.abr_x || SUMMARY) {
+        const double rx = G.ref_img ? G.ref_img[tile*2 + 0] : 0.0;
+        const double ry = G.ref_img ? G.ref_img[tile*2 + 1] : 0.0;
+        double dist = G.foc/R.d.z;
+        double ax = (R.p.x + dist*R.d.x) - rx;
+        double ay = (R.p.y + dist*R.d.y) - ry;
+        if (out.abr_x) { out.abr_x[k] = ax; out.abr_y[k] = ay; }
+        if (SUMMARY) {
+            if (R.status == RT_RAY_OK) {
+                v[0] = 1.0;
+                v[5] = ax; v[6] = ay; v[7] = ax*ax; v[8] = ay*ay; v[9] = ax*ay;
+                v[10] = v[11] = ax; v[12] = v[13] = ay;
+                v[14] = R.op;
+            } else if (R.status == RT_RAY_MISSED) v[1] = 1.0;
+            else if (R.status == RT_RAY_TIR) v[2] = 1.0;
+            else if (R.status == RT_RAY_BLOCKED) v[3] = 1.0;
+            else v[4] = 1.0;
         }
-        dst[k] = x;
     }
-    __syncthreads();
+}
+
+__device__ __forceinline__ void summary_init(double (&v)[RT_SUMMARY_DOUBLES])
+{
+#pragma unroll
+    for (int k = 0; k < RT_SUMMARY_DOUBLES; k++) v[k] = 0.0;
+    v[10] = v[12] = CUDART_INF;
+    v[11] = v[13] = -CUDART_INF;
 }
 
 template <bool FULL, bool SUMMARY, bool STAGE>
@@ -208,87 +259,192 @@ k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restri
     for (int64_t c = chunk_begin + blockIdx.x; c < chunk_end; c += gridDim.x) {
         const int64_t tile = c/G.chunks_per_tile;
         const int64_t loc = (c - tile*G.chunks_per_tile)*RT_BLOCK + threadIdx.x;
-        const bool valid = loc < G.rays_per_tile;
         const int f = (int)(tile/G.n_wvls);
         const int w = (int)(tile - (int64_t)f*G.n_wvls);
         double v[RT_SUMMARY_DOUBLES];
-        if (SUMMARY) {
-#pragma unroll
-            for (int k = 0; k < RT_SUMMARY_DOUBLES; k++) v[k] = 0.0;
-            v[10] = v[12] = CUDART_INF;
-            v[11] = v[13] = -CUDART_INF;
-        }
-        if (valid) {
-            const int i = (int)(loc/G.ny), j = (int)(loc - (int64_t)i*G.ny);
-            const rt_field_desc F = G.fields[f];
-            /* Field.apply_vignetting, opticalspec.py:1339-1353 */
-            double pupx = G.pupil_x[(int64_t)f*G.nx + i], pupy = G.pupil_y[(int64_t)f*G.ny + j];
-            if (G.apply_vignetting) {
-                if (pupx < 0.0) { if (F.vlx != 0.0) pupx *= (1.0 - F.vlx); }
-                else            { if (F.vux != 0.0) pupx *= (1.0 - F.vux); }
-                if (pupy < 0.0) { if (F.vly != 0.0) pupy *= (1.0 - F.vly); }
-                else            { if (F.vuy != 0.0) pupy *= (1.0 - F.vuy); }
-            }
-            /* ray_start_from_osp 'epd' branch, opticalspec.py:354-366 */
-            Vec3 p0 = {F.pt0[0], F.pt0[1], F.pt0[2]};
-            Vec3 pt1 = {G.eprad*pupx + F.aim[0], G.eprad*pupy + F.aim[1], G.z_pupil};
-            Vec3 dv = {pt1.x - p0.x, pt1.y - p0.y, pt1.z - p0.z};
-            Vec3 d0 = normalize3(dv);
-            /* trace_base virtual-object flip, trace.py:305-308 */
-            if (d0.z*(double)G.flip_z_dir < 0) { d0.x = -d0.x; d0.y = -d0.y; d0.z = -d0.z; }
-
+        if (SUMMARY) summary_init(v);
+        if (loc < G.rays_per_tile) {
+            Vec3 p0, d0;
+            grid_start_ray<false>(G, f, loc, p0, d0);
             const int64_t k = tile*G.rays_per_tile + loc - ray0;
             FullWriter fw = {FULL ? out.full + k : nullptr, out.full_stride};
             RayResult R;
             trace_ray<FULL>(tab, ntab + (int64_t)G.wvl_idx[w]*n_ifc, n_ifc, o, p0, d0, fw, R);
             store_result(out, k, R);
-
-            if (out.abr_x || SUMMARY) {
-                /* focus_pupil_coords, analyses.py:561-580 */
-                const double rx = G.ref_img ? G.ref_img[(tile)*2 + 0] : 0.0;
-                const double ry = G.ref_img ? G.ref_img[(tile)*2 + 1] : 0.0;
-                double dist = G.foc/R.d.z;
-                double ax = (R.p.x + dist*R.d.x) - rx;
-                double ay = (R.p.y + dist*R.d.y) - ry;
-                if (out.abr_x) { out.abr_x[k] = ax; out.abr_y[k] = ay; }
-                if (SUMMARY) {
-                    if (R.status == RT_RAY_OK) {
-                        v[0] = 1.0;
-                        v[5] = ax; v[6] = ay; v[7] = ax*ax; v[8] = ay*ay; v[9] = ax*ay;
-                        v[10] = v[11] = ax; v[12] = v[13] = ay;
-                        v[14] = R.op;
-                    } else if (R.status == RT_RAY_MISSED) v[1] = 1.0;
-                    else if (R.status == RT_RAY_TIR) v[2] = 1.0;
-                    else if (R.status == RT_RAY_BLOCKED) v[3] = 1.0;
-                    else v[4] = 1.0;
-                }
-            }
+            grid_epilogue<SUMMARY>(G, out, tile, k, R, v);
         }
         if (SUMMARY)
-            block_reduce_summary(v, scratch + (c - chunk_begin)*RT_SUMMARY_DOUBLES);
+            warp_reduce_summary(v, scratch + ((c - chunk_begin)*(RT_BLOCK/32) + (threadIdx.x >> 5))
+                                              *RT_SUMMARY_DOUBLES);
     }
 }
 
-/* one thread per (tile, quantity): sum this call's chunk partials in chunk order */
-__global__ void k_reduce_summary(const double *__restrict__ scratch, int64_t chunk_begin,
-                                 int64_t chunk_end, int64_t chunks_per_tile, int64_t n_tiles,
-                                 double *__restrict__ summary)
+/* ---- lean kernels: plan built in shared memory by the CTA (rt_lean.cuh) */
+template <int OUT>
+__global__ void __launch_bounds__(RT_BLOCK, 3)
+k_trace_bundle_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
+                    int n_ifc, int n_wvl, int64_t n_rays,
+                    const double *__restrict__ px, const double *__restrict__ py,
+                    const double *__restrict__ pz, const double *__restrict__ dx,
+                    const double *__restrict__ dy, const double *__restrict__ dz,
+                    const int32_t *__restrict__ wvl_idx, rt_opts o, rt_out out)
 {
-    const int64_t idx = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
-    if (idx >= n_tiles*RT_SUMMARY_DOUBLES) return;
-    const int64_t tile = idx/RT_SUMMARY_DOUBLES;
-    const int k = (int)(idx - tile*RT_SUMMARY_DOUBLES);
+    extern __shared__ __align__(16) unsigned char smem[];
+    LeanSurf *ls = reinterpret_cast<LeanSurf *>(smem);
+    LeanIdx *li = reinterpret_cast<LeanIdx *>(ls + n_ifc);
+    build_plan(g_surfs, g_n, n_ifc, n_wvl, o, ls, li);
+    __syncthreads();
+
+    const int64_t step = (int64_t)gridDim.x*blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x*blockDim.x + threadIdx.x; r < n_rays; r += step) {
+        Vec3 p0 = {px[r], py[r], pz[r]};
+        Vec3 d0 = {dx[r], dy[r], dz[r]};
+        const int w = wvl_idx ? wvl_idx[r] : o.wvl_idx;
+        FullWriter fw = {OUT == 2 ? out.full + r : nullptr, out.full_stride};
+        RayResult R;
+        trace_ray_lean<OUT>(ls, li + (int64_t)w*n_ifc, n_ifc, o, p0, d0, fw, R);
+        store_result(out, r, R);
+    }
+}
+
+template <int OUT, bool SUMMARY>
+__global__ void __launch_bounds__(RT_BLOCK, 3)
+k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
+                  int n_ifc, int n_wvl, GridDev G, int64_t chunk_begin, int64_t chunk_end,
+                  rt_opts o, rt_out out, double *__restrict__ scratch)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    LeanSurf *ls = reinterpret_cast<LeanSurf *>(smem);
+    LeanIdx *li = reinterpret_cast<LeanIdx *>(ls + n_ifc);
+    build_plan(g_surfs, g_n, n_ifc, n_wvl, o, ls, li);
+    __syncthreads();
+
+    const int64_t tile0 = chunk_begin/G.chunks_per_tile;
+    const int64_t ray0 = tile0*G.rays_per_tile + (chunk_begin - tile0*G.chunks_per_tile)*RT_BLOCK;
+
+    for (int64_t c = chunk_begin + blockIdx.x; c < chunk_end; c += gridDim.x) {
+        const int64_t tile = c/G.chunks_per_tile;
+        const int64_t loc = (c - tile*G.chunks_per_tile)*RT_BLOCK + threadIdx.x;
+        const int f = (int)(tile/G.n_wvls);
+        const int w = (int)(tile - (int64_t)f*G.n_wvls);
+        double v[RT_SUMMARY_DOUBLES];
+        if (SUMMARY) summary_init(v);
+        if (loc < G.rays_per_tile) {
+            Vec3 p0, d0;
+            grid_start_ray<true>(G, f, loc, p0, d0);
+            const int64_t k = tile*G.rays_per_tile + loc - ray0;
+            FullWriter fw = {OUT == 2 ? out.full + k : nullptr, out.full_stride};
+            RayResult R;
+            trace_ray_lean<OUT>(ls, li + (int64_t)G.wvl_idx[w]*n_ifc, n_ifc, o, p0, d0, fw, R);
+            store_result(out, k, R);
+            grid_epilogue<SUMMARY>(G, out, tile, k, R, v);
+        }
+        if (SUMMARY)
+            warp_reduce_summary(v, scratch + ((c - chunk_begin)*(RT_BLOCK/32) + (threadIdx.x >> 5))
+                                              *RT_SUMMARY_DOUBLES);
+    }
+}
+
+/* division self-test: div_shared/normalize3_shared against the IEEE `/` */
+__global__ void k_selftest_division(uint64_t seed, int64_t n_per_thread, unsigned long long *mismatch)
+{
+    uint64_t x = seed + 0x9E3779B97F4A7C15ull*(uint64_t)(blockIdx.x*blockDim.x + threadIdx.x + 1);
+    unsigned long long bad = 0;
+    for (int64_t it = 0; it < n_per_thread; it++) {
+        uint64_t r[4];
+        for (int k = 0; k < 4; k++) {          /* splitmix64 */
+            x += 0x9E3779B97F4A7C15ull;
+            uint64_t z = x;
+            z = (z ^ (z >> 30))*0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27))*0x94D049BB133111EBull;
+            r[k] = z ^ (z >> 31);
+        }
+        /* operands: random mantissas, exponents spread over a window chosen by the draw:
+         * mostly ordinary magnitudes, sometimes extreme (exercise the fallback) */
+        const int mode = (int)(r[3] & 15);
+        const int span = mode < 12 ? 40 : (mode < 15 ? 600 : 2046);
+        double a[3], b;
+        uint64_t bm = (r[3] >> 8) & 0xFFFFFFFFFFFFFull;
+        if (((r[3] >> 4) & 15) == 0) bm = 0xFFFFFFFFFFFFFull;        /* all-ones mantissa */
+        if (((r[3] >> 4) & 15) == 1) bm = 0;                          /* power of two */
+        int be = 1023 + (int)((r[2] >> 40) % (uint64_t)span) - span/2;
+        be = be < 0 ? 0 : (be > 2047 ? 2047 : be);
+        b = __longlong_as_double((long long)(((r[2] & 1) << 63) | ((uint64_t)be << 52) | bm));
+        for (int k = 0; k < 3; k++) {
+            int ae = 1023 + (int)((r[k] >> 53) % (uint64_t)span) - span/2;
+            ae = ae < 0 ? 0 : (ae > 2047 ? 2047 : ae);
+            uint64_t am = r[k] & 0xFFFFFFFFFFFFFull;
+            if (((r[k] >> 60) & 7) == 0) am = 0;
+            a[k] = __longlong_as_double((long long)(((r[k] >> 52 & 1) << 63) | ((uint64_t)ae << 52) | am));
+            if (mode == 7 && k == 2) a[k] = 0.0;
+        }
+        const double rr = rcp_refined(b);
+        for (int k = 0; k < 3; k++) {
+            double q1 = div_shared(a[k], b, rr), q2 = a[k]/b;
+            if (__double_as_longlong(q1) != __double_as_longlong(q2) && !(isnan(q1) && isnan(q2))) bad++;
+        }
+        Vec3 v = {a[0], a[1], a[2]};
+        if (mode < 12) {
+            Vec3 n1 = normalize3_shared(v), n2 = normalize3(v);
+            if (__double_as_longlong(n1.x) != __double_as_longlong(n2.x) ||
+                __double_as_longlong(n1.y) != __double_as_longlong(n2.y) ||
+                __double_as_longlong(n1.z) != __double_as_longlong(n2.z)) {
+                if (!(isnan(n1.x) && isnan(n2.x)) ) bad++;
+            }
+        }
+    }
+    if (bad) atomicAdd(mismatch, bad);
+}
+
+/* One CTA per tile: fixed-order reduction of this call's per-warp partials.
+ * Thread t accumulates partials t, t+256, ... (ascending), then the 256 thread
+ * sums are combined by a fixed binary tree in shared memory -> bit-reproducible
+ * for a given chunk range. */
+#define RT_RED_THREADS 256
+__global__ void __launch_bounds__(RT_RED_THREADS)
+k_reduce_summary(const double *__restrict__ scratch, int64_t chunk_begin, int64_t chunk_end,
+                 int64_t chunks_per_tile, double *__restrict__ summary)
+{
+    __shared__ double sh[RT_RED_THREADS][RT_SUMMARY_DOUBLES + 1];
+    const int64_t tile = blockIdx.x;
     int64_t c0 = tile*chunks_per_tile, c1 = c0 + chunks_per_tile;
     if (c0 < chunk_begin) c0 = chunk_begin;
     if (c1 > chunk_end) c1 = chunk_end;
-    double x = (k == 10 || k == 12) ? CUDART_INF : ((k == 11 || k == 13) ? -CUDART_INF : 0.0);
-    for (int64_t c = c0; c < c1; c++) {
-        double y = scratch[(c - chunk_begin)*RT_SUMMARY_DOUBLES + k];
-        if (k == 10 || k == 12) x = fmin(x, y);
-        else if (k == 11 || k == 13) x = fmax(x, y);
-        else x = x + y;
+    const int64_t w0 = (c0 - chunk_begin)*(RT_BLOCK/32), w1 = (c1 - chunk_begin)*(RT_BLOCK/32);
+    double x[RT_SUMMARY_DOUBLES];
+#pragma unroll
+    for (int k = 0; k < RT_SUMMARY_DOUBLES; k++) x[k] = 0.0;
+    x[10] = x[12] = CUDART_INF;
+    x[11] = x[13] = -CUDART_INF;
+    for (int64_t w = w0 + threadIdx.x; w < w1; w += RT_RED_THREADS) {
+        const double *p = scratch + w*RT_SUMMARY_DOUBLES;
+#pragma unroll
+        for (int k = 0; k < RT_SUMMARY_DOUBLES - 1; k++) {
+            double y = p[k];
+            if (k == 10 || k == 12) x[k] = fmin(x[k], y);
+            else if (k == 11 || k == 13) x[k] = fmax(x[k], y);
+            else x[k] = x[k] + y;
+        }
     }
-    summary[idx] = x;
+#pragma unroll
+    for (int k = 0; k < RT_SUMMARY_DOUBLES; k++) sh[threadIdx.x][k] = x[k];
+    __syncthreads();
+    for (int off = RT_RED_THREADS/2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+#pragma unroll
+            for (int k = 0; k < RT_SUMMARY_DOUBLES - 1; k++) {
+                double a = sh[threadIdx.x][k], y = sh[threadIdx.x + off][k];
+                if (k == 10 || k == 12) a = fmin(a, y);
+                else if (k == 11 || k == 13) a = fmax(a, y);
+                else a = a + y;
+                sh[threadIdx.x][k] = a;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < RT_SUMMARY_DOUBLES)
+        summary[tile*RT_SUMMARY_DOUBLES + threadIdx.x] =
+            (threadIdx.x == RT_SUMMARY_DOUBLES - 1) ? 0.0 : sh[0][threadIdx.x];
 }
 
 /* fp64 FMA microbenchmark: 8 independent chains per thread */
@@ -384,6 +540,52 @@ static int launch_grid(const rt_table *t, const rt_grid *g, const GridDev &G, in
     return RT_OK;
 }
 
+template <int OUT>
+static int launch_bundle_lean(const rt_table *t, int64_t n_rays, const double *px, const double *py,
+                              const double *pz, const double *dx, const double *dy, const double *dz,
+                              const int32_t *wvl_idx, const rt_opts *o, const rt_out *out,
+                              cudaStream_t stream)
+{
+    auto kern = k_trace_bundle_lean<OUT>;
+    const size_t smem = t->lean_bytes;
+    int rc = prep_kernel(kern, smem);
+    if (rc) return rc;
+    int grid;
+    rc = persistent_grid(kern, smem, t->sm_count, (n_rays + RT_BLOCK - 1)/RT_BLOCK, &grid);
+    if (rc) return rc;
+    kern<<<grid, RT_BLOCK, smem, stream>>>(t->d_surfs, t->d_n, t->n_ifc, t->n_wvl, n_rays,
+                                           px, py, pz, dx, dy, dz, wvl_idx, *o, *out);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+template <int OUT, bool SUMMARY>
+static int launch_grid_lean(const rt_table *t, const GridDev &G, int64_t cb, int64_t ce,
+                            const rt_opts *o, const rt_out *out, double *scratch, cudaStream_t stream)
+{
+    auto kern = k_trace_grid_lean<OUT, SUMMARY>;
+    const size_t smem = t->lean_bytes;
+    int rc = prep_kernel(kern, smem);
+    if (rc) return rc;
+    int grid;
+    rc = persistent_grid(kern, smem, t->sm_count, ce - cb, &grid);
+    if (rc) return rc;
+    kern<<<grid, RT_BLOCK, smem, stream>>>(t->d_surfs, t->d_n, t->n_ifc, t->n_wvl, G, cb, ce, *o, *out,
+                                           scratch);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+/* 0: p,d only; 1: + normal/dst; 2: whole ray */
+static int out_kind(const rt_out *out)
+{
+    if (out->full) return 2;
+    if (out->nx || out->ny || out->nz || out->dst) return 1;
+    return 0;
+}
+
 /* ------------------------------------------------------------------ C ABI */
 extern "C" {
 
@@ -416,6 +618,13 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
     t->d_surfs = nullptr; t->d_n = nullptr;
     t->stage_bytes = (size_t)n_ifc*sizeof(rt_surface_desc) + (size_t)n_ifc*n_wvl*sizeof(double);
     t->stage = t->stage_bytes <= RT_MAX_STAGE_BYTES;
+    t->lean_bytes = (size_t)n_ifc*sizeof(LeanSurf) + (size_t)n_ifc*n_wvl*sizeof(LeanIdx);
+    t->lean = t->lean_bytes <= RT_MAX_STAGE_BYTES;
+    for (int i = 0; i < n_ifc; i++) {
+        const rt_surface_desc &s = surfs[i];
+        if (s.profile > RT_PROFILE_CONIC || s.has_tfrm != 0 || s.n_apertures != 0) t->lean = false;
+    }
+    if (getenv("B200RT_NO_LEAN")) t->lean = false;
     cudaError_t e = cudaMalloc(&t->d_surfs, (size_t)n_ifc*sizeof(rt_surface_desc));
     if (e == cudaSuccess) e = cudaMalloc(&t->d_n, (size_t)n_ifc*n_wvl*sizeof(double));
     if (e == cudaSuccess)
@@ -462,6 +671,13 @@ int rt_trace_bundle(const rt_table *t, int64_t n_rays, const double *px, const d
         return fail(RT_ERR_INVALID, "rt_trace_bundle: full_stride < n_rays");
     DeviceGuard guard(t->device);
     cudaStream_t s = (cudaStream_t)stream;
+    if (t->lean) {
+        switch (out_kind(out)) {
+        case 0: return launch_bundle_lean<0>(t, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o, out, s);
+        case 1: return launch_bundle_lean<1>(t, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o, out, s);
+        default: return launch_bundle_lean<2>(t, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o, out, s);
+        }
+    }
     if (out->full) {
         return t->stage ? launch_bundle<true, true>(t, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o, out, s)
                         : launch_bundle<true, false>(t, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o, out, s);
@@ -522,7 +738,7 @@ int rt_grid_dims(const rt_grid *g, int64_t *n_rays, int64_t *n_chunks, int32_t *
 int64_t rt_grid_scratch_bytes(const rt_grid *g, int64_t chunk_begin, int64_t chunk_end)
 {
     if (!g || chunk_end < chunk_begin) return 0;
-    return (chunk_end - chunk_begin)*RT_SUMMARY_DOUBLES*(int64_t)sizeof(double);
+    return (chunk_end - chunk_begin)*(RT_BLOCK/32)*RT_SUMMARY_DOUBLES*(int64_t)sizeof(double);
 }
 
 int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int64_t chunk_end,
@@ -549,6 +765,15 @@ int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int6
     G.rays_per_tile = g->rays_per_tile; G.chunks_per_tile = g->chunks_per_tile;
     double *scr = (double *)scratch;
     const bool full = out->full != nullptr, summ = summary != nullptr, st = t->stage;
+    if (t->lean) {
+        const int kind = out_kind(out);
+#define RT_LEAN_CASE(K, S)                                                                   \
+        if (kind == K && summ == S)                                                          \
+            rc = launch_grid_lean<K, S>(t, G, chunk_begin, chunk_end, o, out, scr, s);
+        RT_LEAN_CASE(0, false) RT_LEAN_CASE(0, true) RT_LEAN_CASE(1, false)
+        RT_LEAN_CASE(1, true) RT_LEAN_CASE(2, false) RT_LEAN_CASE(2, true)
+#undef RT_LEAN_CASE
+    } else {
 #define RT_GRID_CASE(F, S, T)                                                               \
     if (full == F && summ == S && st == T)                                                  \
         rc = launch_grid<F, S, T>(t, g, G, chunk_begin, chunk_end, o, out, scr, s);
@@ -561,11 +786,11 @@ int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int6
     RT_GRID_CASE(true, false, false)
     RT_GRID_CASE(true, true, false)
 #undef RT_GRID_CASE
+    }
     if (rc) return rc;
     if (summ) {
-        const int64_t n = g->n_tiles*RT_SUMMARY_DOUBLES;
-        k_reduce_summary<<<(unsigned)((n + 127)/128), 128, 0, s>>>(scr, chunk_begin, chunk_end,
-                                                                   g->chunks_per_tile, g->n_tiles, summary);
+        k_reduce_summary<<<(unsigned)g->n_tiles, RT_RED_THREADS, 0, s>>>(scr, chunk_begin, chunk_end,
+                                                                        g->chunks_per_tile, summary);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -601,6 +826,29 @@ int rt_measure_fp64_peak(int32_t device, double *tflops)
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
     *tflops = best;
+    return RT_OK;
+}
+
+/* Self-test of the shared-reciprocal division used by the lean kernels:
+ * n_blocks x 256 threads x n_per_thread random operand sets (3 quotients + one
+ * normalisation each) compared bit-for-bit with the IEEE `/`.  *mismatches
+ * must come back 0. */
+int rt_selftest_division(int32_t device, int32_t n_blocks, int64_t n_per_thread, uint64_t seed,
+                         uint64_t *mismatches)
+{
+    if (!mismatches || n_blocks < 1 || n_per_thread < 1)
+        return fail(RT_ERR_INVALID, "rt_selftest_division: bad arguments");
+    DeviceGuard guard(device);
+    unsigned long long *d_bad;
+    CUDA_TRY(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(d_bad, 0, sizeof(unsigned long long)));
+    k_selftest_division<<<n_blocks, 256>>>(seed, n_per_thread, d_bad);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long bad = 0;
+    CUDA_TRY(cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+    cudaFree(d_bad);
+    *mismatches = bad;
     return RT_OK;
 }
 
