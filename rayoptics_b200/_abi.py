@@ -104,7 +104,9 @@ _lib = None
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', LIB_NAME)
+    # B200RT_LIB: alternative build of the same ABI (kernel tuning experiments)
+    return os.environ.get('B200RT_LIB') or os.path.join(
+        os.path.dirname(os.path.abspath(__file__)), 'csrc', LIB_NAME)
 
 
 class EngineError(RuntimeError):

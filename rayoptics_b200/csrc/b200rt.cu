@@ -30,6 +30,9 @@
 using namespace b200rt;
 
 #define RT_BLOCK 256          /* threads per CTA = rays per chunk */
+#ifndef RT_LEAN_MIN_CTAS
+#define RT_LEAN_MIN_CTAS 3   /* resident CTAs per SM the lean kernels are register-limited for */
+#endif
 #define RT_MAX_STAGE_BYTES (200*1024)
 
 /* ------------------------------------------------------------------ errors */
@@ -281,7 +284,7 @@ k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restri
 
 /* ---- lean kernels: plan built in shared memory by the CTA (rt_lean.cuh) */
 template <int OUT>
-__global__ void __launch_bounds__(RT_BLOCK, 3)
+__global__ void __launch_bounds__(RT_BLOCK, RT_LEAN_MIN_CTAS)
 k_trace_bundle_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
                     int n_ifc, int n_wvl, int64_t n_rays,
                     const double *__restrict__ px, const double *__restrict__ py,
@@ -308,7 +311,7 @@ k_trace_bundle_lean(const rt_surface_desc *__restrict__ g_surfs, const double *_
 }
 
 template <int OUT, bool SUMMARY>
-__global__ void __launch_bounds__(RT_BLOCK, 3)
+__global__ void __launch_bounds__(RT_BLOCK, RT_LEAN_MIN_CTAS)
 k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
                   int n_ifc, int n_wvl, GridDev G, int64_t chunk_begin, int64_t chunk_end,
                   rt_opts o, rt_out out, double *__restrict__ scratch)
@@ -392,6 +395,11 @@ __global__ void k_selftest_division(uint64_t seed, int64_t n_per_thread, unsigne
                 if (!(isnan(n1.x) && isnan(n2.x)) ) bad++;
             }
         }
+    }
+    {   /* sqrt_near_one against sqrt for every bit pattern within 2048 ulps of 1 */
+        long long k = (long long)((blockIdx.x*blockDim.x + threadIdx.x) % 4097) - 2048;
+        double sv = __longlong_as_double(0x3FF0000000000000LL + k);
+        if (__double_as_longlong(sqrt_near_one(sv)) != __double_as_longlong(sqrt(sv))) bad++;
     }
     if (bad) atomicAdd(mismatch, bad);
 }
