@@ -219,7 +219,7 @@ __device__ __forceinline__ void grid_epilogue(const GridDev &G, const rt_out &ou
     if (out.abr_x || SUMMARY) {
         const double rx = G.ref_img ? G.ref_img[tile*2 + 0] : 0.0;
         const double ry = G.ref_img ? G.ref_img[tile*2 + 1] : 0.0;
-        double dist = G.foc/R.d.z;
+        double dist = div_maybe_zero(G.foc, R.d.z);
         double ax = (R.p.x + dist*R.d.x) - rx;
         double ay = (R.p.y + dist*R.d.y) - ry;
         if (out.abr_x) { out.abr_x[k] = ax; out.abr_y[k] = ay; }
