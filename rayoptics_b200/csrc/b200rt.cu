@@ -165,15 +165,53 @@ k_trace_bundle(const rt_surface_desc *__restrict__ g_surfs, const double *__rest
     }
 }
 
-/* Deterministic warp reduction of the 16 summary quantities; lane 0 writes the
- * warp's partial.  No CTA barrier: warps whose rays were clipped early do not
- * wait for the others. */
-__device__ __forceinline__ void warp_reduce_summary(double (&v)[RT_SUMMARY_DOUBLES], double *dst)
+/* ---- per-(field, wvl) spot sums.
+ * Every thread keeps 15 running values in shared memory (acc[k*RT_BLOCK + tid],
+ * conflict-free); when the CTA moves on to another tile (or finishes) each warp
+ * shuffle-reduces its lanes and lane 0 writes one 16-double record (15 values +
+ * a valid flag) to its slot of the tile.  Slots of a tile: RT_WARPS x SL,
+ * SL = min(chunks_per_tile, RT_MAX_GRID); slot = local chunk when
+ * chunks_per_tile <= gridDim.x (then a CTA never meets a tile twice), else
+ * blockIdx.x (a CTA's chunks of one tile are consecutive => one record).  The
+ * scratch buffer is zeroed before the launch, k_reduce_summary adds up the valid
+ * records of a tile in slot order: bit-reproducible for a given launch shape,
+ * and no CTA barrier / per-chunk shuffle traffic in the trace kernel. */
+#define RT_WARPS (RT_BLOCK/32)
+#define RT_MAX_GRID 1024
+#define RT_ACC 15
+#define RT_ACC_BYTES (RT_ACC*RT_BLOCK*sizeof(double))
+
+__device__ __forceinline__ void acc_init(double *acc)
+{
+#pragma unroll
+    for (int k = 0; k < RT_ACC; k++)
+        acc[k*RT_BLOCK + threadIdx.x] =
+            (k == 10 || k == 12) ? CUDART_INF : ((k == 11 || k == 13) ? -CUDART_INF : 0.0);
+}
+
+__device__ __forceinline__ void acc_add(double *acc, int status, double ax, double ay, double op)
+{
+    double *a = acc + threadIdx.x;
+    const int ck = status == RT_RAY_OK ? 0 : (status <= RT_RAY_BLOCKED ? status : 4);
+    a[ck*RT_BLOCK] += 1.0;
+    if (status == RT_RAY_OK) {
+        a[5*RT_BLOCK] += ax; a[6*RT_BLOCK] += ay;
+        a[7*RT_BLOCK] += ax*ax; a[8*RT_BLOCK] += ay*ay; a[9*RT_BLOCK] += ax*ay;
+        a[10*RT_BLOCK] = fmin(a[10*RT_BLOCK], ax); a[11*RT_BLOCK] = fmax(a[11*RT_BLOCK], ax);
+        a[12*RT_BLOCK] = fmin(a[12*RT_BLOCK], ay); a[13*RT_BLOCK] = fmax(a[13*RT_BLOCK], ay);
+        a[14*RT_BLOCK] += op;
+    }
+}
+
+/* warp-reduce the accumulators into the warp's record of (tile, slot) and reset them */
+__device__ __forceinline__ void acc_flush(double *acc, double *scratch, int64_t tile, int64_t slot,
+                                          int64_t slots_per_tile)
 {
     const int lane = threadIdx.x & 31;
+    double *dst = scratch + ((tile*slots_per_tile + slot)*RT_WARPS + (threadIdx.x >> 5))*RT_SUMMARY_DOUBLES;
 #pragma unroll
-    for (int k = 0; k < RT_SUMMARY_DOUBLES - 1; k++) {
-        double x = v[k];
+    for (int k = 0; k < RT_ACC; k++) {
+        double x = acc[k*RT_BLOCK + threadIdx.x];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             double y = __shfl_down_sync(0xffffffffu, x, off);
@@ -183,6 +221,8 @@ __device__ __forceinline__ void warp_reduce_summary(double (&v)[RT_SUMMARY_DOUBL
         }
         if (lane == 0) dst[k] = x;
     }
+    if (lane == 0) dst[RT_ACC] = 1.0;
+    acc_init(acc);
 }
 
 /* start ray of grid ray (tile, loc): Field.apply_vignetting + ray_start_from_osp
@@ -210,39 +250,83 @@ __device__ __forceinline__ void grid_start_ray(const GridDev &G, int f, int64_t 
     if (d0.z*(double)G.flip_z_dir < 0) { d0.x = -d0.x; d0.y = -d0.y; d0.z = -d0.z; }
 }
 
-/* transverse aberration (focus_pupil_coords, analyses.py:561-580) + spot sums */
-template <bool SUMMARY>
-__device__ __forceinline__ void grid_epilogue(const GridDev &G, const rt_out &out, int64_t tile,
-                                              int64_t k, const RayResult &R,
-                                              double (&v)[RT_SUMMARY_DOUBLES])
+/* per-chunk variant (chunk slots): the lanes' contributions are reduced straight
+ * from registers; lanes without a ray contribute the identity */
+__device__ __forceinline__ void warp_record_from_regs(bool have, int status, double ax, double ay,
+                                                      double op, double *scratch, int64_t tile,
+                                                      int64_t slot, int64_t slots_per_tile)
 {
-    if (out.abr_x || SUMMARY) {
-        const double rx = G.ref_img ? G.ref_img[tile*2 + 0] : 0.0;
-        const double ry = G.ref_img ? G.ref_img[tile*2 + 1] : 0.0;
-        double dist = div_maybe_zero(G.foc, R.d.z);
-        double ax = (R.p.x + dist*R.d.x) - rx;
-        double ay = (R.p.y + dist*R.d.y) - ry;
-        if (out.abr_x) { out.abr_x[k] = ax; out.abr_y[k] = ay; }
-        if (SUMMARY) {
-            if (R.status == RT_RAY_OK) {
-                v[0] = 1.0;
-                v[5] = ax; v[6] = ay; v[7] = ax*ax; v[8] = ay*ay; v[9] = ax*ay;
-                v[10] = v[11] = ax; v[12] = v[13] = ay;
-                v[14] = R.op;
-            } else if (R.status == RT_RAY_MISSED) v[1] = 1.0;
-            else if (R.status == RT_RAY_TIR) v[2] = 1.0;
-            else if (R.status == RT_RAY_BLOCKED) v[3] = 1.0;
-            else v[4] = 1.0;
+    const int lane = threadIdx.x & 31;
+    double *dst = scratch + ((tile*slots_per_tile + slot)*RT_WARPS + (threadIdx.x >> 5))*RT_SUMMARY_DOUBLES;
+    const bool ok = have && status == RT_RAY_OK;
+#pragma unroll
+    for (int k = 0; k < RT_ACC; k++) {
+        double x;
+        if (k < 5) {
+            const int ck = status == RT_RAY_OK ? 0 : (status <= RT_RAY_BLOCKED ? status : 4);
+            x = (have && ck == k) ? 1.0 : 0.0;
+        } else if (k == 10 || k == 12) x = ok ? (k == 10 ? ax : ay) : CUDART_INF;
+        else if (k == 11 || k == 13) x = ok ? (k == 11 ? ax : ay) : -CUDART_INF;
+        else if (!ok) x = 0.0;
+        else x = k == 5 ? ax : k == 6 ? ay : k == 7 ? ax*ax : k == 8 ? ay*ay : k == 9 ? ax*ay : op;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double y = __shfl_down_sync(0xffffffffu, x, off);
+            if (k == 10 || k == 12) x = fmin(x, y);
+            else if (k == 11 || k == 13) x = fmax(x, y);
+            else x = x + y;
         }
+        if (lane == 0) dst[k] = x;
     }
+    if (lane == 0) dst[RT_ACC] = 1.0;
 }
 
-__device__ __forceinline__ void summary_init(double (&v)[RT_SUMMARY_DOUBLES])
+/* chunk loop shared by the general and the lean grid kernels: start ray ->
+ * trace -> per-ray results -> transverse aberration (focus_pupil_coords,
+ * analyses.py:561-580) -> spot sums */
+template <bool SUMMARY, typename TraceFn>
+__device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_begin, int64_t chunk_end,
+                                                const rt_out &out, double *scratch, double *acc,
+                                                TraceFn trace)
 {
-#pragma unroll
-    for (int k = 0; k < RT_SUMMARY_DOUBLES; k++) v[k] = 0.0;
-    v[10] = v[12] = CUDART_INF;
-    v[11] = v[13] = -CUDART_INF;
+    const int64_t tile0 = chunk_begin/G.chunks_per_tile;
+    const int64_t ray0 = tile0*G.rays_per_tile + (chunk_begin - tile0*G.chunks_per_tile)*RT_BLOCK;
+    const int64_t sl = G.chunks_per_tile < RT_MAX_GRID ? G.chunks_per_tile : RT_MAX_GRID;
+    const bool chunk_slots = G.chunks_per_tile <= (int64_t)gridDim.x;
+    int64_t cur_tile = -1;
+    if (SUMMARY && !chunk_slots) acc_init(acc);
+    for (int64_t c = chunk_begin + blockIdx.x; c < chunk_end; c += gridDim.x) {
+        const int64_t tile = c/G.chunks_per_tile;
+        const int64_t lc = c - tile*G.chunks_per_tile;
+        const int64_t loc = lc*RT_BLOCK + threadIdx.x;
+        const bool have = loc < G.rays_per_tile;
+        if (SUMMARY && !chunk_slots && tile != cur_tile) {
+            if (cur_tile >= 0) acc_flush(acc, scratch, cur_tile, blockIdx.x, sl);
+            cur_tile = tile;
+        }
+        int status = RT_RAY_OK;
+        double ax = 0.0, ay = 0.0, op = 0.0;
+        if (have) {
+            const int f = (int)(tile/G.n_wvls);
+            const int w = (int)(tile - (int64_t)f*G.n_wvls);
+            const int64_t k = tile*G.rays_per_tile + loc - ray0;
+            RayResult R;
+            trace(f, w, loc, k, R);
+            store_result(out, k, R);
+            status = R.status; op = R.op;
+            if (out.abr_x || SUMMARY) {
+                const double rx = G.ref_img ? G.ref_img[tile*2 + 0] : 0.0;
+                const double ry = G.ref_img ? G.ref_img[tile*2 + 1] : 0.0;
+                double dist = div_maybe_zero(G.foc, R.d.z);
+                ax = (R.p.x + dist*R.d.x) - rx;
+                ay = (R.p.y + dist*R.d.y) - ry;
+                if (out.abr_x) { out.abr_x[k] = ax; out.abr_y[k] = ay; }
+                if (SUMMARY && !chunk_slots) acc_add(acc, status, ax, ay, op);
+            }
+        }
+        if (SUMMARY && chunk_slots) warp_record_from_regs(have, status, ax, ay, op, scratch, tile, lc, sl);
+    }
+    if (SUMMARY && !chunk_slots && cur_tile >= 0) acc_flush(acc, scratch, cur_tile, blockIdx.x, sl);
 }
 
 template <bool FULL, bool SUMMARY, bool STAGE>
@@ -254,32 +338,15 @@ k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restri
     extern __shared__ __align__(16) unsigned char smem[];
     const rt_surface_desc *tab;
     const double *ntab;
-    stage_table<STAGE>(g_surfs, g_n, n_ifc, n_wvl, smem, tab, ntab);
-
-    const int64_t tile0 = chunk_begin/G.chunks_per_tile;
-    const int64_t ray0 = tile0*G.rays_per_tile + (chunk_begin - tile0*G.chunks_per_tile)*RT_BLOCK;
-
-    for (int64_t c = chunk_begin + blockIdx.x; c < chunk_end; c += gridDim.x) {
-        const int64_t tile = c/G.chunks_per_tile;
-        const int64_t loc = (c - tile*G.chunks_per_tile)*RT_BLOCK + threadIdx.x;
-        const int f = (int)(tile/G.n_wvls);
-        const int w = (int)(tile - (int64_t)f*G.n_wvls);
-        double v[RT_SUMMARY_DOUBLES];
-        if (SUMMARY) summary_init(v);
-        if (loc < G.rays_per_tile) {
+    double *acc = reinterpret_cast<double *>(smem);          /* [RT_ACC][RT_BLOCK] when SUMMARY */
+    stage_table<STAGE>(g_surfs, g_n, n_ifc, n_wvl, smem + (SUMMARY ? RT_ACC_BYTES : 0), tab, ntab);
+    grid_chunk_loop<SUMMARY>(G, chunk_begin, chunk_end, out, scratch, acc,
+        [&](int f, int w, int64_t loc, int64_t k, RayResult &R) {
             Vec3 p0, d0;
             grid_start_ray<false>(G, f, loc, p0, d0);
-            const int64_t k = tile*G.rays_per_tile + loc - ray0;
             FullWriter fw = {FULL ? out.full + k : nullptr, out.full_stride};
-            RayResult R;
             trace_ray<FULL>(tab, ntab + (int64_t)G.wvl_idx[w]*n_ifc, n_ifc, o, p0, d0, fw, R);
-            store_result(out, k, R);
-            grid_epilogue<SUMMARY>(G, out, tile, k, R, v);
-        }
-        if (SUMMARY)
-            warp_reduce_summary(v, scratch + ((c - chunk_begin)*(RT_BLOCK/32) + (threadIdx.x >> 5))
-                                              *RT_SUMMARY_DOUBLES);
-    }
+        });
 }
 
 /* ---- lean kernels: plan built in shared memory by the CTA (rt_lean.cuh) */
@@ -317,35 +384,18 @@ k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__r
                   rt_opts o, rt_out out, double *__restrict__ scratch)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    LeanSurf *ls = reinterpret_cast<LeanSurf *>(smem);
+    double *acc = reinterpret_cast<double *>(smem);          /* [RT_ACC][RT_BLOCK] when SUMMARY */
+    LeanSurf *ls = reinterpret_cast<LeanSurf *>(smem + (SUMMARY ? RT_ACC_BYTES : 0));
     LeanIdx *li = reinterpret_cast<LeanIdx *>(ls + n_ifc);
     build_plan(g_surfs, g_n, n_ifc, n_wvl, o, ls, li);
     __syncthreads();
-
-    const int64_t tile0 = chunk_begin/G.chunks_per_tile;
-    const int64_t ray0 = tile0*G.rays_per_tile + (chunk_begin - tile0*G.chunks_per_tile)*RT_BLOCK;
-
-    for (int64_t c = chunk_begin + blockIdx.x; c < chunk_end; c += gridDim.x) {
-        const int64_t tile = c/G.chunks_per_tile;
-        const int64_t loc = (c - tile*G.chunks_per_tile)*RT_BLOCK + threadIdx.x;
-        const int f = (int)(tile/G.n_wvls);
-        const int w = (int)(tile - (int64_t)f*G.n_wvls);
-        double v[RT_SUMMARY_DOUBLES];
-        if (SUMMARY) summary_init(v);
-        if (loc < G.rays_per_tile) {
+    grid_chunk_loop<SUMMARY>(G, chunk_begin, chunk_end, out, scratch, acc,
+        [&](int f, int w, int64_t loc, int64_t k, RayResult &R) {
             Vec3 p0, d0;
             grid_start_ray<true>(G, f, loc, p0, d0);
-            const int64_t k = tile*G.rays_per_tile + loc - ray0;
             FullWriter fw = {OUT == 2 ? out.full + k : nullptr, out.full_stride};
-            RayResult R;
             trace_ray_lean<OUT>(ls, li + (int64_t)G.wvl_idx[w]*n_ifc, n_ifc, o, p0, d0, fw, R);
-            store_result(out, k, R);
-            grid_epilogue<SUMMARY>(G, out, tile, k, R, v);
-        }
-        if (SUMMARY)
-            warp_reduce_summary(v, scratch + ((c - chunk_begin)*(RT_BLOCK/32) + (threadIdx.x >> 5))
-                                              *RT_SUMMARY_DOUBLES);
-    }
+        });
 }
 
 /* division self-test: div_shared/normalize3_shared against the IEEE `/` */
@@ -404,55 +454,69 @@ __global__ void k_selftest_division(uint64_t seed, int64_t n_per_thread, unsigne
     if (bad) atomicAdd(mismatch, bad);
 }
 
-/* One CTA per tile: fixed-order reduction of this call's per-warp partials.
- * Thread t accumulates partials t, t+256, ... (ascending), then the 256 thread
- * sums are combined by a fixed binary tree in shared memory -> bit-reproducible
- * for a given chunk range. */
+/* Fixed-order reduction of the valid records of each tile.  RT_RED_SPLIT CTAs per
+ * tile each add up a contiguous range of records (thread t takes records t,
+ * t+256, ... ascending, then a fixed binary tree over the 256 thread sums); the
+ * CTA that finishes last (ticket) combines the RT_RED_SPLIT partials in order. */
 #define RT_RED_THREADS 256
+#define RT_RED_SPLIT 16
+__device__ __forceinline__ double red_op(int k, double a, double y)
+{
+    if (k == 10 || k == 12) return fmin(a, y);
+    if (k == 11 || k == 13) return fmax(a, y);
+    return a + y;
+}
+
 __global__ void __launch_bounds__(RT_RED_THREADS)
-k_reduce_summary(const double *__restrict__ scratch, int64_t chunk_begin, int64_t chunk_end,
-                 int64_t chunks_per_tile, double *__restrict__ summary)
+k_reduce_summary(const double *__restrict__ scratch, int64_t recs_per_tile, double *partials,
+                 unsigned int *tickets, double *__restrict__ summary)
 {
     __shared__ double sh[RT_RED_THREADS][RT_SUMMARY_DOUBLES + 1];
-    const int64_t tile = blockIdx.x;
-    int64_t c0 = tile*chunks_per_tile, c1 = c0 + chunks_per_tile;
-    if (c0 < chunk_begin) c0 = chunk_begin;
-    if (c1 > chunk_end) c1 = chunk_end;
-    const int64_t w0 = (c0 - chunk_begin)*(RT_BLOCK/32), w1 = (c1 - chunk_begin)*(RT_BLOCK/32);
-    double x[RT_SUMMARY_DOUBLES];
+    __shared__ bool last;
+    const int64_t tile = blockIdx.x/RT_RED_SPLIT;
+    const int part = blockIdx.x%RT_RED_SPLIT;
+    const int64_t per = (recs_per_tile + RT_RED_SPLIT - 1)/RT_RED_SPLIT;
+    int64_t r0 = part*per, r1 = r0 + per;
+    if (r1 > recs_per_tile) r1 = recs_per_tile;
+    double x[RT_ACC];
 #pragma unroll
-    for (int k = 0; k < RT_SUMMARY_DOUBLES; k++) x[k] = 0.0;
-    x[10] = x[12] = CUDART_INF;
-    x[11] = x[13] = -CUDART_INF;
-    for (int64_t w = w0 + threadIdx.x; w < w1; w += RT_RED_THREADS) {
-        const double *p = scratch + w*RT_SUMMARY_DOUBLES;
+    for (int k = 0; k < RT_ACC; k++)
+        x[k] = (k == 10 || k == 12) ? CUDART_INF : ((k == 11 || k == 13) ? -CUDART_INF : 0.0);
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += RT_RED_THREADS) {
+        const double *p = scratch + (tile*recs_per_tile + r)*RT_SUMMARY_DOUBLES;
+        if (p[RT_ACC] != 0.0) {
 #pragma unroll
-        for (int k = 0; k < RT_SUMMARY_DOUBLES - 1; k++) {
-            double y = p[k];
-            if (k == 10 || k == 12) x[k] = fmin(x[k], y);
-            else if (k == 11 || k == 13) x[k] = fmax(x[k], y);
-            else x[k] = x[k] + y;
+            for (int k = 0; k < RT_ACC; k++) x[k] = red_op(k, x[k], p[k]);
         }
     }
 #pragma unroll
-    for (int k = 0; k < RT_SUMMARY_DOUBLES; k++) sh[threadIdx.x][k] = x[k];
+    for (int k = 0; k < RT_ACC; k++) sh[threadIdx.x][k] = x[k];
     __syncthreads();
     for (int off = RT_RED_THREADS/2; off > 0; off >>= 1) {
         if (threadIdx.x < off) {
 #pragma unroll
-            for (int k = 0; k < RT_SUMMARY_DOUBLES - 1; k++) {
-                double a = sh[threadIdx.x][k], y = sh[threadIdx.x + off][k];
-                if (k == 10 || k == 12) a = fmin(a, y);
-                else if (k == 11 || k == 13) a = fmax(a, y);
-                else a = a + y;
-                sh[threadIdx.x][k] = a;
-            }
+            for (int k = 0; k < RT_ACC; k++)
+                sh[threadIdx.x][k] = red_op(k, sh[threadIdx.x][k], sh[threadIdx.x + off][k]);
         }
         __syncthreads();
     }
-    if (threadIdx.x < RT_SUMMARY_DOUBLES)
-        summary[tile*RT_SUMMARY_DOUBLES + threadIdx.x] =
-            (threadIdx.x == RT_SUMMARY_DOUBLES - 1) ? 0.0 : sh[0][threadIdx.x];
+    double *mine = partials + ((int64_t)blockIdx.x)*RT_SUMMARY_DOUBLES;
+    if (threadIdx.x < RT_ACC) mine[threadIdx.x] = sh[0][threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&tickets[tile], 1u) == RT_RED_SPLIT - 1);
+    __syncthreads();
+    if (last && threadIdx.x < RT_SUMMARY_DOUBLES) {
+        __threadfence();
+        const int k = threadIdx.x;
+        double v = 0.0;
+        if (k < RT_ACC) {
+            const volatile double *pp = partials + tile*RT_RED_SPLIT*RT_SUMMARY_DOUBLES;
+            v = pp[k];
+            for (int j = 1; j < RT_RED_SPLIT; j++) v = red_op(k, v, pp[j*RT_SUMMARY_DOUBLES + k]);
+        }
+        summary[tile*RT_SUMMARY_DOUBLES + k] = v;
+    }
 }
 
 /* fp64 FMA microbenchmark: 8 independent chains per thread */
@@ -479,6 +543,7 @@ static int persistent_grid(K kernel, size_t smem, int sm_count, int64_t work_ite
     if (per_sm < 1) per_sm = 1;
     int64_t g = (int64_t)sm_count*per_sm;
     if (g > work_items) g = work_items;
+    if (g > RT_MAX_GRID) g = RT_MAX_GRID;
     if (g < 1) g = 1;
     *grid = (int)g;
     return RT_OK;
@@ -535,7 +600,7 @@ static int launch_grid(const rt_table *t, const rt_grid *g, const GridDev &G, in
                        const rt_opts *o, const rt_out *out, double *scratch, cudaStream_t stream)
 {
     auto kern = k_trace_grid<FULL, SUMMARY, STAGE>;
-    const size_t smem = STAGE ? t->stage_bytes : 0;
+    const size_t smem = (STAGE ? t->stage_bytes : 0) + (SUMMARY ? RT_ACC_BYTES : 0);
     int rc = prep_kernel(kern, smem);
     if (rc) return rc;
     int grid;
@@ -573,7 +638,7 @@ static int launch_grid_lean(const rt_table *t, const GridDev &G, int64_t cb, int
                             const rt_opts *o, const rt_out *out, double *scratch, cudaStream_t stream)
 {
     auto kern = k_trace_grid_lean<OUT, SUMMARY>;
-    const size_t smem = t->lean_bytes;
+    const size_t smem = t->lean_bytes + (SUMMARY ? RT_ACC_BYTES : 0);
     int rc = prep_kernel(kern, smem);
     if (rc) return rc;
     int grid;
@@ -625,9 +690,9 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
     t->sm_count = prop.multiProcessorCount;
     t->d_surfs = nullptr; t->d_n = nullptr;
     t->stage_bytes = (size_t)n_ifc*sizeof(rt_surface_desc) + (size_t)n_ifc*n_wvl*sizeof(double);
-    t->stage = t->stage_bytes <= RT_MAX_STAGE_BYTES;
+    t->stage = t->stage_bytes <= RT_MAX_STAGE_BYTES - RT_ACC_BYTES;
     t->lean_bytes = (size_t)n_ifc*sizeof(LeanSurf) + (size_t)n_ifc*n_wvl*sizeof(LeanIdx);
-    t->lean = t->lean_bytes <= RT_MAX_STAGE_BYTES;
+    t->lean = t->lean_bytes <= RT_MAX_STAGE_BYTES - RT_ACC_BYTES;
     for (int i = 0; i < n_ifc; i++) {
         const rt_surface_desc &s = surfs[i];
         if (s.profile > RT_PROFILE_CONIC || s.has_tfrm != 0 || s.n_apertures != 0) t->lean = false;
@@ -743,10 +808,19 @@ int rt_grid_dims(const rt_grid *g, int64_t *n_rays, int64_t *n_chunks, int32_t *
     return RT_OK;
 }
 
+/* records (16 doubles each): n_tiles x min(chunks_per_tile, RT_MAX_GRID) x RT_WARPS, then
+ * the reduce kernel's partials (n_tiles x RT_RED_SPLIT records) and tickets */
+static int64_t scratch_records(const rt_grid *g)
+{
+    const int64_t sl = g->chunks_per_tile < RT_MAX_GRID ? g->chunks_per_tile : RT_MAX_GRID;
+    return g->n_tiles*sl*RT_WARPS;
+}
+
 int64_t rt_grid_scratch_bytes(const rt_grid *g, int64_t chunk_begin, int64_t chunk_end)
 {
     if (!g || chunk_end < chunk_begin) return 0;
-    return (chunk_end - chunk_begin)*(RT_BLOCK/32)*RT_SUMMARY_DOUBLES*(int64_t)sizeof(double);
+    return (scratch_records(g) + g->n_tiles*RT_RED_SPLIT)*RT_SUMMARY_DOUBLES*(int64_t)sizeof(double) +
+           g->n_tiles*(int64_t)sizeof(double);
 }
 
 int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int64_t chunk_end,
@@ -772,6 +846,8 @@ int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int6
     G.pupil_x = g->d_pupil_x; G.pupil_y = g->d_pupil_y; G.ref_img = g->d_ref_img;
     G.rays_per_tile = g->rays_per_tile; G.chunks_per_tile = g->chunks_per_tile;
     double *scr = (double *)scratch;
+    if (summary)
+        CUDA_TRY(cudaMemsetAsync(scr, 0, (size_t)rt_grid_scratch_bytes(g, chunk_begin, chunk_end), s));
     const bool full = out->full != nullptr, summ = summary != nullptr, st = t->stage;
     if (t->lean) {
         const int kind = out_kind(out);
@@ -797,8 +873,11 @@ int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int6
     }
     if (rc) return rc;
     if (summ) {
-        k_reduce_summary<<<(unsigned)g->n_tiles, RT_RED_THREADS, 0, s>>>(scr, chunk_begin, chunk_end,
-                                                                        g->chunks_per_tile, summary);
+        const int64_t recs = scratch_records(g);
+        double *partials = scr + recs*RT_SUMMARY_DOUBLES;
+        unsigned int *tickets = (unsigned int *)(partials + g->n_tiles*RT_RED_SPLIT*RT_SUMMARY_DOUBLES);
+        k_reduce_summary<<<(unsigned)(g->n_tiles*RT_RED_SPLIT), RT_RED_THREADS, 0, s>>>(
+            scr, recs/g->n_tiles, partials, tickets, summary);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
     }

@@ -1,0 +1,169 @@
+"""Drop-in ``trace()`` / ``trace_raw()`` on the B200 engine.
+
+Same signatures, return values and exceptions as
+/root/reference/src/rayoptics/raytr/raytrace.py:51-264:
+
+    trace(seq_model, pt0, dir0, wvl, **kwargs)        -> (ray, op_delta, wvl)
+    trace_raw(path, pt0, dir0, wvl, eps=1e-12, check_apertures=False,
+              intersect_obj=True, filter_out_phantoms=False, **kwargs)
+
+``ray`` is a list with one ``[p, d, dst, nrml]`` entry per interface (numpy
+3-vectors + float), indexed by the reference's ``mc.p/d/dst/nrml``.  Per-ray
+failures come back from the kernel as data (status, failing surface) and are
+re-raised here as the reference's ``TraceError`` subclasses with ``.surf``,
+``.ifc``, ``.ray_pkg`` (partial ray), ``.int_pt`` / ``.prev_tfrm`` filled the
+way raytrace.py:231-257 fills them.
+
+``install()`` rebinds ``rayoptics.raytr.raytrace.trace`` / ``trace_raw`` so that
+every caller in the reference (``trace_base``, ``iterate_ray``, ``vigcalc``,
+``wideangle`` ... they all call ``rt.trace`` through the module attribute) runs
+on the GPU without touching reference sources.
+
+A single ray costs a kernel launch and a device->host copy (~0.1 ms): this entry
+point exists for compatibility; throughput comes from ``engine.trace_bundle`` /
+``engine.trace_grid`` / ``analyses``.  There is no CPU fallback: models with
+interfaces the table cannot represent raise ``UnsupportedInterfaceError``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _abi, engine as E
+from .table import SurfaceTable, describe_path
+
+try:                                    # the reference's own exception classes, when importable
+    from rayoptics.raytr.traceerror import (TraceError, TraceMissedSurfaceError,   # type: ignore
+                                            TraceTIRError, TraceRayBlockedError,
+                                            TraceEvanescentRayError)
+except Exception:                       # noqa: BLE001 - any import problem -> local mirrors
+    from .traceerror import (TraceError, TraceMissedSurfaceError, TraceTIRError,
+                             TraceRayBlockedError, TraceEvanescentRayError)
+
+
+class TraceNumericError(TraceError):
+    """The reference would have died with an uncaught ValueError/ZeroDivisionError
+    inside a polynomial profile (status RT_RAY_NUMERIC)."""
+
+    def __init__(self, ifc=None, prev_seg=None):
+        self.ifc = ifc
+        self.prev_seg = prev_seg
+
+
+_DEVICE = 0
+_PATH_CACHE = {}          # fingerprint -> SurfaceTable
+
+
+def set_device(device):
+    global _DEVICE
+    _DEVICE = int(device)
+
+
+def _fingerprint(segs):
+    fp = []
+    for seg in segs:
+        ifc, _gap, tfrm, n, z_dir = (tuple(seg) + (None,)*5)[:5]
+        prf = getattr(ifc, 'profile', None)
+        coefs = getattr(prf, 'coefs', None)
+        fp.append((id(ifc), type(prf).__name__, getattr(prf, 'cv', None), getattr(prf, 'cc', None),
+                   getattr(prf, 'cR', None), None if coefs is None else tuple(coefs),
+                   getattr(ifc, 'interact_mode', None), getattr(ifc, 'max_aperture', None),
+                   len(getattr(ifc, 'clear_apertures', ()) or ()), n, z_dir,
+                   None if tfrm is None else (tfrm[0].tobytes() if hasattr(tfrm[0], 'tobytes')
+                                              else repr(tfrm[0]), tuple(map(float, tfrm[1])))))
+    return tuple(fp)
+
+
+def _table_for_path(segs):
+    """Surface table of a path, cached on its content (the reference clears its
+    own path cache in update_model; here any change of the numbers the table is
+    built from changes the fingerprint)."""
+    fp = _fingerprint(segs)
+    tab = _PATH_CACHE.get(fp)
+    if tab is None:
+        if len(_PATH_CACHE) > 64:
+            _PATH_CACHE.clear()
+        tab = SurfaceTable.from_path(segs, device=_DEVICE)
+        _PATH_CACHE[fp] = tab
+    return tab
+
+
+def _ray_list(full, n_seg):
+    ray = []
+    for k in range(n_seg):
+        s = full[k]
+        ray.append([s[0:3].copy(), s[3:6].copy(), float(s[6]), s[7:10].copy()])
+    return ray
+
+
+def trace_raw(path, pt0, dir0, wvl, eps=1.0e-12, check_apertures=False,
+              intersect_obj=True, filter_out_phantoms=False, **kwargs):
+    """fundamental raytrace function (raytrace.py:83-264) -- one ray on the GPU."""
+    segs = list(path)
+    tab = _table_for_path(segs)
+    first_surf = kwargs.get('first_surf', 0)
+    last_surf = kwargs.get('last_surf', None)
+    pt_inside_fuzz = kwargs.get('pt_inside_fuzz', None)
+    p = np.asarray(pt0, dtype=np.float64).reshape(3, 1)
+    d = np.asarray(dir0, dtype=np.float64).reshape(3, 1)
+    res = E.trace_bundle(tab, p, d, full=True, outputs=('op', 'status', 'fail_surf', 'n_seg'),
+                         eps=eps, check_apertures=check_apertures, intersect_obj=intersect_obj,
+                         filter_out_phantoms=filter_out_phantoms, first_surf=first_surf,
+                         last_surf=last_surf, pt_inside_fuzz=pt_inside_fuzz)
+    full = res.full[:, :, 0].cpu().numpy()
+    meta = torch.stack([res.status, res.fail_surf, res.n_seg]).cpu().numpy()[:, 0]
+    op = float(res.op.cpu().numpy()[0])
+    status, surf, n_seg = int(meta[0]), int(meta[1]), int(meta[2])
+    ray = _ray_list(full, n_seg)
+    if status == _abi.RAY_OK:
+        return ray, op, wvl
+    ifc = segs[surf][0] if 0 <= surf < len(segs) else None
+    if status == _abi.RAY_MISSED:
+        err = TraceMissedSurfaceError(ifc, None)
+        err.prev_tfrm = segs[surf - 1][2] if surf >= 1 else None
+    elif status == _abi.RAY_TIR:
+        n_in = segs[surf - 1][3]
+        n_out = segs[surf][3]
+        err = TraceTIRError(ray[-2][1] if len(ray) > 1 else None, ray[-1][3], n_in, n_out)
+        err.ifc = ifc
+        err.int_pt = ray[-1][0]
+    elif status == _abi.RAY_BLOCKED:
+        err = TraceRayBlockedError(ifc, ray[-1][0])
+    elif status == _abi.RAY_EVANESCENT:
+        err = TraceEvanescentRayError(ifc, ray[-1][0], None, None, None, None)
+    else:
+        err = TraceNumericError(ifc, None)
+    err.surf = surf
+    if surf == 0 and status in (_abi.RAY_MISSED, _abi.RAY_NUMERIC):
+        # the reference intersects the object outside its try block
+        # (raytrace.py:147-151): the error propagates without a ray package
+        err.ray_pkg = None
+    else:
+        err.ray_pkg = ray, op, wvl
+    raise err
+
+
+def trace(seq_model, pt0, dir0, wvl, **kwargs):
+    """fundamental raytrace function (raytrace.py:51-80)."""
+    path = seq_model.path(wvl)
+    kwargs['first_surf'] = kwargs.get('first_surf', 1)
+    kwargs['last_surf'] = kwargs.get('last_surf', seq_model.get_num_surfaces() - 2)
+    return trace_raw(path, pt0, dir0, wvl, **kwargs)
+
+
+_saved = {}
+
+
+def install():
+    """Rebind the reference's ``rayoptics.raytr.raytrace.trace/trace_raw``."""
+    import rayoptics.raytr.raytrace as rt      # type: ignore
+    if 'trace' not in _saved:
+        _saved['trace'], _saved['trace_raw'] = rt.trace, rt.trace_raw
+    rt.trace, rt.trace_raw = trace, trace_raw
+    return rt
+
+
+def uninstall():
+    if _saved:
+        import rayoptics.raytr.raytrace as rt  # type: ignore
+        rt.trace, rt.trace_raw = _saved.pop('trace'), _saved.pop('trace_raw')

@@ -246,3 +246,41 @@ def test_general_and_specialised_kernels_agree(name, monkeypatch):
     torch.cuda.synchronize()
     for k in ('p', 'd', 'nrml', 'dst', 'op', 'status', 'fail_surf', 'n_seg', 'abr', 'full', 'summary'):
         assert same(np_(getattr(a, k)), np_(getattr(b, k))), k
+
+
+def test_dropin_trace_matches_reference_vectors(tables):
+    """rayoptics_b200.raytrace.trace()/trace_raw(): the reference's call surface
+    (raytrace.py:51-264) -- ray lists and TraceError subclasses -- reproduce the
+    reference's own outputs on the golden rays, one call per ray."""
+    from rayoptics_b200 import raytrace as rt
+    ERR = {1: rt.TraceMissedSurfaceError, 2: rt.TraceTIRError, 3: rt.TraceRayBlockedError}
+    for name in ('dblgauss', 'rc', 'cellphone'):
+        opm = load_model(name)
+        sm = opm.seq_model
+        v = load_vectors(name)
+        n_full = v['full'].shape[2]
+        seen = set()
+        for k in list(range(0, n_full, 3)) + list(range(n_full, v['p0'].shape[1], 11)):
+            case = dict(v['cases'][v['case'][k]])
+            wvl = sm.wvlns[v['wvl_idx'][k]]
+            st = int(v['status'][k])
+            seen.add(st)
+            try:
+                if case['first_surf'] == 1 and case['last_surf'] == sm.get_num_surfaces() - 2 \
+                        and len(case) == 3:
+                    ray, op, w = rt.trace(sm, v['p0'][:, k], v['d0'][:, k], wvl,
+                                          check_apertures=case['check_apertures'])
+                else:
+                    ray, op, w = rt.trace_raw(sm.path(wvl), v['p0'][:, k], v['d0'][:, k], wvl, **case)
+                assert st == 0
+            except rt.TraceError as e:
+                assert isinstance(e, ERR[st]) and e.surf == v['fail_surf'][k]
+                ray, op, w = e.ray_pkg
+            assert w == wvl and op == v['op'][k] and len(ray) == v['n_seg'][k]
+            if len(ray):
+                last = np.concatenate([ray[-1][0], ray[-1][1], [ray[-1][2]], ray[-1][3]])
+                assert same(last, v['last'][:, k])
+            if k < n_full:
+                got = np.array([np.concatenate([s[0], s[1], [s[2]], s[3]]) for s in ray])
+                assert same(got, v['full'][:len(ray), :, k])
+        assert {0, 3} <= seen
