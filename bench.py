@@ -2,21 +2,23 @@
 """bench.py -- rays/sec (fp64) through a sequential model on B200(s).
 
 Metric (BASELINE.json): rays/sec in fp64 through an N-surface sequential model.
-Workload at N=1: BASELINE configs[1] -- double Gauss (13 interfaces), 3 fields x
-3 wavelengths x 512 x 512 pupil grid = 2,359,296 rays per step, apertures
-checked, start rays generated on the device, per-ray last-segment records
-(p, d, op, status, fail_surf: 64 B) + transverse aberration (16 B) written to
-HBM, per-(field, wvl) spot sums reduced.  Multi-GPU: the chunk space of the same
-grid is weak-scaled (every rank traces the full 2.36 M-ray grid of its own
-replica ... no: see `scaling` below) -- ranks shard nothing but summaries.
+Workload: BASELINE configs[1] -- double Gauss (13 interfaces), 3 fields x 3
+wavelengths x 512 x 512 pupil grid = 2,359,296 rays per step, apertures checked,
+start rays generated on the device, per-ray last-segment records (p, d, op,
+status, fail_surf: 64 B) + transverse aberration (16 B) written to HBM,
+per-(field, wvl) spot sums reduced.  A step = one pass over that grid.
+
+Multi-GPU (`--gpus N` under torchrun): weak scaling -- every rank traces a full
+replica of the grid on its own GPU (per-GPU work fixed); the only collective is
+the all-gather of the [n_tiles, 16] spot sums.  value = N x rays / max-rank time.
 
   python bench.py --gpus N --steps K --warmup W            (this repo's engine)
   python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the oracle
         port of the reference's trace_raw on all host threads; the reference is
-        pure Python and cannot travel to the GPU box -- DESIGN.md)
+        pure Python and cannot travel to the GPU box -- DESIGN.md "reference arm")
 
-One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for how every
-field is obtained.
+One JSON line on stdout (rank 0).  DESIGN.md "Measurement" says how every field
+is obtained.
 """
 import argparse
 import json
@@ -283,10 +285,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    n_warm, t_w = 0, time.perf_counter()
+    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_w < 0.7:
+        step()                          # >= W warm-up steps, and long enough for the
+        n_warm += 1                     # clocks to ramp and nvidia-smi to sample under load
+        if n_warm % 16 == 0:
+            torch.cuda.synchronize()
+    barrier()
     launches0 = E.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
@@ -310,7 +316,6 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
-    clocks = sampler.stop() if sampler else None
 
     # ---- end to end through the public API, host buffers both sides
     e2e = None
@@ -336,6 +341,7 @@ def run_b200(args):
                'api': 'rayoptics_b200.analyses.spot_diagram(opt_model, 512): grid spec from host, '
                       'aberrations + status into pinned host memory'}
 
+    clocks = sampler.stop() if sampler else None   # window: warm-up + timed steps + e2e steps
     if rank == 0:
         status = res.status.cpu().numpy()
         fail_surf = res.fail_surf.cpu().numpy()
@@ -363,7 +369,7 @@ def run_b200(args):
                          'algorithmic_flop_per_full_ray': flops_full_ray,
                          'algorithmic_flop_per_step': flops}}
         line = {'metric': METRIC, 'value': world*n_rays*args.steps/(dev_ms_max*1e-3), 'unit': UNIT,
-                'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+                'n_gpus': world, 'steps': args.steps, 'warmup': n_warm,
                 'ms_per_step': dev_ms_max/args.steps, 'wall_ms_per_step': wall_ms_max/args.steps,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic', 'config': config_dict(args, opm, grid, world),

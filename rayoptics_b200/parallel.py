@@ -34,9 +34,11 @@ def gather_summaries(partial, group=None):
         return partial.clone()
     world = dist.get_world_size(group)
     partial = partial.contiguous()
-    out = torch.empty((world,) + tuple(partial.shape), dtype=partial.dtype, device=partial.device)
+    # concatenated layout [world*n_tiles, 16]: accepted by both NCCL and gloo
+    out = torch.empty((world*partial.shape[0],) + tuple(partial.shape[1:]), dtype=partial.dtype,
+                      device=partial.device)
     dist.all_gather_into_tensor(out, partial, group=group)
-    return combine_summaries(out)
+    return combine_summaries(out.view((world,) + tuple(partial.shape)))
 
 
 def trace_grid_sharded(table, grid, group=None, **kwargs):
