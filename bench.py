@@ -300,12 +300,19 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     e_first.record()
+    pending = None
     for k in range(args.steps):
         ev[k][0].record()
         E.trace_grid(tab, grid, res=res)          # dominant kernel, bracketed for the roofline
         ev[k][1].record()
         if world > 1:
-            res.summary = P.gather_summaries(res.summary)
+            # the all-gather of step k overlaps the trace of step k+1 (NCCL stream);
+            # every step's combined summary is materialised before the region ends
+            if pending is not None:
+                combined = pending.result()
+            pending = P.gather_summaries(res.summary, async_op=True)
+    if pending is not None:
+        combined = pending.result()
     e_last.record()
     barrier()
     wall = time.perf_counter() - t0

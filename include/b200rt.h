@@ -40,6 +40,7 @@ extern "C" {
 #define RT_MAX_APERTURES 4  /* Surface.clear_apertures entries honoured per interface */
 #define RT_SEG_DOUBLES 10   /* one ray segment = p[3], d[3], dst, nrml[3]  (raytr/__init__.py:36) */
 #define RT_SUMMARY_DOUBLES 16
+#define RT_WAVE_DOUBLES 24   /* per-(field, wvl) chief-ray / reference-sphere record, see rt_grid_spec.wave */
 
 /* error codes (function return values) */
 enum rt_error {
@@ -152,6 +153,10 @@ typedef struct rt_out {
     /* transverse ray aberration at the image (grid traces only):
      * p + (foc/d_z) d - ref_img, analyses.py:561-580 */
     double *abr_x, *abr_y;
+    /* optical path difference w.r.t. the chief ray on the reference sphere (grid traces
+     * with rt_grid_spec.wave): wave_abr_full_calc_finite_pup, raytr/waveabr.py:255-305.
+     * System units (mm); NaN for rays that do not reach the image. */
+    double *opd;
 } rt_out;
 
 typedef struct rt_table rt_table;
@@ -198,8 +203,18 @@ typedef struct rt_grid_spec {
     const double *pupil_x;     /* HOST [n_fields][nx] relative pupil x before vignetting */
     const double *pupil_y;     /* HOST [n_fields][ny] */
     const double *ref_img;     /* HOST [n_fields][n_wvls][2] reference image point (ref_sphere[0]) or NULL (=0) */
+    const double *wave;        /* HOST [n_fields][n_wvls][RT_WAVE_DOUBLES] or NULL.  Chief ray and reference
+                                  sphere of each tile, what wave_abr_full_calc_finite_pup reads
+                                  (raytr/waveabr.py:255-305, 24-76, 79-113):
+                                  0-2 cr.ray[1].p   3-5 cr.ray[0].d   6-8 cr.ray[-2].p  9-11 cr.ray[-2].d
+                                  12 cr_op  13-15 cr_exp_pt  16 cr_exp_dist  17-19 ref_dir
+                                  20 ref_sphere_radius  21 sign_soln (+1/-1)  22 |n_obj|  23 |n_img| */
     int32_t apply_vignetting;  /* trace_base(apply_vignetting=...) trace.py:289-292 */
     int32_t flip_z_dir;        /* seq_model.z_dir[0]: dir0 is negated when dir0.z*z_dir < 0 (trace.py:305-308) */
+    int32_t paired;            /* 0: product grid pupil_x[i] x pupil_y[j]; 1: ray list -- ny must be 1 and
+                                  pupil_y is [n_fields][nx]: ray i uses (pupil_x[i], pupil_y[i])
+                                  (trace_ray_list / trace_ray_fan, analyses.py:212-230,437-455) */
+    int32_t reserved;
     double eprad;              /* pupil_value/2 (opticalspec.py:340) */
     double z_pupil;            /* fod.obj_dist + z_enp: z of the aim plane (opticalspec.py:360) */
     double foc;                /* focus shift used for abr_x/abr_y (analyses.py:572) */

@@ -619,7 +619,8 @@ int rto_grid_start_rays(const rt_grid_spec *g, int64_t ray_begin, int64_t ray_en
         int f = (int)(tile/g->n_wvls), w = (int)(tile - (int64_t)f*g->n_wvls);
         int i = (int)(loc/g->ny), j = (int)(loc - (int64_t)i*g->ny);
         const rt_field_desc *F = &g->fields[f];
-        double pup[2] = {g->pupil_x[(size_t)f*g->nx + i], g->pupil_y[(size_t)f*g->ny + j]};
+        double pup[2] = {g->pupil_x[(size_t)f*g->nx + i],
+                         g->paired ? g->pupil_y[(size_t)f*g->nx + i] : g->pupil_y[(size_t)f*g->ny + j]};
         if (g->apply_vignetting) {
             if (pup[0] < 0.0) { if (F->vlx != 0.0) pup[0] *= (1.0 - F->vlx); }
             else              { if (F->vux != 0.0) pup[0] *= (1.0 - F->vux); }
@@ -654,6 +655,38 @@ int rto_transverse_abr(int64_t n, const double *px, const double *py,
     return 0;
 }
 
+/* ---- wave_abr_full_calc_finite_pup (raytr/waveabr.py:255-305) for an interface
+ * k = -2 without decenter; eic_distance (waveabr.py:117-132).  W: the tile's
+ * RT_WAVE_DOUBLES record (layout in include/b200rt.h).  `F**2` on a numpy float64
+ * scalar is libm pow(F, 2.0) -- kept as pow() here so that this restatement is
+ * bit-identical to the reference on the build box (tests/golden/vectors/<model>_opd.npz). */
+static double eic_distance(const double p[3], const double d[3], const double p0[3], const double d0[3])
+{
+    double a[3] = {d[0] + d0[0], d[1] + d0[1], d[2] + d0[2]};
+    double b[3] = {p[0] - p0[0], p[1] - p0[1], p[2] - p0[2]};
+    return dot3(a, b)/(1. + dot3(d, d0));
+}
+
+double rto_wave_opd(const double *W, const double p1[3], const double d0[3],
+                    const double pk[3], const double dk[3], double ray_op)
+{
+    const double *cr_p1 = W, *cr_d0 = W + 3, *cr_pk = W + 6, *cr_dk = W + 9;
+    const double cr_op = W[12], *cr_exp_pt = W + 13, cr_exp_dist = W[16], *ref_dir = W + 17;
+    const double R = W[20], sign_soln = W[21], n_obj = W[22], n_img = W[23];
+    double e1 = eic_distance(p1, d0, cr_p1, cr_d0);
+    double ekp = eic_distance(pk, dk, cr_pk, cr_dk);
+    double dst = ekp - cr_exp_dist;
+    double pc[3];
+    for (int c = 0; c < 3; c++) pc[c] = (pk[c] - dst*dk[c]) - cr_exp_pt[c];
+    double F = dot3(ref_dir, dk) - dot3(dk, pc)/R;
+    double J = dot3(pc, pc)/R - 2.0*dot3(ref_dir, pc);
+    double rad = pow(F, 2.0) + J/R;
+    if (rad < 0.0) return NAN;              /* math.sqrt ValueError in the reference */
+    double denom = F + sign_soln*sqrt(rad);
+    double ep = (denom == 0) ? 0 : J/denom;
+    return -n_obj*e1 - ray_op + n_img*ekp + cr_op - n_img*ep;
+}
+
 /* ---- whole grid on the host: start rays + trace + transverse aberration, split
  * over n_threads pthreads.  This is the CPU baseline / reference arm of bench.py
  * (the reference evaluates the same thing with a Python loop, trace.py:563-605).
@@ -662,7 +695,7 @@ int rto_transverse_abr(int64_t n, const double *px, const double *py,
 typedef struct {
     const rt_grid_spec *g; const rt_surface_desc *surfs; int32_t n_ifc; const double *n_by_wvl;
     const rt_opts *o; int64_t ray_begin, n; int64_t r0, r1;
-    double *last, *op, *abr_x, *abr_y; int32_t *status, *fail_surf;
+    double *last, *op, *abr_x, *abr_y, *opd; int32_t *status, *fail_surf;
 } grid_job;
 
 static void *grid_worker(void *arg)
@@ -670,6 +703,7 @@ static void *grid_worker(void *arg)
     grid_job *J = (grid_job *)arg;
     const rt_grid_spec *g = J->g;
     const int64_t per_tile = (int64_t)g->nx*g->ny;
+    double *ray = J->opd ? (double *)malloc(sizeof(double)*RT_SEG_DOUBLES*(size_t)J->n_ifc) : NULL;
     for (int64_t r = J->r0; r < J->r1; r++) {
         double px, py, pz, dx, dy, dz;
         int32_t w;
@@ -677,8 +711,14 @@ static void *grid_worker(void *arg)
         double p0[3] = {px, py, pz}, d0[3] = {dx, dy, dz}, lseg[RT_SEG_DOUBLES], opl;
         int32_t ns, st, fs;
         rto_trace_ray(J->surfs, J->n_ifc, J->n_by_wvl + (size_t)w*J->n_ifc, p0, d0, J->o,
-                      NULL, lseg, &ns, &opl, &st, &fs);
+                      ray, lseg, &ns, &opl, &st, &fs);
         int64_t k = r - J->ray_begin;
+        if (J->opd) {
+            const double *s1 = ray + RT_SEG_DOUBLES, *sk = ray + (size_t)(J->n_ifc - 2)*RT_SEG_DOUBLES;
+            J->opd[k] = (st == 0) ? rto_wave_opd(g->wave + (r/per_tile)*RT_WAVE_DOUBLES, s1, ray + 3,
+                                                 sk, sk + 3, opl)
+                                  : NAN;
+        }
         if (J->last) for (int c = 0; c < RT_SEG_DOUBLES; c++) J->last[(size_t)c*J->n + k] = lseg[c];
         if (J->op) J->op[k] = opl;
         if (J->status) J->status[k] = st;
@@ -691,13 +731,14 @@ static void *grid_worker(void *arg)
             J->abr_y[k] = (lseg[1] + dist*lseg[4]) - ry;
         }
     }
+    free(ray);
     return NULL;
 }
 
 int rto_trace_grid(const rt_grid_spec *g, const rt_surface_desc *surfs, int32_t n_ifc,
                    const double *n_by_wvl, int64_t ray_begin, int64_t ray_end, const rt_opts *o,
                    double *last, double *op, int32_t *status, int32_t *fail_surf,
-                   double *abr_x, double *abr_y, int32_t n_threads)
+                   double *abr_x, double *abr_y, double *opd, int32_t n_threads)
 {
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 256) n_threads = 256;
@@ -706,7 +747,7 @@ int rto_trace_grid(const rt_grid_spec *g, const rt_surface_desc *surfs, int32_t 
     int64_t n = ray_end - ray_begin, per = (n + n_threads - 1)/n_threads;
     for (int t = 0; t < n_threads; t++) {
         grid_job J = {g, surfs, n_ifc, n_by_wvl, o, ray_begin, n, 0, 0, last, op, abr_x, abr_y,
-                      status, fail_surf};
+                      (opd && g->wave) ? opd : NULL, status, fail_surf};
         J.r0 = ray_begin + t*per; J.r1 = J.r0 + per;
         if (J.r0 > ray_end) J.r0 = ray_end;
         if (J.r1 > ray_end) J.r1 = ray_end;

@@ -112,9 +112,18 @@ def trace_grid(spec: rt_grid_spec, descs, n_by_wvl, ray_begin, ray_end, opts, n_
     status = np.zeros(n, dtype=np.int32)
     fail_surf = np.zeros(n, dtype=np.int32)
     ax, ay = np.zeros(n), np.zeros(n)
+    opd = np.full(n, np.nan) if bool(spec.wave) else None
     lib().rto_trace_grid(C.byref(spec), descs, C.c_int32(len(descs)), _dp(n_by_wvl),
                          C.c_int64(ray_begin), C.c_int64(ray_end), C.byref(opts),
                          _dp(last), _dp(op), _ip(status), _ip(fail_surf), _dp(ax), _dp(ay),
-                         C.c_int32(n_threads))
+                         _dp(opd), C.c_int32(n_threads))
     return {'last': last, 'op': op, 'status': status, 'fail_surf': fail_surf,
-            'abr': np.stack([ax, ay])}
+            'abr': np.stack([ax, ay]), 'opd': opd}
+
+
+def wave_opd(W, p1, d0, pk, dk, ray_op):
+    """wave_abr_full_calc_finite_pup for one ray (W: RT_WAVE_DOUBLES record)."""
+    f = lib().rto_wave_opd
+    f.restype = C.c_double
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (W, p1, d0, pk, dk)]
+    return f(*[_dp(a) for a in arrs], C.c_double(ray_op))

@@ -14,6 +14,7 @@ RT_MAX_COEFS = 20
 RT_MAX_APERTURES = 4
 RT_SEG_DOUBLES = 10
 RT_SUMMARY_DOUBLES = 16
+RT_WAVE_DOUBLES = 24
 
 # enum rt_profile
 PROFILE_IDS = {'Spherical': 0, 'Conic': 1, 'EvenPolynomial': 2,
@@ -59,7 +60,7 @@ class rt_out(C.Structure):
                 ('dst', C.c_void_p), ('op', C.c_void_p),
                 ('status', C.c_void_p), ('fail_surf', C.c_void_p), ('n_seg', C.c_void_p),
                 ('full', C.c_void_p), ('full_stride', C.c_int64),
-                ('abr_x', C.c_void_p), ('abr_y', C.c_void_p)]
+                ('abr_x', C.c_void_p), ('abr_y', C.c_void_p), ('opd', C.c_void_p)]
 
 
 class rt_field_desc(C.Structure):
@@ -74,8 +75,9 @@ class rt_grid_spec(C.Structure):
                 ('fields', C.POINTER(rt_field_desc)),
                 ('wvl_idx', c_int32_p),
                 ('pupil_x', c_double_p), ('pupil_y', c_double_p),
-                ('ref_img', c_double_p),
+                ('ref_img', c_double_p), ('wave', c_double_p),
                 ('apply_vignetting', C.c_int32), ('flip_z_dir', C.c_int32),
+                ('paired', C.c_int32), ('reserved', C.c_int32),
                 ('eprad', C.c_double), ('z_pupil', C.c_double), ('foc', C.c_double)]
 
 

@@ -133,3 +133,164 @@ def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table
                       len(wvls), grid.first_ray_of_chunk(c0), grid.n_rays, io)
     grid.close()
     return out
+
+
+# --------------------------------------------------------------------------
+# RayFan / RayList / RayGrid: the reference's analysis classes
+# (/root/reference/src/rayoptics/raytr/analyses.py:121-187,343-434,584-663) with
+# the same constructor arguments and result attributes, each evaluated by one
+# grid launch (chief rays: one more tiny launch).
+# --------------------------------------------------------------------------
+from . import waveabr as W                      # noqa: E402
+from . import sampler                           # noqa: E402
+
+
+def _resolve(opt_model, f, wl, foc):
+    osp = opt_model.optical_spec
+    fld = osp.field_of_view.fields[f] if isinstance(f, int) else f
+    wvl = osp.spectral_region.central_wvl if wl is None else wl
+    foc = osp.defocus.focus_shift if foc is None else foc
+    return fld, wvl, foc
+
+
+def _trace_pupil_points(opt_model, table, fld, wvl, foc, px, py, paired, apply_vignetting,
+                        check_apertures, image_pt_2d, image_delta, want_opd):
+    """One (field, wvl) tile of pupil points -> host dict(pupil, abr, opd, status)."""
+    osp, sm = opt_model.optical_spec, opt_model.seq_model
+    wave, ref_img, pkgs = W.setup_tiles(opt_model, table, [fld], [wvl], foc, image_pt_2d, image_delta)
+    recs, eprad, z_pupil = osp.grid_fields([fld])
+    grid = E.PupilGrid(recs, [table.wvl_index(wvl)], px, py, eprad, z_pupil, ref_img=ref_img,
+                       apply_vignetting=apply_vignetting, flip_z_dir=sm.z_dir[0], foc=foc,
+                       paired=paired, wave=wave if want_opd else None, device=table.device)
+    outs = ('abr', 'status') + (('opd',) if want_opd else ())
+    res = E.trace_grid(table, grid, outputs=outs, summary=False, check_apertures=check_apertures)
+    out = {'abr': res.abr.cpu().numpy(), 'status': res.status.cpu().numpy(),
+           'opd': res.opd.cpu().numpy() if want_opd else None, 'ref_sphere': pkgs[0][0][1],
+           'chief_ray': pkgs[0][0][0]}
+    grid.close()
+    return out
+
+
+def _vignetted(fld, px, py, apply_vignetting):
+    """pupil coordinates as the reference records them (after Field.apply_vignetting
+    when it is applied: trace.trace_grid forwards the vignetted values)."""
+    if not apply_vignetting:
+        return np.array(px, dtype=float), np.array(py, dtype=float)
+    vx, vy = np.array(px, dtype=float), np.array(py, dtype=float)
+    for k in range(len(vx)):
+        v = fld.apply_vignetting(np.array([vx[k], vy[k]]))
+        vx[k], vy[k] = v[0], v[1]
+    return vx, vy
+
+
+class RayFan:
+    """A fan of rays across the pupil (analyses.py:121-187).
+
+    ``fan``: list of ``((pupil_x, pupil_y), (dx, dy, opd))`` for the rays that
+    reach the image, ``opd`` in waves -- the output of ``focus_fan``
+    (analyses.py:313-339)."""
+
+    def __init__(self, opt_model, f=0, wl=None, foc=None, image_pt_2d=None, image_delta=None,
+                 num_rays=21, xyfan='y', output_filter=None, rayerr_filter=None, color=None,
+                 clip_rays=False, table=None, device=0, **kwargs):
+        self.opt_model = opt_model
+        self.fld, self.wvl, self.foc = _resolve(opt_model, f, wl, foc)
+        self.image_pt_2d, self.image_delta = image_pt_2d, image_delta
+        self.num_rays = num_rays
+        self.xyfan = 0 if xyfan == 'x' else (1 if xyfan == 'y' else int(xyfan))
+        self.color = color
+        self.clip_rays = clip_rays
+        self._table = _table_for(opt_model, table, device)
+        self.update_data()
+
+    def update_data(self, **kwargs):
+        t = E.accumulated_steps(-1.0, 1.0, self.num_rays)
+        zeros = E.accumulated_steps(0.0, 0.0, self.num_rays)
+        px, py = (t, zeros) if self.xyfan == 0 else (zeros, t)
+        r = _trace_pupil_points(self.opt_model, self._table, self.fld, self.wvl, self.foc, px, py,
+                                True, True, self.clip_rays, self.image_pt_2d, self.image_delta, True)
+        convert_to_opd = 1/self.opt_model.nm_to_sys_units(self.wvl)
+        vx, vy = _vignetted(self.fld, px, py, True)
+        self.fan = [((vx[k], vy[k]), (r['abr'][0, k], r['abr'][1, k], convert_to_opd*r['opd'][k]))
+                    for k in range(self.num_rays) if r['status'][k] == 0]
+        return self
+
+
+class RayList:
+    """Rays from a list / generator of pupil coordinates (analyses.py:343-434).
+
+    ``ray_abr``: ``[2, n_ok]`` transverse aberrations of the rays that reach the
+    image (``np.rollaxis(focus_pupil_coords(...), 1)``, analyses.py:432)."""
+
+    def __init__(self, opt_model, pupil_gen=None, pupil_coords=None, num_rays=21, f=0, wl=None,
+                 foc=None, image_pt_2d=None, image_delta=None, output_filter=None,
+                 rayerr_filter=None, clip_rays=False, apply_vignetting=True, table=None, device=0,
+                 **kwargs):
+        self.opt_model = opt_model
+        if pupil_coords is not None and pupil_gen is None:
+            self.pupil_coords, self.pupil_gen = pupil_coords, None
+        else:
+            if pupil_gen is None:
+                grid_def = [np.array([-1., -1.]), np.array([1., 1.]), num_rays]
+                pupil_gen = (sampler.csd_grid_ray_generator, (grid_def,), {})
+            self.pupil_gen = pupil_gen
+            fct, args, kwa = pupil_gen
+            self.pupil_coords = fct(*args, **kwa)
+        self.fld, self.wvl, self.foc = _resolve(opt_model, f, wl, foc)
+        self.image_pt_2d, self.image_delta = image_pt_2d, image_delta
+        self.apply_vignetting = apply_vignetting
+        # trace_pupil_coords defaults check_apertures to True when the key is absent;
+        # RayList always passes clip_rays (analyses.py:389,554)
+        self.clip_rays = clip_rays
+        self._table = _table_for(opt_model, table, device)
+        self.update_data()
+
+    def update_data(self, **kwargs):
+        if self.pupil_gen:
+            fct, args, kwa = self.pupil_gen
+            self.pupil_coords = fct(*args, **kwa)
+        pts = np.array([np.array(p, dtype=float) for p in self.pupil_coords]).reshape(-1, 2)
+        r = _trace_pupil_points(self.opt_model, self._table, self.fld, self.wvl, self.foc,
+                                pts[:, 0], pts[:, 1], True, self.apply_vignetting, self.clip_rays,
+                                self.image_pt_2d, self.image_delta, False)
+        ok = r['status'] == 0
+        self.ray_abr = r['abr'][:, ok]
+        self.pupil = pts[ok].T
+        return self
+
+
+class RayGrid:
+    """Square grid of rays over the vignetted pupil -> wavefront map
+    (analyses.py:584-663).  ``grid``: ``[3, num, num]`` = pupil x, pupil y, OPD
+    in waves (``value_if_none`` where the ray does not reach the image)."""
+
+    def __init__(self, opt_model, f=0, wl=None, foc=None, image_pt_2d=None, image_delta=None,
+                 output_filter=None, rayerr_filter=None, num_rays=21, clip_rays=True,
+                 value_if_none=np.nan, oversize=1., table=None, device=0, **kwargs):
+        self.opt_model = opt_model
+        self.fld, self.wvl, self.foc = _resolve(opt_model, f, wl, foc)
+        self.image_pt_2d, self.image_delta = image_pt_2d, image_delta
+        self.num_rays, self.value_if_none, self.oversize = num_rays, value_if_none, oversize
+        self.clip_rays = clip_rays
+        self._table = _table_for(opt_model, table, device)
+        self.update_data()
+
+    def vignetting_bbox(self):
+        """Field.vignetting_bbox (raytr/opticalspec.py:1326-1333)."""
+        poly = [self.fld.apply_vignetting(list(pr)) for pr in self.opt_model.optical_spec.pupil.pupil_rays]
+        poly = np.array(poly)
+        return self.oversize*np.array([poly.min(axis=0), poly.max(axis=0)])
+
+    def update_data(self, **kwargs):
+        bbox = self.vignetting_bbox()
+        n = self.num_rays
+        px = E.accumulated_steps(bbox[0][0], bbox[1][0], n)
+        py = E.accumulated_steps(bbox[0][1], bbox[1][1], n)
+        # trace_ray_grid: apply_vignetting defaults to False (analyses.py:674)
+        r = _trace_pupil_points(self.opt_model, self._table, self.fld, self.wvl, self.foc, px, py,
+                                False, False, self.clip_rays, self.image_pt_2d, self.image_delta, True)
+        convert_to_opd = 1/self.opt_model.nm_to_sys_units(self.wvl)
+        opd = np.where(r['status'] == 0, convert_to_opd*r['opd'], self.value_if_none).reshape(n, n)
+        gx, gy = np.meshgrid(px, py, indexing='ij')
+        self.grid = np.stack([gx, gy, opd])
+        return self

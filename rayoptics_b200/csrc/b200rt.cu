@@ -78,27 +78,28 @@ struct rt_table {
     size_t stage_bytes;      /* shared memory needed to stage the table */
     bool stage;              /* false: table too large, read it from global/L1 */
     bool lean;               /* all interfaces quadric, unrotated, max_aperture clipping only */
+    bool wave_ok;            /* interface n_ifc-2 carries no decenter: OPD epilogue applicable */
     size_t lean_bytes;       /* shared memory of the lean plan */
 };
 
 struct rt_grid {
     int32_t device;
     int32_t n_fields, n_wvls, nx, ny;
-    int32_t apply_vignetting, flip_z_dir;
+    int32_t apply_vignetting, flip_z_dir, paired;
     double eprad, z_pupil, foc;
     rt_field_desc *d_fields;
     int32_t *d_wvl_idx;
-    double *d_pupil_x, *d_pupil_y, *d_ref_img;
+    double *d_pupil_x, *d_pupil_y, *d_ref_img, *d_wave;
     int64_t rays_per_tile, chunks_per_tile, n_tiles, n_chunks, n_rays;
 };
 
 /* what the grid kernel needs, passed by value */
 struct GridDev {
-    int32_t n_wvls, nx, ny, apply_vignetting, flip_z_dir;
+    int32_t n_wvls, nx, ny, apply_vignetting, flip_z_dir, paired;
     double eprad, z_pupil, foc;
     const rt_field_desc *fields;
     const int32_t *wvl_idx;
-    const double *pupil_x, *pupil_y, *ref_img;
+    const double *pupil_x, *pupil_y, *ref_img, *wave;
     int64_t rays_per_tile, chunks_per_tile;
 };
 
@@ -233,7 +234,8 @@ __device__ __forceinline__ void grid_start_ray(const GridDev &G, int f, int64_t 
     const int i = (int)(loc/G.ny), j = (int)(loc - (int64_t)i*G.ny);
     const rt_field_desc &F = G.fields[f];
     /* Field.apply_vignetting, opticalspec.py:1339-1353 */
-    double pupx = G.pupil_x[(int64_t)f*G.nx + i], pupy = G.pupil_y[(int64_t)f*G.ny + j];
+    double pupx = G.pupil_x[(int64_t)f*G.nx + i];
+    double pupy = G.paired ? G.pupil_y[(int64_t)f*G.nx + i] : G.pupil_y[(int64_t)f*G.ny + j];
     if (G.apply_vignetting) {
         const double vlx = F.vlx, vux = F.vux, vly = F.vly, vuy = F.vuy;
         if (pupx < 0.0) { if (vlx != 0.0) pupx *= (1.0 - vlx); }
@@ -284,7 +286,7 @@ __device__ __forceinline__ void warp_record_from_regs(bool have, int status, dou
 /* chunk loop shared by the general and the lean grid kernels: start ray ->
  * trace -> per-ray results -> transverse aberration (focus_pupil_coords,
  * analyses.py:561-580) -> spot sums */
-template <bool SUMMARY, typename TraceFn>
+template <bool SUMMARY, bool WAVE, typename TraceFn>
 __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_begin, int64_t chunk_end,
                                                 const rt_out &out, double *scratch, double *acc,
                                                 TraceFn trace)
@@ -311,9 +313,14 @@ __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_
             const int w = (int)(tile - (int64_t)f*G.n_wvls);
             const int64_t k = tile*G.rays_per_tile + loc - ray0;
             RayResult R;
-            trace(f, w, loc, k, R);
+            Vec3 d0;
+            trace(f, w, loc, k, R, d0);
             store_result(out, k, R);
             status = R.status; op = R.op;
+            if (WAVE)
+                out.opd[k] = (R.status == RT_RAY_OK)
+                                 ? wave_opd(G.wave + tile*RT_WAVE_DOUBLES, R.p1, d0, R.pk, R.dk, R.op)
+                                 : CUDART_NAN;
             if (out.abr_x || SUMMARY) {
                 const double rx = G.ref_img ? G.ref_img[tile*2 + 0] : 0.0;
                 const double ry = G.ref_img ? G.ref_img[tile*2 + 1] : 0.0;
@@ -329,7 +336,7 @@ __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_
     if (SUMMARY && !chunk_slots && cur_tile >= 0) acc_flush(acc, scratch, cur_tile, blockIdx.x, sl);
 }
 
-template <bool FULL, bool SUMMARY, bool STAGE>
+template <bool FULL, bool SUMMARY, bool STAGE, bool WAVE>
 __global__ void __launch_bounds__(RT_BLOCK)
 k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
              int n_ifc, int n_wvl, GridDev G, int64_t chunk_begin, int64_t chunk_end,
@@ -340,12 +347,12 @@ k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restri
     const double *ntab;
     double *acc = reinterpret_cast<double *>(smem);          /* [RT_ACC][RT_BLOCK] when SUMMARY */
     stage_table<STAGE>(g_surfs, g_n, n_ifc, n_wvl, smem + (SUMMARY ? RT_ACC_BYTES : 0), tab, ntab);
-    grid_chunk_loop<SUMMARY>(G, chunk_begin, chunk_end, out, scratch, acc,
-        [&](int f, int w, int64_t loc, int64_t k, RayResult &R) {
-            Vec3 p0, d0;
+    grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc,
+        [&](int f, int w, int64_t loc, int64_t k, RayResult &R, Vec3 &d0) {
+            Vec3 p0;
             grid_start_ray<false>(G, f, loc, p0, d0);
             FullWriter fw = {FULL ? out.full + k : nullptr, out.full_stride};
-            trace_ray<FULL>(tab, ntab + (int64_t)G.wvl_idx[w]*n_ifc, n_ifc, o, p0, d0, fw, R);
+            trace_ray<FULL, WAVE>(tab, ntab + (int64_t)G.wvl_idx[w]*n_ifc, n_ifc, o, p0, d0, fw, R);
         });
 }
 
@@ -377,7 +384,7 @@ k_trace_bundle_lean(const rt_surface_desc *__restrict__ g_surfs, const double *_
     }
 }
 
-template <int OUT, bool SUMMARY>
+template <int OUT, bool SUMMARY, bool WAVE>
 __global__ void __launch_bounds__(RT_BLOCK, RT_LEAN_MIN_CTAS)
 k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
                   int n_ifc, int n_wvl, GridDev G, int64_t chunk_begin, int64_t chunk_end,
@@ -389,12 +396,12 @@ k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__r
     LeanIdx *li = reinterpret_cast<LeanIdx *>(ls + n_ifc);
     build_plan(g_surfs, g_n, n_ifc, n_wvl, o, ls, li);
     __syncthreads();
-    grid_chunk_loop<SUMMARY>(G, chunk_begin, chunk_end, out, scratch, acc,
-        [&](int f, int w, int64_t loc, int64_t k, RayResult &R) {
-            Vec3 p0, d0;
+    grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc,
+        [&](int f, int w, int64_t loc, int64_t k, RayResult &R, Vec3 &d0) {
+            Vec3 p0;
             grid_start_ray<true>(G, f, loc, p0, d0);
             FullWriter fw = {OUT == 2 ? out.full + k : nullptr, out.full_stride};
-            trace_ray_lean<OUT>(ls, li + (int64_t)G.wvl_idx[w]*n_ifc, n_ifc, o, p0, d0, fw, R);
+            trace_ray_lean<OUT, WAVE>(ls, li + (int64_t)G.wvl_idx[w]*n_ifc, n_ifc, o, p0, d0, fw, R);
         });
 }
 
@@ -595,11 +602,11 @@ static cudaError_t upload(T **dst, const T *src, size_t n)
     return cudaMemcpy(*dst, src, n*sizeof(T), cudaMemcpyHostToDevice);
 }
 
-template <bool FULL, bool SUMMARY, bool STAGE>
+template <bool FULL, bool SUMMARY, bool STAGE, bool WAVE = false>
 static int launch_grid(const rt_table *t, const rt_grid *g, const GridDev &G, int64_t cb, int64_t ce,
                        const rt_opts *o, const rt_out *out, double *scratch, cudaStream_t stream)
 {
-    auto kern = k_trace_grid<FULL, SUMMARY, STAGE>;
+    auto kern = k_trace_grid<FULL, SUMMARY, STAGE, WAVE>;
     const size_t smem = (STAGE ? t->stage_bytes : 0) + (SUMMARY ? RT_ACC_BYTES : 0);
     int rc = prep_kernel(kern, smem);
     if (rc) return rc;
@@ -633,11 +640,11 @@ static int launch_bundle_lean(const rt_table *t, int64_t n_rays, const double *p
     return RT_OK;
 }
 
-template <int OUT, bool SUMMARY>
+template <int OUT, bool SUMMARY, bool WAVE = false>
 static int launch_grid_lean(const rt_table *t, const GridDev &G, int64_t cb, int64_t ce,
                             const rt_opts *o, const rt_out *out, double *scratch, cudaStream_t stream)
 {
-    auto kern = k_trace_grid_lean<OUT, SUMMARY>;
+    auto kern = k_trace_grid_lean<OUT, SUMMARY, WAVE>;
     const size_t smem = t->lean_bytes + (SUMMARY ? RT_ACC_BYTES : 0);
     int rc = prep_kernel(kern, smem);
     if (rc) return rc;
@@ -698,6 +705,10 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
         if (s.profile > RT_PROFILE_CONIC || s.has_tfrm != 0 || s.n_apertures != 0) t->lean = false;
     }
     if (getenv("B200RT_NO_LEAN")) t->lean = false;
+    {
+        const rt_surface_desc &k = surfs[n_ifc >= 2 ? n_ifc - 2 : 0];
+        t->wave_ok = n_ifc >= 3 && k.has_tfrm == 0 && k.t[0] == 0.0 && k.t[1] == 0.0;
+    }
     cudaError_t e = cudaMalloc(&t->d_surfs, (size_t)n_ifc*sizeof(rt_surface_desc));
     if (e == cudaSuccess) e = cudaMalloc(&t->d_n, (size_t)n_ifc*n_wvl*sizeof(double));
     if (e == cudaSuccess)
@@ -764,7 +775,7 @@ int rt_grid_destroy(rt_grid *g)
     if (!g) return RT_OK;
     DeviceGuard guard(g->device);
     cudaFree(g->d_fields); cudaFree(g->d_wvl_idx);
-    cudaFree(g->d_pupil_x); cudaFree(g->d_pupil_y); cudaFree(g->d_ref_img);
+    cudaFree(g->d_pupil_x); cudaFree(g->d_pupil_y); cudaFree(g->d_ref_img); cudaFree(g->d_wave);
     delete g;
     return RT_OK;
 }
@@ -772,7 +783,8 @@ int rt_grid_destroy(rt_grid *g)
 int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out)
 {
     if (!spec || !out || spec->n_fields < 1 || spec->n_wvls < 1 || spec->nx < 1 || spec->ny < 1 ||
-        !spec->fields || !spec->wvl_idx || !spec->pupil_x || !spec->pupil_y)
+        !spec->fields || !spec->wvl_idx || !spec->pupil_x || !spec->pupil_y ||
+        (spec->paired && spec->ny != 1))
         return fail(RT_ERR_INVALID, "rt_grid_create: bad arguments");
     DeviceGuard guard(device);
     rt_grid *g = new (std::nothrow) rt_grid();
@@ -780,6 +792,7 @@ int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out)
     g->device = device;
     g->n_fields = spec->n_fields; g->n_wvls = spec->n_wvls; g->nx = spec->nx; g->ny = spec->ny;
     g->apply_vignetting = spec->apply_vignetting; g->flip_z_dir = spec->flip_z_dir;
+    g->paired = spec->paired;
     g->eprad = spec->eprad; g->z_pupil = spec->z_pupil; g->foc = spec->foc;
     g->rays_per_tile = (int64_t)spec->nx*spec->ny;
     g->chunks_per_tile = (g->rays_per_tile + RT_BLOCK - 1)/RT_BLOCK;
@@ -789,8 +802,10 @@ int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out)
     cudaError_t e = upload(&g->d_fields, spec->fields, (size_t)spec->n_fields);
     if (e == cudaSuccess) e = upload(&g->d_wvl_idx, spec->wvl_idx, (size_t)spec->n_wvls);
     if (e == cudaSuccess) e = upload(&g->d_pupil_x, spec->pupil_x, (size_t)spec->n_fields*spec->nx);
-    if (e == cudaSuccess) e = upload(&g->d_pupil_y, spec->pupil_y, (size_t)spec->n_fields*spec->ny);
+    if (e == cudaSuccess)
+        e = upload(&g->d_pupil_y, spec->pupil_y, (size_t)spec->n_fields*(spec->paired ? spec->nx : spec->ny));
     if (e == cudaSuccess) e = upload(&g->d_ref_img, spec->ref_img, (size_t)g->n_tiles*2);
+    if (e == cudaSuccess) e = upload(&g->d_wave, spec->wave, (size_t)g->n_tiles*RT_WAVE_DOUBLES);
     if (e != cudaSuccess) {
         rt_grid_destroy(g);
         return fail(RT_ERR_CUDA, "rt_grid_create: %s", cudaGetErrorString(e));
@@ -840,16 +855,32 @@ int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int6
     if (chunk_begin == chunk_end) return RT_OK;
     GridDev G;
     G.n_wvls = g->n_wvls; G.nx = g->nx; G.ny = g->ny;
-    G.apply_vignetting = g->apply_vignetting; G.flip_z_dir = g->flip_z_dir;
+    G.apply_vignetting = g->apply_vignetting; G.flip_z_dir = g->flip_z_dir; G.paired = g->paired;
     G.eprad = g->eprad; G.z_pupil = g->z_pupil; G.foc = g->foc;
     G.fields = g->d_fields; G.wvl_idx = g->d_wvl_idx;
-    G.pupil_x = g->d_pupil_x; G.pupil_y = g->d_pupil_y; G.ref_img = g->d_ref_img;
+    G.pupil_x = g->d_pupil_x; G.pupil_y = g->d_pupil_y; G.ref_img = g->d_ref_img; G.wave = g->d_wave;
     G.rays_per_tile = g->rays_per_tile; G.chunks_per_tile = g->chunks_per_tile;
     double *scr = (double *)scratch;
     if (summary)
         CUDA_TRY(cudaMemsetAsync(scr, 0, (size_t)rt_grid_scratch_bytes(g, chunk_begin, chunk_end), s));
     const bool full = out->full != nullptr, summ = summary != nullptr, st = t->stage;
-    if (t->lean) {
+    const bool wave = out->opd != nullptr;
+    if (wave) {
+        if (!g->d_wave) return fail(RT_ERR_INVALID, "rt_trace_grid: out.opd needs rt_grid_spec.wave");
+        if (out_kind(out) != 0) return fail(RT_ERR_UNSUPPORTED, "rt_trace_grid: opd cannot be combined with normals / whole rays");
+        if (!t->wave_ok)
+            return fail(RT_ERR_UNSUPPORTED, "rt_trace_grid: opd needs >= 3 interfaces and no decenter on the last one before the image");
+        if (t->lean) {
+            rc = summ ? launch_grid_lean<0, true, true>(t, G, chunk_begin, chunk_end, o, out, scr, s)
+                      : launch_grid_lean<0, false, true>(t, G, chunk_begin, chunk_end, o, out, scr, s);
+        } else if (st) {
+            rc = summ ? launch_grid<false, true, true, true>(t, g, G, chunk_begin, chunk_end, o, out, scr, s)
+                      : launch_grid<false, false, true, true>(t, g, G, chunk_begin, chunk_end, o, out, scr, s);
+        } else {
+            rc = summ ? launch_grid<false, true, false, true>(t, g, G, chunk_begin, chunk_end, o, out, scr, s)
+                      : launch_grid<false, false, false, true>(t, g, G, chunk_begin, chunk_end, o, out, scr, s);
+        }
+    } else if (t->lean) {
         const int kind = out_kind(out);
 #define RT_LEAN_CASE(K, S)                                                                   \
         if (kind == K && summ == S)                                                          \

@@ -65,7 +65,7 @@ class BundleResult:
         f64 = dict(dtype=torch.float64, device=device)
         i32 = dict(dtype=torch.int32, device=device)
         want = set(outputs)
-        unknown = want - set(BUNDLE_OUTPUTS) - {'full', 'abr'}
+        unknown = want - set(BUNDLE_OUTPUTS) - {'full', 'abr', 'opd'}
         if unknown:
             raise ValueError(f'unknown outputs {sorted(unknown)}')
         self.n = n
@@ -80,6 +80,7 @@ class BundleResult:
         self.full = (torch.full((n_ifc, RT_SEG_DOUBLES, n), float('nan'), **f64)
                      if 'full' in want else None)
         self.abr = torch.empty((2, n), **f64) if 'abr' in want else None
+        self.opd = torch.empty(n, **f64) if 'opd' in want else None
         self.summary = None
 
     def c_struct(self):
@@ -97,13 +98,14 @@ class BundleResult:
             o.full_stride = self.n
         if self.abr is not None:
             o.abr_x, o.abr_y = _ptr(self.abr[0]), _ptr(self.abr[1])
+        o.opd = _ptr(self.opd)
         return o
 
     def bytes_per_ray(self):
         """bytes the kernel writes per ray for the allocated outputs"""
         b = 0
         for t in (self.p, self.d, self.nrml, self.abr, self.dst, self.op, self.status,
-                  self.fail_surf, self.n_seg):
+                  self.fail_surf, self.n_seg, self.opd):
             if t is not None:
                 b += t.element_size()*(t.numel()//max(self.n, 1))
         return b
@@ -170,8 +172,9 @@ class PupilGridSpec:
     ``[n_fields, n_wvls, 2]`` reference image points or None."""
 
     def __init__(self, fields, wvl_idx, pupil_x, pupil_y, eprad, z_pupil, ref_img=None,
-                 apply_vignetting=True, flip_z_dir=1, foc=0.0):
+                 apply_vignetting=True, flip_z_dir=1, foc=0.0, paired=False, wave=None):
         nf = len(fields)
+        self.paired = int(bool(paired))
         self.n_fields = nf
         self.wvl_idx = np.ascontiguousarray(wvl_idx, dtype=np.int32)
         self.n_wvls = len(self.wvl_idx)
@@ -183,6 +186,10 @@ class PupilGridSpec:
             py = np.ascontiguousarray(np.broadcast_to(py, (nf, py.shape[0])))
         self.pupil_x, self.pupil_y = px, py
         self.nx, self.ny = px.shape[1], py.shape[1]
+        if self.paired:          # ray list: (pupil_x[i], pupil_y[i]), one "row" of nx rays
+            if py.shape[1] != px.shape[1]:
+                raise ValueError('paired pupil lists need as many y as x coordinates')
+            self.ny = 1
         self.fields = (rt_field_desc*nf)()
         for i, f in enumerate(fields):
             get = (lambda k, f=f: f[k]) if isinstance(f, dict) else (lambda k, f=f: getattr(f, k))
@@ -195,6 +202,10 @@ class PupilGridSpec:
         self.ref_img = None
         if ref_img is not None:
             self.ref_img = np.ascontiguousarray(ref_img, dtype=np.float64).reshape(nf, self.n_wvls, 2)
+        self.wave = None
+        if wave is not None:
+            self.wave = np.ascontiguousarray(wave, dtype=np.float64).reshape(
+                nf, self.n_wvls, _abi.RT_WAVE_DOUBLES)
         self.eprad, self.z_pupil, self.foc = float(eprad), float(z_pupil), float(foc)
         self.apply_vignetting, self.flip_z_dir = int(bool(apply_vignetting)), int(flip_z_dir)
         self.chunk_rays = CHUNK_RAYS
@@ -207,7 +218,8 @@ class PupilGridSpec:
     def host_bytes(self):
         """bytes rt_grid_create copies to the device"""
         return (C.sizeof(rt_field_desc)*self.n_fields + self.wvl_idx.nbytes + self.pupil_x.nbytes
-                + self.pupil_y.nbytes + (0 if self.ref_img is None else self.ref_img.nbytes))
+                + self.pupil_y.nbytes + (0 if self.ref_img is None else self.ref_img.nbytes)
+                + (0 if self.wave is None else self.wave.nbytes))
 
     def c_spec(self):
         """The rt_grid_spec (host pointers into arrays owned by this object)."""
@@ -218,7 +230,9 @@ class PupilGridSpec:
         s.pupil_x = self.pupil_x.ctypes.data_as(_abi.c_double_p)
         s.pupil_y = self.pupil_y.ctypes.data_as(_abi.c_double_p)
         s.ref_img = None if self.ref_img is None else self.ref_img.ctypes.data_as(_abi.c_double_p)
+        s.wave = None if self.wave is None else self.wave.ctypes.data_as(_abi.c_double_p)
         s.apply_vignetting, s.flip_z_dir = self.apply_vignetting, self.flip_z_dir
+        s.paired = self.paired
         s.eprad, s.z_pupil, s.foc = self.eprad, self.z_pupil, self.foc
         return s
 

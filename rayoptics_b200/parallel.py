@@ -25,18 +25,40 @@ def shard_chunks(n_chunks, rank, world_size):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
-def gather_summaries(partial, group=None):
+class PendingSummary:
+    """Handle of an in-flight all-gather (``gather_summaries(..., async_op=True)``):
+    the collective runs on NCCL's stream while the next grid is traced;
+    ``result()`` waits and combines."""
+
+    def __init__(self, work, out, shape, world):
+        self.work, self.out, self.shape, self.world = work, out, shape, world
+
+    def result(self):
+        self.work.wait()
+        return combine_summaries(self.out.view((self.world,) + self.shape))
+
+
+def gather_summaries(partial, group=None, async_op=False):
     """All-gather the per-rank partial summaries and combine them.
 
     ``partial``: ``[n_tiles, 16]`` float64 tensor (CUDA for NCCL, CPU for gloo).
-    Returns the combined ``[n_tiles, 16]`` summary, identical on every rank."""
+    Returns the combined ``[n_tiles, 16]`` summary, identical on every rank
+    (or a ``PendingSummary`` when ``async_op``)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if async_op:
+            class _Done:
+                def result(self_inner):
+                    return partial.clone()
+            return _Done()
         return partial.clone()
     world = dist.get_world_size(group)
     partial = partial.contiguous()
     # concatenated layout [world*n_tiles, 16]: accepted by both NCCL and gloo
     out = torch.empty((world*partial.shape[0],) + tuple(partial.shape[1:]), dtype=partial.dtype,
                       device=partial.device)
+    if async_op:
+        work = dist.all_gather_into_tensor(out, partial, group=group, async_op=True)
+        return PendingSummary(work, out, tuple(partial.shape), world)
     dist.all_gather_into_tensor(out, partial, group=group)
     return combine_summaries(out.view((world,) + tuple(partial.shape)))
 

@@ -1,0 +1,140 @@
+"""Chief rays, reference spheres and the per-tile records of the OPD epilogue.
+
+Host side of the wavefront stage.  The per-ray OPD
+(``wave_abr_full_calc_finite_pup``, /root/reference/src/rayoptics/raytr/waveabr.py:255-305)
+is evaluated by the grid kernel; what it needs per (field, wavelength) tile is
+computed here, once, with the reference's own expressions:
+
+* chief ray = pupil (0, 0) traced whole (``trace_chief_ray``, raytr/trace.py:513-534)
+  -- all tiles in one launch;
+* ``transfer_to_exit_pupil`` (waveabr.py:79-113, interfaces without decenter);
+* ``calculate_reference_sphere`` (waveabr.py:24-76).
+
+Supported: finite reference spheres (``ref_sphere_radius <= 1e8``); the
+infinite-reference variant (waveabr.py:356-488) is not implemented.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine as E
+from ._abi import RT_WAVE_DOUBLES
+
+
+def normalize(v):
+    length = np.linalg.norm(v)
+    return v if length == 0.0 else v/length
+
+
+def transfer_to_exit_pupil(ray_seg, exp_dst_parax):
+    """waveabr.py:79-113 for an exiting interface without decenter."""
+    b4_pt, b4_dir = ray_seg
+    h = b4_pt[1]
+    u = b4_dir[1]
+    if abs(u) < 1e-14:
+        exp_dst = exp_dst_parax
+    else:
+        exp_dst = -h/u
+    exp_pt = b4_pt + exp_dst*b4_dir
+    return exp_pt, b4_dir, exp_dst, None, b4_pt, b4_dir
+
+
+def trace_chief_rays(opt_model, table, fields, wvls):
+    """Whole chief rays of every (field, wvl): one launch.  Returns
+    ``full [n_ifc, 10, n_tiles]``, ``op [n_tiles]``, ``status [n_tiles]`` (numpy)."""
+    osp, sm = opt_model.optical_spec, opt_model.seq_model
+    recs, eprad, z_pupil = osp.grid_fields(fields)
+    g0 = E.PupilGrid(recs, [table.wvl_index(w) for w in wvls], [0.0], [0.0], eprad, z_pupil,
+                     apply_vignetting=True, flip_z_dir=sm.z_dir[0], device=table.device)
+    r0 = E.trace_grid(table, g0, outputs=('op', 'status'), full=True, summary=False,
+                      check_apertures=False)
+    out = r0.full.cpu().numpy(), r0.op.cpu().numpy(), r0.status.cpu().numpy()
+    g0.close()
+    return out
+
+
+def chief_ray_pkg(opt_model, full, op, wvl, tile):
+    """(cr, cr_exp_seg) of one tile from the bundle output (trace.py:513-534)."""
+    n_ifc = full.shape[0]
+    ray = [[full[k, 0:3, tile].copy(), full[k, 3:6, tile].copy(), float(full[k, 6, tile]),
+            full[k, 7:10, tile].copy()] for k in range(n_ifc)]
+    cr = (ray, float(op[tile]), wvl)
+    fod = opt_model.optical_spec.fod
+    cr_exp_seg = transfer_to_exit_pupil((ray[-2][0], ray[-2][1]), fod.exp_dist)
+    return cr, cr_exp_seg
+
+
+def calculate_reference_sphere(opt_model, fld, wvl, foc, chief_ray_pkg_, image_pt_2d=None,
+                               image_delta=None):
+    """waveabr.py:24-76 -> (image_pt, ref_dir, ref_sphere_radius, lcl_tfrm_last)."""
+    cr, cr_exp_seg = chief_ray_pkg_
+    ray = cr[0]
+    if image_pt_2d is None:
+        dist = foc/ray[-1][1][2]
+        image_pt = ray[-1][0] + dist*ray[-1][1]
+    else:
+        image_pt = np.array([image_pt_2d[0], image_pt_2d[1], foc])
+    if image_delta is not None:
+        image_pt[:2] += image_delta
+    seq_model = opt_model.seq_model
+    lcl_tfrm_last = seq_model.lcl_tfrms[-2]
+    image_thi = seq_model.gaps[-1].thi
+    img_pt = np.array(image_pt)
+    img_pt[2] += image_thi
+    ref_sphere_vec = img_pt - cr_exp_seg[0]
+    ref_sphere_radius = np.linalg.norm(ref_sphere_vec)
+    ref_dir = normalize(ref_sphere_vec)
+    return image_pt, ref_dir, ref_sphere_radius, lcl_tfrm_last
+
+
+def wave_record(opt_model, chief_ray_pkg_, ref_sphere):
+    """The RT_WAVE_DOUBLES record of a tile (layout: include/b200rt.h)."""
+    cr, cr_exp_seg = chief_ray_pkg_
+    ray, cr_op, _ = cr
+    image_pt, ref_dir, radius, _ = ref_sphere
+    if not np.isfinite(radius) or abs(radius) > 1e8:
+        raise NotImplementedError('infinite reference sphere (waveabr.py:356-488) not implemented')
+    fod = opt_model.optical_spec.fod
+    W = np.zeros(RT_WAVE_DOUBLES)
+    W[0:3], W[3:6] = ray[1][0], ray[0][1]
+    W[6:9], W[9:12] = ray[-2][0], ray[-2][1]
+    W[12] = cr_op
+    W[13:16] = cr_exp_seg[0]
+    W[16] = cr_exp_seg[2]
+    W[17:20] = ref_dir
+    W[20] = radius
+    W[21] = -1.0 if ref_dir[2]*ray[-1][1][2] < 0 else 1.0
+    W[22], W[23] = abs(fod.n_obj), abs(fod.n_img)
+    return W
+
+
+def setup_tiles(opt_model, table, fields, wvls, foc, image_pt_2d=None, image_delta=None,
+                ref_wvl_for_image_pt=None):
+    """Chief rays + reference spheres of all tiles.
+
+    Returns ``(wave [n_f, n_w, 24], ref_img [n_f, n_w, 2], pkgs)`` where
+    ``pkgs[f][w] = (chief_ray_pkg, ref_sphere)``.  ``ref_wvl_for_image_pt``: use
+    the image point of that wavelength's chief ray for every wavelength (what
+    ``SequentialModel.trace_fan/trace_grid`` do, seq/sequential.py:1015-1040)."""
+    full, op, status = trace_chief_rays(opt_model, table, fields, wvls)
+    if (status != 0).any():
+        raise RuntimeError('a chief ray did not reach the image')
+    nf, nw = len(fields), len(wvls)
+    wave = np.zeros((nf, nw, RT_WAVE_DOUBLES))
+    ref_img = np.zeros((nf, nw, 2))
+    pkgs = []
+    for fi, fld in enumerate(fields):
+        row = []
+        base_pt = image_pt_2d
+        if ref_wvl_for_image_pt is not None and image_pt_2d is None:
+            wi0 = wvls.index(ref_wvl_for_image_pt)
+            crp = chief_ray_pkg(opt_model, full, op, wvls[wi0], fi*nw + wi0)
+            base_pt = calculate_reference_sphere(opt_model, fld, wvls[wi0], foc, crp)[0]
+        for wi, wvl in enumerate(wvls):
+            crp = chief_ray_pkg(opt_model, full, op, wvl, fi*nw + wi)
+            rs = calculate_reference_sphere(opt_model, fld, wvl, foc, crp, base_pt, image_delta)
+            wave[fi, wi] = wave_record(opt_model, crp, rs)
+            ref_img[fi, wi] = rs[0][:2]
+            row.append((crp, rs))
+        pkgs.append(row)
+    return wave, ref_img, pkgs

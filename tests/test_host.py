@@ -27,7 +27,7 @@ def test_struct_layout_matches_header():
     from oracle import rt_oracle
     assert rt_oracle.lib().rto_sizeof_surface_desc() == C.sizeof(_abi.rt_surface_desc) == 480
     assert C.sizeof(_abi.rt_opts) == 40
-    assert C.sizeof(_abi.rt_out) == 18*8
+    assert C.sizeof(_abi.rt_out) == 19*8
     assert C.sizeof(_abi.rt_field_desc) == 72
 
 
