@@ -90,8 +90,8 @@ def test_cuda_opd_matches_oracle_and_reference(oracle, name):
     torch.cuda.synchronize()
     opd = res.opd.cpu().numpy()
     assert same(res.status.cpu().numpy(), v['status'])
-    assert same(res.abr.cpu().numpy(), v['abr'])
     ok = v['status'] == 0
+    assert same(res.abr.cpu().numpy()[:, ok], v['abr'][:, ok])
     assert np.isnan(opd[~ok]).all()
     np.testing.assert_allclose(opd[ok], v['opd'][ok], rtol=0, atol=1e-12)
     assert (opd[ok] == v['opd'][ok]).mean() > 0.95
