@@ -284,3 +284,40 @@ def test_dropin_trace_matches_reference_vectors(tables):
                 got = np.array([np.concatenate([s[0], s[1], [s[2]], s[3]]) for s in ray])
                 assert same(got, v['full'][:len(ray), :, k])
         assert {0, 3} <= seen
+
+
+@pytest.mark.parametrize('name,num,n_rays', [
+    ('rc', 1024, 5*1024*1024),                 # BASELINE configs[2]: reflect path, 5 fields x 1024^2
+    ('evenasph', 256, 9*3*256*256),            # configs[3]: even-asphere lens, 9 fields x 3 wvls x 256^2
+    ('cellphone', 256, 9*3*256*256),           # configs[3] alternative: 8 RadialPolynomial surfaces
+    ('zoom52', 1024, 25*7*1024*1024//8),       # configs[4]: one rank's 1/8 share of 183.5 M rays
+])
+def test_full_size_configs(tables, oracle, name, num, n_rays):
+    """BASELINE configs 3-5 at full size: seeded chunks against the oracle
+    (bit-exact) + invariants (counts add up, idempotent, shard == whole)."""
+    opm, tab = tables(name)
+    grid = E.grid_for_model(opm, tab, num)
+    if name == 'zoom52':
+        c0, c1 = grid.n_chunks//8*3, grid.n_chunks//8*4          # the 4th of 8 ranks' shard
+    else:
+        c0, c1 = 0, grid.n_chunks
+        assert grid.n_rays == n_rays
+    r = E.trace_grid(tab, grid, c0, c1, outputs=('p', 'd', 'op', 'status', 'abr'))
+    r2 = E.trace_grid(tab, grid, c0, c1, outputs=('status', 'abr'))
+    torch.cuda.synchronize()
+    assert r.n == n_rays
+    assert torch.equal(r.abr, r2.abr) and torch.equal(r.summary, r2.summary)
+    summ = np_(r.summary)
+    assert summ[:, 0:5].sum() == r.n
+    st = np_(r.status)
+    assert (st == 0).sum() == summ[:, 0].sum() and (st == 0).mean() > 0.5
+    rng = np.random.default_rng(11)
+    opts = _abi.make_opts(first_surf=1, last_surf=tab.n_ifc - 2, check_apertures=True)
+    base = grid.first_ray_of_chunk(c0)
+    for c in rng.integers(c0, c1, 24):
+        a, b = grid.first_ray_of_chunk(int(c)), grid.first_ray_of_chunk(int(c) + 1)
+        ref = oracle.trace_grid(grid.c_spec(), tab.descs, tab.n_by_wvl, a, b, opts, n_threads=8)
+        sl = slice(a - base, b - base)
+        assert same(st[sl], ref['status'])
+        assert same(np_(r.p[:, sl]), ref['last'][0:3]) and same(np_(r.d[:, sl]), ref['last'][3:6])
+        assert same(np_(r.op[sl]), ref['op']) and same(np_(r.abr[:, sl]), ref['abr'])
