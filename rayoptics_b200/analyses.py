@@ -62,6 +62,15 @@ class SpotDiagram:
         return self._grids
 
 
+_STREAMS = {}
+
+
+def _side_streams(dev):
+    if dev not in _STREAMS:
+        _STREAMS[dev] = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    return _STREAMS[dev]
+
+
 def _table_for(opt_model, table=None, device=0):
     if table is not None:
         return table
@@ -93,7 +102,7 @@ def chief_ray_image_points(opt_model, table, fields, wvl=None, foc=0.0, io=None)
 
 
 def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table=None,
-                 device=0, pinned=None, shard=None, group=None, **kwargs):
+                 device=0, pinned=None, shard=None, group=None, pieces=4, **kwargs):
     """Spot diagrams of all fields and wavelengths in one launch.
 
     Host buffers in, host buffers out: the grid description goes to the device
@@ -102,7 +111,9 @@ def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table
     ``shard=(rank, world)`` traces only that rank's slice of the chunk space and
     all-gathers the per-(field, wvl) sums over ``group`` (parallel.py).
     ``pinned``: optional dict of pinned host tensors ``abr`` ``[2, >=n]`` and
-    ``status`` ``[>=n]`` to re-use across calls."""
+    ``status`` ``[>=n]`` to re-use across calls.  ``pieces``: the chunk range is
+    traced in that many launches on two streams so that the device->host copy of
+    one piece overlaps the trace of the next."""
     from .parallel import shard_chunks, gather_summaries
     osp, sm = opt_model.optical_spec, opt_model.seq_model
     table = _table_for(opt_model, table, device)
@@ -116,18 +127,38 @@ def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table
                             ref_img=ref_fw)
     io['h2d'] += grid.host_bytes()
     c0, c1 = (0, grid.n_chunks) if shard is None else shard_chunks(grid.n_chunks, *shard)
-    res = E.trace_grid(table, grid, c0, c1, outputs=('abr', 'status'), **kwargs)
-    n = res.n
+    n = grid.rays_in_chunks(c0, c1)
     if pinned is None:
         pinned = {'abr': torch.empty((2, n), dtype=torch.float64).pin_memory(),
                   'status': torch.empty(n, dtype=torch.int32).pin_memory()}
     h_abr, h_status = pinned['abr'][:, :n], pinned['status'][:n]
-    h_abr.copy_(res.abr, non_blocking=True)
-    h_status.copy_(res.status, non_blocking=True)
+    # pipeline: the device->host copy of piece i overlaps the trace of piece i+1
+    n_pieces = max(1, min(pieces, (c1 - c0)//64))
+    cuts = [c0 + (c1 - c0)*i//n_pieces for i in range(n_pieces + 1)]
+    dev = torch.device('cuda', table.device)
+    main = torch.cuda.current_stream(dev)
+    streams = _side_streams(dev) if n_pieces > 1 else [main]
+    parts, keep, base = [], [], grid.first_ray_of_chunk(c0)
+    for i in range(n_pieces):
+        st = streams[i % len(streams)]
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            r = E.trace_grid(table, grid, cuts[i], cuts[i + 1], outputs=('abr', 'status'), **kwargs)
+            a = grid.first_ray_of_chunk(cuts[i]) - base
+            h_abr[0, a:a + r.n].copy_(r.abr[0], non_blocking=True)
+            h_abr[1, a:a + r.n].copy_(r.abr[1], non_blocking=True)
+            h_status[a:a + r.n].copy_(r.status, non_blocking=True)
+        parts.append(r.summary)
+        keep.append(r)
+    for st in streams:
+        main.wait_stream(st)
+    res = keep[-1]
+    res.summary = parts[0] if n_pieces == 1 else E.combine_summaries(parts)
     summ = res.summary if shard is None else gather_summaries(res.summary, group)
-    stats = E.spot_statistics(summ)
-    stats_host = {k: v.cpu().numpy().reshape(len(fields), len(wvls)) for k, v in stats.items()}
+    summ_host = summ.cpu().numpy()                  # one small copy; also waits for the stream
     torch.cuda.current_stream(table.device).synchronize()
+    stats_host = {k: np.asarray(v).reshape(len(fields), len(wvls))
+                  for k, v in E.spot_statistics(summ_host).items()}
     io['d2h'] += h_abr.numel()*8 + h_status.numel()*4 + sum(v.nbytes for v in stats_host.values())
     out = SpotDiagram(h_abr.numpy(), h_status.numpy(), stats_host, ref, num_rays, len(fields),
                       len(wvls), grid.first_ray_of_chunk(c0), grid.n_rays, io)

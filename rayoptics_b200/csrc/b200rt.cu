@@ -90,6 +90,7 @@ struct rt_grid {
     rt_field_desc *d_fields;
     int32_t *d_wvl_idx;
     double *d_pupil_x, *d_pupil_y, *d_ref_img, *d_wave;
+    void *d_block;           /* the one device allocation the pointers above point into */
     int64_t rays_per_tile, chunks_per_tile, n_tiles, n_chunks, n_rays;
 };
 
@@ -591,17 +592,6 @@ static int launch_bundle(const rt_table *t, int64_t n_rays, const double *px, co
     return RT_OK;
 }
 
-/* ---- grids */
-template <typename T>
-static cudaError_t upload(T **dst, const T *src, size_t n)
-{
-    *dst = nullptr;
-    if (!src || n == 0) return cudaSuccess;
-    cudaError_t e = cudaMalloc(dst, n*sizeof(T));
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(*dst, src, n*sizeof(T), cudaMemcpyHostToDevice);
-}
-
 template <bool FULL, bool SUMMARY, bool STAGE, bool WAVE = false>
 static int launch_grid(const rt_table *t, const rt_grid *g, const GridDev &G, int64_t cb, int64_t ce,
                        const rt_opts *o, const rt_out *out, double *scratch, cudaStream_t stream)
@@ -774,12 +764,14 @@ int rt_grid_destroy(rt_grid *g)
 {
     if (!g) return RT_OK;
     DeviceGuard guard(g->device);
-    cudaFree(g->d_fields); cudaFree(g->d_wvl_idx);
-    cudaFree(g->d_pupil_x); cudaFree(g->d_pupil_y); cudaFree(g->d_ref_img); cudaFree(g->d_wave);
+    cudaFree(g->d_block);
     delete g;
     return RT_OK;
 }
 
+/* All arrays of the description go to the device as ONE allocation and ONE copy
+ * (host staging buffer): grids are created per analysis call, so the create /
+ * destroy cost is on the end-to-end path. */
 int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out)
 {
     if (!spec || !out || spec->n_fields < 1 || spec->n_wvls < 1 || spec->nx < 1 || spec->ny < 1 ||
@@ -799,17 +791,37 @@ int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out)
     g->n_tiles = (int64_t)spec->n_fields*spec->n_wvls;
     g->n_chunks = g->n_tiles*g->chunks_per_tile;
     g->n_rays = g->n_tiles*g->rays_per_tile;
-    cudaError_t e = upload(&g->d_fields, spec->fields, (size_t)spec->n_fields);
-    if (e == cudaSuccess) e = upload(&g->d_wvl_idx, spec->wvl_idx, (size_t)spec->n_wvls);
-    if (e == cudaSuccess) e = upload(&g->d_pupil_x, spec->pupil_x, (size_t)spec->n_fields*spec->nx);
-    if (e == cudaSuccess)
-        e = upload(&g->d_pupil_y, spec->pupil_y, (size_t)spec->n_fields*(spec->paired ? spec->nx : spec->ny));
-    if (e == cudaSuccess) e = upload(&g->d_ref_img, spec->ref_img, (size_t)g->n_tiles*2);
-    if (e == cudaSuccess) e = upload(&g->d_wave, spec->wave, (size_t)g->n_tiles*RT_WAVE_DOUBLES);
+
+    const size_t nf = (size_t)spec->n_fields, nw = (size_t)spec->n_wvls;
+    const size_t b_fields = nf*sizeof(rt_field_desc);
+    const size_t b_px = nf*spec->nx*sizeof(double);
+    const size_t b_py = nf*(spec->paired ? spec->nx : spec->ny)*sizeof(double);
+    const size_t b_ref = spec->ref_img ? (size_t)g->n_tiles*2*sizeof(double) : 0;
+    const size_t b_wave = spec->wave ? (size_t)g->n_tiles*RT_WAVE_DOUBLES*sizeof(double) : 0;
+    const size_t b_wvl = (nw*sizeof(int32_t) + 7)/8*8;
+    const size_t o_fields = 0, o_px = o_fields + b_fields, o_py = o_px + b_px, o_ref = o_py + b_py,
+                 o_wave = o_ref + b_ref, o_wvl = o_wave + b_wave, total = o_wvl + b_wvl;
+    std::vector<unsigned char> stage(total);
+    memcpy(&stage[o_fields], spec->fields, b_fields);
+    memcpy(&stage[o_px], spec->pupil_x, b_px);
+    memcpy(&stage[o_py], spec->pupil_y, b_py);
+    if (b_ref) memcpy(&stage[o_ref], spec->ref_img, b_ref);
+    if (b_wave) memcpy(&stage[o_wave], spec->wave, b_wave);
+    memcpy(&stage[o_wvl], spec->wvl_idx, nw*sizeof(int32_t));
+    cudaError_t e = cudaMalloc(&g->d_block, total);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_block, stage.data(), total, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
-        rt_grid_destroy(g);
+        cudaFree(g->d_block);
+        delete g;
         return fail(RT_ERR_CUDA, "rt_grid_create: %s", cudaGetErrorString(e));
     }
+    unsigned char *base = (unsigned char *)g->d_block;
+    g->d_fields = (rt_field_desc *)(base + o_fields);
+    g->d_pupil_x = (double *)(base + o_px);
+    g->d_pupil_y = (double *)(base + o_py);
+    g->d_ref_img = b_ref ? (double *)(base + o_ref) : nullptr;
+    g->d_wave = b_wave ? (double *)(base + o_wave) : nullptr;
+    g->d_wvl_idx = (int32_t *)(base + o_wvl);
     *out = g;
     return RT_OK;
 }

@@ -13,6 +13,7 @@ Replaces the per-ray Python loops of the reference:
 from __future__ import annotations
 
 import ctypes as C
+import functools
 
 import numpy as np
 import torch
@@ -148,7 +149,11 @@ def trace_bundle(table, p, d, wvl_idx=None, full=False, outputs=BUNDLE_OUTPUTS, 
 def accumulated_steps(start, stop, num):
     """The reference's pupil sampling: ``start += step`` repeated (NOT linspace),
     /root/reference/src/rayoptics/raytr/trace.py:567-604."""
-    num = int(num)
+    return _accumulated_steps(float(start), float(stop), int(num)).copy()
+
+
+@functools.lru_cache(maxsize=64)
+def _accumulated_steps(start, stop, num):
     vals = np.empty(num)
     step = np.array((np.float64(stop) - np.float64(start))/(num - 1)) if num > 1 else np.float64(0.)
     x = np.float64(start)
@@ -328,13 +333,19 @@ def combine_summaries(parts):
 
 
 def spot_statistics(summary):
-    """Per-(field, wvl) spot centroid and RMS radius from a combined summary."""
+    """Per-(field, wvl) spot centroid and RMS radius from a combined summary
+    (torch tensor or numpy array ``[n_tiles, 16]``; same type out)."""
     s = summary
-    n = s[:, 0].clamp(min=1.0)
+    if torch.is_tensor(s):
+        n = s[:, 0].clamp(min=1.0)
+        sqrt0 = lambda v: v.clamp(min=0.0).sqrt()      # noqa: E731
+    else:
+        n = np.maximum(s[:, 0], 1.0)
+        sqrt0 = lambda v: np.sqrt(np.maximum(v, 0.0))  # noqa: E731
     cx, cy = s[:, 5]/n, s[:, 6]/n
     var = (s[:, 7] + s[:, 8])/n - (cx*cx + cy*cy)
     return {'n_ok': s[:, 0], 'n_missed': s[:, 1], 'n_tir': s[:, 2], 'n_blocked': s[:, 3],
-            'centroid_x': cx, 'centroid_y': cy, 'rms_radius': var.clamp(min=0.0).sqrt(),
+            'centroid_x': cx, 'centroid_y': cy, 'rms_radius': sqrt0(var),
             'min_x': s[:, 10], 'max_x': s[:, 11], 'min_y': s[:, 12], 'max_y': s[:, 13],
             'mean_op': s[:, 14]/n}
 
