@@ -78,6 +78,7 @@ struct rt_table {
     size_t stage_bytes;      /* shared memory needed to stage the table */
     bool stage;              /* false: table too large, read it from global/L1 */
     bool lean;               /* all interfaces quadric, unrotated, max_aperture clipping only */
+    bool lean_poly;          /* lean, with polynomial / toroid profiles (out-of-line Newton) */
     bool wave_ok;            /* interface n_ifc-2 carries no decenter: OPD epilogue applicable */
     size_t lean_bytes;       /* shared memory of the lean plan */
 };
@@ -358,8 +359,8 @@ k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restri
 }
 
 /* ---- lean kernels: plan built in shared memory by the CTA (rt_lean.cuh) */
-template <int OUT>
-__global__ void __launch_bounds__(RT_BLOCK, RT_LEAN_MIN_CTAS)
+template <int OUT, bool POLY>
+__global__ void __launch_bounds__(RT_BLOCK, POLY ? 2 : RT_LEAN_MIN_CTAS)
 k_trace_bundle_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
                     int n_ifc, int n_wvl, int64_t n_rays,
                     const double *__restrict__ px, const double *__restrict__ py,
@@ -380,13 +381,13 @@ k_trace_bundle_lean(const rt_surface_desc *__restrict__ g_surfs, const double *_
         const int w = wvl_idx ? wvl_idx[r] : o.wvl_idx;
         FullWriter fw = {OUT == 2 ? out.full + r : nullptr, out.full_stride};
         RayResult R;
-        trace_ray_lean<OUT>(ls, li + (int64_t)w*n_ifc, n_ifc, o, p0, d0, fw, R);
+        trace_ray_lean<OUT, false, POLY>(ls, li + (int64_t)w*n_ifc, g_surfs, n_ifc, o, p0, d0, fw, R);
         store_result(out, r, R);
     }
 }
 
-template <int OUT, bool SUMMARY, bool WAVE>
-__global__ void __launch_bounds__(RT_BLOCK, RT_LEAN_MIN_CTAS)
+template <int OUT, bool SUMMARY, bool WAVE, bool POLY>
+__global__ void __launch_bounds__(RT_BLOCK, POLY ? 2 : RT_LEAN_MIN_CTAS)
 k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
                   int n_ifc, int n_wvl, GridDev G, int64_t chunk_begin, int64_t chunk_end,
                   rt_opts o, rt_out out, double *__restrict__ scratch)
@@ -402,7 +403,7 @@ k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__r
             Vec3 p0;
             grid_start_ray<true>(G, f, loc, p0, d0);
             FullWriter fw = {OUT == 2 ? out.full + k : nullptr, out.full_stride};
-            trace_ray_lean<OUT, WAVE>(ls, li + (int64_t)G.wvl_idx[w]*n_ifc, n_ifc, o, p0, d0, fw, R);
+            trace_ray_lean<OUT, WAVE, POLY>(ls, li + (int64_t)G.wvl_idx[w]*n_ifc, g_surfs, n_ifc, o, p0, d0, fw, R);
         });
 }
 
@@ -610,13 +611,13 @@ static int launch_grid(const rt_table *t, const rt_grid *g, const GridDev &G, in
     return RT_OK;
 }
 
-template <int OUT>
-static int launch_bundle_lean(const rt_table *t, int64_t n_rays, const double *px, const double *py,
+template <int OUT, bool POLY>
+static int launch_bundle_lean_(const rt_table *t, int64_t n_rays, const double *px, const double *py,
                               const double *pz, const double *dx, const double *dy, const double *dz,
                               const int32_t *wvl_idx, const rt_opts *o, const rt_out *out,
                               cudaStream_t stream)
 {
-    auto kern = k_trace_bundle_lean<OUT>;
+    auto kern = k_trace_bundle_lean<OUT, POLY>;
     const size_t smem = t->lean_bytes;
     int rc = prep_kernel(kern, smem);
     if (rc) return rc;
@@ -630,11 +631,11 @@ static int launch_bundle_lean(const rt_table *t, int64_t n_rays, const double *p
     return RT_OK;
 }
 
-template <int OUT, bool SUMMARY, bool WAVE = false>
-static int launch_grid_lean(const rt_table *t, const GridDev &G, int64_t cb, int64_t ce,
+template <int OUT, bool SUMMARY, bool WAVE, bool POLY>
+static int launch_grid_lean_(const rt_table *t, const GridDev &G, int64_t cb, int64_t ce,
                             const rt_opts *o, const rt_out *out, double *scratch, cudaStream_t stream)
 {
-    auto kern = k_trace_grid_lean<OUT, SUMMARY, WAVE>;
+    auto kern = k_trace_grid_lean<OUT, SUMMARY, WAVE, POLY>;
     const size_t smem = t->lean_bytes + (SUMMARY ? RT_ACC_BYTES : 0);
     int rc = prep_kernel(kern, smem);
     if (rc) return rc;
@@ -646,6 +647,25 @@ static int launch_grid_lean(const rt_table *t, const GridDev &G, int64_t cb, int
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return RT_OK;
+}
+
+template <int OUT>
+static int launch_bundle_lean(const rt_table *t, int64_t n_rays, const double *px, const double *py,
+                              const double *pz, const double *dx, const double *dy, const double *dz,
+                              const int32_t *wvl_idx, const rt_opts *o, const rt_out *out,
+                              cudaStream_t stream)
+{
+    return t->lean_poly
+        ? launch_bundle_lean_<OUT, true>(t, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o, out, stream)
+        : launch_bundle_lean_<OUT, false>(t, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o, out, stream);
+}
+
+template <int OUT, bool SUMMARY, bool WAVE = false>
+static int launch_grid_lean(const rt_table *t, const GridDev &G, int64_t cb, int64_t ce,
+                            const rt_opts *o, const rt_out *out, double *scratch, cudaStream_t stream)
+{
+    return t->lean_poly ? launch_grid_lean_<OUT, SUMMARY, WAVE, true>(t, G, cb, ce, o, out, scratch, stream)
+                        : launch_grid_lean_<OUT, SUMMARY, WAVE, false>(t, G, cb, ce, o, out, scratch, stream);
 }
 
 /* 0: p,d only; 1: + normal/dst; 2: whole ray */
@@ -690,9 +710,11 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
     t->stage = t->stage_bytes <= RT_MAX_STAGE_BYTES - RT_ACC_BYTES;
     t->lean_bytes = (size_t)n_ifc*sizeof(LeanSurf) + (size_t)n_ifc*n_wvl*sizeof(LeanIdx);
     t->lean = t->lean_bytes <= RT_MAX_STAGE_BYTES - RT_ACC_BYTES;
+    t->lean_poly = false;
     for (int i = 0; i < n_ifc; i++) {
         const rt_surface_desc &s = surfs[i];
-        if (s.profile > RT_PROFILE_CONIC || s.has_tfrm != 0 || s.n_apertures != 0) t->lean = false;
+        if (s.has_tfrm != 0 || s.n_apertures != 0) t->lean = false;
+        if (s.profile > RT_PROFILE_CONIC) t->lean_poly = true;
     }
     if (getenv("B200RT_NO_LEAN")) t->lean = false;
     {
