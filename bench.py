@@ -383,13 +383,20 @@ def run_b200(args):
         except Exception:
             pass
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        traffic = None
+        try:     # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+            if args.model == 'dblgauss' and args.num == 512:
+                traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_dblgauss_512.json')))[
+                    'dram_bytes_per_launch']
+        except Exception:
+            pass
         ach_gbs = n_rays*bpr/(kern_ms*1e-3)/1e9
         ach_tf = flops/(kern_ms*1e-3)/1e12
         roof = {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': ach_gbs/hbm_peak,
                 'peak_source': 'MEASURED_PEAKS.json (of measured)' if 'hbm_gbs' in peaks
                 else 'B200_PROFILING.md fallback (of fallback)',
-                'traffic': None, 'bytes_per_ray': bpr, 'kernel': 'k_trace_grid_lean<0,1>',
+                'traffic': traffic, 'bytes_per_ray': bpr, 'kernel': 'k_trace_grid_lean<0,1>',
                 'kernel_ms': kern_ms,
                 'limiter': 'fp64 vector pipe (kernel is register-resident; HBM only receives results)',
                 'fp64': {'achieved_tflops': ach_tf, 'peak_tflops': fp64_peak,

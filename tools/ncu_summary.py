@@ -78,6 +78,16 @@ def main():
         lines.append(f'| total | {tot} | |')
     open(dst, 'w').write('\n'.join(lines) + '\n')
     print('wrote', dst)
+    # per-launch DRAM traffic of the first kernel, for bench.py's roofline.traffic
+    if len(sys.argv) > 3:
+        import json
+        d = dict(zip(hdr, raw[2]))
+        scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        tr = sum(float(d[k])*scale[units[hdr.index(k)]] for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+        json.dump({'kernel': d.get('Kernel Name', '?'), 'dram_bytes_per_launch': tr,
+                   'source': rep.split('/')[-1] + ' (ncu --set full, one launch)'},
+                  open(sys.argv[3], 'w'), indent=1)
+        print('wrote', sys.argv[3])
 
 
 if __name__ == '__main__':
