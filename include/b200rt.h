@@ -58,7 +58,14 @@ enum rt_profile {
     RT_PROFILE_EVENPOLY = 2,   /* profiles.py:682-889 */
     RT_PROFILE_RADIALPOLY = 3, /* profiles.py:891-1116 */
     RT_PROFILE_YTOROID = 4,    /* profiles.py:1119-1372 */
-    RT_PROFILE_XTOROID = 5     /* profiles.py:1375-1437 */
+    RT_PROFILE_XTOROID = 5,    /* profiles.py:1375-1437 */
+    RT_PROFILE_THINLENS = 6    /* oprops/thinlens.py:130-137: plane z=0, normal (0,0,1) */
+};
+
+/* phase elements (Interface.phase_element), src/rayoptics/oprops/doe.py */
+enum rt_phase {
+    RT_PHASE_NONE = 0,
+    RT_PHASE_HOE = 1           /* HolographicElement, doe.py:326-395 (also every ThinLens) */
 };
 
 /* Interface.interact_mode, src/rayoptics/seq/interface.py:42-49 */
@@ -75,7 +82,7 @@ enum rt_status {
     RT_RAY_MISSED = 1,     /* TraceMissedSurfaceError */
     RT_RAY_TIR = 2,        /* TraceTIRError */
     RT_RAY_BLOCKED = 3,    /* TraceRayBlockedError */
-    RT_RAY_EVANESCENT = 4, /* TraceEvanescentRayError (phase elements; never produced in v1) */
+    RT_RAY_EVANESCENT = 4, /* TraceEvanescentRayError (phase element: sqrt of a negative, raytrace.py:41-48) */
     RT_RAY_NUMERIC = 5     /* the reference would raise an uncaught ValueError /
                               ZeroDivisionError (sqrt of a negative in
                               EvenPolynomial.df, profiles.py:870-873) */
@@ -120,6 +127,12 @@ typedef struct rt_surface_desc {
     double rt[9];         /* Tfrm[0], row-major: applied as rt . (p - t) on the way to the NEXT interface */
     double t[3];          /* Tfrm[1] */
     rt_aperture_desc apertures[RT_MAX_APERTURES];
+    /* phase element (hasattr(ifc, 'phase_element'), raytrace.py:205-210) */
+    int32_t phase_kind;   /* rt_phase */
+    int32_t phase_flags;  /* HOE: bit 0 ref_virtual, bit 1 obj_virtual */
+    double phase_ref_wl;  /* HOE ref_wl (nm) */
+    double phase_ref_pt[3];
+    double phase_obj_pt[3];
 } rt_surface_desc;
 
 /* keyword arguments of trace_raw(), raytrace.py:83-121 */
@@ -171,6 +184,9 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc,
                     int32_t device, rt_table **out);
 int rt_table_destroy(rt_table *table);
 int rt_table_dims(const rt_table *table, int32_t *n_ifc, int32_t *n_wvl, int32_t *device);
+/* wavelengths (nm) of the rows of n_by_wvl: needed only by phase elements (mu = wvl/ref_wl,
+ * doe.py:384).  wvl_nm: HOST [n_wvl]. */
+int rt_table_set_wavelengths(rt_table *table, const double *wvl_nm);
 
 /* ---- bundle trace: replaces a Python loop over rt.trace()/trace_raw()
  * (raytrace.py:51-264; callers raytr/trace.py:250,310; analyses.py:458-510).

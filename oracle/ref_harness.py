@@ -82,6 +82,17 @@ def ref_profile(prf):
 
 
 def ref_surface(ifc):
+    if type(ifc).__name__ == 'ThinLens':
+        import importlib
+        TL = importlib.import_module('rayoptics.oprops.thinlens')
+        DOE = importlib.import_module('rayoptics.oprops.doe')
+        pe = ifc.phase_element
+        t = TL.ThinLens(power=ifc.optical_power, ref_index=ifc.ref_index, max_ap=ifc.max_aperture)
+        t.interact_mode = ifc.interact_mode
+        t.phase_element = DOE.HolographicElement(ref_pt=np.array(pe.ref_pt), ref_virtual=pe.ref_virtual,
+                                                 obj_pt=np.array(pe.obj_pt), obj_virtual=pe.obj_virtual,
+                                                 ref_wl=pe.ref_wl)
+        return t
     S = ref().surface
     s = S.Surface(profile=ref_profile(ifc.profile), interact_mode=ifc.interact_mode,
                   max_ap=ifc.max_aperture)

@@ -296,6 +296,12 @@ static int ifc_intersect(const rt_surface_desc *S, const double p[3], const doub
 {
     int st;
     switch (S->profile) {
+    case RT_PROFILE_THINLENS: {             /* oprops/thinlens.py:133-136 */
+        double s1 = -p[2]/d[2];
+        *s = s1;
+        p1[0] = p[0] + s1*d[0]; p1[1] = p[1] + s1*d[1]; p1[2] = p[2] + s1*d[2];
+        return ST_OK;
+    }
     case RT_PROFILE_SPHERICAL: {            /* profiles.py:310-336 */
         double ax2 = S->cv;
         double cx2 = S->cv*dot3(p, p) - 2*p[2];
@@ -322,6 +328,10 @@ static int ifc_intersect(const rt_surface_desc *S, const double p[3], const doub
 static int ifc_normal(const rt_surface_desc *S, const double p[3], double n[3])
 {
     double g[3];
+    if (S->profile == RT_PROFILE_THINLENS) {    /* oprops/thinlens.py:130-131 */
+        n[0] = 0.; n[1] = 0.; n[2] = 1.;
+        return ST_OK;
+    }
     int st = prof_df(S, p, g);
     if (st) return st;
     normalize3(g, n);
@@ -376,6 +386,36 @@ static inline void apply_tfrm(const rt_surface_desc *S, const double p[3], const
     }
 }
 
+/* HolographicElement.phase (oprops/doe.py:372-395); returns ST_OK or
+ * RT_RAY_EVANESCENT where math.sqrt raises (raytrace.py:41-48) */
+static int hoe_phase(const rt_surface_desc *S, const double pt[3], const double in_dir[3],
+                     const double srf_nrml[3], double z_dir, double wvl, double out_dir[3])
+{
+    double normal[3], ref_dir[3], obj_dir[3], v[3];
+    normalize3(srf_nrml, normal);
+    for (int c = 0; c < 3; c++) v[c] = pt[c] - S->phase_ref_pt[c];
+    normalize3(v, ref_dir);
+    if (S->phase_flags & 1) for (int c = 0; c < 3; c++) ref_dir[c] = -ref_dir[c];
+    double ref_cosI = dot3(ref_dir, normal);
+    for (int c = 0; c < 3; c++) v[c] = pt[c] - S->phase_obj_pt[c];
+    normalize3(v, obj_dir);
+    if (S->phase_flags & 2) for (int c = 0; c < 3; c++) obj_dir[c] = -obj_dir[c];
+    double obj_cosI = dot3(obj_dir, normal);
+    double in_cosI = dot3(in_dir, normal);
+    double mu = wvl/S->phase_ref_wl;
+    double b = in_cosI + mu*(obj_cosI - ref_cosI);
+    double refp_cosI = dot3(ref_dir, in_dir);
+    double objp_cosI = dot3(obj_dir, in_dir);
+    double ro_cosI = dot3(ref_dir, obj_dir);
+    double c_ = mu*(mu*(1.0 - ro_cosI) + (objp_cosI - refp_cosI));
+    double rad = b*b - 2*c_;
+    if (rad < 0.0) return RT_RAY_EVANESCENT;
+    double Q = -b + z_dir*sqrt(rad);
+    for (int c = 0; c < 3; c++)
+        out_dir[c] = in_dir[c] + mu*(obj_dir[c] - ref_dir[c]) + Q*normal[c];
+    return ST_OK;
+}
+
 static inline void put_seg(double *ray, int k, const double p[3], const double d[3],
                            double dst, const double n[3])
 {
@@ -391,7 +431,7 @@ static inline void put_seg(double *ray, int k, const double p[3], const double d
  *  n_row[i]  : refractive index following interface i (path tuple Indx)
  *  ray       : [n_ifc][RT_SEG_DOUBLES] or NULL
  *  last      : [RT_SEG_DOUBLES] copy of ray[-1] or NULL                       */
-int rto_trace_ray(const rt_surface_desc *surfs, int32_t n_ifc, const double *n_row,
+int rto_trace_ray(const rt_surface_desc *surfs, int32_t n_ifc, const double *n_row, double wvl,
                   const double pt0[3], const double dir0[3], const rt_opts *o,
                   double *ray, double *last, int32_t *n_seg_out, double *op_out,
                   int32_t *status_out, int32_t *fail_surf_out)
@@ -480,7 +520,18 @@ int rto_trace_ray(const rt_surface_desc *surfs, int32_t n_ifc, const double *n_r
             }
         }
 
-        if (ifc->mode == RT_MODE_REFLECT) {
+        if (ifc->phase_kind == RT_PHASE_HOE) {
+            /* raytrace.py:205-210: the phase element sets after_dir (phs = 0 for a HOE) */
+            st = hoe_phase(ifc, inc_pt, b4_dir, normal, z_dir_before, wvl, after_dir);
+            if (st) {
+                /* TraceEvanescentRayError, raytrace.py:253-257 */
+                put_seg(ray, n_seg, inc_pt, before_dir, 0.0, normal);
+                put_seg(lseg, 0, inc_pt, before_dir, 0.0, normal);
+                n_seg++;
+                status = st; fail_surf = surf;
+                goto done;
+            }
+        } else if (ifc->mode == RT_MODE_REFLECT) {
             /* reflect, raytrace.py:33-38 */
             double normal_len = sqrt(dot3(normal, normal));
             double cosI = dot3(b4_dir, normal)/normal_len;
@@ -543,6 +594,7 @@ done:
 typedef struct {
     const rt_surface_desc *surfs; int32_t n_ifc; const double *n_by_wvl; int64_t n_rays;
     const double *px, *py, *pz, *dx, *dy, *dz; const int32_t *wvl_idx; const rt_opts *o;
+    const double *wvl_nm;
     double *last, *full; int64_t full_stride;
     double *op; int32_t *status, *fail_surf, *n_seg;
     int64_t r0, r1;
@@ -559,8 +611,8 @@ static void *bundle_worker(void *arg)
         int w = J->wvl_idx ? J->wvl_idx[r] : J->o->wvl_idx;
         int32_t ns, st, fs;
         double opl;
-        rto_trace_ray(J->surfs, n_ifc, J->n_by_wvl + (size_t)w*n_ifc, p0, d0, J->o,
-                      J->full ? ray : NULL, lseg, &ns, &opl, &st, &fs);
+        rto_trace_ray(J->surfs, n_ifc, J->n_by_wvl + (size_t)w*n_ifc, J->wvl_nm ? J->wvl_nm[w] : NAN,
+                      p0, d0, J->o, J->full ? ray : NULL, lseg, &ns, &opl, &st, &fs);
         if (J->op) J->op[r] = opl;
         if (J->status) J->status[r] = st;
         if (J->fail_surf) J->fail_surf[r] = fs;
@@ -580,7 +632,7 @@ int rto_trace_bundle(const rt_surface_desc *surfs, int32_t n_ifc, const double *
                      int64_t n_rays,
                      const double *px, const double *py, const double *pz,
                      const double *dx, const double *dy, const double *dz,
-                     const int32_t *wvl_idx, const rt_opts *o,
+                     const int32_t *wvl_idx, const rt_opts *o, const double *wvl_nm,
                      double *last, double *full, int64_t full_stride,
                      double *op, int32_t *status, int32_t *fail_surf, int32_t *n_seg,
                      int32_t n_threads)
@@ -591,7 +643,7 @@ int rto_trace_bundle(const rt_surface_desc *surfs, int32_t n_ifc, const double *
     pthread_t tids[256];
     int64_t per = (n_rays + n_threads - 1)/n_threads;
     for (int t = 0; t < n_threads; t++) {
-        bundle_job J = {surfs, n_ifc, n_by_wvl, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o,
+        bundle_job J = {surfs, n_ifc, n_by_wvl, n_rays, px, py, pz, dx, dy, dz, wvl_idx, o, wvl_nm,
                         last, full, full_stride, op, status, fail_surf, n_seg, 0, 0};
         J.r0 = t*per; J.r1 = (t + 1)*per;
         if (J.r0 > n_rays) J.r0 = n_rays;
@@ -695,7 +747,7 @@ double rto_wave_opd(const double *W, const double p1[3], const double d0[3],
 typedef struct {
     const rt_grid_spec *g; const rt_surface_desc *surfs; int32_t n_ifc; const double *n_by_wvl;
     const rt_opts *o; int64_t ray_begin, n; int64_t r0, r1;
-    double *last, *op, *abr_x, *abr_y, *opd; int32_t *status, *fail_surf;
+    double *last, *op, *abr_x, *abr_y, *opd; int32_t *status, *fail_surf; const double *wvl_nm;
 } grid_job;
 
 static void *grid_worker(void *arg)
@@ -710,8 +762,8 @@ static void *grid_worker(void *arg)
         rto_grid_start_rays(g, r, r + 1, &px, &py, &pz, &dx, &dy, &dz, &w, NULL, NULL);
         double p0[3] = {px, py, pz}, d0[3] = {dx, dy, dz}, lseg[RT_SEG_DOUBLES], opl;
         int32_t ns, st, fs;
-        rto_trace_ray(J->surfs, J->n_ifc, J->n_by_wvl + (size_t)w*J->n_ifc, p0, d0, J->o,
-                      ray, lseg, &ns, &opl, &st, &fs);
+        rto_trace_ray(J->surfs, J->n_ifc, J->n_by_wvl + (size_t)w*J->n_ifc,
+                      J->wvl_nm ? J->wvl_nm[w] : NAN, p0, d0, J->o, ray, lseg, &ns, &opl, &st, &fs);
         int64_t k = r - J->ray_begin;
         if (J->opd) {
             const double *s1 = ray + RT_SEG_DOUBLES, *sk = ray + (size_t)(J->n_ifc - 2)*RT_SEG_DOUBLES;
@@ -738,7 +790,7 @@ static void *grid_worker(void *arg)
 int rto_trace_grid(const rt_grid_spec *g, const rt_surface_desc *surfs, int32_t n_ifc,
                    const double *n_by_wvl, int64_t ray_begin, int64_t ray_end, const rt_opts *o,
                    double *last, double *op, int32_t *status, int32_t *fail_surf,
-                   double *abr_x, double *abr_y, double *opd, int32_t n_threads)
+                   double *abr_x, double *abr_y, double *opd, const double *wvl_nm, int32_t n_threads)
 {
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 256) n_threads = 256;
@@ -747,7 +799,7 @@ int rto_trace_grid(const rt_grid_spec *g, const rt_surface_desc *surfs, int32_t 
     int64_t n = ray_end - ray_begin, per = (n + n_threads - 1)/n_threads;
     for (int t = 0; t < n_threads; t++) {
         grid_job J = {g, surfs, n_ifc, n_by_wvl, o, ray_begin, n, 0, 0, last, op, abr_x, abr_y,
-                      (opd && g->wave) ? opd : NULL, status, fail_surf};
+                      (opd && g->wave) ? opd : NULL, status, fail_surf, wvl_nm};
         J.r0 = ray_begin + t*per; J.r1 = J.r0 + per;
         if (J.r0 > ray_end) J.r0 = ray_end;
         if (J.r1 > ray_end) J.r1 = ray_end;

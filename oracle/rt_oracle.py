@@ -42,7 +42,7 @@ def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
 
 
-def trace_ray(descs, n_row, pt0, dir0, opts):
+def trace_ray(descs, n_row, pt0, dir0, opts, wvl=float('nan')):
     """One ray -> dict(ray [n_seg,10], op, status, fail_surf)."""
     n_ifc = len(descs)
     n_row = np.ascontiguousarray(n_row, dtype=np.float64)
@@ -52,13 +52,13 @@ def trace_ray(descs, n_row, pt0, dir0, opts):
     d0 = np.ascontiguousarray(dir0, dtype=np.float64)
     n_seg, st, fs = C.c_int32(), C.c_int32(), C.c_int32()
     op = C.c_double()
-    lib().rto_trace_ray(descs, C.c_int32(n_ifc), _dp(n_row), _dp(p0), _dp(d0), C.byref(opts),
+    lib().rto_trace_ray(descs, C.c_int32(n_ifc), _dp(n_row), C.c_double(wvl), _dp(p0), _dp(d0), C.byref(opts),
                         _dp(ray), _dp(last), C.byref(n_seg), C.byref(op), C.byref(st), C.byref(fs))
     return {'ray': ray[:n_seg.value].copy(), 'last': last, 'op': op.value,
             'status': st.value, 'fail_surf': fs.value, 'n_seg': n_seg.value}
 
 
-def trace_bundle(descs, n_by_wvl, p, d, wvl_idx, opts, want_full=False, n_threads=1):
+def trace_bundle(descs, n_by_wvl, p, d, wvl_idx, opts, want_full=False, n_threads=1, wvls=None):
     """p, d: [3, n] arrays.  Returns dict of SoA numpy arrays like rt_out."""
     n_ifc = len(descs)
     n = p.shape[1]
@@ -66,6 +66,7 @@ def trace_bundle(descs, n_by_wvl, p, d, wvl_idx, opts, want_full=False, n_thread
     p = np.ascontiguousarray(p, dtype=np.float64)
     d = np.ascontiguousarray(d, dtype=np.float64)
     wv = None if wvl_idx is None else np.ascontiguousarray(wvl_idx, dtype=np.int32)
+    wl = None if wvls is None else np.ascontiguousarray(wvls, dtype=np.float64)
     last = np.zeros((RT_SEG_DOUBLES, n))
     full = np.full((n_ifc, RT_SEG_DOUBLES, n), np.nan) if want_full else None
     op = np.zeros(n)
@@ -74,7 +75,7 @@ def trace_bundle(descs, n_by_wvl, p, d, wvl_idx, opts, want_full=False, n_thread
     n_seg = np.zeros(n, dtype=np.int32)
     lib().rto_trace_bundle(descs, C.c_int32(n_ifc), _dp(n_by_wvl), C.c_int64(n),
                            _dp(p[0]), _dp(p[1]), _dp(p[2]), _dp(d[0]), _dp(d[1]), _dp(d[2]),
-                           _ip(wv), C.byref(opts), _dp(last), _dp(full), C.c_int64(n),
+                           _ip(wv), C.byref(opts), _dp(wl), _dp(last), _dp(full), C.c_int64(n),
                            _dp(op), _ip(status), _ip(fail_surf), _ip(n_seg), C.c_int32(n_threads))
     return {'last': last, 'full': full, 'op': op, 'status': status,
             'fail_surf': fail_surf, 'n_seg': n_seg}
@@ -103,7 +104,7 @@ def transverse_abr(px, py, dx, dy, dz, foc, ref_x, ref_y):
 
 
 def trace_grid(spec: rt_grid_spec, descs, n_by_wvl, ray_begin, ray_end, opts, n_threads=1,
-               want_last=True):
+               want_last=True, wvls=None):
     """Whole grid on the host (start rays + trace + transverse aberration)."""
     n = ray_end - ray_begin
     n_by_wvl = np.ascontiguousarray(n_by_wvl, dtype=np.float64)
@@ -113,10 +114,11 @@ def trace_grid(spec: rt_grid_spec, descs, n_by_wvl, ray_begin, ray_end, opts, n_
     fail_surf = np.zeros(n, dtype=np.int32)
     ax, ay = np.zeros(n), np.zeros(n)
     opd = np.full(n, np.nan) if bool(spec.wave) else None
+    wl = None if wvls is None else np.ascontiguousarray(wvls, dtype=np.float64)
     lib().rto_trace_grid(C.byref(spec), descs, C.c_int32(len(descs)), _dp(n_by_wvl),
                          C.c_int64(ray_begin), C.c_int64(ray_end), C.byref(opts),
                          _dp(last), _dp(op), _ip(status), _ip(fail_surf), _dp(ax), _dp(ay),
-                         _dp(opd), C.c_int32(n_threads))
+                         _dp(opd), _dp(wl), C.c_int32(n_threads))
     return {'last': last, 'op': op, 'status': status, 'fail_surf': fail_surf,
             'abr': np.stack([ax, ay]), 'opd': opd}
 

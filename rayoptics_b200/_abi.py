@@ -18,7 +18,8 @@ RT_WAVE_DOUBLES = 24
 
 # enum rt_profile
 PROFILE_IDS = {'Spherical': 0, 'Conic': 1, 'EvenPolynomial': 2,
-               'RadialPolynomial': 3, 'YToroid': 4, 'XToroid': 5}
+               'RadialPolynomial': 3, 'YToroid': 4, 'XToroid': 5, 'ThinLens': 6}
+PHASE_IDS = {'HolographicElement': 1}
 # enum rt_mode
 MODE_IDS = {'transmit': 0, 'reflect': 1, 'dummy': 2, 'phantom': 3}
 # enum rt_status
@@ -43,7 +44,10 @@ class rt_surface_desc(C.Structure):
                 ('max_aperture', C.c_double),
                 ('coefs', C.c_double*RT_MAX_COEFS),
                 ('rt', C.c_double*9), ('t', C.c_double*3),
-                ('apertures', rt_aperture_desc*RT_MAX_APERTURES)]
+                ('apertures', rt_aperture_desc*RT_MAX_APERTURES),
+                ('phase_kind', C.c_int32), ('phase_flags', C.c_int32),
+                ('phase_ref_wl', C.c_double),
+                ('phase_ref_pt', C.c_double*3), ('phase_obj_pt', C.c_double*3)]
 
 
 class rt_opts(C.Structure):
@@ -96,7 +100,7 @@ def make_opts(eps=1.0e-12, check_apertures=False, intersect_obj=True,
 
 
 LIB_NAME = 'libb200rt.so'
-EXPORTS = ['rt_table_create', 'rt_table_destroy', 'rt_table_dims',
+EXPORTS = ['rt_table_create', 'rt_table_destroy', 'rt_table_dims', 'rt_table_set_wavelengths',
            'rt_trace_bundle', 'rt_grid_create', 'rt_grid_destroy', 'rt_grid_dims',
            'rt_grid_scratch_bytes', 'rt_trace_grid',
            'rt_last_error', 'rt_abi_version', 'rt_launch_count', 'rt_measure_fp64_peak',
@@ -134,6 +138,8 @@ def load_library():
                                     C.POINTER(vp)]
     lib.rt_table_destroy.argtypes = [vp]
     lib.rt_table_dims.argtypes = [vp, c_int32_p, c_int32_p, c_int32_p]
+    lib.rt_table_set_wavelengths.argtypes = [vp, c_double_p]
+    lib.rt_table_set_wavelengths.restype = i32
     lib.rt_trace_bundle.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp,
                                     C.POINTER(rt_opts), C.POINTER(rt_out), vp]
     lib.rt_grid_create.argtypes = [C.POINTER(rt_grid_spec), i32, C.POINTER(vp)]

@@ -19,6 +19,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -75,6 +76,8 @@ struct rt_table {
     int32_t device, n_ifc, n_wvl, sm_count;
     rt_surface_desc *d_surfs;
     double *d_n;
+    double *d_wvl;           /* [n_wvl] wavelengths in nm (NaN until rt_table_set_wavelengths) */
+    bool has_phase;
     size_t stage_bytes;      /* shared memory needed to stage the table */
     bool stage;              /* false: table too large, read it from global/L1 */
     bool lean;               /* all interfaces quadric, unrotated, max_aperture clipping only */
@@ -149,7 +152,8 @@ k_trace_bundle(const rt_surface_desc *__restrict__ g_surfs, const double *__rest
                const double *__restrict__ px, const double *__restrict__ py,
                const double *__restrict__ pz, const double *__restrict__ dx,
                const double *__restrict__ dy, const double *__restrict__ dz,
-               const int32_t *__restrict__ wvl_idx, rt_opts o, rt_out out)
+               const int32_t *__restrict__ wvl_idx, rt_opts o, rt_out out,
+               const double *__restrict__ g_wvl)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const rt_surface_desc *tab;
@@ -163,7 +167,7 @@ k_trace_bundle(const rt_surface_desc *__restrict__ g_surfs, const double *__rest
         const int w = wvl_idx ? wvl_idx[r] : o.wvl_idx;
         FullWriter fw = {FULL ? out.full + r : nullptr, out.full_stride};
         RayResult R;
-        trace_ray<FULL>(tab, ntab + (int64_t)w*n_ifc, n_ifc, o, p0, d0, fw, R);
+        trace_ray<FULL>(tab, ntab + (int64_t)w*n_ifc, g_wvl[w], n_ifc, o, p0, d0, fw, R);
         store_result(out, r, R);
     }
 }
@@ -342,7 +346,7 @@ template <bool FULL, bool SUMMARY, bool STAGE, bool WAVE>
 __global__ void __launch_bounds__(RT_BLOCK)
 k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
              int n_ifc, int n_wvl, GridDev G, int64_t chunk_begin, int64_t chunk_end,
-             rt_opts o, rt_out out, double *__restrict__ scratch)
+             rt_opts o, rt_out out, double *__restrict__ scratch, const double *__restrict__ g_wvl)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const rt_surface_desc *tab;
@@ -354,7 +358,8 @@ k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restri
             Vec3 p0;
             grid_start_ray<false>(G, f, loc, p0, d0);
             FullWriter fw = {FULL ? out.full + k : nullptr, out.full_stride};
-            trace_ray<FULL, WAVE>(tab, ntab + (int64_t)G.wvl_idx[w]*n_ifc, n_ifc, o, p0, d0, fw, R);
+            const int wi = G.wvl_idx[w];
+            trace_ray<FULL, WAVE>(tab, ntab + (int64_t)wi*n_ifc, g_wvl[wi], n_ifc, o, p0, d0, fw, R);
         });
 }
 
@@ -587,7 +592,7 @@ static int launch_bundle(const rt_table *t, int64_t n_rays, const double *px, co
     rc = persistent_grid(kern, smem, t->sm_count, (n_rays + RT_BLOCK - 1)/RT_BLOCK, &grid);
     if (rc) return rc;
     kern<<<grid, RT_BLOCK, smem, stream>>>(t->d_surfs, t->d_n, t->n_ifc, t->n_wvl, n_rays,
-                                           px, py, pz, dx, dy, dz, wvl_idx, *o, *out);
+                                           px, py, pz, dx, dy, dz, wvl_idx, *o, *out, t->d_wvl);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return RT_OK;
@@ -605,7 +610,7 @@ static int launch_grid(const rt_table *t, const rt_grid *g, const GridDev &G, in
     rc = persistent_grid(kern, smem, t->sm_count, ce - cb, &grid);
     if (rc) return rc;
     kern<<<grid, RT_BLOCK, smem, stream>>>(t->d_surfs, t->d_n, t->n_ifc, t->n_wvl, G, cb, ce, *o, *out,
-                                           scratch);
+                                           scratch, t->d_wvl);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return RT_OK;
@@ -617,7 +622,7 @@ static int launch_bundle_lean_(const rt_table *t, int64_t n_rays, const double *
                               const int32_t *wvl_idx, const rt_opts *o, const rt_out *out,
                               cudaStream_t stream)
 {
-    auto kern = k_trace_bundle_lean<OUT, POLY>;
+    auto kern = k_trace_bundle_lean<OUT, POLY>;   /* (lean kernels: no phase elements, no wavelengths) */
     const size_t smem = t->lean_bytes;
     int rc = prep_kernel(kern, smem);
     if (rc) return rc;
@@ -690,13 +695,15 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
         return fail(RT_ERR_INVALID, "rt_table_create: bad arguments");
     for (int i = 0; i < n_ifc; i++) {
         const rt_surface_desc &s = surfs[i];
-        if (s.profile < RT_PROFILE_SPHERICAL || s.profile > RT_PROFILE_XTOROID)
+        if (s.profile < RT_PROFILE_SPHERICAL || s.profile > RT_PROFILE_THINLENS)
             return fail(RT_ERR_UNSUPPORTED, "rt_table_create: unknown profile id");
         if (s.mode < RT_MODE_TRANSMIT || s.mode > RT_MODE_PHANTOM)
             return fail(RT_ERR_UNSUPPORTED, "rt_table_create: unknown interact mode");
         if (s.n_coefs < 0 || s.n_coefs > RT_MAX_COEFS || s.n_apertures < 0 ||
             s.n_apertures > RT_MAX_APERTURES)
             return fail(RT_ERR_INVALID, "rt_table_create: coefficient / aperture count out of range");
+        if (s.phase_kind != RT_PHASE_NONE && s.phase_kind != RT_PHASE_HOE)
+            return fail(RT_ERR_UNSUPPORTED, "rt_table_create: unknown phase element kind");
     }
     DeviceGuard guard(device);
     cudaDeviceProp prop;
@@ -705,7 +712,7 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
     if (!t) return fail(RT_ERR_NOMEM, "rt_table_create: out of host memory");
     t->device = device; t->n_ifc = n_ifc; t->n_wvl = n_wvl;
     t->sm_count = prop.multiProcessorCount;
-    t->d_surfs = nullptr; t->d_n = nullptr;
+    t->d_surfs = nullptr; t->d_n = nullptr; t->d_wvl = nullptr; t->has_phase = false;
     t->stage_bytes = (size_t)n_ifc*sizeof(rt_surface_desc) + (size_t)n_ifc*n_wvl*sizeof(double);
     t->stage = t->stage_bytes <= RT_MAX_STAGE_BYTES - RT_ACC_BYTES;
     t->lean_bytes = (size_t)n_ifc*sizeof(LeanSurf) + (size_t)n_ifc*n_wvl*sizeof(LeanIdx);
@@ -714,6 +721,7 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
     for (int i = 0; i < n_ifc; i++) {
         const rt_surface_desc &s = surfs[i];
         if (s.has_tfrm != 0 || s.n_apertures != 0) t->lean = false;
+        if (s.phase_kind != RT_PHASE_NONE || s.profile == RT_PROFILE_THINLENS) { t->lean = false; t->has_phase = true; }
         if (s.profile > RT_PROFILE_CONIC) t->lean_poly = true;
     }
     if (getenv("B200RT_NO_LEAN")) t->lean = false;
@@ -727,8 +735,13 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
         e = cudaMemcpy(t->d_surfs, surfs, (size_t)n_ifc*sizeof(rt_surface_desc), cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
         e = cudaMemcpy(t->d_n, n_by_wvl, (size_t)n_ifc*n_wvl*sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_wvl, (size_t)n_wvl*sizeof(double));
+    if (e == cudaSuccess) {
+        std::vector<double> nanv((size_t)n_wvl, (double)NAN);
+        e = cudaMemcpy(t->d_wvl, nanv.data(), (size_t)n_wvl*sizeof(double), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
-        cudaFree(t->d_surfs); cudaFree(t->d_n); delete t;
+        cudaFree(t->d_surfs); cudaFree(t->d_n); cudaFree(t->d_wvl); delete t;
         return fail(RT_ERR_CUDA, "rt_table_create: %s", cudaGetErrorString(e));
     }
     *out = t;
@@ -741,7 +754,16 @@ int rt_table_destroy(rt_table *t)
     DeviceGuard guard(t->device);
     cudaFree(t->d_surfs);
     cudaFree(t->d_n);
+    cudaFree(t->d_wvl);
     delete t;
+    return RT_OK;
+}
+
+int rt_table_set_wavelengths(rt_table *t, const double *wvl_nm)
+{
+    if (!t || !wvl_nm) return fail(RT_ERR_INVALID, "rt_table_set_wavelengths: bad arguments");
+    DeviceGuard guard(t->device);
+    CUDA_TRY(cudaMemcpy(t->d_wvl, wvl_nm, (size_t)t->n_wvl*sizeof(double), cudaMemcpyHostToDevice));
     return RT_OK;
 }
 

@@ -37,7 +37,9 @@ def _matrix(sm, wi, first, last):
     for i in range(first, last):
         ifc = sm.ifcs[i]
         n_b, n_a = ns[i - 1], ns[i]
-        if ifc.interact_mode in ('transmit', 'reflect'):
+        if type(ifc).__name__ == 'ThinLens':
+            pwr = ifc.optical_power                 # oprops/thinlens.py:93-95
+        elif ifc.interact_mode in ('transmit', 'reflect'):
             pwr = (n_a - n_b)*ifc.profile.cv
         else:
             pwr, n_a = 0.0, n_b
@@ -80,7 +82,10 @@ def compute_first_order(sm, osp, wvl=None):
     Mlast = _matrix(sm, wi, 1, img - 1) if img - 1 >= 1 else np.identity(2)
     Rl = sm.ifcs[img - 1]
     n_b, n_a = ns[img - 2] if img - 2 >= 0 else n_0, ns[img - 1]
-    pwr_l = (n_a - n_b)*Rl.profile.cv if Rl.interact_mode in ('transmit', 'reflect') else 0.0
+    if type(Rl).__name__ == 'ThinLens':
+        pwr_l = Rl.optical_power
+    else:
+        pwr_l = (n_a - n_b)*Rl.profile.cv if Rl.interact_mode in ('transmit', 'reflect') else 0.0
     Mk = np.array([[1.0, 0.0], [-pwr_l, 1.0]]) @ Mlast   # to just after the last powered surface
     ck1, dk1, ak1 = Mk[1, 0], Mk[1, 1], Mk[0, 0]
     fod.power = -ck1

@@ -224,6 +224,65 @@ class Surface:
         return self
 
 
+class HolographicElement:
+    """Two-point hologram phase element: data mirror of oprops/doe.py:326-370."""
+
+    def __init__(self, label='', ref_pt=None, ref_virtual=False, obj_pt=None, obj_virtual=False,
+                 ref_wl=550.):
+        self.label = label
+        self.ref_pt = np.array([0., 0., -1e10]) if ref_pt is None else np.array(ref_pt, dtype=float)
+        self.ref_virtual = ref_virtual
+        self.obj_pt = np.array([0., 0., -1e10]) if obj_pt is None else np.array(obj_pt, dtype=float)
+        self.obj_virtual = obj_virtual
+        self.ref_wl = ref_wl
+
+    def to_dict(self):
+        return {'type': 'HolographicElement', 'label': self.label,
+                'ref_pt': self.ref_pt.tolist(), 'ref_virtual': bool(self.ref_virtual),
+                'obj_pt': self.obj_pt.tolist(), 'obj_virtual': bool(self.obj_virtual),
+                'ref_wl': self.ref_wl}
+
+    @classmethod
+    def from_dict(cls, d):
+        d = dict(d)
+        d.pop('type', None)
+        return cls(**d)
+
+
+class ThinLens:
+    """Thin lens interface (oprops/thinlens.py:17-140): a plane with a
+    HolographicElement whose object point encodes the power."""
+
+    def __init__(self, lbl='', power=0.0, ref_index=1.5, center_wvl=550., max_aperture=1.0,
+                 phase_element=None, interact_mode='transmit'):
+        self.label = lbl
+        self.interact_mode = interact_mode
+        self.max_aperture = max_aperture
+        self.ref_index = ref_index
+        self.decenter = None
+        self.delta_n = 0.0
+        self.phase_element = phase_element or HolographicElement(ref_wl=center_wvl)
+        self._power = power
+        if phase_element is None:
+            self.optical_power = power
+
+    @property
+    def optical_power(self):
+        return self._power
+
+    @optical_power.setter
+    def optical_power(self, pwr):          # thinlens.py:97-105
+        self._power = pwr
+        self.phase_element.obj_pt[2] = 1./pwr if pwr != 0 else 1e+10
+        self.phase_element.obj_virtual = True if pwr > 0. else False
+
+    def set_max_aperture(self, max_ap):
+        self.max_aperture = max_ap
+
+    def update(self):
+        return self
+
+
 # -------------------------------------------------------------------- media
 class Medium:
     """Refractive-index source of a gap: ``rindex(wvl_nm)``.
@@ -393,9 +452,14 @@ class SequentialModel:
         ifcs = []
         for i, ifc in enumerate(self.ifcs):
             e = {'label': ifc.label, 'mode': ifc.interact_mode,
-                 'max_aperture': ifc.max_aperture,
-                 'profile': ifc.profile.to_dict()}
-            if ifc.clear_apertures:
+                 'max_aperture': ifc.max_aperture}
+            if type(ifc).__name__ == 'ThinLens':
+                e['thin_lens'] = {'power': ifc.optical_power, 'ref_index': ifc.ref_index}
+            else:
+                e['profile'] = ifc.profile.to_dict()
+            if hasattr(ifc, 'phase_element'):
+                e['phase_element'] = ifc.phase_element.to_dict()
+            if getattr(ifc, 'clear_apertures', None):
                 e['clear_apertures'] = [ca.to_dict() for ca in ifc.clear_apertures]
             if i < len(self.gaps):
                 e['thi'] = self.gaps[i].thi
@@ -415,9 +479,18 @@ class SequentialModel:
         ifcs, gaps, z_dir, tfrms, any_tfrm = [], [], [], [], False
         n = len(d['ifcs'])
         for i, e in enumerate(d['ifcs']):
-            s = Surface(lbl=e.get('label', ''), profile=profile_from_dict(e['profile']),
-                        interact_mode=e['mode'], max_aperture=e.get('max_aperture', 1.0),
-                        clear_apertures=[aperture_from_dict(a) for a in e.get('clear_apertures', [])])
+            if 'thin_lens' in e:
+                s = ThinLens(lbl=e.get('label', ''), power=e['thin_lens']['power'],
+                             ref_index=e['thin_lens'].get('ref_index', 1.5),
+                             max_aperture=e.get('max_aperture', 1.0), interact_mode=e['mode'],
+                             phase_element=HolographicElement.from_dict(e['phase_element']))
+            else:
+                s = Surface(lbl=e.get('label', ''), profile=profile_from_dict(e['profile']),
+                            interact_mode=e['mode'], max_aperture=e.get('max_aperture', 1.0),
+                            clear_apertures=[aperture_from_dict(a)
+                                             for a in e.get('clear_apertures', [])])
+                if 'phase_element' in e:
+                    s.phase_element = HolographicElement.from_dict(e['phase_element'])
             ifcs.append(s)
             if i < n - 1:
                 gaps.append(Gap(e['thi'], medium_from_dict(e['medium'])))

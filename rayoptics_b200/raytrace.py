@@ -59,6 +59,14 @@ def set_device(device):
     _DEVICE = int(device)
 
 
+def _phase_fp(pe):
+    if pe is None:
+        return None
+    return (type(pe).__name__, tuple(map(float, getattr(pe, 'ref_pt', ()))),
+            tuple(map(float, getattr(pe, 'obj_pt', ()))), getattr(pe, 'ref_virtual', None),
+            getattr(pe, 'obj_virtual', None), getattr(pe, 'ref_wl', None))
+
+
 def _fingerprint(segs):
     fp = []
     for seg in segs:
@@ -69,21 +77,22 @@ def _fingerprint(segs):
                    getattr(prf, 'cR', None), None if coefs is None else tuple(coefs),
                    getattr(ifc, 'interact_mode', None), getattr(ifc, 'max_aperture', None),
                    len(getattr(ifc, 'clear_apertures', ()) or ()), n, z_dir,
+                   _phase_fp(getattr(ifc, 'phase_element', None)),
                    None if tfrm is None else (tfrm[0].tobytes() if hasattr(tfrm[0], 'tobytes')
                                               else repr(tfrm[0]), tuple(map(float, tfrm[1])))))
     return tuple(fp)
 
 
-def _table_for_path(segs):
+def _table_for_path(segs, wvl=None):
     """Surface table of a path, cached on its content (the reference clears its
     own path cache in update_model; here any change of the numbers the table is
     built from changes the fingerprint)."""
-    fp = _fingerprint(segs)
+    fp = (_fingerprint(segs), wvl)
     tab = _PATH_CACHE.get(fp)
     if tab is None:
         if len(_PATH_CACHE) > 64:
             _PATH_CACHE.clear()
-        tab = SurfaceTable.from_path(segs, device=_DEVICE)
+        tab = SurfaceTable.from_path(segs, device=_DEVICE, wvl=wvl)
         _PATH_CACHE[fp] = tab
     return tab
 
@@ -100,7 +109,7 @@ def trace_raw(path, pt0, dir0, wvl, eps=1.0e-12, check_apertures=False,
               intersect_obj=True, filter_out_phantoms=False, **kwargs):
     """fundamental raytrace function (raytrace.py:83-264) -- one ray on the GPU."""
     segs = list(path)
-    tab = _table_for_path(segs)
+    tab = _table_for_path(segs, wvl)
     first_surf = kwargs.get('first_surf', 0)
     last_surf = kwargs.get('last_surf', None)
     pt_inside_fuzz = kwargs.get('pt_inside_fuzz', None)

@@ -125,9 +125,19 @@ def open_roa(path):
     for i in sm_a['ifcs']:
         kind = i['__instance_type__'][1]
         a = i['attributes']
+        if kind == 'ThinLens':
+            pe = a['phase_element']['attributes']
+            hoe = M.HolographicElement(pe.get('label', ''), _val(pe['ref_pt']), pe['ref_virtual'],
+                                       _val(pe['obj_pt']), pe['obj_virtual'], pe['ref_wl'])
+            ifcs.append(M.ThinLens(lbl=a.get('label', ''), power=a['_power'],
+                                   ref_index=a.get('ref_index', 1.5),
+                                   max_aperture=a.get('max_aperture', 1.0),
+                                   interact_mode=a['interact_mode'], phase_element=hoe))
+            continue
         if kind != 'Surface':
-            raise NotImplementedError(f'.roa interface type {kind} (thin lens / phase elements '
-                                      f'are not traced by the B200 engine)')
+            raise NotImplementedError(f'.roa interface type {kind}')
+        if a.get('phase_element') is not None:
+            raise NotImplementedError('.roa surfaces with diffractive phase elements')
         if a.get('decenter') is not None:
             raise NotImplementedError('.roa decentered interfaces: supply lcl_tfrms explicitly')
         prf = a.get('profile')

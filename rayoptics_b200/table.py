@@ -16,7 +16,11 @@ import numpy as np
 
 from . import _abi
 from ._abi import (rt_surface_desc, RT_MAX_COEFS, RT_MAX_APERTURES,
-                   PROFILE_IDS, MODE_IDS, APERTURE_IDS)
+                   PROFILE_IDS, MODE_IDS, APERTURE_IDS, PHASE_IDS)
+
+
+class _ThinLensProfile:
+    cv = 0.0
 
 
 class UnsupportedInterfaceError(NotImplementedError):
@@ -28,10 +32,22 @@ def _describe_interface(seg, prev_n, prev_zdir):
     ifc, _gap, tfrm, n, z_dir = (tuple(seg) + (None,)*5)[:5]
     d = rt_surface_desc()
     if hasattr(ifc, 'phase_element'):   # same test as raytrace.py:205
-        raise UnsupportedInterfaceError(
-            f'{type(ifc).__name__} with a phase element is not supported by the B200 table')
+        pe = ifc.phase_element
+        kname = type(pe).__name__
+        if kname not in PHASE_IDS:
+            raise UnsupportedInterfaceError(
+                f'{type(ifc).__name__} with a {kname} phase element is not supported by the B200 table')
+        d.phase_kind = PHASE_IDS[kname]
+        d.phase_flags = int(bool(pe.ref_virtual)) | (int(bool(pe.obj_virtual)) << 1)
+        d.phase_ref_wl = float(pe.ref_wl)
+        for i in range(3):
+            d.phase_ref_pt[i] = float(pe.ref_pt[i])
+            d.phase_obj_pt[i] = float(pe.obj_pt[i])
     profile = getattr(ifc, 'profile', None)
     pname = type(profile).__name__
+    if type(ifc).__name__ == 'ThinLens':        # oprops/thinlens.py: no profile object
+        pname = 'ThinLens'
+        profile = _ThinLensProfile()
     if profile is None or pname not in PROFILE_IDS:
         raise UnsupportedInterfaceError(
             f'interface {type(ifc).__name__} / profile {pname} is not supported by the B200 table')
@@ -40,7 +56,7 @@ def _describe_interface(seg, prev_n, prev_zdir):
     d.mode = MODE_IDS.get(getattr(ifc, 'interact_mode', 'dummy'), MODE_IDS['dummy'])
     d.z_dir = int(z_dir if z_dir is not None else prev_zdir)
     d.cv = float(profile.cv)
-    if pname == 'Spherical':
+    if pname in ('Spherical', 'ThinLens'):
         d.cc, d.ec = 0.0, 1.0
     else:
         d.cc, d.ec = float(profile.cc), float(profile.ec)
@@ -140,6 +156,9 @@ class SurfaceTable:
                                        self.n_wvl, self.device, C.byref(handle)))
         self._handle = handle
         self._lib = lib
+        if wvls is not None and all(isinstance(w, (int, float)) for w in wvls):
+            w = np.ascontiguousarray(wvls, dtype=np.float64)
+            _abi.check(lib.rt_table_set_wavelengths(handle, w.ctypes.data_as(_abi.c_double_p)))
 
     @classmethod
     def from_model(cls, seq_model, wvls=None, device=0):
@@ -147,9 +166,9 @@ class SurfaceTable:
         return cls(descs, n_by_wvl, wvls, device)
 
     @classmethod
-    def from_path(cls, path, device=0):
+    def from_path(cls, path, device=0, wvl=None):
         descs, ns = describe_path(path)
-        return cls(descs, np.array([ns]), None, device)
+        return cls(descs, np.array([ns]), None if wvl is None else [float(wvl)], device)
 
     @property
     def handle(self):

@@ -138,7 +138,7 @@ def main():
     rng = np.random.default_rng(0)
     plan = {'singlet': (7, 60), 'dblgauss': (5, 150), 'triplet': (5, 80), 'rc': (5, 60),
             'cellphone': (3, 100), 'cellphone_even': (3, 100), 'evenasph': (3, 100),
-            'zoom52': (3, 80)}
+            'zoom52': (3, 80), 'thin_triplet': (5, 100)}
     only = sys.argv[1:]
     for name, (num, n_wild) in plan.items():
         if only and name not in only:

@@ -178,6 +178,8 @@ def main():
         'cellphone_even': cellphone_even,
         'evenasph': evenasph,
         'zoom52': zoom52,
+        # 3 ThinLens interfaces (HolographicElement phase), models/thin_triplet.roa
+        'thin_triplet': lambda: from_roa('models/thin_triplet.roa', 'thin_triplet'),
     }
     only = sys.argv[1:]
     for name, fn in models.items():

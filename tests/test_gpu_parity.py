@@ -97,7 +97,7 @@ def test_cuda_matches_oracle_bundle(tables, oracle, name):
                  dict(first_surf=1, last_surf=n_ifc - 2, check_apertures=False)):
         opts = _abi.make_opts(**case)
         ref = oracle.trace_bundle(tab.descs, tab.n_by_wvl, p0, d0, wv, opts, want_full=True,
-                                  n_threads=8)
+                                  n_threads=8, wvls=tab.wvls)
         r = E.trace_bundle(tab, p0, d0, wvl_idx=wv, full=True, **case)
         torch.cuda.synchronize()
         assert same(np_(r.status), ref['status'])
@@ -117,13 +117,14 @@ def test_cuda_matches_oracle_bundle(tables, oracle, name):
 def oracle_grid(oracle, tab, grid, r0, r1, opts):
     spec = grid.c_spec()
     p, d, wv, pup = oracle.grid_start_rays(spec, r0, r1)
-    ref = oracle.trace_bundle(tab.descs, tab.n_by_wvl, p, d, wv, opts, n_threads=8)
+    ref = oracle.trace_bundle(tab.descs, tab.n_by_wvl, p, d, wv, opts, n_threads=8, wvls=tab.wvls)
     ref['p0'], ref['d0'] = p, d
     return ref
 
 
 @pytest.mark.parametrize('name,num', [('singlet', 7), ('dblgauss', 64), ('rc', 64),
-                                      ('cellphone', 32), ('evenasph', 32), ('zoom52', 16)])
+                                      ('cellphone', 32), ('evenasph', 32), ('zoom52', 16),
+                                      ('thin_triplet', 48)])
 def test_cuda_grid_matches_oracle(tables, oracle, name, num):
     opm, tab = tables(name)
     grid = E.grid_for_model(opm, tab, num)
@@ -316,7 +317,8 @@ def test_full_size_configs(tables, oracle, name, num, n_rays):
     base = grid.first_ray_of_chunk(c0)
     for c in rng.integers(c0, c1, 24):
         a, b = grid.first_ray_of_chunk(int(c)), grid.first_ray_of_chunk(int(c) + 1)
-        ref = oracle.trace_grid(grid.c_spec(), tab.descs, tab.n_by_wvl, a, b, opts, n_threads=8)
+        ref = oracle.trace_grid(grid.c_spec(), tab.descs, tab.n_by_wvl, a, b, opts, n_threads=8,
+                                wvls=tab.wvls)
         sl = slice(a - base, b - base)
         assert same(st[sl], ref['status'])
         assert same(np_(r.p[:, sl]), ref['last'][0:3]) and same(np_(r.d[:, sl]), ref['last'][3:6])

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     """ctypes mirrors have the sizes nvcc/gcc give the C structs."""
     from oracle import rt_oracle
-    assert rt_oracle.lib().rto_sizeof_surface_desc() == C.sizeof(_abi.rt_surface_desc) == 480
+    assert rt_oracle.lib().rto_sizeof_surface_desc() == C.sizeof(_abi.rt_surface_desc) == 544
     assert C.sizeof(_abi.rt_opts) == 40
     assert C.sizeof(_abi.rt_out) == 19*8
     assert C.sizeof(_abi.rt_field_desc) == 72
@@ -58,6 +58,10 @@ def test_model_roundtrip_and_table(name):
     assert len(a) == sm.get_num_surfaces() and na.shape == (len(sm.wvlns), len(a))
     assert a[len(a) - 1].mode == _abi.MODE_IDS['dummy']
     for i, ifc in enumerate(sm.ifcs):
+        if type(ifc).__name__ == 'ThinLens':
+            assert a[i].profile == _abi.PROFILE_IDS['ThinLens'] and a[i].phase_kind == 1
+            assert a[i].phase_obj_pt[2] == ifc.phase_element.obj_pt[2]
+            continue
         assert a[i].profile == _abi.PROFILE_IDS[type(ifc.profile).__name__]
         assert a[i].cv == ifc.profile.cv and a[i].max_aperture == ifc.max_aperture
 

@@ -38,7 +38,7 @@ def run_oracle_on_vectors(oracle, name):
             continue
         opts = _abi.make_opts(**case)
         r = oracle.trace_bundle(descs, n_by_wvl, v['p0'][:, idx], v['d0'][:, idx],
-                                v['wvl_idx'][idx], opts, want_full=True)
+                                v['wvl_idx'][idx], opts, want_full=True, wvls=opm.seq_model.wvlns)
         out['last'][:, idx] = r['last']
         for k in ('op', 'status', 'fail_surf', 'n_seg'):
             out[k][idx] = r[k]
