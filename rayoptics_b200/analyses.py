@@ -325,3 +325,47 @@ class RayGrid:
         gx, gy = np.meshgrid(px, py, indexing='ij')
         self.grid = np.stack([gx, gy, opd])
         return self
+
+
+# --- PSF from a wavefront map (raytr/analyses.py:795-875) -------------------
+def psf_sampling(n=None, n_pupil=None, n_airy=None):
+    """Given 2 of (grid width, pupil samples, Airy-peak samples) compute the third
+    (analyses.py:795-815)."""
+    npa = n, n_pupil, n_airy
+    i = npa.index(None)
+    if i == 0:
+        n = round((n_pupil*n_airy)/2.44)
+    elif i == 1:
+        n_pupil = round(2.44*n/n_airy)
+    else:
+        n_airy = round(2.44*n/n_pupil)
+    return n, n_pupil, n_airy
+
+
+def calc_psf_scaling(opt_model, ref_sphere_radius, wvl, ndim, maxdim, exp_radius):
+    """Input / output grid spacings of the FFT PSF (analyses.py:818-845)."""
+    fod = opt_model.optical_spec.fod
+    wl = opt_model.nm_to_sys_units(wvl)
+    fill_factor = ndim/maxdim
+    max_D = 2*fod.enp_radius/fill_factor
+    delta_x = max_D/maxdim
+    delta_theta = (fill_factor*(wl/exp_radius))/2
+    return delta_x, delta_theta*ref_sphere_radius
+
+
+def calc_psf(wavefront, ndim, maxdim, device=0):
+    """Point spread function of a wavefront map (analyses.py:848-875): embed the
+    ``ndim x ndim`` OPD map (waves, NaN = no data) in a ``maxdim`` grid, form the
+    pupil function ``exp(2 pi i W)`` (entries equal to 1 are zeroed, as the
+    reference does), FFT, normalise to the peak.  The FFT is ``torch.fft`` on the
+    GPU (a plain library transform; tolerance vs numpy 1e-12)."""
+    dev = torch.device('cuda', device)
+    Wm = torch.zeros((maxdim, maxdim), dtype=torch.float64, device=dev)
+    w = torch.as_tensor(np.nan_to_num(np.asarray(wavefront, dtype=np.float64)), device=dev)
+    m2, nd2 = maxdim//2, ndim//2
+    Wm[m2 - (nd2 - 1):m2 + (nd2 + 1), m2 - (nd2 - 1):m2 + (nd2 + 1)] = w
+    phase = torch.exp(1j*2*np.pi*Wm.to(torch.complex128))
+    phase = torch.where(phase == 1, torch.zeros_like(phase), phase)
+    AP = torch.fft.fftshift(torch.fft.fft2(torch.fft.fftshift(phase))).abs()**2
+    AP = AP/AP.max()
+    return AP.cpu().numpy()

@@ -140,3 +140,24 @@ def test_analysis_classes(oracle):
     gold = np.where(v['status'][m0] == 0, conv*v['opd'][m0], np.nan).reshape(num, num)
     np.testing.assert_allclose(grid.grid[2], gold, rtol=0, atol=1e-12*conv, equal_nan=True)
     assert same(grid.grid[0][:, 0], xs) and same(grid.grid[1][0, :], xs)
+
+
+@pytest.mark.gpu
+def test_psf_matches_numpy_restatement():
+    """calc_psf (raytr/analyses.py:848-875) on torch.fft vs the same steps in numpy."""
+    from numpy.fft import fftshift, fft2
+    from rayoptics_b200 import analyses as A
+    opm = load_model('dblgauss')
+    ndim, maxdim = 32, 128
+    grid = A.RayGrid(opm, f=1, wl=opm.seq_model.wvlns[1], num_rays=ndim)
+    AP = A.calc_psf(grid.grid[2], ndim, maxdim)
+    W = np.zeros([maxdim, maxdim])
+    nd2, m2 = ndim//2, maxdim//2
+    W[m2 - (nd2 - 1):m2 + (nd2 + 1), m2 - (nd2 - 1):m2 + (nd2 + 1)] = np.nan_to_num(grid.grid[2])
+    phase = np.exp(1j*2*np.pi*W)
+    phase[phase == 1] = 0
+    ref = abs(fftshift(fft2(fftshift(phase))))**2
+    ref = ref/np.nanmax(ref)
+    assert AP.shape == (maxdim, maxdim) and AP.max() == 1.0
+    np.testing.assert_allclose(AP, ref, rtol=0, atol=1e-12)
+    assert A.psf_sampling(n=128, n_pupil=32) == (128, 32, round(2.44*128/32))
