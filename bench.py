@@ -264,7 +264,9 @@ def run_b200(args):
     assert torch.cuda.is_available(), 'bench.py --impl b200 needs a CUDA device'
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local),
+                                timeout=datetime.timedelta(seconds=180))   # fail fast, never hang
     dev = torch.device('cuda', local)
     _abi.load_library()
 
@@ -286,11 +288,15 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
-    n_warm, t_w = 0, time.perf_counter()
-    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_w < 0.7:
-        step()                          # >= W warm-up steps, and long enough for the
-        n_warm += 1                     # clocks to ramp and nvidia-smi to sample under load
-        if n_warm % 16 == 0:
+    n_warm = max(args.warmup, 3)
+    for _ in range(n_warm):             # W warm-up steps: SAME count on every rank (each
+        step()                          # step holds a collective)
+    torch.cuda.synchronize()
+    t_w, extra = time.perf_counter(), 0
+    while time.perf_counter() - t_w < 0.7:
+        E.trace_grid(tab, grid, res=res)    # collective-free extra warm-up, long enough for the
+        extra += 1                          # clocks to ramp and nvidia-smi to sample under load
+        if extra % 16 == 0:
             torch.cuda.synchronize()
     barrier()
     launches0 = E.launch_count()
@@ -405,7 +411,7 @@ def run_b200(args):
                          'algorithmic_flop_per_full_ray': flops_full_ray,
                          'algorithmic_flop_per_step': flops}}
         line = {'metric': METRIC, 'value': world*n_rays*args.steps/(dev_ms_max*1e-3), 'unit': UNIT,
-                'n_gpus': world, 'steps': args.steps, 'warmup': n_warm,
+                'n_gpus': world, 'steps': args.steps, 'warmup': n_warm, 'extra_warmup_traces': extra,
                 'ms_per_step': dev_ms_max/args.steps, 'wall_ms_per_step': wall_ms_max/args.steps,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic', 'config': config_dict(args, opm, grid, world),

@@ -30,8 +30,9 @@ class PendingSummary:
     the collective runs on NCCL's stream while the next grid is traced;
     ``result()`` waits and combines."""
 
-    def __init__(self, work, out, shape, world):
+    def __init__(self, work, out, shape, world, keep=None):
         self.work, self.out, self.shape, self.world = work, out, shape, world
+        self._keep = keep      # the input tensor stays referenced until the collective is done
 
     def result(self):
         self.work.wait()
@@ -58,7 +59,7 @@ def gather_summaries(partial, group=None, async_op=False):
                       device=partial.device)
     if async_op:
         work = dist.all_gather_into_tensor(out, partial, group=group, async_op=True)
-        return PendingSummary(work, out, tuple(partial.shape), world)
+        return PendingSummary(work, out, tuple(partial.shape), world, keep=partial)
     dist.all_gather_into_tensor(out, partial, group=group)
     return combine_summaries(out.view((world,) + tuple(partial.shape)))
 

@@ -25,7 +25,9 @@ def main():
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     local = int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import datetime
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local),
+                            timeout=datetime.timedelta(seconds=180))
     opm = M.OpticalModel.load(os.path.join(ROOT, 'tests', 'golden', 'models', 'dblgauss.json'))
     tab = T.SurfaceTable.from_model(opm.seq_model, device=local)
     whole = A.spot_diagram(opm, 200, table=tab)
