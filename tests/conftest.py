@@ -9,7 +9,7 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 MODEL_NAMES = ['singlet', 'dblgauss', 'triplet', 'rc', 'cellphone', 'cellphone_even',
-               'evenasph', 'zoom52', 'thin_triplet']
+               'evenasph', 'zoom52', 'thin_triplet', 'exotic']
 
 
 def pytest_configure(config):

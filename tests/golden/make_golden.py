@@ -39,7 +39,12 @@ OUT = os.path.join(HERE, 'vectors')
 N_FULL = 48
 
 # keyword sets of trace_raw exercised by the vectors ("cases")
-def cases_for(n_ifc):
+def cases_for(n_ifc, extra=False):
+    if extra:      # model 'exotic': additionally phantom filtering and a raw (not re-intersected) object
+        return cases_for(n_ifc) + [
+            dict(first_surf=1, last_surf=n_ifc - 2, check_apertures=True, filter_out_phantoms=True),
+            dict(first_surf=2, last_surf=n_ifc - 3, check_apertures=False, intersect_obj=False),
+        ]
     return [
         dict(first_surf=1, last_surf=n_ifc - 2, check_apertures=True),     # grid analyses
         dict(first_surf=1, last_surf=n_ifc - 2, check_apertures=False),    # trace() default
@@ -69,7 +74,7 @@ def wild_rays(opm, n, rng, rays):
     osp, sm = opm.optical_spec, opm.seq_model
     fod = osp.fod
     thi0 = sm.gaps[0].thi
-    n_cases = len(cases_for(sm.get_num_surfaces()))
+    n_cases = len(cases_for(sm.get_num_surfaces(), opm.name == 'exotic'))
     for k in range(n):
         wi = int(rng.integers(len(sm.wvlns)))
         aim = fod.enp_radius*rng.uniform(-3.0, 3.0, 2)
@@ -90,7 +95,7 @@ def wild_rays(opm, n, rng, rays):
 def trace_all(opm, rays):
     sm = opm.seq_model
     n_ifc = sm.get_num_surfaces()
-    cases = cases_for(n_ifc)
+    cases = cases_for(n_ifc, opm.name == 'exotic')
     paths = [rh.ref_path(sm, w) for w in sm.wvlns]
     n = len(rays)
     out = dict(p0=np.zeros((3, n)), d0=np.zeros((3, n)), wvl_idx=np.zeros(n, np.int32),
@@ -138,7 +143,7 @@ def main():
     rng = np.random.default_rng(0)
     plan = {'singlet': (7, 60), 'dblgauss': (5, 150), 'triplet': (5, 80), 'rc': (5, 60),
             'cellphone': (3, 100), 'cellphone_even': (3, 100), 'evenasph': (3, 100),
-            'zoom52': (3, 80), 'thin_triplet': (5, 100)}
+            'zoom52': (3, 80), 'thin_triplet': (5, 100), 'exotic': (7, 400)}
     only = sys.argv[1:]
     for name, (num, n_wild) in plan.items():
         if only and name not in only:
@@ -148,6 +153,9 @@ def main():
         grid_rays(opm, num, 0, rays)
         if name in ('dblgauss', 'rc', 'cellphone'):
             grid_rays(opm, 3, 1, rays)
+        if name == 'exotic':
+            grid_rays(opm, 5, 4, rays)
+            grid_rays(opm, 3, 5, rays)
         wild_rays(opm, n_wild, rng, rays)
         out = trace_all(opm, rays)
         np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)

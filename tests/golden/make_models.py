@@ -166,6 +166,52 @@ def zoom52():
     return finish(opm)
 
 
+def exotic():
+    """Synthetic model exercising everything the quadric lenses do not: Y/X toroids,
+    even and radial polynomials, rectangular aperture with offset, circular
+    obscuration, a phantom interface, tilted / decentered transforms in both
+    numpy memory layouts (rayoptics_b200/table.py has_tfrm 1 and 2), finite object."""
+    def rot(ax, ay):
+        cx, sx, cy, sy = np.cos(ax), np.sin(ax), np.cos(ay), np.sin(ay)
+        Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        return Rx @ Ry
+    g1, g2 = M.AbbeGlass(1.6, 50.0, 'g1'), M.AbbeGlass(1.7, 30.0, 'g2')
+    spec = [  # profile, mode, thi, medium, max_aperture
+        (M.Spherical(0.0), 'dummy', 200.0, M.Air(), 50.0),
+        (M.Conic(c=0.02, cc=-0.6), 'transmit', 6.0, g1, 14.0),
+        (M.YToroid(c=-0.01, cR=-0.012, cc=0.2, coefs=[0.0, 2e-7]), 'transmit', 3.0, M.Air(), 14.0),
+        (M.XToroid(c=0.015, cR=0.013, cc=-0.3, coefs=[0.0, -1e-7, 1e-10]), 'transmit', 5.0, g2, 13.0),
+        (M.Spherical(0.0), 'phantom', 2.0, g2, 13.0),
+        (M.EvenPolynomial(c=-0.025, cc=-0.4, coefs=[0.0, 1.5e-6, -2e-9, 1e-12]), 'transmit', 8.0, M.Air(), 12.0),
+        (M.RadialPolynomial(c=0.03, ec=0.8, coefs=[0.0, 0.0, 2e-5, -3e-6, 1e-7]), 'transmit', 4.0, g1, 11.0),
+        (M.Conic(c=-0.028, cc=0.5), 'transmit', 60.0, M.Air(), 11.0),
+        (M.Spherical(0.0), 'dummy', 0.0, None, 30.0)]
+    ifcs, gaps = [], []
+    for prf, mode, thi, med, ap in spec:
+        ifcs.append(M.Surface(profile=prf, interact_mode=mode, max_aperture=ap))
+        if med is not None:
+            gaps.append(M.Gap(thi, med))
+    ifcs[2].clear_apertures = [M.Rectangular(12.0, 9.0, x_offset=0.5, y_offset=-0.4)]
+    ifcs[5].clear_apertures = [M.Circular(11.5), M.Circular(1.2, is_obscuration=True, x_offset=0.3)]
+    tf = []
+    for i, g in enumerate(gaps):
+        if i in (1, 2, 5, 6):
+            R = rot(0.01*(i + 1)*(-1)**i, 0.008*(i + 2))
+            rt = R.T if i % 2 else np.ascontiguousarray(R)     # F-ordered view / C array
+            tf.append((rt, np.array([0.05*(i - 3), -0.03*i, g.thi])))
+        else:
+            tf.append((np.identity(3), np.array([0., 0., g.thi])))
+    tf.append((np.identity(3), np.zeros(3)))
+    wvls = [656.3, 587.6, 486.1]
+    sm = M.SequentialModel(ifcs, gaps, stop_surface=None, wvlns=wvls, ref_wvl=1, lcl_tfrms=tf)
+    sm.stop_surface = 4
+    fields = [M.Field(y=0.0), M.Field(y=6.0), M.Field(x=4.0, y=-5.0)]
+    osp = OpticalSpecs(WvlSpec(wvls, 1), PupilSpec(('object', 'epd'), 16.0),
+                       FieldSpec(('object', 'height'), 6.0, fields))
+    return finish(M.OpticalModel(sm, osp, name='exotic'), aim=False, apertures=False)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     models = {
@@ -180,6 +226,7 @@ def main():
         'zoom52': zoom52,
         # 3 ThinLens interfaces (HolographicElement phase), models/thin_triplet.roa
         'thin_triplet': lambda: from_roa('models/thin_triplet.roa', 'thin_triplet'),
+        'exotic': exotic,
     }
     only = sys.argv[1:]
     for name, fn in models.items():
@@ -190,7 +237,7 @@ def main():
         fod = opm.optical_spec.fod
         print(f'{name:15s} n_ifc={opm.seq_model.get_num_surfaces():3d} efl={fod.efl:10.4f} '
               f'enp_dist={fod.enp_dist:10.4f} enp_r={fod.enp_radius:8.4f} '
-              f'aims={[list(np.round(f.aim_info, 6)) for f in opm.optical_spec.fov.fields][:3]}')
+              f'aims={[None if f.aim_info is None else list(np.round(f.aim_info, 6)) for f in opm.optical_spec.fov.fields][:3]}')
 
 
 if __name__ == '__main__':

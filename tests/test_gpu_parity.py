@@ -124,7 +124,7 @@ def oracle_grid(oracle, tab, grid, r0, r1, opts):
 
 @pytest.mark.parametrize('name,num', [('singlet', 7), ('dblgauss', 64), ('rc', 64),
                                       ('cellphone', 32), ('evenasph', 32), ('zoom52', 16),
-                                      ('thin_triplet', 48)])
+                                      ('thin_triplet', 48), ('exotic', 24)])
 def test_cuda_grid_matches_oracle(tables, oracle, name, num):
     opm, tab = tables(name)
     grid = E.grid_for_model(opm, tab, num)
