@@ -187,7 +187,32 @@ def cpu_trace(spec, descs, n_by_wvl, r0, r1, threads):
     return time.perf_counter() - t0, r
 
 
-def cpu_baseline(opm, num, target_s=12.0):
+def parity_vs_oracle(spec, descs, n_by_wvl, r0, r1, cores, gpu):
+    """ray-intercept RMS / max-abs at the image interface between the
+    engine's records of the timed steps and the oracle on the same grid rays, plus
+    exact equality of status / fail_surf.  `gpu(r0, r1)` returns host copies."""
+    from oracle import rt_oracle
+    from rayoptics_b200 import _abi
+    opts = _abi.make_opts(first_surf=1, last_surf=len(descs) - 2, check_apertures=True)
+    ref = rt_oracle.trace_grid(spec.c_spec(), descs, n_by_wvl, r0, r1, opts, n_threads=cores)
+    g = gpu(r0, r1)
+    ok = ref['status'] == 0
+    dxy = g['p'][0:2][:, ok] - ref['last'][0:2][:, ok]
+    dist = np.sqrt((dxy**2).sum(0))
+    bit_equal = all(np.array_equal(a, b, equal_nan=True) for a, b in (
+        (g['p'], ref['last'][0:3]), (g['d'], ref['last'][3:6]), (g['op'], ref['op']),
+        (g['abr'], ref['abr'])))
+    return {'rays': int(r1 - r0), 'rays_ok': int(ok.sum()),
+            'intercept_rms_mm': float(np.sqrt((dist**2).mean())) if ok.any() else 0.0,
+            'intercept_max_abs_mm': float(dist.max()) if ok.any() else 0.0,
+            'status_equal': bool(np.array_equal(g['status'], ref['status'])),
+            'fail_surf_equal': bool(np.array_equal(g['fail_surf'], ref['fail_surf'])),
+            'bit_identical_p_d_op_abr': bool(bit_equal), 'target_mm': 1e-10,
+            'against': 'oracle/rt_oracle.c (pinned on the reference golden vectors), '
+                       'tile field 1 / wvl 1 of the timed grid'}
+
+
+def cpu_baseline(opm, num, target_s=12.0, gpu=None):
     """The oracle port on all host threads, on a bounded contiguous sample of the
     same grid (one tile = field 1, wavelength 1)."""
     cores = os.cpu_count() or 1
@@ -201,10 +226,16 @@ def cpu_baseline(opm, num, target_s=12.0):
         dt, _ = cpu_trace(spec, descs, n_by_wvl, r0, r1, cores)
         total_t += dt; total_n += r1 - r0; reps += 1
     dt1, _ = cpu_trace(spec, descs, n_by_wvl, r0, r0 + min(100000, per_tile), 1)
-    return {'value': total_n/total_t, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': f'{reps} x {r1 - r0} rays (tile field 1 / wvl 1 of the same grid), '
-                      f'oracle/rt_oracle.c on {cores} pthreads',
-            'single_thread': min(100000, per_tile)/dt1}
+    out = {'value': total_n/total_t, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+           'sample': f'{reps} x {r1 - r0} rays (tile field 1 / wvl 1 of the same grid), '
+                     f'oracle/rt_oracle.c on {cores} pthreads',
+           'single_thread': min(100000, per_tile)/dt1}
+    if gpu is not None:
+        try:
+            out['parity'] = parity_vs_oracle(spec, descs, n_by_wvl, r0, r1, cores, gpu)
+        except Exception as e:      # noqa: BLE001 - never lose the bench line over the checker
+            out['parity'] = {'error': repr(e)}
+    return out
 
 
 # ------------------------------------------------------------ reference arm
@@ -419,8 +450,11 @@ def run_b200(args):
                 'full_ray_regime': None if full_ray is None else dict(
                     full_ray, frac_of_hbm_peak=full_ray['achieved_gbs']/hbm_peak),
                 'rays_ok_frac': float((status == 0).mean())}
-        if not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_baseline(opm, args.num)
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only
+            def gpu_records(r0, r1):
+                return {k: getattr(res, k)[..., r0:r1].cpu().numpy()
+                        for k in ('p', 'd', 'op', 'abr', 'status', 'fail_surf')}
+            line['cpu_baseline'] = cpu_baseline(opm, args.num, gpu=gpu_records)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
