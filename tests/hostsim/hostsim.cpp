@@ -1,0 +1,122 @@
+/*
+ * tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE (see cuda_runtime.h here).
+ * The per-ray device functions of rayoptics_b200/csrc compiled for the host and
+ * driven ray by ray; what a CTA does around them (plan staging, store_result)
+ * is restated in a few lines below.
+ */
+#define RT_HOSTSIM 1
+#include "cuda_runtime.h"
+#include "../../rayoptics_b200/csrc/rt_lean.cuh"
+#include <vector>
+
+using namespace b200rt;
+
+namespace {
+
+struct Out {
+    double *last, *op, *full;
+    int32_t *status, *fail_surf, *n_seg;
+    int64_t n;
+};
+
+void store(const Out &o, int64_t k, const RayResult &R, bool has_n)
+{
+    double *l = o.last + k;
+    l[0] = R.p.x; l[o.n] = R.p.y; l[2*o.n] = R.p.z;
+    l[3*o.n] = R.d.x; l[4*o.n] = R.d.y; l[5*o.n] = R.d.z;
+    l[6*o.n] = has_n ? R.dst : 0.0;
+    l[7*o.n] = has_n ? R.n.x : 0.0; l[8*o.n] = has_n ? R.n.y : 0.0; l[9*o.n] = has_n ? R.n.z : 0.0;
+    o.op[k] = R.op; o.status[k] = R.status; o.fail_surf[k] = R.fail_surf; o.n_seg[k] = R.n_seg;
+}
+
+template <int OUT, bool POLY>
+void run_lean(const rt_surface_desc *surfs, int n_ifc, const double *n_by_wvl, int n_wvl, int64_t n,
+              const double *p0, const double *d0, const int32_t *wvl_idx, const rt_opts &o, const Out &out)
+{
+    std::vector<LeanSurf> ls(n_ifc);
+    std::vector<LeanIdx> li((size_t)n_ifc*n_wvl);
+    build_plan(surfs, n_by_wvl, n_ifc, n_wvl, o, ls.data(), li.data());
+    for (int64_t r = 0; r < n; r++) {
+        Vec3 p = {p0[r], p0[n + r], p0[2*n + r]}, d = {d0[r], d0[n + r], d0[2*n + r]};
+        const int w = wvl_idx ? wvl_idx[r] : o.wvl_idx;
+        FullWriter fw = {OUT == 2 ? out.full + r : nullptr, n};
+        RayResult R;
+        trace_ray_lean<OUT, false, POLY>(ls.data(), li.data() + (int64_t)w*n_ifc, surfs, n_ifc, o, p, d, fw, R);
+        store(out, r, R, OUT >= 1);
+    }
+}
+
+template <bool FULL>
+void run_general(const rt_surface_desc *surfs, int n_ifc, const double *n_by_wvl, const double *wvls,
+                 int64_t n, const double *p0, const double *d0, const int32_t *wvl_idx, const rt_opts &o,
+                 const Out &out)
+{
+    for (int64_t r = 0; r < n; r++) {
+        Vec3 p = {p0[r], p0[n + r], p0[2*n + r]}, d = {d0[r], d0[n + r], d0[2*n + r]};
+        const int w = wvl_idx ? wvl_idx[r] : o.wvl_idx;
+        FullWriter fw = {FULL ? out.full + r : nullptr, n};
+        RayResult R;
+        trace_ray<FULL>(surfs, n_by_wvl + (int64_t)w*n_ifc, wvls ? wvls[w] : 0.0, n_ifc, o, p, d, fw, R);
+        store(out, r, R, true);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+/* kernel: 0 = general trace_ray, 1 = trace_ray_lean, 2 = trace_ray_lean with POLY.
+ * out_kind (lean only): 0 p,d / 1 + normal,dst / 2 whole ray.  p0, d0: [3][n]. */
+int hostsim_trace_bundle(const rt_surface_desc *surfs, int n_ifc, const double *n_by_wvl, int n_wvl,
+                         const double *wvls, int64_t n, const double *p0, const double *d0,
+                         const int32_t *wvl_idx, const rt_opts *o, int kernel, int out_kind,
+                         double *last, double *op, int32_t *status, int32_t *fail_surf, int32_t *n_seg,
+                         double *full)
+{
+    Out out = {last, op, full, status, fail_surf, n_seg, n};
+    if (out_kind == 2 && !full) return -1;
+    if (kernel == 0) {
+        if (out_kind == 2) run_general<true>(surfs, n_ifc, n_by_wvl, wvls, n, p0, d0, wvl_idx, *o, out);
+        else run_general<false>(surfs, n_ifc, n_by_wvl, wvls, n, p0, d0, wvl_idx, *o, out);
+        return 0;
+    }
+#define LEAN(OUT) do { if (kernel == 2) run_lean<OUT, true>(surfs, n_ifc, n_by_wvl, n_wvl, n, p0, d0, wvl_idx, *o, out); \
+                       else run_lean<OUT, false>(surfs, n_ifc, n_by_wvl, n_wvl, n, p0, d0, wvl_idx, *o, out); } while (0)
+    if (out_kind == 0) LEAN(0);
+    else if (out_kind == 1) LEAN(1);
+    else LEAN(2);
+#undef LEAN
+    return 0;
+}
+
+/* building blocks against the plain IEEE operations (the CPU sibling of
+ * rt_selftest_division): returns the number of mismatches where the fast flag is set */
+int64_t hostsim_check_division(int64_t n, const double *a, const double *b, int64_t *n_fast)
+{
+    int64_t bad = 0, fast_cnt = 0;
+    for (int64_t i = 0; i < n; i++) {
+        bool f;
+        double q = quot_seq(a[i], b[i], rcp_refined(b[i]), f);
+        if (f) { fast_cnt++; if (!(q == a[i]/b[i])) bad++; }
+        double q2 = div_shared(a[i], b[i], rcp_refined(b[i])), q3 = a[i]/b[i];
+        if (std::memcmp(&q2, &q3, 8) != 0 && !(q2 != q2 && q3 != q3)) bad++;
+    }
+    *n_fast = fast_cnt;
+    return bad;
+}
+
+int64_t hostsim_check_sqrt(int64_t n, const double *x, int64_t *n_fast)
+{
+    int64_t bad = 0, fast_cnt = 0;
+    for (int64_t i = 0; i < n; i++) {
+        bool f;
+        double s = sqrt_seq(x[i], f);
+        if (f) { fast_cnt++; if (!(s == std::sqrt(x[i]))) bad++; }
+        double s1 = sqrt_near_one(x[i]);
+        if (x[i] >= 0 && !(s1 == std::sqrt(x[i]))) bad++;
+    }
+    *n_fast = fast_cnt;
+    return bad;
+}
+
+}

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import MODEL_NAMES, load_model, load_vectors
+from conftest import MODEL_NAMES, load_model, load_vectors, seeded_bundle
 from rayoptics_b200 import _abi, table as T, engine as E
 
 pytestmark = pytest.mark.gpu
@@ -60,30 +60,6 @@ def test_cuda_matches_reference_vectors(tables, name):
         assert same(last, v['last'][:, idx])
         sel = idx < n_full
         assert same(np_(r.full)[:, :, sel], v['full'][:, :, idx[sel]])
-
-
-def seeded_bundle(opm, n, rng):
-    """Start rays around the model's pupil / field, some of them wild."""
-    osp, sm = opm.optical_spec, opm.seq_model
-    fod = osp.fod
-    z_pupil = fod.obj_dist + fod.enp_dist
-    p0 = np.zeros((3, n))
-    d0 = np.zeros((3, n))
-    scale = np.where(rng.random(n) < 0.8, 1.05, 3.0)
-    aim = fod.enp_radius*scale*rng.uniform(-1, 1, (2, n))
-    if abs(sm.gaps[0].thi) > 1e8:
-        fmax = abs(osp.fov.max_field_value()) if osp.fov.key[1] == 'angle' else \
-            np.degrees(abs(np.arctan(fod.pr_slp0)))
-        ang = np.deg2rad(scale*max(fmax, 0.2)*rng.uniform(-1, 1, (2, n)))
-        dd = np.array([np.sin(ang[0])*np.cos(ang[1]), np.sin(ang[1]),
-                       np.cos(ang[0])*np.cos(ang[1])])
-        p0[0], p0[1] = -z_pupil*dd[0]/dd[2], -z_pupil*dd[1]/dd[2]
-    else:
-        p0[:2] = scale*max(abs(fod.pr_ht0), 0.5)*rng.uniform(-1, 1, (2, n))
-    v = np.array([aim[0] - p0[0], aim[1] - p0[1], z_pupil - p0[2]])
-    d0 = v/np.sqrt((v*v).sum(0))
-    wv = rng.integers(0, len(sm.wvlns), n).astype(np.int32)
-    return p0, d0, wv
 
 
 @pytest.mark.parametrize('name', MODEL_NAMES)
