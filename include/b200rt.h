@@ -35,8 +35,9 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2
 #define RT_MAX_COEFS 20     /* EvenPolynomial uses <=10, RadialPolynomial <=20 */
+#define RT_MAX_PHASE_COEFS 10
 #define RT_MAX_APERTURES 4  /* Surface.clear_apertures entries honoured per interface */
 #define RT_SEG_DOUBLES 10   /* one ray segment = p[3], d[3], dst, nrml[3]  (raytr/__init__.py:36) */
 #define RT_SUMMARY_DOUBLES 16
@@ -65,7 +66,9 @@ enum rt_profile {
 /* phase elements (Interface.phase_element), src/rayoptics/oprops/doe.py */
 enum rt_phase {
     RT_PHASE_NONE = 0,
-    RT_PHASE_HOE = 1           /* HolographicElement, doe.py:326-395 (also every ThinLens) */
+    RT_PHASE_HOE = 1,          /* HolographicElement, doe.py:326-395 (also every ThinLens) */
+    RT_PHASE_GRATING = 2,      /* DiffractionGrating.phase_ludwig, doe.py:57-172 */
+    RT_PHASE_RADIAL = 3        /* DiffractiveElement with radial_phase_fct, doe.py:28-54,214-323 */
 };
 
 /* Interface.interact_mode, src/rayoptics/seq/interface.py:42-49 */
@@ -130,9 +133,13 @@ typedef struct rt_surface_desc {
     /* phase element (hasattr(ifc, 'phase_element'), raytrace.py:205-210) */
     int32_t phase_kind;   /* rt_phase */
     int32_t phase_flags;  /* HOE: bit 0 ref_virtual, bit 1 obj_virtual */
-    double phase_ref_wl;  /* HOE ref_wl (nm) */
-    double phase_ref_pt[3];
-    double phase_obj_pt[3];
+    double phase_ref_wl;  /* HOE / radial DOE: ref_wl (nm); grating: _grating_spacing_nm */
+    double phase_ref_pt[3];   /* HOE: ref_pt; grating: grating_normal */
+    double phase_obj_pt[3];   /* HOE: obj_pt */
+    double phase_order;   /* grating / radial DOE: order */
+    int32_t n_phase_coefs;    /* radial DOE: len(coefficients) */
+    int32_t phase_pad;
+    double phase_coefs[RT_MAX_PHASE_COEFS];   /* radial DOE: r**2, r**4, ... coefficients */
 } rt_surface_desc;
 
 /* keyword arguments of trace_raw(), raytrace.py:83-121 */

@@ -110,6 +110,27 @@ def ref_surface(ifc):
             cas.append(S.Elliptical(x_half_width=ca.x_half_width,
                                     y_half_width=ca.y_half_width, **kw))
     s.clear_apertures = cas
+    pe = getattr(ifc, 'phase_element', None)
+    if pe is not None:
+        import importlib
+        DOE = importlib.import_module('rayoptics.oprops.doe')
+        kind = type(pe).__name__
+        if kind == 'DiffractionGrating':
+            s.phase_element = DOE.DiffractionGrating(order=pe.order,
+                                                     grating_normal=np.array(pe.grating_normal),
+                                                     grating_lpmm=pe.grating_lpmm,
+                                                     interact_mode=pe.interact_mode)
+        elif kind == 'DiffractiveElement':
+            s.phase_element = DOE.DiffractiveElement(coefficients=list(pe.coefficients),
+                                                     ref_wl=pe.ref_wl, order=pe.order,
+                                                     phase_fct=DOE.radial_phase_fct)
+        elif kind == 'HolographicElement':
+            s.phase_element = DOE.HolographicElement(ref_pt=np.array(pe.ref_pt),
+                                                     ref_virtual=pe.ref_virtual,
+                                                     obj_pt=np.array(pe.obj_pt),
+                                                     obj_virtual=pe.obj_virtual, ref_wl=pe.ref_wl)
+        else:
+            raise ValueError(kind)
     return s
 
 

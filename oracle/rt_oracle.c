@@ -416,6 +416,117 @@ static int hoe_phase(const rt_surface_desc *S, const double pt[3], const double 
     return ST_OK;
 }
 
+/* bend (raytrace.py:19-30) as called from DiffractiveElement.phase: math.sqrt of a
+ * negative raises ValueError, which raytrace.phase() turns into the evanescent error */
+static int bend_for_phase(const double d_in[3], const double normal[3], double n_in, double n_out,
+                          double d_out[3])
+{
+    double normal_len = sqrt(dot3(normal, normal));
+    double cosI = dot3(d_in, normal)/normal_len;
+    double sinI_sqr = 1.0 - cosI*cosI;
+    double arg = n_out*n_out - n_in*n_in*sinI_sqr;
+    if (arg < 0.0) return RT_RAY_TIR;   /* bend() raises TraceTIRError itself (raytrace.py:28-30) */
+    double n_cosIp = copysign(sqrt(arg), cosI);
+    double alpha = n_cosIp - n_in*cosI;
+    for (int c = 0; c < 3; c++) d_out[c] = (n_in*d_in[c] + alpha*normal[c])/n_out;
+    return ST_OK;
+}
+
+/* np.cross for two 3-vectors: multiply, multiply, subtract (numpy/_core/numeric.py cross) */
+static inline void cross3(const double a[3], const double b[3], double o[3])
+{
+    double t;
+    o[0] = a[1]*b[2]; t = a[2]*b[1]; o[0] -= t;
+    o[1] = a[2]*b[0]; t = a[0]*b[2]; o[1] -= t;
+    o[2] = a[0]*b[1]; t = a[1]*b[0]; o[2] -= t;
+}
+
+/* DiffractionGrating.phase -> phase_ludwig (oprops/doe.py:119-172).  `x**2` on a Python /
+ * numpy float is libm pow(x, 2.0): kept as pow() here so that this oracle, on the same
+ * glibc, reproduces the reference bit for bit (pow(x, 2.0) != x*x for ~0.08 % of x).
+ * np.sqrt of a negative gives NaN (no exception): the NaN direction propagates;
+ * math.sqrt of a negative raises ValueError -> evanescent. */
+static int grating_phase(const rt_surface_desc *S, const double in_dir[3], const double srf_nrml[3],
+                         double z_dir, double wvl, double n_in, double n_out,
+                         double out_dir[3], double *dW)
+{
+    const int reflect = S->mode == RT_MODE_REFLECT;
+    const double refl = reflect ? -1.0 : 1.0;
+    double normal[3], P[3], D[3], c[3];
+    normalize3(srf_nrml, normal);
+    for (int i = 0; i < 3; i++) normal[i] = z_dir*normal[i];
+    cross3(S->phase_ref_pt, normal, P);
+    cross3(normal, P, c);
+    normalize3(c, D);
+    const double spacing = S->phase_ref_wl;
+    double mu = n_in/n_out;
+    double T = refl*(wvl*S->phase_order)/(spacing*n_out);
+    double in_cosI = dot3(in_dir, normal);
+    double V = mu*in_cosI;
+    double W = pow(mu, 2.0) - 1 + pow(T, 2.0) - 2*mu*T*dot3(D, in_dir);
+    double result = sqrt(pow(V, 2.0) - W);          /* np.sqrt: NaN when negative */
+    double Q1 = result - V, Q2 = -result - V, Q;
+    if (!reflect) Q = (Q2 > Q1) ? Q2 : Q1;           /* max(Q1, Q2) */
+    else Q = (Q2 < Q1) ? Q2 : Q1;                    /* min(Q1, Q2) */
+    for (int i = 0; i < 3; i++) out_dir[i] = mu*in_dir[i] - T*D[i] + Q*normal[i];
+    double a0 = 1 - pow(out_dir[0], 2.0) - pow(out_dir[1], 2.0);
+    if (a0 < 0.0) return RT_RAY_EVANESCENT;          /* math.sqrt */
+    out_dir[2] = copysign(sqrt(a0), out_dir[2]);
+    double a1 = 1 - pow(in_cosI, 2.0);
+    if (a1 < 0.0) return RT_RAY_EVANESCENT;
+    double in_sinI = sqrt(a1);
+    double out_cosI = dot3(out_dir, normal);
+    double a2 = 1 - pow(out_cosI, 2.0);
+    if (a2 < 0.0) return RT_RAY_EVANESCENT;
+    double out_sinI = sqrt(a2);
+    *dW = (spacing/wvl)*(n_in*in_sinI + refl*n_out*out_sinI);
+    return ST_OK;
+}
+
+/* DiffractiveElement.phase with radial_phase_fct (oprops/doe.py:28-54,272-323) */
+static int radial_doe_phase(const rt_surface_desc *S, const double pt[3], const double in_dir[3],
+                            const double srf_nrml[3], double z_dir, double wvl, double n_in,
+                            double n_out, double out_dir[3], double *dW_out)
+{
+    const double order = S->phase_order;
+    double normal[3], inc_dir[3];
+    normalize3(srf_nrml, normal);
+    for (int i = 0; i < 3; i++) inc_dir[i] = in_dir[i];
+    if (n_in != 1.0) {
+        int st = bend_for_phase(in_dir, srf_nrml, n_in, 1.0, inc_dir);
+        if (st) return st;
+    }
+    double in_cosI = dot3(inc_dir, normal);
+    double mu = wvl/S->phase_ref_wl;
+    const double x = pt[0], y = pt[1];
+    double r_sqr = x*x + y*y;
+    double dW = 0, dWdX = 0, dWdY = 0;
+    for (int i = 0; i < S->n_phase_coefs; i++) {
+        const double c = S->phase_coefs[i];
+        dW += c*pow(r_sqr, (double)(i + 1));
+        double r_exp = pow(r_sqr, (double)i);
+        double factor = 2*(i + 1);
+        dWdX += factor*c*x*r_exp;
+        dWdY += factor*c*y*r_exp;
+    }
+    double b = in_cosI + order*mu*(normal[0]*dWdX + normal[1]*dWdY);
+    double c_ = mu*(mu*(pow(dWdX, 2.0) + pow(dWdY, 2.0))/2 + order*(inc_dir[0]*dWdX + inc_dir[1]*dWdY));
+    double rad = b*b - 2*c_;
+    if (rad < 0.0) return RT_RAY_EVANESCENT;         /* math.sqrt */
+    double Q = -b + z_dir*sqrt(rad);
+    const double om = order*mu;
+    const double g[3] = {om*dWdX, om*dWdY, om*0.0};
+    for (int i = 0; i < 3; i++) out_dir[i] = inc_dir[i] + g[i] + Q*normal[i];
+    dW *= mu;
+    if (n_in != 1.0) {
+        double t[3] = {out_dir[0], out_dir[1], out_dir[2]};
+        int st = bend_for_phase(t, srf_nrml, 1.0, n_out, out_dir);
+        if (st) return st;
+    }
+    *dW_out = dW;
+    return ST_OK;
+}
+
 static inline void put_seg(double *ray, int k, const double p[3], const double d[3],
                            double dst, const double n[3])
 {
@@ -441,6 +552,7 @@ int rto_trace_ray(const rt_surface_desc *surfs, int32_t n_ifc, const double *n_r
     const int last_surf = o->last_surf;     /* <0: None */
     int n_seg = 0, status = ST_OK, fail_surf = -1;
     double opl = 0.0;
+    double phs_sum = 0.0;     /* op_delta before `op_delta += opl` (raytrace.py:210,260) */
     double before_pt[3], before_dir[3], before_nrml[3];
     double inc_pt[3] = {0, 0, 0}, normal[3] = {0, 0, 1}, after_dir[3] = {0, 0, 0};
     double lseg[RT_SEG_DOUBLES];
@@ -520,9 +632,18 @@ int rto_trace_ray(const rt_surface_desc *surfs, int32_t n_ifc, const double *n_r
             }
         }
 
-        if (ifc->phase_kind == RT_PHASE_HOE) {
+        if (ifc->phase_kind != RT_PHASE_NONE) {
             /* raytrace.py:205-210: the phase element sets after_dir (phs = 0 for a HOE) */
-            st = hoe_phase(ifc, inc_pt, b4_dir, normal, z_dir_before, wvl, after_dir);
+            double phs = 0.0;
+            if (ifc->phase_kind == RT_PHASE_HOE)
+                st = hoe_phase(ifc, inc_pt, b4_dir, normal, z_dir_before, wvl, after_dir);
+            else if (ifc->phase_kind == RT_PHASE_GRATING)
+                st = grating_phase(ifc, b4_dir, normal, z_dir_before, wvl, n_before, n_row[surf],
+                                   after_dir, &phs);
+            else
+                st = radial_doe_phase(ifc, inc_pt, b4_dir, normal, z_dir_before, wvl, n_before,
+                                      n_row[surf], after_dir, &phs);
+            if (!st) phs_sum += phs;
             if (st) {
                 /* TraceEvanescentRayError, raytrace.py:253-257 */
                 put_seg(ray, n_seg, inc_pt, before_dir, 0.0, normal);
@@ -582,7 +703,8 @@ int rto_trace_ray(const rt_surface_desc *surfs, int32_t n_ifc, const double *n_r
 done:
     if (last) memcpy(last, lseg, sizeof lseg);
     *n_seg_out = n_seg;
-    *op_out = opl;
+    /* success: op_delta (sum of phases) += opl, raytrace.py:260; failure: ray_pkg carries opl */
+    *op_out = (status == ST_OK) ? phs_sum + opl : opl;
     *status_out = status;
     *fail_surf_out = fail_surf;
     return 0;

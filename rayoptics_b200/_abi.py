@@ -9,8 +9,9 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-RT_ABI_VERSION = 1
+RT_ABI_VERSION = 2
 RT_MAX_COEFS = 20
+RT_MAX_PHASE_COEFS = 10
 RT_MAX_APERTURES = 4
 RT_SEG_DOUBLES = 10
 RT_SUMMARY_DOUBLES = 16
@@ -19,7 +20,7 @@ RT_WAVE_DOUBLES = 24
 # enum rt_profile
 PROFILE_IDS = {'Spherical': 0, 'Conic': 1, 'EvenPolynomial': 2,
                'RadialPolynomial': 3, 'YToroid': 4, 'XToroid': 5, 'ThinLens': 6}
-PHASE_IDS = {'HolographicElement': 1}
+PHASE_IDS = {'HolographicElement': 1, 'DiffractionGrating': 2, 'DiffractiveElement': 3}
 # enum rt_mode
 MODE_IDS = {'transmit': 0, 'reflect': 1, 'dummy': 2, 'phantom': 3}
 # enum rt_status
@@ -47,7 +48,9 @@ class rt_surface_desc(C.Structure):
                 ('apertures', rt_aperture_desc*RT_MAX_APERTURES),
                 ('phase_kind', C.c_int32), ('phase_flags', C.c_int32),
                 ('phase_ref_wl', C.c_double),
-                ('phase_ref_pt', C.c_double*3), ('phase_obj_pt', C.c_double*3)]
+                ('phase_ref_pt', C.c_double*3), ('phase_obj_pt', C.c_double*3),
+                ('phase_order', C.c_double), ('n_phase_coefs', C.c_int32), ('phase_pad', C.c_int32),
+                ('phase_coefs', C.c_double*RT_MAX_PHASE_COEFS)]
 
 
 class rt_opts(C.Structure):

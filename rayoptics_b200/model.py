@@ -249,6 +249,75 @@ class HolographicElement:
         return cls(**d)
 
 
+def radial_phase_fct(pt, coefficients):
+    """Name-compatible stand-in for oprops/doe.py:28-54: the table compiles a
+    DiffractiveElement by the NAME of its phase function (table.py); the phase itself
+    is evaluated on the device (csrc/rt_device.cuh radial_doe_phase)."""
+    raise NotImplementedError('evaluated on the device; see rayoptics_b200.table')
+
+
+class DiffractionGrating:
+    """Linear grating phase element: data mirror of oprops/doe.py:57-117."""
+
+    def __init__(self, label='', order=1, grating_normal=None, grating_freq_um=1.0,
+                 grating_lpmm=None, interact_mode='transmit'):
+        self.label = label
+        self.grating_normal = (np.array([0., 1., 0.]) if grating_normal is None
+                               else np.array(grating_normal, dtype=float))
+        # same expressions as the reference constructor / setter (doe.py:82-99)
+        self.grating_lpmm = grating_lpmm if grating_lpmm is not None else 1/(grating_freq_um*1000)
+        self.order = order
+        self.interact_mode = interact_mode
+
+    @property
+    def grating_lpmm(self):
+        return self._grating_lpmm
+
+    @grating_lpmm.setter
+    def grating_lpmm(self, grating_lpmm):
+        self._grating_lpmm = grating_lpmm
+        self._grating_spacing_nm = 1e6/grating_lpmm
+
+    def to_dict(self):
+        return {'type': 'DiffractionGrating', 'label': self.label, 'order': self.order,
+                'grating_normal': self.grating_normal.tolist(), 'grating_lpmm': self._grating_lpmm,
+                'interact_mode': self.interact_mode}
+
+    @classmethod
+    def from_dict(cls, d):
+        d = dict(d)
+        d.pop('type', None)
+        return cls(**d)
+
+
+class DiffractiveElement:
+    """Phase-function DOE: data mirror of oprops/doe.py:214-270.  Only the
+    reference's own ``radial_phase_fct`` is compiled into the surface table."""
+
+    def __init__(self, label='', coefficients=None, ref_wl=550., order=1, phase_fct=None):
+        self.label = label
+        self.coefficients = [] if coefficients is None else list(coefficients)
+        self.ref_wl = ref_wl
+        self.order = order
+        self.phase_fct = radial_phase_fct if phase_fct is None else phase_fct
+
+    def to_dict(self):
+        return {'type': 'DiffractiveElement', 'label': self.label,
+                'coefficients': list(self.coefficients), 'ref_wl': self.ref_wl, 'order': self.order}
+
+    @classmethod
+    def from_dict(cls, d):
+        d = dict(d)
+        d.pop('type', None)
+        return cls(**d)
+
+
+def phase_element_from_dict(d):
+    kinds = {'HolographicElement': HolographicElement, 'DiffractionGrating': DiffractionGrating,
+             'DiffractiveElement': DiffractiveElement}
+    return kinds[d.get('type', 'HolographicElement')].from_dict(d)
+
+
 class ThinLens:
     """Thin lens interface (oprops/thinlens.py:17-140): a plane with a
     HolographicElement whose object point encodes the power."""
@@ -490,7 +559,7 @@ class SequentialModel:
                             clear_apertures=[aperture_from_dict(a)
                                              for a in e.get('clear_apertures', [])])
                 if 'phase_element' in e:
-                    s.phase_element = HolographicElement.from_dict(e['phase_element'])
+                    s.phase_element = phase_element_from_dict(e['phase_element'])
             ifcs.append(s)
             if i < n - 1:
                 gaps.append(Gap(e['thi'], medium_from_dict(e['medium'])))

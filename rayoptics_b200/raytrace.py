@@ -62,9 +62,13 @@ def set_device(device):
 def _phase_fp(pe):
     if pe is None:
         return None
-    return (type(pe).__name__, tuple(map(float, getattr(pe, 'ref_pt', ()))),
-            tuple(map(float, getattr(pe, 'obj_pt', ()))), getattr(pe, 'ref_virtual', None),
-            getattr(pe, 'obj_virtual', None), getattr(pe, 'ref_wl', None))
+    fp = [type(pe).__name__, getattr(getattr(pe, 'phase_fct', None), '__name__', None)]
+    for k in ('ref_pt', 'obj_pt', 'grating_normal', 'coefficients'):
+        v = getattr(pe, k, None)
+        fp.append(None if v is None else tuple(map(float, v)))
+    for k in ('ref_virtual', 'obj_virtual', 'ref_wl', 'order', '_grating_spacing_nm'):
+        fp.append(getattr(pe, k, None))
+    return tuple(fp)
 
 
 def _fingerprint(segs):

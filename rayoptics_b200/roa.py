@@ -114,6 +114,28 @@ def _aperture(c):
     raise NotImplementedError(f'.roa aperture type {kind}')
 
 
+def _phase_element(pe):
+    """phase element of a Surface (oprops/doe.py json encodings)"""
+    if pe is None:
+        return None
+    kind = pe['__instance_type__'][1]
+    a = pe['attributes']
+    if kind == 'DiffractiveElement':
+        if a.get('phase_fct_name', 'radial_phase_fct') != 'radial_phase_fct':
+            raise NotImplementedError(f".roa DiffractiveElement with phase_fct {a['phase_fct_name']}")
+        return M.DiffractiveElement(label=a.get('label', ''), coefficients=_val(a['coefficients']),
+                                    ref_wl=a['ref_wl'], order=a['order'])
+    if kind == 'DiffractionGrating':
+        return M.DiffractionGrating(label=a.get('label', ''), order=a['order'],
+                                    grating_normal=_val(a['grating_normal']),
+                                    grating_lpmm=a['_grating_lpmm'],
+                                    interact_mode=a.get('interact_mode', 'transmit'))
+    if kind == 'HolographicElement':
+        return M.HolographicElement(a.get('label', ''), _val(a['ref_pt']), a['ref_virtual'],
+                                    _val(a['obj_pt']), a['obj_virtual'], a['ref_wl'])
+    raise NotImplementedError(f'.roa phase element {kind}')
+
+
 def open_roa(path):
     """Read a ``.roa`` file into an ``OpticalModel`` mirror."""
     with open(path) as f:
@@ -136,8 +158,7 @@ def open_roa(path):
             continue
         if kind != 'Surface':
             raise NotImplementedError(f'.roa interface type {kind}')
-        if a.get('phase_element') is not None:
-            raise NotImplementedError('.roa surfaces with diffractive phase elements')
+        phase_element = _phase_element(a.get('phase_element'))
         if a.get('decenter') is not None:
             raise NotImplementedError('.roa decentered interfaces: supply lcl_tfrms explicitly')
         prf = a.get('profile')
@@ -146,6 +167,8 @@ def open_roa(path):
                               interact_mode=a['interact_mode'],
                               max_aperture=a.get('max_aperture', 1.0),
                               clear_apertures=[_aperture(c) for c in a.get('clear_apertures', [])]))
+        if phase_element is not None:       # the reference tests hasattr(ifc, 'phase_element')
+            ifcs[-1].phase_element = phase_element
     gaps = [M.Gap(g['attributes']['thi'], _medium(g['attributes']['medium']))
             for g in sm_a['gaps']]
     osp_a = om['optical_spec']['attributes']

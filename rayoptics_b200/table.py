@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (rt_surface_desc, RT_MAX_COEFS, RT_MAX_APERTURES,
+from ._abi import (rt_surface_desc, RT_MAX_COEFS, RT_MAX_APERTURES, RT_MAX_PHASE_COEFS,
                    PROFILE_IDS, MODE_IDS, APERTURE_IDS, PHASE_IDS)
 
 
@@ -38,11 +38,35 @@ def _describe_interface(seg, prev_n, prev_zdir):
             raise UnsupportedInterfaceError(
                 f'{type(ifc).__name__} with a {kname} phase element is not supported by the B200 table')
         d.phase_kind = PHASE_IDS[kname]
-        d.phase_flags = int(bool(pe.ref_virtual)) | (int(bool(pe.obj_virtual)) << 1)
-        d.phase_ref_wl = float(pe.ref_wl)
-        for i in range(3):
-            d.phase_ref_pt[i] = float(pe.ref_pt[i])
-            d.phase_obj_pt[i] = float(pe.obj_pt[i])
+        if kname == 'HolographicElement':         # doe.py:326-395
+            d.phase_flags = int(bool(pe.ref_virtual)) | (int(bool(pe.obj_virtual)) << 1)
+            d.phase_ref_wl = float(pe.ref_wl)
+            for i in range(3):
+                d.phase_ref_pt[i] = float(pe.ref_pt[i])
+                d.phase_obj_pt[i] = float(pe.obj_pt[i])
+        elif kname == 'DiffractionGrating':       # doe.py:57-172 (phase() -> phase_ludwig)
+            if getattr(ifc, 'interact_mode', None) not in ('transmit', 'reflect'):
+                raise UnsupportedInterfaceError(
+                    'DiffractionGrating on an interface that neither transmits nor reflects')
+            d.phase_ref_wl = float(pe._grating_spacing_nm)
+            d.phase_order = float(pe.order)
+            for i in range(3):
+                d.phase_ref_pt[i] = float(pe.grating_normal[i])
+        else:                                     # DiffractiveElement, doe.py:214-323
+            fct = getattr(pe, 'phase_fct', None)
+            if getattr(fct, '__name__', None) != 'radial_phase_fct':
+                raise UnsupportedInterfaceError(
+                    'DiffractiveElement: only radial_phase_fct (doe.py:28-54) is compiled into the '
+                    f'table, not {getattr(fct, "__name__", fct)!r}')
+            cf = [float(c) for c in pe.coefficients]
+            if len(cf) > RT_MAX_PHASE_COEFS:
+                raise UnsupportedInterfaceError(
+                    f'DiffractiveElement with {len(cf)} coefficients (max {RT_MAX_PHASE_COEFS})')
+            d.phase_ref_wl = float(pe.ref_wl)
+            d.phase_order = float(pe.order)
+            d.n_phase_coefs = len(cf)
+            for i, c in enumerate(cf):
+                d.phase_coefs[i] = c
     profile = getattr(ifc, 'profile', None)
     pname = type(profile).__name__
     if type(ifc).__name__ == 'ThinLens':        # oprops/thinlens.py: no profile object

@@ -11,6 +11,9 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 MODEL_NAMES = ['singlet', 'dblgauss', 'triplet', 'rc', 'cellphone', 'cellphone_even',
                'evenasph', 'zoom52', 'thin_triplet', 'exotic']
+# models with diffractive phase elements: the reference evaluates x**k with libm pow(), so the
+# device carries tolerance parity there (the oracle, on the same libm, stays bit-exact)
+PHASE_MODEL_NAMES = ['hybrid', 'diffractive', 'diffractive_wild']
 
 
 def pytest_configure(config):

@@ -143,7 +143,7 @@ def main():
     rng = np.random.default_rng(0)
     plan = {'singlet': (7, 60), 'dblgauss': (5, 150), 'triplet': (5, 80), 'rc': (5, 60),
             'cellphone': (3, 100), 'cellphone_even': (3, 100), 'evenasph': (3, 100),
-            'zoom52': (3, 80), 'thin_triplet': (5, 100), 'exotic': (7, 400)}
+            'zoom52': (3, 80), 'thin_triplet': (5, 100), 'exotic': (7, 400), 'hybrid': (5, 300), 'diffractive': (7, 500), 'diffractive_wild': (9, 800)}
     only = sys.argv[1:]
     for name, (num, n_wild) in plan.items():
         if only and name not in only:
@@ -153,6 +153,8 @@ def main():
         grid_rays(opm, num, 0, rays)
         if name in ('dblgauss', 'rc', 'cellphone'):
             grid_rays(opm, 3, 1, rays)
+        if name == 'diffractive':
+            grid_rays(opm, 9, 1, rays)
         if name == 'exotic':
             grid_rays(opm, 5, 4, rays)
             grid_rays(opm, 3, 5, rays)

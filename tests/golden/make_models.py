@@ -212,6 +212,77 @@ def exotic():
     return finish(M.OpticalModel(sm, osp, name='exotic'), aim=False, apertures=False)
 
 
+def diffractive():
+    """Hybrid lens with the three diffractive phase elements of oprops/doe.py that have
+    closed forms: radial-phase DiffractiveElement on a glass->air surface (bends to and
+    from index 1, doe.py:296-299,319-321) and on an air->glass surface (no bends: the
+    reference tests n_in only), a transmission DiffractionGrating and a reflective one
+    on a concave mirror (z_dir flips, negative gap)."""
+    g1, g2 = M.AbbeGlass(1.5168, 64.2, 'g1'), M.AbbeGlass(1.6, 40.0, 'g2')
+    spec = [  # profile, mode, thi, medium, max_aperture, phase element
+        (M.Spherical(0.0), 'dummy', 1e10, M.Air(), 1e9, None),
+        (M.Spherical(0.02), 'transmit', 4.0, g1, 9.0, None),
+        (M.Spherical(-0.01), 'transmit', 10.0, M.Air(), 9.0,
+         M.DiffractiveElement(coefficients=[-1.0e-3, 1.0e-7, -2.0e-10], ref_wl=587.6, order=1)),
+        (M.Conic(0.004, cc=-0.5), 'transmit', 3.0, g2, 9.0,
+         M.DiffractiveElement(coefficients=[4.0e-4, -3.0e-8], ref_wl=550.0, order=-1)),
+        (M.Spherical(0.0), 'transmit', 20.0, M.Air(), 9.0, None),
+        (M.Spherical(0.0), 'transmit', 30.0, M.Air(), 12.0,
+         M.DiffractionGrating(order=1, grating_lpmm=100.0, interact_mode='transmit')),
+        (M.Spherical(-0.004), 'reflect', -60.0, M.Air(), 20.0,
+         M.DiffractionGrating(order=-1, grating_normal=[0.2, 1.0, 0.05], grating_lpmm=150.0,
+                              interact_mode='reflect')),
+        (M.Spherical(0.0), 'dummy', 0.0, None, 60.0, None)]
+    ifcs, gaps = [], []
+    for prf, mode, thi, med, ap, pe in spec:
+        sfc = M.Surface(profile=prf, interact_mode=mode, max_aperture=ap)
+        if pe is not None:
+            sfc.phase_element = pe
+        ifcs.append(sfc)
+        if med is not None:
+            gaps.append(M.Gap(thi, med))
+    wvls = [656.3, 587.6, 486.1]
+    sm = M.SequentialModel(ifcs, gaps, stop_surface=1, wvlns=wvls, ref_wvl=1)
+    fields = [M.Field(y=0.0), M.Field(y=1.0), M.Field(x=0.5, y=-1.0)]
+    osp = OpticalSpecs(WvlSpec(wvls, 1), PupilSpec(('object', 'epd'), 12.0),
+                       FieldSpec(('object', 'angle'), 1.0, fields))
+    return finish(M.OpticalModel(sm, osp, name='diffractive'), aim=False, apertures=False)
+
+
+def diffractive_wild():
+    """Strong diffractive elements at steep angles: exercises the failure branches of
+    oprops/doe.py (math.sqrt ValueError -> TraceEvanescentRayError in the DOE bends and
+    roots, np.sqrt NaN propagation in the grating) against the reference itself."""
+    g = M.ConstantIndex(1.7, 'n17')
+    spec = [
+        (M.Spherical(0.0), 'dummy', 20.0, M.Air(), 50.0, None),
+        (M.Spherical(0.0), 'transmit', 5.0, g, 40.0,
+         M.DiffractiveElement(coefficients=[4.0e-3, -2.0e-5], ref_wl=550.0, order=2)),
+        (M.Spherical(0.01), 'transmit', 10.0, M.Air(), 40.0,
+         M.DiffractiveElement(coefficients=[-3.0e-3, 2.0e-5, 1.0e-7], ref_wl=600.0, order=1)),
+        (M.Spherical(0.0), 'transmit', 10.0, M.Air(), 60.0,
+         M.DiffractionGrating(order=1, grating_normal=[0.0, 1.0, 0.0], grating_lpmm=800.0,
+                              interact_mode='transmit')),
+        (M.Spherical(0.002), 'reflect', -20.0, M.Air(), 80.0,
+         M.DiffractionGrating(order=1, grating_normal=[1.0, 0.3, 0.0], grating_lpmm=500.0,
+                              interact_mode='reflect')),
+        (M.Spherical(0.0), 'dummy', 0.0, None, 400.0, None)]
+    ifcs, gaps = [], []
+    for prf, mode, thi, med, ap, pe in spec:
+        sfc = M.Surface(profile=prf, interact_mode=mode, max_aperture=ap)
+        if pe is not None:
+            sfc.phase_element = pe
+        ifcs.append(sfc)
+        if med is not None:
+            gaps.append(M.Gap(thi, med))
+    wvls = [656.3, 587.6, 486.1]
+    sm = M.SequentialModel(ifcs, gaps, stop_surface=1, wvlns=wvls, ref_wvl=1)
+    fields = [M.Field(y=0.0), M.Field(y=4.0), M.Field(x=-3.0, y=2.0)]
+    osp = OpticalSpecs(WvlSpec(wvls, 1), PupilSpec(('object', 'epd'), 24.0),
+                       FieldSpec(('object', 'height'), 4.0, fields))
+    return finish(M.OpticalModel(sm, osp, name='diffractive_wild'), aim=False, apertures=False)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     models = {
@@ -227,6 +298,9 @@ def main():
         # 3 ThinLens interfaces (HolographicElement phase), models/thin_triplet.roa
         'thin_triplet': lambda: from_roa('models/thin_triplet.roa', 'thin_triplet'),
         'exotic': exotic,
+        'hybrid': lambda: from_roa('models/HybridAchromat.roa', 'hybrid'),
+        'diffractive': diffractive,
+        'diffractive_wild': diffractive_wild,
     }
     only = sys.argv[1:]
     for name, fn in models.items():

@@ -6,7 +6,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, MODEL_NAMES, load_model
+from conftest import ROOT, MODEL_NAMES, PHASE_MODEL_NAMES, load_model
 from rayoptics_b200 import _abi, table as T, model as M, engine as E, parallel as P
 
 
@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     """ctypes mirrors have the sizes nvcc/gcc give the C structs."""
     from oracle import rt_oracle
-    assert rt_oracle.lib().rto_sizeof_surface_desc() == C.sizeof(_abi.rt_surface_desc) == 544
+    assert rt_oracle.lib().rto_sizeof_surface_desc() == C.sizeof(_abi.rt_surface_desc) == 640
     assert C.sizeof(_abi.rt_opts) == 40
     assert C.sizeof(_abi.rt_out) == 19*8
     assert C.sizeof(_abi.rt_field_desc) == 72
@@ -47,7 +47,7 @@ def test_no_cpu_fallback_when_library_missing(monkeypatch):
         _abi.load_library()
 
 
-@pytest.mark.parametrize('name', MODEL_NAMES)
+@pytest.mark.parametrize('name', MODEL_NAMES + PHASE_MODEL_NAMES)
 def test_model_roundtrip_and_table(name):
     opm = load_model(name)
     sm = opm.seq_model

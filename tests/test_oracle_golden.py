@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, MODEL_NAMES, load_model, load_vectors
+from conftest import GOLDEN, MODEL_NAMES, PHASE_MODEL_NAMES, load_model, load_vectors
 from rayoptics_b200 import _abi, table as T, model as M
 
 
@@ -47,7 +47,7 @@ def run_oracle_on_vectors(oracle, name):
     return v, out
 
 
-@pytest.mark.parametrize('name', MODEL_NAMES)
+@pytest.mark.parametrize('name', MODEL_NAMES + PHASE_MODEL_NAMES)
 def test_oracle_matches_reference_vectors(oracle, name):
     v, out = run_oracle_on_vectors(oracle, name)
     assert (v['status'] <= 4).all()          # the reference never crashed on these
