@@ -214,6 +214,50 @@ def _vignetted(fld, px, py, apply_vignetting):
     return vx, vy
 
 
+class Ray:
+    """A ray at the given field and wavelength (analyses.py:46-118): ``ray_seg`` (the
+    segment at ``srf_indx``), ``ray_pkg`` when ``srf_save='all'``, ``t_abr`` the
+    transverse aberration w.r.t. the reference image point."""
+
+    def __init__(self, opt_model, p, f=0, wl=None, foc=None, image_pt_2d=None, image_delta=None,
+                 srf_indx=-1, srf_save='single', output_filter=None, rayerr_filter=None,
+                 color=None, clip_rays=False, table=None, device=0, tracer=None):
+        self.opt_model = opt_model
+        self.pupil = p
+        self.fld, self.wvl, self.foc = _resolve(opt_model, f, wl, foc)
+        self.image_pt_2d, self.image_delta = image_pt_2d, image_delta
+        self.output_filter, self.rayerr_filter = output_filter, rayerr_filter
+        self.clip_rays = clip_rays
+        self.color = color
+        self.srf_save, self.srf_indx = srf_save, srf_indx
+        self._engine = dict(table=table, device=device, tracer=tracer)
+        self.update_data()
+
+    def update_data(self, **kwargs):
+        from . import trace
+        ref_sphere, cr_pkg = trace.setup_pupil_coords(self.opt_model, self.fld, self.wvl, self.foc,
+                                                      image_pt=self.image_pt_2d,
+                                                      image_delta=self.image_delta, **self._engine)
+        build = kwargs.pop('build', 'rebuild')
+        if build == 'rebuild':
+            ray_pkg, ray_err = trace.trace_safe(self.opt_model, self.pupil, self.fld, self.wvl,
+                                                self.output_filter, self.rayerr_filter,
+                                                use_named_tuples=True,
+                                                check_apertures=self.clip_rays, **self._engine,
+                                                **kwargs)
+            if ray_pkg is None:
+                raise ray_err if ray_err is not None else RuntimeError('ray failed')
+            self.ray_seg = ray_pkg.ray[self.srf_indx]
+            if self.srf_save == 'all':
+                self.ray_pkg = ray_pkg
+        ray_seg = self.ray_seg
+        dist = self.foc/ray_seg[1][2]
+        defocused_pt = ray_seg[0] + dist*ray_seg[1]
+        reference_image_pt = ref_sphere[0]
+        self.t_abr = defocused_pt[:2] - reference_image_pt[:2]
+        return self
+
+
 class RayFan:
     """A fan of rays across the pupil (analyses.py:121-187).
 

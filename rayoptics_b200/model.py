@@ -516,6 +516,99 @@ class SequentialModel:
                                      rndx,
                                      self.z_dir[start:stop:step])))
 
+    # -- analysis drivers of the reference's SequentialModel (seq/sequential.py:1006-1135):
+    #    same arguments and return shapes, rays traced in one launch per (field, wavelength)
+    def trace(self, pt0, dir0, wvl, **kwargs):
+        from . import raytrace
+        return raytrace.trace(self, pt0, dir0, wvl, **kwargs)
+
+    def trace_fan(self, fct, fi, xy, num_rays=21, **kwargs):
+        """xy determines whether x (=0) or y (=1) fan (sequential.py:1006-1056).
+        Returns ``fans_x, fans_y, (max_rho_val, max_y_val), render_colors``."""
+        from . import trace
+        opm = self.opt_model
+        osp = opm.optical_spec
+        fld = osp.field_of_view.fields[fi]
+        wvl = self.central_wavelength()
+        foc = osp.defocus.get_focus()
+        engine = {k: kwargs.pop(k) for k in ('table', 'device', 'tracer') if k in kwargs}
+        rs_pkg, cr_pkg = trace.setup_pupil_coords(opm, fld, wvl, foc, **engine)
+        fld.chief_ray = cr_pkg
+        fld.ref_sphere = rs_pkg
+        ref_img_pt = rs_pkg[0]      # central-wavelength image point for every wavelength
+        wvls = osp.spectral_region
+        fans_x, fans_y, rc = [], [], []
+        fan_start, fan_stop = np.array([0., 0.]), np.array([0., 0.])
+        fan_start[xy], fan_stop[xy] = -1.0, 1.0
+        fan_def = [fan_start, fan_stop, num_rays]
+        max_rho_val = max_y_val = 0.0
+        for wi, wvl in enumerate(wvls.wavelengths):
+            rc.append(wvls.render_colors[wi])
+            rs_pkg, cr_pkg = trace.setup_pupil_coords(opm, fld, wvl, foc, image_pt=ref_img_pt,
+                                                      **engine)
+            fld.chief_ray = cr_pkg
+            fld.ref_sphere = rs_pkg
+            fan = trace.trace_fan(opm, fan_def, fld, wvl, foc,
+                                  img_filter=lambda p, ray_pkg, wvl=wvl:
+                                  fct(p, xy, ray_pkg, fld, wvl, foc), **engine, **kwargs)
+            f_x, f_y = [], []
+            for p, y_val in fan:
+                f_x.append(p[xy])
+                f_y.append(y_val)
+                max_rho_val = max(max_rho_val, abs(p[xy]))
+                max_y_val = max(max_y_val, abs(y_val))
+            fans_x.append(f_x)
+            fans_y.append(f_y)
+        return np.array(fans_x), np.array(fans_y), (max_rho_val, max_y_val), rc
+
+    def trace_grid(self, fct, fi, wl=None, num_rays=21, form='grid', append_if_none=True,
+                   **kwargs):
+        """fct is applied to the raw grid and returned as a grid (sequential.py:1058-1085).
+        Returns ``grids, render_colors``."""
+        from . import trace
+        opm = self.opt_model
+        osp = opm.optical_spec
+        wvls = osp.spectral_region
+        wvl = self.central_wavelength()
+        wv_list = wvls.wavelengths if wl is None else [wl]
+        fld = osp.field_of_view.fields[fi]
+        foc = osp.defocus.get_focus()
+        engine = {k: kwargs.pop(k) for k in ('table', 'device', 'tracer') if k in kwargs}
+        rs_pkg, cr_pkg = trace.setup_pupil_coords(opm, fld, wvl, foc, **engine)
+        fld.chief_ray = cr_pkg
+        fld.ref_sphere = rs_pkg
+        grids = []
+        grid_def = [np.array([-1., -1.]), np.array([1., 1.]), num_rays]
+        for wi, wvl in enumerate(wv_list):
+            grid = trace.trace_grid(opm, grid_def, fld, wvl, foc, form=form,
+                                    append_if_none=append_if_none,
+                                    img_filter=lambda p, ray_pkg, wi=wi, wvl=wvl:
+                                    fct(p, wi, ray_pkg, fld, wvl, foc), **engine, **kwargs)
+            grids.append(grid)
+        return grids, wvls.render_colors
+
+    def trace_wavefront(self, fld, wvl, foc, num_rays=32, **engine):
+        """``[num, num, 3]`` grid of (pupil x, pupil y, OPD in waves), 0 where the ray does
+        not reach the image (sequential.py:1087-1119)."""
+        from . import trace, waveabr
+        opm = self.opt_model
+        rs_pkg, cr_pkg = trace.setup_pupil_coords(opm, fld, wvl, foc, **engine)
+        fld.chief_ray = cr_pkg
+        fld.ref_sphere = rs_pkg
+        fod = opm.optical_spec.fod
+
+        def wave(p, ray_pkg):
+            if ray_pkg is not None:
+                opd = waveabr.wave_abr_full_calc(fod, fld, wvl, foc, ray_pkg, fld.chief_ray,
+                                                 fld.ref_sphere)
+                opd = opd/opm.nm_to_sys_units(wvl)
+            else:
+                opd = 0.0
+            return np.array([p[0], p[1], opd])
+
+        grid_def = (np.array([-1., -1.]), np.array([1., 1.]), num_rays)
+        return trace.trace_grid(opm, grid_def, fld, wvl, foc, img_filter=wave, form='grid', **engine)
+
     # -- persistence
     def to_dict(self):
         ifcs = []
@@ -651,6 +744,7 @@ class OpticalModel:
         self.seq_model = seq_model
         self.optical_spec = optical_spec
         self.analysis_results = {'parax_data': None}
+        seq_model.opt_model = self
         if optical_spec is not None:
             optical_spec.opt_model = self
             optical_spec.update_model()

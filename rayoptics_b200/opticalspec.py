@@ -32,6 +32,7 @@ class WvlSpec:
         self.wavelengths = list(wavelengths)
         self.reference_wvl = ref_wl
         self.spectral_wts = list(spectral_wts) if spectral_wts else [1.0]*len(self.wavelengths)
+        self.render_colors = [None]*len(self.wavelengths)   # plotting detail of the reference
 
     @property
     def central_wvl(self):
@@ -72,6 +73,10 @@ class FocusRange:
     def __init__(self, focus_shift=0.0, defocus_range=0.0):
         self.focus_shift = focus_shift
         self.defocus_range = defocus_range
+
+    def get_focus(self, fr=0.0):
+        """opticalspec.py FocusRange.get_focus: focus for the fractional range position"""
+        return self.focus_shift + fr*self.defocus_range
 
 
 class OpticalSpecs:

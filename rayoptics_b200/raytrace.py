@@ -126,10 +126,19 @@ def trace_raw(path, pt0, dir0, wvl, eps=1.0e-12, check_apertures=False,
     full = res.full[:, :, 0].cpu().numpy()
     meta = torch.stack([res.status, res.fail_surf, res.n_seg]).cpu().numpy()[:, 0]
     op = float(res.op.cpu().numpy()[0])
-    status, surf, n_seg = int(meta[0]), int(meta[1]), int(meta[2])
+    ray_pkg, err = package_ray(segs, full, op, int(meta[0]), int(meta[1]), int(meta[2]), wvl)
+    if err is not None:
+        raise err
+    return ray_pkg
+
+
+def package_ray(segs, full, op, status, surf, n_seg, wvl):
+    """One ray of a bundle / grid result -> ``((ray, op, wvl), None)`` or
+    ``(None, TraceError)`` with the error filled as raytrace.py:231-257 fills it.
+    ``segs``: the path list, ``full``: ``[n_ifc, 10]`` segments of this ray."""
     ray = _ray_list(full, n_seg)
     if status == _abi.RAY_OK:
-        return ray, op, wvl
+        return (ray, op, wvl), None
     ifc = segs[surf][0] if 0 <= surf < len(segs) else None
     if status == _abi.RAY_MISSED:
         err = TraceMissedSurfaceError(ifc, None)
@@ -153,7 +162,7 @@ def trace_raw(path, pt0, dir0, wvl, eps=1.0e-12, check_apertures=False,
         err.ray_pkg = None
     else:
         err.ray_pkg = ray, op, wvl
-    raise err
+    return None, err
 
 
 def trace(seq_model, pt0, dir0, wvl, **kwargs):

@@ -1,0 +1,210 @@
+"""Batched drivers with the call surface of ``rayoptics.raytr.trace``.
+
+The reference's ``trace_fan`` / ``trace_grid`` (/root/reference/src/rayoptics/raytr/trace.py:537-605)
+call ``trace_safe`` -> ``trace_base`` -> ``rt.trace`` once per pupil point and hand
+every ray to a Python callback (``img_filter``).  Here all pupil points of one
+(field, wavelength) go through ONE grid launch that writes whole rays; the result
+containers (``RaySeg`` / ``RayPkg`` / ``RayResult``, raytr/__init__.py:24-40), the
+``output_filter`` / ``rayerr_filter`` conventions of ``trace_safe`` (trace.py:159-219),
+the accumulated pupil stepping and the shape of what is returned are the
+reference's, so ``SequentialModel.trace_fan / trace_grid / trace_wavefront``
+(seq/sequential.py:1006-1120) and the figure classes above them keep working.
+
+The callbacks stay Python (they are user code); only the ray tracing is batched.
+There is no CPU path: the default tracer is the CUDA engine.  ``tracer=`` is a seam
+for tests (the CPU suite passes the oracle to check the host logic) -- same idea
+as ``vigcalc``'s ``trace_fn``.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+
+import numpy as np
+
+from . import engine as E
+from . import waveabr as W
+
+RayResult = namedtuple('RayResult', ['pkg', 'err'])
+RayPkg = namedtuple('RayPkg', ['ray', 'op', 'wvl'])
+RaySeg = namedtuple('RaySeg', ['p', 'd', 'dst', 'nrml'])
+
+_TRACE_RAW_KEYS = ('eps', 'check_apertures', 'intersect_obj', 'filter_out_phantoms',
+                   'first_surf', 'last_surf', 'pt_inside_fuzz')
+
+
+def _table_for(opt_model, table=None, device=0):
+    from .analyses import _table_for as tf
+    return tf(opt_model, table, device)
+
+
+def cuda_tracer(opt_model, table, fld, wvl, px, py, apply_vignetting, trace_kwargs):
+    """Whole rays of the pupil points ``(px[k], py[k])`` of one field / wavelength:
+    one paired-grid launch.  Returns host arrays ``full [n_ifc, 10, n]``, ``op``,
+    ``status``, ``fail_surf``, ``n_seg``."""
+    osp, sm = opt_model.optical_spec, opt_model.seq_model
+    recs, eprad, z_pupil = osp.grid_fields([fld])
+    grid = E.PupilGrid(recs, [table.wvl_index(wvl)], px, py, eprad, z_pupil,
+                       apply_vignetting=apply_vignetting, flip_z_dir=sm.z_dir[0], paired=True,
+                       device=table.device)
+    kw = {k: v for k, v in trace_kwargs.items() if k in _TRACE_RAW_KEYS}
+    kw.setdefault('check_apertures', False)          # trace_raw's default (raytrace.py:83)
+    res = E.trace_grid(table, grid, outputs=('op', 'status', 'fail_surf', 'n_seg'), full=True,
+                       summary=False, **kw)
+    out = {'full': res.full.cpu().numpy(), 'op': res.op.cpu().numpy(),
+           'status': res.status.cpu().numpy(), 'fail_surf': res.fail_surf.cpu().numpy(),
+           'n_seg': res.n_seg.cpu().numpy()}
+    grid.close()
+    return out
+
+
+def trace_pupil_rays(opt_model, pupils, fld, wvl, output_filter=None, rayerr_filter=None,
+                     apply_vignetting=True, table=None, device=0, tracer=None, **kwargs):
+    """``[trace_safe(opt_model, p, fld, wvl, output_filter, rayerr_filter, **kwargs) for p in
+    pupils]`` (trace.py:159-219) with one launch.  Returns a list of ``RayResult``."""
+    from . import raytrace as RT
+    if opt_model.optical_spec.field_of_view.is_wide_angle:
+        raise NotImplementedError('wide-angle start rays (raytr/wideangle.py) are not generated on '
+                                  'the device yet')
+    if kwargs.get('pupil_type', 'rel pupil') != 'rel pupil':
+        raise NotImplementedError("pupil_type other than 'rel pupil'")
+    use_named_tuples = kwargs.get('use_named_tuples', False)
+    pts = np.array([np.array(p, dtype=float) for p in pupils], dtype=float).reshape(-1, 2)
+    if tracer is None:
+        table = _table_for(opt_model, table, device)
+        tracer = cuda_tracer
+    r = tracer(opt_model, table, fld, wvl, pts[:, 0].copy(), pts[:, 1].copy(), apply_vignetting,
+               kwargs)
+    segs = list(opt_model.seq_model.path(wvl))
+    results = []
+    for k in range(pts.shape[0]):
+        pkg, err = RT.package_ray(segs, r['full'][:, :, k], float(r['op'][k]), int(r['status'][k]),
+                                  int(r['fail_surf'][k]), int(r['n_seg'][k]), wvl)
+        if err is not None:
+            if rayerr_filter == 'full':
+                if err.ray_pkg is not None:
+                    ray, op_delta, w = err.ray_pkg
+                    err.ray_pkg = RayPkg([RaySeg(*rs) for rs in ray], op_delta, w)
+                results.append(RayResult(err.ray_pkg, err))
+            elif rayerr_filter == 'summary':
+                err.ray_pkg = None
+                results.append(RayResult(None, err))
+            else:
+                results.append(RayResult(None, None))
+            continue
+        if use_named_tuples:
+            ray, op_delta, w = pkg
+            pkg = RayPkg([RaySeg(*rs) for rs in ray], op_delta, w)
+        if output_filter is None:
+            results.append(RayResult(pkg, None))
+        elif output_filter == 'last':
+            ray, op_delta, w = pkg
+            results.append(RayResult(RayPkg([ray[-1]], op_delta, w), None))
+        else:
+            results.append(RayResult(output_filter(pkg), None))
+    return results
+
+
+def trace_safe(opt_model, pupil, fld, wvl, output_filter, rayerr_filter, **kwargs):
+    """trace.py:159-219 for one pupil point."""
+    return trace_pupil_rays(opt_model, [pupil], fld, wvl, output_filter, rayerr_filter, **kwargs)[0]
+
+
+def trace_base(opt_model, pupil, fld, wvl, apply_vignetting=True, **kwargs):
+    """trace.py:253-310 for one pupil point: the ray package, or the TraceError raised."""
+    res = trace_pupil_rays(opt_model, [pupil], fld, wvl, None, 'full',
+                           apply_vignetting=apply_vignetting, **kwargs)[0]
+    if res.err is not None:
+        raise res.err
+    return res.pkg
+
+
+def trace_fan(opt_model, fan_rng, fld, wvl, foc, img_filter=None, **kwargs):
+    """trace.py:537-560: ``[[pupil, img_filter(pupil, ray_pkg)], ...]`` for the rays that
+    yield a package; pupil coordinates are the accumulated ``start += step`` values."""
+    output_filter = kwargs.pop('output_filter', None)
+    rayerr_filter = kwargs.pop('rayerr_filter', None)
+    start = np.array(fan_rng[0], dtype=float)
+    stop = fan_rng[1]
+    num = fan_rng[2]
+    step = (stop - start)/(num - 1)
+    pupils = []
+    for _ in range(num):
+        pupils.append(np.array(start))
+        start += step
+    results = trace_pupil_rays(opt_model, pupils, fld, wvl, output_filter, rayerr_filter, **kwargs)
+    fan = []
+    for pupil, ray_result in zip(pupils, results):
+        if ray_result.pkg is not None:
+            if img_filter:
+                fan.append([pupil, img_filter(pupil, ray_result.pkg)])
+            else:
+                fan.append([pupil, ray_result.pkg])
+    return fan
+
+
+def trace_grid(opt_model, grid_rng, fld, wvl, foc, img_filter=None, form='grid',
+               append_if_none=True, **kwargs):
+    """trace.py:563-605: x outer / y inner, ``check_apertures=True``, same nesting
+    (``form='grid'`` rows or one flat ``'list'``) and ``append_if_none`` handling."""
+    output_filter = kwargs.pop('output_filter', None)
+    rayerr_filter = kwargs.pop('rayerr_filter', None)
+    start = np.array(grid_rng[0], dtype=float)
+    stop = grid_rng[1]
+    num = grid_rng[2]
+    step = np.array((stop - start)/(num - 1))
+    pupils = []
+    for i in range(num):
+        for j in range(num):
+            pupils.append(np.array(start))
+            start[1] += step[1]
+        start[0] += step[0]
+        start[1] = grid_rng[0][1]
+    kwargs['check_apertures'] = True
+    results = trace_pupil_rays(opt_model, pupils, fld, wvl, output_filter, rayerr_filter, **kwargs)
+    grid = []
+    k = 0
+    for i in range(num):
+        working_grid = grid if form == 'list' else []
+        for j in range(num):
+            pupil, ray_result = pupils[k], results[k]
+            k += 1
+            if ray_result.pkg is not None:
+                if img_filter:
+                    working_grid.append(img_filter(pupil, ray_result.pkg))
+                else:
+                    working_grid.append([pupil[0], pupil[1], ray_result.pkg])
+            else:                                   # ray outside pupil or failed
+                if img_filter:
+                    result = img_filter(pupil, None)
+                    if result is not None or append_if_none:
+                        working_grid.append(result)
+                elif append_if_none:
+                    working_grid.append([pupil[0], pupil[1], None])
+        if form == 'grid':
+            grid.append(working_grid)
+    try:
+        return np.array(grid)
+    except ValueError:                              # ragged / object entries (numpy >= 1.24)
+        return np.array(grid, dtype=object)
+
+
+def trace_chief_ray(opt_model, fld, wvl, foc, table=None, device=0, tracer=None):
+    """trace.py:513-534: ``(chief_ray, cr_exp_seg)``; pupil (0, 0), apertures not checked."""
+    res = trace_pupil_rays(opt_model, [np.array([0., 0.])], fld, wvl, None, 'full', table=table,
+                           device=device, tracer=tracer)[0]
+    if res.err is not None:
+        raise res.err
+    cr = RayPkg(*res.pkg)
+    fod = opt_model.optical_spec.fod
+    cr_exp_seg = W.transfer_to_exit_pupil((cr.ray[-2][0], cr.ray[-2][1]), fod.exp_dist)
+    return cr, cr_exp_seg
+
+
+def setup_pupil_coords(opt_model, fld, wvl, foc, image_pt=None, image_delta=None, table=None,
+                       device=0, tracer=None):
+    """trace.py:607-624: ``(ref_sphere, chief_ray_pkg)`` of a field / wavelength."""
+    chief_ray_pkg = trace_chief_ray(opt_model, fld, wvl, foc, table=table, device=device,
+                                    tracer=tracer)
+    ref_sphere = W.calculate_reference_sphere(opt_model, fld, wvl, foc, chief_ray_pkg,
+                                              image_pt_2d=image_pt, image_delta=image_delta)
+    return ref_sphere, chief_ray_pkg

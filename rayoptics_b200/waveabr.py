@@ -138,3 +138,41 @@ def setup_tiles(opt_model, table, fields, wvls, foc, image_pt_2d=None, image_del
             row.append((crp, rs))
         pkgs.append(row)
     return wave, ref_img, pkgs
+
+
+# --- per-ray OPD on the host (for img_filter callbacks of trace.trace_fan/trace_grid;
+#     the batched analyses use the kernel epilogue instead) ---------------------------------
+def eic_distance(r, r0):
+    """equally inclined chord distance, waveabr.py:117-132 (r = (p, d))"""
+    e = (np.dot(r[1] + r0[1], r[0] - r0[0])/(1. + np.dot(r[1], r0[1])))
+    return e
+
+
+def wave_abr_full_calc(fod, fld, wvl, foc, ray_pkg, chief_ray_pkg_, ref_sphere):
+    """OPD of a ray w.r.t. the chief ray on a FINITE reference sphere:
+    ``wave_abr_full_calc_finite_pup`` (waveabr.py:255-305), same expressions
+    (``F**2`` on a numpy scalar included).  System units."""
+    from math import sqrt
+    image_pt, ref_dir, ref_sphere_radius, lcl_tfrm_last = ref_sphere
+    if not np.isfinite(ref_sphere_radius) or abs(ref_sphere_radius) > 1e8:
+        raise NotImplementedError('infinite reference sphere (waveabr.py:356-488) not implemented')
+    cr, cr_exp_seg = chief_ray_pkg_
+    cr_ray, cr_op, _ = cr
+    cr_exp_pt, cr_exp_dir, cr_exp_dist, ifc, cr_b4_pt, cr_b4_dir = cr_exp_seg
+    ray, ray_op, _ = ray_pkg
+    k = -2
+    e1 = eic_distance((ray[1][0], ray[0][1]), (cr_ray[1][0], cr_ray[0][1]))
+    ekp = eic_distance((ray[k][0], ray[k][1]), (cr_ray[k][0], cr_ray[k][1]))
+    b4_pt, b4_dir = ray[k][0], ray[k][1]            # transform_after_surface(None, ...)
+    dst = ekp - cr_exp_dist
+    eic_exp_pt = b4_pt - dst*b4_dir
+    p_coord = eic_exp_pt - cr_exp_pt
+    F = ref_dir.dot(b4_dir) - b4_dir.dot(p_coord)/ref_sphere_radius
+    J = p_coord.dot(p_coord)/ref_sphere_radius - 2.0*ref_dir.dot(p_coord)
+    sign_soln = -1 if ref_dir[2]*cr_ray[-1][1][2] < 0 else 1
+    denom = F + sign_soln*sqrt(F**2 + J/ref_sphere_radius)
+    ep = 0 if denom == 0 else J/denom
+    n_obj = abs(fod.n_obj)
+    n_img = abs(fod.n_img)
+    opd = -n_obj*e1 - ray_op + n_img*ekp + cr_op - n_img*ep
+    return opd

@@ -1,0 +1,165 @@
+"""Host logic of rayoptics_b200/trace.py, SequentialModel.trace_fan/trace_grid/
+trace_wavefront and analyses.Ray (the reference's raytr/trace.py:159-219,537-624,
+seq/sequential.py:1006-1120, raytr/analyses.py:46-118).
+
+CPU: the `tracer=` seam is fed by the oracle, the expected values come from the
+reference's own trace_raw on start rays built by opticalspec.ray_start_from_osp
+(skipped without /root/reference) and from the golden OPD vectors.  The GPU run of the
+same calls is in tests/test_zz_gpu_additions.py.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_model
+from rayoptics_b200 import _abi, engine as E, table as T, trace as TR, waveabr as W
+from rayoptics_b200 import analyses as A
+
+
+def oracle_tracer(opt_model, table, fld, wvl, px, py, apply_vignetting, trace_kwargs):
+    """tracer= seam: start rays + trace by oracle/rt_oracle.c (test infrastructure)."""
+    from oracle import rt_oracle
+    osp, sm = opt_model.optical_spec, opt_model.seq_model
+    descs, n_by_wvl, wvls = T.describe_model(sm)
+    recs, eprad, z_pupil = osp.grid_fields([fld])
+    spec = E.PupilGridSpec(recs, [sm.index_for_wavelength(wvl)], px, py, eprad, z_pupil,
+                           apply_vignetting=apply_vignetting, flip_z_dir=sm.z_dir[0], paired=True)
+    p, d, wv, _ = rt_oracle.grid_start_rays(spec.c_spec(), 0, spec.n_rays)
+    kw = {k: v for k, v in trace_kwargs.items() if k in TR._TRACE_RAW_KEYS}
+    kw.setdefault('check_apertures', False)
+    kw.setdefault('first_surf', 1)
+    kw.setdefault('last_surf', len(descs) - 2)
+    r = rt_oracle.trace_bundle(descs, n_by_wvl, p, d, wv, _abi.make_opts(**kw), want_full=True,
+                               wvls=wvls)
+    return r
+
+
+def ref_pkg(opm, fld, wvl, pupil, apply_vignetting=True, **kw):
+    from oracle import ref_harness as rh
+    osp, sm = opm.optical_spec, opm.seq_model
+    vp = fld.apply_vignetting(np.array(pupil)) if apply_vignetting else np.array(pupil)
+    pt0, dir0 = osp.ray_start_from_osp(vp, fld)
+    if dir0[2]*sm.z_dir[0] < 0:
+        dir0 = -dir0
+    kw.setdefault('first_surf', 1)
+    kw.setdefault('last_surf', sm.get_num_surfaces() - 2)
+    return rh.ref_trace(rh.ref_path(sm, wvl), pt0, dir0, wvl, **kw)
+
+
+def assert_pkg_equals(pkg, ref):
+    ray, op, _ = pkg
+    assert len(ray) == ref['n_seg']
+    for k, seg in enumerate(ray):
+        assert np.array_equal(seg[0], ref['ray'][k, 0:3]) and np.array_equal(seg[1], ref['ray'][k, 3:6])
+        assert seg[2] == ref['ray'][k, 6] and np.array_equal(seg[3], ref['ray'][k, 7:10])
+    assert op == ref['op']
+
+
+needs_ref = pytest.mark.skipif(not __import__('oracle.ref_harness', fromlist=['x']).available(),
+                               reason='/root/reference not present')
+
+
+@needs_ref
+def test_trace_fan_and_grid_against_reference_rays():
+    opm = load_model('dblgauss')
+    osp = opm.optical_spec
+    fld, wvl = osp.field_of_view.fields[2], 486.1
+    fan_def = [np.array([0., -1.]), np.array([0., 1.]), 9]
+    fan = TR.trace_fan(opm, fan_def, fld, wvl, 0.0, tracer=oracle_tracer)
+    t = E.accumulated_steps(-1.0, 1.0, 9)
+    assert [f[0][1] for f in fan] == list(t)                  # accumulated pupil values
+    for pupil, pkg in fan:
+        assert_pkg_equals(pkg, ref_pkg(opm, fld, wvl, pupil))
+    # grid: check_apertures forced on, failed rays -> None entries, x outer / y inner
+    grid_def = [np.array([-1., -1.]), np.array([1., 1.]), 7]
+    seen = []
+    g = TR.trace_grid(opm, grid_def, fld, wvl, 0.0, tracer=oracle_tracer, form='list',
+                      img_filter=lambda p, pkg: seen.append((tuple(p), pkg)) or (None if pkg is None else 1.0),
+                      append_if_none=False)
+    assert len(seen) == 49
+    xs = E.accumulated_steps(-1.0, 1.0, 7)
+    assert seen[8][0] == (xs[1], xs[1]) and seen[6][0] == (xs[0], xs[6])
+    n_ok = 0
+    for pupil, pkg in seen:
+        ref = ref_pkg(opm, fld, wvl, pupil, check_apertures=True)
+        assert (pkg is None) == (ref['status'] != 0)
+        if pkg is not None:
+            n_ok += 1
+            assert_pkg_equals(pkg, ref)
+    assert 0 < n_ok < 49 and g.shape == (n_ok,)
+    g2 = TR.trace_grid(opm, grid_def, fld, wvl, 0.0, tracer=oracle_tracer)
+    assert g2.shape[:2] == (7, 7)
+
+
+def test_trace_safe_filters_and_errors():
+    opm = load_model('dblgauss')
+    fld, wvl = opm.optical_spec.field_of_view.fields[0], 587.6
+    kw = dict(tracer=oracle_tracer, check_apertures=True)
+    ok, bad = np.array([0., 0.5]), np.array([0., 1.3])
+    r = TR.trace_safe(opm, ok, fld, wvl, None, None, use_named_tuples=True, **kw)
+    assert r.err is None and isinstance(r.pkg, TR.RayPkg) and isinstance(r.pkg.ray[0], TR.RaySeg)
+    assert len(r.pkg.ray) == opm.seq_model.get_num_surfaces() and r.pkg.wvl == wvl
+    last = TR.trace_safe(opm, ok, fld, wvl, 'last', None, **kw)
+    assert len(last.pkg.ray) == 1 and np.array_equal(last.pkg.ray[0][0], r.pkg.ray[-1].p)
+    assert TR.trace_safe(opm, ok, fld, wvl, lambda pkg: 42, None, **kw).pkg == 42
+    assert TR.trace_safe(opm, bad, fld, wvl, None, None, **kw) == (None, None)
+    s = TR.trace_safe(opm, bad, fld, wvl, None, 'summary', **kw)
+    assert s.pkg is None and type(s.err).__name__ == 'TraceRayBlockedError' and s.err.ray_pkg is None
+    f = TR.trace_safe(opm, bad, fld, wvl, None, 'full', **kw)
+    assert isinstance(f.pkg, TR.RayPkg) and f.err.surf == len(f.pkg.ray) - 1 and f.pkg is f.err.ray_pkg
+    with pytest.raises(type(f.err)):
+        TR.trace_base(opm, bad, fld, wvl, **kw)
+
+
+def test_sequential_model_drivers_and_ray():
+    opm = load_model('dblgauss')
+    sm, osp = opm.seq_model, opm.optical_spec
+    fod = osp.fod
+
+    def y_abr(p, xy, ray_pkg, fld, wvl, foc):
+        return ray_pkg[0][-1][0][xy] - fld.ref_sphere[0][xy]
+
+    fx, fy, (max_rho, max_y), rc = sm.trace_fan(y_abr, 1, 1, num_rays=11, tracer=oracle_tracer)
+    assert fx.shape == fy.shape == (3, 11) and max_rho == 1.0 and max_y > 0 and len(rc) == 3
+    assert abs(fy[1, 5]) < 1e-12                    # chief ray of the central wavelength
+
+    def opd(p, wi, ray_pkg, fld, wvl, foc):
+        if ray_pkg is None:
+            return None
+        return W.wave_abr_full_calc(fod, fld, wvl, foc, ray_pkg, fld.chief_ray, fld.ref_sphere)
+
+    grids, _ = sm.trace_grid(opd, 0, wl=587.6, num_rays=9, form='list', append_if_none=False,
+                             tracer=oracle_tracer)
+    assert len(grids) == 1 and 20 < grids[0].shape[0] < 81 and np.isfinite(grids[0].astype(float)).all()
+    wf = sm.trace_wavefront(osp.field_of_view.fields[0], 587.6, 0.0, num_rays=8, tracer=oracle_tracer)
+    assert wf.shape == (8, 8, 3) and wf[0, 0, 2] == 0.0 and np.abs(wf[:, :, 2]).max() < 50
+    ray = A.Ray(opm, [0., 0.7], f=1, wl=656.3, srf_save='all', tracer=oracle_tracer)
+    assert ray.t_abr.shape == (2,) and len(ray.ray_pkg.ray) == sm.get_num_surfaces()
+    cr = A.Ray(opm, [0., 0.], f=1, tracer=oracle_tracer)
+    assert np.abs(cr.t_abr).max() == 0.0
+
+
+@pytest.mark.parametrize('name', ['dblgauss', 'rc'])
+def test_host_opd_matches_reference(oracle, name):
+    """waveabr.wave_abr_full_calc (numpy, for callbacks) against the reference's OPDs"""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, 'vectors', name + '_opd.npz'))
+    v = {k: z[k] for k in z.files}
+    opm = load_model(name)
+    osp, sm = opm.optical_spec, opm.seq_model
+    descs, n_by_wvl, _ = T.describe_model(sm)
+    n_ifc = len(descs)
+    opts = _abi.make_opts(first_surf=1, last_surf=n_ifc - 2, check_apertures=True)
+    r = oracle.trace_bundle(descs, n_by_wvl, v['p0'], v['d0'], v['wvl_idx'], opts, want_full=True)
+    fields, wvls = osp.field_of_view.fields, sm.wvlns
+    checked = 0
+    for k in np.nonzero(v['status'] == 0)[0][::7]:
+        fi, wi = divmod(int(v['tile'][k]), len(wvls))
+        fld, wvl = fields[fi], wvls[wi]
+        rs, crp = TR.setup_pupil_coords(opm, fld, wvl, 0.0, tracer=oracle_tracer)
+        pkg, err = __import__('rayoptics_b200.raytrace', fromlist=['x']).package_ray(
+            list(sm.path(wvl)), r['full'][:, :, k], float(r['op'][k]), 0, -1, n_ifc, wvl)
+        got = W.wave_abr_full_calc(osp.fod, fld, wvl, 0.0, pkg, crp, rs)
+        assert got == v['opd'][k]
+        checked += 1
+    assert checked > 20

@@ -4,16 +4,19 @@ DiffractiveElement; oprops/doe.py) -- TOLERANCE parity: the reference evaluates
 pow_int_rn), so ~0.1 % of the rays differ in the last bits.  Bar: status, failing
 surface and segment counts exact; coordinates within 1e-11 mm (north star 1e-10).
 
-Sorted last on purpose: these kernels were added after the last GPU session of the
-round in which they were written; the host-compiled device source
-(tests/test_hostsim.py) is what pinned them first.
+Also here: the batched drivers of rayoptics_b200/trace.py through the CUDA engine.
+
+Sorted last on purpose: this code was added after the last GPU session of the round in
+which it was written; the host-compiled device source (tests/test_hostsim.py) and the
+oracle-fed `tracer=` seam (tests/test_trace_drivers.py) are what pinned it first.
 """
 import numpy as np
 import pytest
 import torch
 
 from conftest import PHASE_MODEL_NAMES, load_model, load_vectors, seeded_bundle
-from rayoptics_b200 import _abi, engine as E, table as T
+from rayoptics_b200 import _abi, engine as E, table as T, trace as TR, analyses as A
+from test_trace_drivers import oracle_tracer
 
 pytestmark = pytest.mark.gpu
 TOL_MM = 1e-11
@@ -89,3 +92,29 @@ def test_cuda_phase_grid(oracle):
     assert np.abs(np_(r.op)[ok] - ref['op'][ok]).max() <= TOL_MM*1e3
     summ = np_(r.summary)
     assert summ[:, 0].sum() == ok.sum()
+
+
+def test_cuda_drivers_match_oracle_seam():
+    """the same driver calls through the CUDA engine give the same packages"""
+    opm = load_model('dblgauss')
+    fld, wvl = opm.optical_spec.field_of_view.fields[1], 656.3
+    fan_def = [np.array([0., -1.]), np.array([0., 1.]), 13]
+    a = TR.trace_fan(opm, fan_def, fld, wvl, 0.0)
+    b = TR.trace_fan(opm, [np.array([0., -1.]), np.array([0., 1.]), 13], fld, wvl, 0.0,
+                     tracer=oracle_tracer)
+    assert len(a) == len(b) == 13
+    for (pa, ka), (pb, kb) in zip(a, b):
+        assert np.array_equal(pa, pb) and ka[1] == kb[1]
+        for sa, sb in zip(ka[0], kb[0]):
+            assert all(np.array_equal(x, y) for x, y in zip(sa, sb))
+    grid_def = [np.array([-1., -1.]), np.array([1., 1.]), 9]
+    ga = TR.trace_grid(opm, grid_def, fld, wvl, 0.0, img_filter=lambda p, k: -1.0 if k is None else k[1])
+    gb = TR.trace_grid(opm, [np.array([-1., -1.]), np.array([1., 1.]), 9], fld, wvl, 0.0,
+                       img_filter=lambda p, k: -1.0 if k is None else k[1], tracer=oracle_tracer)
+    assert np.array_equal(ga, gb) and ga.shape == (9, 9)
+    ray = A.Ray(opm, [0.2, -0.4], f=2, wl=486.1)
+    ref = A.Ray(opm, [0.2, -0.4], f=2, wl=486.1, tracer=oracle_tracer)
+    assert np.array_equal(ray.t_abr, ref.t_abr)
+    wf = opm.seq_model.trace_wavefront(fld, wvl, 0.0, num_rays=8)
+    wf2 = opm.seq_model.trace_wavefront(fld, wvl, 0.0, num_rays=8, tracer=oracle_tracer)
+    assert np.array_equal(wf, wf2)
