@@ -231,7 +231,12 @@ typedef struct rt_grid_spec {
                                   (raytr/waveabr.py:255-305, 24-76, 79-113):
                                   0-2 cr.ray[1].p   3-5 cr.ray[0].d   6-8 cr.ray[-2].p  9-11 cr.ray[-2].d
                                   12 cr_op  13-15 cr_exp_pt  16 cr_exp_dist  17-19 ref_dir
-                                  20 ref_sphere_radius  21 sign_soln (+1/-1)  22 |n_obj|  23 |n_img| */
+                                  20 ref_sphere_radius  21 sign_soln (+1/-1)  22 |n_obj|  23 |n_img|
+                                  A record with [21] == 0 selects wave_abr_full_calc_inf_ref (waveabr.py:356-420,
+                                  exit pupil beyond 1e8; image gap without tilt/decenter):
+                                  0-2 cr.ray[1].p  3-5 cr.ray[0].d  6-8 cr.ray[-1].p  9-11 cr.ray[-1].d
+                                  12 V_BE = cr_op + op_cr_b4  13-15 image_pt  17-19 d_cr_b4  20 t_z of the
+                                  image gap  22 |n_obj|  23 |n_img| */
     int32_t apply_vignetting;  /* trace_base(apply_vignetting=...) trace.py:289-292 */
     int32_t flip_z_dir;        /* seq_model.z_dir[0]: dir0 is negated when dir0.z*z_dir < 0 (trace.py:305-308) */
     int32_t paired;            /* 0: product grid pupil_x[i] x pupil_y[j]; 1: ray list -- ny must be 1 and

@@ -841,9 +841,62 @@ static double eic_distance(const double p[3], const double d[3], const double p0
     return dot3(a, b)/(1. + dot3(d, d0));
 }
 
-double rto_wave_opd(const double *W, const double p1[3], const double d0[3],
-                    const double pk[3], const double dk[3], double ray_op)
+/* wave_abr_full_calc_inf_ref (raytr/waveabr.py:356-420) for a last gap without tilt or
+ * decenter (lcl_tfrm_last = (identity, [0, 0, tz])).  Record layout of this variant
+ * (flag W[21] == 0): W[0:3] cr ray[1].p, W[3:6] cr ray[0].d, W[6:9] cr ray[-1].p,
+ * W[9:12] cr ray[-1].d, W[12] V_BE = cr_op + op_cr_b4, W[13:16] image_pt,
+ * W[17:20] d_cr_b4, W[20] tz, W[22] n_obj, W[23] n_img. */
+static double wave_opd_inf_ref(const double *W, const double p1[3], const double d0[3],
+                               const double pk[3], const double dk[3], const double pl[3],
+                               const double dl[3], double ray_op)
 {
+    const double *cr_p1 = W, *cr_d0 = W + 3, *cr_pl = W + 6, *cr_dl = W + 9;
+    const double V_BE = W[12], *image_pt = W + 13, *d_cr_b4 = W + 17, tz = W[20];
+    const double n_obj = W[22], n_img = W[23];
+    double e1 = eic_distance(p1, d0, cr_p1, cr_d0);
+    const double p_b4[3] = {pk[0] - 0.0, pk[1] - 0.0, pk[2] - tz};
+    const double *d_b4 = dk;
+    const double mp[3] = {-p_b4[0], -p_b4[1], -p_b4[2]};
+    double op_b4 = dot3(d_b4, mp);                       /* ray_dist_to_perp_from_origin */
+    /* dist_to_shortest_join((cr[-1].p, cr[-1].d), (ray[-1].p, ray[-1].d)), waveabr.py:163-187 */
+    double del_p[3], n[3], P1[3], P2[3];
+    for (int c = 0; c < 3; c++) del_p[c] = pl[c] - cr_pl[c];
+    cross3(cr_dl, dl, n);
+    double nn = dot3(n, n);
+    if (nn == 0) {
+        double q[3] = {cr_pl[0] - pl[0], cr_pl[1] - pl[1], cr_pl[2] - pl[2]};
+        double t2 = dot3(q, cr_dl)*dot3(cr_dl, dl);
+        for (int c = 0; c < 3; c++) { P1[c] = cr_pl[c]; P2[c] = pl[c] + t2*dl[c]; }
+    } else {
+        double c2n[3], c1n[3];
+        cross3(dl, n, c2n);
+        cross3(cr_dl, n, c1n);
+        double t1 = dot3(c2n, del_p)/nn, t2 = dot3(c1n, del_p)/nn;
+        for (int c = 0; c < 3; c++) { P1[c] = cr_pl[c] + t1*cr_dl[c]; P2[c] = pl[c] + t2*dl[c]; }
+    }
+    double rF0[3], dd[3], ta[3], v[3];
+    for (int c = 0; c < 3; c++) {
+        rF0[c] = (P1[c] + P2[c])/2;
+        dd[c] = d_b4[c] - d_cr_b4[c];
+        ta[c] = pl[c] - image_pt[c];
+    }
+    double V_B = ray_op + op_b4;
+    double W0 = V_B - V_BE + n_img*dot3(dd, rF0);
+    double dbc = dot3(d_b4, d_cr_b4);
+    for (int c = 0; c < 3; c++) v[c] = d_cr_b4[c] - d_b4[c]*dbc;
+    double numer = dot3(v, ta);
+    double denom = 1 + dot3(d_b4, d_cr_b4);
+    double W_inf = W0 + n_img*numer/denom;
+    return -n_obj*e1 - W_inf;
+}
+
+/* wave_abr_full_calc (raytr/waveabr.py:206-253): finite reference sphere (:255-305) or,
+ * for a record flagged W[21] == 0, the infinite-reference variant.  pl, dl: ray[-1]. */
+double rto_wave_opd(const double *W, const double p1[3], const double d0[3],
+                    const double pk[3], const double dk[3], const double pl[3],
+                    const double dl[3], double ray_op)
+{
+    if (W[21] == 0.0) return wave_opd_inf_ref(W, p1, d0, pk, dk, pl, dl, ray_op);
     const double *cr_p1 = W, *cr_d0 = W + 3, *cr_pk = W + 6, *cr_dk = W + 9;
     const double cr_op = W[12], *cr_exp_pt = W + 13, cr_exp_dist = W[16], *ref_dir = W + 17;
     const double R = W[20], sign_soln = W[21], n_obj = W[22], n_img = W[23];
@@ -890,7 +943,7 @@ static void *grid_worker(void *arg)
         if (J->opd) {
             const double *s1 = ray + RT_SEG_DOUBLES, *sk = ray + (size_t)(J->n_ifc - 2)*RT_SEG_DOUBLES;
             J->opd[k] = (st == 0) ? rto_wave_opd(g->wave + (r/per_tile)*RT_WAVE_DOUBLES, s1, ray + 3,
-                                                 sk, sk + 3, opl)
+                                                 sk, sk + 3, lseg, lseg + 3, opl)
                                   : NAN;
         }
         if (J->last) for (int c = 0; c < RT_SEG_DOUBLES; c++) J->last[(size_t)c*J->n + k] = lseg[c];

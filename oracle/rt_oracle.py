@@ -123,9 +123,12 @@ def trace_grid(spec: rt_grid_spec, descs, n_by_wvl, ray_begin, ray_end, opts, n_
             'abr': np.stack([ax, ay]), 'opd': opd}
 
 
-def wave_opd(W, p1, d0, pk, dk, ray_op):
-    """wave_abr_full_calc_finite_pup for one ray (W: RT_WAVE_DOUBLES record)."""
+def wave_opd(W, p1, d0, pk, dk, ray_op, pl=None, dl=None):
+    """wave_abr_full_calc for one ray (W: RT_WAVE_DOUBLES record; pl, dl: ray[-1],
+    needed by the infinite-reference variant only)."""
     f = lib().rto_wave_opd
     f.restype = C.c_double
-    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (W, p1, d0, pk, dk)]
+    if pl is None:
+        pl, dl = np.zeros(3), np.zeros(3)
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (W, p1, d0, pk, dk, pl, dl)]
     return f(*[_dp(a) for a in arrs], C.c_double(ray_op))

@@ -325,7 +325,7 @@ __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_
             status = R.status; op = R.op;
             if (WAVE)
                 out.opd[k] = (R.status == RT_RAY_OK)
-                                 ? wave_opd(G.wave + tile*RT_WAVE_DOUBLES, R.p1, d0, R.pk, R.dk, R.op)
+                                 ? wave_opd(G.wave + tile*RT_WAVE_DOUBLES, R.p1, d0, R.pk, R.dk, R.p, R.d, R.op)
                                  : CUDART_NAN;
             if (out.abr_x || SUMMARY) {
                 const double rx = G.ref_img ? G.ref_img[tile*2 + 0] : 0.0;

@@ -10,8 +10,10 @@ computed here, once, with the reference's own expressions:
 * ``transfer_to_exit_pupil`` (waveabr.py:79-113, interfaces without decenter);
 * ``calculate_reference_sphere`` (waveabr.py:24-76).
 
-Supported: finite reference spheres (``ref_sphere_radius <= 1e8``); the
-infinite-reference variant (waveabr.py:356-488) is not implemented.
+Both branches of ``wave_abr_full_calc`` (waveabr.py:206-253) are covered: finite
+reference spheres and -- for exit pupils farther than 1e8 (telecentric image
+space) -- the infinite-reference variant (waveabr.py:356-420), the latter for an
+image gap without tilt / decenter.
 """
 from __future__ import annotations
 
@@ -24,6 +26,11 @@ from ._abi import RT_WAVE_DOUBLES
 def normalize(v):
     length = np.linalg.norm(v)
     return v if length == 0.0 else v/length
+
+
+def is_kinda_big(x, kinda_big=1e8):
+    """util/misc_math.py:22-29"""
+    return bool(np.isinf(x) or np.abs(x) > kinda_big)
 
 
 def transfer_to_exit_pupil(ray_seg, exp_dst_parax):
@@ -91,11 +98,27 @@ def wave_record(opt_model, chief_ray_pkg_, ref_sphere):
     """The RT_WAVE_DOUBLES record of a tile (layout: include/b200rt.h)."""
     cr, cr_exp_seg = chief_ray_pkg_
     ray, cr_op, _ = cr
-    image_pt, ref_dir, radius, _ = ref_sphere
-    if not np.isfinite(radius) or abs(radius) > 1e8:
-        raise NotImplementedError('infinite reference sphere (waveabr.py:356-488) not implemented')
+    image_pt, ref_dir, radius, lcl_tfrm_last = ref_sphere
     fod = opt_model.optical_spec.fod
     W = np.zeros(RT_WAVE_DOUBLES)
+    if is_kinda_big(radius):
+        # wave_abr_full_calc_inf_ref (waveabr.py:356-420): everything that depends on the
+        # chief ray only, with the reference's expressions
+        rt, t = lcl_tfrm_last
+        if not np.array_equal(rt, np.identity(3)) or t[0] != 0.0 or t[1] != 0.0:
+            raise NotImplementedError('infinite reference sphere with a tilted / decentered image gap')
+        k = -2
+        p_cr_b4, d_cr_b4 = rt.dot(ray[k][0] - t), rt.dot(ray[k][1])
+        op_cr_b4 = np.dot(d_cr_b4, -p_cr_b4)
+        W[0:3], W[3:6] = ray[1][0], ray[0][1]
+        W[6:9], W[9:12] = ray[-1][0], ray[-1][1]
+        W[12] = cr_op + op_cr_b4
+        W[13:16] = image_pt
+        W[17:20] = d_cr_b4
+        W[20] = t[2]
+        W[21] = 0.0                      # flag: infinite-reference variant
+        W[22], W[23] = abs(fod.n_obj), abs(fod.n_img)
+        return W
     W[0:3], W[3:6] = ray[1][0], ray[0][1]
     W[6:9], W[9:12] = ray[-2][0], ray[-2][1]
     W[12] = cr_op
@@ -148,14 +171,59 @@ def eic_distance(r, r0):
     return e
 
 
+def dist_to_shortest_join(r1, r2):
+    """points (and distances) of the closest join of two rays, waveabr.py:163-187"""
+    p1, d1 = r1
+    p2, d2 = r2
+    del_p = p2 - p1
+    n = np.cross(d1, d2)
+    nn = np.dot(n, n)
+    if nn == 0:
+        t2 = np.dot((p1 - p2), d1)*np.dot(d1, d2)
+        return (p1, 0), (p2 + t2*d2, t2)
+    t1 = np.dot(np.cross(d2, n), del_p)/nn
+    t2 = np.dot(np.cross(d1, n), del_p)/nn
+    return (p1 + t1*d1, t1), (p2 + t2*d2, t2)
+
+
+def wave_abr_full_calc_inf_ref(fod, fld, wvl, foc, ray_pkg, chief_ray_pkg_, ref_sphere):
+    """waveabr.py:356-420 (Miks: infinite reference sphere), same expressions."""
+    image_pt, ref_dir, ref_sphere_radius, lcl_tfrm_last = ref_sphere
+    cr, cr_exp_seg = chief_ray_pkg_
+    cr_ray, cr_op, _ = cr
+    ray, ray_op, _ = ray_pkg
+    k = -2
+    n_obj, n_img = abs(fod.n_obj), abs(fod.n_img)
+    e1 = eic_distance((ray[1][0], ray[0][1]), (cr_ray[1][0], cr_ray[0][1]))
+    if lcl_tfrm_last is not None:
+        rt, t = lcl_tfrm_last
+        p_b4, d_b4 = rt.dot(ray[k][0] - t), rt.dot(ray[k][1])
+        p_cr_b4, d_cr_b4 = rt.dot(cr_ray[k][0] - t), rt.dot(cr_ray[k][1])
+    else:
+        p_b4, d_b4 = ray[k][0], ray[k][1]
+        p_cr_b4, d_cr_b4 = cr_ray[k][0], cr_ray[k][1]
+    op_b4 = np.dot(d_b4, -p_b4)
+    op_cr_b4 = np.dot(d_cr_b4, -p_cr_b4)
+    P1, P2 = dist_to_shortest_join((cr_ray[-1][0], cr_ray[-1][1]), (ray[-1][0], ray[-1][1]))
+    rF0 = (P1[0] + P2[0])/2
+    V_B = ray_op + op_b4
+    V_BE = cr_op + op_cr_b4
+    W0 = V_B - V_BE + n_img*np.dot((d_b4 - d_cr_b4), rF0)
+    ta = ray[-1][0] - image_pt
+    numer = np.dot(d_cr_b4 - d_b4*np.dot(d_b4, d_cr_b4), ta)
+    denom = 1 + np.dot(d_b4, d_cr_b4)
+    W_inf = W0 + n_img*numer/denom
+    return -n_obj*e1 - W_inf
+
+
 def wave_abr_full_calc(fod, fld, wvl, foc, ray_pkg, chief_ray_pkg_, ref_sphere):
-    """OPD of a ray w.r.t. the chief ray on a FINITE reference sphere:
-    ``wave_abr_full_calc_finite_pup`` (waveabr.py:255-305), same expressions
-    (``F**2`` on a numpy scalar included).  System units."""
+    """OPD of a ray w.r.t. the chief ray (``wave_abr_full_calc``, waveabr.py:206-253):
+    finite reference sphere (``..._finite_pup``, :255-305, ``F**2`` on a numpy scalar
+    included) or the infinite-reference variant.  System units."""
     from math import sqrt
     image_pt, ref_dir, ref_sphere_radius, lcl_tfrm_last = ref_sphere
-    if not np.isfinite(ref_sphere_radius) or abs(ref_sphere_radius) > 1e8:
-        raise NotImplementedError('infinite reference sphere (waveabr.py:356-488) not implemented')
+    if is_kinda_big(ref_sphere_radius):
+        return wave_abr_full_calc_inf_ref(fod, fld, wvl, foc, ray_pkg, chief_ray_pkg_, ref_sphere)
     cr, cr_exp_seg = chief_ray_pkg_
     cr_ray, cr_op, _ = cr
     cr_exp_pt, cr_exp_dir, cr_exp_dist, ifc, cr_b4_pt, cr_b4_dir = cr_exp_seg

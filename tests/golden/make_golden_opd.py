@@ -33,7 +33,8 @@ def main():
     R = rh.ref()
     W = importlib.import_module('rayoptics.raytr.waveabr')
     num = 9
-    for name in ('dblgauss', 'rc', 'cellphone', 'triplet'):
+    names = sys.argv[1:] or ('dblgauss', 'rc', 'cellphone', 'triplet', 'telecentric')
+    for name in names:
         opm = M.OpticalModel.load(os.path.join(HERE, 'models', name + '.json'))
         osp, sm = opm.optical_spec, opm.seq_model
         fod = types.SimpleNamespace(n_obj=osp.fod.n_obj, n_img=osp.fod.n_img, exp_dist=osp.fod.exp_dist)
@@ -64,11 +65,22 @@ def main():
                 image_pt, ref_dir, radius, _ = ref_sphere
                 rec = np.zeros(24)
                 rec[0:3], rec[3:6] = cr[0][1][0], cr[0][0][1]
-                rec[6:9], rec[9:12] = cr[0][-2][0], cr[0][-2][1]
-                rec[12] = cr[1]
-                rec[13:16], rec[16] = cr_exp_seg[0], cr_exp_seg[2]
-                rec[17:20], rec[20] = ref_dir, radius
-                rec[21] = -1.0 if ref_dir[2]*cr[0][-1][1][2] < 0 else 1.0
+                if R.misc_math.is_kinda_big(radius):
+                    # infinite-reference variant (waveabr.py:356-420): the chief-ray-only
+                    # quantities, with the reference's own expressions (include/b200rt.h layout)
+                    rt_, t_ = ref_sphere[3]
+                    p_cr_b4, d_cr_b4 = rt_.dot(cr[0][-2][0] - t_), rt_.dot(cr[0][-2][1])
+                    op_cr_b4 = W.ray_dist_to_perp_from_origin((p_cr_b4, d_cr_b4))
+                    rec[6:9], rec[9:12] = cr[0][-1][0], cr[0][-1][1]
+                    rec[12] = cr[1] + op_cr_b4
+                    rec[13:16] = image_pt
+                    rec[17:20], rec[20], rec[21] = d_cr_b4, t_[2], 0.0
+                else:
+                    rec[6:9], rec[9:12] = cr[0][-2][0], cr[0][-2][1]
+                    rec[12] = cr[1]
+                    rec[13:16], rec[16] = cr_exp_seg[0], cr_exp_seg[2]
+                    rec[17:20], rec[20] = ref_dir, radius
+                    rec[21] = -1.0 if ref_dir[2]*cr[0][-1][1][2] < 0 else 1.0
                 rec[22], rec[23] = abs(fod.n_obj), abs(fod.n_img)
                 recs.append(rec)
                 for i in range(num):

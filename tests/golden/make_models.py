@@ -283,6 +283,53 @@ def diffractive_wild():
     return finish(M.OpticalModel(sm, osp, name='diffractive_wild'), aim=False, apertures=False)
 
 
+def telecentric():
+    """Image-space telecentric lens: aperture stop in the front focal plane of a
+    two-element group, so the exit pupil is ~1e10+ mm away and the reference's
+    wavefront code takes the INFINITE reference sphere branch
+    (raytr/waveabr.py:206-253 `is_kinda_big(ref_sphere_radius)`, :356-420)."""
+    g1, g2 = M.AbbeGlass(1.6204, 60.3, 'SK16'), M.AbbeGlass(1.6727, 32.2, 'SF5')
+
+    def build(d_stop, bfl):
+        spec = [(0.0, 'dummy', 1e10, M.Air(), None), (0.0, 'dummy', d_stop, M.Air(), None),
+                (1/80.0, 'transmit', 7.0, g1, None), (-1/45.0, 'transmit', 2.5, g2, None),
+                (-1/160.0, 'transmit', 30.0, M.Air(), None),
+                (1/70.0, 'transmit', 6.0, g1, None), (0.0, 'transmit', bfl, M.Air(), None),
+                (0.0, 'dummy', 0.0, None, None)]
+        ifcs, gaps = [], []
+        for cv, mode, thi, med, _ in spec:
+            ifcs.append(M.Surface(profile=M.Spherical(cv), interact_mode=mode))
+            if med is not None:
+                gaps.append(M.Gap(thi, med))
+        wvls = [656.3, 587.6, 486.1]
+        sm = M.SequentialModel(ifcs, gaps, stop_surface=1, wvlns=wvls, ref_wvl=1)
+        fields = [M.Field(y=0.0), M.Field(y=3.5), M.Field(y=5.0)]
+        osp = OpticalSpecs(WvlSpec(wvls, 1), PupilSpec(('object', 'epd'), 10.0),
+                           FieldSpec(('object', 'angle'), 5.0, fields))
+        return M.OpticalModel(sm, osp, name='telecentric')
+
+    # stop distance that sends the exit pupil to infinity (secant on 1/exp_dist), then
+    # the paraxial image distance
+    def inv_exp(d):
+        opm = build(d, 50.0)
+        opm.update_model()
+        return 1.0/opm.optical_spec.fod.exp_dist
+    d0, d1 = 30.0, 40.0
+    f0, f1 = inv_exp(d0), inv_exp(d1)
+    for _ in range(60):
+        if f1 == f0:
+            break
+        d2 = d1 - f1*(d1 - d0)/(f1 - f0)
+        d0, f0, d1, f1 = d1, f1, d2, inv_exp(d2)
+        if abs(f1) < 1e-13:
+            break
+    opm = build(d1, 50.0)
+    opm.update_model()
+    opm = build(d1, opm.optical_spec.fod.img_dist if hasattr(opm.optical_spec.fod, 'img_dist')
+                else opm.optical_spec.fod.bfl)
+    return finish(opm)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     models = {
@@ -298,6 +345,7 @@ def main():
         # 3 ThinLens interfaces (HolographicElement phase), models/thin_triplet.roa
         'thin_triplet': lambda: from_roa('models/thin_triplet.roa', 'thin_triplet'),
         'exotic': exotic,
+        'telecentric': telecentric,
         'hybrid': lambda: from_roa('models/HybridAchromat.roa', 'hybrid'),
         'diffractive': diffractive,
         'diffractive_wild': diffractive_wild,

@@ -35,6 +35,7 @@ def lib():
         _lib = C.CDLL(build())
         _lib.hostsim_check_division.restype = C.c_int64
         _lib.hostsim_check_sqrt.restype = C.c_int64
+        _lib.hostsim_wave_opd.restype = C.c_double
     return _lib
 
 
@@ -94,3 +95,8 @@ def check_sqrt(x):
     nf = C.c_int64(0)
     bad = lib().hostsim_check_sqrt(C.c_int64(x.size), _dp(x), C.byref(nf))
     return int(bad), int(nf.value)
+
+
+def wave_opd(W, p1, d0, pk, dk, pl, dl, ray_op):
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (W, p1, d0, pk, dk, pl, dl)]
+    return lib().hostsim_wave_opd(*[_dp(a) for a in arrs], C.c_double(ray_op))

@@ -105,6 +105,15 @@ int64_t hostsim_check_division(int64_t n, const double *a, const double *b, int6
     return bad;
 }
 
+/* the OPD epilogue of the grid kernels (csrc/b200rt.cu grid_chunk_loop -> wave_opd) */
+double hostsim_wave_opd(const double *W, const double *p1, const double *d0, const double *pk,
+                        const double *dk, const double *pl, const double *dl, double ray_op)
+{
+    const Vec3 a = {p1[0], p1[1], p1[2]}, b = {d0[0], d0[1], d0[2]}, c = {pk[0], pk[1], pk[2]};
+    const Vec3 d = {dk[0], dk[1], dk[2]}, e = {pl[0], pl[1], pl[2]}, f = {dl[0], dl[1], dl[2]};
+    return wave_opd(W, a, b, c, d, e, f, ray_op);
+}
+
 int64_t hostsim_check_sqrt(int64_t n, const double *x, int64_t *n_fast)
 {
     int64_t bad = 0, fast_cnt = 0;

@@ -136,6 +136,38 @@ def test_device_source_phase_elements(hostsim, oracle, name):
                                atol=PHASE_TOL_MM)
 
 
+@pytest.mark.parametrize('name', ['dblgauss', 'rc', 'cellphone', 'triplet', 'telecentric'])
+def test_device_opd_epilogue(hostsim, oracle, name):
+    """wave_opd of rt_device.cuh (finite and infinite reference sphere) on the reference's
+    golden OPDs.  Finite spheres: F**2 is libm pow() in the reference, F*F on the device
+    (<= 1e-12 mm, > 95 % bit-equal); the infinite-reference variant has no power and is
+    bit-exact."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, 'vectors', name + '_opd.npz'))
+    v = {k: z[k] for k in z.files}
+    opm = load_model(name)
+    descs, n_by_wvl, _ = T.describe_model(opm.seq_model)
+    n_ifc = len(descs)
+    opts = _abi.make_opts(first_surf=1, last_surf=n_ifc - 2, check_apertures=True)
+    r = hostsim.trace_bundle(descs, n_by_wvl, v['p0'], v['d0'], v['wvl_idx'], opts,
+                             kernel=HS.lean_kind(descs), out_kind=2)
+    assert same(r['status'], v['status'])
+    ok = np.nonzero(v['status'] == 0)[0]
+    got = np.full(v['opd'].shape, np.nan)
+    for k in ok:
+        full = r['full'][:, :, k]
+        got[k] = hostsim.wave_opd(v['wave'][v['tile'][k]], full[1, 0:3], full[0, 3:6],
+                                  full[n_ifc - 2, 0:3], full[n_ifc - 2, 3:6],
+                                  full[n_ifc - 1, 0:3], full[n_ifc - 1, 3:6], r['op'][k])
+    np.testing.assert_allclose(got[ok], v['opd'][ok], rtol=0, atol=1e-12)
+    assert (got[ok] == v['opd'][ok]).mean() > 0.95
+    inf = v['wave'][v['tile'], 21] == 0
+    if name == 'telecentric':
+        assert (inf & (v['status'] == 0)).sum() > 100
+    assert same(got[inf], v['opd'][inf])
+
+
 def test_division_and_sqrt_sequences(hostsim):
     """CPU sibling of rt_selftest_division (b200rt.cu): wherever a sequence reports
     'fast' it equals the IEEE operation; div_shared() and sqrt_near_one() always do."""

@@ -17,6 +17,9 @@ from conftest import GOLDEN, load_model
 from rayoptics_b200 import _abi, table as T, engine as E, waveabr as W
 
 OPD_MODELS = ['dblgauss', 'rc', 'cellphone', 'triplet']
+# 'telecentric': exit pupil at ~4e14 mm -> the axial tiles take the infinite-reference branch
+# (raytr/waveabr.py:356-420).  Its GPU run lives in tests/test_zz_gpu_additions.py.
+OPD_MODELS_CPU = OPD_MODELS + ['telecentric']
 
 
 def load_opd(name):
@@ -28,7 +31,7 @@ def same(a, b):
     return np.array_equal(a, b, equal_nan=True)
 
 
-@pytest.mark.parametrize('name', OPD_MODELS)
+@pytest.mark.parametrize('name', OPD_MODELS_CPU)
 def test_oracle_opd_matches_reference(oracle, name):
     opm = load_model(name)
     v = load_opd(name)
@@ -42,11 +45,14 @@ def test_oracle_opd_matches_reference(oracle, name):
     for k in ok:
         full = r['full'][:, :, k]
         got[k] = oracle.wave_opd(v['wave'][v['tile'][k]], full[1, 0:3], full[0, 3:6],
-                                 full[n_ifc - 2, 0:3], full[n_ifc - 2, 3:6], r['op'][k])
+                                 full[n_ifc - 2, 0:3], full[n_ifc - 2, 3:6], r['op'][k],
+                                 pl=full[n_ifc - 1, 0:3], dl=full[n_ifc - 1, 3:6])
     assert same(got, v['opd'])
+    if name == 'telecentric':
+        assert (v['wave'][:, 21] == 0).sum() == 3        # the axial tiles are infinite-reference
 
 
-@pytest.mark.parametrize('name', OPD_MODELS)
+@pytest.mark.parametrize('name', OPD_MODELS_CPU)
 def test_host_wave_records_match_reference(oracle, name):
     """chief ray -> exit pupil segment -> reference sphere -> 24-double record,
     computed by rayoptics_b200/waveabr.py from oracle-traced chief rays."""

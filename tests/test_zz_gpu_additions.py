@@ -17,6 +17,7 @@ import torch
 from conftest import PHASE_MODEL_NAMES, load_model, load_vectors, seeded_bundle
 from rayoptics_b200 import _abi, engine as E, table as T, trace as TR, analyses as A
 from test_trace_drivers import oracle_tracer
+from test_wave import test_cuda_opd_matches_oracle_and_reference as _opd_check
 
 pytestmark = pytest.mark.gpu
 TOL_MM = 1e-11
@@ -118,3 +119,8 @@ def test_cuda_drivers_match_oracle_seam():
     wf = opm.seq_model.trace_wavefront(fld, wvl, 0.0, num_rays=8)
     wf2 = opm.seq_model.trace_wavefront(fld, wvl, 0.0, num_rays=8, tracer=oracle_tracer)
     assert np.array_equal(wf, wf2)
+
+
+def test_cuda_opd_infinite_reference(oracle):
+    """telecentric image space: the axial tiles use wave_abr_full_calc_inf_ref"""
+    _opd_check(oracle, 'telecentric')
