@@ -91,6 +91,15 @@ enum rt_status {
                               EvenPolynomial.df, profiles.py:870-873) */
 };
 
+/* pupil specification after the image-space substitution of opticalspec.py:311-325 */
+enum rt_pupil_kind {
+    RT_PUPIL_EPD = 0,   /* spatial: aim at the entrance pupil plane, opticalspec.py:329-366.
+                           rt_field_desc: pt0 = -(obj_dist + z_enp) [d0x/d0z, d0y/d0z, 0], aim = aim_pt */
+    RT_PUPIL_NA = 1,    /* angular, object-space NA: dir_tot = sin_ang*pupil + cr_dir, :368-398.
+                           rt_field_desc: pt0 = object point p0, aim = chief ray direction d0[:2] */
+    RT_PUPIL_FNO = 2    /* angular, object-space f/#: pupil_dir = slope*pupil/hypt, :378-384 */
+};
+
 /* Aperture subclasses, src/rayoptics/elem/surface.py:340-494 */
 enum rt_aperture_type {
     RT_APERTURE_CIRCULAR = 1,    /* surface.py:397-431 */
@@ -242,8 +251,9 @@ typedef struct rt_grid_spec {
     int32_t paired;            /* 0: product grid pupil_x[i] x pupil_y[j]; 1: ray list -- ny must be 1 and
                                   pupil_y is [n_fields][nx]: ray i uses (pupil_x[i], pupil_y[i])
                                   (trace_ray_list / trace_ray_fan, analyses.py:212-230,437-455) */
-    int32_t reserved;
-    double eprad;              /* pupil_value/2 (opticalspec.py:340) */
+    int32_t pupil_kind;        /* rt_pupil_kind: which branch of ray_start_from_osp generates the rays */
+    double eprad;              /* RT_PUPIL_EPD: pupil_value/2 (opticalspec.py:340); RT_PUPIL_NA: sin_ang = NA/n
+                                  (:373-377); RT_PUPIL_FNO: slope = -1/(2 f/#) (:378-380) */
     double z_pupil;            /* fod.obj_dist + z_enp: z of the aim plane (opticalspec.py:360) */
     double foc;                /* focus shift used for abr_x/abr_y (analyses.py:572) */
 } rt_grid_spec;

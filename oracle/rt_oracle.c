@@ -801,10 +801,24 @@ int rto_grid_start_rays(const rt_grid_spec *g, int64_t ray_begin, int64_t ray_en
             if (pup[1] < 0.0) { if (F->vly != 0.0) pup[1] *= (1.0 - F->vly); }
             else              { if (F->vuy != 0.0) pup[1] *= (1.0 - F->vuy); }
         }
-        double pt1[3] = {g->eprad*pup[0] + F->aim[0], g->eprad*pup[1] + F->aim[1], g->z_pupil};
-        double v[3] = {pt1[0] - F->pt0[0], pt1[1] - F->pt0[1], pt1[2] - F->pt0[2]};
         double d[3];
-        normalize3(v, d);
+        if (g->pupil_kind == RT_PUPIL_EPD) {
+            double pt1[3] = {g->eprad*pup[0] + F->aim[0], g->eprad*pup[1] + F->aim[1], g->z_pupil};
+            double v[3] = {pt1[0] - F->pt0[0], pt1[1] - F->pt0[1], pt1[2] - F->pt0[2]};
+            normalize3(v, d);
+        } else {
+            /* angular pupil, opticalspec.py:368-398: dir_tot = pupil_dir + cr_dir (aim = d0[:2]) */
+            double pd[2];
+            if (g->pupil_kind == RT_PUPIL_NA) {
+                pd[0] = g->eprad*pup[0]; pd[1] = g->eprad*pup[1];
+            } else {
+                const double slope = g->eprad;
+                double hypt = sqrt(1 + pow(pup[0]*slope, 2.0) + pow(pup[1]*slope, 2.0));
+                pd[0] = slope*pup[0]/hypt; pd[1] = slope*pup[1]/hypt;
+            }
+            d[0] = pd[0] + F->aim[0]; d[1] = pd[1] + F->aim[1];
+            d[2] = sqrt(1 - fma(d[1], d[1], d[0]*d[0]));     /* np.sqrt(1 - np.dot(dir_tot, dir_tot)) */
+        }
         if (d[2]*(double)g->flip_z_dir < 0) { d[0] = -d[0]; d[1] = -d[1]; d[2] = -d[2]; }
         int64_t k = r - ray_begin;
         px[k] = F->pt0[0]; py[k] = F->pt0[1]; pz[k] = F->pt0[2];

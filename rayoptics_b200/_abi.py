@@ -21,6 +21,8 @@ RT_WAVE_DOUBLES = 24
 PROFILE_IDS = {'Spherical': 0, 'Conic': 1, 'EvenPolynomial': 2,
                'RadialPolynomial': 3, 'YToroid': 4, 'XToroid': 5, 'ThinLens': 6}
 PHASE_IDS = {'HolographicElement': 1, 'DiffractionGrating': 2, 'DiffractiveElement': 3}
+# enum rt_pupil_kind
+PUPIL_EPD, PUPIL_NA, PUPIL_FNO = 0, 1, 2
 # enum rt_mode
 MODE_IDS = {'transmit': 0, 'reflect': 1, 'dummy': 2, 'phantom': 3}
 # enum rt_status
@@ -84,7 +86,7 @@ class rt_grid_spec(C.Structure):
                 ('pupil_x', c_double_p), ('pupil_y', c_double_p),
                 ('ref_img', c_double_p), ('wave', c_double_p),
                 ('apply_vignetting', C.c_int32), ('flip_z_dir', C.c_int32),
-                ('paired', C.c_int32), ('reserved', C.c_int32),
+                ('paired', C.c_int32), ('pupil_kind', C.c_int32),
                 ('eprad', C.c_double), ('z_pupil', C.c_double), ('foc', C.c_double)]
 
 

@@ -27,6 +27,7 @@
 
 #include "rt_device.cuh"
 #include "rt_lean.cuh"
+#include "rt_grid.cuh"
 
 using namespace b200rt;
 
@@ -89,7 +90,7 @@ struct rt_table {
 struct rt_grid {
     int32_t device;
     int32_t n_fields, n_wvls, nx, ny;
-    int32_t apply_vignetting, flip_z_dir, paired;
+    int32_t apply_vignetting, flip_z_dir, paired, pupil_kind;
     double eprad, z_pupil, foc;
     rt_field_desc *d_fields;
     int32_t *d_wvl_idx;
@@ -99,15 +100,6 @@ struct rt_grid {
 };
 
 /* what the grid kernel needs, passed by value */
-struct GridDev {
-    int32_t n_wvls, nx, ny, apply_vignetting, flip_z_dir, paired;
-    double eprad, z_pupil, foc;
-    const rt_field_desc *fields;
-    const int32_t *wvl_idx;
-    const double *pupil_x, *pupil_y, *ref_img, *wave;
-    int64_t rays_per_tile, chunks_per_tile;
-};
-
 /* ------------------------------------------------------------------ kernels */
 
 /* Stage the table into shared memory (8-byte words, coalesced) or, for very
@@ -232,32 +224,6 @@ __device__ __forceinline__ void acc_flush(double *acc, double *scratch, int64_t 
     acc_init(acc);
 }
 
-/* start ray of grid ray (tile, loc): Field.apply_vignetting + ray_start_from_osp
- * 'epd' branch + the virtual-object flip of trace_base */
-template <bool LEAN>
-__device__ __forceinline__ void grid_start_ray(const GridDev &G, int f, int64_t loc, Vec3 &p0, Vec3 &d0)
-{
-    const int i = (int)(loc/G.ny), j = (int)(loc - (int64_t)i*G.ny);
-    const rt_field_desc &F = G.fields[f];
-    /* Field.apply_vignetting, opticalspec.py:1339-1353 */
-    double pupx = G.pupil_x[(int64_t)f*G.nx + i];
-    double pupy = G.paired ? G.pupil_y[(int64_t)f*G.nx + i] : G.pupil_y[(int64_t)f*G.ny + j];
-    if (G.apply_vignetting) {
-        const double vlx = F.vlx, vux = F.vux, vly = F.vly, vuy = F.vuy;
-        if (pupx < 0.0) { if (vlx != 0.0) pupx *= (1.0 - vlx); }
-        else            { if (vux != 0.0) pupx *= (1.0 - vux); }
-        if (pupy < 0.0) { if (vly != 0.0) pupy *= (1.0 - vly); }
-        else            { if (vuy != 0.0) pupy *= (1.0 - vuy); }
-    }
-    /* ray_start_from_osp 'epd' branch, opticalspec.py:354-366 */
-    p0.x = F.pt0[0]; p0.y = F.pt0[1]; p0.z = F.pt0[2];
-    Vec3 pt1 = {G.eprad*pupx + F.aim[0], G.eprad*pupy + F.aim[1], G.z_pupil};
-    Vec3 dv = {pt1.x - p0.x, pt1.y - p0.y, pt1.z - p0.z};
-    d0 = LEAN ? normalize3_shared(dv) : normalize3(dv);
-    /* trace_base virtual-object flip, trace.py:305-308 */
-    if (d0.z*(double)G.flip_z_dir < 0) { d0.x = -d0.x; d0.y = -d0.y; d0.z = -d0.z; }
-}
-
 /* per-chunk variant (chunk slots): the lanes' contributions are reduced straight
  * from registers; lanes without a ray contribute the identity */
 __device__ __forceinline__ void warp_record_from_regs(bool have, int status, double ax, double ay,
@@ -346,7 +312,8 @@ template <bool FULL, bool SUMMARY, bool STAGE, bool WAVE>
 __global__ void __launch_bounds__(RT_BLOCK)
 k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
              int n_ifc, int n_wvl, GridDev G, int64_t chunk_begin, int64_t chunk_end,
-             rt_opts o, rt_out out, double *__restrict__ scratch, const double *__restrict__ g_wvl)
+             rt_opts o, rt_out out, double *__restrict__ scratch, const double *__restrict__ g_wvl,
+             int pupil_kind)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const rt_surface_desc *tab;
@@ -356,7 +323,7 @@ k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restri
     grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc,
         [&](int f, int w, int64_t loc, int64_t k, RayResult &R, Vec3 &d0) {
             Vec3 p0;
-            grid_start_ray<false>(G, f, loc, p0, d0);
+            grid_start_ray<false>(G, pupil_kind, f, loc, p0, d0);
             FullWriter fw = {FULL ? out.full + k : nullptr, out.full_stride};
             const int wi = G.wvl_idx[w];
             trace_ray<FULL, WAVE>(tab, ntab + (int64_t)wi*n_ifc, g_wvl[wi], n_ifc, o, p0, d0, fw, R);
@@ -406,7 +373,7 @@ k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__r
     grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc,
         [&](int f, int w, int64_t loc, int64_t k, RayResult &R, Vec3 &d0) {
             Vec3 p0;
-            grid_start_ray<true>(G, f, loc, p0, d0);
+            grid_start_ray<true>(G, RT_PUPIL_EPD, f, loc, p0, d0);
             FullWriter fw = {OUT == 2 ? out.full + k : nullptr, out.full_stride};
             trace_ray_lean<OUT, WAVE, POLY>(ls, li + (int64_t)G.wvl_idx[w]*n_ifc, g_surfs, n_ifc, o, p0, d0, fw, R);
         });
@@ -610,7 +577,7 @@ static int launch_grid(const rt_table *t, const rt_grid *g, const GridDev &G, in
     rc = persistent_grid(kern, smem, t->sm_count, ce - cb, &grid);
     if (rc) return rc;
     kern<<<grid, RT_BLOCK, smem, stream>>>(t->d_surfs, t->d_n, t->n_ifc, t->n_wvl, G, cb, ce, *o, *out,
-                                           scratch, t->d_wvl);
+                                           scratch, t->d_wvl, g->pupil_kind);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return RT_OK;
@@ -820,7 +787,8 @@ int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out)
 {
     if (!spec || !out || spec->n_fields < 1 || spec->n_wvls < 1 || spec->nx < 1 || spec->ny < 1 ||
         !spec->fields || !spec->wvl_idx || !spec->pupil_x || !spec->pupil_y ||
-        (spec->paired && spec->ny != 1))
+        (spec->paired && spec->ny != 1) || spec->pupil_kind < RT_PUPIL_EPD ||
+        spec->pupil_kind > RT_PUPIL_FNO)
         return fail(RT_ERR_INVALID, "rt_grid_create: bad arguments");
     DeviceGuard guard(device);
     rt_grid *g = new (std::nothrow) rt_grid();
@@ -828,7 +796,7 @@ int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out)
     g->device = device;
     g->n_fields = spec->n_fields; g->n_wvls = spec->n_wvls; g->nx = spec->nx; g->ny = spec->ny;
     g->apply_vignetting = spec->apply_vignetting; g->flip_z_dir = spec->flip_z_dir;
-    g->paired = spec->paired;
+    g->paired = spec->paired; g->pupil_kind = spec->pupil_kind;
     g->eprad = spec->eprad; g->z_pupil = spec->z_pupil; g->foc = spec->foc;
     g->rays_per_tile = (int64_t)spec->nx*spec->ny;
     g->chunks_per_tile = (g->rays_per_tile + RT_BLOCK - 1)/RT_BLOCK;
@@ -921,12 +889,14 @@ int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int6
         CUDA_TRY(cudaMemsetAsync(scr, 0, (size_t)rt_grid_scratch_bytes(g, chunk_begin, chunk_end), s));
     const bool full = out->full != nullptr, summ = summary != nullptr, st = t->stage;
     const bool wave = out->opd != nullptr;
+    /* angular pupil specifications are generated by the general kernels only (rt_grid.cuh) */
+    const bool lean = t->lean && g->pupil_kind == RT_PUPIL_EPD;
     if (wave) {
         if (!g->d_wave) return fail(RT_ERR_INVALID, "rt_trace_grid: out.opd needs rt_grid_spec.wave");
         if (out_kind(out) != 0) return fail(RT_ERR_UNSUPPORTED, "rt_trace_grid: opd cannot be combined with normals / whole rays");
         if (!t->wave_ok)
             return fail(RT_ERR_UNSUPPORTED, "rt_trace_grid: opd needs >= 3 interfaces and no decenter on the last one before the image");
-        if (t->lean) {
+        if (lean) {
             rc = summ ? launch_grid_lean<0, true, true>(t, G, chunk_begin, chunk_end, o, out, scr, s)
                       : launch_grid_lean<0, false, true>(t, G, chunk_begin, chunk_end, o, out, scr, s);
         } else if (st) {
@@ -936,7 +906,7 @@ int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int6
             rc = summ ? launch_grid<false, true, false, true>(t, g, G, chunk_begin, chunk_end, o, out, scr, s)
                       : launch_grid<false, false, false, true>(t, g, G, chunk_begin, chunk_end, o, out, scr, s);
         }
-    } else if (t->lean) {
+    } else if (lean) {
         const int kind = out_kind(out);
 #define RT_LEAN_CASE(K, S)                                                                   \
         if (kind == K && summ == S)                                                          \

@@ -171,14 +171,21 @@ class PupilGridSpec:
     (the arrays behind ``rt_grid_spec``; no CUDA involved).
 
     ``fields``: list of dicts / objects with ``pt0`` (3), ``aim`` (2), ``vlx,
-    vux, vly, vuy``; ``pupil_x`` / ``pupil_y``: ``[n_fields, nx]`` / ``[n_fields,
+    vux, vly, vuy`` (and optionally ``pupil_kind``, see ``rt_pupil_kind``: for the
+    angular kinds ``pt0`` is the object point, ``aim`` the chief-ray direction
+    cosines and ``eprad`` the sine / slope scale); ``pupil_x`` / ``pupil_y``: ``[n_fields, nx]`` / ``[n_fields,
     ny]`` relative pupil coordinates before vignetting (or 1-D, shared by all
     fields); ``wvl_idx``: rows of the table's index table; ``ref_img``:
     ``[n_fields, n_wvls, 2]`` reference image points or None."""
 
     def __init__(self, fields, wvl_idx, pupil_x, pupil_y, eprad, z_pupil, ref_img=None,
-                 apply_vignetting=True, flip_z_dir=1, foc=0.0, paired=False, wave=None):
+                 apply_vignetting=True, flip_z_dir=1, foc=0.0, paired=False, wave=None,
+                 pupil_kind=None):
         nf = len(fields)
+        if pupil_kind is None:      # records of OpticalSpecs.grid_fields carry it
+            f0 = fields[0]
+            pupil_kind = f0.get('pupil_kind', 0) if isinstance(f0, dict) else getattr(f0, 'pupil_kind', 0)
+        self.pupil_kind = int(pupil_kind)
         self.paired = int(bool(paired))
         self.n_fields = nf
         self.wvl_idx = np.ascontiguousarray(wvl_idx, dtype=np.int32)
@@ -238,6 +245,7 @@ class PupilGridSpec:
         s.wave = None if self.wave is None else self.wave.ctypes.data_as(_abi.c_double_p)
         s.apply_vignetting, s.flip_z_dir = self.apply_vignetting, self.flip_z_dir
         s.paired = self.paired
+        s.pupil_kind = self.pupil_kind
         s.eprad, s.z_pupil, s.foc = self.eprad, self.z_pupil, self.foc
         return s
 

@@ -169,9 +169,11 @@ class OpticalSpecs:
         if pupil_oi_key == 'image':
             if abs(fod.m) < 1e-10:
                 pupil_value_key, pupil_value = 'epd', 2*fod.enp_radius
-            elif abs(fod.enp_dist) > 1e10:
+            elif abs(fod.enp_dist) > 1e10:      # telecentric entrance pupil
                 pupil_value_key = 'NA'
-                pupil_value = fod.obj_na
+                n_obj = self.obj_img_rindex()[0]
+                slp0 = fod.obj_na/n_obj                                  # etendue.na2slp_parax
+                pupil_value = n_obj*math.sin(math.atan(slp0/n_obj))      # etendue.slp2na
             else:
                 pupil_value_key, pupil_value = 'epd', 2*fod.enp_radius
         return pupil_oi_key, pupil_value_key, pupil_value
@@ -218,23 +220,41 @@ class OpticalSpecs:
 
     # ------------------------------------------------- grid field records
     def grid_fields(self, fields=None):
-        """Per-field constants of the 'epd' start-ray branch for the grid kernel:
-        list of dicts (pt0, aim, vlx, vux, vly, vuy) plus (eprad, z_pupil)."""
+        """Per-field constants of the start-ray generation for the grid kernels: list of
+        dicts (pt0, aim, vlx, vux, vly, vuy, pupil_kind) plus (scale, z_pupil).
+
+        'epd' pupils (``rt_pupil_kind`` 0): pt0 = the ray origin in the object plane, aim =
+        aim point, scale = entrance pupil radius.  Angular pupils ('NA' 1, 'f/#' 2;
+        opticalspec.py:368-398): pt0 = object point, aim = chief-ray direction cosines
+        ``d0[:2]``, scale = NA/n or -1/(2 f/#)."""
         pupil_oi_key, pupil_value_key, pupil_value = self._epd_pupil()
-        if pupil_value_key != 'epd':
-            raise NotImplementedError('grid start rays need an epd-type pupil specification')
+        if self.field_of_view.is_wide_angle:
+            raise NotImplementedError('wide-angle start rays are not generated on the device')
         fod = self.fod
-        eprad = pupil_value/2
         z_pupil = fod.obj_dist + fod.enp_dist
-        obj2enp_dist = -(fod.obj_dist + fod.enp_dist)
+        flds = fields if fields is not None else self.field_of_view.fields
         out = []
-        for fld in (fields if fields is not None else self.field_of_view.fields):
-            p0, d0 = self.obj_coords(fld)
-            pt0 = obj2enp_dist*np.array([d0[0]/d0[2], d0[1]/d0[2], 0.])
-            aim = [0., 0.] if getattr(fld, 'aim_info', None) is None else fld.aim_info
-            out.append({'pt0': pt0, 'aim': [float(aim[0]), float(aim[1])],
-                        'vlx': fld.vlx, 'vux': fld.vux, 'vly': fld.vly, 'vuy': fld.vuy})
-        return out, eprad, z_pupil
+        if pupil_value_key == 'epd':
+            kind, scale = 0, pupil_value/2
+            obj2enp_dist = -(fod.obj_dist + fod.enp_dist)
+            for fld in flds:
+                p0, d0 = self.obj_coords(fld)
+                pt0 = obj2enp_dist*np.array([d0[0]/d0[2], d0[1]/d0[2], 0.])
+                aim = [0., 0.] if getattr(fld, 'aim_info', None) is None else fld.aim_info
+                out.append({'pt0': pt0, 'aim': [float(aim[0]), float(aim[1])]})
+        else:
+            n_obj, n_img = self.obj_img_rindex()
+            if 'NA' in pupil_value_key:
+                n = n_obj if pupil_oi_key == 'object' else n_img
+                kind, scale = 1, pupil_value/n
+            else:
+                kind, scale = 2, -1/(2*pupil_value)
+            for fld in flds:
+                p0, d0 = self.obj_coords(fld)
+                out.append({'pt0': p0, 'aim': [float(d0[0]), float(d0[1])]})
+        for rec, fld in zip(out, flds):
+            rec.update(vlx=fld.vlx, vux=fld.vux, vly=fld.vly, vuy=fld.vuy, pupil_kind=kind)
+        return out, scale, z_pupil
 
     # ------------------------------------------------------- persistence
     def to_dict(self):

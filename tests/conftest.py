@@ -13,6 +13,8 @@ MODEL_NAMES = ['singlet', 'dblgauss', 'triplet', 'rc', 'cellphone', 'cellphone_e
                'evenasph', 'zoom52', 'thin_triplet', 'exotic']
 # models with diffractive phase elements: the reference evaluates x**k with libm pow(), so the
 # device carries tolerance parity there (the oracle, on the same libm, stays bit-exact)
+# finite-conjugate relays specified by an angular object-space pupil ('NA', 'f/#')
+ANGULAR_MODEL_NAMES = ['relay_na', 'relay_fno']
 PHASE_MODEL_NAMES = ['hybrid', 'diffractive', 'diffractive_wild']
 
 

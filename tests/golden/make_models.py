@@ -330,6 +330,26 @@ def telecentric():
     return finish(opm)
 
 
+def relay(pupil_key, pupil_value, name):
+    """Finite-conjugate relay specified by an ANGULAR object-space pupil ('NA' or 'f/#'):
+    the start rays take the angular branch of ray_start_from_osp (opticalspec.py:368-398)."""
+    g = M.AbbeGlass(1.5168, 64.2, 'BK7')
+    spec = [(0.0, 'dummy', 100.0, M.Air()), (1/55.0, 'transmit', 6.0, g), (-1/55.0, 'transmit', 12.0, M.Air()),
+            (0.0, 'dummy', 12.0, M.Air()), (1/60.0, 'transmit', 6.0, g), (-1/50.0, 'transmit', 95.0, M.Air()),
+            (0.0, 'dummy', 0.0, None)]
+    ifcs, gaps = [], []
+    for cv, mode, thi, med in spec:
+        ifcs.append(M.Surface(profile=M.Spherical(cv), interact_mode=mode))
+        if med is not None:
+            gaps.append(M.Gap(thi, med))
+    wvls = [656.3, 587.6, 486.1]
+    sm = M.SequentialModel(ifcs, gaps, stop_surface=3, wvlns=wvls, ref_wvl=1)
+    fields = [M.Field(y=0.0), M.Field(y=3.0), M.Field(x=2.0, y=-4.0)]
+    osp = OpticalSpecs(WvlSpec(wvls, 1), PupilSpec(('object', pupil_key), pupil_value),
+                       FieldSpec(('object', 'height'), 4.0, fields))
+    return finish(M.OpticalModel(sm, osp, name=name), aim=False, apertures=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     models = {
@@ -346,6 +366,8 @@ def main():
         'thin_triplet': lambda: from_roa('models/thin_triplet.roa', 'thin_triplet'),
         'exotic': exotic,
         'telecentric': telecentric,
+        'relay_na': lambda: relay('NA', 0.07, 'relay_na'),
+        'relay_fno': lambda: relay('f/#', 7.0, 'relay_fno'),
         'hybrid': lambda: from_roa('models/HybridAchromat.roa', 'hybrid'),
         'diffractive': diffractive,
         'diffractive_wild': diffractive_wild,

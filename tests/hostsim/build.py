@@ -14,6 +14,7 @@ LIB = os.path.join(HERE, '_build', 'libhostsim.so')
 SOURCES = [os.path.join(HERE, 'hostsim.cpp'), os.path.join(HERE, 'cuda_runtime.h'),
            os.path.join(ROOT, 'rayoptics_b200', 'csrc', 'rt_device.cuh'),
            os.path.join(ROOT, 'rayoptics_b200', 'csrc', 'rt_lean.cuh'),
+           os.path.join(ROOT, 'rayoptics_b200', 'csrc', 'rt_grid.cuh'),
            os.path.join(ROOT, 'include', 'b200rt.h')]
 
 _lib = None
@@ -100,3 +101,13 @@ def check_sqrt(x):
 def wave_opd(W, p1, d0, pk, dk, pl, dl, ray_op):
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (W, p1, d0, pk, dk, pl, dl)]
     return lib().hostsim_wave_opd(*[_dp(a) for a in arrs], C.c_double(ray_op))
+
+
+def grid_start_rays(spec, r0, r1, lean=False):
+    """spec: rt_grid_spec (PupilGridSpec.c_spec()) -> p [3, n], d [3, n]"""
+    n = r1 - r0
+    p, d = np.zeros((3, n)), np.zeros((3, n))
+    rc = lib().hostsim_grid_start_rays(C.byref(spec), C.c_int64(r0), C.c_int64(r1), C.c_int(int(lean)),
+                                       _dp(p), _dp(d))
+    assert rc == 0
+    return p, d

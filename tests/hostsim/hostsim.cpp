@@ -7,6 +7,7 @@
 #define RT_HOSTSIM 1
 #include "cuda_runtime.h"
 #include "../../rayoptics_b200/csrc/rt_lean.cuh"
+#include "../../rayoptics_b200/csrc/rt_grid.cuh"
 #include <vector>
 
 using namespace b200rt;
@@ -103,6 +104,32 @@ int64_t hostsim_check_division(int64_t n, const double *a, const double *b, int6
     }
     *n_fast = fast_cnt;
     return bad;
+}
+
+/* start rays of grid rays [r0, r1): grid_start_ray of rt_grid.cuh (lean: the lean kernels'
+ * instance, 'epd' pupils only).  p, d: [3][r1 - r0]. */
+int hostsim_grid_start_rays(const rt_grid_spec *g, int64_t r0, int64_t r1, int lean, double *p, double *d)
+{
+    GridDev G;
+    G.n_wvls = g->n_wvls; G.nx = g->nx; G.ny = g->ny;
+    G.apply_vignetting = g->apply_vignetting; G.flip_z_dir = g->flip_z_dir; G.paired = g->paired;
+    G.eprad = g->eprad; G.z_pupil = g->z_pupil; G.foc = g->foc;
+    G.fields = g->fields; G.wvl_idx = g->wvl_idx;
+    G.pupil_x = g->pupil_x; G.pupil_y = g->pupil_y; G.ref_img = g->ref_img; G.wave = g->wave;
+    G.rays_per_tile = (int64_t)g->nx*g->ny; G.chunks_per_tile = 0;
+    if (lean && g->pupil_kind != RT_PUPIL_EPD) return -1;
+    const int64_t n = r1 - r0;
+    for (int64_t r = r0; r < r1; r++) {
+        const int64_t tile = r/G.rays_per_tile, loc = r - tile*G.rays_per_tile;
+        const int f = (int)(tile/G.n_wvls);
+        Vec3 p0, d0;
+        if (lean) grid_start_ray<true>(G, RT_PUPIL_EPD, f, loc, p0, d0);
+        else grid_start_ray<false>(G, g->pupil_kind, f, loc, p0, d0);
+        const int64_t k = r - r0;
+        p[k] = p0.x; p[n + k] = p0.y; p[2*n + k] = p0.z;
+        d[k] = d0.x; d[n + k] = d0.y; d[2*n + k] = d0.z;
+    }
+    return 0;
 }
 
 /* the OPD epilogue of the grid kernels (csrc/b200rt.cu grid_chunk_loop -> wave_opd) */

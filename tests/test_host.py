@@ -6,7 +6,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, MODEL_NAMES, PHASE_MODEL_NAMES, load_model
+from conftest import ROOT, MODEL_NAMES, PHASE_MODEL_NAMES, ANGULAR_MODEL_NAMES, load_model
 from rayoptics_b200 import _abi, table as T, model as M, engine as E, parallel as P
 
 
@@ -47,7 +47,7 @@ def test_no_cpu_fallback_when_library_missing(monkeypatch):
         _abi.load_library()
 
 
-@pytest.mark.parametrize('name', MODEL_NAMES + PHASE_MODEL_NAMES)
+@pytest.mark.parametrize('name', MODEL_NAMES + PHASE_MODEL_NAMES + ANGULAR_MODEL_NAMES + ['telecentric'])
 def test_model_roundtrip_and_table(name):
     opm = load_model(name)
     sm = opm.seq_model

@@ -168,6 +168,44 @@ def test_device_opd_epilogue(hostsim, oracle, name):
     assert same(got[inf], v['opd'][inf])
 
 
+@pytest.mark.parametrize('name', ['dblgauss', 'rc', 'cellphone', 'exotic', 'relay_na', 'relay_fno'])
+def test_device_grid_start_rays(hostsim, oracle, name):
+    """grid_start_ray of rt_grid.cuh (both instances) == oracle == the numpy expressions of
+    ray_start_from_osp (rayoptics_b200/opticalspec.py, reference order of operations),
+    for spatial ('epd') and angular ('NA', 'f/#') pupil specifications."""
+    from rayoptics_b200 import engine as E
+    opm = load_model(name)
+    osp = opm.optical_spec
+    num = 11
+    spec = E.grid_spec_for_model(opm, num)
+    kind = {'relay_na': 1, 'relay_fno': 2}.get(name, 0)
+    assert spec.pupil_kind == kind
+    cs = spec.c_spec()
+    p, d, wv, pup = oracle.grid_start_rays(cs, 0, spec.n_rays)
+    # numpy restatement, ray by ray (first wavelength tile of every field)
+    xs = E.accumulated_steps(-1.0, 1.0, num)
+    n_w = spec.n_wvls
+    for fi, fld in enumerate(osp.field_of_view.fields):
+        base = fi*n_w*num*num
+        for i in range(0, num, 2):
+            for j in range(0, num, 3):
+                pt0, dir0 = osp.ray_start_from_osp(fld.apply_vignetting(np.array([xs[i], xs[j]])), fld)
+                if dir0[2]*opm.seq_model.z_dir[0] < 0:
+                    dir0 = -dir0
+                k = base + i*num + j
+                assert same(p[:, k], pt0) and same(d[:, k], dir0)
+    pg, dg = hostsim.grid_start_rays(cs, 0, spec.n_rays, lean=False)
+    assert same(pg, p)
+    if kind == 2:         # (pupil*slope)**2 is libm pow() in the reference
+        np.testing.assert_allclose(dg, d, rtol=0, atol=2e-16)
+        assert (dg == d).mean() > 0.99
+    else:
+        assert same(dg, d)
+    if kind == 0:
+        pl, dl = hostsim.grid_start_rays(cs, 0, spec.n_rays, lean=True)
+        assert same(pl, p) and same(dl, d)
+
+
 def test_division_and_sqrt_sequences(hostsim):
     """CPU sibling of rt_selftest_division (b200rt.cu): wherever a sequence reports
     'fast' it equals the IEEE operation; div_shared() and sqrt_near_one() always do."""

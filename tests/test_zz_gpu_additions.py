@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import PHASE_MODEL_NAMES, load_model, load_vectors, seeded_bundle
+from conftest import ANGULAR_MODEL_NAMES, PHASE_MODEL_NAMES, load_model, load_vectors, seeded_bundle
 from rayoptics_b200 import _abi, engine as E, table as T, trace as TR, analyses as A
 from test_trace_drivers import oracle_tracer
 from test_wave import test_cuda_opd_matches_oracle_and_reference as _opd_check
@@ -124,3 +124,27 @@ def test_cuda_drivers_match_oracle_seam():
 def test_cuda_opd_infinite_reference(oracle):
     """telecentric image space: the axial tiles use wave_abr_full_calc_inf_ref"""
     _opd_check(oracle, 'telecentric')
+
+
+@pytest.mark.parametrize('name', ANGULAR_MODEL_NAMES)
+def test_cuda_angular_pupil_grid(oracle, name):
+    """start rays from an angular object-space pupil ('NA' bit-exact; 'f/#' has one libm
+    pow() in the reference -> <= 1e-11 mm), generated by the general grid kernel"""
+    opm = load_model(name)
+    tab = T.SurfaceTable.from_model(opm.seq_model, device=0)
+    grid = E.grid_for_model(opm, tab, 24)
+    assert grid.pupil_kind == (1 if name == 'relay_na' else 2)
+    r = E.trace_grid(tab, grid)
+    torch.cuda.synchronize()
+    opts = _abi.make_opts(first_surf=1, last_surf=tab.n_ifc - 2, check_apertures=True)
+    ref = oracle.trace_grid(grid.c_spec(), tab.descs, tab.n_by_wvl, 0, grid.n_rays, opts, n_threads=4)
+    assert np.array_equal(np_(r.status), ref['status'])
+    ok = ref['status'] == 0
+    assert ok.sum() > grid.n_rays//3
+    got = np.concatenate([np_(r.p), np_(r.d)])
+    if name == 'relay_na':
+        assert np.array_equal(got, ref['last'][0:6]) and np.array_equal(np_(r.op), ref['op'])
+        assert np.array_equal(np_(r.abr)[:, ok], ref['abr'][:, ok])
+    else:
+        assert np.abs(got - ref['last'][0:6]).max() <= TOL_MM
+        assert (got == ref['last'][0:6]).mean() > 0.9
