@@ -371,6 +371,62 @@ class RayGrid:
         return self
 
 
+# --- raw ray list (analyses.py:458-510) ------------------------------------------------------
+def _cuda_bundle_tracer(opt_model, table, p0, d0, wvl_idx, trace_kwargs):
+    res = E.trace_bundle(table, p0, d0, wvl_idx=wvl_idx, full=True,
+                         outputs=('op', 'status', 'fail_surf', 'n_seg'), **trace_kwargs)
+    return {'full': res.full.cpu().numpy(), 'op': res.op.cpu().numpy(),
+            'status': res.status.cpu().numpy(), 'fail_surf': res.fail_surf.cpu().numpy(),
+            'n_seg': res.n_seg.cpu().numpy()}
+
+
+def trace_list_of_rays(opt_model, rays, output_filter=None, rayerr_filter=None, table=None,
+                       device=0, tracer=None, **kwargs):
+    """Trace a list of rays ``(pt0, dir0, wvl)`` and return the ray packages in a list
+    (analyses.py:458-510): one bundle launch instead of one ``trace()`` per ray, same
+    ``output_filter`` / ``rayerr_filter`` conventions and the same list out."""
+    from . import raytrace as RT
+    from . import trace as TR
+    sm = opt_model.seq_model
+    rays = list(rays)
+    if not rays:
+        return []
+    p0 = np.array([np.asarray(r[0], dtype=float) for r in rays]).T.copy()
+    d0 = np.array([np.asarray(r[1], dtype=float) for r in rays]).T.copy()
+    wvl_idx = np.array([sm.index_for_wavelength(r[2]) for r in rays], dtype=np.int32)
+    kw = {k: v for k, v in kwargs.items() if k in TR._TRACE_RAW_KEYS}
+    kw.setdefault('first_surf', 1)                       # raytrace.trace defaults (raytrace.py:77-79)
+    kw.setdefault('last_surf', sm.get_num_surfaces() - 2)
+    if tracer is None:
+        table = _table_for(opt_model, table, device)
+        tracer = _cuda_bundle_tracer
+    r = tracer(opt_model, table, p0, d0, wvl_idx, kw)
+    paths = {}
+    ray_list = []
+    for k, ray in enumerate(rays):
+        wvl = ray[2]
+        if wvl not in paths:
+            paths[wvl] = list(sm.path(wvl))
+        pkg, err = RT.package_ray(paths[wvl], r['full'][:, :, k], float(r['op'][k]),
+                                  int(r['status'][k]), int(r['fail_surf'][k]), int(r['n_seg'][k]), wvl)
+        if err is not None:
+            if rayerr_filter == 'full':
+                ray_list.append((ray, err))
+            elif rayerr_filter == 'summary':
+                err.ray_pkg = None
+                ray_list.append((ray, err))
+            continue
+        pkg = TR.RayPkg(*pkg)
+        if output_filter is None:
+            ray_list.append(pkg)
+        elif output_filter == 'last':
+            rr, op_delta, w = pkg
+            ray_list.append((rr[-1], op_delta, w))
+        else:
+            ray_list.append(output_filter(pkg))
+    return ray_list
+
+
 # --- PSF from a wavefront map (raytr/analyses.py:795-875) -------------------
 def psf_sampling(n=None, n_pupil=None, n_airy=None):
     """Given 2 of (grid width, pupil samples, Airy-peak samples) compute the third

@@ -138,6 +138,41 @@ def test_sequential_model_drivers_and_ray():
     assert np.abs(cr.t_abr).max() == 0.0
 
 
+def oracle_bundle_tracer(opt_model, table, p0, d0, wvl_idx, trace_kwargs):
+    from oracle import rt_oracle
+    descs, n_by_wvl, wvls = T.describe_model(opt_model.seq_model)
+    return rt_oracle.trace_bundle(descs, n_by_wvl, p0, d0, wvl_idx, _abi.make_opts(**trace_kwargs),
+                                  want_full=True, wvls=wvls)
+
+
+@needs_ref
+def test_trace_list_of_rays():
+    from conftest import load_vectors
+    from oracle import ref_harness as rh
+    opm = load_model('triplet')
+    sm = opm.seq_model
+    v = load_vectors('triplet')
+    idx = np.nonzero(v['case'] == 0)[0][:40]
+    rays = [(v['p0'][:, k], v['d0'][:, k], sm.wvlns[v['wvl_idx'][k]]) for k in idx]
+    case = dict(v['cases'][0])
+    out = A.trace_list_of_rays(opm, rays, rayerr_filter='full', tracer=oracle_bundle_tracer,
+                               check_apertures=case['check_apertures'])
+    assert len(out) == len(rays)
+    n_err = 0
+    for (pt0, dir0, wvl), item in zip(rays, out):
+        ref = rh.ref_trace(rh.ref_path(sm, wvl), pt0, dir0, wvl, **case)
+        if ref['status'] == 0:
+            assert_pkg_equals(item, ref)
+        else:
+            n_err += 1
+            ray, err = item
+            assert err.surf == ref['fail_surf'] and len(err.ray_pkg[0]) == ref['n_seg']
+    last = A.trace_list_of_rays(opm, rays, output_filter='last', tracer=oracle_bundle_tracer,
+                                check_apertures=case['check_apertures'])
+    assert len(last) == len(rays) - n_err and len(last[0]) == 3 and len(last[0][0]) == 4
+    assert A.trace_list_of_rays(opm, [], tracer=oracle_bundle_tracer) == []
+
+
 @pytest.mark.parametrize('name', ['dblgauss', 'rc'])
 def test_host_opd_matches_reference(oracle, name):
     """waveabr.wave_abr_full_calc (numpy, for callbacks) against the reference's OPDs"""

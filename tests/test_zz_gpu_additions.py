@@ -148,3 +148,19 @@ def test_cuda_angular_pupil_grid(oracle, name):
     else:
         assert np.abs(got - ref['last'][0:6]).max() <= TOL_MM
         assert (got == ref['last'][0:6]).mean() > 0.9
+
+
+def test_cuda_trace_list_of_rays():
+    from test_trace_drivers import oracle_bundle_tracer
+    opm = load_model('triplet')
+    sm = opm.seq_model
+    v = load_vectors('triplet')
+    idx = np.nonzero(v['case'] == 0)[0][:64]
+    rays = [(v['p0'][:, k], v['d0'][:, k], sm.wvlns[v['wvl_idx'][k]]) for k in idx]
+    ca = v['cases'][0]['check_apertures']
+    a = A.trace_list_of_rays(opm, rays, output_filter='last', check_apertures=ca)
+    b = A.trace_list_of_rays(opm, rays, output_filter='last', check_apertures=ca,
+                             tracer=oracle_bundle_tracer)
+    assert len(a) == len(b) > 0
+    for (sa, oa, wa), (sb, ob, wb) in zip(a, b):
+        assert oa == ob and wa == wb and all(np.array_equal(x, y) for x, y in zip(sa, sb))
