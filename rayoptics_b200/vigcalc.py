@@ -9,8 +9,11 @@ Host-side model preparation (tens of rays per field, run once per model):
   (max radial height of the 5 boundary rays per field -> ``max_aperture``;
   the stop surface is set from the first field only)
 
-Both take the tracer as an argument (``trace_fn(seq_model, pt0, dir0, wvl,
-**kw) -> (ray, op, wvl)``): the product passes the GPU drop-in
+``aim_all_fields_batched`` / ``set_clear_apertures_batched`` do the same with all fields
+per bundle launch.
+
+The per-ray versions take the tracer as an argument (``trace_fn(seq_model, pt0, dir0, wvl,
+**kw) -> (ray, op, wvl)``; the batched ones a ``bundle_fn``): the product passes the GPU drop-in
 ``rayoptics_b200.raytrace.trace``; the fixture generator, which runs where no
 GPU exists, passes the reference's own ``trace``.  Not on the parity path --
 their results are inputs shared by oracle and engine.
@@ -143,3 +146,131 @@ def set_clear_apertures(opt_model, trace_fn, wvl=None):
         m = max_ap([rayset[0]], i) if i == stop else max_ap(rayset, i)
         if m is not None:
             sm.ifcs[i].set_max_aperture(m)
+
+
+# --- batched versions: all fields per launch --------------------------------------------------
+def cuda_bundle_fn(opt_model, table=None, device=0):
+    """``bundle_fn(p0 [3, n], d0 [3, n], wvl, last_surf) -> (full [n_ifc, 10, n], n_seg [n])``
+    on the CUDA engine (whole rays: aiming and aperture setting read interior interfaces)."""
+    from . import engine as E
+    from .analyses import _table_for
+    tab = _table_for(opt_model, table, device)
+
+    def fn(p0, d0, wvl):
+        w = np.full(p0.shape[1], tab.wvl_index(wvl), dtype=np.int32)
+        r = E.trace_bundle(tab, p0, d0, wvl_idx=w, full=True, outputs=('n_seg',), first_surf=1,
+                           last_surf=tab.n_ifc - 2)
+        return r.full.cpu().numpy(), r.n_seg.cpu().numpy()
+    return fn
+
+
+def _start_rays(opt_model, fields, aims, pupils):
+    """(p0, d0) [3, n] for field k aimed at aims[k] with relative pupil pupils[k]"""
+    osp, sm = opt_model.optical_spec, opt_model.seq_model
+    p0, d0 = np.zeros((3, len(fields))), np.zeros((3, len(fields)))
+    for k, (fld, aim, pupil) in enumerate(zip(fields, aims, pupils)):
+        saved = fld.aim_info
+        fld.aim_info = None if aim is None else np.array(aim, dtype=float)
+        try:
+            pt0, dir0 = osp.ray_start_from_osp(np.array(pupil, dtype=float), fld, 'rel pupil')
+        finally:
+            fld.aim_info = saved
+        if dir0[2]*sm.z_dir[0] < 0:
+            dir0 = -dir0
+        p0[:, k], d0[:, k] = pt0, dir0
+    return p0, d0
+
+
+def aim_all_fields_batched(opt_model, bundle_fn=None, wvl=None, tol=1e-13, max_iter=30):
+    """``aim_chief_ray`` for every field at once (raytr/trace.py:313-415,627-640): each
+    Newton iteration traces base + two finite-difference rays of ALL fields in one bundle,
+    each backtracking round one more.  Same iteration as ``aim_chief_ray`` field by field,
+    so the aim points are the same numbers.  Sets ``fld.aim_info``; returns the list."""
+    osp, sm = opt_model.optical_spec, opt_model.seq_model
+    stop = sm.stop_surface
+    fields = list(osp.field_of_view.fields)
+    nf = len(fields)
+    if stop is None:
+        for fld in fields:
+            fld.aim_info = np.array([0., 0.])
+        return [f.aim_info for f in fields]
+    if bundle_fn is None:
+        bundle_fn = cuda_bundle_fn(opt_model)
+    wvl = osp.spectral_region.central_wvl if wvl is None else wvl
+    zero = [0., 0.]
+
+    def stop_xy(idx, aims):
+        """stop intercepts of the (0, 0) pupil rays of fields idx (NaN rows where a ray fails)"""
+        p0, d0 = _start_rays(opt_model, [fields[i] for i in idx], aims, [zero]*len(idx))
+        full, n_seg = bundle_fn(p0, d0, wvl)
+        out = full[stop, 0:2, :].T.copy()
+        out[n_seg <= stop] = np.nan
+        return out
+
+    x = np.zeros((nf, 2))
+    f = stop_xy(range(nf), x)
+    active = [i for i in range(nf) if np.isfinite(f[i]).all()]
+    h = 1e-4*max(1.0, osp.fod.enp_radius)
+    for _ in range(max_iter):
+        active = [i for i in active if np.max(np.abs(f[i])) >= tol]
+        if not active:
+            break
+        fx = stop_xy(active, [x[i] + [h, 0.] for i in active])
+        fy = stop_xy(active, [x[i] + [0., h] for i in active])
+        steps, keep = {}, []
+        for k, i in enumerate(active):
+            if not (np.isfinite(fx[k]).all() and np.isfinite(fy[k]).all()):
+                continue
+            J = np.stack([(fx[k] - f[i])/h, (fy[k] - f[i])/h], axis=1)
+            try:
+                steps[i] = np.linalg.solve(J, -f[i])
+            except np.linalg.LinAlgError:
+                continue
+            keep.append(i)
+        # backtracking, all still-unaccepted fields per launch
+        lam = {i: 1.0 for i in keep}
+        pending, accepted = list(keep), []
+        for _bt in range(20):
+            if not pending:
+                break
+            trial = stop_xy(pending, [x[i] + lam[i]*steps[i] for i in pending])
+            nxt = []
+            for k, i in enumerate(pending):
+                if np.isfinite(trial[k]).all() and np.max(np.abs(trial[k])) < np.max(np.abs(f[i])):
+                    x[i], f[i] = x[i] + lam[i]*steps[i], trial[k]
+                    accepted.append(i)
+                else:
+                    lam[i] *= 0.5
+                    nxt.append(i)
+            pending = nxt
+        active = accepted
+    for i, fld in enumerate(fields):
+        if fld.x == 0.0:
+            x[i, 0] = 0.0
+        fld.aim_info = x[i].copy()
+    return [f.aim_info for f in fields]
+
+
+def set_clear_apertures_batched(opt_model, bundle_fn=None, wvl=None):
+    """``set_clear_apertures`` (raytr/vigcalc.py:45-80) with the 5 boundary rays of all
+    fields in one bundle."""
+    osp, sm = opt_model.optical_spec, opt_model.seq_model
+    if bundle_fn is None:
+        bundle_fn = cuda_bundle_fn(opt_model)
+    wvl = osp.spectral_region.central_wvl if wvl is None else wvl
+    fields = list(osp.field_of_view.fields)
+    rays_f, rays_p = [], []
+    for fld in fields:
+        for pr in osp.pupil.pupil_rays:
+            rays_f.append(fld)
+            rays_p.append(fld.apply_vignetting(list(pr)))
+    p0, d0 = _start_rays(opt_model, rays_f, [f.aim_info for f in rays_f], rays_p)
+    full, n_seg = bundle_fn(p0, d0, wvl)
+    per = len(osp.pupil.pupil_rays)
+    r = np.sqrt(full[:, 0, :]*full[:, 0, :] + full[:, 1, :]*full[:, 1, :])      # [n_ifc, n]
+    stop = sm.stop_surface
+    for i in range(sm.get_num_surfaces()):
+        sel = slice(0, per) if i == stop else slice(None)
+        if (n_seg[sel] <= i).any():           # a ray failed before this interface: keep the value
+            continue
+        sm.ifcs[i].set_max_aperture(float(r[i, sel].max()))

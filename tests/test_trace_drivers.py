@@ -198,3 +198,37 @@ def test_host_opd_matches_reference(oracle, name):
         assert got == v['opd'][k]
         checked += 1
     assert checked > 20
+
+
+def oracle_bundle_fn(opm):
+    from oracle import rt_oracle
+    descs, n_by_wvl, wvls = T.describe_model(opm.seq_model)
+
+    def fn(p0, d0, wvl):
+        w = np.full(p0.shape[1], opm.seq_model.index_for_wavelength(wvl), dtype=np.int32)
+        r = rt_oracle.trace_bundle(descs, n_by_wvl, p0, d0, w,
+                                   _abi.make_opts(first_surf=1, last_surf=len(descs) - 2),
+                                   want_full=True, wvls=wvls)
+        return r['full'], r['n_seg']
+    return fn
+
+
+@pytest.mark.parametrize('name', ['triplet', 'dblgauss', 'evenasph'])
+def test_batched_aiming_and_apertures(name):
+    """aim points: the stored ones of the reference's .roa files (its iterate_ray) where the
+    model came from a .roa, the per-ray Newton iteration otherwise; apertures: the per-ray
+    version on the same rays"""
+    import copy
+    from rayoptics_b200 import vigcalc as V, raytrace as RT
+    opm = load_model(name)
+    stored = [None if f.aim_info is None else np.array(f.aim_info, dtype=float)
+              for f in opm.optical_spec.field_of_view.fields]
+    stored_ap = [ifc.max_aperture for ifc in opm.seq_model.ifcs]
+    fn = oracle_bundle_fn(opm)
+    aims = V.aim_all_fields_batched(opm, fn)
+    for a, s in zip(aims, stored):
+        if s is not None:
+            assert np.abs(a - s).max() < 1e-7   # .roa aim points: scipy newton at its default tol (1.5e-8)
+    V.set_clear_apertures_batched(opm, fn)
+    got_ap = [ifc.max_aperture for ifc in opm.seq_model.ifcs]
+    np.testing.assert_allclose(got_ap[1:-1], stored_ap[1:-1], rtol=1e-6)

@@ -164,3 +164,16 @@ def test_cuda_trace_list_of_rays():
     assert len(a) == len(b) > 0
     for (sa, oa, wa), (sb, ob, wb) in zip(a, b):
         assert oa == ob and wa == wb and all(np.array_equal(x, y) for x, y in zip(sa, sb))
+
+
+def test_cuda_batched_aiming():
+    """chief-ray aiming and clear apertures of all fields through bundle launches"""
+    from rayoptics_b200 import vigcalc as V
+    from test_trace_drivers import oracle_bundle_fn
+    opm_a, opm_b = load_model('dblgauss'), load_model('dblgauss')
+    a = V.aim_all_fields_batched(opm_a)
+    b = V.aim_all_fields_batched(opm_b, oracle_bundle_fn(opm_b))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    V.set_clear_apertures_batched(opm_a)
+    V.set_clear_apertures_batched(opm_b, oracle_bundle_fn(opm_b))
+    assert [i.max_aperture for i in opm_a.seq_model.ifcs] == [i.max_aperture for i in opm_b.seq_model.ifcs]
