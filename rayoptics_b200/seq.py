@@ -1,0 +1,189 @@
+"""Self-contained reader of CODE V ``.seq`` lens files.
+
+The reference imports ``.seq`` files through ``codev/cmdproc.py:56-449`` and
+``codev/reader.py``, resolving glass names with the un-vendored ``opticalglass``
+catalogs.  This reader builds the same ``OpticalModel`` mirror the rest of this package
+consumes (``model.py`` / ``opticalspec.py``) from the commands that describe a
+rotationally symmetric sequential system:
+
+  RDM, TITLE, DIM, EPD / FNO / NA / NAO, WL, REF, XAN YAN / XOB YOB / XIM YIM,
+  VUX VLX VUY VLY, SO / S / SI (curvature or radius, thickness, glass | REFL),
+  STO, CIR [EDG], K / CON, ASP with A..J (r**4 .. r**20), SPS coefficients are not read.
+
+Glasses: ``REFL`` / ``AIR`` / empty, a fictitious glass code ``nnn.vvv`` (n_d = 1.nnn,
+V_d = vv.v, CODE V's six-digit form), or a catalog name looked up in ``glass_map``
+(name -> Medium, index, or ``(n_d, V_d)``; matched case-insensitively, with and without
+the ``_CATALOG`` suffix).  There is no glass catalog in this package: an unknown name
+raises ``KeyError`` naming the glass, it is never guessed.
+
+Not read (raise ``NotImplementedError``): tilts and decenters (ADE.. / XDE.. / DAR / BEN),
+zoom data, special surface types.  Solves (CCY, THC, PIM) and DER lines are ignored like
+the reference does when it only builds the model.
+"""
+from __future__ import annotations
+
+import re
+
+from . import model as M
+from .opticalspec import OpticalSpecs, WvlSpec, PupilSpec, FieldSpec, FocusRange
+
+_IGNORED = {'LEN', 'INI', 'WTW', 'WTF', 'CCY', 'THC', 'PIM', 'DER', 'GO', 'CUF', 'GL1', 'GL2',
+            'SLB', 'THM', 'TEM', 'PRE', 'INF', 'MNR', 'MXR', 'CUM', 'VLZ', 'VUZ', 'RMD', 'GLB'}
+_TILTS = {'ADE', 'BDE', 'CDE', 'XDE', 'YDE', 'ZDE', 'DAR', 'BEN', 'REV', 'BAS', 'RET'}
+_ASP_COEFS = 'ABCDEFGHJ'
+
+
+def _commands(text):
+    """lines / ';'-separated commands, comments ('!') dropped, quoted strings kept whole"""
+    for line in text.splitlines():
+        line = line.split('!', 1)[0]
+        for part in line.split(';'):
+            toks = re.findall(r"'[^']*'|\"[^\"]*\"|\S+", part)
+            if toks:
+                yield toks
+
+
+def _medium(token, glass_map):
+    if token is None or token.upper() in ('AIR', ''):
+        return M.Air()
+    m = re.fullmatch(r'(\d{3})\.(\d{3})', token)
+    if m:                                   # fictitious glass: n_d = 1.nnn, V_d = vv.v
+        return M.AbbeGlass(1.0 + int(m.group(1))/1000.0, int(m.group(2))/10.0, label=token)
+    keys = [token, token.upper(), token.upper().split('_')[0]]
+    for k in keys:
+        for gk, gv in (glass_map or {}).items():
+            if gk.upper() == k.upper():
+                if isinstance(gv, M.Medium):
+                    return gv
+                if isinstance(gv, (tuple, list)):
+                    return M.AbbeGlass(gv[0], gv[1], label=token)
+                return M.ConstantIndex(float(gv), label=token)
+    raise KeyError(f'glass {token!r}: not in glass_map (this package ships no glass catalog)')
+
+
+def open_seq(path, glass_map=None):
+    """Read a CODE V ``.seq`` file into an ``OpticalModel`` mirror."""
+    with open(path) as f:
+        text = f.read()
+    radius_mode = False
+    title = ''
+    wvls, ref_wl = [587.6], 0
+    pupil = None
+    fld = {}
+    vig = {}
+    surfs = []        # dicts: cv, thi, glass token, mode, stop, cc, coefs, cir
+    cur = None
+    for toks in _commands(text):
+        tla = toks[0][:3].upper()
+        args = toks[1:]
+        if tla == 'RDM':
+            radius_mode = (not args) or args[0].upper().startswith('Y')
+        elif tla == 'TIT':
+            title = ' '.join(args).strip('\'"')
+        elif tla == 'DIM':
+            if args and args[0].upper()[0] != 'M':
+                raise NotImplementedError('DIM other than millimetres')
+        elif toks[0].upper() in ('EPD', 'FNO', 'NA', 'NAO'):
+            key = {'EPD': ('object', 'epd'), 'FNO': ('image', 'f/#'), 'NA': ('image', 'NA'),
+                   'NAO': ('object', 'NA')}[toks[0].upper()]
+            pupil = (key, float(args[0]))
+        elif tla == 'WL':
+            wvls = [float(a) for a in args]
+        elif tla == 'REF':
+            ref_wl = int(args[0]) - 1
+        elif tla in ('XAN', 'YAN', 'XOB', 'YOB', 'XIM', 'YIM', 'XRI', 'YRI'):
+            fld[toks[0].upper()[:3]] = [float(a) for a in args]
+        elif tla in ('VUX', 'VLX', 'VUY', 'VLY'):
+            vig[tla.lower()] = [float(a) for a in args]
+        elif tla in ('SO', 'S', 'SI') and toks[0].upper() in ('SO', 'S', 'SI'):
+            c = float(args[0]) if args else 0.0
+            if radius_mode:
+                c = 1.0/c if c != 0.0 else 0.0
+            thi = float(args[1]) if len(args) > 1 else 0.0
+            g = args[2] if len(args) > 2 else None
+            cur = {'cv': c, 'thi': thi, 'glass': g, 'stop': False, 'cc': None, 'coefs': None,
+                   'cir': None, 'kind': toks[0].upper()}
+            surfs.append(cur)
+        elif tla == 'STO':
+            cur['stop'] = True
+        elif tla == 'CIR':
+            vals = [a for a in args if re.fullmatch(r'[-+0-9.eE]+', a)]
+            if vals and (len(args) == 1 or args[0].upper() != 'OBS'):
+                cur['cir'] = float(vals[0])
+        elif tla == 'K' and toks[0].upper() == 'K':
+            cur['cc'] = float(args[0])
+        elif tla == 'CON':
+            cur['cc'] = cur['cc'] if cur['cc'] is not None else 0.0
+        elif tla == 'ASP':
+            cur['coefs'] = cur['coefs'] or [0.0]*10
+        elif toks[0].upper() in _ASP_COEFS and cur is not None:
+            cur['coefs'] = cur['coefs'] or [0.0]*10
+            cur['coefs'][_ASP_COEFS.index(toks[0].upper()) + 1] = float(args[0])   # A -> r**4
+        elif tla in _TILTS:
+            raise NotImplementedError(f'.seq command {toks[0]}: tilts / decenters are not read')
+        elif tla in _IGNORED or tla in ('SPS', 'SCO', 'SCC'):
+            if tla in ('SPS', 'SCO'):
+                raise NotImplementedError(f'.seq command {toks[0]}: special surface types are not read')
+        # anything else: not part of the path description (the reference logs and skips it too)
+
+    if len(surfs) < 2:
+        raise ValueError(f'{path}: no surfaces')
+    ifcs, gaps, z_dir = [], [], []
+    stop_surface = None
+    z = 1
+    medium_before = None
+    for i, s in enumerate(surfs):
+        g = s['glass']
+        mode = 'transmit'
+        if g is not None and g.upper() in ('REFL', 'REFLECT'):
+            mode, g = 'reflect', None
+        if s['coefs'] is not None and any(c != 0.0 for c in s['coefs']):
+            prf = M.EvenPolynomial(c=s['cv'], cc=s['cc'] or 0.0, coefs=s['coefs'])
+        elif s['cc'] is not None and s['cc'] != 0.0:
+            prf = M.Conic(c=s['cv'], cc=s['cc'])
+        else:
+            prf = M.Spherical(c=s['cv'])
+        if s['kind'] in ('SO', 'SI'):
+            mode = 'dummy'
+        ifc = M.Surface(profile=prf, interact_mode=mode)
+        if s['cir'] is not None:
+            ifc.max_aperture = s['cir']
+        if s['stop']:
+            stop_surface = i
+        ifcs.append(ifc)
+        if i < len(surfs) - 1:
+            if mode == 'reflect':
+                med = medium_before if medium_before is not None else M.Air()
+                z = -z
+            else:
+                med = _medium(g, glass_map)
+            gaps.append(M.Gap(s['thi'], med))
+            z_dir.append(z)
+            medium_before = med
+    sm = M.SequentialModel(ifcs, gaps, z_dir=z_dir, stop_surface=stop_surface, wvlns=wvls,
+                           ref_wvl=ref_wl)
+    # optical specification
+    if pupil is None:
+        pupil = (('object', 'epd'), 1.0)
+    if 'XAN' in fld or 'YAN' in fld:
+        fkey, fx, fy = ('object', 'angle'), fld.get('XAN'), fld.get('YAN')
+    elif 'XOB' in fld or 'YOB' in fld:
+        fkey, fx, fy = ('object', 'height'), fld.get('XOB'), fld.get('YOB')
+    elif 'XIM' in fld or 'YIM' in fld:
+        fkey, fx, fy = ('image', 'height'), fld.get('XIM'), fld.get('YIM')
+    elif 'XRI' in fld or 'YRI' in fld:
+        fkey, fx, fy = ('image', 'real height'), fld.get('XRI'), fld.get('YRI')
+    else:
+        fkey, fx, fy = ('object', 'angle'), [0.0], [0.0]
+    n_f = max(len(fx or []), len(fy or []))
+    fx = (fx or [0.0]*n_f) + [0.0]*(n_f - len(fx or []))
+    fy = (fy or [0.0]*n_f) + [0.0]*(n_f - len(fy or []))
+    fields = []
+    for k in range(n_f):
+        v = {key: (vals[k] if k < len(vals) else 0.0) for key, vals in vig.items()}
+        fields.append(M.Field(x=fx[k], y=fy[k], **v))
+    max_f = max((abs(a) for a in fx + fy), default=0.0)
+    # the thickness on the SI line is the defocus from the image surface
+    osp = OpticalSpecs(WvlSpec(wvls, ref_wl), PupilSpec(*pupil), FieldSpec(fkey, max_f, fields),
+                       FocusRange(surfs[-1]['thi'], 0.0))
+    return M.OpticalModel(sm, osp, name=title or str(path).rsplit('/', 1)[-1])

@@ -155,3 +155,66 @@ def test_first_order_against_stored_reference_values():
     fod = opm.optical_spec.fod
     assert fod.efl == pytest.approx(50.0, rel=2e-4)
     assert load_model('dblgauss').optical_spec.fod.efl == pytest.approx(100.0, rel=2e-4)
+
+
+def _same_prescription(a, b, skip_modes=()):
+    """two SequentialModel mirrors describe the same path (all wavelengths)"""
+    assert a.wvlns == pytest.approx(b.wvlns, rel=1e-15) and a.get_num_surfaces() == b.get_num_surfaces()
+    for wa, wb in zip(a.wvlns, b.wvlns):
+        da, na = T.describe_path(a.path(wa))
+        db, nb = T.describe_path(b.path(wb))
+        assert na == nb
+        for i, (x, y) in enumerate(zip(da, db)):
+            assert (x.profile, x.cv, x.cc, list(x.coefs), list(x.t), x.z_dir) == \
+                   (y.profile, y.cv, y.cc, list(y.coefs), list(y.t), y.z_dir)
+            assert x.mode == y.mode or i in skip_modes
+
+
+def test_seq_reader():
+    """CODE V .seq reader (codev/cmdproc.py:56-449): own sample everywhere, the reference's
+    double Gauss where /root/reference exists (same table as the numeric fixture)."""
+    from rayoptics_b200 import seq
+    m = seq.open_seq(os.path.join(ROOT, 'tests', 'golden', 'samples', 'triplet_fict.seq'))
+    sm, osp = m.seq_model, m.optical_spec
+    assert m.name == 'fictitious triplet' and sm.get_num_surfaces() == 9 and sm.stop_surface == 4
+    assert sm.ifcs[1].profile.cv == 1/21.25 and sm.gaps[1].thi == 5.0          # radius mode
+    assert type(sm.ifcs[3].profile).__name__ == 'EvenPolynomial' and sm.ifcs[3].profile.cc == -0.25
+    assert sm.ifcs[3].profile.coefs[:3] == [0.0, 1.5e-6, -2.0e-9]              # A -> r**4
+    assert sm.gaps[1].medium.rindex(587.5618) == pytest.approx(1.620, abs=1e-9)   # 620.603
+    assert sm.ifcs[2].max_aperture == 9.0 and sm.wvlns == [656.3, 587.6, 486.1] and sm.ref_wvl == 1
+    assert osp.pupil.key == ('image', 'f/#') and osp.fod.fno == pytest.approx(4.5, rel=1e-12)
+    assert [(f.y, f.vuy, f.vly) for f in osp.field_of_view.fields] == \
+        [(0.0, 0.0, 0.0), (7.0, 0.05, 0.05), (10.0, 0.1, 0.15)]
+    assert osp.defocus.focus_shift == -0.05
+    T.describe_model(sm)                                   # compiles into a surface table
+    with pytest.raises(KeyError):
+        seq._medium('NBK7_SCHOTT', {})
+    ref = '/root/reference/src/rayoptics/codev/tests/ag_dblgauss.seq'
+    if os.path.exists(ref):
+        fx = load_model('dblgauss').seq_model
+        gm = {'NSSK2_SCHOTT': fx.gaps[1].medium, 'NSK2_SCHOTT': fx.gaps[3].medium,
+              'F5_SCHOTT': fx.gaps[4].medium, 'NSK16_SCHOTT': fx.gaps[8].medium}
+        o = seq.open_seq(ref, glass_map=gm)
+        o.seq_model.gaps[-1].thi += o.optical_spec.defocus.focus_shift   # the fixture lumps the defocus
+        o.update_model()
+        _same_prescription(o.seq_model, fx, skip_modes=(0, 6))
+        assert o.optical_spec.fod.efl == pytest.approx(100.0038, abs=1e-4)      # .lis: EFL 100.0038
+
+
+def test_zmx_reader():
+    """Zemax .zmx reader (zemax/zmxread.py:93-388) on the file the `evenasph` fixture was
+    transcribed from (reference tree only)."""
+    import glob
+    from rayoptics_b200 import zmx
+    hits = [f for f in glob.glob('/root/reference/src/rayoptics/zemax/tests/*') if 'US08427765-1' in f]
+    if not hits:
+        pytest.skip('/root/reference not present')
+    glass = {'J-LAK14': (1.6968, 55.5), 'L-TIM28': (1.68893, 31.1), 'SF11': (1.78472, 25.7),
+             'TAF3': (1.8042, 46.5), 'TAFD30': (1.883, 40.8)}
+    m = zmx.open_zmx(hits[0], glass_map=glass)
+    fx = load_model('evenasph')
+    _same_prescription(m.seq_model, fx.seq_model, skip_modes=(5,))
+    assert m.seq_model.stop_surface == 5 and m.optical_spec.pupil.key == ('image', 'f/#')
+    assert [f.y for f in m.optical_spec.field_of_view.fields] == [0.0, 8.0, 13.6]
+    with pytest.raises(KeyError):
+        zmx.open_zmx(hits[0], glass_map={})
