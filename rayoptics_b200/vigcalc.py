@@ -274,3 +274,113 @@ def set_clear_apertures_batched(opt_model, bundle_fn=None, wvl=None):
         if (n_seg[sel] <= i).any():           # a ray failed before this interface: keep the value
             continue
         sm.ifcs[i].set_max_aperture(float(r[i, sel].max()))
+
+
+# --- vignetting factors from clear apertures (raytr/vigcalc.py:83-93,227-342,393-471) ----------
+def _edge_pt_target(ifc, rel_dir):
+    """Surface.edge_pt_target / Aperture.edge_pt_target (elem/surface.py:210-218,422-427,459-464)"""
+    d = np.array(rel_dir, dtype=float)
+    length = np.linalg.norm(d)
+    d = d if length == 0.0 else d/length
+    cas = getattr(ifc, 'clear_apertures', None) or []
+    if cas:
+        ca = cas[0]
+        if type(ca).__name__ == 'Circular':
+            return ca.radius*d
+        return np.array([ca.x_half_width*d[0], ca.y_half_width*d[1]])
+    return ifc.max_aperture*d
+
+
+def iterate_pupil_ray(opt_model, indx, xy, start_r0, r_target, fld, wvl, **engine):
+    """Pupil coordinate whose ray passes interface ``indx`` at radial height ``r_target``
+    (vigcalc.py:393-471): scipy's secant ``newton`` with the reference's tolerance."""
+    from scipy.optimize import newton
+    from . import trace as TR
+    from .raytrace import TraceError, TraceMissedSurfaceError
+
+    def r_pupil_coordinate(xy_coord):
+        rel_p1 = np.array([0., 0.])
+        rel_p1[xy] = xy_coord
+        try:
+            ray_pkg = TR.trace_base(opt_model, rel_p1, fld, wvl, apply_vignetting=False,
+                                    check_apertures=False, **engine)
+        except TraceError as ray_error:
+            ray_pkg = ray_error.ray_pkg
+            limit = indx if isinstance(ray_error, TraceMissedSurfaceError) else indx - 1
+            if ray_error.surf <= limit:
+                ray_error.rel_p1 = rel_p1
+                raise ray_error
+        p = ray_pkg[0][indx][0]
+        r_ray = math.copysign(math.sqrt(p[0]**2 + p[1]**2), r_target)
+        return r_ray - r_target
+
+    start_coords = np.array([0., 0.])
+    if indx is None:                    # floating stop: use the entrance pupil for aiming
+        start_coords[xy] = r_target
+        return start_coords
+    try:
+        start_r, results = newton(r_pupil_coordinate, start_r0, tol=1e-6, disp=False,
+                                  full_output=True)
+    except TraceError as rt_err:
+        start_r = 0.9*rt_err.rel_p1[xy]
+    start_coords[xy] = start_r
+    return start_coords
+
+
+def calc_vignetted_ray(opm, xy, start_dir, fld, wvl, max_iter_count=50, **engine):
+    """Find the limiting aperture along ``start_dir`` and return ``(vig, clip_indx, ray_pkg)``
+    (vigcalc.py:248-342), same search: trace with clipping; when a surface blocks, iterate
+    the pupil ray to its edge; stop when the same surface blocks twice or the ray passes."""
+    from . import trace as TR
+    from .raytrace import TraceError
+    rel_p1 = np.array(start_dir, dtype=float)
+    sm = opm.seq_model
+    still_iterating, clip_indx, iter_count, ray_pkg = True, None, 0, None
+    while still_iterating and iter_count < max_iter_count:
+        iter_count += 1
+        try:
+            ray_pkg = TR.trace_base(opm, rel_p1, fld, wvl, apply_vignetting=False,
+                                    check_apertures=True, pt_inside_fuzz=1e-4, **engine)
+        except TraceError as ray_error:
+            ray_pkg = ray_error.ray_pkg
+            indx = ray_error.surf
+            if indx == clip_indx:
+                still_iterating = False
+            else:
+                r_target = _edge_pt_target(sm.ifcs[indx], start_dir)
+                rel_p1 = iterate_pupil_ray(opm, indx, xy, rel_p1[xy], r_target[xy], fld, wvl, **engine)
+                clip_indx = indx
+        else:
+            if clip_indx is not None:
+                still_iterating = False
+            else:                       # first pass succeeded: go to the edge of the stop
+                stop_indx = sm.stop_surface
+                if stop_indx is not None:
+                    r_target = _edge_pt_target(sm.ifcs[stop_indx], start_dir)
+                    rel_p1 = iterate_pupil_ray(opm, stop_indx, xy, rel_p1[xy], r_target[xy], fld,
+                                               wvl, **engine)
+                    clip_indx = stop_indx
+                else:
+                    still_iterating = False
+    vig = 1.0 - (rel_p1[xy]/start_dir[xy])
+    return vig, clip_indx, ray_pkg
+
+
+def calc_vignetting_for_field(opm, fld, wvl, **kwargs):
+    """vigcalc.py:227-245: the four pupil directions -> fld.vux, vlx, vuy, vly"""
+    vg = {k: kwargs.pop(k) for k in ('max_iter_count',) if k in kwargs}
+    pupil_starts = opm.optical_spec.pupil.pupil_rays[1:]
+    vig_factors = [0.]*4
+    for i in range(4):
+        vig_factors[i] = calc_vignetted_ray(opm, i//2, pupil_starts[i], fld, wvl, **vg, **kwargs)[0]
+    fld.vux, fld.vlx, fld.vuy, fld.vly = vig_factors
+
+
+def set_vig(opm, **kwargs):
+    """From the existing fields and clear apertures, calculate the vignetting factors
+    (vigcalc.py:83-90).  ``tracer=`` / ``table=`` / ``device=`` select the engine
+    (default: CUDA)."""
+    osp = opm.optical_spec
+    wvl = osp.spectral_region.central_wvl
+    for fld in osp.field_of_view.fields:
+        calc_vignetting_for_field(opm, fld, wvl, **kwargs)

@@ -232,3 +232,32 @@ def test_batched_aiming_and_apertures(name):
     V.set_clear_apertures_batched(opm, fn)
     got_ap = [ifc.max_aperture for ifc in opm.seq_model.ifcs]
     np.testing.assert_allclose(got_ap[1:-1], stored_ap[1:-1], rtol=1e-6)
+
+
+def test_set_vig_grazes_the_limiting_apertures():
+    """set_vig (raytr/vigcalc.py:83-90,227-342): after it, every boundary ray of every field
+    passes with clipping and touches a clear aperture (the limiting one) to the secant
+    tolerance; on axis nothing is vignetted (apertures were set from the same rays)."""
+    from rayoptics_b200 import vigcalc as V
+    opm = load_model('dblgauss')
+    osp, sm = opm.optical_spec, opm.seq_model
+    fields = osp.field_of_view.fields
+    stored = [(f.vux, f.vlx, f.vuy, f.vly) for f in fields]
+    for f in fields:
+        f.vux = f.vlx = f.vuy = f.vly = 0.0
+    V.set_vig(opm, tracer=oracle_tracer)
+    got = [(f.vux, f.vlx, f.vuy, f.vly) for f in fields]
+    assert max(abs(v) for v in got[0]) < 1e-5               # axial bundle fills the stop
+    # the fixture's apertures were set to pass the rays with VUY/VLY = .2/.25 and .4/.4, so
+    # the apertures cannot vignette more than that
+    for g, s in zip(got[1:], stored[1:]):
+        assert -1e-4 <= g[2] <= s[2] + 1e-4 and -1e-4 <= g[3] <= s[3] + 1e-4 and 0 <= g[0] < 0.5
+    wvl = osp.spectral_region.central_wvl
+    for f in fields:
+        for pr in osp.pupil.pupil_rays[1:]:
+            res = TR.trace_safe(opm, np.array(pr), f, wvl, None, 'full', tracer=oracle_tracer,
+                                check_apertures=True, pt_inside_fuzz=2e-4)
+            assert res.err is None                          # with the new factors the ray passes
+            slack = min(ifc.max_aperture - np.hypot(seg[0][0], seg[0][1])
+                        for ifc, seg in list(zip(sm.ifcs, res.pkg[0]))[1:-1])
+            assert -2e-4 < slack < 2e-3                     # ... and grazes the limiting aperture
