@@ -121,10 +121,10 @@ def open_seq(path, glass_map=None):
             cur['coefs'][_ASP_COEFS.index(toks[0].upper()) + 1] = float(args[0])   # A -> r**4
         elif tla in _TILTS:
             raise NotImplementedError(f'.seq command {toks[0]}: tilts / decenters are not read')
-        elif tla in _IGNORED or tla in ('SPS', 'SCO', 'SCC'):
-            if tla in ('SPS', 'SCO'):
-                raise NotImplementedError(f'.seq command {toks[0]}: special surface types are not read')
-        # anything else: not part of the path description (the reference logs and skips it too)
+        elif tla in ('SPS', 'SCO'):
+            raise NotImplementedError(f'.seq command {toks[0]}: special surface types are not read')
+        # _IGNORED and anything else: not part of the path description (the reference logs
+        # and skips unknown commands too)
 
     if len(surfs) < 2:
         raise ValueError(f'{path}: no surfaces')

@@ -5,7 +5,7 @@ resolved by the un-vendored ``opticalglass`` catalogs.  This reader builds the
 ``OpticalModel`` mirror of this package from the keywords that describe a rotationally
 symmetric sequential system:
 
-  UNIT, NAME, ENPD / FNUM / OBNA, WAVM (or WAVL / WWGT), PWAV, FTYP, XFLN / YFLN,
+  UNIT, NAME, ENPD / FNUM / OBNA, WAVM (or WAVL / WWGT), FTYP, XFLN / YFLN,
   VDXN VDYN VCXN VCYN, SURF with TYPE (STANDARD, EVENASPH), CURV, DISZ, GLAS, DIAM,
   CONI, PARM, STOP.
 
@@ -41,7 +41,7 @@ def open_zmx(path, glass_map=None):
     """Read a Zemax ``.zmx`` file into an ``OpticalModel`` mirror."""
     title = ''
     pupil = None
-    wvls, wts, pwav = [], [], None
+    wvls, wts = [], []
     ftyp, n_fields = 0, None
     xf, yf = [], []
     vig = {}
@@ -75,8 +75,6 @@ def open_zmx(path, glass_map=None):
             wvls = [float(i)*1e3 for i in items]
         elif cmd == 'WWGT':
             wts = [float(i) for i in items]
-        elif cmd == 'PWAV':
-            pwav = int(items[0])
         elif cmd == 'FTYP':
             ftyp = int(items[0])
             if len(items) > 2:
@@ -113,8 +111,6 @@ def open_zmx(path, glass_map=None):
             cur['parm'][int(items[0])] = float(items[1])
         elif cmd == 'DIAM':
             cur['diam'] = float(items[0])
-        elif cmd == 'MIRR' and False:
-            pass
     if len(surfs) < 2:
         raise ValueError(f'{path}: no surfaces')
     if wvls and len(wvls) > 1 and wvls[-1] == 550.0:       # zmxread.py:251-254
@@ -153,8 +149,7 @@ def open_zmx(path, glass_map=None):
             elif s['model'] is not None:
                 med = M.AbbeGlass(s['model'][0], s['model'][1], label='model')
             else:
-                name = None if g is None else g
-                med = _medium(name, glass_map) if name is None else _zmx_medium(name, glass_map)
+                med = _medium(None, glass_map) if g is None else _zmx_medium(g, glass_map)
             thi = 1e10 if math.isinf(s['thi']) else s['thi']
             gaps.append(M.Gap(thi, med))
             z_dir.append(z)
