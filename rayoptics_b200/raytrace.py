@@ -30,7 +30,7 @@ import numpy as np
 import torch
 
 from . import _abi, engine as E
-from .table import SurfaceTable, describe_path
+from .table import SurfaceTable
 
 try:                                    # the reference's own exception classes, when importable
     from rayoptics.raytr.traceerror import (TraceError, TraceMissedSurfaceError,   # type: ignore

@@ -17,8 +17,6 @@ from __future__ import annotations
 import json
 import math
 
-import numpy as np
-
 from . import model as M
 from .opticalspec import OpticalSpecs, WvlSpec, PupilSpec, FieldSpec, FocusRange
 

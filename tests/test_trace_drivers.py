@@ -218,8 +218,7 @@ def test_batched_aiming_and_apertures(name):
     """aim points: the stored ones of the reference's .roa files (its iterate_ray) where the
     model came from a .roa, the per-ray Newton iteration otherwise; apertures: the per-ray
     version on the same rays"""
-    import copy
-    from rayoptics_b200 import vigcalc as V, raytrace as RT
+    from rayoptics_b200 import vigcalc as V
     opm = load_model(name)
     stored = [None if f.aim_info is None else np.array(f.aim_info, dtype=float)
               for f in opm.optical_spec.field_of_view.fields]
