@@ -173,6 +173,43 @@ def trace(seq_model, pt0, dir0, wvl, **kwargs):
     return trace_raw(path, pt0, dir0, wvl, **kwargs)
 
 
+# --- the module's small host-side helpers, for callers that use them directly
+#     (oprops/doe.py:298,321 calls rt.bend; analyses call calc_optical_path) -------------------
+def bend(d_in, normal, n_in, n_out):
+    """refract incoming direction, d_in, about normal (raytrace.py:19-30)"""
+    from math import sqrt, copysign
+    try:
+        normal_len = np.linalg.norm(normal)
+        cosI = np.dot(d_in, normal)/normal_len
+        sinI_sqr = 1.0 - cosI*cosI
+        n_cosIp = copysign(sqrt(n_out*n_out - n_in*n_in*sinI_sqr), cosI)
+        alpha = n_cosIp - n_in*cosI
+        d_out = (n_in*d_in + alpha*normal)/n_out
+        return d_out
+    except ValueError:
+        raise TraceTIRError(d_in, normal, n_in, n_out)
+
+
+def reflect(d_in, normal):
+    """reflect incoming direction, d_in, about normal (raytrace.py:33-38)"""
+    normal_len = np.linalg.norm(normal)
+    cosI = np.dot(d_in, normal)/normal_len
+    d_out = d_in - 2.0*cosI*normal
+    return d_out
+
+
+def calc_optical_path(ray, path):
+    """optical path between the first and last optical surfaces (raytrace.py:267-293)"""
+    num_items = len(ray)
+    ray_seq_iter = zip(ray, path)
+    next(ray_seq_iter)
+    ray_op = 0
+    for i in range(1, num_items - 2):
+        after_ray_seg, surf = next(ray_seq_iter)
+        ray_op += surf[3]*after_ray_seg[2]
+    return ray_op
+
+
 _saved = {}
 
 

@@ -218,3 +218,33 @@ def test_zmx_reader():
     assert [f.y for f in m.optical_spec.field_of_view.fields] == [0.0, 8.0, 13.6]
     with pytest.raises(KeyError):
         zmx.open_zmx(hits[0], glass_map={})
+
+
+def test_small_raytrace_helpers_match_reference():
+    """bend / reflect / calc_optical_path of rayoptics_b200.raytrace against the reference's"""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip('/root/reference not present')
+    from rayoptics_b200 import raytrace as RT
+    R = rh.ref().raytrace
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        d = rng.standard_normal(3); d /= np.linalg.norm(d)
+        n = rng.standard_normal(3); n /= np.linalg.norm(n)
+        assert np.array_equal(RT.reflect(d, n), R.reflect(d, n))
+        n_in, n_out = rng.uniform(1, 2, 2)
+        try:
+            want = R.bend(d, n, n_in, n_out)
+        except rh.ref().traceerror.TraceTIRError:
+            with pytest.raises(RT.TraceTIRError):
+                RT.bend(d, n, n_in, n_out)
+        else:
+            assert np.array_equal(RT.bend(d, n, n_in, n_out), want)
+    opm = load_model('triplet')
+    sm = opm.seq_model
+    wvl = sm.central_wavelength()
+    r = rh.ref_trace(rh.ref_path(sm, wvl), [0., 1., 0.], [0., 0., 1.], wvl, first_surf=1,
+                     last_surf=sm.get_num_surfaces() - 2)
+    ray = [[s[0:3], s[3:6], s[6], s[7:10]] for s in r['ray']]
+    path = list(sm.path(wvl))
+    assert RT.calc_optical_path(ray, path) == R.calc_optical_path(ray, iter(rh.ref_path(sm, wvl)))
