@@ -208,3 +208,42 @@ def setup_pupil_coords(opt_model, fld, wvl, foc, image_pt=None, image_delta=None
     ref_sphere = W.calculate_reference_sphere(opt_model, fld, wvl, foc, chief_ray_pkg,
                                               image_pt_2d=image_pt, image_delta=image_delta)
     return ref_sphere, chief_ray_pkg
+
+
+def trace_ray(opt_model, pupil, fld, wvl, output_filter=None, rayerr_filter='full', **kwargs):
+    """Trace a single ray via pupil, field and wavelength specs (trace.py:103-157):
+    ``trace_safe`` with named tuples by default."""
+    kwargs.setdefault('use_named_tuples', True)
+    return trace_safe(opt_model, pupil, fld, wvl, output_filter, rayerr_filter, **kwargs)
+
+
+def trace_boundary_rays_at_field(opt_model, fld, wvl, use_named_tuples=False, **kwargs):
+    """list of RayPkgs of the boundary (pupil) rays of field ``fld`` (trace.py:441-458) -- the
+    chief-ray setup plus ONE launch for all pupil rays"""
+    rayerr_filter = kwargs.pop('rayerr_filter', 'full')
+    output_filter = kwargs.pop('output_filter', None)
+    engine = {k: kwargs[k] for k in ('table', 'device', 'tracer') if k in kwargs}
+    ref_sphere, cr_pkg = setup_pupil_coords(opt_model, fld, wvl, 0.0, **engine)
+    fld.chief_ray = cr_pkg
+    fld.ref_sphere = ref_sphere
+    results = trace_pupil_rays(opt_model, opt_model.optical_spec.pupil.pupil_rays, fld, wvl,
+                               output_filter, rayerr_filter, use_named_tuples=use_named_tuples,
+                               **kwargs)
+    return [r.pkg for r in results]
+
+
+def boundary_ray_dict(opt_model, rim_rays):
+    """trace.py:461-465"""
+    labels = getattr(opt_model.optical_spec.pupil, 'ray_labels', ['00', '+X', '-X', '+Y', '-Y'])
+    return dict(zip(labels, rim_rays))
+
+
+def trace_boundary_rays(opt_model, **kwargs):
+    """boundary rays of every field at the central wavelength (trace.py:468-476)"""
+    rayset = []
+    wvl = opt_model.seq_model.central_wavelength()
+    for fld in opt_model.optical_spec.field_of_view.fields:
+        rim_rays = trace_boundary_rays_at_field(opt_model, fld, wvl, **kwargs)
+        fld.pupil_rays = boundary_ray_dict(opt_model, rim_rays)
+        rayset.append(rim_rays)
+    return rayset

@@ -260,3 +260,19 @@ def test_set_vig_grazes_the_limiting_apertures():
             slack = min(ifc.max_aperture - np.hypot(seg[0][0], seg[0][1])
                         for ifc, seg in list(zip(sm.ifcs, res.pkg[0]))[1:-1])
             assert -2e-4 < slack < 2e-3                     # ... and grazes the limiting aperture
+
+
+def test_trace_ray_and_boundary_rays():
+    opm = load_model('triplet')
+    osp = opm.optical_spec
+    fld, wvl = osp.field_of_view.fields[-1], opm.seq_model.central_wavelength()
+    rr = TR.trace_ray(opm, [0., 0.5], fld, wvl, tracer=oracle_tracer)
+    assert rr.err is None and isinstance(rr.pkg, TR.RayPkg) and isinstance(rr.pkg.ray[0], TR.RaySeg)
+    rayset = TR.trace_boundary_rays(opm, tracer=oracle_tracer, use_named_tuples=True)
+    assert len(rayset) == len(osp.field_of_view.fields) and all(len(r) == 5 for r in rayset)
+    assert set(fld.pupil_rays) == {'00', '+X', '-X', '+Y', '-Y'}
+    # the chief ray of the set is the (0, 0) ray setup_pupil_coords traced
+    assert np.array_equal(rayset[-1][0].ray[-1].p, fld.chief_ray[0].ray[-1][0])
+    # the clear apertures of the .roa model are the max heights of exactly these rays
+    hts = [max(np.hypot(r.ray[2].p[0], r.ray[2].p[1]) for rim in rayset for r in rim)]
+    assert hts[0] == pytest.approx(opm.seq_model.ifcs[2].max_aperture, rel=1e-6)
