@@ -384,3 +384,76 @@ def set_vig(opm, **kwargs):
     wvl = osp.spectral_region.central_wvl
     for fld in osp.field_of_view.fields:
         calc_vignetting_for_field(opm, fld, wvl, **kwargs)
+
+
+# --- the reference's own aiming iteration (raytr/trace.py:313-415) ----------------------------
+def iterate_ray(opt_model, ifcx, xy_target, fld, wvl, trace_fn=None):
+    """Iterate a ray to ``xy_target`` on interface ``ifcx``; returns the aim point on the
+    paraxial entrance pupil plane -- ``iterate_ray`` of the reference with the same solvers
+    (scipy ``newton`` in 1-D when field and target have x == 0, else ``fsolve`` with
+    ``epsfcn = 1e-4 enp_radius``) on top of the engine's ``trace``: with the same residual
+    function the iterates are the reference's (tests/test_trace_drivers.py runs the
+    reference's own function text next to this one: identical result).
+
+    Note for infinite conjugates: ``obj_coords`` returns the object point mirrored about the
+    axis with respect to the ``pt0`` that ``ray_start_from_osp`` builds
+    (opticalspec.py:1047-1051 vs :359-366), so the aim point found here has the opposite
+    sign of the one ``ray_start_from_osp`` needs -- the aim points stored in the reference's
+    ``.roa`` files have the consistent sign.  ``aim_chief_ray`` / ``aim_all_fields_batched``
+    above iterate on ``ray_start_from_osp`` itself and reproduce the stored values."""
+    import warnings
+    from scipy.optimize import newton, fsolve
+    from . import raytrace as RT
+    if trace_fn is None:
+        trace_fn = RT.trace
+    seq_model, osp = opt_model.seq_model, opt_model.optical_spec
+    fod = osp.fod
+    obj2enp_dist = fod.obj_dist + fod.enp_dist
+    not_wa = not osp.field_of_view.is_wide_angle
+    pt0, d0 = osp.obj_coords(fld)
+
+    def final_coord(pt1):
+        v = pt1 - pt0
+        dir0 = v/np.linalg.norm(v)
+        if not_wa and dir0[2]*seq_model.z_dir[0] < 0:
+            dir0 = -dir0
+        try:
+            ray = trace_fn(seq_model, pt0, dir0, wvl)[0]
+        except RT.TraceError as ray_error:
+            if ray_error.surf < ifcx:
+                raise ray_error
+            return np.array([0., 0., 0.])
+        return ray[ifcx][0]
+
+    def y_stop_coordinate(y1, y_target):
+        return final_coord(np.array([0., y1, obj2enp_dist]))[1] - y_target
+
+    def surface_coordinate(coord, target):
+        fc = final_coord(np.array([coord[0], coord[1], obj2enp_dist]))
+        return np.array([fc[0], fc[1]]) - target
+
+    if ifcx is None:                       # floating stop: use the entrance pupil for aiming
+        return np.array([0., 0.]) + xy_target
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        if pt0[0] == 0.0 and xy_target[0] == 0.0:
+            try:
+                start_y, results = newton(y_stop_coordinate, 0., args=(xy_target[1],), disp=False,
+                                          full_output=True)
+            except RuntimeError:
+                start_y = 0.0
+            except RT.TraceError:
+                start_y = 0.0
+            return np.array([0., start_y])
+        try:
+            return fsolve(surface_coordinate, np.array([0., 0.]), epsfcn=0.0001*fod.enp_radius,
+                          args=(np.array(xy_target, dtype=float),))
+        except RT.TraceError:
+            return np.array([0., 0.])
+
+
+def aim_chief_ray_like_reference(opt_model, fld, wvl=None, trace_fn=None):
+    """``trace.aim_chief_ray`` (raytr/trace.py:627-640): aim at the centre of the stop surface"""
+    sm = opt_model.seq_model
+    wvl = sm.central_wavelength() if wvl is None else wvl
+    return iterate_ray(opt_model, sm.stop_surface, np.array([0., 0.]), fld, wvl, trace_fn=trace_fn)

@@ -276,3 +276,68 @@ def test_trace_ray_and_boundary_rays():
     # the clear apertures of the .roa model are the max heights of exactly these rays
     hts = [max(np.hypot(r.ray[2].p[0], r.ray[2].p[1]) for rim in rayset for r in rim)]
     assert hts[0] == pytest.approx(opm.seq_model.ifcs[2].max_aperture, rel=1e-6)
+
+
+@needs_ref
+def test_iterate_ray_is_the_references():
+    """vigcalc.iterate_ray against the reference's iterate_ray, whose source text is executed
+    from /root/reference (its module cannot be imported: opticalglass is absent) on the
+    reference's own trace_raw."""
+    import ast
+    import logging
+    import warnings
+    from scipy.optimize import newton, fsolve
+    from oracle import ref_harness as rh
+    from rayoptics_b200 import vigcalc as V
+    R = rh.ref()
+    src = open('/root/reference/src/rayoptics/raytr/trace.py').read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == 'iterate_ray'][0]
+    for name, fi in (('triplet', 1), ('thin_triplet', 1), ('exotic', 2)):
+        opm = load_model(name)
+        sm, osp = opm.seq_model, opm.optical_spec
+        paths = {}
+
+        def ref_trace(seq_model, pt0, dir0, wvl, **kw):
+            if wvl not in paths:
+                paths[wvl] = rh.ref_path(sm, wvl)
+            kw.setdefault('first_surf', 1)
+            kw.setdefault('last_surf', sm.get_num_surfaces() - 2)
+            return R.raytrace.trace_raw(iter(paths[wvl]), np.array(pt0, dtype=float),
+                                        np.array(dir0, dtype=float), wvl, **kw)
+
+        class Osp:
+            def __getitem__(self, k):
+                return {'fov': osp.field_of_view}[k]
+
+            def obj_coords(self, fld):
+                return osp.obj_coords(fld)
+
+        class Opm:
+            def __getitem__(self, k):
+                return {'seq_model': sm, 'optical_spec': Osp(),
+                        'analysis_results': opm.analysis_results}[k]
+
+        ns = dict(np=np, rt=type('rt', (), {'trace': staticmethod(ref_trace)}),
+                  normalize=R.misc_math.normalize, RayPkg=TR.RayPkg, RayResult=TR.RayResult,
+                  TraceError=R.traceerror.TraceError, newton=newton, fsolve=fsolve,
+                  warnings=warnings, logger=logging.getLogger('ref'), mc=type('mc', (), {'p': 0}))
+        exec(ast.get_source_segment(src, fn), ns)
+        fld = osp.field_of_view.fields[fi]
+        wvl = sm.central_wavelength()
+        want, _ = ns['iterate_ray'](Opm(), sm.stop_surface, np.array([0., 0.]), fld, wvl)
+
+        def our_trace(seq_model, pt0, dir0, wvl, **kw):       # engine stand-in: the oracle
+            r = oracle_bundle_tracer(opm, None, np.array(pt0, dtype=float).reshape(3, 1),
+                                     np.array(dir0, dtype=float).reshape(3, 1),
+                                     np.array([sm.index_for_wavelength(wvl)], dtype=np.int32),
+                                     dict(first_surf=1, last_surf=sm.get_num_surfaces() - 2))
+            from rayoptics_b200 import raytrace as RT
+            pkg, err = RT.package_ray(list(sm.path(wvl)), r['full'][:, :, 0], float(r['op'][0]),
+                                      int(r['status'][0]), int(r['fail_surf'][0]),
+                                      int(r['n_seg'][0]), wvl)
+            if err is not None:
+                raise err
+            return pkg
+
+        got = V.iterate_ray(opm, sm.stop_surface, np.array([0., 0.]), fld, wvl, trace_fn=our_trace)
+        assert np.array_equal(got, want), (name, got, want)
