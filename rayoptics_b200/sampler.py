@@ -47,3 +47,39 @@ def csd_grid_ray_generator(grid_rng):
             start[1] += step[1]
         start[0] += step[0]
         start[1] = grid_rng[0][1]
+
+
+def polar_grid_ray_generator(grid_rng):
+    """sampler.py:55-66 -- the same traversal as the square grid (the reference does not map
+    to polar coordinates here either)"""
+    return grid_ray_generator(grid_rng)
+
+
+def phi(d):
+    """generalised golden ratio by the nested radical, sampler.py:73-77"""
+    x = 2.0000
+    for i in range(10):
+        x = pow(1 + x, 1/(d + 1))
+    return x
+
+
+def R_2_quasi_random_generator(n):
+    """2-D R2 low-discrepancy sequence, sampler.py:80-102"""
+    d = 2
+    g = phi(d)
+    alpha = np.zeros(d)
+    for j in range(d):
+        alpha[j] = pow(1/g, j + 1) % 1
+    seed = 0.5
+    z = np.zeros((n, d))
+    for i in range(n):
+        z[i] = (seed + alpha*(i + 1)) % 1
+        yield z[i]
+
+
+def create_generator(sampler, *sampler_args, mapper=None, **kwargs):
+    """sampler.py:125-132 -- chain a sampler with an optional mapping function"""
+    def gen():
+        for xy in sampler(*sampler_args):
+            yield mapper(xy, **kwargs) if mapper else xy
+    return gen()

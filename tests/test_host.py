@@ -248,3 +248,25 @@ def test_small_raytrace_helpers_match_reference():
     ray = [[s[0:3], s[3:6], s[6], s[7:10]] for s in r['ray']]
     path = list(sm.path(wvl))
     assert RT.calc_optical_path(ray, path) == R.calc_optical_path(ray, iter(rh.ref_path(sm, wvl)))
+
+
+def test_samplers_match_reference():
+    """rayoptics_b200/sampler.py against rayoptics.raytr.sampler (importable)"""
+    import importlib
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip('/root/reference not present')
+    rh.ref()
+    RS = importlib.import_module('rayoptics.raytr.sampler')
+    from rayoptics_b200 import sampler as S
+
+    def rng():
+        return [np.array([-1., -0.5]), np.array([1., 0.75]), 11]
+    for name in ('grid_ray_generator', 'csd_grid_ray_generator', 'polar_grid_ray_generator'):
+        a, b = list(getattr(RS, name)(rng())), list(getattr(S, name)(rng()))
+        assert len(a) == len(b) == 121 and all(np.array_equal(x, y) for x, y in zip(a, b))
+    a, b = [z.copy() for z in RS.R_2_quasi_random_generator(50)], [z.copy() for z in S.R_2_quasi_random_generator(50)]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and S.phi(2) == RS.phi(2)
+    a = list(RS.create_generator(RS.R_2_quasi_random_generator, 20, mapper=RS.concentric_sample_disk))
+    b = list(S.create_generator(S.R_2_quasi_random_generator, 20, mapper=S.concentric_sample_disk))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
