@@ -729,6 +729,14 @@ class Field:
                 vig_pupil[1] *= (1.0 - self.vuy)
         return vig_pupil
 
+    def vignetting_bbox(self, pupil_spec, oversize=1.):
+        """bbox of the vignetted pupil ray extents (opticalspec.py:1326-1333)"""
+        poly = [self.apply_vignetting(pup_ray) for pup_ray in pupil_spec.pupil_rays]
+        return oversize*np.array([np.min(poly, axis=0), np.max(poly, axis=0)])
+
+    def clear_vignetting(self):
+        self.vux = self.vuy = self.vlx = self.vly = 0.
+
     def to_dict(self):
         return {'x': self.x, 'y': self.y, 'wt': self.wt, 'vux': self.vux, 'vuy': self.vuy,
                 'vlx': self.vlx, 'vly': self.vly,

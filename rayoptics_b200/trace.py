@@ -118,6 +118,16 @@ def trace_base(opt_model, pupil, fld, wvl, apply_vignetting=True, **kwargs):
     return res.pkg
 
 
+def _as_recorded(fld, pupils, kwargs):
+    """The pupil coordinates the reference hands to ``img_filter`` and stores in its results:
+    ``trace_base`` applies ``Field.apply_vignetting`` to the ndarray IN PLACE
+    (``vig_pupil = pupil[:]`` is a view, opticalspec.py:1339-1353), so what the loops of
+    trace.py:546-559,572-604 record are the VIGNETTED coordinates."""
+    if not kwargs.get('apply_vignetting', True):
+        return pupils
+    return [fld.apply_vignetting(np.array(p)) for p in pupils]
+
+
 def trace_fan(opt_model, fan_rng, fld, wvl, foc, img_filter=None, **kwargs):
     """trace.py:537-560: ``[[pupil, img_filter(pupil, ray_pkg)], ...]`` for the rays that
     yield a package; pupil coordinates are the accumulated ``start += step`` values."""
@@ -132,6 +142,7 @@ def trace_fan(opt_model, fan_rng, fld, wvl, foc, img_filter=None, **kwargs):
         pupils.append(np.array(start))
         start += step
     results = trace_pupil_rays(opt_model, pupils, fld, wvl, output_filter, rayerr_filter, **kwargs)
+    pupils = _as_recorded(fld, pupils, kwargs)
     fan = []
     for pupil, ray_result in zip(pupils, results):
         if ray_result.pkg is not None:
@@ -161,6 +172,7 @@ def trace_grid(opt_model, grid_rng, fld, wvl, foc, img_filter=None, form='grid',
         start[1] = grid_rng[0][1]
     kwargs['check_apertures'] = True
     results = trace_pupil_rays(opt_model, pupils, fld, wvl, output_filter, rayerr_filter, **kwargs)
+    pupils = _as_recorded(fld, pupils, kwargs)
     grid = []
     k = 0
     for i in range(num):

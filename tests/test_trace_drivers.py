@@ -66,9 +66,11 @@ def test_trace_fan_and_grid_against_reference_rays():
     fan_def = [np.array([0., -1.]), np.array([0., 1.]), 9]
     fan = TR.trace_fan(opm, fan_def, fld, wvl, 0.0, tracer=oracle_tracer)
     t = E.accumulated_steps(-1.0, 1.0, 9)
-    assert [f[0][1] for f in fan] == list(t)                  # accumulated pupil values
-    for pupil, pkg in fan:
-        assert_pkg_equals(pkg, ref_pkg(opm, fld, wvl, pupil))
+    # what is recorded are the accumulated pupil values AFTER Field.apply_vignetting (the
+    # reference's trace_base vignettes its ndarray argument in place)
+    assert [f[0][1] for f in fan] == [fld.apply_vignetting(np.array([0., v]))[1] for v in t]
+    for (pupil, pkg), v in zip(fan, t):
+        assert_pkg_equals(pkg, ref_pkg(opm, fld, wvl, [0., v]))
     # grid: check_apertures forced on, failed rays -> None entries, x outer / y inner
     grid_def = [np.array([-1., -1.]), np.array([1., 1.]), 7]
     seen = []
@@ -77,10 +79,12 @@ def test_trace_fan_and_grid_against_reference_rays():
                       append_if_none=False)
     assert len(seen) == 49
     xs = E.accumulated_steps(-1.0, 1.0, 7)
-    assert seen[8][0] == (xs[1], xs[1]) and seen[6][0] == (xs[0], xs[6])
+    vig = lambda a, b: tuple(fld.apply_vignetting(np.array([a, b])))     # noqa: E731
+    assert seen[8][0] == vig(xs[1], xs[1]) and seen[6][0] == vig(xs[0], xs[6])
     n_ok = 0
-    for pupil, pkg in seen:
-        ref = ref_pkg(opm, fld, wvl, pupil, check_apertures=True)
+    raw = [[xs[i], xs[j]] for i in range(7) for j in range(7)]
+    for (pupil, pkg), p_raw in zip(seen, raw):
+        ref = ref_pkg(opm, fld, wvl, p_raw, check_apertures=True)
         assert (pkg is None) == (ref['status'] != 0)
         if pkg is not None:
             n_ok += 1
@@ -119,7 +123,8 @@ def test_sequential_model_drivers_and_ray():
         return ray_pkg[0][-1][0][xy] - fld.ref_sphere[0][xy]
 
     fx, fy, (max_rho, max_y), rc = sm.trace_fan(y_abr, 1, 1, num_rays=11, tracer=oracle_tracer)
-    assert fx.shape == fy.shape == (3, 11) and max_rho == 1.0 and max_y > 0 and len(rc) == 3
+    assert fx.shape == fy.shape == (3, 11) and max_y > 0 and len(rc) == 3
+    assert max_rho == 1.0 - osp.field_of_view.fields[1].vuy          # vignetted pupil coordinates
     assert abs(fy[1, 5]) < 1e-12                    # chief ray of the central wavelength
 
     def opd(p, wi, ray_pkg, fld, wvl, foc):
@@ -341,3 +346,88 @@ def test_iterate_ray_is_the_references():
 
         got = V.iterate_ray(opm, sm.stop_surface, np.array([0., 0.]), fld, wvl, trace_fn=our_trace)
         assert np.array_equal(got, want), (name, got, want)
+
+
+@needs_ref
+@pytest.mark.parametrize('name,fi,wvl', [('dblgauss', 2, 486.1), ('rc', 3, 550.0), ('thin_triplet', 1, 587.6)])
+def test_drivers_against_the_references_drivers(name, fi, wvl):
+    """trace_fan / trace_grid / trace_base / setup_pupil_coords of rayoptics_b200.trace (oracle-fed)
+    against the REFERENCE's own functions of the same names (rayoptics.raytr.trace is importable)
+    running on a hybrid model with the reference's trace_raw (oracle/ref_model.py)."""
+    from oracle import ref_model
+    RT, RA = ref_model.modules()
+    opm = load_model(name)
+    if wvl not in opm.seq_model.wvlns:
+        wvl = opm.seq_model.central_wavelength()
+    H = ref_model.HybridModel(opm)
+    fld = opm.optical_spec.field_of_view.fields[fi]
+
+    def same_pkg(a, b):
+        assert len(a[0]) == len(b[0]) and a[1] == b[1]
+        for sa, sb in zip(a[0], b[0]):
+            assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1])
+            assert sa[2] == sb[2] and np.array_equal(sa[3], sb[3])
+
+    # chief ray + reference sphere
+    rs_ref, cr_ref = RT.setup_pupil_coords(H, fld, wvl, 0.0)
+    rs_own, cr_own = TR.setup_pupil_coords(opm, fld, wvl, 0.0, tracer=oracle_tracer)
+    same_pkg(cr_own[0], cr_ref[0])
+    assert np.array_equal(rs_own[0], rs_ref[0]) and np.array_equal(rs_own[1], rs_ref[1])
+    assert rs_own[2] == rs_ref[2]
+    for a, b in zip(cr_own[1][:3], cr_ref[1][:3]):
+        assert np.array_equal(a, b)
+    # fan with an OPD callback evaluated by the reference's waveabr on both sides
+    import importlib
+    WR = importlib.import_module('rayoptics.raytr.waveabr')
+    fod = opm.optical_spec.fod
+
+    def opd_ref(p, pkg):
+        return WR.wave_abr_full_calc(fod, fld, wvl, 0.0, pkg, cr_ref, rs_ref)
+
+    def opd_own(p, pkg):
+        return W.wave_abr_full_calc(fod, fld, wvl, 0.0, pkg, cr_own, rs_own)
+
+    fan_def = lambda: [np.array([0., -1.]), np.array([0., 1.]), 11]      # noqa: E731
+    f_ref = RT.trace_fan(H, fan_def(), fld, wvl, 0.0, img_filter=opd_ref)
+    f_own = TR.trace_fan(opm, fan_def(), fld, wvl, 0.0, img_filter=opd_own, tracer=oracle_tracer)
+    assert len(f_ref) == len(f_own) > 3
+    for (pa, va), (pb, vb) in zip(f_own, f_ref):
+        assert np.array_equal(pa, pb) and va == vb
+    # grid with a callback (the reference's own np.array(grid) cannot hold raw packages under
+    # numpy >= 1.24); blocked rays reach the callback as None
+    grid_def = lambda: [np.array([-1., -1.]), np.array([1., 1.]), 7]     # noqa: E731
+    seen_ref, seen_own = [], []
+
+    def cb(store):
+        def f(p, pkg):
+            store.append(pkg)
+            return np.array([p[0], p[1], np.nan if pkg is None else pkg[1]])
+        return f
+
+    g_ref = RT.trace_grid(H, grid_def(), fld, wvl, 0.0, form='grid', img_filter=cb(seen_ref))
+    g_own = TR.trace_grid(opm, grid_def(), fld, wvl, 0.0, form='grid', img_filter=cb(seen_own),
+                          tracer=oracle_tracer)
+    assert g_ref.shape == g_own.shape == (7, 7, 3) and np.array_equal(g_ref, g_own, equal_nan=True)
+    assert 0 < np.isnan(g_ref[:, :, 2]).sum() < 49
+    for a, b in zip(seen_own, seen_ref):
+        assert (a is None) == (b is None)
+        if a is not None:
+            same_pkg(a, b)
+    # single ray, error packaging
+    for pupil in ([0.3, -0.2], [0., 1.4]):
+        try:
+            want = RT.trace_base(H, np.array(pupil), fld, wvl, check_apertures=True)
+        except R_TraceError() as e:
+            with pytest.raises(type(TR.trace_pupil_rays(opm, [pupil], fld, wvl, None, 'full',
+                                                        tracer=oracle_tracer,
+                                                        check_apertures=True)[0].err)) as info:
+                TR.trace_base(opm, np.array(pupil), fld, wvl, tracer=oracle_tracer, check_apertures=True)
+            assert type(info.value).__name__ == type(e).__name__ and info.value.surf == e.surf
+        else:
+            same_pkg(TR.trace_base(opm, np.array(pupil), fld, wvl, tracer=oracle_tracer,
+                                   check_apertures=True), want)
+
+
+def R_TraceError():
+    from oracle import ref_harness as rh
+    return rh.ref().traceerror.TraceError

@@ -177,3 +177,36 @@ def test_cuda_batched_aiming():
     V.set_clear_apertures_batched(opm_a)
     V.set_clear_apertures_batched(opm_b, oracle_bundle_fn(opm_b))
     assert [i.max_aperture for i in opm_a.seq_model.ifcs] == [i.max_aperture for i in opm_b.seq_model.ifcs]
+
+
+@pytest.mark.parametrize('name', ['dblgauss', 'rc', 'triplet', 'telecentric', 'cellphone'])
+def test_cuda_analysis_classes_match_the_references(name):
+    """RayFan / RayList / RayGrid against the SAME classes of the reference run on its own
+    trace_raw (tests/golden/vectors/<model>_analyses.npz, generator make_golden_analyses.py):
+    pupil coordinates and transverse aberrations bit for bit; OPD within 1e-12 mm (F**2 is
+    libm pow() in the reference) expressed in waves."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, 'vectors', name + '_analyses.npz'))
+    n_fan, n_list, n_grid = (int(x) for x in z['num'])
+    opm = load_model(name)
+    for ci, (f, wl) in enumerate(z['cases']):
+        f, wl = int(f), (None if wl < 0 else float(wl))
+        wvl = opm.seq_model.central_wavelength() if wl is None else wl
+        tol = 1e-12/opm.nm_to_sys_units(wvl)            # 1e-12 mm in waves
+        for xy in 'xy':
+            fan = A.RayFan(opm, f=f, wl=wl, xyfan=xy, num_rays=n_fan)
+            pup = np.array([p for p, v in fan.fan], dtype=float).reshape(-1, 2)
+            val = np.array([v for p, v in fan.fan], dtype=float).reshape(-1, 3)
+            assert np.array_equal(pup, z[f'fan{xy}_pupil_{ci}'])
+            gold = z[f'fan{xy}_vals_{ci}']
+            assert np.array_equal(val[:, :2], gold[:, :2])
+            assert np.abs(val[:, 2] - gold[:, 2]).max() <= tol
+        rl = A.RayList(opm, num_rays=n_list, f=f, wl=wl)
+        assert np.array_equal(rl.ray_abr, z[f'list_abr_{ci}'])
+        rg = A.RayGrid(opm, f=f, wl=wl, num_rays=n_grid)
+        gold = z[f'grid_{ci}']
+        assert rg.grid.shape == gold.shape
+        assert np.array_equal(rg.grid[0], gold[0]) and np.array_equal(rg.grid[1], gold[1])
+        np.testing.assert_allclose(rg.grid[2], gold[2], rtol=0, atol=tol, equal_nan=True)
+        assert (rg.grid[2][np.isfinite(gold[2])] == gold[2][np.isfinite(gold[2])]).mean() > 0.9
