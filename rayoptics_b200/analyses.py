@@ -185,11 +185,22 @@ def _resolve(opt_model, f, wl, foc):
 
 
 def _trace_pupil_points(opt_model, table, fld, wvl, foc, px, py, paired, apply_vignetting,
-                        check_apertures, image_pt_2d, image_delta, want_opd):
-    """One (field, wvl) tile of pupil points -> host dict(pupil, abr, opd, status)."""
+                        check_apertures, image_pt_2d, image_delta, want_opd, backend=None):
+    """One (field, wvl) tile of pupil points -> host dict(pupil, abr, opd, status).
+    ``backend``: test seam (object with ``chief_rays(opt_model, fields, wvls)`` and
+    ``trace_tile(opt_model, spec, want_opd, check_apertures)``); None = the CUDA engine."""
     osp, sm = opt_model.optical_spec, opt_model.seq_model
-    wave, ref_img, pkgs = W.setup_tiles(opt_model, table, [fld], [wvl], foc, image_pt_2d, image_delta)
+    wave, ref_img, pkgs = W.setup_tiles(opt_model, table, [fld], [wvl], foc, image_pt_2d, image_delta,
+                                        chief_tracer=None if backend is None else backend.chief_rays)
     recs, eprad, z_pupil = osp.grid_fields([fld])
+    if backend is not None:
+        spec = E.PupilGridSpec(recs, [sm.index_for_wavelength(wvl)], px, py, eprad, z_pupil,
+                               ref_img=ref_img, apply_vignetting=apply_vignetting,
+                               flip_z_dir=sm.z_dir[0], foc=foc, paired=paired,
+                               wave=wave if want_opd else None)
+        out = backend.trace_tile(opt_model, spec, want_opd, check_apertures)
+        out.update(ref_sphere=pkgs[0][0][1], chief_ray=pkgs[0][0][0])
+        return out
     grid = E.PupilGrid(recs, [table.wvl_index(wvl)], px, py, eprad, z_pupil, ref_img=ref_img,
                        apply_vignetting=apply_vignetting, flip_z_dir=sm.z_dir[0], foc=foc,
                        paired=paired, wave=wave if want_opd else None, device=table.device)
@@ -267,15 +278,16 @@ class RayFan:
 
     def __init__(self, opt_model, f=0, wl=None, foc=None, image_pt_2d=None, image_delta=None,
                  num_rays=21, xyfan='y', output_filter=None, rayerr_filter=None, color=None,
-                 clip_rays=False, table=None, device=0, **kwargs):
+                 clip_rays=False, table=None, device=0, backend=None, **kwargs):
         self.opt_model = opt_model
+        self._backend = backend
         self.fld, self.wvl, self.foc = _resolve(opt_model, f, wl, foc)
         self.image_pt_2d, self.image_delta = image_pt_2d, image_delta
         self.num_rays = num_rays
         self.xyfan = 0 if xyfan == 'x' else (1 if xyfan == 'y' else int(xyfan))
         self.color = color
         self.clip_rays = clip_rays
-        self._table = _table_for(opt_model, table, device)
+        self._table = None if backend is not None else _table_for(opt_model, table, device)
         self.update_data()
 
     def update_data(self, **kwargs):
@@ -283,7 +295,8 @@ class RayFan:
         zeros = E.accumulated_steps(0.0, 0.0, self.num_rays)
         px, py = (t, zeros) if self.xyfan == 0 else (zeros, t)
         r = _trace_pupil_points(self.opt_model, self._table, self.fld, self.wvl, self.foc, px, py,
-                                True, True, self.clip_rays, self.image_pt_2d, self.image_delta, True)
+                                True, True, self.clip_rays, self.image_pt_2d, self.image_delta, True,
+                                backend=self._backend)
         convert_to_opd = 1/self.opt_model.nm_to_sys_units(self.wvl)
         vx, vy = _vignetted(self.fld, px, py, True)
         self.fan = [((vx[k], vy[k]), (r['abr'][0, k], r['abr'][1, k], convert_to_opd*r['opd'][k]))
@@ -300,8 +313,9 @@ class RayList:
     def __init__(self, opt_model, pupil_gen=None, pupil_coords=None, num_rays=21, f=0, wl=None,
                  foc=None, image_pt_2d=None, image_delta=None, output_filter=None,
                  rayerr_filter=None, clip_rays=False, apply_vignetting=True, table=None, device=0,
-                 **kwargs):
+                 backend=None, **kwargs):
         self.opt_model = opt_model
+        self._backend = backend
         if pupil_coords is not None and pupil_gen is None:
             self.pupil_coords, self.pupil_gen = pupil_coords, None
         else:
@@ -317,7 +331,7 @@ class RayList:
         # trace_pupil_coords defaults check_apertures to True when the key is absent;
         # RayList always passes clip_rays (analyses.py:389,554)
         self.clip_rays = clip_rays
-        self._table = _table_for(opt_model, table, device)
+        self._table = None if backend is not None else _table_for(opt_model, table, device)
         self.update_data()
 
     def update_data(self, **kwargs):
@@ -327,7 +341,7 @@ class RayList:
         pts = np.array([np.array(p, dtype=float) for p in self.pupil_coords]).reshape(-1, 2)
         r = _trace_pupil_points(self.opt_model, self._table, self.fld, self.wvl, self.foc,
                                 pts[:, 0], pts[:, 1], True, self.apply_vignetting, self.clip_rays,
-                                self.image_pt_2d, self.image_delta, False)
+                                self.image_pt_2d, self.image_delta, False, backend=self._backend)
         ok = r['status'] == 0
         self.ray_abr = r['abr'][:, ok]
         self.pupil = pts[ok].T
@@ -341,13 +355,14 @@ class RayGrid:
 
     def __init__(self, opt_model, f=0, wl=None, foc=None, image_pt_2d=None, image_delta=None,
                  output_filter=None, rayerr_filter=None, num_rays=21, clip_rays=True,
-                 value_if_none=np.nan, oversize=1., table=None, device=0, **kwargs):
+                 value_if_none=np.nan, oversize=1., table=None, device=0, backend=None, **kwargs):
         self.opt_model = opt_model
+        self._backend = backend
         self.fld, self.wvl, self.foc = _resolve(opt_model, f, wl, foc)
         self.image_pt_2d, self.image_delta = image_pt_2d, image_delta
         self.num_rays, self.value_if_none, self.oversize = num_rays, value_if_none, oversize
         self.clip_rays = clip_rays
-        self._table = _table_for(opt_model, table, device)
+        self._table = None if backend is not None else _table_for(opt_model, table, device)
         self.update_data()
 
     def vignetting_bbox(self):
@@ -363,7 +378,8 @@ class RayGrid:
         py = E.accumulated_steps(bbox[0][1], bbox[1][1], n)
         # trace_ray_grid: apply_vignetting defaults to False (analyses.py:674)
         r = _trace_pupil_points(self.opt_model, self._table, self.fld, self.wvl, self.foc, px, py,
-                                False, False, self.clip_rays, self.image_pt_2d, self.image_delta, True)
+                                False, False, self.clip_rays, self.image_pt_2d, self.image_delta, True,
+                                backend=self._backend)
         convert_to_opd = 1/self.opt_model.nm_to_sys_units(self.wvl)
         opd = np.where(r['status'] == 0, convert_to_opd*r['opd'], self.value_if_none).reshape(n, n)
         gx, gy = np.meshgrid(px, py, indexing='ij')

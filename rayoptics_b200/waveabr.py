@@ -132,14 +132,16 @@ def wave_record(opt_model, chief_ray_pkg_, ref_sphere):
 
 
 def setup_tiles(opt_model, table, fields, wvls, foc, image_pt_2d=None, image_delta=None,
-                ref_wvl_for_image_pt=None):
+                ref_wvl_for_image_pt=None, chief_tracer=None):
     """Chief rays + reference spheres of all tiles.
 
     Returns ``(wave [n_f, n_w, 24], ref_img [n_f, n_w, 2], pkgs)`` where
     ``pkgs[f][w] = (chief_ray_pkg, ref_sphere)``.  ``ref_wvl_for_image_pt``: use
     the image point of that wavelength's chief ray for every wavelength (what
     ``SequentialModel.trace_fan/trace_grid`` do, seq/sequential.py:1015-1040)."""
-    full, op, status = trace_chief_rays(opt_model, table, fields, wvls)
+    # chief_tracer: test seam (the CPU suite feeds the oracle), same role as trace.py's tracer=
+    full, op, status = (trace_chief_rays(opt_model, table, fields, wvls) if chief_tracer is None
+                        else chief_tracer(opt_model, fields, wvls))
     if (status != 0).any():
         raise RuntimeError('a chief ray did not reach the image')
     nf, nw = len(fields), len(wvls)

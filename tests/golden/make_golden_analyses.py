@@ -4,6 +4,16 @@ own analysis classes (build container only): rayoptics.raytr.analyses.RayFan / R
 (/root/reference/src/rayoptics/raytr/analyses.py:121-187,343-434,584-663) run on a hybrid model
 (oracle/ref_model.py) with the reference's trace_raw.
 
+The reference's chief-ray RE-AIMING is bypassed: `get_chief_ray_pkg` (raytr/trace.py:660-687) calls
+`aim_chief_ray` whenever `fld.chief_ray is None`, and at this commit `iterate_ray` starts from the
+object point of `obj_coords`, which for infinite conjugates is the mirror image of the point
+`ray_start_from_osp` launches from -- the aim point comes back with the wrong sign and the chief
+ray misses the stop centre (dblgauss 10 deg: +0.1522 instead of -0.1522, 0.19 mm off; shown by
+tests/test_trace_drivers.py::test_iterate_ray_is_the_references and DESIGN.md).  The fixtures'
+aim points (chief ray through the stop centre, as stored in the reference's .roa files) are kept
+by giving every field a placeholder `chief_ray` of another wavelength, which makes
+`get_chief_ray_pkg` re-trace the chief ray without re-aiming.
+
 Per model and (field, wavelength) case: the y- and x-fan (pupil coordinates, dx, dy, OPD in
 waves), the default ray list (transverse aberrations of the rays that reach the image) and the
 wavefront grid [3, n, n].
@@ -34,12 +44,22 @@ def main():
         out = {'cases': np.array([[f, -1.0 if w is None else w] for f, w in CASES[name]]),
                'num': np.array([NUM_FAN, NUM_LIST, NUM_GRID])}
         for ci, (f, wl) in enumerate(CASES[name]):
+            fld = opm.optical_spec.field_of_view.fields[f]
+            aim = None if fld.aim_info is None else np.array(fld.aim_info)
+
+            def keep_aim():
+                fld.aim_info = None if aim is None else aim.copy()
+                fld.chief_ray = ((None, None, -1.0), None)     # != wvl: re-trace, do not re-aim
+
             for xy in 'xy':
+                keep_aim()
                 fan = RA.RayFan(H, f=f, wl=wl, xyfan=xy, num_rays=NUM_FAN)
                 out[f'fan{xy}_pupil_{ci}'] = np.array([p for p, v in fan.fan], dtype=float).reshape(-1, 2)
                 out[f'fan{xy}_vals_{ci}'] = np.array([v for p, v in fan.fan], dtype=float).reshape(-1, 3)
+            keep_aim()
             rl = RA.RayList(H, num_rays=NUM_LIST, f=f, wl=wl)
             out[f'list_abr_{ci}'] = np.array(rl.ray_abr, dtype=float)
+            keep_aim()
             rg = RA.RayGrid(H, f=f, wl=wl, num_rays=NUM_GRID)
             out[f'grid_{ci}'] = np.array(rg.grid, dtype=float)
         np.savez_compressed(os.path.join(OUT, name + '_analyses.npz'), **out)
