@@ -729,6 +729,31 @@ class Field:
                 vig_pupil[1] *= (1.0 - self.vuy)
         return vig_pupil
 
+    # value / fractional access (opticalspec.py:1182-1222); `fov` is set by FieldSpec
+    fov = None
+
+    def _rel(self, v):
+        fov = self.fov
+        if fov is None or fov.is_relative:
+            return v
+        return v/fov.value if fov.value != 0 else 0.0
+
+    @property
+    def xf(self):
+        return self._rel(self.x)
+
+    @property
+    def yf(self):
+        return self._rel(self.y)
+
+    @property
+    def xv(self):
+        return self.x*self.fov.value if (self.fov is not None and self.fov.is_relative) else self.x
+
+    @property
+    def yv(self):
+        return self.y*self.fov.value if (self.fov is not None and self.fov.is_relative) else self.y
+
     def vignetting_bbox(self, pupil_spec, oversize=1.):
         """bbox of the vignetted pupil ray extents (opticalspec.py:1326-1333)"""
         poly = [self.apply_vignetting(pup_ray) for pup_ray in pupil_spec.pupil_rays]

@@ -42,11 +42,13 @@ class WvlSpec:
 class PupilSpec:
     """key = (object|image, epd|f/#|NA); opticalspec.py:626-760"""
     default_pupil_rays = [[0., 0.], [1., 0.], [-1., 0.], [0., 1.], [0., -1.]]
+    default_ray_labels = ['00', '+X', '-X', '+Y', '-Y']
 
     def __init__(self, key=('object', 'epd'), value=1.0):
         self.key = tuple(key[-2:])
         self.value = value
         self.pupil_rays = [list(r) for r in self.default_pupil_rays]
+        self.ray_labels = list(self.default_ray_labels)
 
 
 class FieldSpec:
@@ -59,6 +61,8 @@ class FieldSpec:
         self.is_relative = is_relative
         self.is_wide_angle = is_wide_angle
         self.fields = list(fields) if fields else [Field()]
+        for f in self.fields:
+            f.fov = self
 
     def max_field_value(self):
         if self.is_relative:
@@ -110,6 +114,12 @@ class OpticalSpecs:
 
     def obj_img_rindex(self):
         return self.fod.n_obj, self.fod.n_img
+
+    def lookup_fld_wvl_focus(self, fi, wl=None, fr=0.0):
+        """field, wavelength (nm) and focus shift for the indices (opticalspec.py:403-427)"""
+        wvl = (self.spectral_region.central_wvl if wl is None
+               else self.spectral_region.wavelengths[wl])
+        return self.field_of_view.fields[fi], wvl, self.defocus.get_focus(fr)
 
     def conjugate_type(self, space='object'):
         sm = self.opt_model.seq_model

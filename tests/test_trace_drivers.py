@@ -431,3 +431,36 @@ def test_drivers_against_the_references_drivers(name, fi, wvl):
 def R_TraceError():
     from oracle import ref_harness as rh
     return rh.ref().traceerror.TraceError
+
+
+@needs_ref
+@pytest.mark.parametrize('name', ['dblgauss', 'triplet'])
+def test_set_vig_and_apertures_equal_the_references(name):
+    """vigcalc.set_clear_apertures_batched and vigcalc.set_vig against the reference's
+    rayoptics.raytr.vigcalc run unmodified on the hybrid model (reference trace_raw, scipy
+    newton): apertures and vignetting factors bit for bit.  The reference's re-aiming is
+    bypassed as in make_golden_analyses.py (placeholder chief_ray)."""
+    import importlib
+    from oracle import ref_model
+    from rayoptics_b200 import vigcalc as V
+    ref_model.modules()
+    RV = importlib.import_module('rayoptics.raytr.vigcalc')
+    a, b = load_model(name), load_model(name)
+    H = ref_model.HybridModel(a)
+    for f in a.optical_spec.field_of_view.fields:
+        f.chief_ray = ((None, None, -1.0), None)
+    RV.set_clear_apertures(H)
+    V.set_clear_apertures_batched(b, oracle_bundle_fn(b))
+    ref_ap = [ifc.max_aperture for ifc in H.seq_model.ifcs]
+    own_ap = [ifc.max_aperture for ifc in b.seq_model.ifcs]
+    assert ref_ap[1:] == own_ap[1:]
+    # vignetting from those apertures (both sides start from zero vignetting)
+    for m in (a, b):
+        for f in m.optical_spec.field_of_view.fields:
+            f.vux = f.vlx = f.vuy = f.vly = 0.0
+    for f in a.optical_spec.field_of_view.fields:
+        f.chief_ray = ((None, None, -1.0), None)
+    RV.set_vig(H)
+    V.set_vig(b, tracer=oracle_tracer)
+    for fa, fb in zip(a.optical_spec.field_of_view.fields, b.optical_spec.field_of_view.fields):
+        assert (fa.vux, fa.vlx, fa.vuy, fa.vly) == (fb.vux, fb.vlx, fb.vuy, fb.vly)
