@@ -458,15 +458,20 @@ def psf_sampling(n=None, n_pupil=None, n_airy=None):
     return n, n_pupil, n_airy
 
 
-def calc_psf_scaling(opt_model, ref_sphere_radius, wvl, ndim, maxdim, exp_radius):
-    """Input / output grid spacings of the FFT PSF (analyses.py:818-845)."""
-    fod = opt_model.optical_spec.fod
+def calc_psf_scaling(opt_model, fld, wvl, ndim, maxdim):
+    """Input / output grid spacings of the FFT PSF (analyses.py:818-845): ``(delta_x, delta_xp)``,
+    the linear grid spacing on the entrance pupil and on the image plane.  ``fld.ref_sphere``
+    must be set (the analysis classes / ``trace.setup_pupil_coords`` do)."""
+    fod = opt_model['analysis_results']['parax_data'].fod
     wl = opt_model.nm_to_sys_units(wvl)
     fill_factor = ndim/maxdim
     max_D = 2*fod.enp_radius/fill_factor
     delta_x = max_D/maxdim
-    delta_theta = (fill_factor*(wl/exp_radius))/2
-    return delta_x, delta_theta*ref_sphere_radius
+    C = wl/fod.exp_radius
+    delta_theta = (fill_factor*C)/2
+    ref_sphere_radius = fld.ref_sphere[2]
+    delta_xp = delta_theta*ref_sphere_radius
+    return delta_x, delta_xp
 
 
 def calc_psf(wavefront, ndim, maxdim, device=0):

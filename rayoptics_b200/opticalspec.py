@@ -11,6 +11,7 @@ Mirrors what the hot path's callers read from the reference's
 """
 from __future__ import annotations
 
+import collections
 import math
 
 import numpy as np
@@ -106,7 +107,7 @@ class OpticalSpecs:
     def update_model(self, **kwargs):
         sm = self.opt_model.seq_model
         fod = compute_first_order(sm, self, self.spectral_region.central_wvl)
-        self.opt_model.analysis_results['parax_data'] = _ParaxData(fod)
+        self.opt_model.analysis_results['parax_data'] = ParaxData(fod.ax_ray, fod.pr_ray, fod)
 
     @property
     def fod(self):
@@ -286,6 +287,5 @@ class OpticalSpecs:
                    FocusRange(d.get('focus_shift', 0.0)))
 
 
-class _ParaxData:
-    def __init__(self, fod):
-        self.fod = fod
+# parax/firstorder.py:29: ParaxData = namedtuple('ParaxData', ['ax_ray', 'pr_ray', 'fod'])
+ParaxData = collections.namedtuple('ParaxData', ['ax_ray', 'pr_ray', 'fod'])

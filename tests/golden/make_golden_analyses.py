@@ -34,6 +34,7 @@ OUT = os.path.join(HERE, 'vectors')
 CASES = {'dblgauss': [(0, 587.6), (1, 656.3), (2, 486.1)], 'rc': [(0, 550.0), (3, 550.0)],
          'triplet': [(1, None)], 'telecentric': [(0, 587.6), (2, 486.1)], 'cellphone': [(4, None)]}
 NUM_FAN, NUM_LIST, NUM_GRID = 21, 15, 16
+PSF_DIM = 64
 
 
 def main():
@@ -42,7 +43,7 @@ def main():
         opm = M.OpticalModel.load(os.path.join(HERE, 'models', name + '.json'))
         H = ref_model.HybridModel(opm)
         out = {'cases': np.array([[f, -1.0 if w is None else w] for f, w in CASES[name]]),
-               'num': np.array([NUM_FAN, NUM_LIST, NUM_GRID])}
+               'num': np.array([NUM_FAN, NUM_LIST, NUM_GRID]), 'psf_dim': np.array(PSF_DIM)}
         for ci, (f, wl) in enumerate(CASES[name]):
             fld = opm.optical_spec.field_of_view.fields[f]
             aim = None if fld.aim_info is None else np.array(fld.aim_info)
@@ -62,6 +63,7 @@ def main():
             keep_aim()
             rg = RA.RayGrid(H, f=f, wl=wl, num_rays=NUM_GRID)
             out[f'grid_{ci}'] = np.array(rg.grid, dtype=float)
+            out[f'psf_{ci}'] = RA.calc_psf(rg.grid[2], NUM_GRID, PSF_DIM)     # analyses.py:848-875
         np.savez_compressed(os.path.join(OUT, name + '_analyses.npz'), **out)
         print(f'{name:12s} cases={len(CASES[name])} fan rays={out["fany_vals_0"].shape[0]} '
               f'list rays={out["list_abr_0"].shape[1]} grid ok={np.isfinite(out["grid_0"][2]).sum()}')

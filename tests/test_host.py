@@ -270,3 +270,19 @@ def test_samplers_match_reference():
     a = list(RS.create_generator(RS.R_2_quasi_random_generator, 20, mapper=RS.concentric_sample_disk))
     b = list(S.create_generator(S.R_2_quasi_random_generator, 20, mapper=S.concentric_sample_disk))
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_psf_helpers_match_reference():
+    """psf_sampling / calc_psf_scaling against rayoptics.raytr.analyses (importable)"""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip('/root/reference not present')
+    from oracle import ref_model
+    from rayoptics_b200 import analyses as A
+    RT, RA = ref_model.modules()
+    for args in ((None, 32, 8), (128, None, 8), (128, 32, None)):
+        assert A.psf_sampling(*args) == RA.psf_sampling(*args)
+    opm = load_model('dblgauss')
+    fld = opm.optical_spec.field_of_view.fields[1]
+    fld.ref_sphere = (np.zeros(3), np.array([0., 0., 1.]), 123.456, None)
+    assert A.calc_psf_scaling(opm, fld, 587.6, 32, 128) == RA.calc_psf_scaling(opm, fld, 587.6, 32, 128)

@@ -210,3 +210,16 @@ def test_cuda_analysis_classes_match_the_references(name):
         assert np.array_equal(rg.grid[0], gold[0]) and np.array_equal(rg.grid[1], gold[1])
         np.testing.assert_allclose(rg.grid[2], gold[2], rtol=0, atol=tol, equal_nan=True)
         assert (rg.grid[2][np.isfinite(gold[2])] == gold[2][np.isfinite(gold[2])]).mean() > 0.9
+
+
+@pytest.mark.parametrize('name', ['dblgauss', 'telecentric'])
+def test_cuda_psf_matches_the_references(name):
+    """calc_psf (torch.fft on the device) on the reference's own wavefront grid against the
+    reference's calc_psf (numpy fft): library transforms, 1e-12 of the normalised peak"""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, 'vectors', name + '_analyses.npz'))
+    n_grid, dim = int(z['num'][2]), int(z['psf_dim'])
+    for ci in range(len(z['cases'])):
+        got = A.calc_psf(z[f'grid_{ci}'][2], n_grid, dim)
+        np.testing.assert_allclose(got, z[f'psf_{ci}'], rtol=0, atol=1e-12)
