@@ -22,6 +22,7 @@ import torch
 
 from . import engine as E
 from .table import SurfaceTable
+from .opticalspec import grid_fields_of
 
 
 class SpotDiagram:
@@ -89,7 +90,7 @@ def chief_ray_image_points(opt_model, table, fields, wvl=None, foc=0.0, io=None)
     raytr/waveabr.py:24-76 for ``image_pt_2d=None``."""
     osp, sm = opt_model.optical_spec, opt_model.seq_model
     wvl = sm.central_wavelength() if wvl is None else wvl
-    recs, eprad, z_pupil = osp.grid_fields(fields)
+    recs, eprad, z_pupil = grid_fields_of(opt_model, fields)
     g0 = E.PupilGrid(recs, [table.wvl_index(wvl)], [0.0], [0.0], eprad, z_pupil,
                      apply_vignetting=False, flip_z_dir=sm.z_dir[0], foc=foc, device=table.device)
     r0 = E.trace_grid(table, g0, outputs=('p',), summary=False, check_apertures=False)
@@ -192,7 +193,7 @@ def _trace_pupil_points(opt_model, table, fld, wvl, foc, px, py, paired, apply_v
     osp, sm = opt_model.optical_spec, opt_model.seq_model
     wave, ref_img, pkgs = W.setup_tiles(opt_model, table, [fld], [wvl], foc, image_pt_2d, image_delta,
                                         chief_tracer=None if backend is None else backend.chief_rays)
-    recs, eprad, z_pupil = osp.grid_fields([fld])
+    recs, eprad, z_pupil = grid_fields_of(opt_model, [fld])
     if backend is not None:
         spec = E.PupilGridSpec(recs, [sm.index_for_wavelength(wvl)], px, py, eprad, z_pupil,
                                ref_img=ref_img, apply_vignetting=apply_vignetting,

@@ -172,22 +172,9 @@ class OpticalSpecs:
 
     # -------------------------------------------------- single start ray
     def _epd_pupil(self):
-        """(pupil_value_key, pupil_value) after the image-space substitution of
+        """(pupil_oi_key, pupil_value_key, pupil_value) after the image-space substitution of
         opticalspec.py:311-325"""
-        pupil_oi_key, pupil_value_key = self.pupil.key
-        pupil_value = self.pupil.value
-        fod = self.fod
-        if pupil_oi_key == 'image':
-            if abs(fod.m) < 1e-10:
-                pupil_value_key, pupil_value = 'epd', 2*fod.enp_radius
-            elif abs(fod.enp_dist) > 1e10:      # telecentric entrance pupil
-                pupil_value_key = 'NA'
-                n_obj = self.obj_img_rindex()[0]
-                slp0 = fod.obj_na/n_obj                                  # etendue.na2slp_parax
-                pupil_value = n_obj*math.sin(math.atan(slp0/n_obj))      # etendue.slp2na
-            else:
-                pupil_value_key, pupil_value = 'epd', 2*fod.enp_radius
-        return pupil_oi_key, pupil_value_key, pupil_value
+        return effective_pupil(self.opt_model)
 
     def ray_start_from_osp(self, pupil, fld, pupil_type='rel pupil'):
         """(pt0, dir0) for one ray, opticalspec.py:289-400 (non wide-angle)."""
@@ -231,41 +218,8 @@ class OpticalSpecs:
 
     # ------------------------------------------------- grid field records
     def grid_fields(self, fields=None):
-        """Per-field constants of the start-ray generation for the grid kernels: list of
-        dicts (pt0, aim, vlx, vux, vly, vuy, pupil_kind) plus (scale, z_pupil).
-
-        'epd' pupils (``rt_pupil_kind`` 0): pt0 = the ray origin in the object plane, aim =
-        aim point, scale = entrance pupil radius.  Angular pupils ('NA' 1, 'f/#' 2;
-        opticalspec.py:368-398): pt0 = object point, aim = chief-ray direction cosines
-        ``d0[:2]``, scale = NA/n or -1/(2 f/#)."""
-        pupil_oi_key, pupil_value_key, pupil_value = self._epd_pupil()
-        if self.field_of_view.is_wide_angle:
-            raise NotImplementedError('wide-angle start rays are not generated on the device')
-        fod = self.fod
-        z_pupil = fod.obj_dist + fod.enp_dist
-        flds = fields if fields is not None else self.field_of_view.fields
-        out = []
-        if pupil_value_key == 'epd':
-            kind, scale = 0, pupil_value/2
-            obj2enp_dist = -(fod.obj_dist + fod.enp_dist)
-            for fld in flds:
-                p0, d0 = self.obj_coords(fld)
-                pt0 = obj2enp_dist*np.array([d0[0]/d0[2], d0[1]/d0[2], 0.])
-                aim = [0., 0.] if getattr(fld, 'aim_info', None) is None else fld.aim_info
-                out.append({'pt0': pt0, 'aim': [float(aim[0]), float(aim[1])]})
-        else:
-            n_obj, n_img = self.obj_img_rindex()
-            if 'NA' in pupil_value_key:
-                n = n_obj if pupil_oi_key == 'object' else n_img
-                kind, scale = 1, pupil_value/n
-            else:
-                kind, scale = 2, -1/(2*pupil_value)
-            for fld in flds:
-                p0, d0 = self.obj_coords(fld)
-                out.append({'pt0': p0, 'aim': [float(d0[0]), float(d0[1])]})
-        for rec, fld in zip(out, flds):
-            rec.update(vlx=fld.vlx, vux=fld.vux, vly=fld.vly, vuy=fld.vuy, pupil_kind=kind)
-        return out, scale, z_pupil
+        """see ``grid_fields_of``"""
+        return grid_fields_of(self.opt_model, fields)
 
     # ------------------------------------------------------- persistence
     def to_dict(self):
@@ -285,6 +239,68 @@ class OpticalSpecs:
                    PupilSpec(d['pupil']['key'], d['pupil']['value']),
                    FieldSpec(fov['key'], fov['value'], fields, fov.get('is_relative', False)),
                    FocusRange(d.get('focus_shift', 0.0)))
+
+
+# --- the same derivations on ANY optical model that follows the reference's interface
+#     (the reference's own OpticalModel or the mirror): used by the batched drivers when they
+#     are installed inside the reference (raytrace.install(batched=True)) --------------------
+def effective_pupil(opt_model):
+    """(pupil_oi_key, pupil_value_key, pupil_value) after the image-space substitution of
+    ``ray_start_from_osp`` (opticalspec.py:311-325)"""
+    osp = opt_model['optical_spec']
+    fod = opt_model['analysis_results']['parax_data'].fod
+    pupil_oi_key, pupil_value_key = osp['pupil'].key
+    pupil_value = osp['pupil'].value
+    if pupil_oi_key == 'image':
+        if abs(fod.m) < 1e-10:
+            pupil_value_key, pupil_value = 'epd', 2*fod.enp_radius
+        elif abs(fod.enp_dist) > 1e10:      # telecentric entrance pupil
+            pupil_value_key = 'NA'
+            n_obj = osp.obj_img_rindex()[0]
+            slp0 = fod.obj_na/n_obj                                  # etendue.na2slp_parax
+            pupil_value = n_obj*math.sin(math.atan(slp0/n_obj))      # etendue.slp2na
+        else:
+            pupil_value_key, pupil_value = 'epd', 2*fod.enp_radius
+    return pupil_oi_key, pupil_value_key, pupil_value
+
+
+def grid_fields_of(opt_model, fields=None):
+    """Per-field constants of the start-ray generation for the grid kernels: list of dicts
+    (pt0, aim, vlx, vux, vly, vuy, pupil_kind) plus (scale, z_pupil).
+
+    'epd' pupils (``rt_pupil_kind`` 0): pt0 = the ray origin in the object plane, aim = aim
+    point, scale = entrance pupil radius.  Angular pupils ('NA' 1, 'f/#' 2;
+    opticalspec.py:368-398): pt0 = object point, aim = chief-ray direction cosines ``d0[:2]``,
+    scale = NA/n or -1/(2 f/#)."""
+    osp = opt_model['optical_spec']
+    fod = opt_model['analysis_results']['parax_data'].fod
+    pupil_oi_key, pupil_value_key, pupil_value = effective_pupil(opt_model)
+    if osp['fov'].is_wide_angle:
+        raise NotImplementedError('wide-angle start rays are not generated on the device')
+    z_pupil = fod.obj_dist + fod.enp_dist
+    flds = fields if fields is not None else osp['fov'].fields
+    out = []
+    if pupil_value_key == 'epd':
+        kind, scale = 0, pupil_value/2
+        obj2enp_dist = -(fod.obj_dist + fod.enp_dist)
+        for fld in flds:
+            p0, d0 = osp.obj_coords(fld)
+            pt0 = obj2enp_dist*np.array([d0[0]/d0[2], d0[1]/d0[2], 0.])
+            aim = [0., 0.] if getattr(fld, 'aim_info', None) is None else fld.aim_info
+            out.append({'pt0': pt0, 'aim': [float(aim[0]), float(aim[1])]})
+    else:
+        n_obj, n_img = osp.obj_img_rindex()
+        if 'NA' in pupil_value_key:
+            n = n_obj if pupil_oi_key == 'object' else n_img
+            kind, scale = 1, pupil_value/n
+        else:
+            kind, scale = 2, -1/(2*pupil_value)
+        for fld in flds:
+            p0, d0 = osp.obj_coords(fld)
+            out.append({'pt0': p0, 'aim': [float(d0[0]), float(d0[1])]})
+    for rec, fld in zip(out, flds):
+        rec.update(vlx=fld.vlx, vux=fld.vux, vly=fld.vly, vuy=fld.vuy, pupil_kind=kind)
+    return out, scale, z_pupil
 
 
 # parax/firstorder.py:29: ParaxData = namedtuple('ParaxData', ['ax_ray', 'pr_ray', 'fod'])

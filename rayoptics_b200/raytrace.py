@@ -213,16 +213,53 @@ def calc_optical_path(ray, path):
 _saved = {}
 
 
-def install():
-    """Rebind the reference's ``rayoptics.raytr.raytrace.trace/trace_raw``."""
+def install(batched=False):
+    """Rebind the reference's ``rayoptics.raytr.raytrace.trace/trace_raw`` to the engine.
+
+    ``batched=True`` additionally rebinds the per-ray LOOPS of the reference to the batched
+    drivers of ``rayoptics_b200.trace`` -- ``rayoptics.raytr.trace.trace_fan / trace_grid`` and
+    ``rayoptics.raytr.analyses.trace_ray_fan / trace_ray_list / trace_ray_grid`` -- so that the
+    reference's own ``RayFan`` / ``RayList`` / ``RayGrid`` / ``SequentialModel.trace_fan`` ...
+    trace each (field, wavelength) in one launch.  Same arguments and results (checked
+    against the unpatched reference in tests/test_dropin_batched.py); wide-angle fields and
+    ``pupil_type`` other than 'rel pupil' keep the reference's loop on the drop-in ``trace``."""
     import rayoptics.raytr.raytrace as rt      # type: ignore
     if 'trace' not in _saved:
         _saved['trace'], _saved['trace_raw'] = rt.trace, rt.trace_raw
     rt.trace, rt.trace_raw = trace, trace_raw
+    if batched:
+        import rayoptics.raytr.trace as rtr        # type: ignore
+        import rayoptics.raytr.analyses as ran     # type: ignore
+        from . import trace as TR
+        pairs = [(rtr, 'trace_fan', TR.trace_fan), (rtr, 'trace_grid', TR.trace_grid),
+                 (ran, 'trace_ray_fan', TR.analyses_trace_ray_fan),
+                 (ran, 'trace_ray_list', TR.analyses_trace_ray_list),
+                 (ran, 'trace_ray_grid', TR.analyses_trace_ray_grid)]
+        for mod, name, fn in pairs:
+            key = (mod.__name__, name)
+            if key not in _saved:
+                _saved[key] = getattr(mod, name)
+            setattr(mod, name, _batched_or_original(fn, _saved[key]))
     return rt
+
+
+def _batched_or_original(batched_fn, original_fn):
+    """the batched driver where it applies, the reference's own loop otherwise"""
+    import functools
+
+    @functools.wraps(original_fn)
+    def wrapper(opt_model, *args, **kwargs):
+        wide = opt_model['optical_spec']['fov'].is_wide_angle
+        if wide or kwargs.get('pupil_type', 'rel pupil') != 'rel pupil':
+            return original_fn(opt_model, *args, **kwargs)
+        return batched_fn(opt_model, *args, **kwargs)
+    return wrapper
 
 
 def uninstall():
     if _saved:
+        import importlib
         import rayoptics.raytr.raytrace as rt  # type: ignore
         rt.trace, rt.trace_raw = _saved.pop('trace'), _saved.pop('trace_raw')
+        for key in [k for k in _saved if isinstance(k, tuple)]:
+            setattr(importlib.import_module(key[0]), key[1], _saved.pop(key))

@@ -23,6 +23,7 @@ import numpy as np
 
 from . import engine as E
 from . import waveabr as W
+from .opticalspec import grid_fields_of
 
 RayResult = namedtuple('RayResult', ['pkg', 'err'])
 RayPkg = namedtuple('RayPkg', ['ray', 'op', 'wvl'])
@@ -42,7 +43,7 @@ def cuda_tracer(opt_model, table, fld, wvl, px, py, apply_vignetting, trace_kwar
     one paired-grid launch.  Returns host arrays ``full [n_ifc, 10, n]``, ``op``,
     ``status``, ``fail_surf``, ``n_seg``."""
     osp, sm = opt_model.optical_spec, opt_model.seq_model
-    recs, eprad, z_pupil = osp.grid_fields([fld])
+    recs, eprad, z_pupil = grid_fields_of(opt_model, [fld])
     grid = E.PupilGrid(recs, [table.wvl_index(wvl)], px, py, eprad, z_pupil,
                        apply_vignetting=apply_vignetting, flip_z_dir=sm.z_dir[0], paired=True,
                        device=table.device)
@@ -207,7 +208,7 @@ def trace_chief_ray(opt_model, fld, wvl, foc, table=None, device=0, tracer=None)
     if res.err is not None:
         raise res.err
     cr = RayPkg(*res.pkg)
-    fod = opt_model.optical_spec.fod
+    fod = opt_model['analysis_results']['parax_data'].fod
     cr_exp_seg = W.transfer_to_exit_pupil((cr.ray[-2][0], cr.ray[-2][1]), fod.exp_dist)
     return cr, cr_exp_seg
 
@@ -259,3 +260,79 @@ def trace_boundary_rays(opt_model, **kwargs):
         fld.pupil_rays = boundary_ray_dict(opt_model, rim_rays)
         rayset.append(rim_rays)
     return rayset
+
+
+# --- batched stand-ins for the per-ray loops of rayoptics.raytr.analyses ------------------------
+# (trace_ray_fan :212-230, trace_ray_list :437-455, trace_ray_grid :666-696): same arguments, same
+# nested lists of [pupil_x, pupil_y, ray_pkg] out.  raytrace.install(batched=True) rebinds the
+# reference's functions to these, so its RayFan / RayList / RayGrid classes trace each (field,
+# wavelength) with one launch.
+def _vignette_like_reference(fld, pupils, kwargs):
+    """trace_base vignettes ndarray pupils IN PLACE (``vig_pupil = pupil[:]`` is a view; a list
+    is copied): do the same to the caller's objects and return the coordinates the
+    reference's loops then record"""
+    if kwargs.get('apply_vignetting', True):
+        for p in pupils:
+            fld.apply_vignetting(p)
+    return [(p[0], p[1]) for p in pupils]
+
+
+def analyses_trace_ray_fan(opt_model, fan_rng, fld, wvl, foc, output_filter=None,
+                           rayerr_filter=None, **kwargs):
+    start = np.array(fan_rng[0], dtype=float)
+    stop, num = fan_rng[1], fan_rng[2]
+    step = (stop - start)/(num - 1)
+    pupils = []
+    for _ in range(num):
+        pupils.append(np.array(start))
+        start += step
+    kwargs['use_named_tuples'] = True
+    results = trace_pupil_rays(opt_model, [p.copy() for p in pupils], fld, wvl, output_filter,
+                               rayerr_filter, **kwargs)
+    rec = _vignette_like_reference(fld, pupils, kwargs)
+    return [[px, py, r.pkg] for (px, py), r in zip(rec, results) if r.pkg is not None]
+
+
+def analyses_trace_ray_list(opt_model, pupil_coords, fld, wvl, foc, append_if_none=False,
+                            output_filter=None, rayerr_filter=None, **kwargs):
+    pupils = list(pupil_coords)
+    results = trace_pupil_rays(opt_model, [np.array(p, dtype=float) for p in pupils], fld, wvl,
+                               output_filter, rayerr_filter, **kwargs)
+    rec = _vignette_like_reference(fld, pupils, kwargs)
+    ray_list = []
+    for (px, py), r in zip(rec, results):
+        if r.pkg is not None:
+            ray_list.append([px, py, r.pkg])
+        elif append_if_none:
+            ray_list.append([px, py, None])
+    return ray_list
+
+
+def analyses_trace_ray_grid(opt_model, grid_rng, fld, wvl, foc, append_if_none=True,
+                            output_filter=None, rayerr_filter=None, **kwargs):
+    start = np.array(grid_rng[0], dtype=float)
+    stop, num = grid_rng[1], grid_rng[2]
+    step = np.array((stop - start)/(num - 1))
+    kwargs['apply_vignetting'] = kwargs.get('apply_vignetting', False)
+    pupils = []
+    for i in range(num):
+        for j in range(num):
+            pupils.append(np.array(start))
+            start[1] += step[1]
+        start[0] += step[0]
+        start[1] = grid_rng[0][1]
+    results = trace_pupil_rays(opt_model, [p.copy() for p in pupils], fld, wvl, output_filter,
+                               rayerr_filter, **kwargs)
+    rec = _vignette_like_reference(fld, pupils, kwargs)
+    grid, k = [], 0
+    for i in range(num):
+        row = []
+        for j in range(num):
+            (px, py), r = rec[k], results[k]
+            k += 1
+            if r.pkg is not None:
+                row.append([px, py, r.pkg])
+            elif append_if_none:
+                row.append([px, py, None])
+        grid.append(row)
+    return grid

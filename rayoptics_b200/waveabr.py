@@ -20,6 +20,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import engine as E
+from .opticalspec import grid_fields_of
 from ._abi import RT_WAVE_DOUBLES
 
 
@@ -50,7 +51,7 @@ def trace_chief_rays(opt_model, table, fields, wvls):
     """Whole chief rays of every (field, wvl): one launch.  Returns
     ``full [n_ifc, 10, n_tiles]``, ``op [n_tiles]``, ``status [n_tiles]`` (numpy)."""
     osp, sm = opt_model.optical_spec, opt_model.seq_model
-    recs, eprad, z_pupil = osp.grid_fields(fields)
+    recs, eprad, z_pupil = grid_fields_of(opt_model, fields)
     g0 = E.PupilGrid(recs, [table.wvl_index(w) for w in wvls], [0.0], [0.0], eprad, z_pupil,
                      apply_vignetting=True, flip_z_dir=sm.z_dir[0], device=table.device)
     r0 = E.trace_grid(table, g0, outputs=('op', 'status'), full=True, summary=False,
@@ -66,7 +67,7 @@ def chief_ray_pkg(opt_model, full, op, wvl, tile):
     ray = [[full[k, 0:3, tile].copy(), full[k, 3:6, tile].copy(), float(full[k, 6, tile]),
             full[k, 7:10, tile].copy()] for k in range(n_ifc)]
     cr = (ray, float(op[tile]), wvl)
-    fod = opt_model.optical_spec.fod
+    fod = opt_model['analysis_results']['parax_data'].fod
     cr_exp_seg = transfer_to_exit_pupil((ray[-2][0], ray[-2][1]), fod.exp_dist)
     return cr, cr_exp_seg
 
@@ -99,7 +100,7 @@ def wave_record(opt_model, chief_ray_pkg_, ref_sphere):
     cr, cr_exp_seg = chief_ray_pkg_
     ray, cr_op, _ = cr
     image_pt, ref_dir, radius, lcl_tfrm_last = ref_sphere
-    fod = opt_model.optical_spec.fod
+    fod = opt_model['analysis_results']['parax_data'].fod
     W = np.zeros(RT_WAVE_DOUBLES)
     if is_kinda_big(radius):
         # wave_abr_full_calc_inf_ref (waveabr.py:356-420): everything that depends on the
