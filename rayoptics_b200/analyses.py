@@ -78,6 +78,12 @@ def _table_for(opt_model, table=None, device=0):
     sm = opt_model.seq_model
     cached = getattr(sm, '_b200_table', None)
     version = getattr(sm, '_version', None)
+    if version is None:
+        # a model of the reference: no edit counter -- key the cache on what the table is
+        # built from (the reference clears its own path cache in update_model; any change of
+        # those numbers changes this fingerprint)
+        from .raytrace import _fingerprint
+        version = tuple(_fingerprint(list(sm.path(w))) for w in sm.wvlns)
     if cached is None or cached[0] != version or cached[1].device != device:
         cached = (version, SurfaceTable.from_model(sm, device=device))
         sm._b200_table = cached
