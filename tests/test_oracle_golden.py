@@ -126,3 +126,23 @@ def test_oracle_live_against_reference(oracle):
                     assert a['n_seg'] == b['n_seg']
                     assert same(a['ray'], b['ray'])
                     assert a['op'] == b['op']
+
+
+def test_config0_singlet_grid_of_the_reference(oracle):
+    """BASELINE configs[0]: the singlet 7x7 grid traced by the reference's own trace_grid loop
+    (tests/golden/vectors/singlet_config0.npz) == oracle on the generated start rays"""
+    from rayoptics_b200 import engine as E
+    z = np.load(os.path.join(GOLDEN, 'vectors', 'singlet_config0.npz'))
+    opm = load_model('singlet')
+    sm = opm.seq_model
+    descs, n_by_wvl, wvls = T.describe_model(sm)
+    spec = E.grid_spec_for_model(opm, int(z['num']), fields=[opm.optical_spec.field_of_view.fields[0]],
+                                 wvls=[float(z['wvl'])])
+    assert spec.n_rays == 49
+    opts = _abi.make_opts(first_surf=1, last_surf=len(descs) - 2, check_apertures=True)
+    r = oracle.trace_grid(spec.c_spec(), descs, n_by_wvl, 0, 49, opts)
+    assert same(r['status'], z['status'])
+    ok = z['status'] == 0
+    assert 0 < ok.sum() < 49
+    assert same(r['last'][0:3].T[ok], z['p'][ok]) and same(r['last'][3:6].T[ok], z['d'][ok])
+    assert same(r['op'][ok], z['op'][ok])

@@ -223,3 +223,22 @@ def test_cuda_psf_matches_the_references(name):
     for ci in range(len(z['cases'])):
         got = A.calc_psf(z[f'grid_{ci}'][2], n_grid, dim)
         np.testing.assert_allclose(got, z[f'psf_{ci}'], rtol=0, atol=1e-12)
+
+
+def test_cuda_config0_singlet_grid_of_the_reference():
+    """BASELINE configs[0] -- singlet, 1 field, 1 wavelength, 7x7 pupil grid: the engine's grid
+    launch against the reference's own trace_grid loop (singlet_config0.npz), bit for bit"""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, 'vectors', 'singlet_config0.npz'))
+    opm = load_model('singlet')
+    tab = T.SurfaceTable.from_model(opm.seq_model, device=0)
+    grid = E.grid_for_model(opm, tab, int(z['num']), fields=[opm.optical_spec.field_of_view.fields[0]],
+                            wvls=[float(z['wvl'])])
+    assert grid.n_rays == 49
+    r = E.trace_grid(tab, grid)
+    torch.cuda.synchronize()
+    assert np.array_equal(np_(r.status), z['status'])
+    ok = z['status'] == 0
+    assert np.array_equal(np_(r.p).T[ok], z['p'][ok]) and np.array_equal(np_(r.d).T[ok], z['d'][ok])
+    assert np.array_equal(np_(r.op)[ok], z['op'][ok])
