@@ -128,21 +128,24 @@ def test_oracle_live_against_reference(oracle):
                     assert a['op'] == b['op']
 
 
-def test_config0_singlet_grid_of_the_reference(oracle):
-    """BASELINE configs[0]: the singlet 7x7 grid traced by the reference's own trace_grid loop
-    (tests/golden/vectors/singlet_config0.npz) == oracle on the generated start rays"""
+GRID_CONFIGS = ['singlet', 'dblgauss', 'rc', 'evenasph', 'cellphone', 'zoom52']
+
+
+@pytest.mark.parametrize('name', GRID_CONFIGS)
+def test_baseline_configs_grid_of_the_reference(oracle, name):
+    """The five BASELINE configurations (+ the EVENASPH lens) at reduced pupil sampling: the body
+    of the reference's own trace_grid loop (tests/golden/vectors/<model>_grid.npz, generator
+    make_golden_grids.py) == start rays generated + traced by the oracle, bit for bit"""
     from rayoptics_b200 import engine as E
-    z = np.load(os.path.join(GOLDEN, 'vectors', 'singlet_config0.npz'))
-    opm = load_model('singlet')
-    sm = opm.seq_model
-    descs, n_by_wvl, wvls = T.describe_model(sm)
-    spec = E.grid_spec_for_model(opm, int(z['num']), fields=[opm.optical_spec.field_of_view.fields[0]],
-                                 wvls=[float(z['wvl'])])
-    assert spec.n_rays == 49
+    z = np.load(os.path.join(GOLDEN, 'vectors', name + '_grid.npz'))
+    opm = load_model(name)
+    descs, n_by_wvl, wvls = T.describe_model(opm.seq_model)
+    spec = E.grid_spec_for_model(opm, int(z['num']))
+    assert spec.n_rays == z['status'].size
     opts = _abi.make_opts(first_surf=1, last_surf=len(descs) - 2, check_apertures=True)
-    r = oracle.trace_grid(spec.c_spec(), descs, n_by_wvl, 0, 49, opts)
+    r = oracle.trace_grid(spec.c_spec(), descs, n_by_wvl, 0, spec.n_rays, opts, n_threads=4)
     assert same(r['status'], z['status'])
     ok = z['status'] == 0
-    assert 0 < ok.sum() < 49
+    assert 0 < ok.sum() < ok.size
     assert same(r['last'][0:3].T[ok], z['p'][ok]) and same(r['last'][3:6].T[ok], z['d'][ok])
     assert same(r['op'][ok], z['op'][ok])
