@@ -212,6 +212,33 @@ def parity_vs_oracle(spec, descs, n_by_wvl, r0, r1, cores, gpu):
                        'tile field 1 / wvl 1 of the timed grid'}
 
 
+def parity_vs_reference_golden(model, opm, tab):
+    """Engine vs tests/golden/vectors/<model>_grid.npz: the model's fields x wavelengths at a
+    reduced pupil grid traced by the body of the reference's own trace_grid loop in the build
+    container (tests/golden/make_golden_grids.py).  Outside every timed region."""
+    import torch
+    from rayoptics_b200 import engine as E
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'vectors', model + '_grid.npz'))
+    grid = E.grid_for_model(opm, tab, int(z['num']))
+    r = E.trace_grid(tab, grid)
+    torch.cuda.synchronize()
+    status = r.status.cpu().numpy()
+    ok = z['status'] == 0
+    p = r.p.cpu().numpy().T
+    dxy = p[ok, 0:2] - z['p'][ok, 0:2]
+    dist = np.sqrt((dxy**2).sum(1))
+    bit = (np.array_equal(p[ok], z['p'][ok]) and np.array_equal(r.d.cpu().numpy().T[ok], z['d'][ok])
+           and np.array_equal(r.op.cpu().numpy()[ok], z['op'][ok]))
+    grid.close()
+    return {'rays': int(ok.size), 'rays_ok': int(ok.sum()), 'pupil_grid': int(z['num']),
+            'intercept_rms_mm': float(np.sqrt((dist**2).mean())),
+            'intercept_max_abs_mm': float(dist.max()),
+            'status_equal': bool(np.array_equal(status, z['status'])),
+            'bit_identical_p_d_op': bool(bit), 'target_mm': 1e-10,
+            'against': 'rayoptics.raytr.trace.trace_safe/trace_base/raytrace.trace_raw of the '
+                       'reference (golden vectors generated in the build container)'}
+
+
 def cpu_baseline(opm, num, target_s=12.0, gpu=None):
     """The oracle port on all host threads, on a bounded contiguous sample of the
     same grid (one tile = field 1, wavelength 1)."""
@@ -450,6 +477,10 @@ def run_b200(args):
                 'full_ray_regime': None if full_ray is None else dict(
                     full_ray, frac_of_hbm_peak=full_ray['achieved_gbs']/hbm_peak),
                 'rays_ok_frac': float((status == 0).mean())}
+        try:      # the same model at 24x24 against rays traced by the REFERENCE's own grid loop
+            line['parity_vs_reference'] = parity_vs_reference_golden(args.model, opm, tab)
+        except Exception as e:      # noqa: BLE001 - never lose the bench line over a checker
+            line['parity_vs_reference'] = {'error': repr(e)}
         if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only
             def gpu_records(r0, r1):
                 return {k: getattr(res, k)[..., r0:r1].cpu().numpy()
