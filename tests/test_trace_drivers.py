@@ -464,3 +464,46 @@ def test_set_vig_and_apertures_equal_the_references(name):
     V.set_vig(b, tracer=oracle_tracer)
     for fa, fb in zip(a.optical_spec.field_of_view.fields, b.optical_spec.field_of_view.fields):
         assert (fa.vux, fa.vlx, fa.vuy, fa.vly) == (fb.vux, fb.vlx, fb.vuy, fb.vly)
+
+
+@needs_ref
+def test_sequential_model_methods_equal_the_references():
+    """SequentialModel.trace_fan / trace_grid / trace_wavefront (seq/sequential.py:1006-1119): the
+    reference's METHOD TEXT (the module cannot be imported: opticalglass) executed on the hybrid
+    model with the reference's trace functions, against the mirror's methods (oracle-fed)."""
+    import ast
+    import importlib
+    from oracle import ref_model
+    RT, RA = ref_model.modules()
+    src = open('/root/reference/src/rayoptics/seq/sequential.py').read()
+    cls = [n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == 'SequentialModel'][0]
+    ns = dict(np=np, trace=RT, waveabr=importlib.import_module('rayoptics.raytr.waveabr'))
+    for fn in cls.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in ('trace_fan', 'trace_grid', 'trace_wavefront'):
+            exec(ast.get_source_segment(src, fn), ns)
+    a, b = load_model('dblgauss'), load_model('dblgauss')
+    H = ref_model.HybridModel(a)
+    H.seq_model.opt_model = H
+    for f in a.optical_spec.field_of_view.fields:          # no re-aiming by the reference
+        f.chief_ray = ((None, None, -1.0), None)
+
+    def y_abr(p, xy, ray_pkg, fld, wvl, foc):
+        return ray_pkg[0][-1][0][xy] - fld.ref_sphere[0][xy]
+
+    want = ns['trace_fan'](H.seq_model, y_abr, 2, 1, num_rays=9)
+    got = b.seq_model.trace_fan(y_abr, 2, 1, num_rays=9, tracer=oracle_tracer)
+    assert np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1]) and want[2] == got[2]
+
+    def ht(p, wi, ray_pkg, fld, wvl, foc):
+        return None if ray_pkg is None else np.array([p[0], p[1], ray_pkg[0][-1][0][1]])
+
+    want, _ = ns['trace_grid'](H.seq_model, ht, 1, num_rays=6, form='list', append_if_none=False)
+    got, _ = b.seq_model.trace_grid(ht, 1, num_rays=6, form='list', append_if_none=False,
+                                    tracer=oracle_tracer)
+    assert len(want) == len(got) == 3
+    for w, g in zip(want, got):
+        assert np.array_equal(np.array(list(w), dtype=float), np.array(list(g), dtype=float))
+    fa, fb = a.optical_spec.field_of_view.fields[1], b.optical_spec.field_of_view.fields[1]
+    want = ns['trace_wavefront'](H.seq_model, fa, 587.6, 0.0, num_rays=8)
+    got = b.seq_model.trace_wavefront(fb, 587.6, 0.0, num_rays=8, tracer=oracle_tracer)
+    assert np.array_equal(want, got)
