@@ -394,6 +394,96 @@ class RayGrid:
         return self
 
 
+# --- the functional forms of the analyses (analyses.py:233-273,513-542,699-732): one launch each,
+#     same arguments and return values ---------------------------------------------------------
+def _engine_kw(kwargs):
+    return {k: kwargs.pop(k) for k in ('table', 'device', 'backend') if k in kwargs}
+
+
+def _tile(opt_model, fld, wvl, foc, px, py, paired, apply_vignetting, check_apertures,
+          image_pt_2d, image_delta, want_opd, eng):
+    backend = eng.get('backend')
+    table = None if backend is not None else _table_for(opt_model, eng.get('table'),
+                                                        eng.get('device', 0))
+    r = _trace_pupil_points(opt_model, table, fld, wvl, foc, px, py, paired, apply_vignetting,
+                            check_apertures, image_pt_2d, image_delta, want_opd, backend=backend)
+    fld.chief_ray, fld.ref_sphere = r['chief_ray'], r['ref_sphere']
+    return r
+
+
+def eval_fan(opt_model, fld, wvl, foc, xy, image_pt_2d=None, image_delta=None, num_rays=21,
+             output_filter=None, rayerr_filter=None, **kwargs):
+    """Trace a fan of rays and evaluate dx, dy, & OPD across the fan (analyses.py:233-273)."""
+    eng = _engine_kw(kwargs)
+    t = E.accumulated_steps(-1.0, 1.0, num_rays)
+    zeros = E.accumulated_steps(0.0, 0.0, num_rays)
+    px, py = (t, zeros) if xy == 0 else (zeros, t)
+    apply_vig = kwargs.get('apply_vignetting', True)
+    r = _tile(opt_model, fld, wvl, foc, px, py, True, apply_vig, kwargs.get('check_apertures', False),
+              image_pt_2d, image_delta, True, eng)
+    convert_to_opd = 1/opt_model.nm_to_sys_units(wvl)
+    vx, vy = _vignetted(fld, px, py, apply_vig)
+    return [((vx[k], vy[k]), (r['abr'][0, k], r['abr'][1, k], convert_to_opd*r['opd'][k]))
+            for k in range(num_rays) if r['status'][k] == 0]
+
+
+def eval_pupil_coords(opt_model, fld, wvl, foc, image_pt_2d=None, image_delta=None, num_rays=21,
+                      **kwargs):
+    """Trace a square grid of rays and return the transverse aberrations ``[n_ok, 2]``
+    (analyses.py:513-542)."""
+    eng = _engine_kw(kwargs)
+    grid_def = [np.array([-1., -1.]), np.array([1., 1.]), num_rays]
+    pts = np.array(list(sampler.grid_ray_generator(grid_def))).reshape(-1, 2)
+    r = _tile(opt_model, fld, wvl, foc, pts[:, 0], pts[:, 1], True,
+              kwargs.get('apply_vignetting', True), kwargs.get('check_apertures', True),
+              image_pt_2d, image_delta, False, eng)
+    ok = r['status'] == 0
+    return r['abr'][:, ok].T.copy()
+
+
+def eval_wavefront(opt_model, fld, wvl, foc, image_pt_2d=None, image_delta=None, num_rays=21,
+                   value_if_none=np.nan, **kwargs):
+    """Trace a grid of rays over the vignetted pupil and evaluate the OPD: ``[num, num, 3]`` of
+    (pupil x, pupil y, OPD in waves) (analyses.py:699-732)."""
+    eng = _engine_kw(kwargs)
+    bbox = fld.vignetting_bbox(opt_model['optical_spec']['pupil'], oversize=kwargs.get('oversize', 1.))
+    px = E.accumulated_steps(bbox[0][0], bbox[1][0], num_rays)
+    py = E.accumulated_steps(bbox[0][1], bbox[1][1], num_rays)
+    r = _tile(opt_model, fld, wvl, foc, px, py, False, kwargs.get('apply_vignetting', False),
+              kwargs.get('check_apertures', True), image_pt_2d, image_delta, True, eng)
+    convert_to_opd = 1/opt_model.nm_to_sys_units(wvl)
+    opd = np.where(r['status'] == 0, convert_to_opd*r['opd'], value_if_none).reshape(num_rays, num_rays)
+    gx, gy = np.meshgrid(px, py, indexing='ij')
+    return np.stack([gx, gy, opd], axis=2)
+
+
+def select_plot_data(fan, xyfan, data_type):
+    """Given a fan of data, select the sample points and the resulting data (analyses.py:190-199)"""
+    f_x = np.array([p[xyfan] for p, val in fan])
+    f_y = np.array([val[data_type] for p, val in fan])
+    return f_x, f_y
+
+
+def smooth_plot_data(f_x, f_y, num_points=100):
+    """Interpolate fan data points and return a smoothed version (analyses.py:202-209)"""
+    from scipy.interpolate import interp1d
+    interpolator = interp1d(f_x, f_y, kind='cubic', assume_sorted=True)
+    x_sample = np.linspace(f_x.min(), f_x.max(), num_points)
+    return x_sample, interpolator(x_sample)
+
+
+def update_psf_data(pupil_grid, build='rebuild'):
+    """analyses.py:878-883"""
+    pupil_grid.update_data(build=build)
+    return calc_psf(pupil_grid.grid[2], pupil_grid.num_rays, pupil_grid.maxdim)
+
+
+# the reference's per-ray loops of this module, batched (rayoptics_b200/trace.py)
+from .trace import (analyses_trace_ray_fan as trace_ray_fan,       # noqa: E402
+                    analyses_trace_ray_list as trace_ray_list,
+                    analyses_trace_ray_grid as trace_ray_grid)
+
+
 # --- raw ray list (analyses.py:458-510) ------------------------------------------------------
 def _cuda_bundle_tracer(opt_model, table, p0, d0, wvl_idx, trace_kwargs):
     res = E.trace_bundle(table, p0, d0, wvl_idx=wvl_idx, full=True,

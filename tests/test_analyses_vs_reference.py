@@ -63,3 +63,44 @@ def test_analysis_classes_equal_the_references(name):
         assert np.array_equal(rl.ray_abr, z[f'list_abr_{ci}'])
         rg = A.RayGrid(opm, f=f, wl=wl, num_rays=n_grid, backend=be)
         assert np.array_equal(rg.grid, z[f'grid_{ci}'], equal_nan=True)
+
+
+def test_functional_forms_equal_the_references():
+    """eval_fan / eval_pupil_coords / eval_wavefront / select_plot_data / smooth_plot_data against
+    rayoptics.raytr.analyses run on the hybrid model (build container only)"""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip('/root/reference not present')
+    from oracle import ref_model
+    RT, RA = ref_model.modules()
+    a, b = load_model('dblgauss'), load_model('dblgauss')
+    H = ref_model.HybridModel(a)
+    be = OracleBackend(b)
+    fa, fb = a.optical_spec.field_of_view.fields[2], b.optical_spec.field_of_view.fields[2]
+    wvl = 656.3
+
+    def keep():
+        fa.chief_ray = ((None, None, -1.0), None)        # no re-aiming by the reference
+    for xy in (0, 1):
+        keep()
+        want = RA.eval_fan(H, fa, wvl, 0.0, xy, num_rays=11)
+        got = A.eval_fan(b, fb, wvl, 0.0, xy, num_rays=11, backend=be)
+        assert len(want) == len(got)
+        for (pw, vw), (pg, vg) in zip(want, got):
+            assert tuple(pw) == tuple(pg) and tuple(vw) == tuple(vg)
+        for dt in (0, 1, 2):
+            xw, yw = RA.select_plot_data(want, xy, dt)
+            xg, yg = A.select_plot_data(got, xy, dt)
+            assert np.array_equal(xw, xg) and np.array_equal(yw, yg)
+        if xy == 1:
+            sw, sg = RA.smooth_plot_data(xw, yw, 25), A.smooth_plot_data(xg, yg, 25)
+            assert np.array_equal(sw[0], sg[0]) and np.array_equal(sw[1], sg[1])
+    keep()
+    want = RA.eval_pupil_coords(H, fa, wvl, 0.0, num_rays=9)
+    got = A.eval_pupil_coords(b, fb, wvl, 0.0, num_rays=9, backend=be)
+    assert np.array_equal(want, got)
+    keep()
+    want = RA.eval_wavefront(H, fa, wvl, 0.0, num_rays=10)
+    got = A.eval_wavefront(b, fb, wvl, 0.0, num_rays=10, backend=be)
+    assert np.array_equal(want, got, equal_nan=True)
+    assert np.array_equal(fa.ref_sphere[0], fb.ref_sphere[0])
