@@ -243,3 +243,30 @@ def test_cuda_baseline_configs_grid_of_the_reference(name):
     ok = z['status'] == 0
     assert np.array_equal(np_(r.p).T[ok], z['p'][ok]) and np.array_equal(np_(r.d).T[ok], z['d'][ok])
     assert np.array_equal(np_(r.op)[ok], z['op'][ok])
+
+
+@pytest.mark.parametrize('lean', [0, 1, 2])
+def test_cuda_random_systems(oracle, lean):
+    """the randomised systems of tests/test_fuzz_three_way.py (reference == oracle == host-compiled
+    device source on CPU) through the CUDA kernels: bit for bit against the oracle, whole rays"""
+    import test_fuzz_three_way as F
+    for seed in range(40):
+        rng = np.random.default_rng(1000 + seed + 100000*lean)
+        segs = F.random_system(rng, lean)
+        tab = T.SurfaceTable.from_path(segs, device=0)
+        n = 400
+        p0 = np.zeros((3, n))
+        p0[:2] = rng.uniform(-6, 6, (2, n))
+        tgt = rng.uniform(-5, 5, (2, n))*np.where(rng.random(n) < 0.85, 1.0, 4.0)
+        v = np.array([tgt[0] - p0[0], tgt[1] - p0[1], np.full(n, abs(segs[0][2][1][2]))])
+        d0 = v/np.sqrt((v*v).sum(0))
+        wv = np.zeros(n, dtype=np.int32)
+        case = F.random_case(rng, tab.n_ifc)
+        ref = oracle.trace_bundle(tab.descs, tab.n_by_wvl, p0, d0, wv, _abi.make_opts(**case),
+                                  want_full=True, n_threads=4)
+        r = E.trace_bundle(tab, p0, d0, wvl_idx=wv, full=True, **case)
+        torch.cuda.synchronize()
+        last = np.concatenate([np_(r.p), np_(r.d), np_(r.dst)[None], np_(r.nrml)])
+        for got, key in ((np_(r.status), 'status'), (np_(r.fail_surf), 'fail_surf'),
+                         (np_(r.n_seg), 'n_seg'), (np_(r.op), 'op'), (last, 'last'), (np_(r.full), 'full')):
+            assert np.array_equal(got, ref[key], equal_nan=True), (lean, seed, key, case)
