@@ -129,3 +129,66 @@ def test_random_system_three_way(oracle, seed, lean):
             assert same(rr['ray'], ref['full'][:rr['n_seg'], :, k])
             if rr['status'] != 0:
                 assert rr['fail_surf'] == ref['fail_surf'][k]
+
+
+def add_phase_elements(rng, segs):
+    """give some refracting / reflecting interfaces a grating, a radial DOE or a hologram"""
+    for seg in segs[1:-1]:
+        ifc = seg[0]
+        if ifc.interact_mode not in ('transmit', 'reflect') or rng.random() < 0.5:
+            continue
+        u = rng.random()
+        if u < 0.4:
+            ifc.phase_element = M.DiffractionGrating(
+                order=int(rng.choice([-1, 1, 2])), grating_lpmm=float(rng.uniform(50, 400)),
+                grating_normal=[float(rng.uniform(-0.3, 0.3)), 1.0, float(rng.uniform(-0.1, 0.1))],
+                interact_mode=ifc.interact_mode)
+        elif u < 0.8 and ifc.interact_mode == 'transmit':
+            ifc.phase_element = M.DiffractiveElement(
+                coefficients=[float(rng.uniform(-2e-3, 2e-3)), float(rng.uniform(-2e-6, 2e-6)),
+                              float(rng.uniform(-1e-9, 1e-9))][:int(rng.integers(1, 4))],
+                ref_wl=float(rng.uniform(450, 650)), order=int(rng.choice([-1, 1, 2])))
+        elif ifc.interact_mode == 'transmit':
+            ifc.phase_element = M.HolographicElement(
+                ref_pt=[float(rng.uniform(-5, 5)), float(rng.uniform(-5, 5)), float(rng.uniform(-200, -50))],
+                ref_virtual=bool(rng.random() < 0.5),
+                obj_pt=[float(rng.uniform(-5, 5)), float(rng.uniform(-5, 5)), float(rng.uniform(50, 200))],
+                obj_virtual=bool(rng.random() < 0.5), ref_wl=float(rng.uniform(450, 650)))
+
+
+@pytest.mark.parametrize('seed', range(30))
+def test_random_phase_systems_three_way(oracle, seed):
+    """the same with diffractive phase elements: reference == oracle bit for bit (same libm);
+    device source == oracle in status / failing surface / segment counts, coordinates within
+    1e-11 mm (x**k: DESIGN.md 2a)"""
+    rng = np.random.default_rng(5000 + seed)
+    segs = random_system(rng, lean=0)
+    add_phase_elements(rng, segs)
+    wvl = 550.0
+    descs, ns = T.describe_path(segs)
+    n_ifc, n_by_wvl = len(descs), np.array([ns])
+    n = 300
+    p0 = np.zeros((3, n))
+    p0[:2] = rng.uniform(-5, 5, (2, n))
+    tgt = rng.uniform(-4, 4, (2, n))
+    v = np.array([tgt[0] - p0[0], tgt[1] - p0[1], np.full(n, abs(segs[0][2][1][2]))])
+    d0 = v/np.sqrt((v*v).sum(0))
+    wv = np.zeros(n, dtype=np.int32)
+    case = random_case(rng, n_ifc)
+    opts = _abi.make_opts(**case)
+    ref = oracle.trace_bundle(descs, n_by_wvl, p0, d0, wv, opts, want_full=True, n_threads=2, wvls=[wvl])
+    r = HS.trace_bundle(descs, n_by_wvl, p0, d0, wv, opts, kernel=0, out_kind=2, wvls=[wvl])
+    for k in ('status', 'fail_surf', 'n_seg'):
+        assert same(r[k], ref[k]), (seed, k, case)
+    assert np.array_equal(np.isnan(r['full']), np.isnan(ref['full']))
+    assert np.nanmax(np.abs(r['full'] - ref['full']), initial=0.0) <= 1e-11
+    assert np.nanmax(np.abs(r['op'] - ref['op']), initial=0.0) <= 1e-8
+    if rh.available():
+        path = rh.ref_path(type('S', (), {'path': lambda self, w: segs})(), wvl)
+        for k in range(0, n, 6):
+            rr = rh.ref_trace(path, p0[:, k], d0[:, k], wvl, **case)
+            if rr['status'] == 5:
+                continue
+            assert rr['status'] == ref['status'][k], (seed, k, case)
+            assert rr['n_seg'] == ref['n_seg'][k] and same(np.float64(rr['op']), ref['op'][k])
+            assert same(rr['ray'], ref['full'][:rr['n_seg'], :, k])
