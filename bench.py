@@ -447,11 +447,11 @@ def run_b200(args):
         except Exception:
             pass
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
-        traffic = None
+        traffic, ncu = None, {}
         try:     # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
             if args.model == 'dblgauss' and args.num == 512:
-                traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_dblgauss_512.json')))[
-                    'dram_bytes_per_launch']
+                ncu = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_dblgauss_512.json')))
+                traffic = ncu['dram_bytes_per_launch']
         except Exception:
             pass
         ach_gbs = n_rays*bpr/(kern_ms*1e-3)/1e9
@@ -466,6 +466,11 @@ def run_b200(args):
                 'fp64': {'achieved_tflops': ach_tf, 'peak_tflops': fp64_peak,
                          'frac': ach_tf/fp64_peak if fp64_peak else None,
                          'peak_source': 'rt_measure_fp64_peak: DFMA chain microbenchmark, this run',
+                         'pipe_utilisation_ncu': (None if ncu.get('fp64_pipe_pct_of_peak') is None
+                                                  else ncu['fp64_pipe_pct_of_peak']/100),
+                         'issue_active_ncu': (None if ncu.get('issue_active_pct') is None
+                                              else ncu['issue_active_pct']/100),
+                         'ncu_source': ncu.get('source'),
                          'algorithmic_flop_per_full_ray': flops_full_ray,
                          'algorithmic_flop_per_step': flops}}
         line = {'metric': METRIC, 'value': world*n_rays*args.steps/(dev_ms_max*1e-3), 'unit': UNIT,

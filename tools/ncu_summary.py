@@ -84,7 +84,13 @@ def main():
         d = dict(zip(hdr, raw[2]))
         scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
         tr = sum(float(d[k])*scale[units[hdr.index(k)]] for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+        def pct(k):
+            return float(d[k]) if k in d else None
         json.dump({'kernel': d.get('Kernel Name', '?'), 'dram_bytes_per_launch': tr,
+                   'fp64_pipe_pct_of_peak': pct('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'),
+                   'issue_active_pct': pct('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                   'dram_throughput_pct': pct('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'),
+                   'kernel_us_under_ncu': pct('gpu__time_duration.sum'),
                    'source': rep.split('/')[-1] + ' (ncu --set full, one launch)'},
                   open(sys.argv[3], 'w'), indent=1)
         print('wrote', sys.argv[3])
