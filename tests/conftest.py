@@ -20,6 +20,9 @@ PHASE_MODEL_NAMES = ['hybrid', 'diffractive', 'diffractive_wild']
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    if os.environ.get('B200RT_DRYRUN') == '1':      # opt-in: exercise GPU test CODE on the oracle
+        import dryrun_engine
+        dryrun_engine.install()
 
 
 @pytest.fixture(scope='session')
