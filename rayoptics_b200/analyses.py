@@ -78,14 +78,17 @@ def _table_for(opt_model, table=None, device=0):
     sm = opt_model.seq_model
     cached = getattr(sm, '_b200_table', None)
     version = getattr(sm, '_version', None)
+    built = None
     if version is None:
-        # a model of the reference: no edit counter -- key the cache on what the table is
-        # built from (the reference clears its own path cache in update_model; any change of
-        # those numbers changes this fingerprint)
-        from .raytrace import _fingerprint
-        version = tuple(_fingerprint(list(sm.path(w))) for w in sm.wvlns)
+        # a model of the reference: no edit counter -- key the cache on the compiled
+        # descriptor records themselves (every number the kernels can see; the reference's
+        # own invalidation point is update_model(), seq/sequential.py:666-668)
+        from .table import describe_model
+        built = describe_model(sm)
+        version = (bytes(built[0]), built[1].tobytes(), tuple(built[2]))
     if cached is None or cached[0] != version or cached[1].device != device:
-        cached = (version, SurfaceTable.from_model(sm, device=device))
+        tab = SurfaceTable(*built, device=device) if built else SurfaceTable.from_model(sm, device=device)
+        cached = (version, tab)
         sm._b200_table = cached
     return cached[1]
 
@@ -330,8 +333,6 @@ class RayList:
                 grid_def = [np.array([-1., -1.]), np.array([1., 1.]), num_rays]
                 pupil_gen = (sampler.csd_grid_ray_generator, (grid_def,), {})
             self.pupil_gen = pupil_gen
-            fct, args, kwa = pupil_gen
-            self.pupil_coords = fct(*args, **kwa)
         self.fld, self.wvl, self.foc = _resolve(opt_model, f, wl, foc)
         self.image_pt_2d, self.image_delta = image_pt_2d, image_delta
         self.apply_vignetting = apply_vignetting
@@ -344,8 +345,15 @@ class RayList:
     def update_data(self, **kwargs):
         if self.pupil_gen:
             fct, args, kwa = self.pupil_gen
-            self.pupil_coords = fct(*args, **kwa)
-        pts = np.array([np.array(p, dtype=float) for p in self.pupil_coords]).reshape(-1, 2)
+            if fct in sampler._ARRAY_FORM and not kwa:      # whole sample set as one array
+                self.pupil_coords = pts = sampler.sample_points(fct, *args)
+            else:
+                self.pupil_coords = fct(*args, **kwa)
+                pts = None
+        else:
+            pts = None
+        if pts is None:
+            pts = np.array([np.array(p, dtype=float) for p in self.pupil_coords]).reshape(-1, 2)
         r = _trace_pupil_points(self.opt_model, self._table, self.fld, self.wvl, self.foc,
                                 pts[:, 0], pts[:, 1], True, self.apply_vignetting, self.clip_rays,
                                 self.image_pt_2d, self.image_delta, False, backend=self._backend)
@@ -433,7 +441,7 @@ def eval_pupil_coords(opt_model, fld, wvl, foc, image_pt_2d=None, image_delta=No
     (analyses.py:513-542)."""
     eng = _engine_kw(kwargs)
     grid_def = [np.array([-1., -1.]), np.array([1., 1.]), num_rays]
-    pts = np.array(list(sampler.grid_ray_generator(grid_def))).reshape(-1, 2)
+    pts = sampler.square_grid_points(grid_def)
     r = _tile(opt_model, fld, wvl, foc, pts[:, 0], pts[:, 1], True,
               kwargs.get('apply_vignetting', True), kwargs.get('check_apertures', True),
               image_pt_2d, image_delta, False, eng)

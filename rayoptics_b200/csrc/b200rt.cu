@@ -669,8 +669,10 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
         if (s.n_coefs < 0 || s.n_coefs > RT_MAX_COEFS || s.n_apertures < 0 ||
             s.n_apertures > RT_MAX_APERTURES)
             return fail(RT_ERR_INVALID, "rt_table_create: coefficient / aperture count out of range");
-        if (s.phase_kind != RT_PHASE_NONE && s.phase_kind != RT_PHASE_HOE)
+        if (s.phase_kind < RT_PHASE_NONE || s.phase_kind > RT_PHASE_RADIAL)
             return fail(RT_ERR_UNSUPPORTED, "rt_table_create: unknown phase element kind");
+        if (s.n_phase_coefs < 0 || s.n_phase_coefs > RT_MAX_PHASE_COEFS)
+            return fail(RT_ERR_INVALID, "rt_table_create: phase coefficient count out of range");
     }
     DeviceGuard guard(device);
     cudaDeviceProp prop;

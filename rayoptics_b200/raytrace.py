@@ -29,7 +29,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _abi, engine as E
+from . import _abi, engine as E, table as T
 from .table import SurfaceTable
 
 try:                                    # the reference's own exception classes, when importable
@@ -59,44 +59,27 @@ def set_device(device):
     _DEVICE = int(device)
 
 
-def _phase_fp(pe):
-    if pe is None:
-        return None
-    fp = [type(pe).__name__, getattr(getattr(pe, 'phase_fct', None), '__name__', None)]
-    for k in ('ref_pt', 'obj_pt', 'grating_normal', 'coefficients'):
-        v = getattr(pe, k, None)
-        fp.append(None if v is None else tuple(map(float, v)))
-    for k in ('ref_virtual', 'obj_virtual', 'ref_wl', 'order', '_grating_spacing_nm'):
-        fp.append(getattr(pe, k, None))
-    return tuple(fp)
-
-
 def _fingerprint(segs):
-    fp = []
-    for seg in segs:
-        ifc, _gap, tfrm, n, z_dir = (tuple(seg) + (None,)*5)[:5]
-        prf = getattr(ifc, 'profile', None)
-        coefs = getattr(prf, 'coefs', None)
-        fp.append((id(ifc), type(prf).__name__, getattr(prf, 'cv', None), getattr(prf, 'cc', None),
-                   getattr(prf, 'cR', None), None if coefs is None else tuple(coefs),
-                   getattr(ifc, 'interact_mode', None), getattr(ifc, 'max_aperture', None),
-                   len(getattr(ifc, 'clear_apertures', ()) or ()), n, z_dir,
-                   _phase_fp(getattr(ifc, 'phase_element', None)),
-                   None if tfrm is None else (tfrm[0].tobytes() if hasattr(tfrm[0], 'tobytes')
-                                              else repr(tfrm[0]), tuple(map(float, tfrm[1])))))
-    return tuple(fp)
+    """Cache key of a path: the bytes of the very descriptor records the device table is
+    built from, plus the indices.  Whatever the kernels can see -- profile numbers,
+    coefficient counts, every clear aperture's type / size / offset / obscuration flag,
+    transforms, z_dir, phase-element parameters -- is in those records, so an in-place
+    edit of any of them yields a new table.  (The reference's invalidation point is
+    update_model(), seq/sequential.py:666-668, which clears its own path cache.)
+    Returns ``(key, descs, indices)``."""
+    descs, ns = T.describe_path(segs)
+    return (bytes(descs), tuple(ns)), descs, ns
 
 
 def _table_for_path(segs, wvl=None):
-    """Surface table of a path, cached on its content (the reference clears its
-    own path cache in update_model; here any change of the numbers the table is
-    built from changes the fingerprint)."""
-    fp = (_fingerprint(segs), wvl)
+    """Surface table of a path, cached on its compiled content."""
+    key, descs, ns = _fingerprint(segs)
+    fp = (key, wvl, _DEVICE)
     tab = _PATH_CACHE.get(fp)
     if tab is None:
         if len(_PATH_CACHE) > 64:
             _PATH_CACHE.clear()
-        tab = SurfaceTable.from_path(segs, device=_DEVICE, wvl=wvl)
+        tab = SurfaceTable(descs, np.array([ns]), None if wvl is None else [float(wvl)], _DEVICE)
         _PATH_CACHE[fp] = tab
     return tab
 

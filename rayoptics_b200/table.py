@@ -151,9 +151,14 @@ def describe_model(seq_model, wvls=None):
     descs = None
     rows = []
     for wl in wvls:
-        arr, ns = describe_path(seq_model.path(wl))
         if descs is None:
-            descs = arr
+            descs, ns = describe_path(seq_model.path(wl))
+        else:               # only the index column depends on the wavelength
+            ns, prev_n = [], 1.0
+            for seg in seq_model.path(wl):
+                n = seg[3] if len(seg) > 3 else None
+                prev_n = float(n if n is not None else prev_n)
+                ns.append(prev_n)
         rows.append(ns)
     return descs, np.ascontiguousarray(np.array(rows, dtype=np.float64)), list(wvls)
 

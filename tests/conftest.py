@@ -21,6 +21,11 @@ PHASE_MODEL_NAMES = ['hybrid', 'diffractive', 'diffractive_wild']
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
     if os.environ.get('B200RT_DRYRUN') == '1':      # opt-in: exercise GPU test CODE on the oracle
+        import torch
+        if torch.cuda.is_available():
+            # never let the oracle stand in for the kernels where the kernels can run
+            raise pytest.UsageError('B200RT_DRYRUN=1 is refused on a machine with a CUDA device: '
+                                    'the -m gpu tests must run the real engine here')
         import dryrun_engine
         dryrun_engine.install()
 

@@ -270,6 +270,19 @@ def test_samplers_match_reference():
     a = list(RS.create_generator(RS.R_2_quasi_random_generator, 20, mapper=RS.concentric_sample_disk))
     b = list(S.create_generator(S.R_2_quasi_random_generator, 20, mapper=S.concentric_sample_disk))
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # whole-array producers == the reference's per-sample generators, bit for bit
+    for num in (2, 21, 64):
+        g = lambda: [np.array([-1., -1.]), np.array([1., 1.]), num]      # noqa: E731
+        assert np.array_equal(S.square_grid_points(g()), np.array(list(RS.grid_ray_generator(g()))))
+        assert np.array_equal(S.disk_grid_points(g()), np.array(list(RS.csd_grid_ray_generator(g()))))
+        xs, ys = S.square_grid_axes(g())
+        assert np.array_equal(S.square_grid_points(g()).reshape(num, num, 2)[:, 0, 0], xs)
+    u = np.array([[0., 0.], [0.5, 0.5], [1., 0.], [0., 1.], [0.25, 0.75], [0.75, 0.25], [0.3, 0.3],
+                  [0.5, 0.1], [0.1, 0.5]])
+    for off in (True, False):
+        want = np.array([RS.concentric_sample_disk(x, offset=off) for x in u], dtype=float)
+        assert np.array_equal(S.concentric_disk(u, offset=off), want)
+    assert np.array_equal(S.r2_sequence(500), np.array([z.copy() for z in RS.R_2_quasi_random_generator(500)]))
 
 
 def test_psf_helpers_match_reference():
@@ -286,3 +299,45 @@ def test_psf_helpers_match_reference():
     fld = opm.optical_spec.field_of_view.fields[1]
     fld.ref_sphere = (np.zeros(3), np.array([0., 0., 1.]), 123.456, None)
     assert A.calc_psf_scaling(opm, fld, 587.6, 32, 128) == RA.calc_psf_scaling(opm, fld, 587.6, 32, 128)
+
+
+def test_table_cache_key_sees_in_place_edits():
+    """The drop-in's table cache (raytrace._table_for_path, analyses._table_for) is keyed on
+    the compiled descriptor records: editing a clear aperture, a conic constant or a
+    polynomial coefficient in place -- without update_model(), whose cache clearing
+    (seq/sequential.py:666-668) is the reference's own invalidation point -- gives a new key."""
+    from rayoptics_b200 import raytrace as RT
+    opm = load_model('exotic')
+    sm = opm.seq_model
+    segs = lambda: list(sm.path(sm.central_wavelength()))       # noqa: E731
+    k0 = RT._fingerprint(segs())[0]
+    assert RT._fingerprint(segs())[0] == k0
+    seen = {k0}
+
+    def changed():
+        k = RT._fingerprint(segs())[0]
+        assert k not in seen
+        seen.add(k)
+
+    ifc_ca = next(i for i in sm.ifcs if getattr(i, 'clear_apertures', None))
+    ca = ifc_ca.clear_apertures[0]
+    for attr in ('radius', 'x_half_width', 'y_half_width'):
+        if hasattr(ca, attr):
+            setattr(ca, attr, getattr(ca, attr)*1.25)
+            changed()
+    ca.x_offset += 0.125
+    changed()
+    ca.y_offset -= 0.25
+    changed()
+    ca.is_obscuration = not getattr(ca, 'is_obscuration', False)
+    changed()
+    ifc_poly = next(i for i in sm.ifcs if len(getattr(i.profile, 'coefs', [])) > 0)
+    ifc_poly.profile.coefs[0] += 1e-9
+    changed()
+    ifc_cc = next(i for i in sm.ifcs if hasattr(i.profile, 'cc'))
+    ifc_cc.profile.cc = ifc_cc.profile.cc - 0.5
+    if hasattr(ifc_cc.profile, 'update'):
+        ifc_cc.profile.update()
+    changed()
+    sm.ifcs[1].max_aperture *= 2.0
+    changed()
