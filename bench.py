@@ -2,20 +2,29 @@
 """bench.py -- rays/sec (fp64) through a sequential model on B200(s).
 
 Metric (BASELINE.json): rays/sec in fp64 through an N-surface sequential model.
-Workload: BASELINE configs[1] -- double Gauss (13 interfaces), 3 fields x 3
+Default workload: BASELINE configs[1] -- double Gauss (13 interfaces), 3 fields x 3
 wavelengths x 512 x 512 pupil grid = 2,359,296 rays per step, apertures checked,
 start rays generated on the device, per-ray last-segment records (p, d, op,
 status, fail_surf: 64 B) + transverse aberration (16 B) written to HBM,
 per-(field, wvl) spot sums reduced.  A step = one pass over that grid.
+`--model rc|evenasph|cellphone|zoom52` selects the other BASELINE configurations
+(their pupil sampling is the default `--num`).
 
-Multi-GPU (`--gpus N` under torchrun): weak scaling -- every rank traces a full
-replica of the grid on its own GPU (per-GPU work fixed); the only collective is
-the all-gather of the [n_tiles, 16] spot sums.  value = N x rays / max-rank time.
+Multi-GPU (`--gpus N` under torchrun):
+  --mode replica (default)  weak scaling: every rank traces a full replica of the grid
+                            on its own GPU; value = N x rays / max-rank time
+  --mode shard              strong scaling: the grid's chunk space (field-major, then
+                            wavelength, then pupil rows) is cut into N contiguous ranges,
+                            one per rank (parallel.shard_chunks); value = rays / max-rank time
+In both the only collective is the all-gather of the [n_tiles, 16] spot sums, issued on a
+side stream together with its one-launch combine.
 
   python bench.py --gpus N --steps K --warmup W            (this repo's engine)
-  python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the oracle
-        port of the reference's trace_raw on all host threads; the reference is
-        pure Python and cannot travel to the GPU box -- DESIGN.md "reference arm")
+  python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the UNMODIFIED Python
+        reference from baseline/_ref on all host cores -- its own trace.trace_grid ->
+        trace_raw, baseline/reference_arm.py -- on a bounded sample of the same workload;
+        the C port oracle/rt_oracle.c is timed next to it.  Falls back to the port alone
+        if baseline/_ref is not installed.)
 
 One JSON line on stdout (rank 0).  DESIGN.md "Measurement" says how every field
 is obtained.
@@ -38,17 +47,33 @@ METRIC = 'rays/sec (fp64) through N-surface seq model'
 UNIT = 'rays/s'
 
 
+# BASELINE.json configs -> fixture model and pupil samples per side
+WORKLOADS = {
+    'singlet': (7, 'BASELINE configs[0]'),
+    'dblgauss': (512, 'BASELINE configs[1]'),
+    'rc': (1024, 'BASELINE configs[2]'),
+    'evenasph': (256, 'BASELINE configs[3], Zemax EVENASPH import'),
+    'cellphone': (256, 'BASELINE configs[3] geometry on the cell-phone lens (8 RadialPolynomial surfaces)'),
+    'zoom52': (1024, 'BASELINE configs[4]'),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--model', default='dblgauss')
-    ap.add_argument('--num', type=int, default=512, help='pupil samples per side')
+    ap.add_argument('--model', default='dblgauss', choices=sorted(WORKLOADS))
+    ap.add_argument('--num', type=int, default=None, help='pupil samples per side (default: the BASELINE config)')
+    ap.add_argument('--mode', default='replica', choices=['replica', 'shard'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.baseline_num = WORKLOADS[args.model][0]
+    if args.num is None:
+        args.num = args.baseline_num
+    return args
 
 
 def load_model(name):
@@ -187,6 +212,48 @@ def cpu_trace(spec, descs, n_by_wvl, r0, r1, threads):
     return time.perf_counter() - t0, r
 
 
+def port_arm(spec, descs, n_by_wvl, r0, r1, target_s=6.0, scaling=True):
+    """oracle/rt_oracle.c (the C port of trace_raw + start rays + transverse aberration) on a
+    persistent pthread pool with dynamic scheduling, output buffers allocated and first touched
+    before the timed calls; only the C call is timed.  Thread scaling at 1 / 32 / all."""
+    from oracle import rt_oracle
+    from rayoptics_b200 import _abi
+    cores = os.cpu_count() or 1
+    opts = _abi.make_opts(first_surf=1, last_surf=len(descs) - 2, check_apertures=True)
+    out = {'unit': UNIT, 'kind': 'port', 'cores': cores, 'threads_scaling': {}}
+    runner = None
+    for th in (sorted({1, min(32, cores), cores}) if scaling else [cores]):
+        runner = rt_oracle.GridRunner(spec, descs, n_by_wvl, opts, r1 - r0, th)
+        n_w = r1 - r0 if th > 1 else min(r1 - r0, 50000)
+        runner.run(r0, r0 + n_w)                                        # warm-up, first touch
+        reps, tot, budget = 0, 0.0, (target_s if th == cores else target_s/4)
+        while tot < budget and reps < 200:
+            tot += runner.run(r0, r0 + n_w)
+            reps += 1
+        out['threads_scaling'][str(th)] = n_w*reps/tot
+        if th == cores:
+            out['value'] = n_w*reps/tot
+            out['sample'] = (f'{reps} x {n_w} rays of the same grid, oracle/rt_oracle.c on a persistent pool of '
+                             f'{cores} pthreads (dynamic blocks of 2048 rays), buffers pre-touched, C call only')
+    return out, runner
+
+
+def python_reference_arm(model, steps, warmup, step_s=1.5):
+    """The unmodified Python reference (baseline/_ref) on one worker process per host core, run
+    by baseline/reference_arm.py in a fresh interpreter (no CUDA context, no NCCL in the
+    workers' parent).  Returns the arm's dict, or (None, reason)."""
+    cmd = [sys.executable, os.path.join(ROOT, 'baseline', 'reference_arm.py'), '--model', model,
+           '--steps', str(steps), '--warmup', str(warmup), '--step-s', str(step_s)]
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, cwd=ROOT)
+        out = json.loads(p.stdout.strip().splitlines()[-1])
+    except Exception as e:      # noqa: BLE001
+        return None, repr(e)
+    if 'unavailable' in out:
+        return None, out['unavailable']
+    return out, None
+
+
 def parity_vs_oracle(spec, descs, n_by_wvl, r0, r1, cores, gpu):
     """ray-intercept RMS / max-abs at the image interface between the
     engine's records of the timed steps and the oracle on the same grid rays, plus
@@ -239,27 +306,28 @@ def parity_vs_reference_golden(model, opm, tab):
                        'reference (golden vectors generated in the build container)'}
 
 
-def cpu_baseline(opm, num, target_s=12.0, gpu=None):
-    """The oracle port on all host threads, on a bounded contiguous sample of the
-    same grid (one tile = field 1, wavelength 1)."""
-    cores = os.cpu_count() or 1
+def cpu_baseline(args, opm, gpu=None):
+    """CPU side of the main line (rank 0, N=1): the Python reference on all cores on a bounded
+    sample (kind "reference") when baseline/_ref is installed, and the C port next to it."""
+    num = args.num
     spec, descs, n_by_wvl = host_grid_spec(opm, num)
     per_tile = num*num
     tile = min(4, spec.n_tiles - 1)
-    r0, r1 = tile*per_tile, (tile + 1)*per_tile
-    dt, _ = cpu_trace(spec, descs, n_by_wvl, r0, r0 + min(20000, per_tile), cores)   # warm-up
-    reps, total_t, total_n = 0, 0.0, 0
-    while total_t < target_s and reps < 50:
-        dt, _ = cpu_trace(spec, descs, n_by_wvl, r0, r1, cores)
-        total_t += dt; total_n += r1 - r0; reps += 1
-    dt1, _ = cpu_trace(spec, descs, n_by_wvl, r0, r0 + min(100000, per_tile), 1)
-    out = {'value': total_n/total_t, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-           'sample': f'{reps} x {r1 - r0} rays (tile field 1 / wvl 1 of the same grid), '
-                     f'oracle/rt_oracle.c on {cores} pthreads',
-           'single_thread': min(100000, per_tile)/dt1}
+    r0 = tile*per_tile
+    r1 = r0 + min(per_tile, 1 << 20)
+    port, _ = port_arm(spec, descs, n_by_wvl, r0, r1)
+    ref, why = None, None
+    try:
+        ref, why = python_reference_arm(args.model, steps=6, warmup=1)
+    except Exception as e:      # noqa: BLE001 - never lose the bench line over the baseline
+        why = repr(e)
+    if ref is not None:
+        out = dict(ref, port=port)
+    else:
+        out = dict(port, reference_unavailable=str(why))
     if gpu is not None:
         try:
-            out['parity'] = parity_vs_oracle(spec, descs, n_by_wvl, r0, r1, cores, gpu)
+            out['parity'] = parity_vs_oracle(spec, descs, n_by_wvl, r0, r1, port['cores'], gpu)
         except Exception as e:      # noqa: BLE001 - never lose the bench line over the checker
             out['parity'] = {'error': repr(e)}
     return out
@@ -271,25 +339,28 @@ def run_reference(args):
     if rank != 0:
         return
     opm = load_model(args.model)
-    cores = os.cpu_count() or 1
     spec, descs, n_by_wvl = host_grid_spec(opm, args.num)
     n = spec.n_rays
-    for _ in range(max(args.warmup, 1)):
-        cpu_trace(spec, descs, n_by_wvl, 0, min(n, 200000), cores)
-    t_tot = 0.0
-    for _ in range(args.steps):
-        dt, _ = cpu_trace(spec, descs, n_by_wvl, 0, n, cores)
-        t_tot += dt
-    val = n*args.steps/t_tot
+    port, runner = port_arm(spec, descs, n_by_wvl, 0, min(n, 1 << 22), target_s=4.0)
+    ref, why = python_reference_arm(args.model, args.steps, args.warmup)
+    if ref is not None:
+        val, ms = ref['value'], ref['ms_per_step']
+        base = dict(ref, port=port)
+    else:       # baseline/_ref missing: the port is the arm, K steps over (a bounded part of) the grid
+        n_s = min(n, 1 << 22)
+        for _ in range(max(args.warmup, 1)):
+            runner.run(0, n_s)
+        t_tot = sum(runner.run(0, n_s) for _ in range(args.steps))
+        val, ms = n_s*args.steps/t_tot, 1e3*t_tot/args.steps
+        base = dict(port, value=val, reference_unavailable=str(why),
+                    sample=f'{args.steps} steps x {n_s} rays, ' + port['sample'].split(', ', 1)[1])
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT,
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': 1e3*t_tot/args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'ms_per_step': ms, 'higher_is_better': True,
+            'scaling': 'weak' if args.mode == 'replica' else 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': config_dict(args, opm, spec, 1),
-            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                             'sample': f'whole grid ({n} rays) per step, oracle/rt_oracle.c port of '
-                                       f'trace_raw on {cores} pthreads; the Python reference itself '
-                                       f'cannot run on this box (no /root/reference)'},
+            'config': config_dict(args, opm, spec, args.gpus),
+            'cpu_baseline': base,
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -297,20 +368,32 @@ def run_reference(args):
 
 def config_dict(args, opm, grid, world):
     sm = opm.seq_model
-    return {'workload': f'{args.model}: {sm.get_num_surfaces()} interfaces, '
-                        f'{grid.n_fields} fields x {grid.n_wvls} wvls x {args.num}x{args.num} pupil '
-                        f'(BASELINE configs[1])' if args.model == 'dblgauss' and args.num == 512 else
-                        f'{args.model}: {sm.get_num_surfaces()} interfaces, {grid.n_fields} fields x '
-                        f'{grid.n_wvls} wvls x {args.num}x{args.num} pupil',
-            'rays_per_step_per_gpu': grid.n_rays, 'check_apertures': True,
+    tag = WORKLOADS[args.model][1] if args.num == args.baseline_num else 'reduced pupil sampling'
+    n_rays = grid.n_rays
+    mode = (f'replica-per-gpu x{world} (weak scaling)' if args.mode == 'replica' else
+            f'grid chunk space sharded over {world} gpu(s) (strong scaling)')
+    return {'workload': f'{args.model}: {sm.get_num_surfaces()} interfaces, {grid.n_fields} fields x '
+                        f'{grid.n_wvls} wvls x {args.num}x{args.num} pupil ({tag})',
+            'rays_per_step_per_gpu': n_rays if args.mode == 'replica' else -(-n_rays//world),
+            'rays_per_step': n_rays*world if args.mode == 'replica' else n_rays,
+            'check_apertures': True,
             'output': 'last segment p,d + op + status + fail_surf (64 B/ray) + transverse '
                       'aberration (16 B/ray) + per-(field,wvl) spot sums',
-            'parallelism': f'replica-per-gpu x{world}, all-gather of [n_tiles,16] spot sums',
+            'parallelism': mode + ', one all-gather of the [n_tiles,16] spot sums per step',
             'l2': 'no HBM input is re-read (start rays are generated on-chip); each step writes '
-                  '189 MB of results > 126 MB L2'}
+                  f'{n_rays*80/1e6:.0f} MB of results per grid (L2: 126 MB)'}
 
 
 # ----------------------------------------------------------------- B200 arm
+def kernel_name(tab_descs, lean_ok=True):
+    poly = any(d.profile > 1 for d in tab_descs)
+    general = any(d.has_tfrm != 0 or d.n_apertures != 0 or d.phase_kind != 0 or d.profile == 6
+                  for d in tab_descs)
+    if general:
+        return 'k_trace_grid<0,1,1,0>'
+    return 'k_trace_grid_lean<0,1,0,%d>' % int(poly)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -331,14 +414,15 @@ def run_b200(args):
     opm = load_model(args.model)
     tab = T.SurfaceTable.from_model(opm.seq_model, device=local)
     grid = E.grid_for_model(opm, tab, args.num)
-    res = E.BundleResult(grid.n_rays, tab.n_ifc, dev, E.GRID_OUTPUTS)
-    n_rays = grid.n_rays                     # weak scaling: every rank traces a full grid replica
+    shard = args.mode == 'shard'
+    c0, c1 = P.shard_chunks(grid.n_chunks, rank, world) if shard else (0, grid.n_chunks)
+    n_mine = grid.rays_in_chunks(c0, c1)             # rays this rank traces per step
+    first = grid.first_ray_of_chunk(c0)
+    n_job = grid.n_rays if shard else world*grid.n_rays
+    res = E.BundleResult(n_mine, tab.n_ifc, dev, E.GRID_OUTPUTS)
 
-    def step():
-        r = E.trace_grid(tab, grid, res=res)
-        if world > 1:
-            r.summary = P.gather_summaries(r.summary)
-        return r
+    def trace():
+        return E.trace_grid(tab, grid, c0, c1, res=res)
 
     def barrier():
         if world > 1:
@@ -348,13 +432,16 @@ def run_b200(args):
     sampler = ClockSampler(local) if rank == 0 else None
     n_warm = max(args.warmup, 3)
     for _ in range(n_warm):             # W warm-up steps: SAME count on every rank (each
-        step()                          # step holds a collective)
+        r = trace()                     # step holds a collective)
+        if world > 1:
+            P.gather_summaries(r.summary)
     torch.cuda.synchronize()
+    step_est = None
     t_w, extra = time.perf_counter(), 0
     while time.perf_counter() - t_w < 0.7:
-        E.trace_grid(tab, grid, res=res)    # collective-free extra warm-up, long enough for the
+        trace()                             # collective-free extra warm-up, long enough for the
         extra += 1                          # clocks to ramp and nvidia-smi to sample under load
-        if extra % 16 == 0:
+        if extra % 16 == 0 or n_mine > (1 << 24):
             torch.cuda.synchronize()
     barrier()
     launches0 = E.launch_count()
@@ -364,14 +451,14 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     e_first.record()
-    pending = None
+    pending, combined = None, None
     for k in range(args.steps):
         ev[k][0].record()
-        E.trace_grid(tab, grid, res=res)          # dominant kernel, bracketed for the roofline
+        trace()                                   # dominant kernel (+ its spot-sum reduction)
         ev[k][1].record()
         if world > 1:
-            # the all-gather of step k overlaps the trace of step k+1 (NCCL stream);
-            # every step's combined summary is materialised before the region ends
+            # all-gather + one-launch combine of step k run on a side stream while step k+1
+            # traces; every step's combined summary exists before the region ends
             if pending is not None:
                 combined = pending.result()
             pending = P.gather_summaries(res.summary, async_op=True)
@@ -383,38 +470,45 @@ def run_b200(args):
     launches = E.launch_count() - launches0
     dev_ms = e_first.elapsed_time(e_last)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    t = torch.tensor([dev_ms, wall*1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, wall*1e3, kern_ms], dtype=torch.float64, device=dev)
+    tmin = t.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    imbalance = {'kernel_ms_max_over_ranks': float(t[2]), 'kernel_ms_min_over_ranks': float(tmin[2])}
 
     # ---- end to end through the public API, host buffers both sides
     e2e = None
     if not args.no_e2e:
-        pinned = {'abr': torch.empty((2, n_rays), dtype=torch.float64).pin_memory(),
-                  'status': torch.empty(n_rays, dtype=torch.int32).pin_memory()}
+        pinned = {'abr': torch.empty((2, n_mine), dtype=torch.float64).pin_memory()}
+        kw = dict(table=tab, pinned=pinned)
+        if shard:
+            kw['shard'] = (rank, world)
         for _ in range(3):
-            sd = A.spot_diagram(opm, args.num, table=tab, pinned=pinned)
+            sd = A.spot_diagram(opm, args.num, **kw)
         barrier()
         t1 = time.perf_counter()
         for _ in range(args.steps):
-            sd = A.spot_diagram(opm, args.num, table=tab, pinned=pinned)
-            if world > 1:
+            sd = A.spot_diagram(opm, args.num, **kw)
+            if world > 1 and not shard:
                 P.gather_summaries(res.summary)
         barrier()
         e2e_s = time.perf_counter() - t1
         te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {'value': world*n_rays*args.steps/float(te[0]), 'unit': UNIT,
+        e2e = {'value': n_job*args.steps/float(te[0]), 'unit': UNIT,
                'h2d_bytes_per_step': int(sd.io_bytes['h2d']),
                'd2h_bytes_per_step': int(sd.io_bytes['d2h']),
-               'api': 'rayoptics_b200.analyses.spot_diagram(opt_model, 512): grid spec from host, '
-                      'aberrations + status into pinned host memory'}
+               'api': f'rayoptics_b200.analyses.spot_diagram(opt_model, {args.num}): grid description from '
+                      'host memory every call (pinned staging, one async copy), chief-ray reference points '
+                      'on the device, aberrations into pinned host memory at 16 B/ray (status / failing '
+                      'surface in the NaN payloads), per-(field,wvl) statistics'}
 
     # ---- second regime (reported, not the headline): whole rays written, HBM-bound
     full_ray = None
-    if rank == 0 and world == 1 and not args.no_e2e:
+    if rank == 0 and world == 1 and not args.no_e2e and grid.n_rays*tab.n_ifc*80 < 40e9:
         resf = E.BundleResult(grid.n_rays, tab.n_ifc, dev, ('status', 'n_seg', 'full'))
         for _ in range(3):
             E.trace_grid(tab, grid, res=resf, summary=False)
@@ -431,14 +525,18 @@ def run_b200(args):
         full_bytes = n_seg*80 + grid.n_rays*8
         full_ray = {'ms_per_step': ms, 'rays_per_s': grid.n_rays/(ms*1e-3),
                     'bytes_per_step': int(full_bytes), 'achieved_gbs': full_bytes/(ms*1e-3)/1e9,
-                    'kernel': 'k_trace_grid_lean<2,0>',
+                    'kernel': kernel_name(tab.descs).replace('<0,1', '<2,0'),
                     'note': 'every ray segment [p,d,dst,nrml] of every interface written (80 B each)'}
         del resf
     clocks = sampler.stop() if sampler else None   # window: warm-up + timed steps + e2e steps
+    # algorithmic flops of this rank's rays (failing-surface histogram of the run), summed over ranks
+    status = res.status.cpu().numpy()
+    fail_surf = res.fail_surf.cpu().numpy()
+    flops, flops_full_ray = algorithmic_flops(tab.descs, status, fail_surf)
+    fl = torch.tensor([flops, float((status == 0).sum()), float(status.size)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
     if rank == 0:
-        status = res.status.cpu().numpy()
-        fail_surf = res.fail_surf.cpu().numpy()
-        flops, flops_full_ray = algorithmic_flops(tab.descs, status, fail_surf)
         fp64_peak = E.measure_fp64_peak(local)
         bpr = res.bytes_per_ray()
         peaks = {}
@@ -448,41 +546,45 @@ def run_b200(args):
             pass
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
         traffic, ncu = None, {}
-        try:     # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
-            if args.model == 'dblgauss' and args.num == 512:
-                ncu = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_dblgauss_512.json')))
-                traffic = ncu['dram_bytes_per_launch']
+        try:     # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+            ncu = json.load(open(os.path.join(ROOT, 'profiles', f'traffic_{args.model}_{args.num}.json')))
+            traffic = ncu['dram_bytes_per_launch']
         except Exception:
             pass
-        ach_gbs = n_rays*bpr/(kern_ms*1e-3)/1e9
+        # the dominant kernel of THIS rank: its rays, its launch duration
         ach_tf = flops/(kern_ms*1e-3)/1e12
-        roof = {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': ach_gbs/hbm_peak,
-                'peak_source': 'MEASURED_PEAKS.json (of measured)' if 'hbm_gbs' in peaks
-                else 'B200_PROFILING.md fallback (of fallback)',
-                'traffic': traffic, 'bytes_per_ray': bpr, 'kernel': 'k_trace_grid_lean<0,1>',
-                'kernel_ms': kern_ms,
-                'limiter': 'fp64 vector pipe (kernel is register-resident; HBM only receives results)',
-                'fp64': {'achieved_tflops': ach_tf, 'peak_tflops': fp64_peak,
-                         'frac': ach_tf/fp64_peak if fp64_peak else None,
-                         'peak_source': 'rt_measure_fp64_peak: DFMA chain microbenchmark, this run',
-                         'pipe_utilisation_ncu': (None if ncu.get('fp64_pipe_pct_of_peak') is None
-                                                  else ncu['fp64_pipe_pct_of_peak']/100),
-                         'issue_active_ncu': (None if ncu.get('issue_active_pct') is None
-                                              else ncu['issue_active_pct']/100),
-                         'ncu_source': ncu.get('source'),
-                         'algorithmic_flop_per_full_ray': flops_full_ray,
-                         'algorithmic_flop_per_step': flops}}
-        line = {'metric': METRIC, 'value': world*n_rays*args.steps/(dev_ms_max*1e-3), 'unit': UNIT,
+        ach_gbs = n_mine*bpr/(kern_ms*1e-3)/1e9
+        roof = {'bound': 'fp64', 'achieved': ach_tf, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                'frac': ach_tf/fp64_peak if fp64_peak else None,
+                'peak_source': 'rt_measure_fp64_peak: DFMA chain microbenchmark on this GPU, this run '
+                               '(MEASURED_PEAKS.json holds no fp64 entry)',
+                'kernel': kernel_name(tab.descs), 'kernel_ms': kern_ms,
+                'rays_per_launch': int(n_mine),
+                'algorithmic_flop_per_launch': flops,
+                'algorithmic_flop_per_full_ray': flops_full_ray,
+                'traffic': traffic, 'traffic_source': ncu.get('source'),
+                'pipe_utilisation_ncu': (None if ncu.get('fp64_pipe_pct_of_peak') is None
+                                         else ncu['fp64_pipe_pct_of_peak']/100),
+                'issue_active_ncu': (None if ncu.get('issue_active_pct') is None
+                                     else ncu['issue_active_pct']/100),
+                'hbm': {'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs/hbm_peak,
+                        'bytes_per_ray': bpr,
+                        'peak_source': 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks
+                        else 'B200_PROFILING.md fallback'},
+                'why_fp64': 'register-resident trace: no HBM input, 80 B/ray of results; the kernel is bound '
+                            'by the fp64 vector pipe / issue (DESIGN.md 5), HBM is the secondary figure'}
+        line = {'metric': METRIC, 'value': n_job*args.steps/(dev_ms_max*1e-3), 'unit': UNIT,
                 'n_gpus': world, 'steps': args.steps, 'warmup': n_warm, 'extra_warmup_traces': extra,
                 'ms_per_step': dev_ms_max/args.steps, 'wall_ms_per_step': wall_ms_max/args.steps,
-                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                'higher_is_better': True, 'scaling': 'strong' if shard else 'weak',
+                'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic', 'config': config_dict(args, opm, grid, world),
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
+                'rank_imbalance': imbalance if world > 1 else None,
                 'full_ray_regime': None if full_ray is None else dict(
                     full_ray, frac_of_hbm_peak=full_ray['achieved_gbs']/hbm_peak),
-                'rays_ok_frac': float((status == 0).mean())}
-        try:      # the same model at 24x24 against rays traced by the REFERENCE's own grid loop
+                'rays_ok_frac': float(fl[1]/fl[2])}
+        try:      # the same model at a reduced grid against rays traced by the REFERENCE's own grid loop
             line['parity_vs_reference'] = parity_vs_reference_golden(args.model, opm, tab)
         except Exception as e:      # noqa: BLE001 - never lose the bench line over a checker
             line['parity_vs_reference'] = {'error': repr(e)}
@@ -490,7 +592,7 @@ def run_b200(args):
             def gpu_records(r0, r1):
                 return {k: getattr(res, k)[..., r0:r1].cpu().numpy()
                         for k in ('p', 'd', 'op', 'abr', 'status', 'fail_surf')}
-            line['cpu_baseline'] = cpu_baseline(opm, args.num, gpu=gpu_records)
+            line['cpu_baseline'] = cpu_baseline(args, opm, gpu=gpu_records)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

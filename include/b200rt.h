@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 2
+#define RT_ABI_VERSION 3
 #define RT_MAX_COEFS 20     /* EvenPolynomial uses <=10, RadialPolynomial <=20 */
 #define RT_MAX_PHASE_COEFS 10
 #define RT_MAX_APERTURES 4  /* Surface.clear_apertures entries honoured per interface */
@@ -186,7 +186,17 @@ typedef struct rt_out {
      * with rt_grid_spec.wave): wave_abr_full_calc_finite_pup, raytr/waveabr.py:255-305.
      * System units (mm); NaN for rays that do not reach the image. */
     double *opd;
+    /* RT_OUT_* bits */
+    int32_t flags;
+    int32_t pad_;
 } rt_out;
+
+/* rt_out.flags */
+#define RT_OUT_ABR_NAN_STATUS 1  /* grid traces: rays that do not reach the image get abr_x = quiet NaN
+                                    whose low mantissa bits hold rt_status and abr_y = quiet NaN whose low
+                                    bits hold fail_surf, so a consumer that only reads abr_x/abr_y (16 B/ray
+                                    instead of 20) still gets both: status = isnan(x) ? bits(x) & 0xFFFF : 0 */
+#define RT_NAN_PAYLOAD_BASE 0x7FF8000000000000ull
 
 typedef struct rt_table rt_table;
 typedef struct rt_grid rt_grid;
@@ -234,7 +244,8 @@ typedef struct rt_grid_spec {
     const int32_t *wvl_idx;    /* HOST [n_wvls] rows of the table's n_by_wvl */
     const double *pupil_x;     /* HOST [n_fields][nx] relative pupil x before vignetting */
     const double *pupil_y;     /* HOST [n_fields][ny] */
-    const double *ref_img;     /* HOST [n_fields][n_wvls][2] reference image point (ref_sphere[0]) or NULL (=0) */
+    const double *ref_img;     /* HOST [n_fields][n_wvls][2] reference image point (ref_sphere[0]) or NULL (=0;
+                                  rt_grid_chief_ref() can fill it on the device afterwards) */
     const double *wave;        /* HOST [n_fields][n_wvls][RT_WAVE_DOUBLES] or NULL.  Chief ray and reference
                                   sphere of each tile, what wave_abr_full_calc_finite_pup reads
                                   (raytr/waveabr.py:255-305, 24-76, 79-113):
@@ -260,6 +271,12 @@ typedef struct rt_grid_spec {
 
 int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out);
 int rt_grid_destroy(rt_grid *grid);
+/* Replace the contents of `grid` by another description of the SAME shape (n_fields, n_wvls,
+ * nx, ny, paired, wave present or not): one asynchronous host->device copy on `stream` from
+ * the handle's pinned staging block, no allocation.  `spec` is read before the call returns;
+ * launches on `stream` issued afterwards see the new description (launches on other streams
+ * must be ordered after it by the caller). */
+int rt_grid_update(rt_grid *grid, const rt_grid_spec *spec, void *stream);
 /* total rays and the chunk geometry used for sharding / summaries */
 int rt_grid_dims(const rt_grid *grid, int64_t *n_rays, int64_t *n_chunks, int32_t *chunk_rays);
 
@@ -278,6 +295,23 @@ int rt_trace_grid(const rt_table *table, const rt_grid *grid,
                   int64_t chunk_begin, int64_t chunk_end,
                   const rt_opts *opts, const rt_out *out,
                   double *summary, void *scratch, void *stream);
+
+/* Reference image points without a host round trip: trace the (0, 0) pupil ray of every
+ * field at row `wvl_idx` of the table (no vignetting, apertures not checked) and store its
+ * image intercept (x, y) as the reference image point of every (field, wvl) tile of `grid` --
+ * ref_sphere[0] of calculate_reference_sphere for image_pt_2d=None (raytr/waveabr.py:24-76,
+ * raytr/trace.py:627-687 without the re-aiming).  One small launch on `stream`; later
+ * rt_trace_grid calls on the same stream see the new points.  ref_out: DEVICE [n_fields][2]
+ * or NULL, receives a copy. */
+int rt_grid_chief_ref(const rt_table *table, rt_grid *grid, int32_t wvl_idx,
+                      double *ref_out, void *stream);
+
+/* Combine n_parts partial summaries (chunk ranges of one grid, or the ranks' rows of an
+ * all-gather): parts DEVICE [n_parts][n_tiles][RT_SUMMARY_DOUBLES] -> out DEVICE
+ * [n_tiles][RT_SUMMARY_DOUBLES]; sums add in part order, the min / max columns take
+ * min / max.  One launch on `stream`. */
+int rt_combine_summaries(const double *parts, int32_t n_parts, int64_t n_tiles,
+                         double *out, void *stream);
 
 /* ---- misc */
 const char *rt_last_error(void);

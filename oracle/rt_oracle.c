@@ -1000,4 +1000,95 @@ int rto_trace_grid(const rt_grid_spec *g, const rt_surface_desc *surfs, int32_t 
     return 0;
 }
 
+/* ---- the same grid trace on a PERSISTENT thread pool with dynamic scheduling: bench.py's CPU
+ * arm.  rto_trace_grid() above creates and joins its threads on every call and splits the
+ * rays statically, which under-uses the host (clipped rays end early: the blocks are uneven);
+ * here the workers live across calls and pull blocks of `block` rays from a shared counter. */
+typedef struct {
+    pthread_mutex_t mu;
+    pthread_cond_t go, done;
+    pthread_t *tids;
+    int n_threads, generation, running, quit;
+    grid_job job;                 /* r0/r1 unused: blocks come from `next` */
+    int64_t ray_end, block;
+    volatile int64_t next;
+} rto_pool;
+
+static rto_pool *g_pool = NULL;
+
+static void *pool_worker(void *arg)
+{
+    rto_pool *P = (rto_pool *)arg;
+    int seen = 0;
+    for (;;) {
+        pthread_mutex_lock(&P->mu);
+        while (P->generation == seen && !P->quit) pthread_cond_wait(&P->go, &P->mu);
+        if (P->quit) { pthread_mutex_unlock(&P->mu); return NULL; }
+        seen = P->generation;
+        pthread_mutex_unlock(&P->mu);
+        for (;;) {
+            int64_t b = __atomic_fetch_add(&P->next, P->block, __ATOMIC_RELAXED);
+            if (b >= P->ray_end) break;
+            grid_job J = P->job;
+            J.r0 = b; J.r1 = b + P->block < P->ray_end ? b + P->block : P->ray_end;
+            grid_worker(&J);
+        }
+        pthread_mutex_lock(&P->mu);
+        if (--P->running == 0) pthread_cond_signal(&P->done);
+        pthread_mutex_unlock(&P->mu);
+    }
+}
+
+int rto_pool_destroy(void)
+{
+    rto_pool *P = g_pool;
+    if (!P) return 0;
+    pthread_mutex_lock(&P->mu);
+    P->quit = 1;
+    pthread_cond_broadcast(&P->go);
+    pthread_mutex_unlock(&P->mu);
+    for (int t = 0; t < P->n_threads; t++) pthread_join(P->tids[t], NULL);
+    free(P->tids); free(P);
+    g_pool = NULL;
+    return 0;
+}
+
+int rto_pool_create(int32_t n_threads)
+{
+    if (g_pool && g_pool->n_threads == n_threads) return 0;
+    rto_pool_destroy();
+    if (n_threads < 1) n_threads = 1;
+    rto_pool *P = (rto_pool *)calloc(1, sizeof *P);
+    if (!P) return -1;
+    pthread_mutex_init(&P->mu, NULL);
+    pthread_cond_init(&P->go, NULL);
+    pthread_cond_init(&P->done, NULL);
+    P->n_threads = n_threads;
+    P->tids = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    for (int t = 0; t < n_threads; t++) pthread_create(&P->tids[t], NULL, pool_worker, P);
+    g_pool = P;
+    return 0;
+}
+
+/* as rto_trace_grid, on the pool created by rto_pool_create(); block: rays per work item */
+int rto_trace_grid_pool(const rt_grid_spec *g, const rt_surface_desc *surfs, int32_t n_ifc,
+                        const double *n_by_wvl, int64_t ray_begin, int64_t ray_end, const rt_opts *o,
+                        double *last, double *op, int32_t *status, int32_t *fail_surf,
+                        double *abr_x, double *abr_y, double *opd, const double *wvl_nm, int64_t block)
+{
+    rto_pool *P = g_pool;
+    if (!P) return -1;
+    grid_job J = {g, surfs, n_ifc, n_by_wvl, o, ray_begin, ray_end - ray_begin, 0, 0, last, op, abr_x, abr_y,
+                  (opd && g->wave) ? opd : NULL, status, fail_surf, wvl_nm};
+    pthread_mutex_lock(&P->mu);
+    P->job = J; P->ray_end = ray_end; P->block = block < 64 ? 64 : block;
+    P->next = ray_begin;
+    P->running = P->n_threads;
+    P->generation++;
+    pthread_cond_broadcast(&P->go);
+    while (P->running > 0) pthread_cond_wait(&P->done, &P->mu);
+    pthread_mutex_unlock(&P->mu);
+    return 0;
+}
+
 int rto_sizeof_surface_desc(void) { return (int)sizeof(rt_surface_desc); }

@@ -132,3 +132,40 @@ def wave_opd(W, p1, d0, pk, dk, ray_op, pl=None, dl=None):
         pl, dl = np.zeros(3), np.zeros(3)
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (W, p1, d0, pk, dk, pl, dl)]
     return f(*[_dp(a) for a in arrs], C.c_double(ray_op))
+
+
+class GridRunner:
+    """bench.py's CPU arm: the whole-grid trace on a persistent pthread pool with dynamic
+    scheduling and output buffers that are allocated (and first touched) once, so that a timed
+    call is nothing but ``rto_trace_grid_pool``."""
+
+    def __init__(self, spec, descs, n_by_wvl, opts, n_rays_max, n_threads, block=2048):
+        self.spec, self.descs, self.opts = spec, descs, opts
+        self.c_spec = spec.c_spec() if hasattr(spec, 'c_spec') else spec
+        self.n_by_wvl = np.ascontiguousarray(n_by_wvl, dtype=np.float64)
+        self.n_threads, self.block = int(n_threads), int(block)
+        n = int(n_rays_max)
+        self.op = np.ones(n)
+        self.status = np.ones(n, dtype=np.int32)
+        self.fail_surf = np.ones(n, dtype=np.int32)
+        self.ax, self.ay = np.ones(n), np.ones(n)
+        lib().rto_pool_create(C.c_int32(self.n_threads))
+
+    def run(self, ray_begin, ray_end):
+        """trace rays [ray_begin, ray_end) into the buffers; returns seconds inside the C call"""
+        import time
+        n = ray_end - ray_begin
+        assert n <= self.op.shape[0]
+        L = lib()
+        t0 = time.perf_counter()
+        rc = L.rto_trace_grid_pool(C.byref(self.c_spec), self.descs, C.c_int32(len(self.descs)),
+                                   _dp(self.n_by_wvl), C.c_int64(ray_begin), C.c_int64(ray_end),
+                                   C.byref(self.opts), None, _dp(self.op), _ip(self.status),
+                                   _ip(self.fail_surf), _dp(self.ax), _dp(self.ay), None, None,
+                                   C.c_int64(self.block))
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        return dt
+
+    def close(self):
+        lib().rto_pool_destroy()

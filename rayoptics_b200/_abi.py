@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-RT_ABI_VERSION = 2
+RT_ABI_VERSION = 3
 RT_MAX_COEFS = 20
 RT_MAX_PHASE_COEFS = 10
 RT_MAX_APERTURES = 4
@@ -69,7 +69,12 @@ class rt_out(C.Structure):
                 ('dst', C.c_void_p), ('op', C.c_void_p),
                 ('status', C.c_void_p), ('fail_surf', C.c_void_p), ('n_seg', C.c_void_p),
                 ('full', C.c_void_p), ('full_stride', C.c_int64),
-                ('abr_x', C.c_void_p), ('abr_y', C.c_void_p), ('opd', C.c_void_p)]
+                ('abr_x', C.c_void_p), ('abr_y', C.c_void_p), ('opd', C.c_void_p),
+                ('flags', C.c_int32), ('pad_', C.c_int32)]
+
+
+RT_OUT_ABR_NAN_STATUS = 1
+RT_NAN_PAYLOAD_BASE = 0x7FF8000000000000
 
 
 class rt_field_desc(C.Structure):
@@ -107,7 +112,8 @@ def make_opts(eps=1.0e-12, check_apertures=False, intersect_obj=True,
 LIB_NAME = 'libb200rt.so'
 EXPORTS = ['rt_table_create', 'rt_table_destroy', 'rt_table_dims', 'rt_table_set_wavelengths',
            'rt_trace_bundle', 'rt_grid_create', 'rt_grid_destroy', 'rt_grid_dims',
-           'rt_grid_scratch_bytes', 'rt_trace_grid',
+           'rt_grid_scratch_bytes', 'rt_trace_grid', 'rt_grid_chief_ref', 'rt_combine_summaries',
+           'rt_grid_update',
            'rt_last_error', 'rt_abi_version', 'rt_launch_count', 'rt_measure_fp64_peak',
            'rt_selftest_division']
 
@@ -154,6 +160,12 @@ def load_library():
     lib.rt_grid_scratch_bytes.restype = i64
     lib.rt_trace_grid.argtypes = [vp, vp, i64, i64, C.POINTER(rt_opts), C.POINTER(rt_out),
                                   vp, vp, vp]
+    lib.rt_grid_update.argtypes = [vp, C.POINTER(rt_grid_spec), vp]
+    lib.rt_grid_update.restype = i32
+    lib.rt_grid_chief_ref.argtypes = [vp, vp, i32, vp, vp]
+    lib.rt_grid_chief_ref.restype = i32
+    lib.rt_combine_summaries.argtypes = [vp, i32, i64, vp, vp]
+    lib.rt_combine_summaries.restype = i32
     lib.rt_last_error.restype = C.c_char_p
     lib.rt_abi_version.restype = i32
     lib.rt_launch_count.restype = i64

@@ -28,29 +28,45 @@ from .opticalspec import grid_fields_of
 class SpotDiagram:
     """Result of ``spot_diagram``.
 
-    ``abr`` ``[2, n]`` / ``status`` ``[n]``: host (pinned) arrays over the rays
-    this process traced, flattened (field, wvl, i, j) order starting at
-    ``first_ray``; ``grids[fi][wi]``: ``[n_ok, 2]`` arrays of the rays that reach
-    the image, in the reference's order (x outer, y inner) -- the ``form='list',
-    append_if_none=False`` shape of seq/sequential.py:1058-1085 -- built lazily
-    (whole grid only); ``summary``: dict of ``[n_fields, n_wvls]`` arrays (n_ok,
-    n_blocked, centroid_x/y, rms_radius ...), combined over all ranks;
-    ``ref_img``: ``[n_fields, 2]`` chief-ray image points."""
+    ``abr`` ``[2, n]``: host (pinned) array over the rays this process traced, flattened
+    (field, wvl, i, j) order starting at ``first_ray``; rays that do not reach the image
+    hold NaNs whose payloads are their status / failing surface (``status``, ``fail_surf``
+    decode them on first use).  ``grids[fi][wi]``: ``[n_ok, 2]`` arrays of the rays that
+    reach the image, in the reference's order (x outer, y inner) -- the ``form='list',
+    append_if_none=False`` shape of seq/sequential.py:1058-1085 -- built lazily (whole grid
+    only); ``summary``: dict of ``[n_fields, n_wvls]`` arrays (n_ok, n_blocked,
+    centroid_x/y, rms_radius ...), combined over all ranks; ``ref_img``: ``[n_fields, 2]``
+    chief-ray image points."""
 
     def __init__(self, abr, status, summary, ref_img, num_rays, n_fields, n_wvls, first_ray,
                  n_rays_total, io_bytes):
-        self.abr, self.status, self.summary, self.ref_img = abr, status, summary, ref_img
+        self.abr, self._status, self.summary, self.ref_img = abr, status, summary, ref_img
+        self._fail_surf = None
         self.num_rays, self.n_fields, self.n_wvls = num_rays, n_fields, n_wvls
         self.first_ray, self.n_rays_total = first_ray, n_rays_total
         self.io_bytes = io_bytes            # {'h2d': ..., 'd2h': ...} of this call
         self._grids = None
 
+    def _decode(self):
+        if self._status is None:
+            self._status, self._fail_surf = E.decode_nan_status(self.abr)
+
+    @property
+    def status(self):
+        self._decode()
+        return self._status
+
+    @property
+    def fail_surf(self):
+        self._decode()
+        return self._fail_surf
+
     @property
     def grids(self):
         if self._grids is None:
-            if self.first_ray != 0 or self.status.shape[0] != self.n_rays_total:
+            if self.first_ray != 0 or self.abr.shape[1] != self.n_rays_total:
                 raise ValueError('per-tile lists need the whole grid on one process')
-            ok = self.status == 0
+            ok = (self._status == 0) if self._status is not None else ~np.isnan(self.abr[0])
             per = self.num_rays*self.num_rays
             self._grids = []
             for fi in range(self.n_fields):
@@ -64,12 +80,31 @@ class SpotDiagram:
 
 
 _STREAMS = {}
+_GRIDS = {}          # shape key -> PupilGrid whose device block / pinned staging is re-used
 
 
 def _side_streams(dev):
     if dev not in _STREAMS:
         _STREAMS[dev] = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
     return _STREAMS[dev]
+
+
+def _reusable_grid(args, kw, device):
+    """A PupilGrid for this description: the first call of a given shape allocates
+    (``rt_grid_create``), later calls re-upload into the same device block with one
+    asynchronous copy (``rt_grid_update``) -- no cudaMalloc / cudaFree per analysis call."""
+    spec = E.PupilGridSpec(*args, **kw)
+    key = (int(device), spec.n_fields, spec.n_wvls, spec.nx, spec.ny, spec.paired, spec.wave is not None)
+    grid = _GRIDS.get(key)
+    if grid is None or grid._handle is None:
+        if len(_GRIDS) > 16:
+            for g in _GRIDS.values():
+                g.close()
+            _GRIDS.clear()
+        grid = _GRIDS[key] = E.PupilGrid(*args, device=device, **kw)
+    else:
+        grid.update(*args, **kw)
+    return grid
 
 
 def _table_for(opt_model, table=None, device=0):
@@ -113,17 +148,18 @@ def chief_ray_image_points(opt_model, table, fields, wvl=None, foc=0.0, io=None)
 
 def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table=None,
                  device=0, pinned=None, shard=None, group=None, pieces=4, **kwargs):
-    """Spot diagrams of all fields and wavelengths in one launch.
+    """Spot diagrams of all fields and wavelengths in one pass over the device.
 
-    Host buffers in, host buffers out: the grid description goes to the device
-    (``rt_grid_create``), ``rt_trace_grid`` generates and traces the rays, and
-    the transverse aberrations + status come back into pinned host memory.
-    ``shard=(rank, world)`` traces only that rank's slice of the chunk space and
-    all-gathers the per-(field, wvl) sums over ``group`` (parallel.py).
-    ``pinned``: optional dict of pinned host tensors ``abr`` ``[2, >=n]`` and
-    ``status`` ``[>=n]`` to re-use across calls.  ``pieces``: the chunk range is
-    traced in that many launches on two streams so that the device->host copy of
-    one piece overlaps the trace of the next."""
+    Host buffers in, host buffers out: the grid description goes to the device (one
+    asynchronous copy into a re-used block), the chief-ray reference image points are
+    computed there (``rt_grid_chief_ref``: no host round trip), ``rt_trace_grid`` generates
+    and traces the rays, and the transverse aberrations come back into pinned host memory,
+    16 B per ray (status / failing surface of the rays that do not arrive ride in the NaN
+    payloads).  ``shard=(rank, world)`` traces only that rank's slice of the chunk space and
+    all-gathers the per-(field, wvl) sums over ``group`` (parallel.py).  ``pinned``:
+    optional dict with a pinned host tensor ``abr`` ``[2, >=n]`` to re-use across calls.
+    ``pieces``: the chunk range is traced in that many launches on two streams so that the
+    device->host copy of one piece overlaps the trace of the next."""
     from .parallel import shard_chunks, gather_summaries
     osp, sm = opt_model.optical_spec, opt_model.seq_model
     table = _table_for(opt_model, table, device)
@@ -131,49 +167,48 @@ def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table
     wvls = list(sm.wvlns if wvls is None else wvls)
     foc = osp.defocus.focus_shift if foc is None else foc
     io = {'h2d': 0, 'd2h': 0}
-    ref = chief_ray_image_points(opt_model, table, fields, foc=foc, io=io)
-    ref_fw = np.repeat(ref[:, None, :], len(wvls), axis=1)
-    grid = E.grid_for_model(opt_model, table, num_rays, fields=fields, wvls=wvls, foc=foc,
-                            ref_img=ref_fw)
-    io['h2d'] += grid.host_bytes()
-    c0, c1 = (0, grid.n_chunks) if shard is None else shard_chunks(grid.n_chunks, *shard)
-    n = grid.rays_in_chunks(c0, c1)
-    if pinned is None:
-        pinned = {'abr': torch.empty((2, n), dtype=torch.float64).pin_memory(),
-                  'status': torch.empty(n, dtype=torch.int32).pin_memory()}
-    h_abr, h_status = pinned['abr'][:, :n], pinned['status'][:n]
-    # pipeline: the device->host copy of piece i overlaps the trace of piece i+1
-    n_pieces = max(1, min(pieces, (c1 - c0)//64))
-    cuts = [c0 + (c1 - c0)*i//n_pieces for i in range(n_pieces + 1)]
     dev = torch.device('cuda', table.device)
-    main = torch.cuda.current_stream(dev)
-    streams = _side_streams(dev) if n_pieces > 1 else [main]
-    parts, keep, base = [], [], grid.first_ray_of_chunk(c0)
-    for i in range(n_pieces):
-        st = streams[i % len(streams)]
-        st.wait_stream(main)
-        with torch.cuda.stream(st):
-            r = E.trace_grid(table, grid, cuts[i], cuts[i + 1], outputs=('abr', 'status'), **kwargs)
-            a = grid.first_ray_of_chunk(cuts[i]) - base
-            h_abr[0, a:a + r.n].copy_(r.abr[0], non_blocking=True)
-            h_abr[1, a:a + r.n].copy_(r.abr[1], non_blocking=True)
-            h_status[a:a + r.n].copy_(r.status, non_blocking=True)
-        parts.append(r.summary)
-        keep.append(r)
-    for st in streams:
-        main.wait_stream(st)
-    res = keep[-1]
-    res.summary = parts[0] if n_pieces == 1 else E.combine_summaries(parts)
-    summ = res.summary if shard is None else gather_summaries(res.summary, group)
-    summ_host = summ.cpu().numpy()                  # one small copy; also waits for the stream
-    torch.cuda.current_stream(table.device).synchronize()
+    with torch.cuda.device(dev):
+        args, kw = E._grid_args(opt_model, table.wvl_index, num_rays, fields, wvls, foc, (-1.0, 1.0), True)
+        grid = _reusable_grid(args, kw, table.device)
+        io['h2d'] += grid.host_bytes()
+        ref_dev = torch.empty((len(fields), 2), dtype=torch.float64, device=dev)
+        grid.chief_ref(table, table.wvl_index(sm.central_wavelength()), out=ref_dev)
+        c0, c1 = (0, grid.n_chunks) if shard is None else shard_chunks(grid.n_chunks, *shard)
+        n = grid.rays_in_chunks(c0, c1)
+        if pinned is None:
+            pinned = {'abr': torch.empty((2, max(n, 1)), dtype=torch.float64).pin_memory()}
+        h_abr = pinned['abr'][:, :n]
+        # pipeline: the device->host copy of piece i overlaps the trace of piece i+1
+        n_pieces = max(1, min(pieces, (c1 - c0)//64))
+        cuts = [c0 + (c1 - c0)*i//n_pieces for i in range(n_pieces + 1)]
+        main = torch.cuda.current_stream(dev)
+        streams = _side_streams(dev) if n_pieces > 1 else [main]
+        parts, keep, base = [], [], grid.first_ray_of_chunk(c0)
+        for i in range(n_pieces):
+            st = streams[i % len(streams)]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                r = E.trace_grid(table, grid, cuts[i], cuts[i + 1], outputs=('abr',), nan_status=True,
+                                 **kwargs)
+                a = grid.first_ray_of_chunk(cuts[i]) - base
+                h_abr[:, a:a + r.n].copy_(r.abr, non_blocking=True)
+            parts.append(r.summary)
+            keep.append(r)
+        for st in streams:
+            main.wait_stream(st)
+        summ = parts[0] if n_pieces == 1 else E.combine_summaries(parts)
+        if shard is not None:
+            summ = gather_summaries(summ, group)
+        tail = torch.cat([summ.reshape(-1), ref_dev.reshape(-1)]).cpu().numpy()   # one small copy; waits
+        main.synchronize()
+    summ_host = tail[:summ.numel()].reshape(summ.shape)
+    ref = tail[summ.numel():].reshape(len(fields), 2).copy()
     stats_host = {k: np.asarray(v).reshape(len(fields), len(wvls))
                   for k, v in E.spot_statistics(summ_host).items()}
-    io['d2h'] += h_abr.numel()*8 + h_status.numel()*4 + sum(v.nbytes for v in stats_host.values())
-    out = SpotDiagram(h_abr.numpy(), h_status.numpy(), stats_host, ref, num_rays, len(fields),
-                      len(wvls), grid.first_ray_of_chunk(c0), grid.n_rays, io)
-    grid.close()
-    return out
+    io['d2h'] += h_abr.numel()*8 + tail.nbytes
+    return SpotDiagram(h_abr.numpy(), None, stats_host, ref, num_rays, len(fields), len(wvls),
+                       grid.first_ray_of_chunk(c0), grid.n_rays, io)
 
 
 # --------------------------------------------------------------------------

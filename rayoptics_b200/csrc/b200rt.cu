@@ -97,6 +97,10 @@ struct rt_grid {
     double *d_pupil_x, *d_pupil_y, *d_ref_img, *d_wave;
     void *d_block;           /* the one device allocation the pointers above point into */
     int64_t rays_per_tile, chunks_per_tile, n_tiles, n_chunks, n_rays;
+    std::vector<int32_t> h_wvl_idx;   /* host copy: range-checked against the table in rt_trace_grid */
+    unsigned char *h_stage;           /* pinned image of d_block */
+    cudaEvent_t uploaded;             /* last rt_grid_update copy */
+    size_t b_fields, b_px, b_py, b_ref, b_wave, o_fields, o_px, o_py, o_ref, o_wave, o_wvl, total;
 };
 
 /* what the grid kernel needs, passed by value */
@@ -299,7 +303,14 @@ __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_
                 double dist = div_maybe_zero(G.foc, R.d.z);
                 ax = (R.p.x + dist*R.d.x) - rx;
                 ay = (R.p.y + dist*R.d.y) - ry;
-                if (out.abr_x) { out.abr_x[k] = ax; out.abr_y[k] = ay; }
+                if (out.abr_x) {
+                    double sx = ax, sy = ay;
+                    if ((out.flags & RT_OUT_ABR_NAN_STATUS) && status != RT_RAY_OK) {
+                        sx = __longlong_as_double((long long)(RT_NAN_PAYLOAD_BASE | (unsigned long long)(status & 0xFFFF)));
+                        sy = __longlong_as_double((long long)(RT_NAN_PAYLOAD_BASE | (unsigned long long)(R.fail_surf & 0xFFFF)));
+                    }
+                    out.abr_x[k] = sx; out.abr_y[k] = sy;
+                }
                 if (SUMMARY && !chunk_slots) acc_add(acc, status, ax, ay, op);
             }
         }
@@ -500,6 +511,49 @@ k_reduce_summary(const double *__restrict__ scratch, int64_t recs_per_tile, doub
     }
 }
 
+/* summary of an empty chunk range: zero counts / sums, identities in the min / max columns */
+__global__ void k_summary_identity(double *__restrict__ summary, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = (int)(i % RT_SUMMARY_DOUBLES);
+    summary[i] = (k == 10 || k == 12) ? CUDART_INF : ((k == 11 || k == 13) ? -CUDART_INF : 0.0);
+}
+
+/* out[tile][k] = parts[0][tile][k] (+|min|max) parts[1][tile][k] ... in part order */
+__global__ void k_combine_summaries(const double *__restrict__ parts, int n_parts, int64_t n,
+                                    double *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = (int)(i % RT_SUMMARY_DOUBLES);
+    double v = parts[i];
+    for (int p = 1; p < n_parts; p++) v = red_op(k, v, parts[(int64_t)p*n + i]);
+    out[i] = v;
+}
+
+/* chief rays of all fields: pupil (0, 0), no vignetting, apertures not checked, general
+ * per-ray code on the global table (bit-identical to the lean loop by construction, and
+ * n_fields rays do not need the specialised kernel).  One thread per field. */
+__global__ void k_chief_ref(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
+                            int n_ifc, GridDev G, int n_fields, int pupil_kind, int wi,
+                            const double *__restrict__ g_wvl, rt_opts o, double *__restrict__ ref_img,
+                            double *__restrict__ ref_out)
+{
+    const int f = blockIdx.x*blockDim.x + threadIdx.x;
+    if (f >= n_fields) return;
+    Vec3 p0, d0;
+    grid_start_ray_at<false>(G, pupil_kind, f, 0.0, 0.0, false, p0, d0);
+    FullWriter fw = {nullptr, 0};
+    RayResult R;
+    trace_ray<false>(g_surfs, g_n + (int64_t)wi*n_ifc, g_wvl[wi], n_ifc, o, p0, d0, fw, R);
+    for (int w = 0; w < G.n_wvls; w++) {
+        ref_img[((int64_t)f*G.n_wvls + w)*2 + 0] = R.p.x;
+        ref_img[((int64_t)f*G.n_wvls + w)*2 + 1] = R.p.y;
+    }
+    if (ref_out) { ref_out[f*2 + 0] = R.p.x; ref_out[f*2 + 1] = R.p.y; }
+}
+
 /* fp64 FMA microbenchmark: 8 independent chains per thread */
 __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b)
 {
@@ -648,6 +702,18 @@ static int out_kind(const rt_out *out)
     return 0;
 }
 
+static GridDev grid_dev(const rt_grid *g)
+{
+    GridDev G;
+    G.n_wvls = g->n_wvls; G.nx = g->nx; G.ny = g->ny;
+    G.apply_vignetting = g->apply_vignetting; G.flip_z_dir = g->flip_z_dir; G.paired = g->paired;
+    G.eprad = g->eprad; G.z_pupil = g->z_pupil; G.foc = g->foc;
+    G.fields = g->d_fields; G.wvl_idx = g->d_wvl_idx;
+    G.pupil_x = g->d_pupil_x; G.pupil_y = g->d_pupil_y; G.ref_img = g->d_ref_img; G.wave = g->d_wave;
+    G.rays_per_tile = g->rays_per_tile; G.chunks_per_tile = g->chunks_per_tile;
+    return G;
+}
+
 /* ------------------------------------------------------------------ C ABI */
 extern "C" {
 
@@ -709,6 +775,8 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
         std::vector<double> nanv((size_t)n_wvl, (double)NAN);
         e = cudaMemcpy(t->d_wvl, nanv.data(), (size_t)n_wvl*sizeof(double), cudaMemcpyHostToDevice);
     }
+    /* pageable copies: see rt_grid_create */
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     if (e != cudaSuccess) {
         cudaFree(t->d_surfs); cudaFree(t->d_n); cudaFree(t->d_wvl); delete t;
         return fail(RT_ERR_CUDA, "rt_table_create: %s", cudaGetErrorString(e));
@@ -733,6 +801,7 @@ int rt_table_set_wavelengths(rt_table *t, const double *wvl_nm)
     if (!t || !wvl_nm) return fail(RT_ERR_INVALID, "rt_table_set_wavelengths: bad arguments");
     DeviceGuard guard(t->device);
     CUDA_TRY(cudaMemcpy(t->d_wvl, wvl_nm, (size_t)t->n_wvl*sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
     return RT_OK;
 }
 
@@ -777,29 +846,50 @@ int rt_grid_destroy(rt_grid *g)
 {
     if (!g) return RT_OK;
     DeviceGuard guard(g->device);
+    if (g->uploaded) { cudaEventSynchronize(g->uploaded); cudaEventDestroy(g->uploaded); }
     cudaFree(g->d_block);
+    cudaFreeHost(g->h_stage);
     delete g;
     return RT_OK;
 }
 
-/* All arrays of the description go to the device as ONE allocation and ONE copy
- * (host staging buffer): grids are created per analysis call, so the create /
- * destroy cost is on the end-to-end path. */
+static bool grid_spec_ok(const rt_grid_spec *spec)
+{
+    return spec && spec->n_fields >= 1 && spec->n_wvls >= 1 && spec->nx >= 1 && spec->ny >= 1 &&
+           spec->fields && spec->wvl_idx && spec->pupil_x && spec->pupil_y &&
+           !(spec->paired && spec->ny != 1) && spec->pupil_kind >= RT_PUPIL_EPD &&
+           spec->pupil_kind <= RT_PUPIL_FNO;
+}
+
+/* scalars of the description + the arrays into the pinned staging block (layout fixed at create) */
+static void grid_fill(rt_grid *g, const rt_grid_spec *spec)
+{
+    g->apply_vignetting = spec->apply_vignetting; g->flip_z_dir = spec->flip_z_dir;
+    g->pupil_kind = spec->pupil_kind;
+    g->eprad = spec->eprad; g->z_pupil = spec->z_pupil; g->foc = spec->foc;
+    unsigned char *st = g->h_stage;
+    memcpy(st + g->o_fields, spec->fields, g->b_fields);
+    memcpy(st + g->o_px, spec->pupil_x, g->b_px);
+    memcpy(st + g->o_py, spec->pupil_y, g->b_py);
+    if (spec->ref_img) memcpy(st + g->o_ref, spec->ref_img, g->b_ref);
+    else memset(st + g->o_ref, 0, g->b_ref);
+    if (g->b_wave) memcpy(st + g->o_wave, spec->wave, g->b_wave);
+    memcpy(st + g->o_wvl, spec->wvl_idx, (size_t)g->n_wvls*sizeof(int32_t));
+    g->h_wvl_idx.assign(spec->wvl_idx, spec->wvl_idx + g->n_wvls);
+}
+
+/* All arrays of the description live in ONE device allocation and travel as ONE copy from a
+ * pinned staging block owned by the handle; rt_grid_update() re-uses both, so an analysis that
+ * is called repeatedly pays one small asynchronous copy per call and no allocation. */
 int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out)
 {
-    if (!spec || !out || spec->n_fields < 1 || spec->n_wvls < 1 || spec->nx < 1 || spec->ny < 1 ||
-        !spec->fields || !spec->wvl_idx || !spec->pupil_x || !spec->pupil_y ||
-        (spec->paired && spec->ny != 1) || spec->pupil_kind < RT_PUPIL_EPD ||
-        spec->pupil_kind > RT_PUPIL_FNO)
-        return fail(RT_ERR_INVALID, "rt_grid_create: bad arguments");
+    if (!grid_spec_ok(spec) || !out) return fail(RT_ERR_INVALID, "rt_grid_create: bad arguments");
     DeviceGuard guard(device);
     rt_grid *g = new (std::nothrow) rt_grid();
     if (!g) return fail(RT_ERR_NOMEM, "rt_grid_create: out of host memory");
     g->device = device;
     g->n_fields = spec->n_fields; g->n_wvls = spec->n_wvls; g->nx = spec->nx; g->ny = spec->ny;
-    g->apply_vignetting = spec->apply_vignetting; g->flip_z_dir = spec->flip_z_dir;
-    g->paired = spec->paired; g->pupil_kind = spec->pupil_kind;
-    g->eprad = spec->eprad; g->z_pupil = spec->z_pupil; g->foc = spec->foc;
+    g->paired = spec->paired;
     g->rays_per_tile = (int64_t)spec->nx*spec->ny;
     g->chunks_per_tile = (g->rays_per_tile + RT_BLOCK - 1)/RT_BLOCK;
     g->n_tiles = (int64_t)spec->n_fields*spec->n_wvls;
@@ -807,36 +897,54 @@ int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out)
     g->n_rays = g->n_tiles*g->rays_per_tile;
 
     const size_t nf = (size_t)spec->n_fields, nw = (size_t)spec->n_wvls;
-    const size_t b_fields = nf*sizeof(rt_field_desc);
-    const size_t b_px = nf*spec->nx*sizeof(double);
-    const size_t b_py = nf*(spec->paired ? spec->nx : spec->ny)*sizeof(double);
-    const size_t b_ref = spec->ref_img ? (size_t)g->n_tiles*2*sizeof(double) : 0;
-    const size_t b_wave = spec->wave ? (size_t)g->n_tiles*RT_WAVE_DOUBLES*sizeof(double) : 0;
+    g->b_fields = nf*sizeof(rt_field_desc);
+    g->b_px = nf*spec->nx*sizeof(double);
+    g->b_py = nf*(spec->paired ? spec->nx : spec->ny)*sizeof(double);
+    g->b_ref = (size_t)g->n_tiles*2*sizeof(double);          /* zeros when spec->ref_img is NULL */
+    g->b_wave = spec->wave ? (size_t)g->n_tiles*RT_WAVE_DOUBLES*sizeof(double) : 0;
     const size_t b_wvl = (nw*sizeof(int32_t) + 7)/8*8;
-    const size_t o_fields = 0, o_px = o_fields + b_fields, o_py = o_px + b_px, o_ref = o_py + b_py,
-                 o_wave = o_ref + b_ref, o_wvl = o_wave + b_wave, total = o_wvl + b_wvl;
-    std::vector<unsigned char> stage(total);
-    memcpy(&stage[o_fields], spec->fields, b_fields);
-    memcpy(&stage[o_px], spec->pupil_x, b_px);
-    memcpy(&stage[o_py], spec->pupil_y, b_py);
-    if (b_ref) memcpy(&stage[o_ref], spec->ref_img, b_ref);
-    if (b_wave) memcpy(&stage[o_wave], spec->wave, b_wave);
-    memcpy(&stage[o_wvl], spec->wvl_idx, nw*sizeof(int32_t));
-    cudaError_t e = cudaMalloc(&g->d_block, total);
-    if (e == cudaSuccess) e = cudaMemcpy(g->d_block, stage.data(), total, cudaMemcpyHostToDevice);
+    g->o_fields = 0; g->o_px = g->o_fields + g->b_fields; g->o_py = g->o_px + g->b_px;
+    g->o_ref = g->o_py + g->b_py; g->o_wave = g->o_ref + g->b_ref; g->o_wvl = g->o_wave + g->b_wave;
+    g->total = g->o_wvl + b_wvl;
+    g->d_block = nullptr; g->h_stage = nullptr; g->uploaded = nullptr;
+    cudaError_t e = cudaMallocHost((void **)&g->h_stage, g->total);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_block, g->total);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->uploaded, cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        grid_fill(g, spec);
+        e = cudaMemcpy(g->d_block, g->h_stage, g->total, cudaMemcpyHostToDevice);
+    }
+    /* callers launch on non-blocking streams: make the block visible to every stream */
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     if (e != cudaSuccess) {
+        if (g->uploaded) cudaEventDestroy(g->uploaded);
         cudaFree(g->d_block);
+        cudaFreeHost(g->h_stage);
         delete g;
         return fail(RT_ERR_CUDA, "rt_grid_create: %s", cudaGetErrorString(e));
     }
     unsigned char *base = (unsigned char *)g->d_block;
-    g->d_fields = (rt_field_desc *)(base + o_fields);
-    g->d_pupil_x = (double *)(base + o_px);
-    g->d_pupil_y = (double *)(base + o_py);
-    g->d_ref_img = b_ref ? (double *)(base + o_ref) : nullptr;
-    g->d_wave = b_wave ? (double *)(base + o_wave) : nullptr;
-    g->d_wvl_idx = (int32_t *)(base + o_wvl);
+    g->d_fields = (rt_field_desc *)(base + g->o_fields);
+    g->d_pupil_x = (double *)(base + g->o_px);
+    g->d_pupil_y = (double *)(base + g->o_py);
+    g->d_ref_img = (double *)(base + g->o_ref);
+    g->d_wave = g->b_wave ? (double *)(base + g->o_wave) : nullptr;
+    g->d_wvl_idx = (int32_t *)(base + g->o_wvl);
     *out = g;
+    return RT_OK;
+}
+
+int rt_grid_update(rt_grid *g, const rt_grid_spec *spec, void *stream)
+{
+    if (!g || !grid_spec_ok(spec)) return fail(RT_ERR_INVALID, "rt_grid_update: bad arguments");
+    if (spec->n_fields != g->n_fields || spec->n_wvls != g->n_wvls || spec->nx != g->nx ||
+        spec->ny != g->ny || spec->paired != g->paired || (spec->wave != nullptr) != (g->b_wave != 0))
+        return fail(RT_ERR_INVALID, "rt_grid_update: the new description has a different shape");
+    DeviceGuard guard(g->device);
+    CUDA_TRY(cudaEventSynchronize(g->uploaded));     /* the previous copy has left the staging block */
+    grid_fill(g, spec);
+    CUDA_TRY(cudaMemcpyAsync(g->d_block, g->h_stage, g->total, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CUDA_TRY(cudaEventRecord(g->uploaded, (cudaStream_t)stream));
     return RT_OK;
 }
 
@@ -876,16 +984,18 @@ int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int6
     if (rc) return rc;
     DeviceGuard guard(t->device);
     cudaStream_t s = (cudaStream_t)stream;
-    if (summary && chunk_begin == chunk_end)
-        CUDA_TRY(cudaMemsetAsync(summary, 0, (size_t)g->n_tiles*RT_SUMMARY_DOUBLES*sizeof(double), s));
+    for (int32_t wi : g->h_wvl_idx)
+        if (wi < 0 || wi >= t->n_wvl)
+            return fail(RT_ERR_INVALID, "rt_trace_grid: the grid's wvl_idx is out of range for this table");
+    if (summary && chunk_begin == chunk_end) {
+        /* an empty shard contributes the identity of every column (min / max: +-inf) */
+        const int64_t n = g->n_tiles*RT_SUMMARY_DOUBLES;
+        k_summary_identity<<<(unsigned)((n + 255)/256), 256, 0, s>>>(summary, n);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
     if (chunk_begin == chunk_end) return RT_OK;
-    GridDev G;
-    G.n_wvls = g->n_wvls; G.nx = g->nx; G.ny = g->ny;
-    G.apply_vignetting = g->apply_vignetting; G.flip_z_dir = g->flip_z_dir; G.paired = g->paired;
-    G.eprad = g->eprad; G.z_pupil = g->z_pupil; G.foc = g->foc;
-    G.fields = g->d_fields; G.wvl_idx = g->d_wvl_idx;
-    G.pupil_x = g->d_pupil_x; G.pupil_y = g->d_pupil_y; G.ref_img = g->d_ref_img; G.wave = g->d_wave;
-    G.rays_per_tile = g->rays_per_tile; G.chunks_per_tile = g->chunks_per_tile;
+    const GridDev G = grid_dev(g);
     double *scr = (double *)scratch;
     if (summary)
         CUDA_TRY(cudaMemsetAsync(scr, 0, (size_t)rt_grid_scratch_bytes(g, chunk_begin, chunk_end), s));
@@ -940,6 +1050,36 @@ int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int6
         g_launches++;
         CUDA_TRY(cudaGetLastError());
     }
+    return RT_OK;
+}
+
+int rt_grid_chief_ref(const rt_table *t, rt_grid *g, int32_t wvl_idx, double *ref_out, void *stream)
+{
+    if (!t || !g) return fail(RT_ERR_INVALID, "rt_grid_chief_ref: bad arguments");
+    if (t->device != g->device) return fail(RT_ERR_INVALID, "rt_grid_chief_ref: table and grid on different devices");
+    if (wvl_idx < 0 || wvl_idx >= t->n_wvl) return fail(RT_ERR_INVALID, "rt_grid_chief_ref: wvl_idx out of range");
+    DeviceGuard guard(t->device);
+    rt_opts o;
+    o.eps = 1.0e-12; o.pt_inside_fuzz = -1.0; o.check_apertures = 0; o.intersect_obj = 1;
+    o.filter_out_phantoms = 0; o.first_surf = 1; o.last_surf = t->n_ifc - 2; o.wvl_idx = wvl_idx;
+    const int threads = 32, blocks = (g->n_fields + threads - 1)/threads;
+    k_chief_ref<<<blocks, threads, 0, (cudaStream_t)stream>>>(t->d_surfs, t->d_n, t->n_ifc, grid_dev(g),
+                                                              g->n_fields, g->pupil_kind, wvl_idx, t->d_wvl,
+                                                              o, g->d_ref_img, ref_out);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_combine_summaries(const double *parts, int32_t n_parts, int64_t n_tiles, double *out, void *stream)
+{
+    if (!parts || !out || n_parts < 1 || n_tiles < 0)
+        return fail(RT_ERR_INVALID, "rt_combine_summaries: bad arguments");
+    if (n_tiles == 0) return RT_OK;
+    const int64_t n = n_tiles*RT_SUMMARY_DOUBLES;
+    k_combine_summaries<<<(unsigned)((n + 255)/256), 256, 0, (cudaStream_t)stream>>>(parts, n_parts, n, out);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
     return RT_OK;
 }
 

@@ -43,15 +43,12 @@ __device__ __noinline__ void angular_start_dir(int pupil_kind, double scale, dou
  * grids (rt_trace_grid routes angular pupils to the general kernels), and keeping it
  * out of GridDev leaves their parameter layout -- and code -- untouched. */
 template <bool LEAN>
-__device__ __forceinline__ void grid_start_ray(const GridDev &G, int pupil_kind, int f, int64_t loc,
-                                               Vec3 &p0, Vec3 &d0)
+__device__ __forceinline__ void grid_start_ray_at(const GridDev &G, int pupil_kind, int f, double pupx,
+                                                  double pupy, bool apply_vignetting, Vec3 &p0, Vec3 &d0)
 {
-    const int i = (int)(loc/G.ny), j = (int)(loc - (int64_t)i*G.ny);
     const rt_field_desc &F = G.fields[f];
     /* Field.apply_vignetting, opticalspec.py:1339-1353 */
-    double pupx = G.pupil_x[(int64_t)f*G.nx + i];
-    double pupy = G.paired ? G.pupil_y[(int64_t)f*G.nx + i] : G.pupil_y[(int64_t)f*G.ny + j];
-    if (G.apply_vignetting) {
+    if (apply_vignetting) {
         const double vlx = F.vlx, vux = F.vux, vly = F.vly, vuy = F.vuy;
         if (pupx < 0.0) { if (vlx != 0.0) pupx *= (1.0 - vlx); }
         else            { if (vux != 0.0) pupx *= (1.0 - vux); }
@@ -71,6 +68,16 @@ __device__ __forceinline__ void grid_start_ray(const GridDev &G, int pupil_kind,
     }
     /* trace_base virtual-object flip, trace.py:305-308 */
     if (d0.z*(double)G.flip_z_dir < 0) { d0.x = -d0.x; d0.y = -d0.y; d0.z = -d0.z; }
+}
+
+template <bool LEAN>
+__device__ __forceinline__ void grid_start_ray(const GridDev &G, int pupil_kind, int f, int64_t loc,
+                                               Vec3 &p0, Vec3 &d0)
+{
+    const int i = (int)(loc/G.ny), j = (int)(loc - (int64_t)i*G.ny);
+    const double pupx = G.pupil_x[(int64_t)f*G.nx + i];
+    const double pupy = G.paired ? G.pupil_y[(int64_t)f*G.nx + i] : G.pupil_y[(int64_t)f*G.ny + j];
+    grid_start_ray_at<LEAN>(G, pupil_kind, f, pupx, pupy, G.apply_vignetting != 0, p0, d0);
 }
 
 }  // namespace b200rt

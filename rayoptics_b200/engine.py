@@ -62,7 +62,8 @@ class BundleResult:
     ``abr``: ``[2, n]`` transverse aberration (grid traces).  Only the
     ``outputs`` asked for are allocated and written (others are None)."""
 
-    def __init__(self, n, n_ifc, device, outputs=BUNDLE_OUTPUTS):
+    def __init__(self, n, n_ifc, device, outputs=BUNDLE_OUTPUTS, nan_status=False):
+        self.nan_status = bool(nan_status)     # RT_OUT_ABR_NAN_STATUS: status / fail_surf ride in abr's NaNs
         f64 = dict(dtype=torch.float64, device=device)
         i32 = dict(dtype=torch.int32, device=device)
         want = set(outputs)
@@ -100,6 +101,7 @@ class BundleResult:
         if self.abr is not None:
             o.abr_x, o.abr_y = _ptr(self.abr[0]), _ptr(self.abr[1])
         o.opd = _ptr(self.opd)
+        o.flags = _abi.RT_OUT_ABR_NAN_STATUS if self.nan_status else 0
         return o
 
     def bytes_per_ray(self):
@@ -279,6 +281,33 @@ class PupilGrid(PupilGridSpec):
             raise RuntimeError('PupilGrid was destroyed')
         return self._handle
 
+    def shape_key(self):
+        return (self.device, self.n_fields, self.n_wvls, self.nx, self.ny, self.paired,
+                self.wave is not None)
+
+    def update(self, *args, **kwargs):
+        """Replace the description by another one of the same shape (``rt_grid_update``: one
+        asynchronous copy on the current stream, no allocation).  Arguments as the constructor."""
+        kwargs.pop('device', None)
+        old = self.shape_key()
+        PupilGridSpec.__init__(self, *args, **kwargs)
+        if self.shape_key() != old:
+            raise ValueError('PupilGrid.update: the new description has a different shape')
+        spec = self.c_spec()
+        with torch.cuda.device(self.device):
+            _abi.check(self._lib.rt_grid_update(self.handle, C.byref(spec),
+                                                _stream_ptr(torch.device('cuda', self.device))))
+        return self
+
+    def chief_ref(self, table, wvl_idx, out=None):
+        """Reference image points = image intercepts of the chief rays at row ``wvl_idx`` of
+        the table, computed and stored on the device (``rt_grid_chief_ref``); ``out``:
+        optional ``[n_fields, 2]`` float64 device tensor that receives a copy."""
+        with torch.cuda.device(self.device):
+            _abi.check(self._lib.rt_grid_chief_ref(table.handle, self.handle, int(wvl_idx), _ptr(out),
+                                                   _stream_ptr(torch.device('cuda', self.device))))
+        return out
+
     def close(self):
         if getattr(self, '_handle', None) is not None:
             self._lib.rt_grid_destroy(self._handle)
@@ -292,7 +321,7 @@ class PupilGrid(PupilGridSpec):
 
 
 def trace_grid(table, grid, chunk_begin=0, chunk_end=None, outputs=GRID_OUTPUTS, full=False,
-               summary=True, res=None, **kwargs):
+               summary=True, res=None, nan_status=False, **kwargs):
     """Trace chunks ``[chunk_begin, chunk_end)`` of a PupilGrid.
 
     Returns a BundleResult whose per-ray tensors (``outputs``; pass ``()`` for
@@ -311,7 +340,8 @@ def trace_grid(table, grid, chunk_begin=0, chunk_end=None, outputs=GRID_OUTPUTS,
     opts = _abi.make_opts(**kwargs)
     n = grid.rays_in_chunks(chunk_begin, chunk_end)
     if res is None:
-        res = BundleResult(n, table.n_ifc, device, tuple(outputs) + (('full',) if full else ()))
+        res = BundleResult(n, table.n_ifc, device, tuple(outputs) + (('full',) if full else ()),
+                           nan_status=nan_status)
     elif res.n != n:
         raise ValueError('res was allocated for a different number of rays')
     out = res.c_struct()
@@ -328,10 +358,32 @@ def trace_grid(table, grid, chunk_begin=0, chunk_end=None, outputs=GRID_OUTPUTS,
     return res
 
 
-def combine_summaries(parts):
+def decode_nan_status(abr):
+    """``(status, fail_surf)`` int32 arrays from an ``abr`` ``[2, n]`` array written with
+    ``nan_status=True`` (numpy, host): rays that reach the image have finite aberrations and
+    status 0 / fail_surf -1; the others carry both numbers in the NaN payloads."""
+    bits = np.ascontiguousarray(abr).view(np.uint64)
+    bad = np.isnan(abr[0])
+    status = np.where(bad, bits[0] & np.uint64(0xFFFF), 0).astype(np.int32)
+    fs = (bits[1] & np.uint64(0xFFFF)).astype(np.int32)
+    fail_surf = np.where(bad, np.where(fs >= 0x8000, fs - 0x10000, fs), -1).astype(np.int32)
+    return status, fail_surf
+
+
+def combine_summaries(parts, out=None):
     """Combine partial ``[n_tiles, 16]`` summaries (from chunk ranges / ranks):
-    sums add, min/max columns take min/max."""
+    sums add, min/max columns take min/max.  CUDA tensors: one ``rt_combine_summaries``
+    launch on the current stream; CPU tensors (gloo tests): torch."""
     parts = torch.stack(list(parts)) if not torch.is_tensor(parts) else parts
+    if parts.is_cuda:
+        parts = parts.contiguous()
+        if out is None:
+            out = torch.empty(parts.shape[1:], dtype=parts.dtype, device=parts.device)
+        with torch.cuda.device(parts.device):
+            _abi.check(_abi.load_library().rt_combine_summaries(
+                _ptr(parts), parts.shape[0], parts.shape[1], _ptr(out), _stream_ptr(parts.device)))
+        out._keep = parts
+        return out
     out = parts.sum(dim=0)
     for k in (10, 12):
         out[:, k] = parts[:, :, k].min(dim=0).values

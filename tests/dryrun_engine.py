@@ -86,7 +86,7 @@ def trace_bundle(table, p, d, wvl_idx=None, full=False, outputs=E.BUNDLE_OUTPUTS
 
 
 def trace_grid(table, grid, chunk_begin=0, chunk_end=None, outputs=E.GRID_OUTPUTS, full=False,
-               summary=True, res=None, **kwargs):
+               summary=True, res=None, nan_status=False, **kwargs):
     chunk_end = grid.n_chunks if chunk_end is None else chunk_end
     kwargs.setdefault('check_apertures', True)
     kwargs.setdefault('first_surf', 1)
@@ -104,7 +104,13 @@ def trace_grid(table, grid, chunk_begin=0, chunk_end=None, outputs=E.GRID_OUTPUT
         res = _result(r1 - r0, table.n_ifc, outputs, full)
     _fill(res, g, outputs)
     if res.abr is not None:
-        res.abr.copy_(torch.from_numpy(g['abr']))
+        abr = g['abr'].copy()
+        if nan_status:
+            bad = g['status'] != 0
+            bits = abr.view(np.uint64)
+            bits[0, bad] = _abi.RT_NAN_PAYLOAD_BASE | g['status'][bad].astype(np.uint64)
+            bits[1, bad] = _abi.RT_NAN_PAYLOAD_BASE | g['fail_surf'][bad].astype(np.uint64)
+        res.abr.copy_(torch.from_numpy(abr))
     if res.opd is not None and g['opd'] is not None:
         res.opd.copy_(torch.from_numpy(g['opd']))
     if summary:

@@ -27,7 +27,7 @@ def test_struct_layout_matches_header():
     from oracle import rt_oracle
     assert rt_oracle.lib().rto_sizeof_surface_desc() == C.sizeof(_abi.rt_surface_desc) == 640
     assert C.sizeof(_abi.rt_opts) == 40
-    assert C.sizeof(_abi.rt_out) == 19*8
+    assert C.sizeof(_abi.rt_out) == 20*8
     assert C.sizeof(_abi.rt_field_desc) == 72
 
 
@@ -341,3 +341,14 @@ def test_table_cache_key_sees_in_place_edits():
     changed()
     sm.ifcs[1].max_aperture *= 2.0
     changed()
+
+
+def test_nan_status_decoding():
+    """engine.decode_nan_status: the payload convention of RT_OUT_ABR_NAN_STATUS (include/b200rt.h)."""
+    base = _abi.RT_NAN_PAYLOAD_BASE
+    bits = np.array([[0, base | 3, base | 1, base | 5], [0, base | 12, base | 0, base | 7]], dtype=np.uint64)
+    abr = bits.view(np.float64).copy()
+    abr[:, 0] = [0.25, -0.5]
+    st, fs = E.decode_nan_status(abr)
+    assert st.tolist() == [0, 3, 1, 5] and fs.tolist() == [-1, 12, 0, 7]
+    assert np.isnan(abr[:, 1:]).all()
