@@ -315,6 +315,25 @@ def block_tasks(n_fields, n_wvls, blocks_per_side, num):
     return tasks
 
 
+def host_info():
+    """what the box really offers: logical CPUs, affinity mask, cgroup CPU quota, load"""
+    info = {'cpu_count': os.cpu_count()}
+    try:
+        info['affinity'] = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    for f in ('/sys/fs/cgroup/cpu.max', '/sys/fs/cgroup/cpu/cpu.cfs_quota_us'):
+        try:
+            info['cgroup:' + os.path.basename(f)] = open(f).read().strip()
+        except Exception:
+            pass
+    try:
+        info['loadavg'] = os.getloadavg()[0]
+    except Exception:
+        pass
+    return info
+
+
 def run_arm(model, steps, warmup, step_s=1.5, procs=None):
     """K timed steps of the reference on `procs` worker processes (default: one per core); each
     step traces every (field, wvl) tile's pupil square cut into blocks (block_tasks), the block
@@ -325,6 +344,12 @@ def run_arm(model, steps, warmup, step_s=1.5, procs=None):
     opm = MM.OpticalModel.load(path)
     n_fields, n_wvls = len(opm.optical_spec.field_of_view.fields), len(opm.seq_model.wvlns)
     cores = int(procs or os.cpu_count() or 1)
+    # one process, one block: the reference's single-core rate on this box
+    R1 = build_model(opm)
+    trace_block(R1, 0, 0, -1.0, 1.0, -1.0, 1.0, 8)
+    t1 = time.perf_counter()
+    n1 = trace_block(R1, n_fields - 1, n_wvls//2, -1.0, 1.0, -1.0, 1.0, 40)
+    single = n1/(time.perf_counter() - t1)
     pool = PoolRunner(path, cores)
     tiles = n_fields*n_wvls
     bps = 1
@@ -349,6 +374,7 @@ def run_arm(model, steps, warmup, step_s=1.5, procs=None):
     tot = float(np.sum(times))
     return {'value': n_step*steps/tot, 'unit': 'rays/s', 'cores': cores, 'kind': 'reference',
             'rays_per_step': int(n_step), 'rays_per_s_per_core': n_step*steps/tot/cores,
+            'single_process': single, 'host': host_info(),
             'ms_per_step': 1e3*tot/steps,
             'sample': f'{steps} steps x {n_step} rays: all {tiles} (field, wvl) tiles, each pupil square cut '
                       f'into {bps}x{bps} blocks of {num_b}x{num_b} samples, every block traced by the unmodified '

@@ -222,17 +222,19 @@ def port_arm(spec, descs, n_by_wvl, r0, r1, target_s=6.0, scaling=True):
     opts = _abi.make_opts(first_surf=1, last_surf=len(descs) - 2, check_apertures=True)
     out = {'unit': UNIT, 'kind': 'port', 'cores': cores, 'threads_scaling': {}}
     runner = None
-    for th in (sorted({1, min(32, cores), cores}) if scaling else [cores]):
+    for th in (sorted({1, min(8, cores), min(16, cores), min(32, cores), min(64, cores), cores})
+               if scaling else [cores]):
         runner = rt_oracle.GridRunner(spec, descs, n_by_wvl, opts, r1 - r0, th)
         n_w = r1 - r0 if th > 1 else min(r1 - r0, 50000)
         runner.run(r0, r0 + n_w)                                        # warm-up, first touch
-        reps, tot, budget = 0, 0.0, (target_s if th == cores else target_s/4)
+        reps, tot, budget = 0, 0.0, (target_s if th == cores else target_s/6)
         while tot < budget and reps < 200:
             tot += runner.run(r0, r0 + n_w)
             reps += 1
         out['threads_scaling'][str(th)] = n_w*reps/tot
         if th == cores:
             out['value'] = n_w*reps/tot
+            out['parallel_speedup'] = out['value']/out['threads_scaling']['1']
             out['sample'] = (f'{reps} x {n_w} rays of the same grid, oracle/rt_oracle.c on a persistent pool of '
                              f'{cores} pthreads (dynamic blocks of 2048 rays), buffers pre-touched, C call only')
     return out, runner

@@ -192,7 +192,10 @@ def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table
                 r = E.trace_grid(table, grid, cuts[i], cuts[i + 1], outputs=('abr',), nan_status=True,
                                  **kwargs)
                 a = grid.first_ray_of_chunk(cuts[i]) - base
-                h_abr[:, a:a + r.n].copy_(r.abr, non_blocking=True)
+                # row by row: each side of both copies is contiguous (a strided pinned destination
+                # would send torch through a synchronous staging copy)
+                h_abr[0, a:a + r.n].copy_(r.abr[0], non_blocking=True)
+                h_abr[1, a:a + r.n].copy_(r.abr[1], non_blocking=True)
             parts.append(r.summary)
             keep.append(r)
         for st in streams:
