@@ -316,11 +316,15 @@ int rt_combine_summaries(const double *parts, int32_t n_parts, int64_t n_tiles,
 /* ---- misc */
 const char *rt_last_error(void);
 int rt_abi_version(void);
+/* rays per chunk (= threads per CTA of this build): the unit of rt_trace_grid's chunk ranges */
+int32_t rt_chunk_rays(void);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 int64_t rt_launch_count(void);
 /* fp64 vector-pipe peak of `device` in TFLOP/s, measured with a chain of
  * independent DFMAs (the roofline denominator of the register-resident trace) */
 int rt_measure_fp64_peak(int32_t device, double *tflops);
+/* cycles between two dependent fp64 FMAs of one warp (dependent-issue latency of the fp64 pipe) */
+int rt_measure_fp64_latency(int32_t device, double *cycles_per_dependent_dfma);
 /* self-test of the shared-reciprocal division of the specialised kernels against
  * the IEEE division (n_blocks x 256 threads x n_per_thread operand sets);
  * *mismatches must come back 0 */

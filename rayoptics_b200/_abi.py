@@ -114,7 +114,7 @@ EXPORTS = ['rt_table_create', 'rt_table_destroy', 'rt_table_dims', 'rt_table_set
            'rt_trace_bundle', 'rt_grid_create', 'rt_grid_destroy', 'rt_grid_dims',
            'rt_grid_scratch_bytes', 'rt_trace_grid', 'rt_grid_chief_ref', 'rt_combine_summaries',
            'rt_grid_update',
-           'rt_last_error', 'rt_abi_version', 'rt_launch_count', 'rt_measure_fp64_peak',
+           'rt_last_error', 'rt_abi_version', 'rt_chunk_rays', 'rt_launch_count', 'rt_measure_fp64_peak', 'rt_measure_fp64_latency',
            'rt_selftest_division']
 
 _lib = None
@@ -168,9 +168,12 @@ def load_library():
     lib.rt_combine_summaries.restype = i32
     lib.rt_last_error.restype = C.c_char_p
     lib.rt_abi_version.restype = i32
+    lib.rt_chunk_rays.restype = i32
     lib.rt_launch_count.restype = i64
     lib.rt_measure_fp64_peak.argtypes = [i32, c_double_p]
     lib.rt_measure_fp64_peak.restype = i32
+    lib.rt_measure_fp64_latency.argtypes = [i32, c_double_p]
+    lib.rt_measure_fp64_latency.restype = i32
     lib.rt_selftest_division.argtypes = [i32, i32, i64, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.rt_selftest_division.restype = i32
     for name in ('rt_table_create', 'rt_table_destroy', 'rt_table_dims', 'rt_trace_bundle',

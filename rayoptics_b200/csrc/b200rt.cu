@@ -31,7 +31,9 @@
 
 using namespace b200rt;
 
+#ifndef RT_BLOCK
 #define RT_BLOCK 256          /* threads per CTA = rays per chunk */
+#endif
 #ifndef RT_LEAN_MIN_CTAS
 #define RT_LEAN_MIN_CTAS 3   /* resident CTAs per SM the lean kernels are register-limited for */
 #endif
@@ -180,7 +182,7 @@ k_trace_bundle(const rt_surface_desc *__restrict__ g_surfs, const double *__rest
  * records of a tile in slot order: bit-reproducible for a given launch shape,
  * and no CTA barrier / per-chunk shuffle traffic in the trace kernel. */
 #define RT_WARPS (RT_BLOCK/32)
-#define RT_MAX_GRID 1024
+#define RT_MAX_GRID 2048
 #define RT_ACC 15
 #define RT_ACC_BYTES (RT_ACC*RT_BLOCK*sizeof(double))
 
@@ -569,6 +571,18 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
     if (s == 12345.678) out[blockIdx.x*blockDim.x + threadIdx.x] = s;
 }
 
+/* dependent-issue latency of the fp64 pipe: one warp, one chain of DFMAs, clock64 around it */
+__global__ void k_dfma_latency(double *out, long long *cycles, int iters, double a, double b)
+{
+    double x = threadIdx.x;
+    long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < iters; i++) x = __fma_rn(x, a, b);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (x == 12345.678) out[threadIdx.x] = x;
+}
+
 /* ------------------------------------------------------------ launch helpers */
 template <typename K>
 static int persistent_grid(K kernel, size_t smem, int sm_count, int64_t work_items, int *grid)
@@ -718,6 +732,7 @@ static GridDev grid_dev(const rt_grid *g)
 extern "C" {
 
 int rt_abi_version(void) { return RT_ABI_VERSION; }
+int32_t rt_chunk_rays(void) { return RT_BLOCK; }
 const char *rt_last_error(void) { return g_err.c_str(); }
 int64_t rt_launch_count(void) { return g_launches.load(); }
 
@@ -1112,6 +1127,29 @@ int rt_measure_fp64_peak(int32_t device, double *tflops)
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
     *tflops = best;
+    return RT_OK;
+}
+
+/* Cycles between two DEPENDENT fp64 FMAs of one warp (the latency that the per-ray chains of
+ * the trace kernels expose; DESIGN.md "what bounds the kernel"). */
+int rt_measure_fp64_latency(int32_t device, double *cycles_per_dependent_dfma)
+{
+    if (!cycles_per_dependent_dfma) return fail(RT_ERR_INVALID, "rt_measure_fp64_latency: NULL output");
+    DeviceGuard guard(device);
+    double *d_out; long long *d_cyc;
+    CUDA_TRY(cudaMalloc(&d_out, 32*sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_cyc, sizeof(long long)));
+    const int iters = 1 << 14;
+    long long best = -1;
+    for (int rep = 0; rep < 3; rep++) {
+        k_dfma_latency<<<1, 32>>>(d_out, d_cyc, iters, 0.999999, 1e-9);
+        g_launches++;
+        long long c = 0;
+        CUDA_TRY(cudaMemcpy(&c, d_cyc, sizeof c, cudaMemcpyDeviceToHost));
+        if (best < 0 || c < best) best = c;
+    }
+    cudaFree(d_out); cudaFree(d_cyc);
+    *cycles_per_dependent_dfma = (double)best/iters;
     return RT_OK;
 }
 

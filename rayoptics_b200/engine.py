@@ -165,7 +165,10 @@ def _accumulated_steps(start, stop, num):
     return vals
 
 
-CHUNK_RAYS = 256   # RT_BLOCK in csrc/b200rt.cu: rays per chunk = threads per CTA
+def chunk_rays():
+    """rays per chunk = threads per CTA of the loaded library (``rt_chunk_rays``; 256)"""
+    return int(_abi.load_library().rt_chunk_rays())
+
 
 
 class PupilGridSpec:
@@ -222,10 +225,10 @@ class PupilGridSpec:
                 nf, self.n_wvls, _abi.RT_WAVE_DOUBLES)
         self.eprad, self.z_pupil, self.foc = float(eprad), float(z_pupil), float(foc)
         self.apply_vignetting, self.flip_z_dir = int(bool(apply_vignetting)), int(flip_z_dir)
-        self.chunk_rays = CHUNK_RAYS
+        self.chunk_rays = chunk_rays()
         self.rays_per_tile = self.nx*self.ny
         self.n_tiles = self.n_fields*self.n_wvls
-        self.chunks_per_tile = (self.rays_per_tile + CHUNK_RAYS - 1)//CHUNK_RAYS
+        self.chunks_per_tile = (self.rays_per_tile + self.chunk_rays - 1)//self.chunk_rays
         self.n_chunks = self.n_tiles*self.chunks_per_tile
         self.n_rays = self.n_tiles*self.rays_per_tile
 
@@ -415,6 +418,14 @@ def measure_fp64_peak(device=0):
     lib = _abi.load_library()
     v = C.c_double()
     _abi.check(lib.rt_measure_fp64_peak(int(device), C.byref(v)))
+    return v.value
+
+
+def measure_fp64_latency(device=0):
+    """cycles between two dependent DFMAs of one warp (``rt_measure_fp64_latency``)"""
+    lib = _abi.load_library()
+    v = C.c_double()
+    _abi.check(lib.rt_measure_fp64_latency(int(device), C.byref(v)))
     return v.value
 
 
