@@ -410,3 +410,28 @@ def test_seq_reader_tilt_commands():
     for (ra, ta), (rb, tb) in zip(opm.seq_model.lcl_tfrms, m2.seq_model.lcl_tfrms):
         assert np.array_equal(ra, rb) and np.array_equal(ta, tb)
         assert ra.flags['C_CONTIGUOUS'] == rb.flags['C_CONTIGUOUS']
+
+
+def test_zmx_reader_coordinate_breaks():
+    """COORDBRK surfaces (zemax/zmxread.py:314-316,341-355) of the reference's own Zemax test files:
+    phantom interfaces with DecenterData; the folded system of HoO-V2C18Ex66 (9 coordinate breaks)
+    brings the axial ray back onto the axis, direction (0, 0, 1)."""
+    from rayoptics_b200 import zmx
+    from oracle import rt_oracle
+    base = '/root/reference/src/rayoptics/zemax/tests'
+    if not os.path.isdir(base):
+        pytest.skip('/root/reference not present')
+    opm = zmx.open_zmx(os.path.join(base, 'HoO-V2C18Ex66.zmx'),
+                       glass_map={'BK7': (1.5168, 64.17), 'SF2': (1.64769, 33.85), 'F2': (1.62004, 36.37),
+                                  'SK16': (1.62041, 60.32), 'N-BK7': (1.5168, 64.17), 'SILICA': (1.4585, 67.8),
+                                  'SF5': (1.6727, 32.2), 'BAK4': (1.5688, 56.1), 'SF1': (1.71736, 29.5),
+                                  'K5': (1.52249, 59.5), 'SK2': (1.60738, 56.65), 'LAK9': (1.691, 54.7)})
+    sm = opm.seq_model
+    cb = [i for i in sm.ifcs if i.decenter is not None]
+    assert len(cb) == 9 and all(i.interact_mode == 'phantom' for i in cb)
+    assert any(i.decenter.dtype == 'reverse' for i in cb) or all(i.decenter.dtype == 'decenter' for i in cb)
+    descs, n_by_wvl, _ = T.describe_model(sm)
+    r = rt_oracle.trace_bundle(descs, n_by_wvl, np.zeros((3, 1)), np.array([[0.], [0.], [1.]]),
+                               np.zeros(1, np.int32), _abi.make_opts(first_surf=1, last_surf=len(descs) - 2))
+    assert r['status'][0] == 0
+    assert np.abs(r['last'][0:2, 0]).max() < 1e-9 and abs(r['last'][5, 0] - 1.0) < 1e-12
