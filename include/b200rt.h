@@ -296,6 +296,22 @@ int rt_trace_grid(const rt_table *table, const rt_grid *grid,
                   const rt_opts *opts, const rt_out *out,
                   double *summary, void *scratch, void *stream);
 
+/* Grid trace with the results delivered to HOST memory -- the data path of the grid analyses
+ * (spot diagrams: seq/sequential.py:1058-1085 evaluated for every field) in one call.  Chunks
+ * [chunk_begin, chunk_end) are traced in n_pieces launches alternating between two streams
+ * owned by the grid handle; each piece's transverse aberrations (RT_OUT_ABR_NAN_STATUS coding)
+ * are copied device -> host right behind its trace, so copies and traces overlap.
+ * d_abr_x/y: DEVICE staging [rays of the range]; h_abr_x/y: HOST, page-locked, same length;
+ * summary: DEVICE [n_tiles][RT_SUMMARY_DOUBLES] or NULL; scratch: DEVICE,
+ * rt_trace_grid_to_host_scratch_bytes(grid, n_pieces) bytes.  Work already queued on `stream`
+ * (rt_grid_update, rt_grid_chief_ref) is waited for; when the call returns, `stream` waits for
+ * all pieces: synchronising `stream` makes h_abr_* and summary valid. */
+int64_t rt_trace_grid_to_host_scratch_bytes(const rt_grid *grid, int32_t n_pieces);
+int rt_trace_grid_to_host(const rt_table *table, rt_grid *grid, int64_t chunk_begin, int64_t chunk_end,
+                          const rt_opts *opts, double *d_abr_x, double *d_abr_y,
+                          double *h_abr_x, double *h_abr_y, double *summary, void *scratch,
+                          int32_t n_pieces, void *stream);
+
 /* Reference image points without a host round trip: trace the (0, 0) pupil ray of every
  * field at row `wvl_idx` of the table (no vignetting, apertures not checked) and store its
  * image intercept (x, y) as the reference image point of every (field, wvl) tile of `grid` --

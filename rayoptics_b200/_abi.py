@@ -113,7 +113,7 @@ LIB_NAME = 'libb200rt.so'
 EXPORTS = ['rt_table_create', 'rt_table_destroy', 'rt_table_dims', 'rt_table_set_wavelengths',
            'rt_trace_bundle', 'rt_grid_create', 'rt_grid_destroy', 'rt_grid_dims',
            'rt_grid_scratch_bytes', 'rt_trace_grid', 'rt_grid_chief_ref', 'rt_combine_summaries',
-           'rt_grid_update',
+           'rt_grid_update', 'rt_trace_grid_to_host', 'rt_trace_grid_to_host_scratch_bytes',
            'rt_last_error', 'rt_abi_version', 'rt_chunk_rays', 'rt_launch_count', 'rt_measure_fp64_peak', 'rt_measure_fp64_latency',
            'rt_selftest_division']
 
@@ -162,6 +162,10 @@ def load_library():
                                   vp, vp, vp]
     lib.rt_grid_update.argtypes = [vp, C.POINTER(rt_grid_spec), vp]
     lib.rt_grid_update.restype = i32
+    lib.rt_trace_grid_to_host_scratch_bytes.argtypes = [vp, i32]
+    lib.rt_trace_grid_to_host_scratch_bytes.restype = i64
+    lib.rt_trace_grid_to_host.argtypes = [vp, vp, i64, i64, C.POINTER(rt_opts), vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.rt_trace_grid_to_host.restype = i32
     lib.rt_grid_chief_ref.argtypes = [vp, vp, i32, vp, vp]
     lib.rt_grid_chief_ref.restype = i32
     lib.rt_combine_summaries.argtypes = [vp, i32, i64, vp, vp]

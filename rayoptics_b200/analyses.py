@@ -81,6 +81,7 @@ class SpotDiagram:
 
 _STREAMS = {}
 _GRIDS = {}          # shape key -> PupilGrid whose device block / pinned staging is re-used
+_WORK = {}           # device -> re-used device staging buffers of spot_diagram
 
 
 def _side_streams(dev):
@@ -89,22 +90,50 @@ def _side_streams(dev):
     return _STREAMS[dev]
 
 
-def _reusable_grid(args, kw, device):
-    """A PupilGrid for this description: the first call of a given shape allocates
-    (``rt_grid_create``), later calls re-upload into the same device block with one
-    asynchronous copy (``rt_grid_update``) -- no cudaMalloc / cudaFree per analysis call."""
-    spec = E.PupilGridSpec(*args, **kw)
-    key = (int(device), spec.n_fields, spec.n_wvls, spec.nx, spec.ny, spec.paired, spec.wave is not None)
-    grid = _GRIDS.get(key)
+def _spec_key(opt_model, table, num_rays, fields, wvls, foc):
+    """Everything the grid description is computed from, as a hashable key: while it does not
+    change, the host-side description (start points, aim points, pupil tables) of the previous
+    call is uploaded again instead of being recomputed."""
+    osp, sm = opt_model.optical_spec, opt_model.seq_model
+    fod = osp.fod if hasattr(osp, 'fod') else opt_model['analysis_results']['parax_data'].fod
+    fkey = tuple((f.x, f.y, f.vux, f.vuy, f.vlx, f.vly,
+                  None if f.aim_info is None else tuple(np.asarray(f.aim_info, dtype=float).ravel()))
+                 for f in fields)
+    fov, pup = osp.field_of_view, osp.pupil
+    return (id(table), num_rays, fkey, tuple(wvls), foc, tuple(pup.key), pup.value, tuple(fov.key),
+            fov.value, fov.is_relative, fov.is_wide_angle, sm.z_dir[0], sm.gaps[0].thi) + tuple(
+                getattr(fod, a, None) for a in ('obj_dist', 'enp_dist', 'enp_radius', 'm', 'obj_na',
+                                                'pr_ht0', 'pr_slp0', 'n_obj', 'n_img'))
+
+
+def _reusable_grid(opt_model, table, num_rays, fields, wvls, foc):
+    """The PupilGrid of this description: the device block and its pinned staging are allocated
+    once per shape (``rt_grid_create``); every call uploads the description again (one
+    asynchronous copy, ``rt_grid_update``) -- no cudaMalloc / cudaFree per analysis call -- and
+    the host-side description itself is recomputed only when its inputs changed."""
+    key = _spec_key(opt_model, table, num_rays, fields, wvls, foc)
+    hit = _SPECS.get(key)
+    if hit is None:
+        args, kw = E._grid_args(opt_model, table.wvl_index, num_rays, fields, wvls, foc, (-1.0, 1.0), True)
+        spec = E.PupilGridSpec(*args, **kw)
+        if len(_SPECS) > 32:
+            _SPECS.clear()
+        hit = _SPECS[key] = (spec, args, kw)
+    spec, args, kw = hit
+    gkey = (int(table.device), spec.n_fields, spec.n_wvls, spec.nx, spec.ny, spec.paired, spec.wave is not None)
+    grid = _GRIDS.get(gkey)
     if grid is None or grid._handle is None:
         if len(_GRIDS) > 16:
             for g in _GRIDS.values():
                 g.close()
             _GRIDS.clear()
-        grid = _GRIDS[key] = E.PupilGrid(*args, device=device, **kw)
+        grid = _GRIDS[gkey] = E.PupilGrid(*args, device=table.device, **kw)
     else:
-        grid.update(*args, **kw)
-    return grid
+        grid.upload(spec)
+    return grid, spec
+
+
+_SPECS = {}
 
 
 def _table_for(opt_model, table=None, device=0):
@@ -147,7 +176,7 @@ def chief_ray_image_points(opt_model, table, fields, wvl=None, foc=0.0, io=None)
 
 
 def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table=None,
-                 device=0, pinned=None, shard=None, group=None, pieces=4, **kwargs):
+                 device=0, pinned=None, shard=None, group=None, pieces=8, **kwargs):
     """Spot diagrams of all fields and wavelengths in one pass over the device.
 
     Host buffers in, host buffers out: the grid description goes to the device (one
@@ -169,42 +198,27 @@ def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table
     io = {'h2d': 0, 'd2h': 0}
     dev = torch.device('cuda', table.device)
     with torch.cuda.device(dev):
-        args, kw = E._grid_args(opt_model, table.wvl_index, num_rays, fields, wvls, foc, (-1.0, 1.0), True)
-        grid = _reusable_grid(args, kw, table.device)
-        io['h2d'] += grid.host_bytes()
-        ref_dev = torch.empty((len(fields), 2), dtype=torch.float64, device=dev)
+        grid, spec = _reusable_grid(opt_model, table, num_rays, fields, wvls, foc)
+        io['h2d'] += spec.host_bytes()
+        ws = _WORK.setdefault(table.device, {})
+        if ws.get('ref') is None or ws['ref'].shape[0] != len(fields):
+            ws['ref'] = torch.empty((len(fields), 2), dtype=torch.float64, device=dev)
+        ref_dev = ws['ref']
         grid.chief_ref(table, table.wvl_index(sm.central_wavelength()), out=ref_dev)
         c0, c1 = (0, grid.n_chunks) if shard is None else shard_chunks(grid.n_chunks, *shard)
         n = grid.rays_in_chunks(c0, c1)
         if pinned is None:
             pinned = {'abr': torch.empty((2, max(n, 1)), dtype=torch.float64).pin_memory()}
         h_abr = pinned['abr'][:, :n]
-        # pipeline: the device->host copy of piece i overlaps the trace of piece i+1
-        n_pieces = max(1, min(pieces, (c1 - c0)//64))
-        cuts = [c0 + (c1 - c0)*i//n_pieces for i in range(n_pieces + 1)]
-        main = torch.cuda.current_stream(dev)
-        streams = _side_streams(dev) if n_pieces > 1 else [main]
-        parts, keep, base = [], [], grid.first_ray_of_chunk(c0)
-        for i in range(n_pieces):
-            st = streams[i % len(streams)]
-            st.wait_stream(main)
-            with torch.cuda.stream(st):
-                r = E.trace_grid(table, grid, cuts[i], cuts[i + 1], outputs=('abr',), nan_status=True,
-                                 **kwargs)
-                a = grid.first_ray_of_chunk(cuts[i]) - base
-                # row by row: each side of both copies is contiguous (a strided pinned destination
-                # would send torch through a synchronous staging copy)
-                h_abr[0, a:a + r.n].copy_(r.abr[0], non_blocking=True)
-                h_abr[1, a:a + r.n].copy_(r.abr[1], non_blocking=True)
-            parts.append(r.summary)
-            keep.append(r)
-        for st in streams:
-            main.wait_stream(st)
-        summ = parts[0] if n_pieces == 1 else E.combine_summaries(parts)
+        # the chunk range is traced in `pieces` launches on two streams of the grid handle, each
+        # followed by its device->host copy (rt_trace_grid_to_host): one C call, no per-piece Python
+        summ, ws['trace'] = E.trace_grid_to_host(table, grid, pinned['abr'], c0, c1,
+                                                 pieces=max(1, min(pieces, (c1 - c0)//64)),
+                                                 workspace=ws.get('trace'), **kwargs)
         if shard is not None:
             summ = gather_summaries(summ, group)
         tail = torch.cat([summ.reshape(-1), ref_dev.reshape(-1)]).cpu().numpy()   # one small copy; waits
-        main.synchronize()
+        torch.cuda.current_stream(dev).synchronize()
     summ_host = tail[:summ.numel()].reshape(summ.shape)
     ref = tail[summ.numel():].reshape(len(fields), 2).copy()
     stats_host = {k: np.asarray(v).reshape(len(fields), len(wvls))

@@ -103,6 +103,10 @@ struct rt_grid {
     unsigned char *h_stage;           /* pinned image of d_block */
     cudaEvent_t uploaded;             /* last rt_grid_update copy */
     size_t b_fields, b_px, b_py, b_ref, b_wave, o_fields, o_px, o_py, o_ref, o_wave, o_wvl, total;
+    /* rt_trace_grid_to_host: two internal streams + events (created on first use) */
+    cudaStream_t side[2];
+    cudaEvent_t ev_in, ev_side[2];
+    bool side_ok;
 };
 
 /* what the grid kernel needs, passed by value */
@@ -356,7 +360,9 @@ k_trace_bundle_lean(const rt_surface_desc *__restrict__ g_surfs, const double *_
     extern __shared__ __align__(16) unsigned char smem[];
     LeanSurf *ls = reinterpret_cast<LeanSurf *>(smem);
     LeanIdx *li = reinterpret_cast<LeanIdx *>(ls + n_ifc);
+    LeanPoly *lp = reinterpret_cast<LeanPoly *>(li + (size_t)n_ifc*n_wvl);      /* POLY instances only */
     build_plan(g_surfs, g_n, n_ifc, n_wvl, o, ls, li);
+    if (POLY) build_poly_plan(g_surfs, n_ifc, lp);
     __syncthreads();
 
     const int64_t step = (int64_t)gridDim.x*blockDim.x;
@@ -366,7 +372,7 @@ k_trace_bundle_lean(const rt_surface_desc *__restrict__ g_surfs, const double *_
         const int w = wvl_idx ? wvl_idx[r] : o.wvl_idx;
         FullWriter fw = {OUT == 2 ? out.full + r : nullptr, out.full_stride};
         RayResult R;
-        trace_ray_lean<OUT, false, POLY>(ls, li + (int64_t)w*n_ifc, g_surfs, n_ifc, o, p0, d0, fw, R);
+        trace_ray_lean<OUT, false, POLY>(ls, li + (int64_t)w*n_ifc, lp, g_surfs, n_ifc, o, p0, d0, fw, R);
         store_result(out, r, R);
     }
 }
@@ -381,14 +387,16 @@ k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__r
     double *acc = reinterpret_cast<double *>(smem);          /* [RT_ACC][RT_BLOCK] when SUMMARY */
     LeanSurf *ls = reinterpret_cast<LeanSurf *>(smem + (SUMMARY ? RT_ACC_BYTES : 0));
     LeanIdx *li = reinterpret_cast<LeanIdx *>(ls + n_ifc);
+    LeanPoly *lp = reinterpret_cast<LeanPoly *>(li + (size_t)n_ifc*n_wvl);      /* POLY instances only */
     build_plan(g_surfs, g_n, n_ifc, n_wvl, o, ls, li);
+    if (POLY) build_poly_plan(g_surfs, n_ifc, lp);
     __syncthreads();
     grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc,
         [&](int f, int w, int64_t loc, int64_t k, RayResult &R, Vec3 &d0) {
             Vec3 p0;
             grid_start_ray<true>(G, RT_PUPIL_EPD, f, loc, p0, d0);
             FullWriter fw = {OUT == 2 ? out.full + k : nullptr, out.full_stride};
-            trace_ray_lean<OUT, WAVE, POLY>(ls, li + (int64_t)G.wvl_idx[w]*n_ifc, g_surfs, n_ifc, o, p0, d0, fw, R);
+            trace_ray_lean<OUT, WAVE, POLY>(ls, li + (int64_t)G.wvl_idx[w]*n_ifc, lp, g_surfs, n_ifc, o, p0, d0, fw, R);
         });
 }
 
@@ -774,6 +782,10 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
         if (s.phase_kind != RT_PHASE_NONE || s.profile == RT_PROFILE_THINLENS) { t->lean = false; t->has_phase = true; }
         if (s.profile > RT_PROFILE_CONIC) t->lean_poly = true;
     }
+    if (t->lean_poly) {
+        t->lean_bytes += (size_t)n_ifc*sizeof(LeanPoly);
+        if (t->lean_bytes > RT_MAX_STAGE_BYTES - RT_ACC_BYTES) t->lean = false;
+    }
     if (getenv("B200RT_NO_LEAN")) t->lean = false;
     {
         const rt_surface_desc &k = surfs[n_ifc >= 2 ? n_ifc - 2 : 0];
@@ -862,6 +874,12 @@ int rt_grid_destroy(rt_grid *g)
     if (!g) return RT_OK;
     DeviceGuard guard(g->device);
     if (g->uploaded) { cudaEventSynchronize(g->uploaded); cudaEventDestroy(g->uploaded); }
+    if (g->side_ok) {
+        for (int k = 0; k < 2; k++) {
+            cudaStreamSynchronize(g->side[k]); cudaStreamDestroy(g->side[k]); cudaEventDestroy(g->ev_side[k]);
+        }
+        cudaEventDestroy(g->ev_in);
+    }
     cudaFree(g->d_block);
     cudaFreeHost(g->h_stage);
     delete g;
@@ -921,7 +939,7 @@ int rt_grid_create(const rt_grid_spec *spec, int32_t device, rt_grid **out)
     g->o_fields = 0; g->o_px = g->o_fields + g->b_fields; g->o_py = g->o_px + g->b_px;
     g->o_ref = g->o_py + g->b_py; g->o_wave = g->o_ref + g->b_ref; g->o_wvl = g->o_wave + g->b_wave;
     g->total = g->o_wvl + b_wvl;
-    g->d_block = nullptr; g->h_stage = nullptr; g->uploaded = nullptr;
+    g->d_block = nullptr; g->h_stage = nullptr; g->uploaded = nullptr; g->side_ok = false;
     cudaError_t e = cudaMallocHost((void **)&g->h_stage, g->total);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_block, g->total);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->uploaded, cudaEventDisableTiming);
@@ -1065,6 +1083,74 @@ int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int6
         g_launches++;
         CUDA_TRY(cudaGetLastError());
     }
+    return RT_OK;
+}
+
+static int64_t first_ray_of_chunk(const rt_grid *g, int64_t c)
+{
+    const int64_t tile = c/g->chunks_per_tile, lc = c - tile*g->chunks_per_tile;
+    const int64_t in_tile = lc*RT_BLOCK < g->rays_per_tile ? lc*RT_BLOCK : g->rays_per_tile;
+    return tile*g->rays_per_tile + in_tile;
+}
+
+int64_t rt_trace_grid_to_host_scratch_bytes(const rt_grid *g, int32_t n_pieces)
+{
+    if (!g || n_pieces < 1) return 0;
+    return 2*rt_grid_scratch_bytes(g, 0, g->n_chunks) +
+           (int64_t)n_pieces*g->n_tiles*RT_SUMMARY_DOUBLES*(int64_t)sizeof(double);
+}
+
+/* The grid analyses' data path in one call: the chunk range is traced in n_pieces launches
+ * alternating between two internal streams, and each piece's aberrations (NaN-coded status) go
+ * device -> host right behind its trace, so the copy of one piece overlaps the trace of the
+ * next without the caller issuing anything per piece. */
+int rt_trace_grid_to_host(const rt_table *t, rt_grid *g, int64_t chunk_begin, int64_t chunk_end,
+                          const rt_opts *o, double *d_abr_x, double *d_abr_y, double *h_abr_x,
+                          double *h_abr_y, double *summary, void *scratch, int32_t n_pieces, void *stream)
+{
+    if (!t || !g || !d_abr_x || !d_abr_y || !h_abr_x || !h_abr_y || !scratch || n_pieces < 1)
+        return fail(RT_ERR_INVALID, "rt_trace_grid_to_host: bad arguments");
+    if (chunk_begin < 0 || chunk_end > g->n_chunks || chunk_end < chunk_begin)
+        return fail(RT_ERR_INVALID, "rt_trace_grid_to_host: chunk range out of bounds");
+    DeviceGuard guard(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!g->side_ok) {
+        for (int k = 0; k < 2; k++) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&g->side[k], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&g->ev_side[k], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventCreateWithFlags(&g->ev_in, cudaEventDisableTiming));
+        g->side_ok = true;
+    }
+    if (n_pieces > chunk_end - chunk_begin) n_pieces = (int32_t)(chunk_end - chunk_begin);
+    if (n_pieces < 1) n_pieces = 1;
+    const int64_t sb = rt_grid_scratch_bytes(g, 0, g->n_chunks);
+    unsigned char *scr = (unsigned char *)scratch;
+    double *partials = (double *)(scr + 2*sb);
+    const int64_t tile_doubles = g->n_tiles*RT_SUMMARY_DOUBLES;
+    const int64_t base = first_ray_of_chunk(g, chunk_begin);
+    CUDA_TRY(cudaEventRecord(g->ev_in, s));                  /* grid upload, chief rays ... */
+    for (int k = 0; k < 2; k++) CUDA_TRY(cudaStreamWaitEvent(g->side[k], g->ev_in, 0));
+    for (int i = 0; i < n_pieces; i++) {
+        const int64_t cb = chunk_begin + (chunk_end - chunk_begin)*i/n_pieces;
+        const int64_t ce = chunk_begin + (chunk_end - chunk_begin)*(i + 1)/n_pieces;
+        const int64_t a = first_ray_of_chunk(g, cb) - base, n = first_ray_of_chunk(g, ce) - first_ray_of_chunk(g, cb);
+        cudaStream_t ss = g->side[i & 1];
+        rt_out out;
+        memset(&out, 0, sizeof out);
+        out.abr_x = d_abr_x + a; out.abr_y = d_abr_y + a;
+        out.flags = RT_OUT_ABR_NAN_STATUS;
+        int rc = rt_trace_grid(t, g, cb, ce, o, &out, summary ? partials + i*tile_doubles : nullptr,
+                               scr + (i & 1)*sb, ss);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_abr_x + a, d_abr_x + a, (size_t)n*sizeof(double), cudaMemcpyDeviceToHost, ss));
+        CUDA_TRY(cudaMemcpyAsync(h_abr_y + a, d_abr_y + a, (size_t)n*sizeof(double), cudaMemcpyDeviceToHost, ss));
+    }
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(cudaEventRecord(g->ev_side[k], g->side[k]));
+        CUDA_TRY(cudaStreamWaitEvent(s, g->ev_side[k], 0));
+    }
+    if (summary) return rt_combine_summaries(partials, n_pieces, g->n_tiles, summary, stream);
     return RT_OK;
 }
 

@@ -302,6 +302,15 @@ class PupilGrid(PupilGridSpec):
                                                 _stream_ptr(torch.device('cuda', self.device))))
         return self
 
+    def upload(self, spec):
+        """``rt_grid_update`` from a PupilGridSpec built earlier (same shape)."""
+        c = spec.c_spec()
+        with torch.cuda.device(self.device):
+            _abi.check(self._lib.rt_grid_update(self.handle, C.byref(c),
+                                                _stream_ptr(torch.device('cuda', self.device))))
+        self.foc, self.apply_vignetting = spec.foc, spec.apply_vignetting
+        return self
+
     def chief_ref(self, table, wvl_idx, out=None):
         """Reference image points = image intercepts of the chief rays at row ``wvl_idx`` of
         the table, computed and stored on the device (``rt_grid_chief_ref``); ``out``:
@@ -359,6 +368,43 @@ def trace_grid(table, grid, chunk_begin=0, chunk_end=None, outputs=GRID_OUTPUTS,
     res.summary = summ
     res._keep = scratch
     return res
+
+
+def trace_grid_to_host(table, grid, h_abr, chunk_begin=0, chunk_end=None, pieces=8, summary=True,
+                       workspace=None, **kwargs):
+    """Trace chunks ``[chunk_begin, chunk_end)`` of a PupilGrid and deliver the transverse
+    aberrations to page-locked HOST memory (``rt_trace_grid_to_host``): ``pieces`` launches on
+    two library-owned streams, each followed by its device->host copy.  ``h_abr``: pinned
+    ``[2, >= n]`` float64 tensor; rays that do not reach the image hold NaNs coding status /
+    failing surface (``decode_nan_status``).  Returns ``(summary [n_tiles, 16] device tensor or
+    None, workspace)``; pass ``workspace`` back in to re-use the device staging buffers.
+    Asynchronous: synchronise the current stream before reading ``h_abr``."""
+    lib = _abi.load_library()
+    device = torch.device('cuda', table.device)
+    if chunk_end is None:
+        chunk_end = grid.n_chunks
+    kwargs.setdefault('check_apertures', True)
+    kwargs.setdefault('first_surf', 1)
+    kwargs.setdefault('last_surf', table.n_ifc - 2)
+    opts = _abi.make_opts(**kwargs)
+    n = grid.rays_in_chunks(chunk_begin, chunk_end)
+    if not (h_abr.is_pinned() and h_abr.dtype == torch.float64 and h_abr.shape[0] == 2
+            and h_abr.shape[1] >= n and h_abr.stride(1) == 1):
+        raise ValueError('h_abr must be a pinned float64 tensor [2, >= n] with contiguous rows')
+    pieces = max(1, min(int(pieces), chunk_end - chunk_begin))
+    nbytes = lib.rt_trace_grid_to_host_scratch_bytes(grid.handle, pieces)
+    ws = workspace
+    if ws is None or ws['abr'].shape[1] < n or ws['scratch'].numel()*8 < nbytes or ws['device'] != device:
+        ws = {'abr': torch.empty((2, max(n, 1)), dtype=torch.float64, device=device),
+              'scratch': torch.empty(max(nbytes//8, 1), dtype=torch.float64, device=device),
+              'device': device}
+    summ = (torch.empty((grid.n_tiles, RT_SUMMARY_DOUBLES), dtype=torch.float64, device=device)
+            if summary else None)
+    _abi.check(lib.rt_trace_grid_to_host(table.handle, grid.handle, chunk_begin, chunk_end, C.byref(opts),
+                                         _ptr(ws['abr'][0]), _ptr(ws['abr'][1]), _ptr(h_abr[0]),
+                                         _ptr(h_abr[1]), _ptr(summ), _ptr(ws['scratch']), pieces,
+                                         _stream_ptr(device)))
+    return summ, ws
 
 
 def decode_nan_status(abr):

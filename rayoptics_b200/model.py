@@ -201,6 +201,113 @@ def aperture_from_dict(d):
     return cls(**d)
 
 
+# ------------------------------------------------------------------ decenters and tilts
+def euler2mat_rxyz(ai, aj, ak):
+    """``transforms3d.euler.euler2mat(ai, aj, ak, axes='rxyz')`` (transforms3d 0.4.x, un-vendored
+    dependency of the reference, setup.cfg:36): the generic Euler-to-matrix construction of
+    Gohlke's transformations.py for the axes tuple 'rxyz' = (firstaxis 2, parity 1, repetition 0,
+    frame 1), restated from the published algorithm.  Angles in radians."""
+    i, j, k = 2, 1, 0                      # firstaxis, NEXT[i + parity], NEXT[i - parity + 1]
+    ai, ak = ak, ai                        # rotating frame
+    ai, aj, ak = -ai, -aj, -ak             # odd parity
+    si, sj, sk = math.sin(ai), math.sin(aj), math.sin(ak)
+    ci, cj, ck = math.cos(ai), math.cos(aj), math.cos(ak)
+    cc, cs = ci*ck, ci*sk
+    sc, ss = si*ck, si*sk
+    M = np.eye(3)
+    M[i, i] = cj*ck
+    M[i, j] = sj*sc - cs
+    M[i, k] = sj*cc + ss
+    M[j, i] = cj*sk
+    M[j, j] = sj*ss + cc
+    M[j, k] = sj*cs - sc
+    M[k, i] = -sj
+    M[k, j] = cj*si
+    M[k, k] = cj*ci
+    return M
+
+
+def euler2rot3d(euler):
+    """util/misc_math.py:151-161: optical-design convention (alpha, beta left-handed), degrees"""
+    e = np.asarray(euler, dtype=float)
+    return euler2mat_rxyz(*np.deg2rad(np.array([-e[0], -e[1], e[2]])))
+
+
+class DecenterData:
+    """Data mirror of elem/surface.py:274-337: position / orientation changes at an interface.
+
+    dtype: 'decenter' (applied before the surface), 'reverse' (applied after it, in reverse),
+    'dec and return' (before, and undone after), 'bend' (fold mirror: before and after)."""
+
+    def __init__(self, dtype, x=0., y=0., alpha=0., beta=0., gamma=0.):
+        self.dtype = dtype
+        self.dec = np.array([x, y, 0.])
+        self.euler = np.array([alpha, beta, gamma], dtype=float)
+        self.rot_pt = np.array([0., 0., 0.])
+        self.rot_mat = None
+        self.update()
+
+    def update(self):
+        self.rot_mat = euler2rot3d(self.euler) if self.euler.any() else None
+
+    def tform_before_surf(self):
+        if self.dtype != 'reverse':
+            return self.rot_mat, self.dec
+        return None, np.array([0., 0., 0.])
+
+    def tform_after_surf(self):
+        if self.dtype in ('reverse', 'dec and return'):
+            rt = self.rot_mat
+            if rt is not None:
+                rt = rt.transpose()
+            return rt, -self.dec
+        if self.dtype == 'bend':
+            return self.rot_mat, np.array([0., 0., 0.])
+        return None, np.array([0., 0., 0.])
+
+    def to_dict(self):
+        return {'dtype': self.dtype, 'dec': self.dec.tolist(), 'euler': self.euler.tolist()}
+
+    @classmethod
+    def from_dict(cls, d):
+        o = cls(d['dtype'], d['dec'][0], d['dec'][1], *d['euler'])
+        o.dec[2] = d['dec'][2]
+        return o
+
+
+def forward_transform(s1, zdist, s2):
+    """Rotation and translation from s1 coordinates to s2 coordinates, elem/transform.py:145-166
+    (same numpy operations in the same order: the memory layout of the result decides which
+    dgemv rounding the trace applies, table.py)."""
+    t_orig = np.array([0., 0., zdist])
+    r_after_s1 = r_before_s2 = None
+    if getattr(s1, 'decenter', None):
+        r_after_s1, t_after_s1 = s1.decenter.tform_after_surf()
+        t_orig += t_after_s1
+    if getattr(s2, 'decenter', None):
+        r_before_s2, t_before_s2 = s2.decenter.tform_before_surf()
+        t_orig += t_before_s2
+    r_cascade = np.identity(3)
+    if r_after_s1 is not None:
+        t_orig = np.matmul(r_after_s1, t_orig)
+        r_cascade = r_after_s1
+        if r_before_s2 is not None:
+            r_cascade = np.matmul(r_after_s1, r_before_s2)
+    elif r_before_s2 is not None:
+        r_cascade = r_before_s2
+    return r_cascade, t_orig
+
+
+def compute_local_transforms(ifcs, gaps):
+    """elem/transform.py:79-107, forward direction: ``(r.T, t)`` per interface"""
+    tfrms = []
+    for i in range(len(ifcs) - 1):
+        r, t = forward_transform(ifcs[i], gaps[i].thi, ifcs[i + 1])
+        tfrms.append((r.transpose(), t))
+    tfrms.append((np.identity(3), np.array([0., 0., 0.])))
+    return tfrms
+
+
 # ------------------------------------------------------------------ surface
 class Surface:
     """Data mirror of elem/surface.py:38 ``Surface(Interface)``."""
@@ -221,6 +328,8 @@ class Surface:
 
     def update(self):
         self.profile.update()
+        if self.decenter is not None:
+            self.decenter.update()
         return self
 
 
@@ -494,14 +603,16 @@ class SequentialModel:
                 z_after = -z_before if ifc.interact_mode == 'reflect' else z_before
                 self.z_dir.append(z_after)
                 z_before = z_after
+        for ifc in self.ifcs:
+            ifc.update()
         if self._tfrms_given is not None:
             self.lcl_tfrms = [(np.array(rt, dtype=float), np.array(t, dtype=float))
                               for rt, t in self._tfrms_given]
+        elif any(getattr(ifc, 'decenter', None) for ifc in self.ifcs):
+            self.lcl_tfrms = compute_local_transforms(self.ifcs, self.gaps)
         else:
             self.lcl_tfrms = [(np.identity(3), np.array([0., 0., g.thi])) for g in self.gaps]
             self.lcl_tfrms.append((np.identity(3), np.array([0., 0., 0.])))
-        for ifc in self.ifcs:
-            ifc.update()
         self._version += 1
 
     def path(self, wl=None, start=None, stop=None, step=1):
@@ -623,12 +734,15 @@ class SequentialModel:
                 e['phase_element'] = ifc.phase_element.to_dict()
             if getattr(ifc, 'clear_apertures', None):
                 e['clear_apertures'] = [ca.to_dict() for ca in ifc.clear_apertures]
+            if getattr(ifc, 'decenter', None):
+                e['decenter'] = ifc.decenter.to_dict()
             if i < len(self.gaps):
                 e['thi'] = self.gaps[i].thi
                 e['medium'] = self.gaps[i].medium.to_dict()
                 e['z_dir'] = self.z_dir[i]
                 rt, t = self.lcl_tfrms[i]
-                if not np.array_equal(rt, np.identity(3)) or t[0] != 0.0 or t[1] != 0.0:
+                if self._tfrms_given is not None and (
+                        not np.array_equal(rt, np.identity(3)) or t[0] != 0.0 or t[1] != 0.0):
                     rt = np.asarray(rt)
                     order = 'C' if (rt.flags['C_CONTIGUOUS'] and not rt.flags['F_CONTIGUOUS']) else 'F'
                     e['tfrm'] = {'rt': rt.tolist(), 't': np.asarray(t).tolist(), 'order': order}
@@ -653,6 +767,8 @@ class SequentialModel:
                                              for a in e.get('clear_apertures', [])])
                 if 'phase_element' in e:
                     s.phase_element = phase_element_from_dict(e['phase_element'])
+            if 'decenter' in e:
+                s.decenter = DecenterData.from_dict(e['decenter'])
             ifcs.append(s)
             if i < n - 1:
                 gaps.append(Gap(e['thi'], medium_from_dict(e['medium'])))

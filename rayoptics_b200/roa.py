@@ -157,14 +157,20 @@ def open_roa(path):
         if kind != 'Surface':
             raise NotImplementedError(f'.roa interface type {kind}')
         phase_element = _phase_element(a.get('phase_element'))
-        if a.get('decenter') is not None:
-            raise NotImplementedError('.roa decentered interfaces: supply lcl_tfrms explicitly')
+        decenter = None
+        if a.get('decenter') is not None:       # DecenterData, elem/surface.py:274-337 (json_tricks: vars())
+            da = a['decenter'].get('attributes', a['decenter'])
+            dec, eul = _val(da['dec']), _val(da['euler'])
+            decenter = M.DecenterData(da.get('_dtype', da.get('dtype', 'decenter')), dec[0], dec[1],
+                                      eul[0], eul[1], eul[2])
+            decenter.dec[2] = dec[2]
         prf = a.get('profile')
         prf = pdict[str(a['profile_id'])] if prf is None else prf
         ifcs.append(M.Surface(lbl=a.get('label', ''), profile=_profile(prf),
                               interact_mode=a['interact_mode'],
                               max_aperture=a.get('max_aperture', 1.0),
                               clear_apertures=[_aperture(c) for c in a.get('clear_apertures', [])]))
+        ifcs[-1].decenter = decenter
         if phase_element is not None:       # the reference tests hasattr(ifc, 'phase_element')
             ifcs[-1].phase_element = phase_element
     gaps = [M.Gap(g['attributes']['thi'], _medium(g['attributes']['medium']))

@@ -16,7 +16,12 @@ V_d = vv.v, CODE V's six-digit form), or a catalog name looked up in ``glass_map
 the ``_CATALOG`` suffix).  There is no glass catalog in this package: an unknown name
 raises ``KeyError`` naming the glass, it is never guessed.
 
-Not read (raise ``NotImplementedError``): tilts and decenters (ADE.. / XDE.. / DAR / BEN),
+Tilts and decenters (codev/cmdproc.py:544-576): XDE YDE ZDE ADE BDE CDE create a
+``DecenterData('decenter')`` on the current surface, DAR / BEN / REV change its type to
+'dec and return' / 'bend' / 'reverse'; the local transforms follow from them as in
+elem/transform.py (model.compute_local_transforms).
+
+Not read (raise ``NotImplementedError``): BAS / RET (basic decenters, return to a surface),
 zoom data, special surface types.  Solves (CCY, THC, PIM) and DER lines are ignored like
 the reference does when it only builds the model.
 """
@@ -29,7 +34,8 @@ from .opticalspec import OpticalSpecs, WvlSpec, PupilSpec, FieldSpec, FocusRange
 
 _IGNORED = {'LEN', 'INI', 'WTW', 'WTF', 'CCY', 'THC', 'PIM', 'DER', 'GO', 'CUF', 'GL1', 'GL2',
             'SLB', 'THM', 'TEM', 'PRE', 'INF', 'MNR', 'MXR', 'CUM', 'VLZ', 'VUZ', 'RMD', 'GLB'}
-_TILTS = {'ADE', 'BDE', 'CDE', 'XDE', 'YDE', 'ZDE', 'DAR', 'BEN', 'REV', 'BAS', 'RET'}
+_TILTS = {'ADE', 'BDE', 'CDE', 'XDE', 'YDE', 'ZDE', 'DAR', 'BEN', 'REV'}
+_TILTS_UNREAD = {'BAS', 'RET'}
 _ASP_COEFS = 'ABCDEFGHJ'
 
 
@@ -119,8 +125,17 @@ def open_seq(path, glass_map=None):
         elif toks[0].upper() in _ASP_COEFS and cur is not None:
             cur['coefs'] = cur['coefs'] or [0.0]*10
             cur['coefs'][_ASP_COEFS.index(toks[0].upper()) + 1] = float(args[0])   # A -> r**4
-        elif tla in _TILTS:
-            raise NotImplementedError(f'.seq command {toks[0]}: tilts / decenters are not read')
+        elif tla in _TILTS and toks[0].upper() == tla and cur is not None:
+            dc = cur.setdefault('decenter', {'dtype': 'decenter', 'dec': [0., 0., 0.],
+                                             'euler': [0., 0., 0.]})
+            if tla in ('XDE', 'YDE', 'ZDE'):
+                dc['dec']['XYZ'.index(tla[0])] = float(args[0])
+            elif tla in ('ADE', 'BDE', 'CDE'):
+                dc['euler']['ABC'.index(tla[0])] = float(args[0])
+            else:
+                dc['dtype'] = {'DAR': 'dec and return', 'BEN': 'bend', 'REV': 'reverse'}[tla]
+        elif tla in _TILTS_UNREAD:
+            raise NotImplementedError(f'.seq command {toks[0]}: basic decenters / returns are not read')
         elif tla in ('SPS', 'SCO'):
             raise NotImplementedError(f'.seq command {toks[0]}: special surface types are not read')
         # _IGNORED and anything else: not part of the path description (the reference logs
@@ -148,6 +163,8 @@ def open_seq(path, glass_map=None):
         ifc = M.Surface(profile=prf, interact_mode=mode)
         if s['cir'] is not None:
             ifc.max_aperture = s['cir']
+        if s.get('decenter'):
+            ifc.decenter = M.DecenterData.from_dict(s['decenter'])
         if s['stop']:
             stop_surface = i
         ifcs.append(ifc)

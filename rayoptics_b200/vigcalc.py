@@ -386,6 +386,163 @@ def set_vig(opm, **kwargs):
         calc_vignetting_for_field(opm, fld, wvl, **kwargs)
 
 
+# --- the same searches for ALL fields and pupil directions in lock step ----------------------
+# Each (field, direction) search of calc_vignetted_ray / iterate_pupil_ray is a generator that
+# yields the ray it wants traced and receives the result; the driver advances all of them
+# together and traces each round's requests as (at most two) bundles.  The arithmetic of every
+# search -- including scipy's secant iteration, restated step for step -- is that of the
+# sequential code above, so the vignetting factors are the same numbers; only the number of
+# launches changes (rounds instead of rounds x searches).
+
+def cuda_ray_fn(opt_model, table=None, device=0):
+    """``ray_fn(p0 [3, n], d0 [3, n], wvl, check_apertures, pt_inside_fuzz) -> dict`` of host
+    arrays ``full [n_ifc, 10, n]``, ``n_seg``, ``status``, ``fail_surf`` on the CUDA engine."""
+    from . import engine as E
+    from .analyses import _table_for
+    tab = _table_for(opt_model, table, device)
+
+    def fn(p0, d0, wvl, check_apertures=False, pt_inside_fuzz=None):
+        w = np.full(p0.shape[1], tab.wvl_index(wvl), dtype=np.int32)
+        r = E.trace_bundle(tab, p0, d0, wvl_idx=w, full=True, outputs=('n_seg', 'status', 'fail_surf'),
+                           first_surf=1, last_surf=tab.n_ifc - 2, check_apertures=check_apertures,
+                           pt_inside_fuzz=pt_inside_fuzz)
+        return {'full': r.full.cpu().numpy(), 'n_seg': r.n_seg.cpu().numpy(),
+                'status': r.status.cpu().numpy(), 'fail_surf': r.fail_surf.cpu().numpy()}
+    return fn
+
+
+class _RayAnswer:
+    """what a search reads from one traced ray"""
+    __slots__ = ('status', 'surf', 'full')
+
+    def __init__(self, status, surf, full):
+        self.status, self.surf, self.full = int(status), int(surf), full
+
+
+def _secant(x0, tol=1e-6, maxiter=50):
+    """scipy.optimize.newton(f, x0, tol=tol) without derivative (the secant branch of
+    scipy/optimize/_zeros_py.py), as a generator: yields x, receives f(x), returns the root."""
+    p0 = 1.0*x0
+    eps = 1e-4
+    p1 = x0*(1 + eps)
+    p1 += (eps if p1 >= 0 else -eps)
+    q0 = yield p0
+    q1 = yield p1
+    if abs(q1) < abs(q0):
+        p0, p1, q0, q1 = p1, p0, q1, q0
+    p = p1
+    for _itr in range(maxiter):
+        if q1 == q0:
+            return (p1 + p0)/2.0
+        if abs(q1) > abs(q0):
+            p = (-q0/q1*p1 + p0)/(1 - q0/q1)
+        else:
+            p = (-q1/q0*p0 + p1)/(1 - q1/q0)
+        if np.isclose(p, p1, rtol=0.0, atol=tol):
+            return p
+        p0, q0 = p1, q1
+        p1 = p
+        q1 = yield p1
+    return p
+
+
+def _pupil_ray_search(indx, xy, start_r0, r_target):
+    """iterate_pupil_ray as a generator of ('free', rel_p1) requests; returns start_coords"""
+    start_coords = np.array([0., 0.])
+    if indx is None:
+        start_coords[xy] = r_target
+        return start_coords
+    sec = _secant(start_r0)
+    try:
+        x = next(sec)
+        while True:
+            rel_p1 = np.array([0., 0.])
+            rel_p1[xy] = x
+            ans = yield ('free', rel_p1)
+            if ans.status != 0:
+                limit = indx if ans.status == 1 else indx - 1       # 1: TraceMissedSurfaceError
+                if ans.surf <= limit:
+                    start_coords[xy] = 0.9*rel_p1[xy]
+                    return start_coords
+            p = ans.full[indx, 0:3]
+            r_ray = math.copysign(math.sqrt(p[0]**2 + p[1]**2), r_target)
+            x = sec.send(r_ray - r_target)
+    except StopIteration as done:
+        start_coords[xy] = done.value
+    return start_coords
+
+
+def _vignetted_ray_search(sm, xy, start_dir, max_iter_count=50):
+    """calc_vignetted_ray as a generator of ('clip' | 'free', rel_p1) requests; returns vig"""
+    rel_p1 = np.array(start_dir, dtype=float)
+    still_iterating, clip_indx, iter_count = True, None, 0
+    while still_iterating and iter_count < max_iter_count:
+        iter_count += 1
+        ans = yield ('clip', rel_p1)
+        if ans.status != 0:
+            indx = ans.surf
+            if indx == clip_indx:
+                still_iterating = False
+            else:
+                r_target = _edge_pt_target(sm.ifcs[indx], start_dir)
+                rel_p1 = yield from _pupil_ray_search(indx, xy, rel_p1[xy], r_target[xy])
+                clip_indx = indx
+        else:
+            if clip_indx is not None:
+                still_iterating = False
+            else:
+                stop_indx = sm.stop_surface
+                if stop_indx is not None:
+                    r_target = _edge_pt_target(sm.ifcs[stop_indx], start_dir)
+                    rel_p1 = yield from _pupil_ray_search(stop_indx, xy, rel_p1[xy], r_target[xy])
+                    clip_indx = stop_indx
+                else:
+                    still_iterating = False
+    return 1.0 - (rel_p1[xy]/start_dir[xy])
+
+
+def set_vig_batched(opm, ray_fn=None, wvl=None, max_iter_count=50):
+    """``set_vig`` (raytr/vigcalc.py:83-90,227-342,393-471) with the four edge searches of every
+    field advanced in lock step: each round traces the pending rays of all searches as one
+    bundle per trace option.  Same vignetting factors as ``set_vig``.  Returns the number of
+    bundle launches."""
+    osp, sm = opm.optical_spec, opm.seq_model
+    if ray_fn is None:
+        ray_fn = cuda_ray_fn(opm)
+    wvl = osp.spectral_region.central_wvl if wvl is None else wvl
+    fields = list(osp.field_of_view.fields)
+    starts = osp.pupil.pupil_rays[1:]
+    searches, want, vig = {}, {}, {}
+    for fi in range(len(fields)):
+        for i in range(4):
+            g = _vignetted_ray_search(sm, i//2, starts[i], max_iter_count)
+            searches[(fi, i)] = g
+            want[(fi, i)] = next(g)
+    launches = 0
+    while want:
+        answers = {}
+        for kind, opts in (('clip', dict(check_apertures=True, pt_inside_fuzz=1e-4)),
+                           ('free', dict(check_apertures=False))):
+            keys = [k for k, (kd, _) in want.items() if kd == kind]
+            if not keys:
+                continue
+            flds = [fields[k[0]] for k in keys]
+            p0, d0 = _start_rays(opm, flds, [f.aim_info for f in flds], [want[k][1] for k in keys])
+            r = ray_fn(p0, d0, wvl, **opts)
+            launches += 1
+            for j, k in enumerate(keys):
+                answers[k] = _RayAnswer(r['status'][j], r['fail_surf'][j], r['full'][:, :, j])
+        for k, ans in answers.items():
+            try:
+                want[k] = searches[k].send(ans)
+            except StopIteration as done:
+                vig[k] = done.value
+                del want[k]
+    for fi, fld in enumerate(fields):
+        fld.vux, fld.vlx, fld.vuy, fld.vly = (vig[(fi, i)] for i in range(4))
+    return launches
+
+
 # --- the reference's own aiming iteration (raytr/trace.py:313-415) ----------------------------
 def iterate_ray(opt_model, ifcx, xy_target, fld, wvl, trace_fn=None):
     """Iterate a ray to ``xy_target`` on interface ``ifcx``; returns the aim point on the

@@ -6,8 +6,13 @@ resolved by the un-vendored ``opticalglass`` catalogs.  This reader builds the
 symmetric sequential system:
 
   UNIT, NAME, ENPD / FNUM / OBNA, WAVM (or WAVL / WWGT), FTYP, XFLN / YFLN,
-  VDXN VDYN VCXN VCYN, SURF with TYPE (STANDARD, EVENASPH), CURV, DISZ, GLAS, DIAM,
-  CONI, PARM, STOP.
+  VDXN VDYN VCXN VCYN, SURF with TYPE (STANDARD, EVENASPH, XOSPHERE, TOROIDAL, COORDBRK),
+  CURV, DISZ, GLAS, DIAM, CONI, PARM, XDAT, STOP.
+
+Coordinate breaks (zmxread.py:314-316,341-355): a COORDBRK surface becomes a phantom
+interface carrying ``DecenterData('decenter')`` with PARM 1,2 = x, y decenter, PARM 3,4,5 =
+tilts about x, y, z and a non-zero PARM 6 (order flag) turning it into a 'reverse' decenter;
+the local transforms follow as in elem/transform.py (model.compute_local_transforms).
 
 Conventions copied from the reference: wavelengths are collected in order of first
 appearance, a trailing 550 nm filler is dropped and the reference wavelength is the middle
@@ -18,8 +23,8 @@ one (zmxread.py:251-257); vignetting is converted to the asymmetric form
 Glasses: ``MIRROR``, a model glass (``GLAS ___BLANK 1 0 nd vd ...``), or a catalog name
 looked up in ``glass_map`` (name -> Medium, index, or ``(n_d, V_d)``; case-insensitive, with
 and without a ``_MOLD``-type suffix).  This package ships no glass catalog: unknown names
-raise ``KeyError``.  Coordinate breaks, non-sequential data, floating apertures (FLOA) and
-other surface types raise ``NotImplementedError``.
+raise ``KeyError``.  Non-sequential data, floating apertures (FLOA) and other surface types
+raise ``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -93,7 +98,7 @@ def open_zmx(path, glass_map=None):
             continue
         elif cmd == 'TYPE':
             cur['type'] = items[0]
-            if items[0] not in ('STANDARD', 'EVENASPH'):
+            if items[0] not in ('STANDARD', 'EVENASPH', 'XOSPHERE', 'TOROIDAL', 'COORDBRK'):
                 raise NotImplementedError(f'.zmx surface TYPE {items[0]}')
         elif cmd == 'CURV':
             cur['cv'] = float(items[0])
@@ -109,6 +114,8 @@ def open_zmx(path, glass_map=None):
             cur['cc'] = float(items[0])
         elif cmd == 'PARM':
             cur['parm'][int(items[0])] = float(items[1])
+        elif cmd == 'XDAT':
+            cur.setdefault('xdat', {})[int(items[0])] = float(items[1])
         elif cmd == 'DIAM':
             cur['diam'] = float(items[0])
     if len(surfs) < 2:
@@ -126,10 +133,27 @@ def open_zmx(path, glass_map=None):
         g = s['glass']
         if g is not None and g.upper() == 'MIRROR':
             mode, g = 'reflect', None
+        decenter = None
         if s['type'] == 'EVENASPH':
             k = max(s['parm']) if s['parm'] else 0
             coefs = [s['parm'].get(j + 1, 0.0) for j in range(max(k, 1))]
             prf = M.EvenPolynomial(c=s['cv'], cc=s['cc'], coefs=coefs)
+        elif s['type'] == 'XOSPHERE':           # XDAT 1 = number of terms, 2 = norm radius, 3.. = r, r^2, ...
+            xd = s.get('xdat', {})
+            coefs = [xd[j] for j in sorted(xd) if j >= 3]
+            prf = M.RadialPolynomial(c=s['cv'], cc=s['cc'], coefs=coefs)
+        elif s['type'] == 'TOROIDAL':           # PARM 1 = radius of rotation, 2.. = y^2, y^4, ...
+            pm = s['parm']
+            coefs = [pm[j] for j in sorted(pm) if j > 1]
+            rR = pm.get(1, 0.0)
+            prf = M.YToroid(c=s['cv'], cR=(1.0/rR if rR != 0.0 else 0.0), cc=s['cc'], coefs=coefs)
+        elif s['type'] == 'COORDBRK':
+            pm = s['parm']
+            decenter = M.DecenterData('reverse' if pm.get(6, 0.0) != 0 else 'decenter',
+                                      x=pm.get(1, 0.0), y=pm.get(2, 0.0), alpha=pm.get(3, 0.0),
+                                      beta=pm.get(4, 0.0), gamma=pm.get(5, 0.0))
+            prf = M.Spherical(c=0.0)
+            mode = 'phantom'
         elif s['cc'] != 0.0:
             prf = M.Conic(c=s['cv'], cc=s['cc'])
         else:
@@ -137,6 +161,7 @@ def open_zmx(path, glass_map=None):
         if i == 0 or i == len(surfs) - 1:
             mode = 'dummy'
         ifc = M.Surface(profile=prf, interact_mode=mode)
+        ifc.decenter = decenter
         if s['diam'] is not None and s['diam'] != 0.0:
             ifc.max_aperture = s['diam']
         if s['stop']:

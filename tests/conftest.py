@@ -10,7 +10,7 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 MODEL_NAMES = ['singlet', 'dblgauss', 'triplet', 'rc', 'cellphone', 'cellphone_even',
-               'evenasph', 'zoom52', 'thin_triplet', 'exotic']
+               'evenasph', 'zoom52', 'thin_triplet', 'exotic', 'threemir']
 # models with diffractive phase elements: the reference evaluates x**k with libm pow(), so the
 # device carries tolerance parity there (the oracle, on the same libm, stays bit-exact)
 # finite-conjugate relays specified by an angular object-space pupil ('NA', 'f/#')

@@ -134,6 +134,21 @@ def write_kat():
     # elem/tests/test_profiles.py:127-154 test_dbgauss_s1: Spherical(c=1/r1), ray from
     # p=[0, 25, 0] along +z (p0 in the test is [0, 0, -1] -> s = 1)
     kat['profile_s1'] = {'r1': 56.20238, 'y0': 25.0, 's': 5.866433424372758, 'rtol': 1e-14}
+    # codev/tests/threemrc.lis (CODE V's own ray listing of codev/tests/threemir.seq), axial field:
+    # rays launched parallel to the axis at height y0 on surface 1; (x, y, z) at surfaces 1..5 and
+    # TAN Y after them.  Pins the decenter / tilt convention (elem/surface.py:274-337,
+    # elem/transform.py:145-166, transforms3d euler2mat 'rxyz') to the listing's 6 decimals.
+    kat['threemir_lis'] = {
+        'source': 'codev/tests/threemrc.lis:233-262',
+        'abs_tol': 5e-6,
+        'rays': [
+            {'y0': 144.927530, 'xyz': [[0., 144.927530, 0.], [0., 97.957122, -4.527500], [0., 0., 0.],
+                                       [0., -6.195034, -0.059224], [0., -113.854355, -14.557556]],
+             'tan_y': [0., 0.344215, 0.309800, -0.363227, -0.165989]},
+            {'y0': 194.927530, 'xyz': [[0., 194.927530, 0.], [0., 149.393568, -10.521171],
+                                       [0., 23.585027, 0.], [0., 17.314156, -0.463156],
+                                       [0., -75.816236, -6.384849]],
+             'tan_y': [0., 0.454650, 0.417646, -0.307504, -0.040803]}]}
     with open(os.path.join(HERE, 'kat.json'), 'w') as f:
         json.dump(kat, f, indent=1)
 
@@ -143,7 +158,7 @@ def main():
     rng = np.random.default_rng(0)
     plan = {'singlet': (7, 60), 'dblgauss': (5, 150), 'triplet': (5, 80), 'rc': (5, 60),
             'cellphone': (3, 100), 'cellphone_even': (3, 100), 'evenasph': (3, 100),
-            'zoom52': (3, 80), 'thin_triplet': (5, 100), 'exotic': (7, 400), 'hybrid': (5, 300), 'diffractive': (7, 500), 'diffractive_wild': (9, 800)}
+            'zoom52': (3, 80), 'threemir': (7, 300), 'thin_triplet': (5, 100), 'exotic': (7, 400), 'hybrid': (5, 300), 'diffractive': (7, 500), 'diffractive_wild': (9, 800)}
     only = sys.argv[1:]
     for name, (num, n_wild) in plan.items():
         if only and name not in only:

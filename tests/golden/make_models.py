@@ -20,6 +20,9 @@ Sources (numbers only; no reference source code is copied):
   evenasph    /root/reference/src/rayoptics/zemax/tests/US08427765-1.ZMX geometry, with
               catalogue glasses replaced by (n_d, V_d) Cauchy models (approximate)
   zoom52      synthetic 50-surface stack (recipe below), 25 fields x 7 wavelengths
+  threemir    /root/reference/src/rayoptics/codev/tests/threemir.seq (CODE V three-mirror
+              compact: conic / aspheric mirrors, every surface decentered and tilted with
+              'dec and return'), read by rayoptics_b200/seq.py
 """
 import importlib.util
 import os
@@ -32,7 +35,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_harness as rh                      # noqa: E402
-from rayoptics_b200 import model as M, roa, vigcalc       # noqa: E402
+from rayoptics_b200 import model as M, roa, vigcalc, seq  # noqa: E402
 from rayoptics_b200.opticalspec import (OpticalSpecs, WvlSpec, PupilSpec, FieldSpec,  # noqa: E402
                                         FocusRange)
 
@@ -350,9 +353,16 @@ def relay(pupil_key, pupil_value, name):
     return finish(M.OpticalModel(sm, osp, name=name), aim=False, apertures=True)
 
 
+def threemir():
+    opm = seq.open_seq(f'{REF}/codev/tests/threemir.seq')
+    opm.name = 'threemir'
+    return finish(opm, aim=True, apertures=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     models = {
+        'threemir': threemir,
         'singlet': lambda: from_roa('models/singlet_f5.roa', 'singlet'),
         'dblgauss': dblgauss,
         'triplet': lambda: from_roa('models/Sasian Triplet.roa', 'triplet'),

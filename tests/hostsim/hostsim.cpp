@@ -36,13 +36,15 @@ void run_lean(const rt_surface_desc *surfs, int n_ifc, const double *n_by_wvl, i
 {
     std::vector<LeanSurf> ls(n_ifc);
     std::vector<LeanIdx> li((size_t)n_ifc*n_wvl);
+    std::vector<LeanPoly> lp(n_ifc);
     build_plan(surfs, n_by_wvl, n_ifc, n_wvl, o, ls.data(), li.data());
+    if (POLY) build_poly_plan(surfs, n_ifc, lp.data());
     for (int64_t r = 0; r < n; r++) {
         Vec3 p = {p0[r], p0[n + r], p0[2*n + r]}, d = {d0[r], d0[n + r], d0[2*n + r]};
         const int w = wvl_idx ? wvl_idx[r] : o.wvl_idx;
         FullWriter fw = {OUT == 2 ? out.full + r : nullptr, n};
         RayResult R;
-        trace_ray_lean<OUT, false, POLY>(ls.data(), li.data() + (int64_t)w*n_ifc, surfs, n_ifc, o, p, d, fw, R);
+        trace_ray_lean<OUT, false, POLY>(ls.data(), li.data() + (int64_t)w*n_ifc, lp.data(), surfs, n_ifc, o, p, d, fw, R);
         store(out, r, R, OUT >= 1);
     }
 }

@@ -168,3 +168,22 @@ def test_spot_diagram_end_to_end(tables, oracle, name, num):
                 m = ok[t*per:(t + 1)*per]
                 assert same(sd.grids[fi][wi], want['abr'][:, t*per:(t + 1)*per][:, m].T)
                 assert sd.summary['n_ok'][fi, wi] == m.sum()
+
+
+@pytest.mark.parametrize('name', ['dblgauss', 'evenasph'])
+def test_cuda_set_vig_batched(name):
+    """vigcalc.set_vig_batched on the CUDA engine (bundles of all fields' edge searches) == the
+    same searches fed by the oracle: identical vignetting factors."""
+    import sys
+    from rayoptics_b200 import vigcalc as V
+    sys.path.insert(0, __file__.rsplit('/', 1)[0])
+    from test_trace_drivers import oracle_ray_fn
+    a, b = load_model(name), load_model(name)
+    for m in (a, b):
+        for f in m.optical_spec.field_of_view.fields:
+            f.vux = f.vlx = f.vuy = f.vly = 0.0
+    V.set_vig_batched(a, oracle_ray_fn(a))
+    launches = V.set_vig_batched(b)                      # cuda_ray_fn
+    for x, y in zip(a.optical_spec.field_of_view.fields, b.optical_spec.field_of_view.fields):
+        assert (x.vux, x.vlx, x.vuy, x.vly) == (y.vux, y.vlx, y.vuy, y.vly)
+    assert 0 < launches < 200

@@ -352,3 +352,86 @@ def test_nan_status_decoding():
     st, fs = E.decode_nan_status(abr)
     assert st.tolist() == [0, 3, 1, 5] and fs.tolist() == [-1, 12, 0, 7]
     assert np.isnan(abr[:, 1:]).all()
+
+
+def test_tilts_and_decenters_against_the_codev_listing(oracle):
+    """Decenter / tilt convention pinned by an external known answer: the reference ships CODE V's
+    ray listing (codev/tests/threemrc.lis) of its three-mirror test lens, whose every surface is
+    decentered and tilted ('dec and return').  Rays of the fixture model (read from the same .seq by
+    rayoptics_b200/seq.py: DecenterData, Euler rotation, forward transforms) land on the listed
+    coordinates to the listing's 6 decimals."""
+    import json
+    kat = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'kat.json')))['threemir_lis']
+    opm = load_model('threemir')
+    sm = opm.seq_model
+    assert sum(1 for ifc in sm.ifcs if ifc.decenter is not None) == 5
+    descs, n_by_wvl, wvls = T.describe_model(sm)
+    opts = _abi.make_opts(first_surf=1, last_surf=len(descs) - 2)
+    for ray in kat['rays']:
+        p0 = np.array([[0.], [ray['y0']], [0.]])
+        d0 = np.array([[0.], [0.], [1.]])
+        r = oracle.trace_bundle(descs, n_by_wvl, p0, d0, np.zeros(1, np.int32), opts, want_full=True)
+        assert r['status'][0] == 0
+        got = r['full'][1:6, 0:3, 0]
+        assert np.abs(got - np.array(ray['xyz'])).max() < kat['abs_tol']
+        d = r['full'][1:6, 3:6, 0]
+        assert np.abs(d[:, 1]/d[:, 2] - np.array(ray['tan_y'])).max() < kat['abs_tol']
+
+
+def test_seq_reader_tilt_commands():
+    """XDE YDE ZDE ADE BDE CDE DAR BEN REV (codev/cmdproc.py:544-576) on the reference's own tilt test
+    files: fold mirrors ('bend') keep the axial ray on every vertex, and the decenter / reverse pairs
+    bring it back onto the axis -- what those files were written to show."""
+    from rayoptics_b200 import seq
+    from oracle import rt_oracle
+    base = '/root/reference/src/rayoptics/codev/tests'
+    if not os.path.isdir(base):
+        pytest.skip('/root/reference not present')
+    for name, on_vertex, on_axis in (('dec_tilt_test.seq', True, True), ('tilt_test.seq', False, False),
+                                     ('dec_test.seq', False, True), ('dec_rev_tilt_test.seq', False, True),
+                                     ('dar_test.seq', False, True)):
+        opm = seq.open_seq(os.path.join(base, name))
+        descs, n_by_wvl, wvls = T.describe_model(opm.seq_model)
+        r = rt_oracle.trace_bundle(descs, n_by_wvl, np.zeros((3, 1)), np.array([[0.], [0.], [1.]]),
+                                   np.zeros(1, np.int32),
+                                   _abi.make_opts(first_surf=1, last_surf=len(descs) - 2), want_full=True)
+        assert r['status'][0] == 0
+        pts, dirs = r['full'][:, 0:3, 0], r['full'][:, 3:6, 0]
+        assert abs(abs(dirs[-1, 2]) - 1.0) < 1e-12
+        if on_axis:
+            assert np.abs(pts[-1, 0:2]).max() < 1e-9
+        else:                                   # tilt_test.seq: 100 mm along a 45 degree leg
+            assert abs(pts[-1, 1] + 100.0*np.sin(np.pi/4)) < 1e-9
+        if on_vertex:
+            assert np.abs(pts).max() < 1e-9
+    d = opm.seq_model.ifcs[2].decenter                      # dar_test.seq: YDE 1; ADE 45; DAR
+    assert d.dtype == 'dec and return' and d.dec[1] == 1.0 and d.euler[0] == 45.0
+    m2 = M.OpticalModel.from_dict(opm.to_dict())            # decenters survive the JSON round trip
+    for (ra, ta), (rb, tb) in zip(opm.seq_model.lcl_tfrms, m2.seq_model.lcl_tfrms):
+        assert np.array_equal(ra, rb) and np.array_equal(ta, tb)
+        assert ra.flags['C_CONTIGUOUS'] == rb.flags['C_CONTIGUOUS']
+
+
+def test_zmx_reader_coordinate_breaks():
+    """COORDBRK surfaces (zemax/zmxread.py:314-316,341-355) of the reference's own Zemax test files:
+    phantom interfaces with DecenterData; the folded system of HoO-V2C18Ex66 (9 coordinate breaks)
+    brings the axial ray back onto the axis, direction (0, 0, 1)."""
+    from rayoptics_b200 import zmx
+    from oracle import rt_oracle
+    base = '/root/reference/src/rayoptics/zemax/tests'
+    if not os.path.isdir(base):
+        pytest.skip('/root/reference not present')
+    opm = zmx.open_zmx(os.path.join(base, 'HoO-V2C18Ex66.zmx'),
+                       glass_map={'BK7': (1.5168, 64.17), 'SF2': (1.64769, 33.85), 'F2': (1.62004, 36.37),
+                                  'SK16': (1.62041, 60.32), 'N-BK7': (1.5168, 64.17), 'SILICA': (1.4585, 67.8),
+                                  'SF5': (1.6727, 32.2), 'BAK4': (1.5688, 56.1), 'SF1': (1.71736, 29.5),
+                                  'K5': (1.52249, 59.5), 'SK2': (1.60738, 56.65), 'LAK9': (1.691, 54.7)})
+    sm = opm.seq_model
+    cb = [i for i in sm.ifcs if i.decenter is not None]
+    assert len(cb) == 9 and all(i.interact_mode == 'phantom' for i in cb)
+    assert any(i.decenter.dtype == 'reverse' for i in cb) or all(i.decenter.dtype == 'decenter' for i in cb)
+    descs, n_by_wvl, _ = T.describe_model(sm)
+    r = rt_oracle.trace_bundle(descs, n_by_wvl, np.zeros((3, 1)), np.array([[0.], [0.], [1.]]),
+                               np.zeros(1, np.int32), _abi.make_opts(first_surf=1, last_surf=len(descs) - 2))
+    assert r['status'][0] == 0
+    assert np.abs(r['last'][0:2, 0]).max() < 1e-9 and abs(r['last'][5, 0] - 1.0) < 1e-12

@@ -428,6 +428,37 @@ def test_drivers_against_the_references_drivers(name, fi, wvl):
                                    check_apertures=True), want)
 
 
+def oracle_ray_fn(opm):
+    from oracle import rt_oracle
+    descs, n_by_wvl, wvls = T.describe_model(opm.seq_model)
+
+    def fn(p0, d0, wvl, check_apertures=False, pt_inside_fuzz=None):
+        w = np.full(p0.shape[1], opm.seq_model.index_for_wavelength(wvl), dtype=np.int32)
+        return rt_oracle.trace_bundle(descs, n_by_wvl, p0, d0, w,
+                                      _abi.make_opts(first_surf=1, last_surf=len(descs) - 2,
+                                                     check_apertures=check_apertures,
+                                                     pt_inside_fuzz=pt_inside_fuzz),
+                                      want_full=True, wvls=wvls)
+    return fn
+
+
+@pytest.mark.parametrize('name', ['dblgauss', 'triplet', 'evenasph', 'rc'])
+def test_set_vig_batched_equals_set_vig(name):
+    """vigcalc.set_vig_batched (all searches in lock step, bundles) gives the vignetting
+    factors of the sequential set_vig bit for bit, in far fewer launches."""
+    from rayoptics_b200 import vigcalc as V
+    a, b = load_model(name), load_model(name)
+    for m in (a, b):
+        for f in m.optical_spec.field_of_view.fields:
+            f.vux = f.vlx = f.vuy = f.vly = 0.0
+    V.set_vig(a, tracer=oracle_tracer)
+    launches = V.set_vig_batched(b, oracle_ray_fn(b))
+    fa, fb = a.optical_spec.field_of_view.fields, b.optical_spec.field_of_view.fields
+    for x, y in zip(fa, fb):
+        assert (x.vux, x.vlx, x.vuy, x.vly) == (y.vux, y.vlx, y.vuy, y.vly)
+    assert launches < 12*len(fa) + 40
+
+
 def R_TraceError():
     from oracle import ref_harness as rh
     return rh.ref().traceerror.TraceError
