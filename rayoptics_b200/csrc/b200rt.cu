@@ -279,10 +279,17 @@ __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_
     const bool chunk_slots = G.chunks_per_tile <= (int64_t)gridDim.x;
     int64_t cur_tile = -1;
     if (SUMMARY && !chunk_slots) acc_init(acc);
-    for (int64_t c = chunk_begin + blockIdx.x; c < chunk_end; c += gridDim.x) {
+    /* Which 32 rays of a chunk a warp takes rotates from chunk to chunk.  A chunk is a run of
+     * consecutive pupil samples along y, so with a fixed assignment the warp that always gets
+     * the pupil-edge end (rays clipped at the first surfaces) would finish all its chunks long
+     * before the warp that always gets the centre, and the SM would run the second half of the
+     * kernel short of warps (ncu r02e: 19.8 of 24 resident warps active on average).  Lanes keep
+     * consecutive rays: every load / store stays coalesced. */
+    unsigned rot = 0;
+    for (int64_t c = chunk_begin + blockIdx.x; c < chunk_end; c += gridDim.x, rot += 32) {
         const int64_t tile = c/G.chunks_per_tile;
         const int64_t lc = c - tile*G.chunks_per_tile;
-        const int64_t loc = lc*RT_BLOCK + threadIdx.x;
+        const int64_t loc = lc*RT_BLOCK + (threadIdx.x + rot) % RT_BLOCK;
         const bool have = loc < G.rays_per_tile;
         if (SUMMARY && !chunk_slots && tile != cur_tile) {
             if (cur_tile >= 0) acc_flush(acc, scratch, cur_tile, blockIdx.x, sl);

@@ -60,6 +60,9 @@ def seeded_bundle(opm, n, rng):
     d0 = np.zeros((3, n))
     scale = np.where(rng.random(n) < 0.8, 1.05, 3.0)
     aim = fod.enp_radius*scale*rng.uniform(-1, 1, (2, n))
+    aims = [f.aim_info for f in osp.field_of_view.fields if f.aim_info is not None]
+    if aims:                                    # off-axis systems: the beam is where the chief rays are aimed
+        aim += np.mean(np.array(aims, dtype=float), axis=0)[:, None]
     if abs(sm.gaps[0].thi) > 1e8:
         fmax = abs(osp.fov.max_field_value()) if osp.fov.key[1] == 'angle' else \
             np.degrees(abs(np.arctan(fod.pr_slp0)))
