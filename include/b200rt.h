@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 3
+#define RT_ABI_VERSION 4
 #define RT_MAX_COEFS 20     /* EvenPolynomial uses <=10, RadialPolynomial <=20 */
 #define RT_MAX_PHASE_COEFS 10
 #define RT_MAX_APERTURES 4  /* Surface.clear_apertures entries honoured per interface */
@@ -97,7 +97,13 @@ enum rt_pupil_kind {
                            rt_field_desc: pt0 = -(obj_dist + z_enp) [d0x/d0z, d0y/d0z, 0], aim = aim_pt */
     RT_PUPIL_NA = 1,    /* angular, object-space NA: dir_tot = sin_ang*pupil + cr_dir, :368-398.
                            rt_field_desc: pt0 = object point p0, aim = chief ray direction d0[:2] */
-    RT_PUPIL_FNO = 2    /* angular, object-space f/#: pupil_dir = slope*pupil/hypt, :378-384 */
+    RT_PUPIL_FNO = 2,   /* angular, object-space f/#: pupil_dir = slope*pupil/hypt, :378-384 */
+    RT_PUPIL_WIDE = 3   /* spatial, wide-angle fields (fov.is_wide_angle), opticalspec.py:342-358: the pupil
+                           plane is normal to the chief ray.  rt_field_desc: pt0 = start point, rot = the
+                           matrix rot_v1_into_v2(d0, z) that takes the pupil plane into surface-1
+                           coordinates, obj2enp = -(obj_dist + z_enp) with z_enp the field's real entrance
+                           pupil position (fld.aim_info, raytr/wideangle.py).  Traced with
+                           intersect_obj = 0 and without the virtual-object flip (trace.py:299-303). */
 };
 
 /* Aperture subclasses, src/rayoptics/elem/surface.py:340-494 */
@@ -235,6 +241,8 @@ typedef struct rt_field_desc {
     double pt0[3];   /* ray start point on the object interface (opticalspec.py:361) */
     double aim[2];   /* fld.aim_info: aim point on the paraxial entrance pupil (opticalspec.py:357) */
     double vlx, vux, vly, vuy; /* Field vignetting factors */
+    double rot[9];   /* RT_PUPIL_WIDE: rot_v1_into_v2(d0, [0,0,1]), row-major (C-contiguous in numpy) */
+    double obj2enp;  /* RT_PUPIL_WIDE: -(fod.obj_dist + z_enp) */
 } rt_field_desc;
 
 typedef struct rt_grid_spec {

@@ -806,6 +806,16 @@ int rto_grid_start_rays(const rt_grid_spec *g, int64_t ray_begin, int64_t ray_en
             double pt1[3] = {g->eprad*pup[0] + F->aim[0], g->eprad*pup[1] + F->aim[1], g->z_pupil};
             double v[3] = {pt1[0] - F->pt0[0], pt1[1] - F->pt0[1], pt1[2] - F->pt0[2]};
             normalize3(v, d);
+        } else if (g->pupil_kind == RT_PUPIL_WIDE) {
+            /* wide-angle fields, opticalspec.py:342-358: pupil plane normal to the chief ray.
+             * np.matmul of the C-contiguous 3x3 with a 3-vector: fma(a2,v2, fma(a0,v0, a1*v1)) */
+            const double *a = F->rot;
+            double vv[3] = {g->eprad*pup[0], g->eprad*pup[1], g->eprad*0.0}, pt1[3];
+            for (int c = 0; c < 3; c++)
+                pt1[c] = fma(a[3*c + 2], vv[2], fma(a[3*c], vv[0], a[3*c + 1]*vv[1]));
+            pt1[2] -= F->obj2enp;
+            double v[3] = {pt1[0] - F->pt0[0], pt1[1] - F->pt0[1], pt1[2] - F->pt0[2]};
+            normalize3(v, d);
         } else {
             /* angular pupil, opticalspec.py:368-398: dir_tot = pupil_dir + cr_dir (aim = d0[:2]) */
             double pd[2];

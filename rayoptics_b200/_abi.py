@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-RT_ABI_VERSION = 3
+RT_ABI_VERSION = 4
 RT_MAX_COEFS = 20
 RT_MAX_PHASE_COEFS = 10
 RT_MAX_APERTURES = 4
@@ -22,7 +22,7 @@ PROFILE_IDS = {'Spherical': 0, 'Conic': 1, 'EvenPolynomial': 2,
                'RadialPolynomial': 3, 'YToroid': 4, 'XToroid': 5, 'ThinLens': 6}
 PHASE_IDS = {'HolographicElement': 1, 'DiffractionGrating': 2, 'DiffractiveElement': 3}
 # enum rt_pupil_kind
-PUPIL_EPD, PUPIL_NA, PUPIL_FNO = 0, 1, 2
+PUPIL_EPD, PUPIL_NA, PUPIL_FNO, PUPIL_WIDE = 0, 1, 2, 3
 # enum rt_mode
 MODE_IDS = {'transmit': 0, 'reflect': 1, 'dummy': 2, 'phantom': 3}
 # enum rt_status
@@ -80,7 +80,8 @@ RT_NAN_PAYLOAD_BASE = 0x7FF8000000000000
 class rt_field_desc(C.Structure):
     _fields_ = [('pt0', C.c_double*3), ('aim', C.c_double*2),
                 ('vlx', C.c_double), ('vux', C.c_double),
-                ('vly', C.c_double), ('vuy', C.c_double)]
+                ('vly', C.c_double), ('vuy', C.c_double),
+                ('rot', C.c_double*9), ('obj2enp', C.c_double)]
 
 
 class rt_grid_spec(C.Structure):

@@ -87,7 +87,11 @@ struct rt_table {
     bool lean_poly;          /* lean, with polynomial / toroid profiles (out-of-line Newton) */
     bool wave_ok;            /* interface n_ifc-2 carries no decenter: OPD epilogue applicable */
     size_t lean_bytes;       /* shared memory of the lean plan */
+    bool dynamic;            /* grid kernels draw 32-ray work items from a counter (B200RT_DYNAMIC) */
+    unsigned long long *d_counters;     /* ring of RT_COUNTERS work counters */
+    std::atomic<unsigned> next_counter;
 };
+#define RT_COUNTERS 64
 
 struct rt_grid {
     int32_t device;
@@ -238,10 +242,10 @@ __device__ __forceinline__ void acc_flush(double *acc, double *scratch, int64_t 
  * from registers; lanes without a ray contribute the identity */
 __device__ __forceinline__ void warp_record_from_regs(bool have, int status, double ax, double ay,
                                                       double op, double *scratch, int64_t tile,
-                                                      int64_t slot, int64_t slots_per_tile)
+                                                      int64_t slot, int64_t slots_per_tile, int slice)
 {
     const int lane = threadIdx.x & 31;
-    double *dst = scratch + ((tile*slots_per_tile + slot)*RT_WARPS + (threadIdx.x >> 5))*RT_SUMMARY_DOUBLES;
+    double *dst = scratch + ((tile*slots_per_tile + slot)*RT_WARPS + slice)*RT_SUMMARY_DOUBLES;
     const bool ok = have && status == RT_RAY_OK;
 #pragma unroll
     for (int k = 0; k < RT_ACC; k++) {
@@ -271,7 +275,7 @@ __device__ __forceinline__ void warp_record_from_regs(bool have, int status, dou
 template <bool SUMMARY, bool WAVE, typename TraceFn>
 __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_begin, int64_t chunk_end,
                                                 const rt_out &out, double *scratch, double *acc,
-                                                TraceFn trace)
+                                                unsigned long long *work_counter, TraceFn trace)
 {
     const int64_t tile0 = chunk_begin/G.chunks_per_tile;
     const int64_t ray0 = tile0*G.rays_per_tile + (chunk_begin - tile0*G.chunks_per_tile)*RT_BLOCK;
@@ -279,17 +283,29 @@ __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_
     const bool chunk_slots = G.chunks_per_tile <= (int64_t)gridDim.x;
     int64_t cur_tile = -1;
     if (SUMMARY && !chunk_slots) acc_init(acc);
-    /* Which 32 rays of a chunk a warp takes rotates from chunk to chunk.  A chunk is a run of
-     * consecutive pupil samples along y, so with a fixed assignment the warp that always gets
-     * the pupil-edge end (rays clipped at the first surfaces) would finish all its chunks long
-     * before the warp that always gets the centre, and the SM would run the second half of the
-     * kernel short of warps (ncu r02e: 19.8 of 24 resident warps active on average).  Lanes keep
-     * consecutive rays: every load / store stays coalesced. */
-    unsigned rot = 0;
-    for (int64_t c = chunk_begin + blockIdx.x; c < chunk_end; c += gridDim.x, rot += 32) {
+    const unsigned long long n_items = (unsigned long long)(chunk_end - chunk_begin)*RT_WARPS;
+    int64_t c = chunk_begin + blockIdx.x;
+    for (;;) {
+        int slice;                       /* which 32 rays of the chunk this warp takes */
+        if (work_counter) {
+            /* dynamic scheduling, one work item = 32 consecutive rays: every warp draws its next
+             * item from a global counter, so no warp idles while rays are left (the cost of a
+             * chunk varies several-fold between the pupil centre and its clipped edge) */
+            unsigned long long u = 0;
+            if ((threadIdx.x & 31) == 0) u = atomicAdd(work_counter, 1ull);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= n_items) break;
+            c = chunk_begin + (int64_t)(u/RT_WARPS);
+            slice = (int)(u % RT_WARPS);
+        } else {
+            if (c >= chunk_end) break;
+            /* static round robin; the slice a warp takes is a hash of the chunk id, so that no
+             * warp is stuck with the pupil-edge (cheap) or the centre (expensive) end of every chunk */
+            slice = (int)(((threadIdx.x >> 5) + ((unsigned)c*0x9E3779B1u >> 27)) % RT_WARPS);
+        }
         const int64_t tile = c/G.chunks_per_tile;
         const int64_t lc = c - tile*G.chunks_per_tile;
-        const int64_t loc = lc*RT_BLOCK + (threadIdx.x + rot) % RT_BLOCK;
+        const int64_t loc = lc*RT_BLOCK + slice*32 + (threadIdx.x & 31);
         const bool have = loc < G.rays_per_tile;
         if (SUMMARY && !chunk_slots && tile != cur_tile) {
             if (cur_tile >= 0) acc_flush(acc, scratch, cur_tile, blockIdx.x, sl);
@@ -327,7 +343,8 @@ __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_
                 if (SUMMARY && !chunk_slots) acc_add(acc, status, ax, ay, op);
             }
         }
-        if (SUMMARY && chunk_slots) warp_record_from_regs(have, status, ax, ay, op, scratch, tile, lc, sl);
+        if (SUMMARY && chunk_slots) warp_record_from_regs(have, status, ax, ay, op, scratch, tile, lc, sl, slice);
+        if (!work_counter) c += gridDim.x;
     }
     if (SUMMARY && !chunk_slots && cur_tile >= 0) acc_flush(acc, scratch, cur_tile, blockIdx.x, sl);
 }
@@ -337,14 +354,14 @@ __global__ void __launch_bounds__(RT_BLOCK)
 k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
              int n_ifc, int n_wvl, GridDev G, int64_t chunk_begin, int64_t chunk_end,
              rt_opts o, rt_out out, double *__restrict__ scratch, const double *__restrict__ g_wvl,
-             int pupil_kind)
+             int pupil_kind, unsigned long long *work_counter)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const rt_surface_desc *tab;
     const double *ntab;
     double *acc = reinterpret_cast<double *>(smem);          /* [RT_ACC][RT_BLOCK] when SUMMARY */
     stage_table<STAGE>(g_surfs, g_n, n_ifc, n_wvl, smem + (SUMMARY ? RT_ACC_BYTES : 0), tab, ntab);
-    grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc,
+    grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc, work_counter,
         [&](int f, int w, int64_t loc, int64_t k, RayResult &R, Vec3 &d0) {
             Vec3 p0;
             grid_start_ray<false>(G, pupil_kind, f, loc, p0, d0);
@@ -388,7 +405,7 @@ template <int OUT, bool SUMMARY, bool WAVE, bool POLY>
 __global__ void __launch_bounds__(RT_BLOCK, POLY ? 2 : RT_LEAN_MIN_CTAS)
 k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
                   int n_ifc, int n_wvl, GridDev G, int64_t chunk_begin, int64_t chunk_end,
-                  rt_opts o, rt_out out, double *__restrict__ scratch)
+                  rt_opts o, rt_out out, double *__restrict__ scratch, unsigned long long *work_counter)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     double *acc = reinterpret_cast<double *>(smem);          /* [RT_ACC][RT_BLOCK] when SUMMARY */
@@ -398,7 +415,7 @@ k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__r
     build_plan(g_surfs, g_n, n_ifc, n_wvl, o, ls, li);
     if (POLY) build_poly_plan(g_surfs, n_ifc, lp);
     __syncthreads();
-    grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc,
+    grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc, work_counter,
         [&](int f, int w, int64_t loc, int64_t k, RayResult &R, Vec3 &d0) {
             Vec3 p0;
             grid_start_ray<true>(G, RT_PUPIL_EPD, f, loc, p0, d0);
@@ -648,6 +665,18 @@ static int launch_bundle(const rt_table *t, int64_t n_rays, const double *px, co
     return RT_OK;
 }
 
+/* work counter of one launch (NULL: static schedule): a slot of the table's ring, zeroed on the stream */
+static int launch_counter(const rt_table *t, cudaStream_t stream, unsigned long long **out)
+{
+    *out = nullptr;
+    if (!t->dynamic) return RT_OK;
+    rt_table *tt = const_cast<rt_table *>(t);
+    unsigned long long *c = t->d_counters + (tt->next_counter++ % RT_COUNTERS);
+    CUDA_TRY(cudaMemsetAsync(c, 0, sizeof(unsigned long long), stream));
+    *out = c;
+    return RT_OK;
+}
+
 template <bool FULL, bool SUMMARY, bool STAGE, bool WAVE = false>
 static int launch_grid(const rt_table *t, const rt_grid *g, const GridDev &G, int64_t cb, int64_t ce,
                        const rt_opts *o, const rt_out *out, double *scratch, cudaStream_t stream)
@@ -659,8 +688,11 @@ static int launch_grid(const rt_table *t, const rt_grid *g, const GridDev &G, in
     int grid;
     rc = persistent_grid(kern, smem, t->sm_count, ce - cb, &grid);
     if (rc) return rc;
+    unsigned long long *wc;
+    rc = launch_counter(t, stream, &wc);
+    if (rc) return rc;
     kern<<<grid, RT_BLOCK, smem, stream>>>(t->d_surfs, t->d_n, t->n_ifc, t->n_wvl, G, cb, ce, *o, *out,
-                                           scratch, t->d_wvl, g->pupil_kind);
+                                           scratch, t->d_wvl, g->pupil_kind, wc);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return RT_OK;
@@ -697,8 +729,11 @@ static int launch_grid_lean_(const rt_table *t, const GridDev &G, int64_t cb, in
     int grid;
     rc = persistent_grid(kern, smem, t->sm_count, ce - cb, &grid);
     if (rc) return rc;
+    unsigned long long *wc;
+    rc = launch_counter(t, stream, &wc);
+    if (rc) return rc;
     kern<<<grid, RT_BLOCK, smem, stream>>>(t->d_surfs, t->d_n, t->n_ifc, t->n_wvl, G, cb, ce, *o, *out,
-                                           scratch);
+                                           scratch, wc);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return RT_OK;
@@ -794,6 +829,8 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
         if (t->lean_bytes > RT_MAX_STAGE_BYTES - RT_ACC_BYTES) t->lean = false;
     }
     if (getenv("B200RT_NO_LEAN")) t->lean = false;
+    t->dynamic = getenv("B200RT_DYNAMIC") != nullptr;
+    t->d_counters = nullptr; t->next_counter = 0;
     {
         const rt_surface_desc &k = surfs[n_ifc >= 2 ? n_ifc - 2 : 0];
         t->wave_ok = n_ifc >= 3 && k.has_tfrm == 0 && k.t[0] == 0.0 && k.t[1] == 0.0;
@@ -805,6 +842,7 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
     if (e == cudaSuccess)
         e = cudaMemcpy(t->d_n, n_by_wvl, (size_t)n_ifc*n_wvl*sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&t->d_wvl, (size_t)n_wvl*sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_counters, RT_COUNTERS*sizeof(unsigned long long));
     if (e == cudaSuccess) {
         std::vector<double> nanv((size_t)n_wvl, (double)NAN);
         e = cudaMemcpy(t->d_wvl, nanv.data(), (size_t)n_wvl*sizeof(double), cudaMemcpyHostToDevice);
@@ -812,7 +850,7 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
     /* pageable copies: see rt_grid_create */
     if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     if (e != cudaSuccess) {
-        cudaFree(t->d_surfs); cudaFree(t->d_n); cudaFree(t->d_wvl); delete t;
+        cudaFree(t->d_surfs); cudaFree(t->d_n); cudaFree(t->d_wvl); cudaFree(t->d_counters); delete t;
         return fail(RT_ERR_CUDA, "rt_table_create: %s", cudaGetErrorString(e));
     }
     *out = t;
@@ -826,6 +864,7 @@ int rt_table_destroy(rt_table *t)
     cudaFree(t->d_surfs);
     cudaFree(t->d_n);
     cudaFree(t->d_wvl);
+    cudaFree(t->d_counters);
     delete t;
     return RT_OK;
 }
@@ -898,7 +937,7 @@ static bool grid_spec_ok(const rt_grid_spec *spec)
     return spec && spec->n_fields >= 1 && spec->n_wvls >= 1 && spec->nx >= 1 && spec->ny >= 1 &&
            spec->fields && spec->wvl_idx && spec->pupil_x && spec->pupil_y &&
            !(spec->paired && spec->ny != 1) && spec->pupil_kind >= RT_PUPIL_EPD &&
-           spec->pupil_kind <= RT_PUPIL_FNO;
+           spec->pupil_kind <= RT_PUPIL_WIDE;
 }
 
 /* scalars of the description + the arrays into the pinned staging block (layout fixed at create) */

@@ -61,6 +61,18 @@ __device__ __forceinline__ void grid_start_ray_at(const GridDev &G, int pupil_ki
         Vec3 pt1 = {G.eprad*pupx + F.aim[0], G.eprad*pupy + F.aim[1], G.z_pupil};
         Vec3 dv = {pt1.x - p0.x, pt1.y - p0.y, pt1.z - p0.z};
         d0 = LEAN ? normalize3_shared(dv) : normalize3(dv);
+    } else if (pupil_kind == RT_PUPIL_WIDE) {
+        /* wide-angle fields, opticalspec.py:342-358: pt1 = matmul(rot_d2s, eprad*[px, py, 0]),
+         * pt1[2] -= obj2enp_dist, dir0 = normalize(pt1 - pt0).  rot is C-contiguous in numpy:
+         * its matmul with a 3-vector rounds as fma(a2,v2, fma(a0,v0, a1*v1)) (table.py has_tfrm 2) */
+        const double *a = F.rot;
+        const double vx = G.eprad*pupx, vy = G.eprad*pupy, vz = G.eprad*0.0;
+        Vec3 pt1 = {__fma_rn(a[2], vz, __fma_rn(a[0], vx, a[1]*vy)),
+                    __fma_rn(a[5], vz, __fma_rn(a[3], vx, a[4]*vy)),
+                    __fma_rn(a[8], vz, __fma_rn(a[6], vx, a[7]*vy))};
+        pt1.z -= F.obj2enp;
+        Vec3 dv = {pt1.x - p0.x, pt1.y - p0.y, pt1.z - p0.z};
+        d0 = normalize3(dv);
     } else {
         double d[3];
         angular_start_dir(pupil_kind, G.eprad, pupx, pupy, F.aim[0], F.aim[1], d);

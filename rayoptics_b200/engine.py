@@ -216,6 +216,11 @@ class PupilGridSpec:
                 self.fields[i].aim[c] = float(get('aim')[c])
             for k in ('vlx', 'vux', 'vly', 'vuy'):
                 setattr(self.fields[i], k, float(get(k)))
+            if self.pupil_kind == _abi.PUPIL_WIDE:
+                rot = np.asarray(get('rot'), dtype=float).reshape(9)
+                for c in range(9):
+                    self.fields[i].rot[c] = float(rot[c])
+                self.fields[i].obj2enp = float(get('obj2enp'))
         self.ref_img = None
         if ref_img is not None:
             self.ref_img = np.ascontiguousarray(ref_img, dtype=np.float64).reshape(nf, self.n_wvls, 2)
@@ -224,7 +229,9 @@ class PupilGridSpec:
             self.wave = np.ascontiguousarray(wave, dtype=np.float64).reshape(
                 nf, self.n_wvls, _abi.RT_WAVE_DOUBLES)
         self.eprad, self.z_pupil, self.foc = float(eprad), float(z_pupil), float(foc)
-        self.apply_vignetting, self.flip_z_dir = int(bool(apply_vignetting)), int(flip_z_dir)
+        # wide-angle fields: no virtual-object flip (trace.py:299-303)
+        self.apply_vignetting = int(bool(apply_vignetting))
+        self.flip_z_dir = 0 if self.pupil_kind == _abi.PUPIL_WIDE else int(flip_z_dir)
         self.chunk_rays = chunk_rays()
         self.rays_per_tile = self.nx*self.ny
         self.n_tiles = self.n_fields*self.n_wvls
@@ -349,6 +356,8 @@ def trace_grid(table, grid, chunk_begin=0, chunk_end=None, outputs=GRID_OUTPUTS,
     kwargs.setdefault('check_apertures', True)
     kwargs.setdefault('first_surf', 1)
     kwargs.setdefault('last_surf', table.n_ifc - 2)
+    if grid.pupil_kind == _abi.PUPIL_WIDE:
+        kwargs['intersect_obj'] = False          # trace_base, trace.py:299-300
     opts = _abi.make_opts(**kwargs)
     n = grid.rays_in_chunks(chunk_begin, chunk_end)
     if res is None:
@@ -386,6 +395,8 @@ def trace_grid_to_host(table, grid, h_abr, chunk_begin=0, chunk_end=None, pieces
     kwargs.setdefault('check_apertures', True)
     kwargs.setdefault('first_surf', 1)
     kwargs.setdefault('last_surf', table.n_ifc - 2)
+    if grid.pupil_kind == _abi.PUPIL_WIDE:
+        kwargs['intersect_obj'] = False
     opts = _abi.make_opts(**kwargs)
     n = grid.rays_in_chunks(chunk_begin, chunk_end)
     if not (h_abr.is_pinned() and h_abr.dtype == torch.float64 and h_abr.shape[0] == 2

@@ -824,7 +824,10 @@ class Field:
                  aim_pt=None):
         self.x, self.y, self.wt = x, y, wt
         self.vux, self.vuy, self.vlx, self.vly = vux, vuy, vlx, vly
-        self.aim_info = None if aim_pt is None else np.array(aim_pt, dtype=float)
+        # [x, y] aim point on the paraxial entrance pupil, or -- wide-angle fields -- the scalar
+        # z position of the field's real entrance pupil (raytr/wideangle.py)
+        self.aim_info = (None if aim_pt is None else float(aim_pt) if np.ndim(aim_pt) == 0
+                         else np.array(aim_pt, dtype=float))
         self.chief_ray = None
         self.ref_sphere = None
 
@@ -881,7 +884,8 @@ class Field:
     def to_dict(self):
         return {'x': self.x, 'y': self.y, 'wt': self.wt, 'vux': self.vux, 'vuy': self.vuy,
                 'vlx': self.vlx, 'vly': self.vly,
-                'aim_pt': None if self.aim_info is None else list(map(float, self.aim_info))}
+                'aim_pt': (None if self.aim_info is None else float(self.aim_info)
+                           if np.ndim(self.aim_info) == 0 else list(map(float, self.aim_info)))}
 
 
 class OpticalModel:

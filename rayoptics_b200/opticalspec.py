@@ -20,6 +20,21 @@ from .model import Field
 from .firstorder import compute_first_order
 
 
+def rot_v1_into_v2(v1, v2):
+    """util/misc_math.py:132-148: "equivalent angle" rotation matrix built from the cross
+    product of v1 and v2 -- every term as the reference writes it, including the signs of the
+    off-diagonal sine terms (the wide-angle start rays are defined by THIS matrix)."""
+    rot_axis = -np.cross(v1, v2)
+    s = np.linalg.norm(rot_axis)
+    c = np.dot(v1, v2)
+    v = 1 - c
+    ax = normalize(rot_axis)
+    return np.array(
+        [[ax[0]*ax[0]*v + c, ax[0]*ax[1]*v - ax[2]*s, ax[0]*ax[2]*v + ax[1]*s],
+         [ax[0]*ax[1]*v + ax[2]*s, ax[1]*ax[1]*v + c, ax[1]*ax[2]*v + ax[0]*s],
+         [ax[0]*ax[2]*v + ax[1]*s, ax[1]*ax[2]*v + ax[0]*s, ax[2]*ax[2]*v + c]])
+
+
 def normalize(v):
     """util/misc_math.py:48-54"""
     length = np.linalg.norm(v)
@@ -155,7 +170,11 @@ class OpticalSpecs:
             dir_cos = np.array([math.sin(ang_x)*math.cos(ang_y),
                                 math.sin(ang_y),
                                 math.cos(ang_x)*math.cos(ang_y)])
-            obj_pt = obj2enp_dist*np.array([dir_cos[0]/dir_cos[2], dir_cos[1]/dir_cos[2], 0.0])
+            if fov.is_wide_angle:               # opticalspec.py:1041-1043
+                rot_mat = rot_v1_into_v2(np.array([0., 0., 1.]), dir_cos)
+                obj_pt = np.matmul(rot_mat, -pt1) + pt1
+            else:
+                obj_pt = obj2enp_dist*np.array([dir_cos[0]/dir_cos[2], dir_cos[1]/dir_cos[2], 0.0])
             return obj_pt, dir_cos
         # finite conjugates
         if obj_img_key == 'image':
@@ -177,7 +196,7 @@ class OpticalSpecs:
         return effective_pupil(self.opt_model)
 
     def ray_start_from_osp(self, pupil, fld, pupil_type='rel pupil'):
-        """(pt0, dir0) for one ray, opticalspec.py:289-400 (non wide-angle)."""
+        """(pt0, dir0) for one ray, opticalspec.py:289-400."""
         pupil_oi_key, pupil_value_key, pupil_value = self._epd_pupil()
         n_obj, n_img = self.obj_img_rindex()
         p0, d0 = self.obj_coords(fld)
@@ -188,6 +207,22 @@ class OpticalSpecs:
             if pupil_type == 'aim pt':
                 pt0 = p0
                 pt1 = np.array([pupil[0], pupil[1], fod.obj_dist + z_enp])
+            elif self.field_of_view.is_wide_angle:      # opticalspec.py:342-358
+                eprad = pupil_value/2
+                # the pupil is normal to the chief ray: pupil point rotated into surface-1 coordinates
+                pupil_pt = eprad*np.array([pupil[0], pupil[1], 0.])
+                rot_mat_d2s = rot_v1_into_v2(d0, np.array([0., 0., 1.]))
+                pt1 = np.matmul(rot_mat_d2s, pupil_pt)
+                if aim_info is not None:
+                    z_enp = aim_info                    # real entrance pupil position of this field
+                obj2enp_dist = -(fod.obj_dist + z_enp)
+                if self.conjugate_type('object') == 'infinite':
+                    enp_pt = np.array([0., 0., obj2enp_dist])
+                    rot_mat_s2d = rot_v1_into_v2(np.array([0., 0., 1.]), d0)
+                    pt0 = np.matmul(rot_mat_s2d, enp_pt) - enp_pt
+                else:
+                    pt0 = p0
+                pt1[2] -= obj2enp_dist
             else:
                 eprad = pupil_value/2
                 aim_pt = [0., 0.] if aim_info is None else aim_info
@@ -228,6 +263,7 @@ class OpticalSpecs:
                 'pupil': {'key': list(self.pupil.key), 'value': self.pupil.value},
                 'fov': {'key': list(self.field_of_view.key), 'value': self.field_of_view.value,
                         'is_relative': self.field_of_view.is_relative,
+                        **({'is_wide_angle': True} if self.field_of_view.is_wide_angle else {}),
                         'fields': [f.to_dict() for f in self.field_of_view.fields]},
                 'focus_shift': self.defocus.focus_shift}
 
@@ -237,7 +273,8 @@ class OpticalSpecs:
         fields = [Field(**f) for f in fov['fields']]
         return cls(WvlSpec(d['wvls'], d.get('ref_wvl', 0)),
                    PupilSpec(d['pupil']['key'], d['pupil']['value']),
-                   FieldSpec(fov['key'], fov['value'], fields, fov.get('is_relative', False)),
+                   FieldSpec(fov['key'], fov['value'], fields, fov.get('is_relative', False),
+                             is_wide_angle=fov.get('is_wide_angle', False)),
                    FocusRange(d.get('focus_shift', 0.0)))
 
 
@@ -275,12 +312,28 @@ def grid_fields_of(opt_model, fields=None):
     osp = opt_model['optical_spec']
     fod = opt_model['analysis_results']['parax_data'].fod
     pupil_oi_key, pupil_value_key, pupil_value = effective_pupil(opt_model)
-    if osp['fov'].is_wide_angle:
-        raise NotImplementedError('wide-angle start rays are not generated on the device')
     z_pupil = fod.obj_dist + fod.enp_dist
     flds = fields if fields is not None else osp['fov'].fields
     out = []
-    if pupil_value_key == 'epd':
+    if pupil_value_key == 'epd' and osp['fov'].is_wide_angle:
+        # rt_pupil_kind 3 (opticalspec.py:342-358): per field the start point, the matrix that
+        # rotates the pupil plane normal to the chief ray into surface-1 coordinates, and the
+        # distance object -> real entrance pupil of that field (aim_info = z_enp)
+        kind, scale = 3, pupil_value/2
+        infinite = osp.conjugate_type('object') == 'infinite'
+        for fld in flds:
+            p0, d0 = osp.obj_coords(fld)
+            z_enp = fod.enp_dist if getattr(fld, 'aim_info', None) is None else float(fld.aim_info)
+            obj2enp_dist = -(fod.obj_dist + z_enp)
+            rot_d2s = rot_v1_into_v2(d0, np.array([0., 0., 1.]))
+            if infinite:
+                enp_pt = np.array([0., 0., obj2enp_dist])
+                pt0 = np.matmul(rot_v1_into_v2(np.array([0., 0., 1.]), d0), enp_pt) - enp_pt
+            else:
+                pt0 = p0
+            out.append({'pt0': pt0, 'aim': [0., 0.], 'rot': np.ascontiguousarray(rot_d2s).reshape(9),
+                        'obj2enp': obj2enp_dist})
+    elif pupil_value_key == 'epd':
         kind, scale = 0, pupil_value/2
         obj2enp_dist = -(fod.obj_dist + fod.enp_dist)
         for fld in flds:

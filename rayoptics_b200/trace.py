@@ -63,9 +63,6 @@ def trace_pupil_rays(opt_model, pupils, fld, wvl, output_filter=None, rayerr_fil
     """``[trace_safe(opt_model, p, fld, wvl, output_filter, rayerr_filter, **kwargs) for p in
     pupils]`` (trace.py:159-219) with one launch.  Returns a list of ``RayResult``."""
     from . import raytrace as RT
-    if opt_model.optical_spec.field_of_view.is_wide_angle:
-        raise NotImplementedError('wide-angle start rays (raytr/wideangle.py) are not generated on '
-                                  'the device yet')
     if kwargs.get('pupil_type', 'rel pupil') != 'rel pupil':
         raise NotImplementedError("pupil_type other than 'rel pupil'")
     use_named_tuples = kwargs.get('use_named_tuples', False)

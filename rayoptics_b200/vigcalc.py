@@ -25,6 +25,21 @@ import math
 import numpy as np
 
 
+def _wide(opt_model):
+    return bool(opt_model.optical_spec.field_of_view.is_wide_angle)
+
+
+def _launch(opt_model, dir0):
+    """trace_base, trace.py:299-308: wide-angle rays start off the object surface and are never
+    flipped; otherwise a ray running against z_dir means a virtual object and is reversed.
+    Returns (dir0, trace keyword arguments)."""
+    if _wide(opt_model):
+        return dir0, {'intersect_obj': False}
+    if dir0[2]*opt_model.seq_model.z_dir[0] < 0:
+        dir0 = -dir0
+    return dir0, {}
+
+
 def _stop_xy(opt_model, trace_fn, fld, wvl, aim, stop):
     osp = opt_model.optical_spec
     saved = fld.aim_info
@@ -34,9 +49,8 @@ def _stop_xy(opt_model, trace_fn, fld, wvl, aim, stop):
     finally:
         fld.aim_info = saved
     sm = opt_model.seq_model
-    if dir0[2]*sm.z_dir[0] < 0:
-        dir0 = -dir0
-    ray, _, _ = trace_fn(sm, pt0, dir0, wvl)
+    dir0, kw = _launch(opt_model, dir0)
+    ray, _, _ = trace_fn(sm, pt0, dir0, wvl, **kw)
     p = ray[stop][0]
     return np.array([p[0], p[1]])
 
@@ -112,10 +126,9 @@ def trace_boundary_rays(opt_model, trace_fn, wvl=None):
         for pr in osp.pupil.pupil_rays:
             pupil = fld.apply_vignetting(list(pr))
             pt0, dir0 = osp.ray_start_from_osp(pupil, fld, 'rel pupil')
-            if dir0[2]*sm.z_dir[0] < 0:
-                dir0 = -dir0
+            dir0, kw = _launch(opt_model, dir0)
             try:
-                ray, _, _ = trace_fn(sm, pt0, dir0, wvl)
+                ray, _, _ = trace_fn(sm, pt0, dir0, wvl, **kw)
             except Exception as e:       # TraceError: keep the partial ray
                 pkg = getattr(e, 'ray_pkg', None)
                 ray = pkg[0] if pkg is not None else []
@@ -159,7 +172,7 @@ def cuda_bundle_fn(opt_model, table=None, device=0):
     def fn(p0, d0, wvl):
         w = np.full(p0.shape[1], tab.wvl_index(wvl), dtype=np.int32)
         r = E.trace_bundle(tab, p0, d0, wvl_idx=w, full=True, outputs=('n_seg',), first_surf=1,
-                           last_surf=tab.n_ifc - 2)
+                           last_surf=tab.n_ifc - 2, intersect_obj=not _wide(opt_model))
         return r.full.cpu().numpy(), r.n_seg.cpu().numpy()
     return fn
 
@@ -175,8 +188,7 @@ def _start_rays(opt_model, fields, aims, pupils):
             pt0, dir0 = osp.ray_start_from_osp(np.array(pupil, dtype=float), fld, 'rel pupil')
         finally:
             fld.aim_info = saved
-        if dir0[2]*sm.z_dir[0] < 0:
-            dir0 = -dir0
+        dir0, _ = _launch(opt_model, dir0)
         p0[:, k], d0[:, k] = pt0, dir0
     return p0, d0
 
@@ -405,7 +417,7 @@ def cuda_ray_fn(opt_model, table=None, device=0):
         w = np.full(p0.shape[1], tab.wvl_index(wvl), dtype=np.int32)
         r = E.trace_bundle(tab, p0, d0, wvl_idx=w, full=True, outputs=('n_seg', 'status', 'fail_surf'),
                            first_surf=1, last_surf=tab.n_ifc - 2, check_apertures=check_apertures,
-                           pt_inside_fuzz=pt_inside_fuzz)
+                           pt_inside_fuzz=pt_inside_fuzz, intersect_obj=not _wide(opt_model))
         return {'full': r.full.cpu().numpy(), 'n_seg': r.n_seg.cpu().numpy(),
                 'status': r.status.cpu().numpy(), 'fail_surf': r.fail_surf.cpu().numpy()}
     return fn

@@ -10,7 +10,7 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 MODEL_NAMES = ['singlet', 'dblgauss', 'triplet', 'rc', 'cellphone', 'cellphone_even',
-               'evenasph', 'zoom52', 'thin_triplet', 'exotic', 'threemir']
+               'evenasph', 'zoom52', 'thin_triplet', 'exotic', 'threemir', 'fisheye']
 # models with diffractive phase elements: the reference evaluates x**k with libm pow(), so the
 # device carries tolerance parity there (the oracle, on the same libm, stays bit-exact)
 # finite-conjugate relays specified by an angular object-space pupil ('NA', 'f/#')
@@ -60,7 +60,8 @@ def seeded_bundle(opm, n, rng):
     d0 = np.zeros((3, n))
     scale = np.where(rng.random(n) < 0.8, 1.05, 3.0)
     aim = fod.enp_radius*scale*rng.uniform(-1, 1, (2, n))
-    aims = [f.aim_info for f in osp.field_of_view.fields if f.aim_info is not None]
+    aims = [f.aim_info for f in osp.field_of_view.fields
+            if f.aim_info is not None and np.ndim(f.aim_info) == 1]
     if aims:                                    # off-axis systems: the beam is where the chief rays are aimed
         aim += np.mean(np.array(aims, dtype=float), axis=0)[:, None]
     if abs(sm.gaps[0].thi) > 1e8:

@@ -40,6 +40,8 @@ N_FULL = 48
 
 # keyword sets of trace_raw exercised by the vectors ("cases")
 def cases_for(n_ifc, extra=False):
+    if extra == 'wide':   # wide-angle fields: rays start off the object surface (trace.py:299-300)
+        return [dict(c, intersect_obj=False) for c in cases_for(n_ifc)]
     if extra:      # model 'exotic': additionally phantom filtering and a raw (not re-intersected) object
         return cases_for(n_ifc) + [
             dict(first_surf=1, last_surf=n_ifc - 2, check_apertures=True, filter_out_phantoms=True),
@@ -54,6 +56,12 @@ def cases_for(n_ifc, extra=False):
     ]
 
 
+def _extra(opm):
+    if opm.optical_spec.field_of_view.is_wide_angle:
+        return 'wide'
+    return opm.name == 'exotic'
+
+
 def grid_rays(opm, num, case_id, rays):
     """The reference's square pupil grid (trace.py:563-605) for every field / wvl."""
     osp, sm = opm.optical_spec, opm.seq_model
@@ -64,7 +72,7 @@ def grid_rays(opm, num, case_id, rays):
                 for j in range(num):
                     pupil = fld.apply_vignetting(np.array([xs[i], xs[j]]))
                     pt0, dir0 = osp.ray_start_from_osp(pupil, fld, 'rel pupil')
-                    if dir0[2]*sm.z_dir[0] < 0:
+                    if not osp.field_of_view.is_wide_angle and dir0[2]*sm.z_dir[0] < 0:
                         dir0 = -dir0
                     rays.append((pt0, dir0, wi, case_id))
 
@@ -74,7 +82,7 @@ def wild_rays(opm, n, rng, rays):
     osp, sm = opm.optical_spec, opm.seq_model
     fod = osp.fod
     thi0 = sm.gaps[0].thi
-    n_cases = len(cases_for(sm.get_num_surfaces(), opm.name == 'exotic'))
+    n_cases = len(cases_for(sm.get_num_surfaces(), _extra(opm)))
     for k in range(n):
         wi = int(rng.integers(len(sm.wvlns)))
         aim = fod.enp_radius*rng.uniform(-3.0, 3.0, 2)
@@ -95,7 +103,7 @@ def wild_rays(opm, n, rng, rays):
 def trace_all(opm, rays):
     sm = opm.seq_model
     n_ifc = sm.get_num_surfaces()
-    cases = cases_for(n_ifc, opm.name == 'exotic')
+    cases = cases_for(n_ifc, _extra(opm))
     paths = [rh.ref_path(sm, w) for w in sm.wvlns]
     n = len(rays)
     out = dict(p0=np.zeros((3, n)), d0=np.zeros((3, n)), wvl_idx=np.zeros(n, np.int32),
@@ -158,7 +166,7 @@ def main():
     rng = np.random.default_rng(0)
     plan = {'singlet': (7, 60), 'dblgauss': (5, 150), 'triplet': (5, 80), 'rc': (5, 60),
             'cellphone': (3, 100), 'cellphone_even': (3, 100), 'evenasph': (3, 100),
-            'zoom52': (3, 80), 'threemir': (7, 300), 'thin_triplet': (5, 100), 'exotic': (7, 400), 'hybrid': (5, 300), 'diffractive': (7, 500), 'diffractive_wild': (9, 800)}
+            'zoom52': (3, 80), 'threemir': (7, 300), 'fisheye': (7, 300), 'thin_triplet': (5, 100), 'exotic': (7, 400), 'hybrid': (5, 300), 'diffractive': (7, 500), 'diffractive_wild': (9, 800)}
     only = sys.argv[1:]
     for name, (num, n_wild) in plan.items():
         if only and name not in only:

@@ -22,7 +22,8 @@ from oracle import ref_model, ref_harness as rh       # noqa: E402
 from rayoptics_b200 import model as M                 # noqa: E402
 
 # model -> pupil samples per axis (BASELINE: 7, 512, 1024, 256, 1024)
-CONFIGS = {'singlet': 7, 'dblgauss': 24, 'rc': 24, 'evenasph': 12, 'cellphone': 10, 'zoom52': 8}
+CONFIGS = {'singlet': 7, 'dblgauss': 24, 'rc': 24, 'evenasph': 12, 'cellphone': 10, 'zoom52': 8,
+           'fisheye': 16, 'threemir': 12}
 
 
 def main():

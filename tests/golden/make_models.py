@@ -20,6 +20,10 @@ Sources (numbers only; no reference source code is copied):
   evenasph    /root/reference/src/rayoptics/zemax/tests/US08427765-1.ZMX geometry, with
               catalogue glasses replaced by (n_d, V_d) Cauchy models (approximate)
   zoom52      synthetic 50-surface stack (recipe below), 25 fields x 7 wavelengths
+  fisheye     synthetic wide-angle lens (two negative menisci, stop, positive group; fields to 75
+              degrees, fov.is_wide_angle): the real entrance pupil position of every field
+              (fld.aim_info = z_enp) is found by the REFERENCE's own raytr/wideangle.py
+              find_real_enp on the hybrid model
   threemir    /root/reference/src/rayoptics/codev/tests/threemir.seq (CODE V three-mirror
               compact: conic / aspheric mirrors, every surface decentered and tilted with
               'dec and return'), read by rayoptics_b200/seq.py
@@ -353,6 +357,50 @@ def relay(pupil_key, pupil_value, name):
     return finish(M.OpticalModel(sm, osp, name=name), aim=False, apertures=True)
 
 
+def fisheye():
+    import importlib
+    import warnings
+    from oracle import ref_model
+    g1 = M.AbbeGlass(1.62041, 60.32, label='SK16')
+    g2 = M.AbbeGlass(1.7847, 25.7, label='SF11')
+
+    def build(img_thi):
+        rows = [(0.0, 1e10, M.Air()),
+                (1/45.0, 2.5, g1), (1/14.0, 11.0, M.Air()),
+                (1/32.0, 2.0, g1), (1/10.5, 14.0, M.Air()),
+                (0.0, 1.5, M.Air()),                                   # stop
+                (1/38.0, 3.5, g1), (-1/15.0, 0.3, M.Air()),
+                (1/22.0, 4.5, g1), (-1/11.0, 1.2, g2), (-1/36.0, img_thi, M.Air()),
+                (0.0, 0.0, None)]
+        ifcs, gaps = [], []
+        for i, (cv, thi, med) in enumerate(rows):
+            mode = 'dummy' if i in (0, 5, len(rows) - 1) else 'transmit'
+            ifcs.append(M.Surface(profile=M.Spherical(c=cv), interact_mode=mode, max_aperture=30.0))
+            if med is not None:
+                gaps.append(M.Gap(thi, med))
+        wv = [656.3, 587.6, 486.1]
+        sm = M.SequentialModel(ifcs, gaps, stop_surface=5, wvlns=wv, ref_wvl=1)
+        fields = [M.Field(0., 0.), M.Field(0., 35.), M.Field(0., 60.), M.Field(0., 75.)]
+        osp = OpticalSpecs(WvlSpec(wv, 1), PupilSpec(('object', 'epd'), 2.0),
+                           FieldSpec(('object', 'angle'), 75.0, fields, is_wide_angle=True),
+                           FocusRange(0.0))
+        opm = M.OpticalModel(sm, osp, name='fisheye')
+        opm.update_model()
+        return opm
+
+    opm = build(build(20.0).optical_spec.fod.bfl)
+    ref_model.modules()
+    WA = importlib.import_module('rayoptics.raytr.wideangle')
+    H = ref_model.HybridModel(opm)
+    for f in opm.optical_spec.field_of_view.fields:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            z_enp, rr = WA.find_real_enp(H, opm.seq_model.stop_surface, f, 587.6)
+        assert rr.err is None
+        f.aim_info = float(z_enp)
+    return finish(opm, aim=False, apertures=True)
+
+
 def threemir():
     opm = seq.open_seq(f'{REF}/codev/tests/threemir.seq')
     opm.name = 'threemir'
@@ -363,6 +411,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     models = {
         'threemir': threemir,
+        'fisheye': fisheye,
         'singlet': lambda: from_roa('models/singlet_f5.roa', 'singlet'),
         'dblgauss': dblgauss,
         'triplet': lambda: from_roa('models/Sasian Triplet.roa', 'triplet'),
@@ -391,7 +440,7 @@ def main():
         fod = opm.optical_spec.fod
         print(f'{name:15s} n_ifc={opm.seq_model.get_num_surfaces():3d} efl={fod.efl:10.4f} '
               f'enp_dist={fod.enp_dist:10.4f} enp_r={fod.enp_radius:8.4f} '
-              f'aims={[None if f.aim_info is None else list(np.round(f.aim_info, 6)) for f in opm.optical_spec.fov.fields][:3]}')
+              f'aims={[None if f.aim_info is None else np.round(f.aim_info, 6).tolist() for f in opm.optical_spec.fov.fields][:3]}')
 
 
 if __name__ == '__main__':

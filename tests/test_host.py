@@ -28,7 +28,7 @@ def test_struct_layout_matches_header():
     assert rt_oracle.lib().rto_sizeof_surface_desc() == C.sizeof(_abi.rt_surface_desc) == 640
     assert C.sizeof(_abi.rt_opts) == 40
     assert C.sizeof(_abi.rt_out) == 20*8
-    assert C.sizeof(_abi.rt_field_desc) == 72
+    assert C.sizeof(_abi.rt_field_desc) == 152
 
 
 def test_bad_arguments_return_error_codes():

@@ -128,7 +128,7 @@ def test_oracle_live_against_reference(oracle):
                     assert a['op'] == b['op']
 
 
-GRID_CONFIGS = ['singlet', 'dblgauss', 'rc', 'evenasph', 'cellphone', 'zoom52']
+GRID_CONFIGS = ['singlet', 'dblgauss', 'rc', 'evenasph', 'cellphone', 'zoom52', 'fisheye', 'threemir']
 
 
 @pytest.mark.parametrize('name', GRID_CONFIGS)
@@ -142,7 +142,9 @@ def test_baseline_configs_grid_of_the_reference(oracle, name):
     descs, n_by_wvl, wvls = T.describe_model(opm.seq_model)
     spec = E.grid_spec_for_model(opm, int(z['num']))
     assert spec.n_rays == z['status'].size
-    opts = _abi.make_opts(first_surf=1, last_surf=len(descs) - 2, check_apertures=True)
+    wide = opm.optical_spec.field_of_view.is_wide_angle          # trace_base, trace.py:299-300
+    opts = _abi.make_opts(first_surf=1, last_surf=len(descs) - 2, check_apertures=True,
+                          intersect_obj=not wide)
     r = oracle.trace_grid(spec.c_spec(), descs, n_by_wvl, 0, spec.n_rays, opts, n_threads=4)
     assert same(r['status'], z['status'])
     ok = z['status'] == 0

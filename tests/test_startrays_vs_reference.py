@@ -96,7 +96,7 @@ class FldShim:
 
 
 @pytest.mark.parametrize('name', ['dblgauss', 'triplet', 'rc', 'cellphone', 'thin_triplet', 'exotic',
-                                  'relay_na', 'relay_fno', 'telecentric', 'singlet'])
+                                  'relay_na', 'relay_fno', 'telecentric', 'singlet', 'fisheye', 'threemir'])
 def test_start_rays_equal_the_references_code(name):
     methods = reference_methods()
     opm = load_model(name)

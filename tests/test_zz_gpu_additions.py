@@ -225,7 +225,8 @@ def test_cuda_psf_matches_the_references(name):
         np.testing.assert_allclose(got, z[f'psf_{ci}'], rtol=0, atol=1e-12)
 
 
-@pytest.mark.parametrize('name', ['singlet', 'dblgauss', 'rc', 'evenasph', 'cellphone', 'zoom52'])
+@pytest.mark.parametrize('name', ['singlet', 'dblgauss', 'rc', 'evenasph', 'cellphone', 'zoom52',
+                                  'fisheye', 'threemir'])
 def test_cuda_baseline_configs_grid_of_the_reference(name):
     """The BASELINE configurations at reduced pupil sampling: one grid launch of the engine
     against the body of the reference's own trace_grid loop (<model>_grid.npz), bit for bit --
