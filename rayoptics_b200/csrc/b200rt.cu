@@ -41,6 +41,8 @@ using namespace b200rt;
 
 /* ------------------------------------------------------------------ errors */
 static thread_local std::string g_err;
+static thread_local int g_last_grid = 0;      /* CTAs of the grid kernel this thread launched last */
+static thread_local int64_t g_item_off = 0;   /* doubles from scratch to the per-item sums (set by rt_trace_grid) */
 static std::atomic<int64_t> g_launches{0};
 
 static int fail(int code, const char *fmt, const char *a = "", const char *b = "")
@@ -216,6 +218,34 @@ __device__ __forceinline__ void acc_add(double *acc, int status, double ax, doub
     }
 }
 
+/* dynamic scheduling: only the order-independent columns (counts, min / max) go through the
+ * per-thread accumulators; the floating-point sums are reduced per work item (item_sums) */
+__device__ __forceinline__ void acc_add_exact(double *acc, int status, double ax, double ay)
+{
+    double *a = acc + threadIdx.x;
+    const int ck = status == RT_RAY_OK ? 0 : (status <= RT_RAY_BLOCKED ? status : 4);
+    a[ck*RT_BLOCK] += 1.0;
+    if (status == RT_RAY_OK) {
+        a[10*RT_BLOCK] = fmin(a[10*RT_BLOCK], ax); a[11*RT_BLOCK] = fmax(a[11*RT_BLOCK], ax);
+        a[12*RT_BLOCK] = fmin(a[12*RT_BLOCK], ay); a[13*RT_BLOCK] = fmax(a[13*RT_BLOCK], ay);
+    }
+}
+
+/* the six sums of one work item (32 rays), fixed shuffle tree, lane 0 stores them */
+#define RT_ITEM_SUMS 6
+__device__ __forceinline__ void item_sums_store(bool ok, double ax, double ay, double op, double *dst)
+{
+    double v[RT_ITEM_SUMS] = {ok ? ax : 0.0, ok ? ay : 0.0, ok ? ax*ax : 0.0, ok ? ay*ay : 0.0,
+                              ok ? ax*ay : 0.0, ok ? op : 0.0};
+#pragma unroll
+    for (int k = 0; k < RT_ITEM_SUMS; k++) {
+        double x = v[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x = x + __shfl_down_sync(0xffffffffu, x, off);
+        if ((threadIdx.x & 31) == 0) dst[k] = x;
+    }
+}
+
 /* warp-reduce the accumulators into the warp's record of (tile, slot) and reset them */
 __device__ __forceinline__ void acc_flush(double *acc, double *scratch, int64_t tile, int64_t slot,
                                           int64_t slots_per_tile)
@@ -275,7 +305,8 @@ __device__ __forceinline__ void warp_record_from_regs(bool have, int status, dou
 template <bool SUMMARY, bool WAVE, typename TraceFn>
 __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_begin, int64_t chunk_end,
                                                 const rt_out &out, double *scratch, double *acc,
-                                                unsigned long long *work_counter, TraceFn trace)
+                                                unsigned long long *work_counter, double *item_sums,
+                                                TraceFn trace)
 {
     const int64_t tile0 = chunk_begin/G.chunks_per_tile;
     const int64_t ray0 = tile0*G.rays_per_tile + (chunk_begin - tile0*G.chunks_per_tile)*RT_BLOCK;
@@ -287,6 +318,7 @@ __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_
     int64_t c = chunk_begin + blockIdx.x;
     for (;;) {
         int slice;                       /* which 32 rays of the chunk this warp takes */
+        unsigned long long item = 0;
         if (work_counter) {
             /* dynamic scheduling, one work item = 32 consecutive rays: every warp draws its next
              * item from a global counter, so no warp idles while rays are left (the cost of a
@@ -297,6 +329,7 @@ __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_
             if (u >= n_items) break;
             c = chunk_begin + (int64_t)(u/RT_WARPS);
             slice = (int)(u % RT_WARPS);
+            item = u;
         } else {
             if (c >= chunk_end) break;
             /* static round robin; the slice a warp takes is a hash of the chunk id, so that no
@@ -340,9 +373,17 @@ __device__ __forceinline__ void grid_chunk_loop(const GridDev &G, int64_t chunk_
                     }
                     out.abr_x[k] = sx; out.abr_y[k] = sy;
                 }
-                if (SUMMARY && !chunk_slots) acc_add(acc, status, ax, ay, op);
+                if (SUMMARY && !chunk_slots) {
+                    if (work_counter) acc_add_exact(acc, status, ax, ay);
+                    else acc_add(acc, status, ax, ay, op);
+                }
             }
         }
+        /* dynamic schedule: which warp adds which rays varies from run to run, so the sums of every
+         * work item are stored on their own and k_reduce_summary adds them in item order --
+         * the summary stays bit-reproducible */
+        if (SUMMARY && !chunk_slots && work_counter)
+            item_sums_store(have && status == RT_RAY_OK, ax, ay, op, item_sums + item*RT_ITEM_SUMS);
         if (SUMMARY && chunk_slots) warp_record_from_regs(have, status, ax, ay, op, scratch, tile, lc, sl, slice);
         if (!work_counter) c += gridDim.x;
     }
@@ -354,14 +395,14 @@ __global__ void __launch_bounds__(RT_BLOCK)
 k_trace_grid(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
              int n_ifc, int n_wvl, GridDev G, int64_t chunk_begin, int64_t chunk_end,
              rt_opts o, rt_out out, double *__restrict__ scratch, const double *__restrict__ g_wvl,
-             int pupil_kind, unsigned long long *work_counter)
+             int pupil_kind, unsigned long long *work_counter, double *item_sums)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const rt_surface_desc *tab;
     const double *ntab;
     double *acc = reinterpret_cast<double *>(smem);          /* [RT_ACC][RT_BLOCK] when SUMMARY */
     stage_table<STAGE>(g_surfs, g_n, n_ifc, n_wvl, smem + (SUMMARY ? RT_ACC_BYTES : 0), tab, ntab);
-    grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc, work_counter,
+    grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc, work_counter, item_sums,
         [&](int f, int w, int64_t loc, int64_t k, RayResult &R, Vec3 &d0) {
             Vec3 p0;
             grid_start_ray<false>(G, pupil_kind, f, loc, p0, d0);
@@ -405,7 +446,8 @@ template <int OUT, bool SUMMARY, bool WAVE, bool POLY>
 __global__ void __launch_bounds__(RT_BLOCK, POLY ? 2 : RT_LEAN_MIN_CTAS)
 k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__restrict__ g_n,
                   int n_ifc, int n_wvl, GridDev G, int64_t chunk_begin, int64_t chunk_end,
-                  rt_opts o, rt_out out, double *__restrict__ scratch, unsigned long long *work_counter)
+                  rt_opts o, rt_out out, double *__restrict__ scratch, unsigned long long *work_counter,
+                  double *item_sums)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     double *acc = reinterpret_cast<double *>(smem);          /* [RT_ACC][RT_BLOCK] when SUMMARY */
@@ -415,7 +457,7 @@ k_trace_grid_lean(const rt_surface_desc *__restrict__ g_surfs, const double *__r
     build_plan(g_surfs, g_n, n_ifc, n_wvl, o, ls, li);
     if (POLY) build_poly_plan(g_surfs, n_ifc, lp);
     __syncthreads();
-    grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc, work_counter,
+    grid_chunk_loop<SUMMARY, WAVE>(G, chunk_begin, chunk_end, out, scratch, acc, work_counter, item_sums,
         [&](int f, int w, int64_t loc, int64_t k, RayResult &R, Vec3 &d0) {
             Vec3 p0;
             grid_start_ray<true>(G, RT_PUPIL_EPD, f, loc, p0, d0);
@@ -495,7 +537,9 @@ __device__ __forceinline__ double red_op(int k, double a, double y)
 
 __global__ void __launch_bounds__(RT_RED_THREADS)
 k_reduce_summary(const double *__restrict__ scratch, int64_t recs_per_tile, double *partials,
-                 unsigned int *tickets, double *__restrict__ summary)
+                 unsigned int *tickets, double *__restrict__ summary,
+                 const double *__restrict__ item_sums, int64_t chunk_begin, int64_t chunk_end,
+                 int64_t chunks_per_tile)
 {
     __shared__ double sh[RT_RED_THREADS][RT_SUMMARY_DOUBLES + 1];
     __shared__ bool last;
@@ -513,6 +557,25 @@ k_reduce_summary(const double *__restrict__ scratch, int64_t recs_per_tile, doub
         if (p[RT_ACC] != 0.0) {
 #pragma unroll
             for (int k = 0; k < RT_ACC; k++) x[k] = red_op(k, x[k], p[k]);
+        }
+    }
+    if (item_sums) {
+        /* the work items of this tile inside the launch's chunk range, in item order: thread t of
+         * part p takes items t, t + 256, ... of the part's contiguous range */
+        int64_t c0 = tile*chunks_per_tile, c1 = c0 + chunks_per_tile;
+        if (c0 < chunk_begin) c0 = chunk_begin;
+        if (c1 > chunk_end) c1 = chunk_end;
+        if (c1 > c0) {
+            const int64_t i0 = (c0 - chunk_begin)*RT_WARPS, n_it = (c1 - c0)*RT_WARPS;
+            const int64_t per_it = (n_it + RT_RED_SPLIT - 1)/RT_RED_SPLIT;
+            int64_t a0 = part*per_it, a1 = a0 + per_it;
+            if (a1 > n_it) a1 = n_it;
+            const int col[RT_ITEM_SUMS] = {5, 6, 7, 8, 9, 14};
+            for (int64_t it = a0 + threadIdx.x; it < a1; it += RT_RED_THREADS) {
+                const double *p = item_sums + (i0 + it)*RT_ITEM_SUMS;
+#pragma unroll
+                for (int k = 0; k < RT_ITEM_SUMS; k++) x[col[k]] += p[k];
+            }
         }
     }
 #pragma unroll
@@ -616,6 +679,20 @@ __global__ void k_dfma_latency(double *out, long long *cycles, int iters, double
 }
 
 /* ------------------------------------------------------------ launch helpers */
+/* records (16 doubles each): n_tiles x min(chunks_per_tile, RT_MAX_GRID) x RT_WARPS, then
+ * the reduce kernel's partials (n_tiles x RT_RED_SPLIT records) and tickets */
+static int64_t scratch_records(const rt_grid *g)
+{
+    const int64_t sl = g->chunks_per_tile < RT_MAX_GRID ? g->chunks_per_tile : RT_MAX_GRID;
+    return g->n_tiles*sl*RT_WARPS;
+}
+
+/* doubles before the per-item sums: records, the reduce kernel's partials, tickets */
+static int64_t scratch_head_doubles(const rt_grid *g)
+{
+    return (scratch_records(g) + g->n_tiles*RT_RED_SPLIT)*RT_SUMMARY_DOUBLES + g->n_tiles;
+}
+
 template <typename K>
 static int persistent_grid(K kernel, size_t smem, int sm_count, int64_t work_items, int *grid)
 {
@@ -691,8 +768,10 @@ static int launch_grid(const rt_table *t, const rt_grid *g, const GridDev &G, in
     unsigned long long *wc;
     rc = launch_counter(t, stream, &wc);
     if (rc) return rc;
+    g_last_grid = grid;
     kern<<<grid, RT_BLOCK, smem, stream>>>(t->d_surfs, t->d_n, t->n_ifc, t->n_wvl, G, cb, ce, *o, *out,
-                                           scratch, t->d_wvl, g->pupil_kind, wc);
+                                           scratch, t->d_wvl, g->pupil_kind, wc,
+                                           (wc && SUMMARY) ? scratch + g_item_off : nullptr);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return RT_OK;
@@ -732,8 +811,9 @@ static int launch_grid_lean_(const rt_table *t, const GridDev &G, int64_t cb, in
     unsigned long long *wc;
     rc = launch_counter(t, stream, &wc);
     if (rc) return rc;
+    g_last_grid = grid;
     kern<<<grid, RT_BLOCK, smem, stream>>>(t->d_surfs, t->d_n, t->n_ifc, t->n_wvl, G, cb, ce, *o, *out,
-                                           scratch, wc);
+                                           scratch, wc, (wc && SUMMARY) ? scratch + g_item_off : nullptr);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return RT_OK;
@@ -1036,19 +1116,10 @@ int rt_grid_dims(const rt_grid *g, int64_t *n_rays, int64_t *n_chunks, int32_t *
     return RT_OK;
 }
 
-/* records (16 doubles each): n_tiles x min(chunks_per_tile, RT_MAX_GRID) x RT_WARPS, then
- * the reduce kernel's partials (n_tiles x RT_RED_SPLIT records) and tickets */
-static int64_t scratch_records(const rt_grid *g)
-{
-    const int64_t sl = g->chunks_per_tile < RT_MAX_GRID ? g->chunks_per_tile : RT_MAX_GRID;
-    return g->n_tiles*sl*RT_WARPS;
-}
-
 int64_t rt_grid_scratch_bytes(const rt_grid *g, int64_t chunk_begin, int64_t chunk_end)
 {
     if (!g || chunk_end < chunk_begin) return 0;
-    return (scratch_records(g) + g->n_tiles*RT_RED_SPLIT)*RT_SUMMARY_DOUBLES*(int64_t)sizeof(double) +
-           g->n_tiles*(int64_t)sizeof(double);
+    return (scratch_head_doubles(g) + (chunk_end - chunk_begin)*RT_WARPS*RT_ITEM_SUMS)*(int64_t)sizeof(double);
 }
 
 int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int64_t chunk_end,
@@ -1076,8 +1147,10 @@ int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int6
     if (chunk_begin == chunk_end) return RT_OK;
     const GridDev G = grid_dev(g);
     double *scr = (double *)scratch;
+    g_item_off = scratch_head_doubles(g);
     if (summary)
-        CUDA_TRY(cudaMemsetAsync(scr, 0, (size_t)rt_grid_scratch_bytes(g, chunk_begin, chunk_end), s));
+        CUDA_TRY(cudaMemsetAsync(scr, 0, (size_t)(t->dynamic ? rt_grid_scratch_bytes(g, chunk_begin, chunk_end)
+                                                              : scratch_head_doubles(g)*(int64_t)sizeof(double)), s));
     const bool full = out->full != nullptr, summ = summary != nullptr, st = t->stage;
     const bool wave = out->opd != nullptr;
     /* angular pupil specifications are generated by the general kernels only (rt_grid.cuh) */
@@ -1124,8 +1197,11 @@ int rt_trace_grid(const rt_table *t, const rt_grid *g, int64_t chunk_begin, int6
         const int64_t recs = scratch_records(g);
         double *partials = scr + recs*RT_SUMMARY_DOUBLES;
         unsigned int *tickets = (unsigned int *)(partials + g->n_tiles*RT_RED_SPLIT*RT_SUMMARY_DOUBLES);
+        const bool chunk_slots = g->chunks_per_tile <= g_last_grid;
         k_reduce_summary<<<(unsigned)(g->n_tiles*RT_RED_SPLIT), RT_RED_THREADS, 0, s>>>(
-            scr, recs/g->n_tiles, partials, tickets, summary);
+            scr, recs/g->n_tiles, partials, tickets, summary,
+            (t->dynamic && !chunk_slots) ? scr + scratch_head_doubles(g) : nullptr, chunk_begin, chunk_end,
+            g->chunks_per_tile);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
     }
