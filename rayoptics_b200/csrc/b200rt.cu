@@ -89,7 +89,7 @@ struct rt_table {
     bool lean_poly;          /* lean, with polynomial / toroid profiles (out-of-line Newton) */
     bool wave_ok;            /* interface n_ifc-2 carries no decenter: OPD epilogue applicable */
     size_t lean_bytes;       /* shared memory of the lean plan */
-    bool dynamic;            /* grid kernels draw 32-ray work items from a counter (B200RT_DYNAMIC) */
+    bool dynamic;            /* grid kernels draw 32-ray work items from a counter (default) */
     unsigned long long *d_counters;     /* ring of RT_COUNTERS work counters */
     std::atomic<unsigned> next_counter;
 };
@@ -231,19 +231,32 @@ __device__ __forceinline__ void acc_add_exact(double *acc, int status, double ax
     }
 }
 
-/* the six sums of one work item (32 rays), fixed shuffle tree, lane 0 stores them */
+/* the six sums of one work item (32 rays) in 9 shuffles instead of 30: at the 16 / 8 / 4
+ * exchanges every lane hands over the half of its values that its partner keeps, so after
+ * three steps each lane owns ONE of (up to 8) values summed over 8 lanes; two more exchanges
+ * finish that value.  The addition tree is fixed: same rays, same bits. */
 #define RT_ITEM_SUMS 6
 __device__ __forceinline__ void item_sums_store(bool ok, double ax, double ay, double op, double *dst)
 {
-    double v[RT_ITEM_SUMS] = {ok ? ax : 0.0, ok ? ay : 0.0, ok ? ax*ax : 0.0, ok ? ay*ay : 0.0,
-                              ok ? ax*ay : 0.0, ok ? op : 0.0};
-#pragma unroll
-    for (int k = 0; k < RT_ITEM_SUMS; k++) {
-        double x = v[k];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) x = x + __shfl_down_sync(0xffffffffu, x, off);
-        if ((threadIdx.x & 31) == 0) dst[k] = x;
-    }
+    const int lane = threadIdx.x & 31;
+    double v0 = ok ? ax : 0.0, v1 = ok ? ay : 0.0, v2 = ok ? ax*ax : 0.0, v3 = ok ? ay*ay : 0.0;
+    double v4 = ok ? ax*ay : 0.0, v5 = ok ? op : 0.0, v6 = 0.0, v7 = 0.0;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    /* 16: lower half-warp keeps v0..v3, upper keeps v4..v7 */
+    double a0 = (h16 ? v4 : v0) + __shfl_xor_sync(0xffffffffu, h16 ? v0 : v4, 16);
+    double a1 = (h16 ? v5 : v1) + __shfl_xor_sync(0xffffffffu, h16 ? v1 : v5, 16);
+    double a2 = (h16 ? v6 : v2) + __shfl_xor_sync(0xffffffffu, h16 ? v2 : v6, 16);
+    double a3 = (h16 ? v7 : v3) + __shfl_xor_sync(0xffffffffu, h16 ? v3 : v7, 16);
+    /* 8: keep a0, a1 | a2, a3 */
+    double b0 = (h8 ? a2 : a0) + __shfl_xor_sync(0xffffffffu, h8 ? a0 : a2, 8);
+    double b1 = (h8 ? a3 : a1) + __shfl_xor_sync(0xffffffffu, h8 ? a1 : a3, 8);
+    /* 4: keep b0 | b1 */
+    double c = (h4 ? b1 : b0) + __shfl_xor_sync(0xffffffffu, h4 ? b0 : b1, 4);
+    c = c + __shfl_xor_sync(0xffffffffu, c, 2);
+    c = c + __shfl_xor_sync(0xffffffffu, c, 1);
+    /* lane 4g holds value index 4*[bit 4] + 2*[bit 3] + [bit 2] of g = lane/4 */
+    const int idx = ((lane >> 4) & 1)*4 + ((lane >> 3) & 1)*2 + ((lane >> 2) & 1);
+    if ((lane & 3) == 0 && idx < RT_ITEM_SUMS) dst[idx] = c;
 }
 
 /* warp-reduce the accumulators into the warp's record of (tile, slot) and reset them */
@@ -909,7 +922,9 @@ int rt_table_create(const rt_surface_desc *surfs, int32_t n_ifc, const double *n
         if (t->lean_bytes > RT_MAX_STAGE_BYTES - RT_ACC_BYTES) t->lean = false;
     }
     if (getenv("B200RT_NO_LEAN")) t->lean = false;
-    t->dynamic = getenv("B200RT_DYNAMIC") != nullptr;
+    /* grid kernels: warps draw 32-ray work items from a counter (B200RT_STATIC=1: fixed round robin
+     * of chunks over CTAs, the round-1 schedule, kept for comparison -- profiles/r02*) */
+    t->dynamic = getenv("B200RT_STATIC") == nullptr;
     t->d_counters = nullptr; t->next_counter = 0;
     {
         const rt_surface_desc &k = surfs[n_ifc >= 2 ? n_ifc - 2 : 0];
