@@ -26,31 +26,18 @@ def shard_chunks(n_chunks, rank, world_size):
 
 
 class PendingSummary:
-    """Handle of an in-flight all-gather + combine (``gather_summaries(..., async_op=True)``).
-    Both run on a side stream (NCCL's own stream hangs off it), so the compute stream keeps
-    tracing; ``result()`` makes the current stream wait for the side stream's event and
-    returns the combined ``[n_tiles, 16]`` tensor."""
+    """Handle of an in-flight all-gather (``gather_summaries(..., async_op=True)``): the
+    collective runs on NCCL's own stream while the next grid is traced; ``result()`` makes the
+    current stream wait for it and combines the ranks' rows with ONE ``rt_combine_summaries``
+    launch (CPU / gloo: torch)."""
 
-    def __init__(self, event, combined, keep=None, work=None):
-        self.event, self.combined, self.work = event, combined, work
-        self._keep = keep      # tensors that must outlive the collective
+    def __init__(self, work, out, shape, world, keep=None):
+        self.work, self.out, self.shape, self.world = work, out, shape, world
+        self._keep = keep      # the input tensor stays referenced until the collective is done
 
     def result(self):
-        if self.work is not None:          # CPU / gloo
-            self.work.wait()
-            out, shape, world = self._keep
-            return combine_summaries(out.view((world,) + shape))
-        torch.cuda.current_stream(self.combined.device).wait_event(self.event)
-        return self.combined
-
-
-_SIDE = {}
-
-
-def _side_stream(device):
-    if device not in _SIDE:
-        _SIDE[device] = torch.cuda.Stream(device)
-    return _SIDE[device]
+        self.work.wait()
+        return combine_summaries(self.out.view((self.world,) + self.shape))
 
 
 def gather_summaries(partial, group=None, async_op=False):
@@ -72,21 +59,9 @@ def gather_summaries(partial, group=None, async_op=False):
     shape = tuple(partial.shape)
     # concatenated layout [world*n_tiles, 16]: accepted by both NCCL and gloo
     out = torch.empty((world*shape[0],) + shape[1:], dtype=partial.dtype, device=partial.device)
-    if async_op and partial.is_cuda:
-        main = torch.cuda.current_stream(partial.device)
-        side = _side_stream(partial.device)
-        side.wait_stream(main)
-        partial.record_stream(side)
-        out.record_stream(side)
-        with torch.cuda.stream(side):
-            dist.all_gather_into_tensor(out, partial, group=group)
-            combined = combine_summaries(out.view((world,) + shape))
-            event = side.record_event()
-        combined.record_stream(main)
-        return PendingSummary(event, combined, keep=(partial, out))
     if async_op:
         work = dist.all_gather_into_tensor(out, partial, group=group, async_op=True)
-        return PendingSummary(None, None, keep=(out, shape, world), work=work)
+        return PendingSummary(work, out, shape, world, keep=partial)
     dist.all_gather_into_tensor(out, partial, group=group)
     return combine_summaries(out.view((world,) + shape))
 
