@@ -498,6 +498,7 @@ def run_b200(args):
         kw = dict(table=tab, pinned=pinned)
         if shard:
             kw['shard'] = (rank, world)
+            kw['chunk_range'] = (c0, c1)
         for _ in range(3):
             sd = A.spot_diagram(opm, args.num, **kw)
         barrier()
