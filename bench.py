@@ -418,6 +418,17 @@ def run_b200(args):
     grid = E.grid_for_model(opm, tab, args.num)
     shard = args.mode == 'shard'
     c0, c1 = P.shard_chunks(grid.n_chunks, rank, world) if shard else (0, grid.n_chunks)
+    balance = None
+    if shard and world > 1:
+        # equal-length ranges leave the ranks with the cheap (clipped) fields idle: one
+        # summary-only pass of the equal split gives per-tile costs, the timed steps use ranges
+        # of equal WORK (parallel.shard_chunks_weighted).  Outside every timed region.
+        r0 = E.trace_grid(tab, grid, c0, c1, outputs=())
+        w = P.weights_from_summary(P.gather_summaries(r0.summary))
+        equal = (c0, c1)
+        c0, c1 = P.shard_chunks_weighted(grid.chunks_per_tile, w, rank, world)
+        balance = {'equal_length_range': list(equal), 'equal_work_range': [c0, c1],
+                   'tile_weight_min_max': [float(w.min()), float(w.max())]}
     n_mine = grid.rays_in_chunks(c0, c1)             # rays this rank traces per step
     first = grid.first_ray_of_chunk(c0)
     n_job = grid.n_rays if shard else world*grid.n_rays
@@ -487,6 +498,7 @@ def run_b200(args):
         kw = dict(table=tab, pinned=pinned)
         if shard:
             kw['shard'] = (rank, world)
+            kw['chunk_range'] = (c0, c1)
         for _ in range(3):
             sd = A.spot_diagram(opm, args.num, **kw)
         barrier()
@@ -582,7 +594,7 @@ def run_b200(args):
                 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic', 'config': config_dict(args, opm, grid, world),
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
-                'rank_imbalance': imbalance if world > 1 else None,
+                'rank_imbalance': (dict(imbalance, shard_balance=balance) if world > 1 else None),
                 'full_ray_regime': None if full_ray is None else dict(
                     full_ray, frac_of_hbm_peak=full_ray['achieved_gbs']/hbm_peak),
                 'rays_ok_frac': float(fl[1]/fl[2])}

@@ -176,7 +176,7 @@ def chief_ray_image_points(opt_model, table, fields, wvl=None, foc=0.0, io=None)
 
 
 def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table=None,
-                 device=0, pinned=None, shard=None, group=None, pieces=8, **kwargs):
+                 device=0, pinned=None, shard=None, group=None, pieces=8, chunk_range=None, **kwargs):
     """Spot diagrams of all fields and wavelengths in one pass over the device.
 
     Host buffers in, host buffers out: the grid description goes to the device (one
@@ -185,7 +185,8 @@ def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table
     and traces the rays, and the transverse aberrations come back into pinned host memory,
     16 B per ray (status / failing surface of the rays that do not arrive ride in the NaN
     payloads).  ``shard=(rank, world)`` traces only that rank's slice of the chunk space and
-    all-gathers the per-(field, wvl) sums over ``group`` (parallel.py).  ``pinned``:
+    all-gathers the per-(field, wvl) sums over ``group`` (parallel.py); ``chunk_range=(c0, c1)``
+    overrides the equal-length slice (e.g. ``parallel.shard_chunks_weighted``).  ``pinned``:
     optional dict with a pinned host tensor ``abr`` ``[2, >=n]`` to re-use across calls.
     ``pieces``: the chunk range is traced in that many launches on two streams so that the
     device->host copy of one piece overlaps the trace of the next."""
@@ -206,6 +207,8 @@ def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table
         ref_dev = ws['ref']
         grid.chief_ref(table, table.wvl_index(sm.central_wavelength()), out=ref_dev)
         c0, c1 = (0, grid.n_chunks) if shard is None else shard_chunks(grid.n_chunks, *shard)
+        if chunk_range is not None:          # this rank's range, e.g. parallel.shard_chunks_weighted
+            c0, c1 = chunk_range
         n = grid.rays_in_chunks(c0, c1)
         if pinned is None:
             pinned = {'abr': torch.empty((2, max(n, 1)), dtype=torch.float64).pin_memory()}

@@ -25,6 +25,32 @@ def shard_chunks(n_chunks, rank, world_size):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def shard_chunks_weighted(chunks_per_tile, tile_weights, rank, world_size):
+    """Contiguous split of the chunk space into ``world_size`` ranges of (nearly) equal WORK
+    instead of equal length.  ``tile_weights[t]``: relative cost of one chunk of tile ``t``
+    (e.g. from the spot sums of an earlier pass: rays that reach the image cost a full trace,
+    clipped rays a fraction -- outer fields of an unvignetted specification are cheaper than the
+    axial one, and an equal-length split leaves the ranks that hold them idle).  Every rank
+    computes the same cut points from the same weights.  Returns ``(begin, end)``."""
+    import numpy as np
+    w = np.repeat(np.maximum(np.asarray(tile_weights, dtype=np.float64), 1e-12), int(chunks_per_tile))
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [int(np.searchsorted(cum, cum[-1]*r/world_size, side='left')) for r in range(world_size + 1)]
+    cuts[0], cuts[-1] = 0, len(w)
+    for r in range(1, world_size + 1):          # monotone, never empty where avoidable
+        cuts[r] = max(cuts[r], cuts[r - 1])
+    return cuts[rank], cuts[rank + 1]
+
+
+def weights_from_summary(summary, clipped_cost=0.3):
+    """Per-tile chunk weights from a combined ``[n_tiles, 16]`` summary: rays that arrive count 1,
+    rays that fail ``clipped_cost`` (they stop part way)."""
+    s = summary.detach().cpu().numpy() if torch.is_tensor(summary) else summary
+    ok = s[:, 0]
+    fail = s[:, 1:5].sum(axis=1)
+    return ok + clipped_cost*fail
+
+
 class PendingSummary:
     """Handle of an in-flight all-gather (``gather_summaries(..., async_op=True)``): the
     collective runs on NCCL's own stream while the next grid is traced; ``result()`` makes the

@@ -435,3 +435,20 @@ def test_zmx_reader_coordinate_breaks():
                                np.zeros(1, np.int32), _abi.make_opts(first_surf=1, last_surf=len(descs) - 2))
     assert r['status'][0] == 0
     assert np.abs(r['last'][0:2, 0]).max() < 1e-9 and abs(r['last'][5, 0] - 1.0) < 1e-12
+
+
+def test_weighted_sharding():
+    """parallel.shard_chunks_weighted: ranges tile the chunk space, equal weights reproduce the
+    plain split to within a chunk, and unequal weights equalise the work."""
+    cpt, n_tiles = 64, 9
+    w = np.ones(n_tiles)
+    cuts = [P.shard_chunks_weighted(cpt, w, r, 4) for r in range(4)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == cpt*n_tiles
+    assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
+    assert all(abs((e - b) - cpt*n_tiles/4) <= 1 for b, e in cuts)
+    w = np.array([1.0, 1.0, 1.0, 0.5, 0.5, 0.5, 0.25, 0.25, 0.25])
+    cuts = [P.shard_chunks_weighted(cpt, w, r, 3) for r in range(3)]
+    work = [np.repeat(w, cpt)[b:e].sum() for b, e in cuts]
+    assert max(work)/min(work) < 1.02 and cuts[0][1] - cuts[0][0] < cuts[2][1] - cuts[2][0]
+    summ = np.zeros((2, 16)); summ[0, 0] = 100; summ[1, 0] = 50; summ[1, 3] = 50
+    assert P.weights_from_summary(summ).tolist() == [100.0, 65.0]
