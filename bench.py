@@ -397,6 +397,21 @@ def kernel_name(tab_descs, lean_ok=True):
     return 'k_trace_grid_lean<0,1,0,%d>' % int(poly)
 
 
+def _watchdog(seconds, what):
+    """A multi-rank run that stops making progress (a peer died, a collective never completes)
+    must end by itself: exit non-zero with a message instead of sitting until the driver's limit."""
+    import threading
+
+    def bark():
+        sys.stderr.write(f'bench.py: {what} made no progress for {seconds} s -- giving up\n')
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, bark)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -407,8 +422,10 @@ def run_b200(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     assert torch.cuda.is_available(), 'bench.py --impl b200 needs a CUDA device'
     torch.cuda.set_device(local)
+    dog = None
     if world > 1:
         import datetime
+        dog = _watchdog(600, f'rank {rank} of {world}')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local),
                                 timeout=datetime.timedelta(seconds=180))   # fail fast, never hang
     dev = torch.device('cuda', local)
@@ -472,7 +489,10 @@ def run_b200(args):
     # host (these boxes share their cores between tenants) cannot stretch the device timeline
     launches_per_step = None
     graph = None
-    if not args.no_graph:
+    # single GPU only: measured this round (6.2e9 rays/s, profiles/r02k).  With NCCL in the step the
+    # capture worked at N=2 and hung at N=4 on the one box it was tried on (NOTES_r02.md), so N > 1
+    # keeps the eager loop, whose collective pattern is the one the round-1 scaling run used.
+    if not args.no_graph and world == 1:
         try:
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -650,6 +670,8 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if dog is not None:
+        dog.cancel()
 
 
 def main():
