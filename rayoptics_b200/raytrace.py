@@ -204,8 +204,9 @@ def install(batched=False):
     ``rayoptics.raytr.analyses.trace_ray_fan / trace_ray_list / trace_ray_grid`` -- so that the
     reference's own ``RayFan`` / ``RayList`` / ``RayGrid`` / ``SequentialModel.trace_fan`` ...
     trace each (field, wavelength) in one launch.  Same arguments and results (checked
-    against the unpatched reference in tests/test_dropin_batched.py); wide-angle fields and
-    ``pupil_type`` other than 'rel pupil' keep the reference's loop on the drop-in ``trace``."""
+    against the unpatched reference in tests/test_dropin_batched.py, wide-angle fields
+    included); ``pupil_type`` other than 'rel pupil' keeps the reference's loop on the drop-in
+    ``trace``."""
     import rayoptics.raytr.raytrace as rt      # type: ignore
     if 'trace' not in _saved:
         _saved['trace'], _saved['trace_raw'] = rt.trace, rt.trace_raw
@@ -232,8 +233,7 @@ def _batched_or_original(batched_fn, original_fn):
 
     @functools.wraps(original_fn)
     def wrapper(opt_model, *args, **kwargs):
-        wide = opt_model['optical_spec']['fov'].is_wide_angle
-        if wide or kwargs.get('pupil_type', 'rel pupil') != 'rel pupil':
+        if kwargs.get('pupil_type', 'rel pupil') != 'rel pupil':
             return original_fn(opt_model, *args, **kwargs)
         return batched_fn(opt_model, *args, **kwargs)
     return wrapper

@@ -32,7 +32,8 @@ from rayoptics_b200 import model as M               # noqa: E402
 
 OUT = os.path.join(HERE, 'vectors')
 CASES = {'dblgauss': [(0, 587.6), (1, 656.3), (2, 486.1)], 'rc': [(0, 550.0), (3, 550.0)],
-         'triplet': [(1, None)], 'telecentric': [(0, 587.6), (2, 486.1)], 'cellphone': [(4, None)]}
+         'triplet': [(1, None)], 'telecentric': [(0, 587.6), (2, 486.1)], 'cellphone': [(4, None)],
+         'fisheye': [(0, 587.6), (2, 656.3), (3, 587.6)], 'threemir': [(1, None), (4, None)]}
 NUM_FAN, NUM_LIST, NUM_GRID = 21, 15, 16
 PSF_DIM = 64
 
@@ -49,7 +50,7 @@ def main():
             aim = None if fld.aim_info is None else np.array(fld.aim_info)
 
             def keep_aim():
-                fld.aim_info = None if aim is None else aim.copy()
+                fld.aim_info = None if aim is None else (float(aim) if aim.ndim == 0 else aim.copy())
                 fld.chief_ray = ((None, None, -1.0), None)     # != wvl: re-trace, do not re-aim
 
             for xy in 'xy':

@@ -23,10 +23,12 @@ class OracleBackend:
         from oracle import rt_oracle
         self.o = rt_oracle
         self.descs, self.n_by_wvl, self.wvls = T.describe_model(opm.seq_model)
+        self.wide = bool(opm.optical_spec.field_of_view.is_wide_angle)
 
     def _opts(self, check_apertures):
+        # what engine.trace_grid does for RT_PUPIL_WIDE grids (trace_base, trace.py:299-300)
         return _abi.make_opts(first_surf=1, last_surf=len(self.descs) - 2,
-                              check_apertures=check_apertures)
+                              check_apertures=check_apertures, intersect_obj=not self.wide)
 
     def chief_rays(self, opt_model, fields, wvls):
         from rayoptics_b200 import engine as E
@@ -45,7 +47,7 @@ class OracleBackend:
         return {'abr': r['abr'], 'status': r['status'], 'opd': r['opd'] if want_opd else None}
 
 
-@pytest.mark.parametrize('name', ['dblgauss', 'rc', 'triplet', 'telecentric', 'cellphone'])
+@pytest.mark.parametrize('name', ['dblgauss', 'rc', 'triplet', 'telecentric', 'cellphone', 'fisheye', 'threemir'])
 def test_analysis_classes_equal_the_references(name):
     z = np.load(os.path.join(GOLDEN, 'vectors', name + '_analyses.npz'))
     n_fan, n_list, n_grid = (int(x) for x in z['num'])

@@ -21,7 +21,7 @@ from test_trace_drivers import oracle_tracer
 pytestmark = pytest.mark.skipif(not rh.available(), reason='/root/reference not present')
 
 
-@pytest.mark.parametrize('name', ['dblgauss', 'rc', 'telecentric'])
+@pytest.mark.parametrize('name', ['dblgauss', 'rc', 'telecentric', 'fisheye', 'threemir'])
 def test_reference_classes_on_batched_loops(name, monkeypatch):
     from oracle import ref_model
     RT, RA = ref_model.modules()
@@ -37,7 +37,7 @@ def test_reference_classes_on_batched_loops(name, monkeypatch):
         aim = None if fld.aim_info is None else np.array(fld.aim_info)
 
         def keep_aim():          # as in make_golden_analyses.py: no re-aiming by the reference
-            fld.aim_info = None if aim is None else aim.copy()
+            fld.aim_info = None if aim is None else (float(aim) if aim.ndim == 0 else aim.copy())
             fld.chief_ray = ((None, None, -1.0), None)
 
         for xy in 'xy':

@@ -28,6 +28,8 @@ def oracle_tracer(opt_model, table, fld, wvl, px, py, apply_vignetting, trace_kw
     kw.setdefault('check_apertures', False)
     kw.setdefault('first_surf', 1)
     kw.setdefault('last_surf', len(descs) - 2)
+    if osp.field_of_view.is_wide_angle:       # engine.trace_grid does this for RT_PUPIL_WIDE grids
+        kw['intersect_obj'] = False
     r = rt_oracle.trace_bundle(descs, n_by_wvl, p, d, wv, _abi.make_opts(**kw), want_full=True,
                                wvls=wvls)
     return r
