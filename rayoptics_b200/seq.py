@@ -13,8 +13,9 @@ rotationally symmetric sequential system:
 Glasses: ``REFL`` / ``AIR`` / empty, a fictitious glass code ``nnn.vvv`` (n_d = 1.nnn,
 V_d = vv.v, CODE V's six-digit form), or a catalog name looked up in ``glass_map``
 (name -> Medium, index, or ``(n_d, V_d)``; matched case-insensitively, with and without
-the ``_CATALOG`` suffix).  There is no glass catalog in this package: an unknown name
-raises ``KeyError`` naming the glass, it is never guessed.
+the ``_CATALOG`` suffix), then in ``glass_table.json`` (the 17 catalog glasses whose coefficients the
+reference's bundled lens files carry).  There is no full glass catalog in this package: an unknown
+name raises ``KeyError`` naming the glass, it is never guessed.
 
 Tilts and decenters (codev/cmdproc.py:544-576): XDE YDE ZDE ADE BDE CDE create a
 ``DecenterData('decenter')`` on the current surface, DAR / BEN / REV change its type to
@@ -64,7 +65,41 @@ def _medium(token, glass_map):
                 if isinstance(gv, (tuple, list)):
                     return M.AbbeGlass(gv[0], gv[1], label=token)
                 return M.ConstantIndex(float(gv), label=token)
-    raise KeyError(f'glass {token!r}: not in glass_map (this package ships no glass catalog)')
+    m = _builtin_glass(token)
+    if m is not None:
+        return m
+    raise KeyError(f'glass {token!r}: neither in glass_map nor among the {len(_glass_table())} glasses of '
+                   f'rayoptics_b200/glass_table.json (this package ships no full catalog)')
+
+
+_GLASS_TABLE = None
+
+
+def _glass_table():
+    """rayoptics_b200/glass_table.json: the catalog glasses that the reference's bundled lens files
+    carry coefficients for (tools/make_glass_table.py)."""
+    global _GLASS_TABLE
+    if _GLASS_TABLE is None:
+        import json
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'glass_table.json')
+        try:
+            _GLASS_TABLE = json.load(open(path))
+        except OSError:
+            _GLASS_TABLE = {}
+    return _GLASS_TABLE
+
+
+def _builtin_glass(token):
+    t = _glass_table()
+    for k in (token.upper(), token.upper().split('_')[0]):
+        e = t.get(k)
+        if e is not None:
+            if e['form'] == 'sellmeier':
+                return M.Sellmeier(e['coefs'], label=e['name'])
+            from .roa import PowerSeries
+            return PowerSeries(e['coefs'], label=e['name'])
+    return None
 
 
 def open_seq(path, glass_map=None):

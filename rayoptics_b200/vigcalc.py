@@ -111,6 +111,10 @@ def aim_chief_ray(opt_model, fld, wvl, trace_fn, tol=1e-13, max_iter=30):
 def aim_all_fields(opt_model, trace_fn, wvl=None):
     osp = opt_model.optical_spec
     wvl = osp.spectral_region.central_wvl if wvl is None else wvl
+    if _wide(opt_model):        # aim_chief_ray, raytr/trace.py:634-635: the real entrance pupil search
+        from . import wideangle
+        wideangle.aim_wide_angle_fields(opt_model, wvl, trace_fn)
+        return
     for fld in osp.field_of_view.fields:
         fld.aim_info = aim_chief_ray(opt_model, fld, wvl, trace_fn)
 
@@ -206,6 +210,9 @@ def aim_all_fields_batched(opt_model, bundle_fn=None, wvl=None, tol=1e-13, max_i
         for fld in fields:
             fld.aim_info = np.array([0., 0.])
         return [f.aim_info for f in fields]
+    if _wide(opt_model):        # wide-angle fields: z_enp search on single rays (wideangle.py)
+        from . import wideangle
+        return wideangle.aim_wide_angle_fields(opt_model, wvl)
     if bundle_fn is None:
         bundle_fn = cuda_bundle_fn(opt_model)
     wvl = osp.spectral_region.central_wvl if wvl is None else wvl

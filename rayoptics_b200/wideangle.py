@@ -1,0 +1,240 @@
+"""Real entrance pupil of wide-angle fields: the search of the reference's
+``raytr/wideangle.py`` (``find_real_enp`` rev1, ``find_edge``, ``find_z_enp_on_interval``;
+/root/reference/src/rayoptics/raytr/wideangle.py:46-93,105-330,333-352,355-446).
+
+Fisheye lenses have strong pupil aberration: the chief ray of an oblique field crosses the
+axis far from the paraxial entrance pupil.  The reference parameterises the pupil position by
+its z offset from the first interface (``z_enp``), samples it from the paraxial value towards
+the first vertex until rays get through and straddle the stop centre, and then iterates
+(scipy secant ``newton``, ``brentq`` as the fallback) to the z for which the central ray hits
+the stop at height 0.  ``fld.aim_info = z_enp`` then feeds the wide-angle start rays
+(``opticalspec.ray_start_from_osp``, ``rt_pupil_kind`` 3 on the device).
+
+Same decisions, same arithmetic, same scipy solvers as the reference -- the result is the same
+double (``tests/test_trace_drivers.py::test_find_real_enp_is_the_references``).  Every ray goes
+through ``trace_fn(seq_model, pt0, dir0, wvl, **kw) -> (ray, op, wvl)``: the drop-in GPU
+``raytrace.trace`` by default, any callable with that signature in tests.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from .opticalspec import rot_v1_into_v2
+
+
+def _is_fuzzy_zero(a):
+    return abs(a) < 1e-14          # util/misc_math.py: is_fuzzy_zero
+
+
+def _default_trace_fn():
+    from . import raytrace as RT
+    return RT.trace
+
+
+def _trace_errors():
+    from .raytrace import TraceError, TraceMissedSurfaceError
+    return TraceError, TraceMissedSurfaceError
+
+
+def enp_z_coordinate(z_enp, seq_model, stop_idx, dir0, obj_dist, wvl, trace_fn):
+    """wideangle.py:46-93: trace the ray through the centre of the pupil plane at ``z_enp``
+    along ``dir0``; returns ``(point at the stop | zeros, ray, error | None)``."""
+    TraceError, _ = _trace_errors()
+    obj2enp_dist = (obj_dist + z_enp)
+    pt1 = np.array([0., 0., obj2enp_dist])
+    rot_mat = rot_v1_into_v2(np.array([0., 0., 1.]), dir0)
+    pt0 = np.matmul(rot_mat, -pt1) + pt1
+    try:
+        ray, op, w = trace_fn(seq_model, pt0, dir0, wvl, intersect_obj=False)
+    except TraceError as ray_error:
+        pkg = ray_error.ray_pkg
+        return np.array([0., 0., 0.]), (pkg[0] if pkg is not None else []), ray_error
+    return ray[stop_idx][0], ray, None
+
+
+def find_edge(f, a, b, max_iter=3):
+    """wideangle.py:333-352: binary search for the edge of the range where ``f`` evaluates"""
+    fa = f(a)
+    fb = f(b)
+    for _ in range(max_iter):
+        c = a + (b - a)/2
+        fc = f(c)
+        if fc is None:
+            b = c
+            fb = fc
+        else:
+            a = c
+            fa = fc
+    if fb is None:
+        return a, fa
+    return b, fb
+
+
+def find_z_enp_on_interval(opt_model, stop_idx, start_z, end_z, z_estimate, fld, wvl, trace_fn):
+    """wideangle.py:355-446: iterate ``z_enp`` until the ray crosses the stop at height 0.
+    Returns ``(start_coords, ray of the last evaluation, converged)``."""
+    from scipy.optimize import newton, brentq
+    TraceError, _ = _trace_errors()
+    sm, osp = opt_model['seq_model'], opt_model['optical_spec']
+    fod = opt_model['analysis_results']['parax_data'].fod
+    pt0, dir0 = osp.obj_coords(fld)
+    last = {}
+
+    def eval_z_enp(z_enp, *args):
+        final_coord, ray, err = enp_z_coordinate(z_enp, sm, stop_idx, dir0, fod.obj_dist, wvl, trace_fn)
+        last['ray'], last['err'] = ray, err
+        return final_coord[1] - 0.0
+
+    if stop_idx is None:                       # floating stop: paraxial entrance pupil
+        return np.array([0., 0., fod.enp_dist]), None, True
+    z_enp, results = z_estimate, None
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        try:
+            z_enp, results = newton(eval_z_enp, z_enp, rtol=1e-7, disp=False, full_output=True)
+        except (RuntimeError, TraceError):
+            z_enp = results.root if results is not None else z_enp
+        converged = bool(results.converged) if results is not None else False
+        ht_at_stop = last['ray'][stop_idx][0][1]
+        if abs(ht_at_stop) < 1e-6:
+            converged = True
+        start_coords = np.array([0., 0., z_enp])
+        if not converged:
+            try:
+                z_enp, results = brentq(eval_z_enp, start_z, end_z, rtol=1e-7, disp=False,
+                                        full_output=True)
+            except RuntimeError:
+                z_enp = results.root
+            start_coords = np.array([0., 0., z_enp])
+            converged = bool(results.converged)
+    return start_coords, last['ray'], converged
+
+
+def find_real_enp(opt_model, stop_idx, fld, wvl, trace_fn=None):
+    """wideangle.py:105-330 (``find_real_enp`` -> rev1): z position, relative to the first
+    interface, of the real entrance pupil of ``fld``.  Returns ``(z_enp, ray)``."""
+    _, TraceMissedSurfaceError = _trace_errors()
+    trace_fn = _default_trace_fn() if trace_fn is None else trace_fn
+    sm, osp = opt_model['seq_model'], opt_model['optical_spec']
+    fod = opt_model['analysis_results']['parax_data'].fod
+    stop_idx = 1 if stop_idx is None else stop_idx
+    pt0, dir0 = osp.obj_coords(fld)
+
+    def at(z):
+        return enp_z_coordinate(z, sm, stop_idx, dir0, fod.obj_dist, wvl, trace_fn)
+
+    def ht(z):                                  # enp_z_coordinate_wrapper
+        final_coord, ray, err = at(z)
+        return final_coord[1] if err is None else None
+
+    if fld.aim_info is not None:                # existing aim info: keep it if it is good
+        z_enp = fld.aim_info
+        final_coord, ray, err = at(z_enp)
+        if abs(final_coord[1]) < 1.48e-08:
+            return z_enp, ray
+    z_enp_0 = fod.enp_dist
+    if dir0[2] == 1:                            # axial chief ray: the paraxial pupil
+        final_coord, ray, err = at(z_enp_0)
+        return z_enp_0, ray
+
+    start_z = prev_z = end_z = None
+    del_z = -z_enp_0/16
+    z_enp = z_enp_0
+    keep_going, direction = True, 'first'
+    first_surf_misses = trial = successes = 0
+    while keep_going and trial < 64 and first_surf_misses < 2:
+        final_coord, ray, err = at(z_enp)
+        if err is None:
+            ht_at_stop = final_coord[1]
+            successes += 1
+            if start_z is None:
+                start_z = z_enp, ht_at_stop
+            prev_z = end_z
+            end_z = z_enp, ht_at_stop
+            if successes > 1:
+                if prev_z[1]*end_z[1] < 0:      # zero crossing: done
+                    keep_going = False
+            if successes == 2:
+                if abs(start_z[1]) < abs(end_z[1]):     # searching away from the crossing
+                    if direction == 'first':
+                        del_z = -del_z
+                        z_enp = z_enp_0
+                        direction = 'reverse'
+                        end_z, start_z = start_z, end_z
+        else:
+            if isinstance(err, TraceMissedSurfaceError):
+                if err.surf == 1:
+                    del_z = -del_z
+                    z_enp = z_enp_0
+                    first_surf_misses += 1
+            if start_z is not None:
+                if direction == 'first':
+                    del_z = -del_z
+                    z_enp = z_enp_0
+                    direction = 'reverse'
+                    end_z, start_z = start_z, end_z
+                else:
+                    keep_going = False
+        z_enp += del_z
+        if _is_fuzzy_zero(z_enp):               # never sample the first vertex itself
+            z_enp = del_z/10
+        trial += 1
+
+    z_enp_a, ht_at_stop_a = start_z
+    z_enp_b, ht_at_stop_b = end_z
+    if z_enp_a == z_enp_b:                      # one successful ray only: sample around it
+        start_new, end_new = z_enp_a - del_z, z_enp_b + del_z
+        start_z = end_z = None
+        for z_enp in np.linspace(start_new, end_new, num=8):
+            final_coord, ray, err = at(z_enp)
+            if err is None:
+                if start_z is None:
+                    start_z = z_enp, final_coord[1]
+                end_z = z_enp, final_coord[1]
+        a, b = start_z[0], end_z[0]
+    elif ht_at_stop_a*ht_at_stop_b < 0:         # crossing inside the interval
+        a, b = z_enp_a, z_enp_b
+        if prev_z is not None:
+            z_enp_c, ht_at_stop_c = prev_z
+            if ht_at_stop_c*ht_at_stop_b < 0:
+                start_z = prev_z
+                a, b = z_enp_c, z_enp_b
+    else:                                       # no crossing yet: look for the beam edges
+        z_enp_edge_b, ht_edge_b = find_edge(ht, z_enp_b, z_enp_b + del_z, max_iter=6)
+        if ht_edge_b*ht_at_stop_b < 0:
+            start_z = z_enp_b, ht_at_stop_b
+            end_z = z_enp_edge_b, ht_edge_b
+            a, b = z_enp_b, z_enp_edge_b
+        else:
+            z_enp_edge_a, ht_edge_a = find_edge(ht, z_enp_a, z_enp_a - del_z, max_iter=6)
+            if ht_edge_a*ht_at_stop_a < 0:
+                start_z = z_enp_a, ht_at_stop_a
+                end_z = z_enp_edge_a, ht_edge_a
+                a, b = z_enp_a, z_enp_edge_a
+            else:                               # no ray through the stop centre
+                z_enp_cntr = z_enp_edge_a + (z_enp_edge_b - z_enp_edge_a)/2
+                final_coord, ray, err = at(z_enp_cntr)
+                return z_enp_b, ray
+
+    if _is_fuzzy_zero(end_z[1] - start_z[1]):
+        z_estimate = start_z[0]
+    else:
+        z_estimate = start_z[0] - ((end_z[0] - start_z[0])/(end_z[1] - start_z[1]))*start_z[1]
+    start_coords, ray, _ = find_z_enp_on_interval(opt_model, stop_idx, a, b, z_estimate, fld, wvl,
+                                                  trace_fn)
+    return start_coords[2], ray
+
+
+def aim_wide_angle_fields(opt_model, wvl=None, trace_fn=None):
+    """``aim_chief_ray`` (raytr/trace.py:627-640) for every field of a wide-angle specification:
+    sets ``fld.aim_info = z_enp``; returns the list."""
+    sm, osp = opt_model['seq_model'], opt_model['optical_spec']
+    wvl = sm.central_wavelength() if wvl is None else wvl
+    out = []
+    for fld in osp['fov'].fields:
+        z_enp, _ = find_real_enp(opt_model, sm.stop_surface, fld, wvl, trace_fn)
+        fld.aim_info = float(z_enp)
+        out.append(fld.aim_info)
+    return out

@@ -452,3 +452,58 @@ def test_weighted_sharding():
     assert max(work)/min(work) < 1.02 and cuts[0][1] - cuts[0][0] < cuts[2][1] - cuts[2][0]
     summ = np.zeros((2, 16)); summ[0, 0] = 100; summ[1, 0] = 50; summ[1, 3] = 50
     assert P.weights_from_summary(summ).tolist() == [100.0, 65.0]
+
+
+def test_local_transforms_equal_the_references():
+    """model.DecenterData / forward_transform / compute_local_transforms against the reference's own
+    elem/surface.py:274-337 + elem/transform.py:79-166 on random decenter sets (all four dtypes):
+    same rotation matrices, translations AND numpy memory layouts (which decide the dgemv rounding of
+    the trace, table.py has_tfrm).  transforms3d is not installed: the reference's euler2rot3d gets
+    this package's restatement of `euler2mat(..., 'rxyz')` through the ref_harness stand-in module,
+    so what is compared is everything around it; the rotation itself is pinned by the CODE V listing."""
+    import importlib
+    import sys
+    import types
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip('/root/reference not present')
+    R = rh.ref()
+    t3 = sys.modules['transforms3d']
+    t3.euler.euler2mat = lambda ai, aj, ak, axes='rxyz': M.euler2mat_rxyz(ai, aj, ak)
+    RT = importlib.import_module('rayoptics.elem.transform')
+    S = R.surface
+    rng = np.random.default_rng(5)
+    dtypes = ['decenter', 'reverse', 'dec and return', 'bend']
+    for trial in range(40):
+        n = int(rng.integers(3, 9))
+        own, ref, thi = [], [], rng.uniform(-30, 60, n - 1)
+        for i in range(n):
+            so, sr = M.Surface(), S.Surface()
+            if rng.random() < 0.6:
+                dt = dtypes[int(rng.integers(4))]
+                vals = [float(v) if rng.random() < 0.7 else 0.0 for v in rng.uniform(-20, 20, 5)]
+                so.decenter = M.DecenterData(dt, *vals)
+                sr.decenter = S.DecenterData(dt, *vals)
+                sr.decenter.update()
+            own.append(so)
+            ref.append(sr)
+        gaps = [M.Gap(float(t)) for t in thi]
+        mine = M.compute_local_transforms(own, gaps)
+        seq = types.SimpleNamespace(ifcs=ref, gaps=gaps, get_num_surfaces=lambda: n)
+        theirs = RT.compute_local_transforms(seq, None, 1)
+        assert len(mine) == len(theirs) == n
+        for (ra, ta), (rb, tb) in zip(mine, theirs):
+            assert np.array_equal(ra, rb) and np.array_equal(ta, tb)
+            assert ra.flags['C_CONTIGUOUS'] == rb.flags['C_CONTIGUOUS']
+            assert ra.flags['F_CONTIGUOUS'] == rb.flags['F_CONTIGUOUS']
+
+
+def test_builtin_glass_table():
+    """glass names resolve without a glass_map for the catalog glasses the reference's lens files
+    carry; N-BK7 gives the datasheet n_d; unknown names still raise."""
+    from rayoptics_b200 import seq
+    assert abs(seq._medium('N-BK7', None).rindex(587.5618) - 1.5168) < 2e-6
+    assert abs(seq._medium('n-lak9_schott', {}).rindex(587.5618) - 1.6910) < 2e-5
+    assert seq._medium('N-BK7', {'N-BK7': 1.5}).rindex(500.0) == 1.5          # the caller's map wins
+    with pytest.raises(KeyError, match='glass_table'):
+        seq._medium('NOT-A-GLASS', None)

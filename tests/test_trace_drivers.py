@@ -540,3 +540,48 @@ def test_sequential_model_methods_equal_the_references():
     want = ns['trace_wavefront'](H.seq_model, fa, 587.6, 0.0, num_rays=8)
     got = b.seq_model.trace_wavefront(fb, 587.6, 0.0, num_rays=8, tracer=oracle_tracer)
     assert np.array_equal(want, got)
+
+
+@needs_ref
+def test_find_real_enp_is_the_references():
+    """rayoptics_b200/wideangle.py (the wide-angle entrance pupil search) against the reference's
+    raytr/wideangle.py find_real_enp run unmodified on the hybrid model: same z_enp, bit for bit,
+    for every field of the fisheye fixture -- from scratch (no aim info) and with the stored value."""
+    import importlib
+    import warnings
+    from oracle import ref_model, ref_harness as rh
+    from rayoptics_b200 import wideangle as W
+    ref_model.modules()
+    RW = importlib.import_module('rayoptics.raytr.wideangle')
+    a, b = load_model('fisheye'), load_model('fisheye')
+    H = ref_model.HybridModel(a)
+    R = rh.ref()
+
+    def ref_trace_fn(sm, pt0, dir0, wvl, **kw):
+        kw.setdefault('first_surf', 1)
+        kw.setdefault('last_surf', sm.get_num_surfaces() - 2)
+        return R.raytrace.trace_raw(iter(rh.ref_path(sm, wvl)), np.array(pt0, dtype=float),
+                                    np.array(dir0, dtype=float), wvl, **kw)
+
+    import rayoptics_b200.raytrace as BR
+    wvl = a.seq_model.central_wavelength()
+    stored = [f.aim_info for f in a.optical_spec.field_of_view.fields]
+    for fa, fb, s in zip(a.optical_spec.field_of_view.fields, b.optical_spec.field_of_view.fields, stored):
+        for start in (None, s):
+            fa.aim_info = fb.aim_info = start
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                z_ref, rr = RW.find_real_enp(H, a.seq_model.stop_surface, fa, wvl)
+                # the mirror's search raises / catches the mirror's TraceError classes: give it a
+                # tracer that translates the reference's exceptions
+                def tf(sm, pt0, dir0, w, **kw):
+                    try:
+                        return ref_trace_fn(sm, pt0, dir0, w, **kw)
+                    except R.traceerror.TraceError as e:
+                        cls = getattr(BR, type(e).__name__)
+                        err = cls.__new__(cls)
+                        err.__dict__.update(e.__dict__)
+                        raise err
+                z_own, ray = W.find_real_enp(b, b.seq_model.stop_surface, fb, wvl, trace_fn=tf)
+            assert z_own == z_ref
+            assert abs(z_ref - s) < 1e-9
