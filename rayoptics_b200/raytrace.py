@@ -29,7 +29,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _abi, engine as E, table as T
+from . import _abi, engine as E
 from .table import SurfaceTable
 
 try:                                    # the reference's own exception classes, when importable
@@ -59,27 +59,61 @@ def set_device(device):
     _DEVICE = int(device)
 
 
+def _phase_key(pe):
+    if pe is None:
+        return None
+    fp = [type(pe).__name__, getattr(getattr(pe, 'phase_fct', None), '__name__', None)]
+    for k in ('ref_pt', 'obj_pt', 'grating_normal', 'coefficients'):
+        v = getattr(pe, k, None)
+        fp.append(None if v is None else tuple(map(float, v)))
+    for k in ('ref_virtual', 'obj_virtual', 'ref_wl', 'order', '_grating_spacing_nm'):
+        fp.append(getattr(pe, k, None))
+    return tuple(fp)
+
+
+def _aperture_key(ca):
+    return (type(ca).__name__, getattr(ca, 'radius', None), getattr(ca, 'x_half_width', None),
+            getattr(ca, 'y_half_width', None), getattr(ca, 'x_offset', 0.0), getattr(ca, 'y_offset', 0.0),
+            bool(getattr(ca, 'is_obscuration', False)))
+
+
 def _fingerprint(segs):
-    """Cache key of a path: the bytes of the very descriptor records the device table is
-    built from, plus the indices.  Whatever the kernels can see -- profile numbers,
-    coefficient counts, every clear aperture's type / size / offset / obscuration flag,
-    transforms, z_dir, phase-element parameters -- is in those records, so an in-place
-    edit of any of them yields a new table.  (The reference's invalidation point is
-    update_model(), seq/sequential.py:666-668, which clears its own path cache.)
-    Returns ``(key, descs, indices)``."""
-    descs, ns = T.describe_path(segs)
-    return (bytes(descs), tuple(ns)), descs, ns
+    """Cache key of a path: every attribute ``table._describe_interface`` reads -- profile numbers and
+    coefficient count, interact mode, max_aperture and each clear aperture's type / size / offsets /
+    obscuration flag, transform (values AND numpy memory order, which selects the dgemv rounding),
+    index, z_dir, phase-element parameters -- as a tuple of Python values (~25 us for 13 interfaces;
+    compiling the descriptors costs 6x that).  An in-place edit of any of them yields a new table
+    (the reference's own invalidation point is update_model(), seq/sequential.py:666-668)."""
+    fp = []
+    for seg in segs:
+        ifc, _gap, tfrm, n, z_dir = (tuple(seg) + (None,)*5)[:5]
+        prf = getattr(ifc, 'profile', None)
+        coefs = getattr(prf, 'coefs', None)
+        cas = getattr(ifc, 'clear_apertures', None)
+        if tfrm is None:
+            tk = None
+        else:
+            r = tfrm[0]
+            tk = ((r.tobytes(), r.flags['C_CONTIGUOUS'], r.flags['F_CONTIGUOUS']) if hasattr(r, 'tobytes')
+                  else repr(r), tuple(map(float, tfrm[1])))
+        fp.append((type(ifc).__name__, type(prf).__name__, getattr(prf, 'cv', None),
+                   getattr(prf, 'cc', None), getattr(prf, 'ec', None), getattr(prf, 'cR', None),
+                   None if coefs is None else tuple(coefs), getattr(prf, 'max_nonzero_coef', None),
+                   getattr(ifc, 'interact_mode', None), getattr(ifc, 'max_aperture', None),
+                   None if not cas else tuple(_aperture_key(ca) for ca in cas), n, z_dir,
+                   _phase_key(getattr(ifc, 'phase_element', None)) if hasattr(ifc, 'phase_element') else 0,
+                   tk))
+    return tuple(fp)
 
 
 def _table_for_path(segs, wvl=None):
-    """Surface table of a path, cached on its compiled content."""
-    key, descs, ns = _fingerprint(segs)
-    fp = (key, wvl, _DEVICE)
+    """Surface table of a path, cached on the content it is compiled from."""
+    fp = (_fingerprint(segs), wvl, _DEVICE)
     tab = _PATH_CACHE.get(fp)
     if tab is None:
         if len(_PATH_CACHE) > 64:
             _PATH_CACHE.clear()
-        tab = SurfaceTable(descs, np.array([ns]), None if wvl is None else [float(wvl)], _DEVICE)
+        tab = SurfaceTable.from_path(segs, device=_DEVICE, wvl=wvl)
         _PATH_CACHE[fp] = tab
     return tab
 

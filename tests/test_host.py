@@ -310,12 +310,12 @@ def test_table_cache_key_sees_in_place_edits():
     opm = load_model('exotic')
     sm = opm.seq_model
     segs = lambda: list(sm.path(sm.central_wavelength()))       # noqa: E731
-    k0 = RT._fingerprint(segs())[0]
-    assert RT._fingerprint(segs())[0] == k0
+    k0 = RT._fingerprint(segs())
+    assert RT._fingerprint(segs()) == k0
     seen = {k0}
 
     def changed():
-        k = RT._fingerprint(segs())[0]
+        k = RT._fingerprint(segs())
         assert k not in seen
         seen.add(k)
 
@@ -341,6 +341,27 @@ def test_table_cache_key_sees_in_place_edits():
     changed()
     sm.ifcs[1].max_aperture *= 2.0
     changed()
+    sm.ifcs[1].interact_mode = 'reflect'
+    changed()
+    sm.ifcs[2].profile.cv += 1e-6
+    changed()
+    rt, t = sm.lcl_tfrms[2]
+    sm.lcl_tfrms[2] = (rt, t + np.array([0., 1e-3, 0.]))
+    changed()
+    sm.lcl_tfrms[3] = (np.ascontiguousarray(sm.lcl_tfrms[3][0].T).T.copy(order='F')
+                       if sm.lcl_tfrms[3][0].flags['C_CONTIGUOUS'] else np.ascontiguousarray(sm.lcl_tfrms[3][0]),
+                       sm.lcl_tfrms[3][1])
+    if not np.array_equal(sm.lcl_tfrms[3][0], np.identity(3)):
+        changed()                          # same numbers, other memory order: other dgemv rounding
+    # and the key is complete with respect to what the table is compiled from: equal keys <=> equal
+    # descriptor bytes over all fixture models
+    seen_keys = {}
+    for name in MODEL_NAMES + PHASE_MODEL_NAMES + ANGULAR_MODEL_NAMES:
+        m = load_model(name).seq_model
+        for w in m.wvlns:
+            p = list(m.path(w))
+            descs, ns = T.describe_path(p)
+            assert seen_keys.setdefault(RT._fingerprint(p), (bytes(descs), tuple(ns))) == (bytes(descs), tuple(ns))
 
 
 def test_nan_status_decoding():
