@@ -8,7 +8,10 @@ rotationally symmetric sequential system:
 
   RDM, TITLE, DIM, EPD / FNO / NA / NAO, WL, REF, XAN YAN / XOB YOB / XIM YIM,
   VUX VLX VUY VLY, SO / S / SI (curvature or radius, thickness, glass | REFL),
-  STO, CIR [EDG], K / CON, ASP with A..J (r**4 .. r**20), SPS coefficients are not read.
+  STO, CIR [EDG], K / CON, ASP with A..J (r**4 .. r**20), private catalogs (PRV / PWL / 'name' n.. /
+  END: tabulated index, linear interpolation between the tabulated wavelengths), diffractive
+  surfaces (DIF DOE, HOR, HWL, HCT R, HCO Cn: DiffractiveElement with the radial phase function,
+  codev/cmdproc.py:579-618), '&' continuation lines.  SPS coefficients are not read.
 
 Glasses: ``REFL`` / ``AIR`` / empty, a fictitious glass code ``nnn.vvv`` (n_d = 1.nnn,
 V_d = vv.v, CODE V's six-digit form), or a catalog name looked up in ``glass_map``
@@ -30,6 +33,8 @@ from __future__ import annotations
 
 import re
 
+import numpy as np
+
 from . import model as M
 from .opticalspec import OpticalSpecs, WvlSpec, PupilSpec, FieldSpec, FocusRange
 
@@ -41,9 +46,19 @@ _ASP_COEFS = 'ABCDEFGHJ'
 
 
 def _commands(text):
-    """lines / ';'-separated commands, comments ('!') dropped, quoted strings kept whole"""
+    """lines / ';'-separated commands, comments ('!') dropped, quoted strings kept whole,
+    '&' continuation lines joined"""
+    joined, pending = [], ''
     for line in text.splitlines():
-        line = line.split('!', 1)[0]
+        line = line.split('!', 1)[0].rstrip()
+        if line.endswith('&'):
+            pending += line[:-1]
+            continue
+        joined.append(pending + line)
+        pending = ''
+    if pending:
+        joined.append(pending)
+    for line in joined:
         for part in line.split(';'):
             toks = re.findall(r"'[^']*'|\"[^\"]*\"|\S+", part)
             if toks:
@@ -114,9 +129,24 @@ def open_seq(path, glass_map=None):
     vig = {}
     surfs = []        # dicts: cv, thi, glass token, mode, stop, cc, coefs, cir
     cur = None
+    private, private_wvls, in_private = {}, None, False
     for toks in _commands(text):
         tla = toks[0][:3].upper()
         args = toks[1:]
+        if tla == 'PRV':                       # private catalog (codev/cmdproc.py:358-368, 330-356)
+            in_private = True
+            continue
+        if in_private:
+            if tla == 'END':
+                in_private, private_wvls = False, None
+            elif tla == 'PWL':
+                private_wvls = [float(a) for a in args]
+            elif toks[0][0] in '\'"' and private_wvls:
+                ns = [float(a) for a in args]
+                order = np.argsort(private_wvls[:len(ns)])          # tabulated index, ascending wavelength
+                private[toks[0].strip('\'"').upper()] = M.TableIndex(
+                    [private_wvls[i] for i in order], [ns[i] for i in order], label=toks[0].strip('\'"'))
+            continue
         if tla == 'RDM':
             radius_mode = (not args) or args[0].upper().startswith('Y')
         elif tla == 'TIT':
@@ -160,6 +190,27 @@ def open_seq(path, glass_map=None):
         elif toks[0].upper() in _ASP_COEFS and cur is not None:
             cur['coefs'] = cur['coefs'] or [0.0]*10
             cur['coefs'][_ASP_COEFS.index(toks[0].upper()) + 1] = float(args[0])   # A -> r**4
+        elif toks[0].upper() in ('DIF', 'HOR', 'HWL', 'HCT', 'HCO') and cur is not None:
+            # diffractive surface (codev/cmdproc.py:579-618): DIF DOE creates the element, HOR the
+            # order, HWL the construction wavelength, HCT R the radial phase function, HCO Cn its
+            # coefficients (HCC: optimisation controls, ignored)
+            key = toks[0].upper()
+            if key == 'DIF':
+                if any(a.upper() == 'DOE' for a in args):
+                    cur['doe'] = {'order': 1, 'ref_wl': 550.0, 'coefs': [], 'radial': False}
+            elif 'doe' in cur:
+                d = cur['doe']
+                if key == 'HOR':
+                    d['order'] = float(args[0])
+                elif key == 'HWL':
+                    d['ref_wl'] = float(args[0])
+                elif key == 'HCT':
+                    d['radial'] = d['radial'] or any(a.upper() == 'R' for a in args)
+                elif key == 'HCO':
+                    cidx = int(args[0].upper().lstrip('C'))
+                    if cidx > len(d['coefs']):
+                        d['coefs'].extend([0.]*(cidx - len(d['coefs'])))
+                    d['coefs'][cidx - 1] = float(args[1])
         elif tla in _TILTS and toks[0].upper() == tla and cur is not None:
             dc = cur.setdefault('decenter', {'dtype': 'decenter', 'dec': [0., 0., 0.],
                                              'euler': [0., 0., 0.]})
@@ -200,6 +251,11 @@ def open_seq(path, glass_map=None):
             ifc.max_aperture = s['cir']
         if s.get('decenter'):
             ifc.decenter = M.DecenterData.from_dict(s['decenter'])
+        if s.get('doe'):
+            if not s['doe']['radial']:
+                raise NotImplementedError('.seq diffractive surface without HCT R (radial phase function)')
+            ifc.phase_element = M.DiffractiveElement(coefficients=s['doe']['coefs'], ref_wl=s['doe']['ref_wl'],
+                                                     order=s['doe']['order'], phase_fct=M.radial_phase_fct)
         if s['stop']:
             stop_surface = i
         ifcs.append(ifc)
@@ -207,6 +263,8 @@ def open_seq(path, glass_map=None):
             if mode == 'reflect':
                 med = medium_before if medium_before is not None else M.Air()
                 z = -z
+            elif g is not None and g.strip('\'"').upper() in private:
+                med = private[g.strip('\'"').upper()]
             else:
                 med = _medium(g, glass_map)
             gaps.append(M.Gap(s['thi'], med))

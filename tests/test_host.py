@@ -528,3 +528,27 @@ def test_builtin_glass_table():
     assert seq._medium('N-BK7', {'N-BK7': 1.5}).rindex(500.0) == 1.5          # the caller's map wins
     with pytest.raises(KeyError, match='glass_table'):
         seq._medium('NOT-A-GLASS', None)
+
+
+def test_seq_reader_private_catalog_and_doe():
+    """CODV_65988.seq (the reference's hybrid-asphere import test): '&' continuation lines, a private
+    catalog glass (PRV / PWL / END -> tabulated index), and a diffractive surface (DIF DOE, HOR, HWL,
+    HCT R, HCO C1; codev/cmdproc.py:579-618) compiled into the table as a radial DOE."""
+    from rayoptics_b200 import seq
+    path = '/root/reference/src/rayoptics/codev/tests/CODV_65988.seq'
+    if not os.path.exists(path):
+        pytest.skip('/root/reference not present')
+    opm = seq.open_seq(path)
+    sm = opm.seq_model
+    assert sm.get_num_surfaces() == 4 and sm.wvlns == [656.2725, 587.5618, 486.1327]
+    med = sm.gaps[1].medium
+    assert type(med).__name__ == 'TableIndex' and med.rindex(587.6) == 1.53116 and med.rindex(486.1) == 1.5378
+    assert 1.527 < med.rindex(656.2725) < 1.5286                  # between the 700 and 650 nm entries
+    pe = sm.ifcs[1].phase_element
+    assert (type(pe).__name__, pe.coefficients, pe.ref_wl, pe.order) == \
+        ('DiffractiveElement', [-0.001807322521767816], 587.5618, 1.0)
+    prf = sm.ifcs[1].profile
+    assert type(prf).__name__ == 'EvenPolynomial' and prf.cc == -0.71
+    assert prf.coefs[1:4] == [-0.1581980090969e-4, -0.2770951746068999e-6, -0.1216086045095e-8]
+    descs, n_by_wvl, _ = T.describe_model(sm)
+    assert descs[1].phase_kind == _abi.PHASE_IDS['DiffractiveElement'] and descs[1].n_phase_coefs == 1
