@@ -6,7 +6,8 @@ resolved by the un-vendored ``opticalglass`` catalogs.  This reader builds the
 symmetric sequential system:
 
   UNIT, NAME, ENPD / FNUM / OBNA, WAVM (or WAVL / WWGT), FTYP, XFLN / YFLN,
-  VDXN VDYN VCXN VCYN, SURF with TYPE (STANDARD, EVENASPH, XOSPHERE, TOROIDAL, COORDBRK),
+  VDXN VDYN VCXN VCYN, SURF with TYPE (STANDARD, EVENASPH, XOSPHERE, TOROIDAL, COORDBRK, PARAXIAL,
+  DGRATING),
   CURV, DISZ, GLAS, DIAM, CONI, PARM, XDAT, STOP.
 
 Coordinate breaks (zmxread.py:314-316,341-355): a COORDBRK surface becomes a phantom
@@ -98,7 +99,7 @@ def open_zmx(path, glass_map=None):
             continue
         elif cmd == 'TYPE':
             cur['type'] = items[0]
-            if items[0] not in ('STANDARD', 'EVENASPH', 'XOSPHERE', 'TOROIDAL', 'COORDBRK'):
+            if items[0] not in ('STANDARD', 'EVENASPH', 'XOSPHERE', 'TOROIDAL', 'COORDBRK', 'PARAXIAL', 'DGRATING'):
                 raise NotImplementedError(f'.zmx surface TYPE {items[0]}')
         elif cmd == 'CURV':
             cur['cv'] = float(items[0])
@@ -160,7 +161,15 @@ def open_zmx(path, glass_map=None):
             prf = M.Spherical(c=s['cv'])
         if i == 0 or i == len(surfs) - 1:
             mode = 'dummy'
-        ifc = M.Surface(profile=prf, interact_mode=mode)
+        if s['type'] == 'PARAXIAL':             # zmxread.py:317-320,364-366: PARM 1 = focal length
+            f = s['parm'].get(1, 0.0)
+            ifc = M.ThinLens(power=(1.0/f if f != 0.0 else 0.0), interact_mode=mode)
+        else:
+            ifc = M.Surface(profile=prf, interact_mode=mode)
+            if s['type'] == 'DGRATING':         # zmxread.py:321-324,356-360: PARM 1 = lines/um, PARM 2 = order
+                # the reference assigns through the grating_freq_um SETTER: lpmm = freq*1000 (doe.py:105-107)
+                ifc.phase_element = M.DiffractionGrating(order=s['parm'].get(2, 1), interact_mode=mode)
+                ifc.phase_element.grating_lpmm = s['parm'].get(1, 1.0)*1000
         ifc.decenter = decenter
         if s['diam'] is not None and s['diam'] != 0.0:
             ifc.max_aperture = s['diam']

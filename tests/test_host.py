@@ -552,3 +552,24 @@ def test_seq_reader_private_catalog_and_doe():
     assert prf.coefs[1:4] == [-0.1581980090969e-4, -0.2770951746068999e-6, -0.1216086045095e-8]
     descs, n_by_wvl, _ = T.describe_model(sm)
     assert descs[1].phase_kind == _abi.PHASE_IDS['DiffractiveElement'] and descs[1].n_phase_coefs == 1
+
+
+def test_zmx_reader_paraxial_and_grating(tmp_path):
+    """PARAXIAL -> ThinLens(power = 1/PARM1), DGRATING -> DiffractionGrating(PARM1 lines/um, PARM2 order)
+    (zemax/zmxread.py:317-324,356-366); both compile into the table."""
+    from rayoptics_b200 import zmx
+    text = '\n'.join([
+        'UNIT MM X W X CM MR CPMM', 'ENPD 10', 'WAVM 1 0.55 1', 'FTYP 0 0 1 1 0 0 0', 'XFLN 0', 'YFLN 0',
+        'SURF 0', ' TYPE STANDARD', ' CURV 0', ' DISZ INFINITY',
+        'SURF 1', ' STOP', ' TYPE PARAXIAL', ' CURV 0', ' DISZ 5', ' PARM 1 100', ' DIAM 5',
+        'SURF 2', ' TYPE DGRATING', ' CURV 0', ' DISZ 95', ' PARM 1 0.3', ' PARM 2 1', ' DIAM 5',
+        'SURF 3', ' TYPE STANDARD', ' CURV 0', ' DISZ 0'])
+    f = tmp_path / 'thin.zmx'
+    f.write_text(text)
+    opm = zmx.open_zmx(str(f))
+    sm = opm.seq_model
+    assert type(sm.ifcs[1]).__name__ == 'ThinLens' and sm.ifcs[1].optical_power == 0.01
+    g = sm.ifcs[2].phase_element
+    assert type(g).__name__ == 'DiffractionGrating' and g.order == 1 and g.grating_lpmm == 0.3*1000
+    descs, _, _ = T.describe_model(sm)
+    assert descs[1].profile == _abi.PROFILE_IDS['ThinLens'] and descs[2].phase_kind == _abi.PHASE_IDS['DiffractionGrating']
