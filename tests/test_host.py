@@ -573,3 +573,19 @@ def test_zmx_reader_paraxial_and_grating(tmp_path):
     assert type(g).__name__ == 'DiffractionGrating' and g.order == 1 and g.grating_lpmm == 0.3*1000
     descs, _, _ = T.describe_model(sm)
     assert descs[1].profile == _abi.PROFILE_IDS['ThinLens'] and descs[2].phase_kind == _abi.PHASE_IDS['DiffractionGrating']
+
+
+def test_seq_tokenizer_known_answers():
+    """The reference's own tokenizer tests (codev/tests/test_reader.py:6-45: continuation lines,
+    ';' commands, '!' comments, blanks as delimiters, quoted strings) applied to seq._commands."""
+    from rayoptics_b200 import seq
+
+    def toks(lines):
+        return [[t.strip('\'"') for t in cmd] for cmd in seq._commands('\n'.join(lines))]
+    assert toks(['ab&', 'cd&', 'ef', 'gh']) == [['abcdef'], ['gh']]
+    assert toks(['ab; cd!ef; gh']) == [['ab'], ['cd']]
+    assert toks(['ab; cd; ef', 'gh;ij& ', 'kl; mn']) == [['ab'], ['cd'], ['ef'], ['gh'], ['ijkl'], ['mn']]
+    assert toks(['s &', '.07 10 ', 's & ', ' 0 .001']) == [['s', '.07', '10'], ['s', '0', '.001']]
+    assert toks(['tit "this is a title"', ' ! this is a comment line', 'dim m', 'so 0 1e11 ! infinite object']) == \
+        [['tit', 'this is a title'], ['dim', 'm'], ['so', '0', '1e11']]
+    assert toks([]) == [] and toks(['', '! this comment will be stripped out', '', '    ! so will this one']) == []
