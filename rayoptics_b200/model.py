@@ -909,8 +909,23 @@ class OpticalModel:
     def __getitem__(self, key):
         return getattr(self, self._keys[key])
 
+    dimensions = 'mm'        # SystemSpec.dimensions (optical/opticalmodel.py:33-97)
+
     def nm_to_sys_units(self, nm):
-        return 1e-6*nm   # millimetres
+        """SystemSpec.nm_to_sys_units, optical/opticalmodel.py:77-97 (the CODE V importer stores
+        'inches', which that function does not know and passes through -- kept as is)"""
+        d = self.dimensions
+        if d == 'm':
+            return 1e-9*nm
+        if d == 'cm':
+            return 1e-7*nm
+        if d == 'mm':
+            return 1e-6*nm
+        if d == 'in':
+            return 1e-6*nm/25.4
+        if d == 'ft':
+            return 1e-6*nm/304.8
+        return nm
 
     def update_model(self, **kwargs):
         self.seq_model.update_model(**kwargs)
@@ -919,6 +934,8 @@ class OpticalModel:
 
     def to_dict(self):
         d = {'format': 'b200rt-model-v1', 'name': self.name}
+        if self.dimensions != 'mm':
+            d['dimensions'] = self.dimensions
         d.update(self.seq_model.to_dict())
         if self.optical_spec is not None:
             d['optical_spec'] = self.optical_spec.to_dict()
@@ -933,7 +950,10 @@ class OpticalModel:
         from .opticalspec import OpticalSpecs
         sm = SequentialModel.from_dict(d)
         osp = OpticalSpecs.from_dict(d['optical_spec']) if 'optical_spec' in d else None
-        return cls(sm, osp, name=d.get('name', ''))
+        opm = cls(sm, osp, name=d.get('name', ''))
+        if 'dimensions' in d:
+            opm.dimensions = d['dimensions']
+        return opm
 
     @classmethod
     def load(cls, path):

@@ -107,8 +107,10 @@ def _glass_table():
 
 def _builtin_glass(token):
     t = _glass_table()
+    squeeze = lambda x: x.replace('-', '').replace(' ', '')          # noqa: E731  (CODE V writes NBK7_SCHOTT)
+    by_squeezed = {squeeze(k): v for k, v in t.items()}
     for k in (token.upper(), token.upper().split('_')[0]):
-        e = t.get(k)
+        e = t.get(k) or by_squeezed.get(squeeze(k))
         if e is not None:
             if e['form'] == 'sellmeier':
                 return M.Sellmeier(e['coefs'], label=e['name'])
@@ -122,6 +124,7 @@ def open_seq(path, glass_map=None):
     with open(path) as f:
         text = f.read()
     radius_mode = False
+    units = 'mm'
     title = ''
     wvls, ref_wl = [587.6], 0
     pupil = None
@@ -141,7 +144,12 @@ def open_seq(path, glass_map=None):
                 in_private, private_wvls = False, None
             elif tla == 'PWL':
                 private_wvls = [float(a) for a in args]
-            elif toks[0][0] in '\'"' and private_wvls:
+            elif toks[0][0] in '\'"' and args and args[0].upper() == 'LAU':
+                # Laurent dispersion formula: n^2 = A0 + A1 l^2 + A2 l^-2 + A3 l^-4 + A4 l^-6 + A5 l^-8 (l in um)
+                from .roa import PowerSeries
+                coefs = ([float(a) for a in args[1:7]] + [0.0]*6)[:6]
+                private[toks[0].strip('\'"').upper()] = PowerSeries(coefs, label=toks[0].strip('\'"'))
+            elif toks[0][0] in '\'"' and private_wvls and args and re.fullmatch(r'[-+0-9.eE]+', args[0]):
                 ns = [float(a) for a in args]
                 order = np.argsort(private_wvls[:len(ns)])          # tabulated index, ascending wavelength
                 private[toks[0].strip('\'"').upper()] = M.TableIndex(
@@ -152,8 +160,10 @@ def open_seq(path, glass_map=None):
         elif tla == 'TIT':
             title = ' '.join(args).strip('\'"')
         elif tla == 'DIM':
-            if args and args[0].upper()[0] != 'M':
-                raise NotImplementedError('DIM other than millimetres')
+            # system units: numbers are kept as written (the reference stores the unit in system_spec,
+            # codev/cmdproc.py:281-289, and traces in those units too); only nm -> system units needs it
+            dim = args[0].upper()[0] if args else 'M'
+            units = {'M': 'mm', 'C': 'cm', 'I': 'inches'}.get(dim, 'mm')
         elif toks[0].upper() in ('EPD', 'FNO', 'NA', 'NAO'):
             key = {'EPD': ('object', 'epd'), 'FNO': ('image', 'f/#'), 'NA': ('image', 'NA'),
                    'NAO': ('object', 'NA')}[toks[0].upper()]
@@ -296,4 +306,6 @@ def open_seq(path, glass_map=None):
     # the thickness on the SI line is the defocus from the image surface
     osp = OpticalSpecs(WvlSpec(wvls, ref_wl), PupilSpec(*pupil), FieldSpec(fkey, max_f, fields),
                        FocusRange(surfs[-1]['thi'], 0.0))
-    return M.OpticalModel(sm, osp, name=title or str(path).rsplit('/', 1)[-1])
+    opm = M.OpticalModel(sm, osp, name=title or str(path).rsplit('/', 1)[-1])
+    opm.dimensions = units
+    return opm

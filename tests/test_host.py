@@ -589,3 +589,23 @@ def test_seq_tokenizer_known_answers():
     assert toks(['tit "this is a title"', ' ! this is a comment line', 'dim m', 'so 0 1e11 ! infinite object']) == \
         [['tit', 'this is a title'], ['dim', 'm'], ['so', '0', '1e11']]
     assert toks([]) == [] and toks(['', '! this comment will be stripped out', '', '    ! so will this one']) == []
+
+
+def test_seq_reader_units_and_laurent_glass(tmp_path):
+    """DIM I / C (codev/cmdproc.py:281-289, SystemSpec.nm_to_sys_units incl. its pass-through for the
+    importer's 'inches'), a private-catalog glass given by Laurent coefficients, and CODE V's hyphen-less
+    catalog names (NBK7_SCHOTT) resolved through the built-in table."""
+    from rayoptics_b200 import seq
+    f = tmp_path / 'u.seq'
+    f.write_text('\n'.join([
+        'RDM', 'DIM I', 'EPD 1', 'WL 587.6', 'PRV', ' PWL 550.0',
+        " 'NOA61' LAU 2.36390625 0.0 0.025493134 -0.000580235 -0.349933e-5 0.445404e-7", 'END',
+        'SO 0 1e11', "S 10 0.2 'NOA61'", ' STO', 'S -10 0.1 NBK7_SCHOTT', 'S 0 9', 'SI 0 0']))
+    opm = seq.open_seq(str(f))
+    assert opm.dimensions == 'inches' and opm.nm_to_sys_units(500.0) == 500.0
+    n = opm.seq_model.gaps[1].medium.rindex(587.5618)
+    assert abs(n - 1.5597) < 2e-4                                  # NOA61: n_d = 1.56
+    assert abs(opm.seq_model.gaps[2].medium.rindex(587.5618) - 1.5168) < 2e-6
+    assert M.OpticalModel.from_dict(opm.to_dict()).dimensions == 'inches'
+    opm.dimensions = 'cm'
+    assert opm.nm_to_sys_units(500.0) == 1e-7*500.0
