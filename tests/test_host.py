@@ -188,7 +188,7 @@ def test_seq_reader():
     assert osp.defocus.focus_shift == -0.05
     T.describe_model(sm)                                   # compiles into a surface table
     with pytest.raises(KeyError):
-        seq._medium('NBK7_SCHOTT', {})
+        seq._medium('NLASF99_SCHOTT', {})            # not among the built-in 17
     ref = '/root/reference/src/rayoptics/codev/tests/ag_dblgauss.seq'
     if os.path.exists(ref):
         fx = load_model('dblgauss').seq_model
