@@ -609,3 +609,51 @@ def test_seq_reader_units_and_laurent_glass(tmp_path):
     assert M.OpticalModel.from_dict(opm.to_dict()).dimensions == 'inches'
     opm.dimensions = 'cm'
     assert opm.nm_to_sys_units(500.0) == 1e-7*500.0
+
+
+@pytest.mark.parametrize('name', MODEL_NAMES + PHASE_MODEL_NAMES + ANGULAR_MODEL_NAMES + ['telecentric'])
+def test_table_validation_accepts_every_fixture_without_a_gpu(name):
+    """rt_table_create validates the descriptors BEFORE its first CUDA call, so the validation
+    is testable here: every fixture model (gratings, radial DOEs, holograms, toroids ...) must get past
+    it -- on a machine without a GPU that means the call then fails with RT_ERR_CUDA (-2), never with
+    RT_ERR_UNSUPPORTED (-3) / RT_ERR_INVALID (-1) -- and broken descriptors must be refused by it.
+    (Round 1 shipped a validation that rejected the grating / DOE kinds; only the GPU run showed it.)"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('needs a machine WITHOUT a CUDA device (the call would succeed)')
+    lib = _abi.load_library()
+    descs, n_by_wvl, _ = T.describe_model(load_model(name).seq_model)
+    n_by_wvl = np.ascontiguousarray(n_by_wvl)
+    h = C.c_void_p()
+
+    def create(d):
+        return lib.rt_table_create(d, len(d), n_by_wvl.ctypes.data_as(_abi.c_double_p),
+                                   n_by_wvl.shape[0], 0, C.byref(h))
+    assert create(descs) == -2, lib.rt_last_error()
+    for field, bad, want in (('phase_kind', 9, -3), ('profile', 11, -3), ('mode', 7, -3),
+                             ('n_coefs', _abi.RT_MAX_COEFS + 1, -1), ('n_apertures', 9, -1),
+                             ('n_phase_coefs', _abi.RT_MAX_PHASE_COEFS + 1, -1)):
+        broken = (type(descs[0])*len(descs))(*descs)
+        setattr(broken[1], field, bad)
+        assert create(broken) == want, (field, lib.rt_last_error())
+
+
+@pytest.mark.parametrize('name', ['dblgauss', 'relay_na', 'relay_fno', 'fisheye'])
+def test_grid_validation_accepts_every_pupil_kind_without_a_gpu(name):
+    """rt_grid_create: the argument checks come before the first CUDA call -- spatial, angular and
+    wide-angle grid descriptions get past them (then RT_ERR_CUDA without a device), a bad pupil kind or a
+    paired list with ny != 1 is refused (RT_ERR_INVALID)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('needs a machine WITHOUT a CUDA device')
+    lib = _abi.load_library()
+    spec = E.grid_spec_for_model(load_model(name), 8)
+    assert spec.pupil_kind == {'dblgauss': 0, 'relay_na': 1, 'relay_fno': 2, 'fisheye': 3}[name]
+    h = C.c_void_p()
+    c = spec.c_spec()
+    assert lib.rt_grid_create(C.byref(c), 0, C.byref(h)) == -2, lib.rt_last_error()
+    c.pupil_kind = 4
+    assert lib.rt_grid_create(C.byref(c), 0, C.byref(h)) == -1
+    c = spec.c_spec()
+    c.paired = 1
+    assert lib.rt_grid_create(C.byref(c), 0, C.byref(h)) == -1
