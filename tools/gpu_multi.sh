@@ -1,4 +1,6 @@
 #!/bin/bash
+# EVERY job carries its own short timeout: a hung collective must cost 150 s x N GPUs, not the round's
+# budget (round 2 lost 112 GPU-minutes to one hang under an outer limit of 843 s).
 # usage (under gpurun --gpus NMAX): bash tools/gpu_multi.sh "<model:mode:N[:extra flags]> ..."
 #   e.g. bash tools/gpu_multi.sh "dblgauss:replica:2:--no-e2e zoom52:shard:8:--steps=10"
 set -u
@@ -13,7 +15,7 @@ for jm in $JOBS; do
   extra=${extra:-}
   port=$((port+1))
   out=gpurun_out/r2_multi_${m}_${mode}_n$N
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port \
+  timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port \
       bench.py --gpus $N --model $m --mode $mode --steps 20 --warmup 5 ${extra//,/ } > $out.json 2> $out.err
   python - $out.json <<'PY'
 import json,sys
