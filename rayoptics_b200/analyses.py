@@ -547,6 +547,127 @@ from .trace import (analyses_trace_ray_fan as trace_ray_fan,       # noqa: E402
                     analyses_trace_ray_grid as trace_ray_grid)
 
 
+# --- trace once, refocus often (analyses.py:276-339,545-580,735-791): the first stage keeps the
+#     whole rays of ONE launch (plus the focus-independent part of every OPD), the second stage is
+#     host arithmetic on them -- no retrace when only ``foc`` / the image point changes.
+#     (``eval_*`` above do both stages on the device and copy back 16-24 B per ray; these exist
+#     for callers that hold on to the traced rays, e.g. the reference's focus sliders.)
+def _stage_setup(opt_model, fld, wvl, foc, image_pt_2d, image_delta, kwargs):
+    from . import trace as TR
+    eng = {k: kwargs[k] for k in ('table', 'device', 'tracer') if k in kwargs}
+    ref_sphere, cr_pkg = TR.setup_pupil_coords(opt_model, fld, wvl, foc, image_pt=image_pt_2d,
+                                               image_delta=image_delta, **eng)
+    return ref_sphere, cr_pkg
+
+
+def _refocused(ray_pkg, foc, image_pt):
+    seg = ray_pkg[0][-1]
+    dist = foc/seg[1][2]
+    defocused_pt = seg[0] + dist*seg[1]
+    return defocused_pt - image_pt
+
+
+def _pre_calc(opt_model, fld, wvl, foc, ray_pkg, cr_pkg, ref_sphere):
+    if ray_pkg is None or isinstance(ray_pkg, Exception):
+        return None
+    fod = opt_model['analysis_results']['parax_data'].fod
+    return W.wave_abr_pre_calc(fod, fld, wvl, foc, ray_pkg, cr_pkg, ref_sphere)
+
+
+def trace_fan(opt_model, fld, wvl, foc, xy, image_pt_2d=None, image_delta=None, num_rays=21,
+              output_filter=None, rayerr_filter=None, **kwargs):
+    """Trace a fan of rays and precalculate data for rapid refocus later (analyses.py:276-310):
+    ``(fan, upd_fan)`` = ``[[pupil_x, pupil_y, ray_pkg], ...]`` and the matching
+    ``wave_abr_pre_calc`` tuples."""
+    ref_sphere, cr_pkg = _stage_setup(opt_model, fld, wvl, foc, image_pt_2d, image_delta, kwargs)
+    fld.chief_ray, fld.ref_sphere = cr_pkg, ref_sphere
+    fan_start, fan_stop = np.array([0., 0.]), np.array([0., 0.])
+    fan_start[xy], fan_stop[xy] = -1.0, 1.0
+    fan = trace_ray_fan(opt_model, [fan_start, fan_stop, num_rays], fld, wvl, foc,
+                        output_filter=output_filter, rayerr_filter=rayerr_filter, **kwargs)
+    upd_fan = [_pre_calc(opt_model, fld, wvl, foc, fi[2], cr_pkg, ref_sphere) for fi in fan]
+    return fan, upd_fan
+
+
+def focus_fan(opt_model, fan_pkg, fld, wvl, foc, image_pt_2d=None, image_delta=None, **kwargs):
+    """Refocus the fan of rays and return the transverse aberration and OPD (analyses.py:313-339):
+    ``[((pupil_x, pupil_y), (dx, dy, opd in waves)), ...]``."""
+    fod = opt_model['analysis_results']['parax_data'].fod
+    fan, upd_fan = fan_pkg
+    ref_sphere, cr_pkg = _stage_setup(opt_model, fld, wvl, foc, image_pt_2d, image_delta, kwargs)
+    convert_to_opd = 1/opt_model.nm_to_sys_units(wvl)
+    fan_data = []
+    for (pupil_x, pupil_y, ray_pkg), pre in zip(fan, upd_fan):
+        if ray_pkg is None or isinstance(ray_pkg, Exception):
+            fan_data.append((pupil_x, pupil_y, np.nan))
+            continue
+        t_abr = _refocused(ray_pkg, foc, ref_sphere[0])
+        opd = convert_to_opd*W.wave_abr_calc(fod, fld, wvl, foc, ray_pkg, cr_pkg, pre, ref_sphere)
+        fan_data.append(((pupil_x, pupil_y), (t_abr[0], t_abr[1], opd)))
+    return fan_data
+
+
+def trace_pupil_coords(opt_model, pupil_coords, fld, wvl, foc, image_pt_2d=None, image_delta=None,
+                       **kwargs):
+    """Trace a list of rays and return data needed for rapid refocus (analyses.py:545-558)."""
+    ref_sphere, cr_pkg = _stage_setup(opt_model, fld, wvl, foc, image_pt_2d, image_delta, kwargs)
+    fld.chief_ray, fld.ref_sphere = cr_pkg, ref_sphere
+    kwargs['check_apertures'] = kwargs.get('check_apertures', True)
+    return trace_ray_list(opt_model, pupil_coords, fld, wvl, foc, **kwargs)
+
+
+def focus_pupil_coords(opt_model, ray_list, fld, wvl, foc, image_pt_2d=None, image_delta=None,
+                       **kwargs):
+    """Given pre-traced rays and a reference sphere, return the transverse aberrations
+    (analyses.py:561-580): ``[n, 2]`` (``nan`` entries for rays recorded as None)."""
+    ref_sphere, cr_pkg = _stage_setup(opt_model, fld, wvl, foc, image_pt_2d, image_delta, kwargs)
+    data = []
+    for pupil_x, pupil_y, ray_pkg in ray_list:
+        if ray_pkg is None:
+            data.append(np.nan)
+        else:
+            t_abr = _refocused(ray_pkg, foc, ref_sphere[0])
+            data.append((t_abr[0], t_abr[1]))
+    return np.array(data)
+
+
+def trace_wavefront(opt_model, fld, wvl, foc, image_pt_2d=None, image_delta=None, num_rays=21,
+                    **kwargs):
+    """Trace a grid of rays over the vignetted pupil and pre-calculate data needed for rapid
+    refocus (analyses.py:735-766): ``(grid, upd_grid)``, rows of ``[pupil_x, pupil_y, ray_pkg]``."""
+    ref_sphere, cr_pkg = _stage_setup(opt_model, fld, wvl, foc, image_pt_2d, image_delta, kwargs)
+    fld.chief_ray, fld.ref_sphere = cr_pkg, ref_sphere
+    vig_bbox = fld.vignetting_bbox(opt_model['optical_spec']['pupil'],
+                                   oversize=kwargs.pop('oversize', 1.))
+    kwargs['check_apertures'] = kwargs.get('check_apertures', True)
+    grid = trace_ray_grid(opt_model, [vig_bbox[0], vig_bbox[1], num_rays], fld, wvl, foc, **kwargs)
+    upd_grid = [[_pre_calc(opt_model, fld, wvl, foc, gij[2], cr_pkg, ref_sphere) for gij in row]
+                for row in grid]
+    return grid, upd_grid
+
+
+def focus_wavefront(opt_model, grid_pkg, fld, wvl, foc, image_pt_2d=None, image_delta=None,
+                    value_if_none=np.nan, **kwargs):
+    """Given pre-traced rays and a reference sphere, return the rays' OPD (analyses.py:769-791):
+    ``[num, num, 3]`` of (pupil x, pupil y, OPD in waves)."""
+    fod = opt_model['analysis_results']['parax_data'].fod
+    grid, upd_grid = grid_pkg
+    ref_sphere, cr_pkg = _stage_setup(opt_model, fld, wvl, foc, image_pt_2d, image_delta, kwargs)
+    convert_to_opd = 1/opt_model.nm_to_sys_units(wvl)
+    out = []
+    for row, upd_row in zip(grid, upd_grid):
+        out_row = []
+        for (pupil_x, pupil_y, ray_pkg), pre in zip(row, upd_row):
+            if ray_pkg is None:
+                out_row.append((pupil_x, pupil_y, value_if_none))
+            else:
+                opd = convert_to_opd*W.wave_abr_calc(fod, fld, wvl, foc, ray_pkg, cr_pkg, pre,
+                                                     ref_sphere)
+                out_row.append((pupil_x, pupil_y, opd))
+        out.append(out_row)
+    return np.array(out)
+
+
 # --- raw ray list (analyses.py:458-510) ------------------------------------------------------
 def _cuda_bundle_tracer(opt_model, table, p0, d0, wvl_idx, trace_kwargs):
     res = E.trace_bundle(table, p0, d0, wvl_idx=wvl_idx, full=True,

@@ -247,3 +247,71 @@ def wave_abr_full_calc(fod, fld, wvl, foc, ray_pkg, chief_ray_pkg_, ref_sphere):
     n_img = abs(fod.n_img)
     opd = -n_obj*e1 - ray_op + n_img*ekp + cr_op - n_img*ep
     return opd
+
+
+# --- focus-independent / focus-dependent halves of the OPD (rapid refocus without a retrace):
+#     wave_abr_pre_calc / wave_abr_calc, waveabr.py:226-253 and their finite-pupil (:310-353) and
+#     infinite-reference (:427-488) variants.  The split changes the rounding (the last
+#     subtraction happens on ``pre_opd``), so the two halves are restated, not derived from the
+#     full calculation above.
+def _image_space_frame(ref_sphere, seg):
+    """(p, d) of a ray segment in the coordinates of the image interface when the last gap has
+    a transform (the infinite-reference variants), the segment itself otherwise"""
+    lcl_tfrm_last = ref_sphere[3]
+    if lcl_tfrm_last is None:
+        return seg[0], seg[1]
+    rt, t = lcl_tfrm_last
+    return rt.dot(seg[0] - t), rt.dot(seg[1])
+
+
+def wave_abr_pre_calc(fod, fld, wvl, foc, ray_pkg, chief_ray_pkg_, ref_sphere):
+    """Everything of a ray's OPD that does not depend on the image point: the tuple the
+    reference's ``focus_*`` functions hand back to ``wave_abr_calc``.
+    finite pupil -> ``(pre_opd, p_coord, b4_pt, b4_dir)``;
+    infinite reference -> ``(pre_opd, W0, p_b4, d_b4, p_cr_b4, d_cr_b4)``."""
+    cr, cr_exp_seg = chief_ray_pkg_
+    cr_ray, cr_op, _ = cr
+    ray, ray_op, _ = ray_pkg
+    k = -2
+    n_obj, n_img = abs(fod.n_obj), abs(fod.n_img)
+    e1 = eic_distance((ray[1][0], ray[0][1]), (cr_ray[1][0], cr_ray[0][1]))
+    if is_kinda_big(ref_sphere[2]):
+        p_b4, d_b4 = _image_space_frame(ref_sphere, ray[k])
+        p_cr_b4, d_cr_b4 = _image_space_frame(ref_sphere, cr_ray[k])
+        op_b4 = np.dot(d_b4, -p_b4)
+        op_cr_b4 = np.dot(d_cr_b4, -p_cr_b4)
+        P1, P2 = dist_to_shortest_join((cr_ray[-1][0], cr_ray[-1][1]), (ray[-1][0], ray[-1][1]))
+        rF0 = (P1[0] + P2[0])/2
+        V_B = ray_op + op_b4
+        V_BE = cr_op + op_cr_b4
+        W0 = V_B - V_BE + n_img*np.dot((d_b4 - d_cr_b4), rF0)
+        return -n_obj*e1 - W0, W0, p_b4, d_b4, p_cr_b4, d_cr_b4
+    cr_exp_pt, cr_exp_dist = cr_exp_seg[0], cr_exp_seg[2]
+    ekp = eic_distance((ray[k][0], ray[k][1]), (cr_ray[k][0], cr_ray[k][1]))
+    pre_opd = -n_obj*e1 - ray_op + n_img*ekp + cr_op
+    b4_pt, b4_dir = ray[k][0], ray[k][1]            # transform_after_surface(None, ...)
+    dst = ekp - cr_exp_dist
+    eic_exp_pt = b4_pt - dst*b4_dir
+    return pre_opd, eic_exp_pt - cr_exp_pt, b4_pt, b4_dir
+
+
+def wave_abr_calc(fod, fld, wvl, foc, ray_pkg, chief_ray_pkg_, pre_opd_pkg, ref_sphere):
+    """OPD of a ray from its ``wave_abr_pre_calc`` tuple and the (refocused / shifted)
+    reference sphere.  System units."""
+    from math import sqrt
+    image_pt, ref_dir, ref_sphere_radius, _ = ref_sphere
+    n_img = abs(fod.n_img)
+    if is_kinda_big(ref_sphere_radius):
+        pre_opd, W0, p_b4, d_b4, p_cr_b4, d_cr_b4 = pre_opd_pkg
+        ta = ray_pkg[0][-1][0] - image_pt
+        numer = np.dot(d_cr_b4 - d_b4*np.dot(d_b4, d_cr_b4), ta)
+        denom = 1 + np.dot(d_b4, d_cr_b4)
+        return pre_opd - n_img*numer/denom
+    pre_opd, p_coord, b4_pt, b4_dir = pre_opd_pkg
+    cr_ray = chief_ray_pkg_[0][0]
+    F = ref_dir.dot(b4_dir) - b4_dir.dot(p_coord)/ref_sphere_radius
+    J = p_coord.dot(p_coord)/ref_sphere_radius - 2.0*ref_dir.dot(p_coord)
+    sign_soln = -1 if ref_dir[2]*cr_ray[-1][1][2] < 0 else 1
+    denom = F + sign_soln*sqrt(F**2 + J/ref_sphere_radius)
+    ep = 0 if denom == 0 else J/denom
+    return pre_opd - n_img*ep

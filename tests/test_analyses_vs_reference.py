@@ -106,3 +106,94 @@ def test_functional_forms_equal_the_references():
     got = A.eval_wavefront(b, fb, wvl, 0.0, num_rays=10, backend=be)
     assert np.array_equal(want, got, equal_nan=True)
     assert np.array_equal(fa.ref_sphere[0], fb.ref_sphere[0])
+
+
+def _same_pkg(a, b):
+    ra, rb = a[0], b[0]
+    assert len(ra) == len(rb) and a[1] == b[1] and a[2] == b[2]
+    for sa, sb in zip(ra, rb):
+        assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1])
+        assert sa[2] == sb[2] and np.array_equal(sa[3], sb[3])
+
+
+def _same_tuple(a, b):
+    assert (a is None) == (b is None)
+    if a is not None:
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
+
+
+@pytest.mark.parametrize('name,fi,wvl', [('dblgauss', 2, 656.3), ('telecentric', 1, 587.6),
+                                         ('threemir', 1, None)])
+def test_trace_then_focus_equal_the_references(name, fi, wvl):
+    """trace_fan / focus_fan, trace_pupil_coords / focus_pupil_coords, trace_wavefront /
+    focus_wavefront (the two-stage forms used for rapid refocus): same traced packages, same
+    pre-calculated tuples, same refocused values as rayoptics.raytr.analyses on the hybrid model --
+    finite and infinite (telecentric) reference spheres, with defocus and an image shift."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip('/root/reference not present')
+    from oracle import ref_model
+    from test_trace_drivers import oracle_tracer
+    RT, RA = ref_model.modules()
+    a, b = load_model(name), load_model(name)
+    H = ref_model.HybridModel(a)
+    fa, fb = a.optical_spec.field_of_view.fields[fi], b.optical_spec.field_of_view.fields[fi]
+    wvl = a.seq_model.central_wavelength() if wvl is None else wvl
+    kw = dict(tracer=oracle_tracer)
+
+    def keep():
+        fa.chief_ray = ((None, None, -1.0), None)        # no re-aiming by the reference
+    for xy in (0, 1):
+        keep()
+        fw = RA.trace_fan(H, fa, wvl, 0.0, xy, num_rays=9)
+        fg = A.trace_fan(b, fb, wvl, 0.0, xy, num_rays=9, **kw)
+        assert len(fw[0]) == len(fg[0]) > 3
+        for (pxw, pyw, pw), (pxg, pyg, pg) in zip(fw[0], fg[0]):
+            assert (pxw, pyw) == (pxg, pyg)
+            _same_pkg(pw, pg)
+        for uw, ug in zip(fw[1], fg[1]):
+            _same_tuple(uw, ug)
+        for foc, delta in ((0.0, None), (0.05, None), (-0.02, np.array([0.001, -0.002]))):
+            keep()
+            want = RA.focus_fan(H, fw, fa, wvl, foc, image_delta=delta)
+            got = A.focus_fan(b, fg, fb, wvl, foc, image_delta=delta, **kw)
+            assert len(want) == len(got)
+            for (pw, vw), (pg, vg) in zip(want, got):
+                assert tuple(pw) == tuple(pg) and tuple(vw) == tuple(vg)
+    # list of pupil coordinates
+    pts = [np.array([x, y]) for x in (-0.9, -0.3, 0.0, 0.4, 1.2) for y in (-0.7, 0.0, 0.8)]
+    keep()
+    lw = RA.trace_pupil_coords(H, [p.copy() for p in pts], fa, wvl, 0.0, append_if_none=True)
+    lg = A.trace_pupil_coords(b, [p.copy() for p in pts], fb, wvl, 0.0, append_if_none=True, **kw)
+    assert len(lw) == len(lg) == len(pts)
+    assert [r[2] is None for r in lw] == [r[2] is None for r in lg]
+    ok_w = [r for r in lw if r[2] is not None]
+    ok_g = [r for r in lg if r[2] is not None]
+    for foc in (0.0, 0.03):
+        keep()
+        want = RA.focus_pupil_coords(H, ok_w, fa, wvl, foc)
+        got = A.focus_pupil_coords(b, ok_g, fb, wvl, foc, **kw)
+        assert want.shape == got.shape and np.array_equal(want, got)
+    # wavefront grid
+    keep()
+    gw = RA.trace_wavefront(H, fa, wvl, 0.0, num_rays=8)
+    gg = A.trace_wavefront(b, fb, wvl, 0.0, num_rays=8, **kw)
+    for row_w, row_g, uw, ug in zip(gw[0], gg[0], gw[1], gg[1]):
+        assert len(row_w) == len(row_g) == 8
+        for (xw, yw, pw), (xg, yg, pg), tw, tg in zip(row_w, row_g, uw, ug):
+            assert (xw, yw) == (xg, yg) and (pw is None) == (pg is None)
+            _same_tuple(tw, tg)
+    for foc, delta in ((0.0, None), (0.04, np.array([0.0005, 0.001]))):
+        keep()
+        want = RA.focus_wavefront(H, gw, fa, wvl, foc, image_delta=delta)
+        got = A.focus_wavefront(b, gg, fb, wvl, foc, image_delta=delta, **kw)
+        assert want.shape == got.shape == (8, 8, 3)
+        assert np.array_equal(want, got, equal_nan=True) and np.isfinite(got[:, :, 2]).sum() > 8
+    # the one-stage device forms agree with the two-stage host forms to rounding
+    be = OracleBackend(b)
+    one = A.eval_wavefront(b, fb, wvl, 0.04, image_delta=np.array([0.0005, 0.001]), num_rays=8, backend=be)
+    m = np.isfinite(one[:, :, 2])
+    assert np.array_equal(m, np.isfinite(got[:, :, 2]))
+    assert np.abs(one[:, :, 2][m] - got[:, :, 2][m]).max() < 1e-6
