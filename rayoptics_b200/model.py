@@ -323,6 +323,17 @@ class Surface:
         self.decenter = None
         self.delta_n = 0.0
 
+    delta_n = 0.0       # index step across the interface at the reference wavelength, signed
+                        # by the propagation direction (set by SequentialModel.update_model)
+
+    @property
+    def optical_power(self):            # elem/surface.py:124-130
+        return self.delta_n*self.profile.cv
+
+    @optical_power.setter
+    def optical_power(self, pwr):
+        self.profile.cv = pwr/self.delta_n if self.delta_n != 0.0 else 0.0
+
     def set_max_aperture(self, max_ap):
         self.max_aperture = max_ap
 
@@ -603,6 +614,15 @@ class SequentialModel:
                 z_after = -z_before if ifc.interact_mode == 'reflect' else z_before
                 self.z_dir.append(z_after)
                 z_before = z_after
+        # seq/sequential.py:628-657: indices stay unsigned, the sign of the propagation direction
+        # goes into delta_n (used by the Coddington trace, trace.trace_coddington_fan)
+        ref = self.index_for_wavelength(self.central_wavelength())
+        n_before = self.rndx[0][ref]
+        for i, ifc in enumerate(self.ifcs[:len(self.gaps)]):
+            n_after = self.rndx[i][ref] if self.z_dir[i] > 0 else -self.rndx[i][ref]
+            if not isinstance(ifc, ThinLens):
+                ifc.delta_n = n_after - n_before
+            n_before = n_after
         for ifc in self.ifcs:
             ifc.update()
         if self._tfrms_given is not None:
@@ -821,7 +841,9 @@ class Field:
     """raytr/opticalspec.py:1197 -- field point + vignetting + aim info."""
 
     def __init__(self, x=0.0, y=0.0, wt=1.0, vux=0.0, vuy=0.0, vlx=0.0, vly=0.0,
-                 aim_pt=None):
+                 aim_pt=None, fov=None):
+        if fov is not None:
+            self.fov = fov
         self.x, self.y, self.wt = x, y, wt
         self.vux, self.vuy, self.vlx, self.vly = vux, vuy, vlx, vly
         # [x, y] aim point on the paraxial entrance pupil, or -- wide-angle fields -- the scalar
@@ -869,9 +891,17 @@ class Field:
     def xv(self):
         return self.x*self.fov.value if (self.fov is not None and self.fov.is_relative) else self.x
 
+    @xv.setter
+    def xv(self, x_val):            # opticalspec.py:1188-1191: unscaled value in, stored per is_relative
+        self.x = x_val/self.fov.value if (self.fov is not None and self.fov.is_relative) else x_val
+
     @property
     def yv(self):
         return self.y*self.fov.value if (self.fov is not None and self.fov.is_relative) else self.y
+
+    @yv.setter
+    def yv(self, y_val):
+        self.y = y_val/self.fov.value if (self.fov is not None and self.fov.is_relative) else y_val
 
     def vignetting_bbox(self, pupil_spec, oversize=1.):
         """bbox of the vignetted pupil ray extents (opticalspec.py:1326-1333)"""

@@ -80,6 +80,32 @@ class FieldSpec:
         for f in self.fields:
             f.fov = self
 
+    def max_field(self):
+        """(magnitude of the maximum field, index of that field), opticalspec.py:1093-1109"""
+        max_fld, max_fld_sqrd = 0, -1.0
+        for i, f in enumerate(self.fields):
+            fld_sqrd = f.x*f.x + f.y*f.y
+            if fld_sqrd > max_fld_sqrd:
+                max_fld_sqrd, max_fld = fld_sqrd, i
+        max_fld_value = math.sqrt(max_fld_sqrd)
+        if self.is_relative:
+            max_fld_value *= self.value
+        return max_fld_value, max_fld
+
+    @property
+    def index_labels(self):
+        """'axis', ' 0.70y', ..., 'edge' (opticalspec.py:907-932, index_label_type 'auto')"""
+        field_norm = 1 if (self.is_relative or self.value == 0) else 1.0/self.value
+        labels = []
+        for f in self.fields:
+            fldx = '{:5.2f}x'.format(field_norm*f.x) if f.x != 0.0 else ''
+            fldy = '{:5.2f}y'.format(field_norm*f.y) if f.y != 0.0 else ''
+            labels.append(fldx + fldy)
+        labels[0] = 'axis'
+        if len(labels) > 1:
+            labels[-1] = 'edge'
+        return labels
+
     def max_field_value(self):
         if self.is_relative:
             return self.value

@@ -333,3 +333,222 @@ def analyses_trace_ray_grid(opt_model, grid_rng, fld, wvl, foc, append_if_none=T
                 row.append([px, py, None])
         grid.append(row)
     return grid
+
+
+# --- the rest of rayoptics.raytr.trace's call surface around the path ---------------------------
+def _engine(kwargs):
+    return {k: kwargs.pop(k) for k in ('table', 'device', 'tracer') if k in kwargs}
+
+
+def ray_pkg(ray_pkg):
+    """a pandas Series holding a ray package (trace.py:31-33)"""
+    import pandas as pd
+    return pd.Series(ray_pkg, index=['ray', 'op', 'wvl'])
+
+
+def ray_df(ray):
+    """a pandas DataFrame holding the segments of a ray (trace.py:36-41)"""
+    import pandas as pd
+    r = pd.DataFrame(ray, columns=['inc_pt', 'after_dir', 'after_dst', 'normal'])
+    r.index.names = ['intrfc']
+    return r
+
+
+def list_ray(ray_obj, tfrms=None, start=0):
+    """pretty print a ray in local or (with ``tfrms``) global coordinates (trace.py:44-79).
+    ``ray_obj``: the return of ``trace_ray`` (package, error), a ray package or a ray."""
+    ray_err = None
+    if isinstance(ray_obj, tuple):
+        if len(ray_obj) == 2:
+            ray_obj, ray_err = ray_obj
+        ray = ray_obj[0]
+    else:
+        ray = ray_obj
+    print('            X            Y            Z           L            M            N'
+          '               Len')
+    fmt = '{:3d}: {:12.5f} {:12.5f} {:12.5g} {:12.6f} {:12.6f} {:12.6f} {:12.5g}'
+    for i, seg in enumerate(ray[start:], start=start):
+        p, d = seg[0], seg[1]
+        if tfrms is not None:
+            rot, trns = tfrms[i]
+            p, d = rot.dot(p) + trns, rot.dot(d)
+        print(fmt.format(i, p[0], p[1], p[2], d[0], d[1], d[2], seg[2]))
+    if ray_err is not None:
+        print(f'ray failure: {type(ray_err).__name__}')
+
+
+def list_in_out_dir(path, ray):
+    """list the incident and exiting direction cosines at every interface (trace.py:82-100)"""
+    lcl_tfrms = [seg[2] for seg in path]
+    row = '{:10.6f} {:10.6f} {:10.6f}'
+    print('                  in_dir              |              out_dir')
+    before_dir = ray[0][1]
+    print(f'{0:2d}:                                   |' + row.format(*before_dir))
+    i = 0
+    for i, (seg, tfrm) in enumerate(zip(ray[1:], lcl_tfrms), start=1):
+        b4_dir = tfrm[0].dot(before_dir)
+        print(f'{i:2d}: ' + row.format(*b4_dir) + '  |' + row.format(*seg[1]))
+        before_dir = seg[1]
+    b4_dir = lcl_tfrms[-1][0].dot(before_dir)
+    print(f'{i+1:2d}: ' + row.format(*b4_dir) + '  |')
+
+
+def aim_chief_ray(opt_model, fld, wvl=None, trace_fn=None):
+    """aim the chief ray at the centre of the stop surface (trace.py:627-640): the aim point on
+    the paraxial entrance pupil, or -- wide-angle specifications -- the z position of the real
+    entrance pupil (raytr/wideangle.py)."""
+    from . import raytrace as RT, vigcalc, wideangle
+    sm = opt_model.seq_model
+    wvl = sm.central_wavelength() if wvl is None else wvl
+    if opt_model.optical_spec.field_of_view.is_wide_angle:
+        z_enp, _ = wideangle.find_real_enp(opt_model, sm.stop_surface, fld, wvl, trace_fn)
+        return float(z_enp)
+    return vigcalc.aim_chief_ray(opt_model, fld, wvl, RT.trace if trace_fn is None else trace_fn)
+
+
+def get_chief_ray_pkg(opt_model, fld, wvl, foc, trace_fn=None, **engine):
+    """the chief ray package of ``fld``, computed (and aimed) when necessary (trace.py:660-687)"""
+    if fld.chief_ray is None:
+        fld.aim_info = aim_chief_ray(opt_model, fld, wvl=wvl, trace_fn=trace_fn)
+        return trace_chief_ray(opt_model, fld, wvl, foc, **engine)
+    if fld.chief_ray[0][2] != wvl:
+        return trace_chief_ray(opt_model, fld, wvl, foc, **engine)
+    return fld.chief_ray
+
+
+def trace_with_opd(opt_model, pupil, fld, wvl, foc, **kwargs):
+    """``(ray, ray_opl, wvl, opd)`` of one pupil point (trace.py:418-438)"""
+    engine = {k: kwargs[k] for k in ('table', 'device', 'tracer') if k in kwargs}
+    chief = get_chief_ray_pkg(opt_model, fld, wvl, foc, trace_fn=kwargs.pop('trace_fn', None),
+                              **engine)
+    ref_sphere = W.calculate_reference_sphere(opt_model, fld, wvl, foc, chief,
+                                              image_pt_2d=kwargs.pop('image_pt', None),
+                                              image_delta=kwargs.pop('image_delta', None))
+    pkg, err = trace_ray(opt_model, pupil, fld, wvl, **kwargs)
+    fld.chief_ray, fld.ref_sphere = chief, ref_sphere
+    fod = opt_model['analysis_results']['parax_data'].fod
+    opd = W.wave_abr_full_calc(fod, fld, wvl, foc, pkg, chief, ref_sphere)
+    ray, ray_op, wvl = pkg
+    return ray, ray_op, wvl, opd
+
+
+def trace_ray_list_at_field(opt_model, ray_list, fld, wvl, foc, **kwargs):
+    """a ray DataFrame per pupil point of ``ray_list`` at ``fld`` (trace.py:478-486); one launch"""
+    kwargs.setdefault('use_named_tuples', True)
+    results = trace_pupil_rays(opt_model, list(ray_list), fld, wvl, kwargs.pop('output_filter', None),
+                               kwargs.pop('rayerr_filter', 'full'), **kwargs)
+    return [ray_df(r.pkg[0]) for r in results]
+
+
+def trace_field(opt_model, fld, wvl, foc, **engine):
+    """DataFrame of the boundary rays of ``fld`` (trace.py:489-496)"""
+    import pandas as pd
+    pupil = opt_model.optical_spec.pupil
+    rdf_list = trace_ray_list_at_field(opt_model, pupil.pupil_rays, fld, wvl, foc, **engine)
+    return pd.concat(rdf_list, keys=pupil.ray_labels, names=['pupil'])
+
+
+def trace_all_fields(opt_model, **engine):
+    """DataFrame of the boundary rays of all fields (trace.py:499-510)"""
+    import pandas as pd
+    osp = opt_model.optical_spec
+    _, wvl, foc = osp.lookup_fld_wvl_focus(0)
+    fov = osp.field_of_view
+    fset = [trace_field(opt_model, f, wvl, foc, **engine) for f in fov.fields]
+    return pd.concat(fset, keys=fov.index_labels, names=['field'])
+
+
+def refocus(opt_model, **engine):
+    """focus shift that brings the axial marginal ray to the axis (trace.py:690-705)"""
+    osp = opt_model['optical_spec']
+    fld = osp['fov'].fields[0]
+    wvl = osp['wvls'].central_wvl
+    res = trace_safe(opt_model, [0., 1.], fld, wvl, output_filter=None, rayerr_filter='full',
+                     use_named_tuples=True, **engine)
+    ray = res.pkg[0]
+    return -ray[-1].p[1]/(ray[-2].d[1]/ray[-2].d[2])
+
+
+def intersect_2_lines(P1, V1, P2, V2):
+    """distance from P1 along V1 to the intersection of two non-parallel lines (trace.py:779-789)"""
+    Vx = np.cross(V1, V2)
+    return np.dot(np.cross(P2 - P1, V1), Vx)/np.dot(Vx, Vx)
+
+
+def trace_astigmatism(opt_model, fld, wvl, foc, dx=0.001, dy=0.001, **engine):
+    """sagittal and tangential focus shifts at ``fld`` from close rays about the chief ray
+    (trace.py:826-863); the five rays go through one launch"""
+    pupils = [[0., 0.], [dx, 0.], [0., dy], [-dx, 0.], [0., -dy]]
+    r = [x.pkg for x in trace_pupil_rays(opt_model, pupils, fld, wvl, None, 'full',
+                                         use_named_tuples=True, **engine)]
+    s = intersect_2_lines(r[1].ray[-1].p, r[1].ray[-1].d, r[3].ray[-1].p, r[3].ray[-1].d)
+    s_foc = s*r[1].ray[-1].d[2]
+    t = intersect_2_lines(r[2].ray[-1].p, r[2].ray[-1].d, r[4].ray[-1].p, r[4].ray[-1].d)
+    t_foc = t*r[2].ray[-1].d[2]
+    if foc is not None:
+        s_foc -= foc
+        t_foc -= foc
+    return s_foc, t_foc
+
+
+def trace_astigmatism_curve(opt_model, num_points=21, **kwargs):
+    """astigmatism over a fan of fields from the axis to the maximum field (trace.py:792-823):
+    ``(field values, sagittal focus shifts, tangential focus shifts)``"""
+    from .model import Field
+    engine = _engine(kwargs)
+    osp = opt_model['optical_spec']
+    fov = osp['fov']
+    _, wvl, foc = osp.lookup_fld_wvl_focus(0)
+    fld = Field(fov=fov)
+    field_data, s_data, t_data = [], [], []
+    for f in np.linspace(0., fov.max_field()[0], num=num_points):
+        fld.yv = f
+        ref_sphere, cr_pkg = setup_pupil_coords(opt_model, fld, wvl, foc, **engine)
+        fld.chief_ray, fld.ref_sphere = cr_pkg, ref_sphere
+        s_foc, t_foc = trace_astigmatism(opt_model, fld, wvl, foc, **kwargs, **engine)
+        s_data.append(s_foc)
+        t_data.append(t_foc)
+        field_data.append(f)
+    return field_data, s_data, t_data
+
+
+def trace_coddington_fan(opt_model, ray_pkg, foc=None):
+    """sagittal / tangential focus along a traced ray by Coddington's equations
+    (trace.py:715-776; spherical surfaces only).  Host arithmetic on one ray package."""
+    import math
+    sm = opt_model.seq_model
+    ray = ray_pkg[0]
+    wl = sm.index_for_wavelength(ray_pkg[2])
+    n_ifc = len(ray)
+    rind = [sm.rndx[i][wl] if i < len(sm.rndx) else None for i in range(n_ifc)]
+    before_rind = sm.rndx[0][wl]
+    s_before = t_before = s_prime = t_prime = None
+    for i, (pt, after_dir, after_dst, normal) in enumerate(ray):
+        after_rind = rind[i] if rind[i] is not None else before_rind
+        if i == 0:
+            s_before = t_before = -after_dst
+        else:
+            cosI_prime = np.dot(after_dir, normal)/np.linalg.norm(normal)
+            sinI_prime = math.sqrt(1.0 - cosI_prime**2)
+            sinI = after_rind*sinI_prime/before_rind
+            cosI = math.sqrt(1.0 - sinI**2)
+            obl_power = sm.ifcs[i].optical_power
+            if obl_power != 0.0:
+                obl_power *= ((after_rind*cosI_prime - before_rind*cosI)/(after_rind - before_rind))
+            s_prime = after_rind/(before_rind/s_before + obl_power)
+            s_before = s_prime - after_dst
+            t_prime = after_rind*cosI_prime**2/(before_rind*cosI**2/t_before + obl_power)
+            t_before = t_prime - after_dst
+        before_rind = after_rind
+    s_dfoc = s_prime*after_dir[2] + pt[2]
+    t_dfoc = t_prime*after_dir[2] + pt[2]
+    if foc is not None:
+        s_dfoc -= foc
+        t_dfoc -= foc
+    return s_dfoc, t_dfoc
+
+
+def trace_astigmatism_coddington_fan(opt_model, fld, wvl, foc, **engine):
+    """astigmatism by a Coddington trace along the chief ray of ``fld`` (trace.py:708-712)"""
+    cr_pkg, _ = trace_ray(opt_model, [0., 0.], fld, wvl, **engine)
+    return trace_coddington_fan(opt_model, cr_pkg, foc=foc)

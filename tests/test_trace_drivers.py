@@ -585,3 +585,107 @@ def test_find_real_enp_is_the_references():
                 z_own, ray = W.find_real_enp(b, b.seq_model.stop_surface, fb, wvl, trace_fn=tf)
             assert z_own == z_ref
             assert abs(z_ref - s) < 1e-9
+
+
+def _hybrid_with_powers(opm):
+    """the reference's analysis layer on the mirror model, with what its Coddington trace reads
+    from a SequentialModel: ``rndx`` and the interfaces' ``delta_n`` (seq/sequential.py:628-657,
+    recomputed here from the index table, not taken from model.Surface.delta_n)"""
+    from oracle import ref_model
+    H = ref_model.HybridModel(opm)
+    sm = opm.seq_model
+    H.seq_model.rndx = sm.rndx
+    ref = sm.index_for_wavelength(sm.central_wavelength())
+    n_before = sm.rndx[0][ref]
+    for i, ifc in enumerate(H.seq_model.ifcs[:len(sm.gaps)]):
+        n_after = sm.rndx[i][ref]*(1 if sm.z_dir[i] > 0 else -1)
+        ifc.delta_n = n_after - n_before
+        n_before = n_after
+        if hasattr(sm.ifcs[i], 'profile'):
+            assert sm.ifcs[i].delta_n == ifc.delta_n
+            assert sm.ifcs[i].optical_power == ifc.optical_power
+    return H
+
+
+@needs_ref
+@pytest.mark.parametrize('name', ['dblgauss', 'triplet', 'rc'])
+def test_trace_module_call_surface_equals_the_references(name, capsys):
+    """refocus, trace_with_opd, trace_astigmatism(_curve), the Coddington trace, the DataFrame
+    listings and the printers of rayoptics.raytr.trace, run by the reference on the hybrid model
+    and here on the batched drivers (oracle in the tracer seam): identical numbers / text."""
+    from oracle import ref_model
+    RT, RA = ref_model.modules()
+    a, b = load_model(name), load_model(name)
+    H = _hybrid_with_powers(a)
+    kw = dict(tracer=oracle_tracer)
+    fa, fb = a.optical_spec.field_of_view.fields[-1], b.optical_spec.field_of_view.fields[-1]
+    wvl = a.seq_model.central_wavelength()
+
+    assert RT.refocus(H) == TR.refocus(b, **kw)
+
+    for foc in (0.0, 0.02):
+        want = RT.trace_astigmatism(H, fa, wvl, foc)
+        got = TR.trace_astigmatism(b, fb, wvl, foc, **kw)
+        assert want == got and np.isfinite(got).all()
+    # trace_astigmatism_curve: the reference's loop body (trace.py:812-822) on the reference's
+    # functions (its own Field class needs opticalglass to import, the mirror's Field stands in)
+    from rayoptics_b200.model import Field
+    fov = a.optical_spec.field_of_view
+    fld = Field(fov=fov)
+    sw, tw = [], []
+    for f in np.linspace(0., fov.max_field()[0], num=5):
+        fld.yv = f
+        ref_sphere, cr_pkg = RT.setup_pupil_coords(H, fld, wvl, 0.0)
+        fld.chief_ray, fld.ref_sphere = cr_pkg, ref_sphere
+        s_foc, t_foc = RT.trace_astigmatism(H, fld, wvl, 0.0)
+        sw.append(s_foc)
+        tw.append(t_foc)
+    fg, sg, tg = TR.trace_astigmatism_curve(b, num_points=5, **kw)
+    assert list(fg) == list(np.linspace(0., fov.max_field()[0], num=5)) and sw == sg and tw == tg
+    assert fov.max_field()[0] > 0 and abs(sg[0] - tg[0]) < 1e-9 < abs(sg[-1] - tg[-1])
+
+    # Coddington trace along the chief ray of the outer field
+    pw = RT.trace_ray(H, [0., 0.], fa, wvl)[0]
+    pg = TR.trace_ray(b, [0., 0.], fb, wvl, **kw)[0]
+    assert_pkg_equals(pg, {'n_seg': len(pw.ray), 'op': pw.op,
+                           'ray': np.array([np.concatenate([s.p, s.d, [s.dst], s.nrml]) for s in pw.ray])})
+    if name != 'rc':                                    # spherical surfaces only
+        for foc in (None, 0.01):
+            want = RT.trace_coddington_fan(H, pw, foc=foc)
+            got = TR.trace_coddington_fan(b, pg, foc=foc)
+            assert want == got and np.isfinite(got).all()
+        assert (RT.trace_astigmatism_coddington_fan(H, fa, wvl, 0.0)
+                == TR.trace_astigmatism_coddington_fan(b, fb, wvl, 0.0, **kw))
+
+    # OPD of single rays (chief ray present on the field: no re-aiming on either side)
+    for pupil in ([0., 0.6], [0.4, -0.3]):
+        fa.chief_ray = ((None, None, -1.0), None)
+        fb.chief_ray = ((None, None, -1.0), None)
+        rw = RT.trace_with_opd(H, list(pupil), fa, wvl, 0.01)
+        rg = TR.trace_with_opd(b, list(pupil), fb, wvl, 0.01, **kw)
+        assert rw[1] == rg[1] and rw[2] == rg[2] and rw[3] == rg[3]
+        assert np.array_equal(rw[0][-1][0], rg[0][-1][0])
+
+    # DataFrames
+    dw, dg = RT.trace_all_fields(H), TR.trace_all_fields(b, **kw)
+    assert list(dw.index) == list(dg.index) and list(dw.columns) == list(dg.columns)
+    for col in dw.columns:
+        for x, y in zip(dw[col], dg[col]):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
+    assert TR.ray_pkg(pg).index.tolist() == RT.ray_pkg(pw).index.tolist()
+
+    # printers
+    capsys.readouterr()
+    RT.list_ray(pw)
+    RT.list_ray((pw, None), tfrms=[(np.identity(3), np.array([0., 0., float(k)])) for k in range(len(pw.ray))], start=2)
+    RT.list_in_out_dir(list(H.seq_model.path(wvl)), pw.ray)
+    want = capsys.readouterr().out
+    TR.list_ray(pg)
+    TR.list_ray((pg, None), tfrms=[(np.identity(3), np.array([0., 0., float(k)])) for k in range(len(pg.ray))], start=2)
+    TR.list_in_out_dir(list(b.seq_model.path(wvl)), pg.ray)
+    got = capsys.readouterr().out
+    assert want == got and len(got.splitlines()) > 2*len(pg.ray)
+
+    P1, V1 = np.array([0., 1., 0.]), np.array([0., -0.1, 1.])/np.linalg.norm([0., -0.1, 1.])
+    P2, V2 = np.array([0., -1., 0.]), np.array([0., 0.1, 1.])/np.linalg.norm([0., 0.1, 1.])
+    assert RT.intersect_2_lines(P1, V1, P2, V2) == TR.intersect_2_lines(P1, V1, P2, V2)
