@@ -141,26 +141,39 @@ def trace_boundary_rays(opt_model, trace_fn, wvl=None):
     return rayset
 
 
-def set_clear_apertures(opt_model, trace_fn, wvl=None):
+def max_aperture_at_surf(rayset, i):
+    """largest radial height at interface ``i`` over a set of boundary rays (per field, per pupil
+    ray; ray packages or plain rays); None when a ray ended before ``i`` (vigcalc.py:31-42)"""
+    max_ap = -1.0e+10
+    for f in rayset:
+        for p in f:
+            ray = p.ray if hasattr(p, 'ray') else p
+            if len(ray) > i:
+                pt = ray[i][0]
+                ap = math.sqrt(pt[0]**2 + pt[1]**2)
+                if ap > max_ap:
+                    max_ap = ap
+            else:
+                return None
+    return max_ap
+
+
+def _include_list(num_surfs, avoid_list, include_list):
+    """vigcalc.py:60-66: everything, the given list, or everything but ``avoid_list``"""
+    if avoid_list is not None:
+        return [i for i in range(num_surfs) if i not in avoid_list]
+    return range(num_surfs) if include_list is None else include_list
+
+
+def set_clear_apertures(opt_model, trace_fn, wvl=None, avoid_list=None, include_list=None):
+    """From the existing fields and vignetting, calculate clear apertures (vigcalc.py:45-80).
+    The stop surface takes its aperture from the boundary rays of the first field."""
     sm = opt_model.seq_model
+    include_list = _include_list(sm.get_num_surfaces(), avoid_list, include_list)
     rayset = trace_boundary_rays(opt_model, trace_fn, wvl)
-    n = sm.get_num_surfaces()
     stop = sm.stop_surface
-
-    def max_ap(fields, i):
-        m = None
-        for rim in fields:
-            for ray in rim:
-                if len(ray) > i:
-                    p = ray[i][0]
-                    ap = math.sqrt(p[0]*p[0] + p[1]*p[1])
-                    m = ap if m is None or ap > m else m
-                else:
-                    return None
-        return m
-
-    for i in range(n):
-        m = max_ap([rayset[0]], i) if i == stop else max_ap(rayset, i)
+    for i in include_list:
+        m = max_aperture_at_surf([rayset[0]] if i == stop else rayset, i)
         if m is not None:
             sm.ifcs[i].set_max_aperture(m)
 
@@ -270,7 +283,8 @@ def aim_all_fields_batched(opt_model, bundle_fn=None, wvl=None, tol=1e-13, max_i
     return [f.aim_info for f in fields]
 
 
-def set_clear_apertures_batched(opt_model, bundle_fn=None, wvl=None):
+def set_clear_apertures_batched(opt_model, bundle_fn=None, wvl=None, avoid_list=None,
+                                include_list=None):
     """``set_clear_apertures`` (raytr/vigcalc.py:45-80) with the 5 boundary rays of all
     fields in one bundle."""
     osp, sm = opt_model.optical_spec, opt_model.seq_model
@@ -288,7 +302,7 @@ def set_clear_apertures_batched(opt_model, bundle_fn=None, wvl=None):
     per = len(osp.pupil.pupil_rays)
     r = np.sqrt(full[:, 0, :]*full[:, 0, :] + full[:, 1, :]*full[:, 1, :])      # [n_ifc, n]
     stop = sm.stop_surface
-    for i in range(sm.get_num_surfaces()):
+    for i in _include_list(sm.get_num_surfaces(), avoid_list, include_list):
         sel = slice(0, per) if i == stop else slice(None)
         if (n_seg[sel] <= i).any():           # a ray failed before this interface: keep the value
             continue
@@ -403,6 +417,116 @@ def set_vig(opm, **kwargs):
     wvl = osp.spectral_region.central_wvl
     for fld in osp.field_of_view.fields:
         calc_vignetting_for_field(opm, fld, wvl, **kwargs)
+
+
+def calc_vignetted_ray_by_bisection(opm, xy, start_dir, fld, wvl, max_iter_count=10, **engine):
+    """The limiting aperture along ``start_dir`` by halving steps in the pupil
+    (vigcalc.py:347-390): ``(vig, clip_indx, ray_pkg)``."""
+    from . import trace as TR
+    from .raytrace import TraceError
+    rel_p1 = np.array(start_dir, dtype=float)
+    clip_indx, ray_pkg, step_size = None, None, 1.0
+    for _ in range(max_iter_count):
+        step_size /= 2
+        try:
+            ray_pkg = TR.trace_base(opm, rel_p1, fld, wvl, apply_vignetting=False,
+                                    check_apertures=True, pt_inside_fuzz=1e-4, **engine)
+        except TraceError as ray_error:
+            ray_pkg = TR.RayPkg(*ray_error.ray_pkg)
+            clip_indx = ray_error.surf
+            rel_p1 = -step_size*np.array(start_dir) + rel_p1
+        else:
+            rel_p1 = step_size*np.array(start_dir) + rel_p1
+    vig = 1.0 - (rel_p1[xy]/start_dir[xy])
+    return vig, clip_indx, ray_pkg
+
+
+def _surface_od(ifc):
+    """Surface.surface_od (elem/surface.py:181-196) without edge apertures"""
+    cas = getattr(ifc, 'clear_apertures', None) or []
+    od = 0
+    for ca in cas:
+        ap = (ca.radius if type(ca).__name__ == 'Circular'
+              else max(ca.x_half_width, ca.y_half_width))
+        od = max(od, ap)
+    return od if cas else ifc.max_aperture
+
+
+def set_stop_aperture(opm, trace_fn=None, **engine):
+    """Set the aperture of the stop surface to satisfy the pupil specification, then recompute
+    the vignetting (vigcalc.py:104-115)."""
+    from . import raytrace as RT
+    sm = opm.seq_model
+    opm.optical_spec.field_of_view.fields[0].clear_vignetting()      # fov['axis']
+    set_clear_apertures(opm, RT.trace if trace_fn is None else trace_fn,
+                        include_list=[sm.stop_surface])
+    set_vig(opm, **engine)
+
+
+def set_pupil(opm, use_parax=False, **engine):
+    """From the existing stop size, calculate the pupil specification and the vignetting
+    (vigcalc.py:118-224): the axial upper marginal ray is iterated through the edge of the stop;
+    its object / image space segment gives the new EPD, NA or f/#."""
+    from . import trace as TR
+    from .firstorder import HT, SLP
+    from .raytrace import TraceRayBlockedError
+    sm, osp = opm.seq_model, opm.optical_spec
+    if sm.stop_surface is None:
+        print('floating stop surface')
+        return
+    idx_stop = sm.stop_surface
+    fld_0, cwl, foc = osp.lookup_fld_wvl_focus(0)
+    stop_radius = _surface_od(sm.ifcs[idx_stop])
+    start_coords = iterate_pupil_ray(opm, idx_stop, 1, 1.0, stop_radius, fld_0, cwl, **engine)
+    ray_pkg, ray_err = TR.trace_safe(opm, start_coords, fld_0, cwl, None, 'full',
+                                     apply_vignetting=False, **engine)
+    pupil = osp.pupil
+    obj_img_key, pupil_spec = pupil.key
+    pupil_value_orig = pupil.value
+    fod = osp.fod
+    ax_ray = fod.ax_ray
+    wi = sm.index_for_wavelength(sm.central_wavelength())
+    n0, nk = sm.rndx[0][wi], sm.rndx[-1][wi]              # central_rndx(0), central_rndx(-1)
+    rs0, rs1, rsm2 = ray_pkg[0][0], ray_pkg[0][1], ray_pkg[0][-2]
+    if use_parax:
+        scale_ratio = stop_radius/ax_ray[idx_stop][HT]
+        if obj_img_key == 'object':
+            if pupil_spec == 'epd':
+                pupil.value = scale_ratio*(2*fod.enp_radius)
+            elif pupil_spec == 'NA':
+                pupil.value = n0*rs0[1][1]
+            elif pupil_spec == 'f/#':
+                pupil.value = 1/(2*(scale_ratio*ax_ray[0][SLP]))
+        elif obj_img_key == 'image':
+            if pupil_spec == 'epd':
+                pupil.value = scale_ratio*(2*fod.exp_radius)
+            elif pupil_spec == 'NA':
+                pupil.value = -nk*rsm2[1][1]
+            elif pupil_spec == 'f/#':
+                pupil.value = -1/(2*(scale_ratio*ax_ray[-1][SLP]))
+    else:                                                   # the real marginal ray
+        scale_ratio = rs1[0][1]/ax_ray[1][HT]
+        if obj_img_key == 'object':
+            if pupil_spec == 'epd':
+                pupil.value *= scale_ratio
+            elif pupil_spec == 'NA':
+                pupil.value = n0*rs0[1][1]
+            elif pupil_spec == 'f/#':
+                pupil.value = 1/(2*(rs0[1][1]/rs0[1][2]))
+        elif obj_img_key == 'image':
+            if pupil_spec == 'epd':
+                pupil.value = 2*rsm2[0][1]
+            elif pupil_spec == 'NA':
+                pupil.value = -nk*rsm2[1][1]
+            elif pupil_spec == 'f/#':
+                pupil.value = -1/(2*(scale_ratio*ax_ray[-1][SLP]))
+    clipped = TR.trace_safe(opm, start_coords, fld_0, cwl, None, 'full', apply_vignetting=False,
+                            check_apertures=True, **engine)
+    if isinstance(clipped.err, TraceRayBlockedError):
+        print(f'Axial bundle limited by surface {clipped.err.surf}, not stop surface.')
+    if pupil_value_orig != pupil.value:
+        opm.update_model()
+        set_vig(opm, **engine)
 
 
 # --- the same searches for ALL fields and pupil directions in lock step ----------------------

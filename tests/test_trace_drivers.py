@@ -689,3 +689,108 @@ def test_trace_module_call_surface_equals_the_references(name, capsys):
     P1, V1 = np.array([0., 1., 0.]), np.array([0., -0.1, 1.])/np.linalg.norm([0., -0.1, 1.])
     P2, V2 = np.array([0., -1., 0.]), np.array([0., 0.1, 1.])/np.linalg.norm([0., 0.1, 1.])
     assert RT.intersect_2_lines(P1, V1, P2, V2) == TR.intersect_2_lines(P1, V1, P2, V2)
+
+
+@needs_ref
+@pytest.mark.parametrize('name,use_parax', [('dblgauss', False), ('dblgauss', True), ('triplet', False),
+                                            ('relay_fno', False)])
+def test_set_pupil_and_bisection_equal_the_references(name, use_parax, capsys):
+    """vigcalc.set_pupil (stop size -> pupil specification + vignetting), set_stop_aperture and
+    calc_vignetted_ray_by_bisection against rayoptics.raytr.vigcalc on the hybrid model."""
+    import importlib
+    from oracle import ref_model
+    from rayoptics_b200 import vigcalc as V
+    ref_model.modules()
+    RV = importlib.import_module('rayoptics.raytr.vigcalc')
+    a, b = load_model(name), load_model(name)
+    H = ref_model.HybridModel(a)
+    H.update_model = a.update_model
+    kw = dict(tracer=oracle_tracer)
+
+    def keep():
+        for f in a.optical_spec.field_of_view.fields:
+            f.chief_ray = ((None, None, -1.0), None)
+    # bisection search of the upper y pupil edge of the outer field
+    fa, fb = a.optical_spec.field_of_view.fields[-1], b.optical_spec.field_of_view.fields[-1]
+    wvl = a.seq_model.central_wavelength()
+    for xy, start in ((1, [0., 1.]), (0, [-1., 0.])):
+        keep()
+        vw, cw, pw = RV.calc_vignetted_ray_by_bisection(H, xy, np.array(start), fa, wvl)
+        vg, cg, pg = V.calc_vignetted_ray_by_bisection(b, xy, np.array(start), fb, wvl, **kw)
+        assert vw == vg and cw == cg and len(pw[0]) == len(pg[0])
+    # a smaller stop: the pupil specification follows
+    stop = a.seq_model.stop_surface
+    r = 0.9*b.seq_model.ifcs[stop].max_aperture
+    H.seq_model.ifcs[stop].set_max_aperture(r)
+    a.seq_model.ifcs[stop].set_max_aperture(r)
+    b.seq_model.ifcs[stop].set_max_aperture(r)
+    before = b.optical_spec.pupil.value
+    keep()
+    a_update = a.update_model
+
+    def update_and_keep(**k):
+        a_update(**k)
+        keep()
+    H.update_model = update_and_keep
+    RV.set_pupil(H, use_parax=use_parax)
+    V.set_pupil(b, use_parax=use_parax, **kw)
+    assert a.optical_spec.pupil.value == b.optical_spec.pupil.value != before
+    # (the reference's image-space f/# comes out negative for the relay: kept, it is its number)
+    assert abs(abs(b.optical_spec.pupil.value/before) - (1/0.9 if b.optical_spec.pupil.key[1] == 'f/#' else 0.9)) < 0.02
+    for x, y in zip(a.optical_spec.field_of_view.fields, b.optical_spec.field_of_view.fields):
+        assert (x.vux, x.vlx, x.vuy, x.vly) == (y.vux, y.vlx, y.vuy, y.vly)
+    assert capsys.readouterr().out.count('Axial bundle limited') in (0, 2)
+
+
+def oracle_trace_fn(opm):
+    """trace_fn= seam (one ray, the drop-in ``raytrace.trace`` signature) fed by the oracle"""
+    from rayoptics_b200 import raytrace as RT
+    sm = opm.seq_model
+
+    def fn(seq_model, pt0, dir0, wvl, **kw):
+        opts = dict(first_surf=1, last_surf=sm.get_num_surfaces() - 2)
+        opts.update({k: v for k, v in kw.items() if k in TR._TRACE_RAW_KEYS})
+        r = oracle_bundle_tracer(opm, None, np.array(pt0, dtype=float).reshape(3, 1),
+                                 np.array(dir0, dtype=float).reshape(3, 1),
+                                 np.array([sm.index_for_wavelength(wvl)], dtype=np.int32), opts)
+        pkg, err = RT.package_ray(list(sm.path(wvl)), r['full'][:, :, 0], float(r['op'][0]),
+                                  int(r['status'][0]), int(r['fail_surf'][0]), int(r['n_seg'][0]), wvl)
+        if err is not None:
+            raise err
+        return pkg
+    return fn
+
+
+def test_aperture_lists_and_stop_aperture():
+    """set_clear_apertures with include / avoid lists (vigcalc.py:45-80) in both forms, and
+    set_stop_aperture (vigcalc.py:104-115): the stop takes the height of the unvignetted axial
+    marginal ray, everything else is left alone, the vignetting is recomputed."""
+    from rayoptics_b200 import vigcalc as V
+    a, b, c = load_model('dblgauss'), load_model('dblgauss'), load_model('dblgauss')
+    n = a.seq_model.get_num_surfaces()
+    stop = a.seq_model.stop_surface
+    orig = [ifc.max_aperture for ifc in a.seq_model.ifcs]
+    for m in (a, b, c):
+        for ifc in m.seq_model.ifcs:
+            ifc.set_max_aperture(1.25*ifc.max_aperture)
+    big = [ifc.max_aperture for ifc in a.seq_model.ifcs]
+    V.set_clear_apertures(a, oracle_trace_fn(a), include_list=[2, 3, stop])
+    V.set_clear_apertures_batched(b, oracle_bundle_fn(b), avoid_list=[i for i in range(n) if i not in (2, 3, stop)])
+    for i in range(n):
+        ap_a, ap_b = a.seq_model.ifcs[i].max_aperture, b.seq_model.ifcs[i].max_aperture
+        assert ap_a == ap_b
+        assert (ap_a != big[i]) == (i in (2, 3, stop))
+    rayset = V.trace_boundary_rays(c, oracle_trace_fn(c))
+    assert V.max_aperture_at_surf([rayset[0]], stop) == a.seq_model.ifcs[stop].max_aperture
+    assert V.max_aperture_at_surf(rayset, n + 3) is None
+    # set_stop_aperture: axial vignetting cleared, stop := axial marginal ray height, set_vig
+    f0 = c.optical_spec.field_of_view.fields[0]
+    f0.vuy = f0.vly = 0.2
+    V.set_stop_aperture(c, trace_fn=oracle_trace_fn(c), tracer=oracle_tracer)
+    ray = TR.trace_base(c, np.array([0., 1.]), f0, c.seq_model.central_wavelength(),
+                        apply_vignetting=False, tracer=oracle_tracer)
+    assert abs(c.seq_model.ifcs[stop].max_aperture - abs(ray[0][stop][0][1])) < 1e-9
+    assert [ifc.max_aperture for i, ifc in enumerate(c.seq_model.ifcs) if i != stop] == \
+           [x for i, x in enumerate(big) if i != stop]
+    assert abs(f0.vuy) < 1e-5 and abs(f0.vly) < 1e-5          # the stop is the limiting aperture on axis
+    assert orig[stop] > 0
