@@ -552,3 +552,18 @@ def trace_astigmatism_coddington_fan(opt_model, fld, wvl, foc, **engine):
     """astigmatism by a Coddington trace along the chief ray of ``fld`` (trace.py:708-712)"""
     cr_pkg, _ = trace_ray(opt_model, [0., 0.], fld, wvl, **engine)
     return trace_coddington_fan(opt_model, cr_pkg, foc=foc)
+
+
+def iterate_ray(opt_model, ifcx, xy_target, fld, wvl, **kwargs):
+    """``(start_coords, (ray_pkg, error))`` as the reference returns it (trace.py:313-415);
+    the solver is ``vigcalc.iterate_ray``"""
+    from . import vigcalc
+    return vigcalc.iterate_ray(opt_model, ifcx, xy_target, fld, wvl,
+                               trace_fn=kwargs.get('trace_fn'), full=True)
+
+
+def iterate_ray_raw(pthlist, ifcx, xy_target, pt0, d0, obj2pup_dist, eprad, wvl, not_wa, **kwargs):
+    """trace.py:866-957, see ``vigcalc.iterate_ray_raw``"""
+    from . import vigcalc
+    return vigcalc.iterate_ray_raw(pthlist, ifcx, xy_target, pt0, d0, obj2pup_dist, eprad, wvl,
+                                   not_wa, **kwargs)

@@ -687,7 +687,7 @@ def set_vig_batched(opm, ray_fn=None, wvl=None, max_iter_count=50):
 
 
 # --- the reference's own aiming iteration (raytr/trace.py:313-415) ----------------------------
-def iterate_ray(opt_model, ifcx, xy_target, fld, wvl, trace_fn=None):
+def iterate_ray(opt_model, ifcx, xy_target, fld, wvl, trace_fn=None, full=False):
     """Iterate a ray to ``xy_target`` on interface ``ifcx``; returns the aim point on the
     paraxial entrance pupil plane -- ``iterate_ray`` of the reference with the same solvers
     (scipy ``newton`` in 1-D when field and target have x == 0, else ``fsolve`` with
@@ -701,29 +701,40 @@ def iterate_ray(opt_model, ifcx, xy_target, fld, wvl, trace_fn=None):
     sign of the one ``ray_start_from_osp`` needs -- the aim points stored in the reference's
     ``.roa`` files have the consistent sign.  ``aim_chief_ray`` / ``aim_all_fields_batched``
     above iterate on ``ray_start_from_osp`` itself and reproduce the stored values."""
-    import warnings
-    from scipy.optimize import newton, fsolve
     from . import raytrace as RT
     if trace_fn is None:
         trace_fn = RT.trace
     seq_model, osp = opt_model.seq_model, opt_model.optical_spec
     fod = osp.fod
-    obj2enp_dist = fod.obj_dist + fod.enp_dist
-    not_wa = not osp.field_of_view.is_wide_angle
     pt0, d0 = osp.obj_coords(fld)
+    coords, rr = _iterate_to_target(lambda p, d: trace_fn(seq_model, p, d, wvl), ifcx, xy_target,
+                                    pt0, fod.obj_dist + fod.enp_dist, fod.enp_radius,
+                                    not osp.field_of_view.is_wide_angle, seq_model.z_dir[0])
+    return (coords, rr) if full else coords      # full: the reference's return value
+
+
+def _iterate_to_target(trace_one, ifcx, xy_target, pt0, obj2enp_dist, eprad, not_wa, z_dir0):
+    """the solver part shared by ``iterate_ray`` and ``iterate_ray_raw`` (trace.py:313-415,
+    866-957): returns ``(start_coords, (ray_pkg, error) of the last ray traced)``"""
+    import warnings
+    from scipy.optimize import newton, fsolve
+    from . import raytrace as RT
+    last = [None]
 
     def final_coord(pt1):
         v = pt1 - pt0
         dir0 = v/np.linalg.norm(v)
-        if not_wa and dir0[2]*seq_model.z_dir[0] < 0:
+        if not_wa and dir0[2]*z_dir0 < 0:
             dir0 = -dir0
         try:
-            ray = trace_fn(seq_model, pt0, dir0, wvl)[0]
+            pkg = trace_one(pt0, dir0)
         except RT.TraceError as ray_error:
+            last[0] = (ray_error.ray_pkg, ray_error)
             if ray_error.surf < ifcx:
                 raise ray_error
             return np.array([0., 0., 0.])
-        return ray[ifcx][0]
+        last[0] = (pkg, None)
+        return pkg[0][ifcx][0]
 
     def y_stop_coordinate(y1, y_target):
         return final_coord(np.array([0., y1, obj2enp_dist]))[1] - y_target
@@ -733,7 +744,7 @@ def iterate_ray(opt_model, ifcx, xy_target, fld, wvl, trace_fn=None):
         return np.array([fc[0], fc[1]]) - target
 
     if ifcx is None:                       # floating stop: use the entrance pupil for aiming
-        return np.array([0., 0.]) + xy_target
+        return np.array([0., 0.]) + xy_target, None
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         if pt0[0] == 0.0 and xy_target[0] == 0.0:
@@ -744,12 +755,24 @@ def iterate_ray(opt_model, ifcx, xy_target, fld, wvl, trace_fn=None):
                 start_y = 0.0
             except RT.TraceError:
                 start_y = 0.0
-            return np.array([0., start_y])
+            return np.array([0., start_y]), last[0]
         try:
-            return fsolve(surface_coordinate, np.array([0., 0.]), epsfcn=0.0001*fod.enp_radius,
-                          args=(np.array(xy_target, dtype=float),))
+            coords = fsolve(surface_coordinate, np.array([0., 0.]), epsfcn=0.0001*eprad,
+                            args=(np.array(xy_target, dtype=float),))
         except RT.TraceError:
-            return np.array([0., 0.])
+            coords = np.array([0., 0.])
+        return coords, last[0]
+
+
+def iterate_ray_raw(pthlist, ifcx, xy_target, pt0, d0, obj2pup_dist, eprad, wvl, not_wa,
+                    trace_raw_fn=None, **kwargs):
+    """``iterate_ray`` on an explicit path list (trace.py:866-957): ``(start_coords, (ray_pkg,
+    error))``.  Rays go through the drop-in ``raytrace.trace_raw`` (one single-ray launch each)."""
+    from . import raytrace as RT
+    trace_raw_fn = RT.trace_raw if trace_raw_fn is None else trace_raw_fn
+    pthlist = list(pthlist)
+    return _iterate_to_target(lambda p, d: trace_raw_fn(iter(pthlist), p, d, wvl), ifcx, xy_target,
+                              np.array(pt0, dtype=float), obj2pup_dist, eprad, not_wa, pthlist[0][4])
 
 
 def aim_chief_ray_like_reference(opt_model, fld, wvl=None, trace_fn=None):

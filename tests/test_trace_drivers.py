@@ -794,3 +794,31 @@ def test_aperture_lists_and_stop_aperture():
            [x for i, x in enumerate(big) if i != stop]
     assert abs(f0.vuy) < 1e-5 and abs(f0.vly) < 1e-5          # the stop is the limiting aperture on axis
     assert orig[stop] > 0
+
+
+@needs_ref
+@pytest.mark.parametrize('name,fi', [('dblgauss', 2), ('triplet', 1), ('evenasph', 1)])
+def test_iterate_ray_raw_equals_the_references(name, fi):
+    """vigcalc.iterate_ray_raw against rayoptics.raytr.trace.iterate_ray_raw (imported, run on
+    the reference's own trace_raw over reference surfaces): same aim point, 1-D (newton) and
+    2-D (fsolve) branches."""
+    from oracle import ref_model, ref_harness as rh
+    from rayoptics_b200 import vigcalc as V
+    RT, RA = ref_model.modules()
+    opm = load_model(name)
+    sm, osp = opm.seq_model, opm.optical_spec
+    fod = osp.fod
+    wvl = sm.central_wavelength()
+    fld = osp.field_of_view.fields[fi]
+    pt0, d0 = osp.obj_coords(fld)
+    one = oracle_trace_fn(opm)
+    args = (fod.obj_dist + fod.enp_dist, fod.enp_radius, wvl, True)
+    for target, p0 in ((np.array([0., 0.]), pt0), (np.array([0.05, -0.02]), pt0),
+                       (np.array([0., 0.1]), pt0 + np.array([0.3, 0., 0.]))):
+        want, rr_w = RT.iterate_ray_raw(rh.ref_path(sm, wvl), sm.stop_surface, target, p0, d0, *args)
+        got, rr_g = V.iterate_ray_raw(sm.path(wvl), sm.stop_surface, target, p0, d0, *args,
+                                      trace_raw_fn=lambda path, p, d, w: one(sm, p, d, w))
+        assert np.array_equal(want, got), (name, target)
+        assert rr_g[1] is None and np.array_equal(rr_w.pkg.ray[-1][0], rr_g[0][0][-1][0])
+    got, rr = V.iterate_ray_raw(sm.path(wvl), None, np.array([0.1, 0.2]), pt0, d0, *args)
+    assert np.array_equal(got, [0.1, 0.2]) and rr is None
