@@ -80,6 +80,10 @@ class FieldSpec:
         for f in self.fields:
             f.fov = self
 
+    def new_field(self, x=0.0, y=0.0, **kwargs):
+        """a Field tied to this specification, not added to ``fields`` (opticalspec.py FieldSpec)"""
+        return Field(x=x, y=y, fov=self, **kwargs)
+
     def max_field(self):
         """(magnitude of the maximum field, index of that field), opticalspec.py:1093-1109"""
         max_fld, max_fld_sqrd = 0, -1.0

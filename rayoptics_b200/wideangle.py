@@ -38,20 +38,23 @@ def _trace_errors():
     return TraceError, TraceMissedSurfaceError
 
 
-def enp_z_coordinate(z_enp, seq_model, stop_idx, dir0, obj_dist, wvl, trace_fn):
+def enp_z_coordinate(z_enp, seq_model, stop_idx, dir0, obj_dist, wvl, trace_fn=None):
     """wideangle.py:46-93: trace the ray through the centre of the pupil plane at ``z_enp``
-    along ``dir0``; returns ``(point at the stop | zeros, ray, error | None)``."""
+    along ``dir0``; returns ``(point at the stop | zeros, RayResult(ray package, error | None))``."""
+    from .trace import RayPkg, RayResult
     TraceError, _ = _trace_errors()
+    trace_fn = _default_trace_fn() if trace_fn is None else trace_fn
     obj2enp_dist = (obj_dist + z_enp)
     pt1 = np.array([0., 0., obj2enp_dist])
     rot_mat = rot_v1_into_v2(np.array([0., 0., 1.]), dir0)
     pt0 = np.matmul(rot_mat, -pt1) + pt1
     try:
-        ray, op, w = trace_fn(seq_model, pt0, dir0, wvl, intersect_obj=False)
+        pkg = RayPkg(*trace_fn(seq_model, pt0, dir0, wvl, intersect_obj=False))
     except TraceError as ray_error:
         pkg = ray_error.ray_pkg
-        return np.array([0., 0., 0.]), (pkg[0] if pkg is not None else []), ray_error
-    return ray[stop_idx][0], ray, None
+        pkg = RayPkg(*pkg) if pkg is not None else RayPkg([], 0.0, wvl)
+        return np.array([0., 0., 0.]), RayResult(pkg, ray_error)
+    return pkg.ray[stop_idx][0], RayResult(pkg, None)
 
 
 def find_edge(f, a, b, max_iter=3):
@@ -74,7 +77,7 @@ def find_edge(f, a, b, max_iter=3):
 
 def find_z_enp_on_interval(opt_model, stop_idx, start_z, end_z, z_estimate, fld, wvl, trace_fn):
     """wideangle.py:355-446: iterate ``z_enp`` until the ray crosses the stop at height 0.
-    Returns ``(start_coords, ray of the last evaluation, converged)``."""
+    Returns ``(start_coords, RayResult of the last evaluation, converged)``."""
     from scipy.optimize import newton, brentq
     TraceError, _ = _trace_errors()
     sm, osp = opt_model['seq_model'], opt_model['optical_spec']
@@ -83,8 +86,8 @@ def find_z_enp_on_interval(opt_model, stop_idx, start_z, end_z, z_estimate, fld,
     last = {}
 
     def eval_z_enp(z_enp, *args):
-        final_coord, ray, err = enp_z_coordinate(z_enp, sm, stop_idx, dir0, fod.obj_dist, wvl, trace_fn)
-        last['ray'], last['err'] = ray, err
+        final_coord, rr = enp_z_coordinate(z_enp, sm, stop_idx, dir0, fod.obj_dist, wvl, trace_fn)
+        last['rr'] = rr
         return final_coord[1] - 0.0
 
     if stop_idx is None:                       # floating stop: paraxial entrance pupil
@@ -97,7 +100,7 @@ def find_z_enp_on_interval(opt_model, stop_idx, start_z, end_z, z_estimate, fld,
         except (RuntimeError, TraceError):
             z_enp = results.root if results is not None else z_enp
         converged = bool(results.converged) if results is not None else False
-        ht_at_stop = last['ray'][stop_idx][0][1]
+        ht_at_stop = last['rr'].pkg.ray[stop_idx][0][1]
         if abs(ht_at_stop) < 1e-6:
             converged = True
         start_coords = np.array([0., 0., z_enp])
@@ -109,12 +112,12 @@ def find_z_enp_on_interval(opt_model, stop_idx, start_z, end_z, z_estimate, fld,
                 z_enp = results.root
             start_coords = np.array([0., 0., z_enp])
             converged = bool(results.converged)
-    return start_coords, last['ray'], converged
+    return start_coords, last['rr'], converged
 
 
 def find_real_enp(opt_model, stop_idx, fld, wvl, trace_fn=None):
     """wideangle.py:105-330 (``find_real_enp`` -> rev1): z position, relative to the first
-    interface, of the real entrance pupil of ``fld``.  Returns ``(z_enp, ray)``."""
+    interface, of the real entrance pupil of ``fld``.  Returns ``(z_enp, RayResult of the last ray)``."""
     _, TraceMissedSurfaceError = _trace_errors()
     trace_fn = _default_trace_fn() if trace_fn is None else trace_fn
     sm, osp = opt_model['seq_model'], opt_model['optical_spec']
@@ -123,21 +126,22 @@ def find_real_enp(opt_model, stop_idx, fld, wvl, trace_fn=None):
     pt0, dir0 = osp.obj_coords(fld)
 
     def at(z):
-        return enp_z_coordinate(z, sm, stop_idx, dir0, fod.obj_dist, wvl, trace_fn)
+        final_coord, rr = enp_z_coordinate(z, sm, stop_idx, dir0, fod.obj_dist, wvl, trace_fn)
+        return final_coord, rr, rr.err
 
     def ht(z):                                  # enp_z_coordinate_wrapper
-        final_coord, ray, err = at(z)
+        final_coord, rr, err = at(z)
         return final_coord[1] if err is None else None
 
     if fld.aim_info is not None:                # existing aim info: keep it if it is good
         z_enp = fld.aim_info
-        final_coord, ray, err = at(z_enp)
+        final_coord, rr, err = at(z_enp)
         if abs(final_coord[1]) < 1.48e-08:
-            return z_enp, ray
+            return z_enp, rr
     z_enp_0 = fod.enp_dist
     if dir0[2] == 1:                            # axial chief ray: the paraxial pupil
-        final_coord, ray, err = at(z_enp_0)
-        return z_enp_0, ray
+        final_coord, rr, err = at(z_enp_0)
+        return z_enp_0, rr
 
     start_z = prev_z = end_z = None
     del_z = -z_enp_0/16
@@ -145,7 +149,7 @@ def find_real_enp(opt_model, stop_idx, fld, wvl, trace_fn=None):
     keep_going, direction = True, 'first'
     first_surf_misses = trial = successes = 0
     while keep_going and trial < 64 and first_surf_misses < 2:
-        final_coord, ray, err = at(z_enp)
+        final_coord, rr, err = at(z_enp)
         if err is None:
             ht_at_stop = final_coord[1]
             successes += 1
@@ -188,7 +192,7 @@ def find_real_enp(opt_model, stop_idx, fld, wvl, trace_fn=None):
         start_new, end_new = z_enp_a - del_z, z_enp_b + del_z
         start_z = end_z = None
         for z_enp in np.linspace(start_new, end_new, num=8):
-            final_coord, ray, err = at(z_enp)
+            final_coord, rr, err = at(z_enp)
             if err is None:
                 if start_z is None:
                     start_z = z_enp, final_coord[1]
@@ -215,16 +219,76 @@ def find_real_enp(opt_model, stop_idx, fld, wvl, trace_fn=None):
                 a, b = z_enp_a, z_enp_edge_a
             else:                               # no ray through the stop centre
                 z_enp_cntr = z_enp_edge_a + (z_enp_edge_b - z_enp_edge_a)/2
-                final_coord, ray, err = at(z_enp_cntr)
-                return z_enp_b, ray
+                final_coord, rr, err = at(z_enp_cntr)
+                return z_enp_b, rr
 
     if _is_fuzzy_zero(end_z[1] - start_z[1]):
         z_estimate = start_z[0]
     else:
         z_estimate = start_z[0] - ((end_z[0] - start_z[0])/(end_z[1] - start_z[1]))*start_z[1]
-    start_coords, ray, _ = find_z_enp_on_interval(opt_model, stop_idx, a, b, z_estimate, fld, wvl,
-                                                  trace_fn)
-    return start_coords[2], ray
+    start_coords, rr, _ = find_z_enp_on_interval(opt_model, stop_idx, a, b, z_estimate, fld, wvl,
+                                                 trace_fn)
+    return start_coords[2], rr
+
+
+def find_z_enp(opt_model, stop_idx, z_enp_0, fld, wvl, trace_fn=None, **kwargs):
+    """wideangle.py:559-617: secant iteration of ``z_enp`` from the estimate ``z_enp_0`` (which
+    must give a ray that reaches the stop); ``(start_coords, RayResult, scipy results)``."""
+    from scipy.optimize import newton
+    TraceError, _ = _trace_errors()
+    sm, osp = opt_model['seq_model'], opt_model['optical_spec']
+    fod = opt_model['analysis_results']['parax_data'].fod
+    pt0, dir0 = osp.obj_coords(fld)
+    last = {'rr': None}
+
+    def eval_z_enp(z_enp):
+        final_coord, last['rr'] = enp_z_coordinate(z_enp, sm, stop_idx, dir0, fod.obj_dist, wvl,
+                                                   trace_fn)
+        return final_coord[1] - 0.
+    if stop_idx is None:
+        return np.array([0., 0., fod.enp_dist]), None, None
+    z_enp, results = z_enp_0, None
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        try:
+            z_enp, results = newton(eval_z_enp, z_enp, rtol=1e-7, disp=False, full_output=True)
+        except (RuntimeError, TraceError):
+            z_enp = results.root if results is not None else z_enp
+    return np.array([0., 0., z_enp]), last['rr'], results
+
+
+def eval_z_enp_curve(opm, printout=True, trace_fn=None, num_fields=21):
+    """the z position of the real entrance pupil across the field of view (wideangle.py:667-705,
+    ('object', 'angle') fields): ``(fields, object angles, image heights, z_enps)``."""
+    import math
+    sm, osp = opm['seq_model'], opm['optical_spec']
+    fov = osp['fov']
+    if tuple(fov.key) != ('object', 'angle'):
+        raise NotImplementedError(f'field type {fov.key}: only (object, angle) fields')
+    save_is_relative = fov.is_relative
+    save_fields = [(f.x, f.y) for f in fov.fields]
+    if not save_is_relative:                      # the fields are re-read as fractions
+        fov.is_relative = True
+    flds, z_enps, obj_angs, img_hts = [], [], [], []
+    cwl = osp['wvls'].central_wvl
+    if printout:
+        print('frac fld     obj angle     img ht      z_enp')
+    try:
+        for fld_ht in np.linspace(0, 1, num_fields):
+            fld = fov.new_field(y=fld_ht)
+            z_enp, cr_rr = find_real_enp(opm, sm.stop_surface, fld, cwl, trace_fn)
+            cr_ray = cr_rr.pkg.ray
+            d0, img_ht = cr_ray[0][1], cr_ray[-1][0]
+            ang_y = np.rad2deg(math.atan2(d0[1], d0[2]))
+            if printout:
+                print(f'{fld.yf:7.2f}     {ang_y:9.3f}     {img_ht[1]:7.2f}    {z_enp:8.4f}')
+            flds.append(fld)
+            obj_angs.append(ang_y)
+            img_hts.append(img_ht[1])
+            z_enps.append(z_enp)
+    finally:
+        fov.is_relative = save_is_relative
+    return flds, obj_angs, img_hts, z_enps
 
 
 def aim_wide_angle_fields(opt_model, wvl=None, trace_fn=None):

@@ -582,9 +582,28 @@ def test_find_real_enp_is_the_references():
                         err = cls.__new__(cls)
                         err.__dict__.update(e.__dict__)
                         raise err
-                z_own, ray = W.find_real_enp(b, b.seq_model.stop_surface, fb, wvl, trace_fn=tf)
+                z_own, rr_own = W.find_real_enp(b, b.seq_model.stop_surface, fb, wvl, trace_fn=tf)
             assert z_own == z_ref
             assert abs(z_ref - s) < 1e-9
+            # the second return value is the reference's: RayResult of the last ray traced
+            assert (rr_own.err is None) == (rr.err is None) and len(rr_own.pkg.ray) == len(rr.pkg.ray)
+            assert np.array_equal(rr_own.pkg.ray[-1][0], rr.pkg.ray[-1][0]) and rr_own.pkg.op == rr.pkg.op
+    # the older secant-only search from the paraxial pupil, and the pupil curve across the field
+    fa, fb = a.optical_spec.field_of_view.fields[1], b.optical_spec.field_of_view.fields[1]
+    fod = a.optical_spec.fod
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        cw, rw, _ = RW.find_z_enp(H, a.seq_model.stop_surface, fod.enp_dist, fa, wvl)
+        cg, rg, res = W.find_z_enp(b, b.seq_model.stop_surface, fod.enp_dist, fb, wvl, trace_fn=tf)
+    assert np.array_equal(cw, cg) and res.converged and abs(cg[2] - stored[1]) < 1e-5
+    rel = b.optical_spec.field_of_view.is_relative
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        flds, angs, hts, zs = W.eval_z_enp_curve(b, printout=False, trace_fn=tf, num_fields=5)
+    assert b.optical_spec.field_of_view.is_relative == rel and len(flds) == 5
+    assert angs[0] == 0.0 and abs(angs[-1] - b.optical_spec.field_of_view.value) < 1e-9
+    assert zs[0] == fod.enp_dist and all(z1 < z0 for z0, z1 in zip(zs, zs[1:]))   # the pupil walks towards the lens
+    assert abs(zs[-1] - stored[-1]) < 1e-9 and hts[0] == 0.0
 
 
 def _hybrid_with_powers(opm):
