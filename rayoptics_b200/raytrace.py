@@ -235,7 +235,8 @@ def install(batched=False):
 
     ``batched=True`` additionally rebinds the per-ray LOOPS of the reference to the batched
     drivers of ``rayoptics_b200.trace`` -- ``rayoptics.raytr.trace.trace_fan / trace_grid`` and
-    ``rayoptics.raytr.analyses.trace_ray_fan / trace_ray_list / trace_ray_grid`` -- so that the
+    ``rayoptics.raytr.analyses.trace_ray_fan / trace_ray_list / trace_ray_grid``, plus the short
+    lists ``trace.trace_boundary_rays_at_field / trace_astigmatism / trace_ray_list_at_field`` -- so that the
     reference's own ``RayFan`` / ``RayList`` / ``RayGrid`` / ``SequentialModel.trace_fan`` ...
     trace each (field, wavelength) in one launch.  Same arguments and results (checked
     against the unpatched reference in tests/test_dropin_batched.py, wide-angle fields
@@ -252,7 +253,11 @@ def install(batched=False):
         pairs = [(rtr, 'trace_fan', TR.trace_fan), (rtr, 'trace_grid', TR.trace_grid),
                  (ran, 'trace_ray_fan', TR.analyses_trace_ray_fan),
                  (ran, 'trace_ray_list', TR.analyses_trace_ray_list),
-                 (ran, 'trace_ray_grid', TR.analyses_trace_ray_grid)]
+                 (ran, 'trace_ray_grid', TR.analyses_trace_ray_grid),
+                 # short pupil-point lists of raytr/trace.py: one launch instead of 5 / n
+                 (rtr, 'trace_boundary_rays_at_field', TR.trace_boundary_rays_at_field),
+                 (rtr, 'trace_astigmatism', TR.trace_astigmatism),
+                 (rtr, 'trace_ray_list_at_field', TR.trace_ray_list_at_field)]
         for mod, name, fn in pairs:
             key = (mod.__name__, name)
             if key not in _saved:

@@ -54,6 +54,46 @@ def test_reference_classes_on_batched_loops(name, monkeypatch):
                               equal_nan=True)
 
 
+@pytest.mark.parametrize('name', ['dblgauss', 'triplet'])
+def test_reference_short_lists_on_batched_loops(name, monkeypatch):
+    """trace_boundary_rays / trace_astigmatism / trace_ray_list_at_field of the reference with their
+    5-ray loops rebound (install(batched=True)): same packages, numbers and DataFrames as unpatched"""
+    from oracle import ref_model
+    RT, RA = ref_model.modules()
+    a, b = load_model(name), load_model(name)
+    Ha, Hb = ref_model.HybridModel(a), ref_model.HybridModel(b)
+    wvl = a.seq_model.central_wavelength()
+
+    def keep(m):
+        for f in m.optical_spec.field_of_view.fields:
+            f.chief_ray = ((None, None, -1.0), None)
+    keep(a)
+    want_rays = RT.trace_boundary_rays(Ha, use_named_tuples=True)
+    fa = a.optical_spec.field_of_view.fields[-1]
+    want_ast = RT.trace_astigmatism(Ha, fa, wvl, 0.01)
+    want_df = RT.trace_ray_list_at_field(Ha, [[0., 0.3], [0.2, -0.5]], fa, wvl, 0.0)
+    for fn in ('trace_boundary_rays_at_field', 'trace_astigmatism', 'trace_ray_list_at_field'):
+        monkeypatch.setattr(RT, fn, functools.partial(getattr(TR, fn), tracer=oracle_tracer))
+    keep(b)
+    got_rays = RT.trace_boundary_rays(Hb, use_named_tuples=True)
+    fb = b.optical_spec.field_of_view.fields[-1]
+    assert RT.trace_astigmatism(Hb, fb, wvl, 0.01) == want_ast
+    got_df = RT.trace_ray_list_at_field(Hb, [[0., 0.3], [0.2, -0.5]], fb, wvl, 0.0)
+    for fw, fg in zip(want_rays, got_rays):
+        assert len(fw) == len(fg) == 5
+        for pw, pg in zip(fw, fg):
+            assert len(pw.ray) == len(pg.ray) and pw.op == pg.op
+            for sw, sg in zip(pw.ray, pg.ray):
+                assert np.array_equal(sw.p, sg.p) and np.array_equal(sw.d, sg.d) and sw.dst == sg.dst
+    for x, y in zip(a.optical_spec.field_of_view.fields, b.optical_spec.field_of_view.fields):
+        assert list(x.pupil_rays) == list(y.pupil_rays) == ['00', '+X', '-X', '+Y', '-Y']
+    for dw, dg in zip(want_df, got_df):
+        assert list(dw.columns) == list(dg.columns) and len(dw) == len(dg)
+        for col in dw.columns:
+            for u, v in zip(dw[col], dg[col]):
+                assert np.array_equal(np.asarray(u), np.asarray(v))
+
+
 def test_install_batched_rebinds_and_restores():
     from oracle import ref_model
     from rayoptics_b200 import raytrace as B
