@@ -100,6 +100,49 @@ def test_kat_profile_s1(oracle):
     np.testing.assert_allclose(r['ray'][1][7:10], nrm/np.linalg.norm(nrm), rtol=1e-14)
 
 
+@pytest.mark.parametrize('backend', ['oracle', 'device source'])
+def test_kat_profile_cases(oracle, backend):
+    """elem/tests/test_profiles.py:36-125 (planar / convex / concave sphere, and a spherical
+    EvenPolynomial that must agree with the Spherical): rays (0,0,-1) and (0,1,-1) along +z.
+    ``intersect`` is reached through a one-surface path whose object plane sits 1 in front of the
+    vertex, so segment 0's ``dst`` is the reference test's ``s`` and segment 1 holds the point and
+    the normal.  The truths are the test file's closed forms."""
+    from math import sqrt
+    from hostsim import build as HS
+    r = 10.0
+    sag = r - sqrt(r*r - 1.0)
+    cases = [(M.Spherical(c=0.0), 1.0, 0.0, 1.0, [0., 1., 0.], [0., 0., 1.]),
+             (M.Spherical(c=1/r), 1.0, 0.0, 1 + sag, [0., 1., sag], None),
+             (M.EvenPolynomial(c=1/r), 1.0, 0.0, 1 + sag, [0., 1., sag], None),
+             (M.Conic(c=1/r, cc=0.0), 1.0, 0.0, 1 + sag, [0., 1., sag], None),
+             (M.Spherical(r=-r), 1.0, 0.0, 1 - sag, [0., 1., -sag], None)]
+    for prof, s0, z0, s1, pt1, n1 in cases:
+        ifcs = [M.Surface(interact_mode='dummy'), M.Surface(profile=prof, max_ap=5.0),
+                M.Surface(interact_mode='dummy')]
+        sm = M.SequentialModel(ifcs, [M.Gap(1.0), M.Gap(10.0)])
+        descs, ns = T.describe_path(sm.path())
+        p = np.array([[0., 0.], [0., 1.], [0., 0.]])
+        d = np.array([[0., 0.], [0., 0.], [1., 1.]])
+        wv = np.zeros(2, dtype=np.int32)
+        if backend == 'oracle':
+            out = oracle.trace_bundle(descs, np.array([ns]), p, d, wv, _abi.make_opts(), want_full=True)
+        else:
+            out = HS.trace_bundle(descs, np.array([ns]), p, d, wv, _abi.make_opts(), kernel=0, out_kind=2)
+        full = out['full']                                   # [n_ifc, 10, n]
+        assert (out['status'] == 0).all()
+        assert full[0, 6, 0] == s0 and same(full[1, 0:3, 0], np.array([0., 0., z0]))
+        assert same(full[1, 7:10, 0], np.array([0., 0., 1.]))
+        assert full[0, 6, 1] == pytest.approx(s1, rel=1e-14, abs=1e-14)
+        np.testing.assert_allclose(full[1, 0:3, 1], pt1, rtol=1e-14, atol=1e-15)
+        cv = prof.cv
+        want_n = np.array([0., 0., 1.]) if cv == 0 else None
+        if want_n is None:
+            c = np.array([0., 0., 1/cv])
+            want_n = -(np.array(pt1) - c)*np.sign(cv)
+            want_n /= np.linalg.norm(want_n)
+        np.testing.assert_allclose(full[1, 7:10, 1], want_n, rtol=1e-14, atol=1e-15)
+
+
 def test_oracle_live_against_reference(oracle):
     """Fresh seeded rays, traced by the reference here and by the oracle."""
     from oracle import ref_harness as rh
