@@ -83,8 +83,26 @@ def _medium(token, glass_map):
     m = _builtin_glass(token)
     if m is not None:
         return m
+    if isinstance(glass_map, SubstituteGlasses):
+        return glass_map.substitute(token)
     raise KeyError(f'glass {token!r}: neither in glass_map nor among the {len(_glass_table())} glasses of '
                    f'rayoptics_b200/glass_table.json (this package ships no full catalog)')
+
+
+class SubstituteGlasses(dict):
+    """``glass_map`` that never fails: names it does not hold resolve through the built-in table
+    and then -- what the reference's importers do when a glass is in none of its catalogs
+    (``GlassHandlerBase.find_glass``, seq/medium.py:165-203) -- become ``ConstantIndex(1.5,
+    'not ' + name)``.  ``not_found`` lists those names after the import."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.not_found = []
+
+    def substitute(self, token):
+        if token not in self.not_found:
+            self.not_found.append(token)
+        return M.ConstantIndex(1.5, label='not ' + token)
 
 
 _GLASS_TABLE = None

@@ -213,10 +213,17 @@ def open_zmx(path, glass_map=None):
 
 
 def _zmx_medium(name, glass_map):
+    from .seq import SubstituteGlasses
+    strict = dict(glass_map) if isinstance(glass_map, SubstituteGlasses) else glass_map
     try:
-        return _medium(name, glass_map)
+        return _medium(name, strict)
     except KeyError:
         base = name.rsplit('_', 1)[0]
         if base != name:
-            return _medium(base, glass_map)
+            try:
+                return _medium(base, strict)
+            except KeyError:
+                pass
+        if strict is not glass_map:
+            return glass_map.substitute(name)
         raise

@@ -657,3 +657,49 @@ def test_grid_validation_accepts_every_pupil_kind_without_a_gpu(name):
     c = spec.c_spec()
     c.paired = 1
     assert lib.rt_grid_create(C.byref(c), 0, C.byref(h)) == -1
+
+
+def test_every_bundled_lens_file_loads_and_traces(oracle):
+    """All .roa / .seq / .zmx files in the reference tree (70) go through the readers, the table
+    compiler and an axial ray by the oracle.  Catalog glasses outside glass_table.json become the
+    reference importers' own last resort, ConstantIndex(1.5, 'not <name>') (seq/medium.py:199-203),
+    through seq.SubstituteGlasses; the one refusal is Zemax's QED surface type (which the
+    reference reads as a plain sphere, zmxread.py:295-362)."""
+    import glob
+    import warnings
+    from rayoptics_b200 import roa, seq, zmx
+    root = '/root/reference/src/rayoptics'
+    if not os.path.isdir(root):
+        pytest.skip('/root/reference not present')
+    files = sorted(set(f for ext in ('roa', 'seq', 'zmx', 'ZMX')
+                       for f in glob.glob(f'{root}/**/*.{ext}', recursive=True)))
+    assert len(files) >= 70
+    refused, substituted = [], set()
+    for f in files:
+        gm = seq.SubstituteGlasses()
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                opm = (roa.open_roa(f) if f.endswith('.roa') else
+                       seq.open_seq(f, glass_map=gm) if f.endswith('.seq') else zmx.open_zmx(f, glass_map=gm))
+        except NotImplementedError as e:
+            refused.append((os.path.basename(f), str(e)))
+            continue
+        substituted.update(gm.not_found)
+        sm, osp = opm.seq_model, opm.optical_spec
+        descs, n_by_wvl, wvls = T.describe_model(sm)
+        wide = bool(osp.field_of_view.is_wide_angle)
+        pt0, dir0 = osp.ray_start_from_osp(np.array([0., 0.]), osp.field_of_view.fields[0], 'rel pupil')
+        if not wide and dir0[2]*sm.z_dir[0] < 0:
+            dir0 = -dir0
+        r = oracle.trace_ray(descs, n_by_wvl[sm.index_for_wavelength(sm.central_wavelength())], pt0, dir0,
+                             _abi.make_opts(first_surf=1, last_surf=len(descs) - 2, intersect_obj=not wide))
+        assert r['status'] == 0 and r['n_seg'] == len(descs), f
+        for m in (g.medium for g in sm.gaps):
+            if getattr(m, 'label', '').startswith('not '):
+                assert m.rindex(550.0) == 1.5
+    assert [r[0] for r in refused] == ['ASL5040-UV-Zemax(ZMX).zmx'] and 'QED' in refused[0][1]
+    assert 10 < len(substituted) < 60 and 'N-BK7' not in substituted
+    # without the substitution policy an unknown catalog glass is an error, not a guess
+    with pytest.raises(KeyError, match='glass_table'):
+        seq.open_seq(f'{root}/codev/tests/ag_dblgauss.seq')
