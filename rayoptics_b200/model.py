@@ -298,6 +298,52 @@ def forward_transform(s1, zdist, s2):
     return r_cascade, t_orig
 
 
+def reverse_transform(s2, zdist, s1):
+    """rotation and translation from s2 coordinates back to s1 coordinates, the decenters applied in
+    reverse order (elem/transform.py:169-191)"""
+    t_orig = np.array([0., 0., zdist])
+    r_before_s2 = r_after_s1 = None
+    if getattr(s2, 'decenter', None):
+        r_before_s2, t_before_s2 = s2.decenter.tform_before_surf()
+        t_orig += t_before_s2
+    if getattr(s1, 'decenter', None):
+        r_after_s1, t_after_s1 = s1.decenter.tform_after_surf()
+        t_orig += t_after_s1
+    r_cascade = np.identity(3)
+    if r_before_s2 is not None:
+        r_cascade = r_before_s2.transpose()
+        t_orig = np.matmul(r_cascade, t_orig)
+        if r_after_s1 is not None:
+            r_cascade = np.matmul(r_cascade, r_after_s1.transpose())
+    elif r_after_s1 is not None:
+        r_cascade = r_after_s1.transpose()
+    return r_cascade, t_orig
+
+
+def compute_global_coords(ifcs, gaps, glo=1, origin=None):
+    """``(rot, t)`` of every interface with respect to interface ``glo`` (elem/transform.py:18-76):
+    ``rot.dot(p) + t`` takes a point from an interface's local frame to the global one --
+    what ``trace.list_ray(ray, tfrms=...)`` prints.  ``origin``: optional ``(r, t)`` from the
+    desired global origin to interface ``glo``."""
+    r0, t0 = (np.identity(3), np.array([0., 0., 0.])) if origin is None else origin
+    tfrms = [(r0, t0)]
+
+    def accumulate(indices, calc, sign):
+        r_prev, t_prev = r0, t0
+        for b4, nxt, gap in indices:
+            r, t = calc(ifcs[b4], sign*gaps[gap].thi, ifcs[nxt])
+            t_new = np.matmul(r_prev, t) + t_prev
+            r_new = np.matmul(r_prev, r)
+            tfrms.append((r_new, t_new))
+            r_prev, t_prev = r_new, t_new
+
+    if glo > 0:                  # from the global surface back to the object surface
+        accumulate([(i, i - 1, i - 1) for i in range(glo, 0, -1)], reverse_transform, -1)
+        tfrms.reverse()
+    accumulate([(i, i + 1, i) for i in range(glo, len(ifcs) - 1)], forward_transform, +1)
+    return tfrms
+
+
 def compute_local_transforms(ifcs, gaps):
     """elem/transform.py:79-107, forward direction: ``(r.T, t)`` per interface"""
     tfrms = []
@@ -633,7 +679,18 @@ class SequentialModel:
         else:
             self.lcl_tfrms = [(np.identity(3), np.array([0., 0., g.thi])) for g in self.gaps]
             self.lcl_tfrms.append((np.identity(3), np.array([0., 0., 0.])))
+        self._gbl_tfrms = None
         self._version += 1
+
+    @property
+    def gbl_tfrms(self):
+        """global coordinates of the interfaces w.r.t. interface 1 (seq/sequential.py:659; lazily)"""
+        if getattr(self, '_gbl_tfrms', None) is None:
+            self._gbl_tfrms = compute_global_coords(self.ifcs, self.gaps, 1)
+        return self._gbl_tfrms
+
+    def compute_global_coords(self, glo=1, origin=None):
+        return compute_global_coords(self.ifcs, self.gaps, glo, origin)
 
     def path(self, wl=None, start=None, stop=None, step=1):
         """Iterator of ``(Intfc, Gap, Tfrm, Indx, Zdir)`` (seq/sequential.py:149-202)."""

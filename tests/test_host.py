@@ -517,6 +517,15 @@ def test_local_transforms_equal_the_references():
             assert np.array_equal(ra, rb) and np.array_equal(ta, tb)
             assert ra.flags['C_CONTIGUOUS'] == rb.flags['C_CONTIGUOUS']
             assert ra.flags['F_CONTIGUOUS'] == rb.flags['F_CONTIGUOUS']
+        # global coordinates w.r.t. a random interface, with and without an origin transform
+        seq.z_dir = [1]*(n - 1)
+        glo = int(rng.integers(0, n - 1))
+        origin = None if trial % 2 else (M.euler2mat_rxyz(0.1, -0.2, 0.05), np.array([1., -2., 3.]))
+        mine = M.compute_global_coords(own, gaps, glo, origin)
+        theirs = RT.compute_global_coords(seq, glo, origin)
+        assert len(mine) == len(theirs) == n
+        for (ra, ta), (rb, tb) in zip(mine, theirs):
+            assert np.array_equal(ra, rb) and np.array_equal(ta, tb)
 
 
 def test_builtin_glass_table():
