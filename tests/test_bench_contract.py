@@ -32,3 +32,34 @@ def test_other_ranks_of_the_reference_arm_stay_silent():
     p = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2'],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ''
+
+
+def test_b200_arm_line_on_the_dry_run_engine():
+    """The B200 arm's host code end to end (tests/dry_bench.py: CUDA entry points replaced by the
+    oracle-backed stand-in): the JSON line carries every key of the bench contract, both step
+    submission modes."""
+    for extra, mode in ((['--no-graph'], 'eager launches'), ([], 'one CUDA graph replay per step')):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'dry_bench.py'), '--steps', '2', '--warmup',
+                            '1', '--num', '24'] + extra, capture_output=True, text=True, timeout=900, cwd=ROOT)
+        assert p.returncode == 0, p.stderr[-3000:]
+        line = json.loads(p.stdout.strip().splitlines()[-1])
+        for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+                  'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'e2e', 'gpu_launches',
+                  'roofline', 'cpu_baseline'):
+            assert k in line, k
+        assert line['steps'] == 2 and line['warmup'] >= 3 and line['n_gpus'] == 1 and line['dtype'] == 'f64'
+        assert line['scaling'] == 'weak' and line['vs_baseline'] is None and line['higher_is_better'] is True
+        assert 'workload' in line['config'] and 'model' not in line['config']
+        assert set(line['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'}
+        assert line['e2e']['h2d_bytes_per_step'] > 0 and line['e2e']['d2h_bytes_per_step'] >= 16*3604
+        roof = line['roofline']
+        for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
+            assert k in roof, k
+        assert roof['bound'] == 'fp64' and roof['unit'] == 'TFLOP/s' and roof['hbm']['unit'] == 'GB/s'
+        assert abs(roof['frac'] - roof['achieved']/roof['peak']) < 1e-12
+        cb = line['cpu_baseline']
+        for k in ('value', 'unit', 'cores', 'kind', 'sample'):
+            assert k in cb, k
+        assert set(line['clocks']) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
+        assert line['step_submission'].startswith(mode)
+        assert line['parity_vs_reference']['bit_identical_p_d_op'] is True
