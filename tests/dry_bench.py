@@ -43,6 +43,18 @@ def _capture(graph):
 
 torch.cuda.Event, torch.cuda.CUDAGraph, torch.cuda.graph = _Event, _Graph, _capture
 
+import torch.distributed as dist  # noqa: E402
+
+_init = dist.init_process_group
+
+
+def _init_gloo(backend=None, **kw):              # multi-rank runs: gloo on CPU tensors
+    kw.pop('device_id', None)
+    return _init('gloo', **kw)
+
+
+dist.init_process_group = _init_gloo
+
 from rayoptics_b200 import engine as E      # noqa: E402
 
 E.measure_fp64_peak = lambda device=0: 34.0

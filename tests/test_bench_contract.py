@@ -63,3 +63,30 @@ def test_b200_arm_line_on_the_dry_run_engine():
         assert set(line['clocks']) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
         assert line['step_submission'].startswith(mode)
         assert line['parity_vs_reference']['bit_identical_p_d_op'] is True
+
+
+def test_b200_arm_two_ranks_on_the_dry_run_engine():
+    """world size 2 over gloo (dry-run engine): the eager multi-rank step loop with its asynchronous
+    all-gather + combine, max-over-ranks timing and the shard mode's equal-work ranges produce
+    ONE line, from rank 0, with whole-job ray counts."""
+    import socket
+    for mode, rays, scaling in (('replica', 2*5184, 'weak'), ('shard', 5184, 'strong')):
+        with socket.socket() as s:
+            s.bind(('127.0.0.1', 0))
+            port = s.getsockname()[1]
+        procs = []
+        for r in range(2):
+            env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1',
+                       MASTER_PORT=str(port))
+            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, 'tests', 'dry_bench.py'), '--gpus', '2',
+                                           '--steps', '3', '--warmup', '1', '--num', '24', '--mode', mode],
+                                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, env=env))
+        outs = [p.communicate(timeout=600) for p in procs]
+        assert all(p.returncode == 0 for p in procs), outs[0][1][-2000:] + outs[1][1][-2000:]
+        assert outs[1][0].strip() == ''
+        line = json.loads(outs[0][0].strip().splitlines()[-1])
+        assert line['n_gpus'] == 2 and line['scaling'] == scaling and line['steps'] == 3
+        assert line['config']['rays_per_step'] == rays and line['step_submission'] == 'eager launches'
+        assert line['rank_imbalance']['kernel_ms_max_over_ranks'] >= line['rank_imbalance']['kernel_ms_min_over_ranks']
+        assert (line['rank_imbalance']['shard_balance'] is not None) == (mode == 'shard')
+        assert line['e2e']['value'] > 0 and 'cpu_baseline' not in line
