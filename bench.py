@@ -16,8 +16,10 @@ Multi-GPU (`--gpus N` under torchrun):
   --mode shard              strong scaling: the grid's chunk space (field-major, then
                             wavelength, then pupil rows) is cut into N contiguous ranges,
                             one per rank (parallel.shard_chunks); value = rays / max-rank time
-In both the only collective is the all-gather of the [n_tiles, 16] spot sums, issued on a
-side stream together with its one-launch combine.
+In both the only collective is the all-gather of the [n_tiles, 16] spot sums; the sums of
+`--gather-every` K consecutive steps (default 8) travel in ONE asynchronous
+all_gather_into_tensor (NCCL's stream) and are combined by one rt_combine_summaries launch, so
+every step's combined sums exist before the timed region ends at 1/K of the collective count.
 
   python bench.py --gpus N --steps K --warmup W            (this repo's engine)
   python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the UNMODIFIED Python
@@ -70,6 +72,8 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager step loop instead of CUDA graph replay')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--gather-every', type=int, default=8,
+                    help='multi-GPU: steps whose spot sums share one all-gather (1 = a collective per step)')
     args = ap.parse_args()
     args.baseline_num = WORKLOADS[args.model][0]
     if args.num is None:
@@ -382,7 +386,8 @@ def config_dict(args, opm, grid, world):
             'check_apertures': True,
             'output': 'last segment p,d + op + status + fail_surf (64 B/ray) + transverse '
                       'aberration (16 B/ray) + per-(field,wvl) spot sums',
-            'parallelism': mode + ', one all-gather of the [n_tiles,16] spot sums per step',
+            'parallelism': mode + (f', the [n_tiles,16] spot sums of every {max(1, min(args.gather_every, args.steps))} steps '
+                                   'all-gathered together' if world > 1 else ''),
             'l2': 'no HBM input is re-read (start rays are generated on-chip); each step writes '
                   f'{n_rays*80/1e6:.0f} MB of results per grid (L2: 126 MB)'}
 
@@ -522,21 +527,37 @@ def run_b200(args):
         for k in range(args.steps):
             graph.replay()
     else:
-        pending, combined = None, None
+        pending, combined, n_gathers = None, None, 0
+        if world > 1:
+            # spot sums of K consecutive steps share one all-gather: two staging blocks alternate, a
+            # block is re-used only after the collective that read it has been waited for
+            K = max(1, min(args.gather_every, args.steps))
+            n_t = grid.n_tiles
+            stage = [torch.empty((K, n_t, E.RT_SUMMARY_DOUBLES), dtype=torch.float64, device=dev)
+                     for _ in range(2)]
+            which, slot = 0, 0
         for k in range(args.steps):
             trace()
             if world > 1:
-                # the all-gather of step k runs on NCCL's stream while step k+1 traces; every
-                # step's combined summary exists before the region ends
-                if pending is not None:
-                    combined = pending.result()
-                pending = P.gather_summaries(res.summary, async_op=True)
+                stage[which][slot].copy_(res.summary)
+                slot += 1
+                if slot == K or k == args.steps - 1:
+                    if pending is not None:
+                        combined = pending.result()       # [slots * n_tiles, 16]: per-step combined sums
+                    pending = P.gather_summaries(stage[which][:slot].reshape(slot*n_t, -1), async_op=True)
+                    n_gathers += 1
+                    which, slot = 1 - which, 0
         if pending is not None:
             combined = pending.result()
     e_last.record()
     barrier()
     wall = time.perf_counter() - t0
     launches = (launches_per_step*args.steps if graph is not None else E.launch_count() - launches0)
+    gather_ok = None
+    if world > 1 and combined is not None:
+        # every rank holds the same combined sums; the ray counts of the last step add up to the job
+        last = combined.reshape(-1, grid.n_tiles, E.RT_SUMMARY_DOUBLES)[-1]
+        gather_ok = bool(int(last[:, 0:5].sum().item()) == n_job)
     dev_ms = e_first.elapsed_time(e_last)
     t = torch.tensor([dev_ms, wall*1e3, kern_ms], dtype=torch.float64, device=dev)
     tmin = t.clone()
@@ -654,6 +675,10 @@ def run_b200(args):
                                     if graph is not None else 'eager launches'),
                 'roofline': roof,
                 'rank_imbalance': (dict(imbalance, shard_balance=balance) if world > 1 else None),
+                'collectives': (None if world == 1 else
+                                {'all_gathers_in_timed_region': n_gathers, 'steps_per_all_gather': K,
+                                 'payload_bytes_per_rank_per_gather': int(K*grid.n_tiles*E.RT_SUMMARY_DOUBLES*8),
+                                 'last_combined_ok': gather_ok}),
                 'full_ray_regime': None if full_ray is None else dict(
                     full_ray, frac_of_hbm_peak=full_ray['achieved_gbs']/hbm_peak),
                 'rays_ok_frac': float(fl[1]/fl[2])}

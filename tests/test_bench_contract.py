@@ -90,3 +90,6 @@ def test_b200_arm_two_ranks_on_the_dry_run_engine():
         assert line['rank_imbalance']['kernel_ms_max_over_ranks'] >= line['rank_imbalance']['kernel_ms_min_over_ranks']
         assert (line['rank_imbalance']['shard_balance'] is not None) == (mode == 'shard')
         assert line['e2e']['value'] > 0 and 'cpu_baseline' not in line
+        c = line['collectives']            # 3 steps, default --gather-every 8: one all-gather for all of them
+        assert c == {'all_gathers_in_timed_region': 1, 'steps_per_all_gather': 3,
+                     'payload_bytes_per_rank_per_gather': 3*9*16*8, 'last_combined_ok': True}
