@@ -567,3 +567,9 @@ def iterate_ray_raw(pthlist, ifcx, xy_target, pt0, d0, obj2pup_dist, eprad, wvl,
     from . import vigcalc
     return vigcalc.iterate_ray_raw(pthlist, ifcx, xy_target, pt0, d0, obj2pup_dist, eprad, wvl,
                                    not_wa, **kwargs)
+
+
+def apply_paraxial_vignetting(opt_model):
+    """trace.py:643-657, see ``vigcalc.apply_paraxial_vignetting``"""
+    from . import vigcalc
+    return vigcalc.apply_paraxial_vignetting(opt_model)

@@ -452,6 +452,45 @@ def _surface_od(ifc):
     return od if cas else ifc.max_aperture
 
 
+def paraxial_vignetting(opt_model, rel_fov=1):
+    """Vignetting factors from the paraxial axial / chief rays and the surface apertures, no real
+    ray involved (ParaxialModel.paraxial_vignetting, parax/paraxialdesign.py:1023-1050):
+    ``((min lower ratio, interface), (min upper ratio, interface))``."""
+    from .firstorder import HT
+    sm = opt_model.seq_model
+    fod = opt_model.optical_spec.fod
+    ax, pr = fod.ax_ray, fod.pr_ray
+    min_vly, min_vuy = (1, None), (1, None)
+    for i, ifc in enumerate(sm.ifcs[:-1]):
+        y = ax[i][HT]
+        if y == 0:
+            continue
+        ybar = rel_fov*pr[i][HT]
+        ratio = (_surface_od(ifc) - abs(ybar))/abs(y)
+        if ratio <= 0:
+            continue
+        if ybar <= 0 and ratio < min_vly[0]:
+            min_vly = ratio, i
+        if ybar >= 0 and ratio < min_vuy[0]:
+            min_vuy = ratio, i
+    return min_vly, min_vuy
+
+
+def apply_paraxial_vignetting(opt_model):
+    """set ``vly`` / ``vuy`` of every field from ``paraxial_vignetting`` (raytr/trace.py:643-657)"""
+    fov = opt_model.optical_spec.field_of_view
+    max_field, _ = fov.max_field()
+    for fld in fov.fields:
+        rel_fov = math.sqrt(fld.x**2 + fld.y**2)
+        if not fov.is_relative and max_field != 0:
+            rel_fov = rel_fov/max_field
+        min_vly, min_vuy = paraxial_vignetting(opt_model, rel_fov)
+        if min_vly[1] is not None:
+            fld.vly = 1 - min_vly[0]
+        if min_vuy[1] is not None:
+            fld.vuy = 1 - min_vuy[0]
+
+
 def set_stop_aperture(opm, trace_fn=None, **engine):
     """Set the aperture of the stop surface to satisfy the pupil specification, then recompute
     the vignetting (vigcalc.py:104-115)."""

@@ -841,3 +841,39 @@ def test_iterate_ray_raw_equals_the_references(name, fi):
         assert rr_g[1] is None and np.array_equal(rr_w.pkg.ray[-1][0], rr_g[0][0][-1][0])
     got, rr = V.iterate_ray_raw(sm.path(wvl), None, np.array([0.1, 0.2]), pt0, d0, *args)
     assert np.array_equal(got, [0.1, 0.2]) and rr is None
+
+
+@needs_ref
+@pytest.mark.parametrize('name', ['dblgauss', 'triplet', 'rc', 'cellphone'])
+def test_paraxial_vignetting_equals_the_references(name):
+    """vigcalc.paraxial_vignetting / apply_paraxial_vignetting against the reference's METHOD TEXT
+    (parax/paraxialdesign.py:1023-1050 -- the module needs opticalglass to import) and
+    rayoptics.raytr.trace.apply_paraxial_vignetting run on shims of the same paraxial data."""
+    import ast
+    from oracle import ref_model, ref_harness as rh
+    from rayoptics_b200 import vigcalc as V
+    RT, RA = ref_model.modules()
+    src = open('/root/reference/src/rayoptics/parax/paraxialdesign.py').read()
+    cls = [n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == 'ParaxialModel'][0]
+    fn = [f for f in cls.body if isinstance(f, ast.FunctionDef) and f.name == 'paraxial_vignetting'][0]
+    ns = dict(mc=type('mc', (), {'ht': 0, 'slp': 1}))
+    exec(ast.get_source_segment(src, fn), ns)
+    a, b = load_model(name), load_model(name)
+    for m in (a, b):                                   # tighter apertures so that something vignettes
+        for ifc in m.seq_model.ifcs[1:-1]:
+            ifc.set_max_aperture(0.8*ifc.max_aperture)
+    H = ref_model.HybridModel(a)
+    for ref_ifc, ifc in zip(H.seq_model.ifcs, a.seq_model.ifcs):
+        ref_ifc.set_max_aperture(ifc.max_aperture)
+    fod = a.optical_spec.fod
+    pm = type('PM', (), {})()
+    pm.seq_model, pm.ax, pm.pr = H.seq_model, fod.ax_ray, fod.pr_ray
+    pm.paraxial_vignetting = lambda rel_fov=1: ns['paraxial_vignetting'](pm, rel_fov)
+    for rel in (0.0, 0.5, 1.0):
+        assert pm.paraxial_vignetting(rel) == V.paraxial_vignetting(b, rel)
+    H.parax_model = pm
+    RT.apply_paraxial_vignetting(H)
+    TR.apply_paraxial_vignetting(b)
+    got = [(f.vly, f.vuy) for f in b.optical_spec.field_of_view.fields]
+    assert [(f.vly, f.vuy) for f in a.optical_spec.field_of_view.fields] == got
+    assert any(v != 0 for pair in got for v in pair)
