@@ -35,6 +35,12 @@ class HybridSeq:
             self._paths[wl] = p
         return iter(self._paths[wl])
 
+    def reverse_path(self, start=None, stop=None, step=-1, wl=None):
+        """the mirror's image-to-object path with the reference's interface objects in it"""
+        mine = {id(seg[0]): ifc for seg, ifc in zip(self.sm.path(), self.ifcs)}
+        return iter([[mine[id(seg[0])]] + list(seg[1:])
+                     for seg in self.sm.reverse_path(start, stop, step, wl)])
+
     def get_num_surfaces(self):
         return self.sm.get_num_surfaces()
 

@@ -344,12 +344,22 @@ def compute_global_coords(ifcs, gaps, glo=1, origin=None):
     return tfrms
 
 
-def compute_local_transforms(ifcs, gaps):
-    """elem/transform.py:79-107, forward direction: ``(r.T, t)`` per interface"""
+def compute_local_transforms(ifcs, gaps, step=1):
+    """elem/transform.py:79-107: ``(r.T, t)`` per interface, in path order (``step=1``) or -- for
+    paths traced from the image back to the object -- from the last interface to the first
+    (``step=-1``, thicknesses negated, decenters undone in reverse order)"""
     tfrms = []
-    for i in range(len(ifcs) - 1):
-        r, t = forward_transform(ifcs[i], gaps[i].thi, ifcs[i + 1])
-        tfrms.append((r.transpose(), t))
+    n = len(ifcs)
+    if step == 1:
+        for i in range(n - 1):
+            r, t = forward_transform(ifcs[i], gaps[i].thi, ifcs[i + 1])
+            tfrms.append((r.transpose(), t))
+    elif step == -1:
+        for i in range(n - 1, 0, -1):
+            r, t = reverse_transform(ifcs[i], -gaps[i - 1].thi, ifcs[i - 1])
+            tfrms.append((r.transpose(), t))
+    else:
+        raise ValueError('step must be 1 or -1')
     tfrms.append((np.identity(3), np.array([0., 0., 0.])))
     return tfrms
 
@@ -703,6 +713,25 @@ class SequentialModel:
                                      self.lcl_tfrms[start:stop:step],
                                      rndx,
                                      self.z_dir[start:stop:step])))
+
+    def reverse_path(self, start=None, stop=None, step=-1, wl=None):
+        """Iterator of path tuples from the image surface back to the object
+        (seq/sequential.py:204-253 for the whole model, ``start = len(ifcs)``): the interfaces in
+        reverse order, each with the gap that FOLLOWS it on the way back, the reverse local
+        transform, that gap's index and the negated propagation direction."""
+        if step != -1 or stop is not None or (start is not None and start < len(self.ifcs) - 1):
+            raise NotImplementedError('reverse_path: the whole model, image to object')
+        if wl is None:
+            wl = self.central_wavelength()
+        wi = self.index_for_wavelength(wl)
+        n = len(self.ifcs)
+        tfrms = compute_local_transforms(self.ifcs, self.gaps, step=-1)
+        path = []
+        for i in range(n):
+            g = n - 2 - i                     # gap between interface n-1-i and the one before it
+            path.append((self.ifcs[n - 1 - i], self.gaps[g] if g >= 0 else None, tfrms[i],
+                         self.rndx[g][wi] if g >= 0 else None, -self.z_dir[g] if g >= 0 else None))
+        return iter(path)
 
     # -- analysis drivers of the reference's SequentialModel (seq/sequential.py:1006-1135):
     #    same arguments and return shapes, rays traced in one launch per (field, wavelength)

@@ -187,6 +187,22 @@ class OpticalSpecs:
         fod = self.fod
         obj2enp_dist = fod.obj_dist + fod.enp_dist
         pt1 = np.array([0., 0., obj2enp_dist])
+        if obj_img_key == 'image' and value_key == 'real height':
+            # opticalspec.py:1018-1034,1060-1075: the real chief ray traced back from the image
+            # point; the pupil offset it implies becomes the field's aim info (side effect kept)
+            from .wideangle import eval_real_image_ht
+            (obj_pt, obj_dir), z_enp = eval_real_image_ht(self.opt_model, fld,
+                                                          self.spectral_region.central_wvl,
+                                                          trace_raw_fn=getattr(self, '_trace_raw_fn', None))
+            if fov.is_wide_angle:
+                fld.aim_info = z_enp
+            else:
+                del_z = fod.enp_dist - z_enp
+                if abs(obj_dir[2]) < 1e-14:
+                    fld.aim_info = np.array([0., 0.])
+                else:
+                    fld.aim_info = del_z*np.array([obj_dir[0]/obj_dir[2], obj_dir[1]/obj_dir[2]])
+            return obj_pt, obj_dir
         if self.conjugate_type('object') == 'infinite':
             if obj_img_key == 'image':
                 max_field_ang = math.atan(fod.pr_slp0)

@@ -257,6 +257,44 @@ def find_z_enp(opt_model, stop_idx, z_enp_0, fld, wvl, trace_fn=None, **kwargs):
     return np.array([0., 0., z_enp]), last['rr'], results
 
 
+def eval_real_image_ht(opt_model, fld, wvl, trace_raw_fn=None):
+    """Object-space chief ray of a field given as a REAL image height (wideangle.py:620-664): the
+    chief ray is traced backwards, from the image point through the centre of the stop (iterated
+    on the reverse path, ``vigcalc.iterate_ray_raw``), and leaves the first surface towards the
+    object.  Returns ``((object point, direction), z_enp)`` -- the implementation of
+    ``obj_coords`` for ('image', 'real height') fields."""
+    from . import vigcalc
+    sm, osp = opt_model['seq_model'], opt_model['optical_spec']
+    fov = osp['fov']
+    fod = opt_model['analysis_results']['parax_data'].fod
+    not_wa = not fov.is_wide_angle
+    stop_idx = 1 if sm.stop_surface is None else sm.stop_surface
+    ifcx = len(sm.ifcs) - stop_idx - 1                    # the stop, counted from the image
+    rpath_list = list(sm.reverse_path(wl=wvl, start=len(sm.ifcs), stop=None, step=-1))
+    obj2pup_dist = fod.exp_dist - fod.img_dist            # image surface -> exit pupil
+    p_exp = np.array([0, 0, obj2pup_dist])
+    p_i = np.array([fld.x, fld.y, 0])
+    if fov.is_relative:
+        p_i = p_i*fov.value
+    v = p_exp - p_i
+    d_i = v/np.linalg.norm(v)
+    start_coords, rrev_cr = vigcalc.iterate_ray_raw(rpath_list, ifcx, [0., 0.], p_i, d_i, obj2pup_dist,
+                                                    fod.exp_radius, wvl, not_wa,
+                                                    trace_raw_fn=trace_raw_fn)
+    ray = rrev_cr[0][0]
+    p_k, d_k = ray[-2][0], ray[-2][1]                     # at the first surface, heading back
+    p_k01 = np.sqrt(p_k[0]**2 + p_k[1]**2)
+    d_o = -d_k
+    d_k01 = np.sqrt(d_k[0]**2 + d_k[1]**2)
+    z_enp = fod.enp_dist if d_k01 == 0. else p_k[2] + p_k01*d_o[2]/d_k01
+    p_o = ray[-1][0]
+    if osp.conjugate_type('object') == 'infinite':
+        obj2enp_dist = fod.obj_dist + z_enp
+        enp_pt = np.array([0., 0., obj2enp_dist])
+        p_o = enp_pt + obj2enp_dist*d_k
+    return (p_o, d_o), z_enp
+
+
 def eval_z_enp_curve(opm, printout=True, trace_fn=None, num_fields=21):
     """the z position of the real entrance pupil across the field of view (wideangle.py:667-705,
     ('object', 'angle') fields): ``(fields, object angles, image heights, z_enps)``."""

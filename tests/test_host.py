@@ -517,6 +517,13 @@ def test_local_transforms_equal_the_references():
             assert np.array_equal(ra, rb) and np.array_equal(ta, tb)
             assert ra.flags['C_CONTIGUOUS'] == rb.flags['C_CONTIGUOUS']
             assert ra.flags['F_CONTIGUOUS'] == rb.flags['F_CONTIGUOUS']
+        back = M.compute_local_transforms(own, gaps, step=-1)          # image -> object paths
+        theirs_back = RT.compute_local_transforms(seq, None, -1)
+        assert len(back) == len(theirs_back) == n
+        for (ra, ta), (rb, tb) in zip(back, theirs_back):
+            assert np.array_equal(ra, rb) and np.array_equal(ta, tb)
+            assert ra.flags['C_CONTIGUOUS'] == rb.flags['C_CONTIGUOUS']
+            assert ra.flags['F_CONTIGUOUS'] == rb.flags['F_CONTIGUOUS']
         # global coordinates w.r.t. a random interface, with and without an origin transform
         seq.z_dir = [1]*(n - 1)
         glo = int(rng.integers(0, n - 1))

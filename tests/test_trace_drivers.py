@@ -877,3 +877,110 @@ def test_paraxial_vignetting_equals_the_references(name):
     got = [(f.vly, f.vuy) for f in b.optical_spec.field_of_view.fields]
     assert [(f.vly, f.vuy) for f in a.optical_spec.field_of_view.fields] == got
     assert any(v != 0 for pair in got for v in pair)
+
+
+def oracle_trace_raw_fn(path, pt0, dir0, wvl, **kw):
+    """trace_raw_fn= seam (an explicit path list, e.g. a reverse path) fed by the oracle"""
+    from oracle import rt_oracle
+    from rayoptics_b200 import raytrace as RT
+    segs = list(path)
+    descs, ns = T.describe_path(segs)
+    opts = {k: v for k, v in kw.items() if k in TR._TRACE_RAW_KEYS}
+    r = rt_oracle.trace_ray(descs, ns, np.array(pt0, dtype=float), np.array(dir0, dtype=float),
+                            _abi.make_opts(**opts))
+    full = np.full((len(descs), 10), np.nan)
+    full[:r['n_seg']] = r['ray']
+    pkg, err = RT.package_ray(segs, full, r['op'], r['status'], r['fail_surf'], r['n_seg'], wvl)
+    if err is not None:
+        raise err
+    return pkg
+
+
+def _real_height_model(name):
+    """a fixture re-specified by REAL image heights: ('image', 'real height') fields at the
+    heights its own chief rays reach"""
+    opm = load_model(name)
+    osp, sm = opm.optical_spec, opm.seq_model
+    sm.ifcs[0].interact_mode = 'dummy'         # as in every reference OpticalModel (sequential.py:600)
+    wvl = sm.central_wavelength()
+    hts = []
+    for f in osp.field_of_view.fields:
+        f.aim_info = None
+        pkg = TR.trace_base(opm, np.array([0., 0.]), f, wvl, tracer=oracle_tracer)
+        hts.append(pkg[0][-1][0][:2].copy())
+    fov = osp.field_of_view
+    fov.key, fov.is_relative = ('image', 'real height'), False
+    for f, h in zip(fov.fields, hts):
+        f.x, f.y, f.aim_info = float(h[0]), float(h[1]), None
+    fov.value = max(abs(h[1]) for h in hts)
+    return opm, hts
+
+
+@needs_ref
+@pytest.mark.parametrize('name', ['dblgauss', 'triplet', 'relay_fno', 'cellphone'])
+def test_real_image_height_fields_equal_the_references(name):
+    """('image', 'real height') fields (Zemax FTYP 3): wideangle.eval_real_image_ht -- the chief ray
+    iterated backwards through the stop centre on SequentialModel.reverse_path -- against the
+    reference's own eval_real_image_ht (its iterate_ray_raw, its trace_raw on reference surfaces in
+    the reversed path); then obj_coords / ray_start_from_osp: the forward chief ray lands on the
+    requested image height."""
+    import importlib
+    from oracle import ref_model
+    from rayoptics_b200 import wideangle as W
+    ref_model.modules()
+    RW = importlib.import_module('rayoptics.raytr.wideangle')
+    (a, hts), (b, _) = _real_height_model(name), _real_height_model(name)
+    H = ref_model.HybridModel(a)
+    wvl = a.seq_model.central_wavelength()
+    b.optical_spec._trace_raw_fn = oracle_trace_raw_fn
+    for fa, fb, h in zip(a.optical_spec.field_of_view.fields, b.optical_spec.field_of_view.fields, hts):
+        (pw, dw), zw = RW.eval_real_image_ht(H, fa, wvl)
+        (pg, dg), zg = W.eval_real_image_ht(b, fb, wvl, trace_raw_fn=oracle_trace_raw_fn)
+        assert np.array_equal(pw, pg) and np.array_equal(dw, dg) and zw == zg
+        # forward: the start ray built from obj_coords (which stores the implied aim point) hits h
+        if name == 'cellphone' and fb is b.optical_spec.field_of_view.fields[-1]:
+            continue     # the reverse secant iteration runs away at this lens' extreme field -- in the
+                         # reference too (same numbers above); nothing to check forwards
+        pkg = TR.trace_base(b, np.array([0., 0.]), fb, wvl, tracer=oracle_tracer)
+        assert fb.aim_info is not None
+        assert np.abs(pkg[0][-1][0][:2] - h).max() < 2e-6*max(1.0, np.abs(h).max())
+        stop = b.seq_model.stop_surface
+        assert np.abs(pkg[0][stop][0][:2]).max() < 1e-3          # the reverse iteration stops at scipy newton's default tolerance
+    # the batched start rays (one reverse iteration per FIELD, then whole grids) are the per-ray ones
+    from oracle import rt_oracle
+    osp, sm = b.optical_spec, b.seq_model
+    flds = osp.field_of_view.fields[:-1] if name == 'cellphone' else osp.field_of_view.fields
+    recs, eprad, z_pupil = osp.grid_fields(flds)
+    px = np.array([-0.7, 0.0, 0.4, 1.0])
+    spec = E.PupilGridSpec(recs, [0], px, px, eprad, z_pupil, apply_vignetting=True, flip_z_dir=sm.z_dir[0])
+    p, d, wv, _ = rt_oracle.grid_start_rays(spec.c_spec(), 0, spec.n_rays)
+    k = 0
+    for fld in flds:
+        for x in px:
+            for y in px:
+                pt0, dir0 = osp.ray_start_from_osp(fld.apply_vignetting(np.array([x, y])), fld, 'rel pupil')
+                if dir0[2]*sm.z_dir[0] < 0:
+                    dir0 = -dir0
+                assert np.array_equal(p[:, k], pt0) and np.array_equal(d[:, k], dir0)
+                k += 1
+
+
+@needs_ref
+@pytest.mark.parametrize('fname', ['zemax/tests/US05831776-1.zmx', 'zemax/tests/US08427765-1.ZMX'])
+def test_zemax_real_image_height_files(fname):
+    """The two bundled Zemax files with FTYP 3 (fields given as real image heights): the chief ray
+    of every field lands on its height and passes the stop centre."""
+    import warnings
+    from rayoptics_b200 import zmx, seq
+    opm = zmx.open_zmx('/root/reference/src/rayoptics/' + fname, glass_map=seq.SubstituteGlasses())
+    osp, sm = opm.optical_spec, opm.seq_model
+    assert tuple(osp.field_of_view.key) == ('image', 'real height')
+    osp._trace_raw_fn = oracle_trace_raw_fn
+    wvl = sm.central_wavelength()
+    for fld in osp.field_of_view.fields:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            pkg = TR.trace_base(opm, np.array([0., 0.]), fld, wvl, tracer=oracle_tracer)
+        want = np.array([fld.x, fld.y])*(osp.field_of_view.value if osp.field_of_view.is_relative else 1.0)
+        assert np.abs(pkg[0][-1][0][:2] - want).max() < 1e-4*max(1.0, np.abs(want).max()), (fld.y, pkg[0][-1][0])
+        assert np.abs(pkg[0][sm.stop_surface][0][:2]).max() < 1e-2
