@@ -40,6 +40,12 @@ def _launch(opt_model, dir0):
     return dir0, {}
 
 
+def _is_trace_error(e):
+    """a per-ray failure (TraceError of this package or of the reference, by name: trace_fn may be
+    either) as opposed to an engine failure"""
+    return any(c.__name__ == 'TraceError' for c in type(e).__mro__)
+
+
 def _stop_xy(opt_model, trace_fn, fld, wvl, aim, stop):
     osp = opt_model.optical_spec
     saved = fld.aim_info
@@ -67,7 +73,9 @@ def aim_chief_ray(opt_model, fld, wvl, trace_fn, tol=1e-13, max_iter=30):
     def f_at(v):
         try:
             return _stop_xy(opt_model, trace_fn, fld, wvl, v, stop)
-        except Exception:       # TraceError: the trial ray did not reach the stop
+        except Exception as e:  # a TraceError (this package's or the reference's, whatever the
+            if not _is_trace_error(e):      # trace_fn raises): the trial ray did not reach the stop
+                raise                       # anything else (engine, CUDA) stays loud
             return None
 
     f = f_at(x)
@@ -134,6 +142,8 @@ def trace_boundary_rays(opt_model, trace_fn, wvl=None):
             try:
                 ray, _, _ = trace_fn(sm, pt0, dir0, wvl, **kw)
             except Exception as e:       # TraceError: keep the partial ray
+                if not _is_trace_error(e):
+                    raise
                 pkg = getattr(e, 'ray_pkg', None)
                 ray = pkg[0] if pkg is not None else []
             rim.append(ray)
@@ -752,6 +762,15 @@ def iterate_ray(opt_model, ifcx, xy_target, fld, wvl, trace_fn=None, full=False)
     return (coords, rr) if full else coords      # full: the reference's return value
 
 
+def solver_gave_up(e):
+    """is this RuntimeError scipy's own (an iteration that did not converge), as opposed to an
+    engine / CUDA failure surfacing inside the residual function?  Only the former may be
+    absorbed by the searches the way the reference absorbs it; the latter must stay loud."""
+    msg = str(e)
+    return (type(e) is RuntimeError
+            and any(k in msg for k in ('onverge', 'olerance', 'erivative was zero', 'f(a) and f(b)')))
+
+
 def _iterate_to_target(trace_one, ifcx, xy_target, pt0, obj2enp_dist, eprad, not_wa, z_dir0):
     """the solver part shared by ``iterate_ray`` and ``iterate_ray_raw`` (trace.py:313-415,
     866-957): returns ``(start_coords, (ray_pkg, error) of the last ray traced)``"""
@@ -790,7 +809,9 @@ def _iterate_to_target(trace_one, ifcx, xy_target, pt0, obj2enp_dist, eprad, not
             try:
                 start_y, results = newton(y_stop_coordinate, 0., args=(xy_target[1],), disp=False,
                                           full_output=True)
-            except RuntimeError:
+            except RuntimeError as e:
+                if not solver_gave_up(e):
+                    raise
                 start_y = 0.0
             except RT.TraceError:
                 start_y = 0.0

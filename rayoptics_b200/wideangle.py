@@ -24,6 +24,11 @@ import numpy as np
 from .opticalspec import rot_v1_into_v2
 
 
+def solver_gave_up(e):
+    from .vigcalc import solver_gave_up as f
+    return f(e)
+
+
 def _is_fuzzy_zero(a):
     return abs(a) < 1e-14          # util/misc_math.py: is_fuzzy_zero
 
@@ -97,7 +102,9 @@ def find_z_enp_on_interval(opt_model, stop_idx, start_z, end_z, z_estimate, fld,
         warnings.simplefilter('ignore')
         try:
             z_enp, results = newton(eval_z_enp, z_enp, rtol=1e-7, disp=False, full_output=True)
-        except (RuntimeError, TraceError):
+        except (RuntimeError, TraceError) as e:
+            if isinstance(e, RuntimeError) and not solver_gave_up(e):
+                raise                      # an engine failure, not an iteration that gave up
             z_enp = results.root if results is not None else z_enp
         converged = bool(results.converged) if results is not None else False
         ht_at_stop = last['rr'].pkg.ray[stop_idx][0][1]
@@ -108,7 +115,9 @@ def find_z_enp_on_interval(opt_model, stop_idx, start_z, end_z, z_estimate, fld,
             try:
                 z_enp, results = brentq(eval_z_enp, start_z, end_z, rtol=1e-7, disp=False,
                                         full_output=True)
-            except RuntimeError:
+            except RuntimeError as e:
+                if not solver_gave_up(e):
+                    raise
                 z_enp = results.root
             start_coords = np.array([0., 0., z_enp])
             converged = bool(results.converged)
@@ -252,7 +261,9 @@ def find_z_enp(opt_model, stop_idx, z_enp_0, fld, wvl, trace_fn=None, **kwargs):
         warnings.simplefilter('ignore')
         try:
             z_enp, results = newton(eval_z_enp, z_enp, rtol=1e-7, disp=False, full_output=True)
-        except (RuntimeError, TraceError):
+        except (RuntimeError, TraceError) as e:
+            if isinstance(e, RuntimeError) and not solver_gave_up(e):
+                raise
             z_enp = results.root if results is not None else z_enp
     return np.array([0., 0., z_enp]), last['rr'], results
 

@@ -675,6 +675,22 @@ def test_grid_validation_accepts_every_pupil_kind_without_a_gpu(name):
     assert lib.rt_grid_create(C.byref(c), 0, C.byref(h)) == -1
 
 
+def oracle_path_tracer(path, pt0, dir0, wvl, **kw):
+    """trace_raw_fn= seam: a ray over an explicit path list by the oracle"""
+    from oracle import rt_oracle
+    from rayoptics_b200 import raytrace as RT, trace as TR
+    segs = list(path)
+    descs, ns = T.describe_path(segs)
+    r = rt_oracle.trace_ray(descs, ns, np.array(pt0, dtype=float), np.array(dir0, dtype=float),
+                            _abi.make_opts(**{k: v for k, v in kw.items() if k in TR._TRACE_RAW_KEYS}))
+    full = np.full((len(descs), 10), np.nan)
+    full[:r['n_seg']] = r['ray']
+    pkg, err = RT.package_ray(segs, full, r['op'], r['status'], r['fail_surf'], r['n_seg'], wvl)
+    if err is not None:
+        raise err
+    return pkg
+
+
 def test_every_bundled_lens_file_loads_and_traces(oracle):
     """All .roa / .seq / .zmx files in the reference tree (70) go through the readers, the table
     compiler and an axial ray by the oracle.  Catalog glasses outside glass_table.json become the
@@ -703,6 +719,7 @@ def test_every_bundled_lens_file_loads_and_traces(oracle):
             continue
         substituted.update(gm.not_found)
         sm, osp = opm.seq_model, opm.optical_spec
+        osp._trace_raw_fn = oracle_path_tracer          # real-image-height fields trace a reverse chief ray
         descs, n_by_wvl, wvls = T.describe_model(sm)
         wide = bool(osp.field_of_view.is_wide_angle)
         pt0, dir0 = osp.ray_start_from_osp(np.array([0., 0.]), osp.field_of_view.fields[0], 'rel pupil')

@@ -984,3 +984,37 @@ def test_zemax_real_image_height_files(fname):
         want = np.array([fld.x, fld.y])*(osp.field_of_view.value if osp.field_of_view.is_relative else 1.0)
         assert np.abs(pkg[0][-1][0][:2] - want).max() < 1e-4*max(1.0, np.abs(want).max()), (fld.y, pkg[0][-1][0])
         assert np.abs(pkg[0][sm.stop_surface][0][:2]).max() < 1e-2
+
+
+def test_engine_failures_stay_loud_inside_the_searches():
+    """The aiming / pupil searches absorb per-ray TraceErrors and scipy's own 'did not converge'
+    the way the reference does -- but an engine failure (EngineError, a CUDA RuntimeError) raised
+    by the tracer inside a residual function must come out, not turn into 'no solution'."""
+    from rayoptics_b200 import vigcalc as V, wideangle as W
+    opm = load_model('dblgauss')
+    sm, osp = opm.seq_model, opm.optical_spec
+    fld, wvl = osp.field_of_view.fields[2], sm.central_wavelength()
+
+    def broken(*a, **k):
+        raise _abi.EngineError('libb200rt error -2: simulated device failure')
+
+    def cuda_broken(*a, **k):
+        raise RuntimeError('CUDA error: an illegal memory access was encountered')
+    for bad in (broken, cuda_broken):
+        with pytest.raises(RuntimeError, match='simulated device failure|illegal memory'):
+            V.iterate_ray(opm, sm.stop_surface, np.array([0., 0.]), fld, wvl, trace_fn=bad)
+        with pytest.raises(RuntimeError, match='simulated device failure|illegal memory'):
+            V.aim_chief_ray(opm, fld, wvl, bad)
+        with pytest.raises(RuntimeError, match='simulated device failure|illegal memory'):
+            V.trace_boundary_rays(opm, bad)
+        with pytest.raises(RuntimeError, match='simulated device failure|illegal memory'):
+            V.iterate_ray_raw(sm.path(wvl), sm.stop_surface, np.array([0., 0.]), *osp.obj_coords(fld),
+                              1e10, 10.0, wvl, True, trace_raw_fn=bad)
+    fish = load_model('fisheye')
+    ff = fish.optical_spec.field_of_view.fields[2]
+    ff.aim_info = None
+    for bad in (broken, cuda_broken):
+        with pytest.raises(RuntimeError, match='simulated device failure|illegal memory'):
+            W.find_real_enp(fish, fish.seq_model.stop_surface, ff, fish.seq_model.central_wavelength(), trace_fn=bad)
+    assert V.solver_gave_up(RuntimeError('Failed to converge after 50 iterations, value is 1.0.'))
+    assert not V.solver_gave_up(_abi.EngineError('Failed to converge'))     # not scipy's class
