@@ -124,117 +124,136 @@ def find_z_enp_on_interval(opt_model, stop_idx, start_z, end_z, z_estimate, fld,
     return start_coords, last['rr'], converged
 
 
+class _PupilScan:
+    """Phase 1 of the real-pupil search: walk z from the paraxial pupil in steps of 1/16 of its
+    distance, remembering the first, previous and latest pupil positions whose ray reached the stop
+    (``first`` / ``prev`` / ``last``: ``(z, height at the stop)``).  The walk turns around at most
+    once -- when the second hit is farther from the stop centre than the first, or when rays
+    stop getting through -- and ends on a sign change between consecutive hits, on a failure
+    after the turn, after two misses of the first surface, or after 64 samples."""
+
+    MAX_SAMPLES = 64
+
+    def __init__(self, z_paraxial):
+        self.home = z_paraxial
+        self.step = -z_paraxial/16
+        self.z = z_paraxial
+        self.first = self.prev = self.last = None
+        self.hits = self.samples = self.front_misses = 0
+        self.turned = self.finished = False
+
+    def active(self):
+        return not self.finished and self.samples < self.MAX_SAMPLES and self.front_misses < 2
+
+    def _restart_reversed(self):
+        self.step = -self.step
+        self.z = self.home
+
+    def _turn_around(self):
+        self._restart_reversed()
+        self.turned = True
+        self.first, self.last = self.last, self.first
+
+    def hit(self, height):
+        self.hits += 1
+        if self.first is None:
+            self.first = (self.z, height)
+        self.prev, self.last = self.last, (self.z, height)
+        if self.hits > 1 and self.prev[1]*self.last[1] < 0:
+            self.finished = True                         # the stop centre lies between the last two
+        if self.hits == 2 and abs(self.first[1]) < abs(self.last[1]) and not self.turned:
+            self._turn_around()                          # walking away from the centre
+
+    def miss(self, err, missed_surface_type):
+        if isinstance(err, missed_surface_type) and err.surf == 1:
+            self._restart_reversed()
+            self.front_misses += 1
+        if self.first is not None:
+            if self.turned:
+                self.finished = True
+            else:
+                self._turn_around()
+
+    def advance(self):
+        self.z += self.step
+        if _is_fuzzy_zero(self.z):                       # never sample the first vertex itself
+            self.z = self.step/10
+        self.samples += 1
+
+
+def _bracket_stop_centre(scan, probe):
+    """Phase 2: from the scan's hits to an interval ``(a, b)`` for the root finder, plus the two
+    samples ``(lo, hi)`` the secant estimate is built from.  ``probe(z) -> (height | None, ray
+    result)``.  Returns ``(a, b, lo, hi, None)``, or ``(None, None, None, None, (z, ray result))``
+    when no ray through the stop centre exists (the answer is then the scan's last hit)."""
+    (z_a, h_a), (z_b, h_b) = scan.first, scan.last
+    step = scan.step
+    if z_a == z_b:                                       # a single hit: resample around it, finer
+        lo = hi = None
+        for z in np.linspace(z_a - step, z_b + step, num=8):
+            h, _ = probe(z)
+            if h is not None:
+                lo = (z, h) if lo is None else lo
+                hi = (z, h)
+        return lo[0], hi[0], lo, hi, None
+    if h_a*h_b < 0:                                      # the scan already straddles the centre
+        if scan.prev is not None and scan.prev[1]*h_b < 0:
+            return scan.prev[0], z_b, scan.prev, scan.last, None
+        return z_a, z_b, scan.first, scan.last, None
+    # no sign change among the hits: the centre may sit between a hit and the edge of the beam
+    height_only = lambda z: probe(z)[0]                  # noqa: E731
+    edge_b = find_edge(height_only, z_b, z_b + step, max_iter=6)
+    if edge_b[1]*h_b < 0:
+        return z_b, edge_b[0], scan.last, edge_b, None
+    edge_a = find_edge(height_only, z_a, z_a - step, max_iter=6)
+    if edge_a[1]*h_a < 0:
+        return z_a, edge_a[0], scan.first, edge_a, None
+    _, rr = probe(edge_a[0] + (edge_b[0] - edge_a[0])/2)
+    return None, None, None, None, (z_b, rr)
+
+
 def find_real_enp(opt_model, stop_idx, fld, wvl, trace_fn=None):
-    """wideangle.py:105-330 (``find_real_enp`` -> rev1): z position, relative to the first
-    interface, of the real entrance pupil of ``fld``.  Returns ``(z_enp, RayResult of the last ray)``."""
+    """z position, relative to the first interface, of the real entrance pupil of ``fld``
+    (``find_real_enp`` / ``find_real_enp_rev1``, wideangle.py:86-312): the scan and bracketing above,
+    a secant estimate from the bracketing samples, then ``find_z_enp_on_interval``.  Same samples,
+    same decisions, same arithmetic as the reference (tests/test_trace_drivers.py drives both with
+    scripted rays through every branch).  Returns ``(z_enp, RayResult of the last ray)``."""
     _, TraceMissedSurfaceError = _trace_errors()
     trace_fn = _default_trace_fn() if trace_fn is None else trace_fn
     sm, osp = opt_model['seq_model'], opt_model['optical_spec']
     fod = opt_model['analysis_results']['parax_data'].fod
     stop_idx = 1 if stop_idx is None else stop_idx
-    pt0, dir0 = osp.obj_coords(fld)
+    _, dir0 = osp.obj_coords(fld)
 
-    def at(z):
-        final_coord, rr = enp_z_coordinate(z, sm, stop_idx, dir0, fod.obj_dist, wvl, trace_fn)
-        return final_coord, rr, rr.err
+    def probe(z):
+        coord, rr = enp_z_coordinate(z, sm, stop_idx, dir0, fod.obj_dist, wvl, trace_fn)
+        return (coord[1] if rr.err is None else None), rr
 
-    def ht(z):                                  # enp_z_coordinate_wrapper
-        final_coord, rr, err = at(z)
-        return final_coord[1] if err is None else None
+    def height_at(z):                                    # zeros when the ray failed, like the reference
+        coord, rr = enp_z_coordinate(z, sm, stop_idx, dir0, fod.obj_dist, wvl, trace_fn)
+        return coord[1], rr
 
-    if fld.aim_info is not None:                # existing aim info: keep it if it is good
-        z_enp = fld.aim_info
-        final_coord, rr, err = at(z_enp)
-        if abs(final_coord[1]) < 1.48e-08:
-            return z_enp, rr
-    z_enp_0 = fod.enp_dist
-    if dir0[2] == 1:                            # axial chief ray: the paraxial pupil
-        final_coord, rr, err = at(z_enp_0)
-        return z_enp_0, rr
+    if fld.aim_info is not None:                         # a stored pupil position that still holds
+        h, rr = height_at(fld.aim_info)
+        if abs(h) < 1.48e-08:
+            return fld.aim_info, rr
+    if dir0[2] == 1:                                     # axial field: the paraxial pupil
+        return fod.enp_dist, height_at(fod.enp_dist)[1]
 
-    start_z = prev_z = end_z = None
-    del_z = -z_enp_0/16
-    z_enp = z_enp_0
-    keep_going, direction = True, 'first'
-    first_surf_misses = trial = successes = 0
-    while keep_going and trial < 64 and first_surf_misses < 2:
-        final_coord, rr, err = at(z_enp)
-        if err is None:
-            ht_at_stop = final_coord[1]
-            successes += 1
-            if start_z is None:
-                start_z = z_enp, ht_at_stop
-            prev_z = end_z
-            end_z = z_enp, ht_at_stop
-            if successes > 1:
-                if prev_z[1]*end_z[1] < 0:      # zero crossing: done
-                    keep_going = False
-            if successes == 2:
-                if abs(start_z[1]) < abs(end_z[1]):     # searching away from the crossing
-                    if direction == 'first':
-                        del_z = -del_z
-                        z_enp = z_enp_0
-                        direction = 'reverse'
-                        end_z, start_z = start_z, end_z
+    scan = _PupilScan(fod.enp_dist)
+    while scan.active():
+        h, rr = probe(scan.z)
+        if rr.err is None:
+            scan.hit(h)
         else:
-            if isinstance(err, TraceMissedSurfaceError):
-                if err.surf == 1:
-                    del_z = -del_z
-                    z_enp = z_enp_0
-                    first_surf_misses += 1
-            if start_z is not None:
-                if direction == 'first':
-                    del_z = -del_z
-                    z_enp = z_enp_0
-                    direction = 'reverse'
-                    end_z, start_z = start_z, end_z
-                else:
-                    keep_going = False
-        z_enp += del_z
-        if _is_fuzzy_zero(z_enp):               # never sample the first vertex itself
-            z_enp = del_z/10
-        trial += 1
+            scan.miss(rr.err, TraceMissedSurfaceError)
+        scan.advance()
 
-    z_enp_a, ht_at_stop_a = start_z
-    z_enp_b, ht_at_stop_b = end_z
-    if z_enp_a == z_enp_b:                      # one successful ray only: sample around it
-        start_new, end_new = z_enp_a - del_z, z_enp_b + del_z
-        start_z = end_z = None
-        for z_enp in np.linspace(start_new, end_new, num=8):
-            final_coord, rr, err = at(z_enp)
-            if err is None:
-                if start_z is None:
-                    start_z = z_enp, final_coord[1]
-                end_z = z_enp, final_coord[1]
-        a, b = start_z[0], end_z[0]
-    elif ht_at_stop_a*ht_at_stop_b < 0:         # crossing inside the interval
-        a, b = z_enp_a, z_enp_b
-        if prev_z is not None:
-            z_enp_c, ht_at_stop_c = prev_z
-            if ht_at_stop_c*ht_at_stop_b < 0:
-                start_z = prev_z
-                a, b = z_enp_c, z_enp_b
-    else:                                       # no crossing yet: look for the beam edges
-        z_enp_edge_b, ht_edge_b = find_edge(ht, z_enp_b, z_enp_b + del_z, max_iter=6)
-        if ht_edge_b*ht_at_stop_b < 0:
-            start_z = z_enp_b, ht_at_stop_b
-            end_z = z_enp_edge_b, ht_edge_b
-            a, b = z_enp_b, z_enp_edge_b
-        else:
-            z_enp_edge_a, ht_edge_a = find_edge(ht, z_enp_a, z_enp_a - del_z, max_iter=6)
-            if ht_edge_a*ht_at_stop_a < 0:
-                start_z = z_enp_a, ht_at_stop_a
-                end_z = z_enp_edge_a, ht_edge_a
-                a, b = z_enp_a, z_enp_edge_a
-            else:                               # no ray through the stop centre
-                z_enp_cntr = z_enp_edge_a + (z_enp_edge_b - z_enp_edge_a)/2
-                final_coord, rr, err = at(z_enp_cntr)
-                return z_enp_b, rr
-
-    if _is_fuzzy_zero(end_z[1] - start_z[1]):
-        z_estimate = start_z[0]
-    else:
-        z_estimate = start_z[0] - ((end_z[0] - start_z[0])/(end_z[1] - start_z[1]))*start_z[1]
+    a, b, lo, hi, no_centre = _bracket_stop_centre(scan, probe)
+    if no_centre is not None:
+        return no_centre
+    rise = hi[1] - lo[1]
+    z_estimate = lo[0] if _is_fuzzy_zero(rise) else lo[0] - ((hi[0] - lo[0])/rise)*lo[1]
     start_coords, rr, _ = find_z_enp_on_interval(opt_model, stop_idx, a, b, z_estimate, fld, wvl,
                                                  trace_fn)
     return start_coords[2], rr

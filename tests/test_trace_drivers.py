@@ -1018,3 +1018,86 @@ def test_engine_failures_stay_loud_inside_the_searches():
             W.find_real_enp(fish, fish.seq_model.stop_surface, ff, fish.seq_model.central_wavelength(), trace_fn=bad)
     assert V.solver_gave_up(RuntimeError('Failed to converge after 50 iterations, value is 1.0.'))
     assert not V.solver_gave_up(_abi.EngineError('Failed to converge'))     # not scipy's class
+
+
+@needs_ref
+def test_real_pupil_search_decisions_equal_the_references(monkeypatch):
+    """Every branch of the wide-angle pupil search (scan direction reversal, first-surface misses,
+    single success, beam edges, no crossing) against the reference's find_real_enp: both run on the
+    same SYNTHETIC 'ray' -- a scripted stop height h(z) with windows where the trace fails in
+    scripted ways -- substituted for enp_z_coordinate in the two modules.  Same z_enp, same
+    sequence of z values evaluated."""
+    import importlib
+    import warnings
+    from oracle import ref_model, ref_harness as rh
+    from rayoptics_b200 import wideangle as W, raytrace as BR
+    ref_model.modules()
+    RW = importlib.import_module('rayoptics.raytr.wideangle')
+    R = rh.ref()
+    opm = load_model('fisheye')
+    H = ref_model.HybridModel(opm)
+    stop = opm.seq_model.stop_surface
+    wvl = opm.seq_model.central_wavelength()
+    fld = opm.optical_spec.field_of_view.fields[3]
+    rng = np.random.default_rng(77)
+    n_ifc = opm.seq_model.get_num_surfaces()
+
+    def scenario():
+        z0 = opm.optical_spec.fod.enp_dist
+        zc = z0*rng.uniform(-0.6, 1.8)                       # where the chief ray crosses the stop centre
+        slope, cubic = rng.uniform(0.05, 2.0)*rng.choice([-1, 1]), rng.uniform(0, 0.02)
+        lo, hi = sorted(z0*rng.uniform(-1.5, 2.5, 2))        # window in which rays get through
+        if rng.random() < 0.3:
+            lo, hi = -1e9, 1e9
+        if rng.random() < 0.15:                              # a sliver: single success / edges
+            mid = z0*rng.uniform(0.2, 1.4)
+            lo, hi = mid - abs(z0)*0.02, mid + abs(z0)*0.02
+        if rng.random() < 0.25:                              # crossing just inside one end of the window
+            w = abs(z0)*rng.uniform(0.1, 0.6)
+            eps = abs(z0)/16*rng.uniform(0.05, 0.9)
+            lo, hi = (zc - eps, zc - eps + w) if rng.random() < 0.5 else (zc + eps - w, zc + eps)
+        kind_lo, kind_hi = rng.integers(0, 3, 2)             # 0: miss at 1, 1: miss later, 2: blocked
+        return dict(h=lambda z: slope*(z - zc) + cubic*(z - zc)**3, lo=lo, hi=hi, kinds=(kind_lo, kind_hi))
+
+    def synthetic(sc, errs, RayPkg, RayResult, log):
+        def fn(z_enp, *args):
+            log.append(float(z_enp))
+            ray = [[np.zeros(3), np.array([0., 0., 1.]), 0.0, np.array([0., 0., 1.])] for _ in range(n_ifc)]
+            if sc['lo'] < z_enp < sc['hi']:
+                ray[stop][0] = np.array([0., sc['h'](z_enp), 0.])
+                return ray[stop][0], RayResult(RayPkg(ray, 0.0, wvl), None)
+            kind = sc['kinds'][0 if z_enp <= sc['lo'] else 1]
+            if kind == 2:
+                err = errs.TraceRayBlockedError(None, np.zeros(3))
+                err.surf = 2
+            else:
+                err = errs.TraceMissedSurfaceError(None, None)
+                err.surf = 1 if kind == 0 else 3
+            err.ray_pkg = (ray[:err.surf + 1], 0.0, wvl)
+            return np.array([0., 0., 0.]), RayResult(RayPkg(ray[:err.surf + 1], 0.0, wvl), err)
+        return fn
+
+    outcomes = set()
+    for trial in range(1500):
+        sc = scenario()
+        log_r, log_m = [], []
+        monkeypatch.setattr(RW, 'enp_z_coordinate', synthetic(sc, R.traceerror, RW.RayPkg, RW.RayResult, log_r))
+        monkeypatch.setattr(W, 'enp_z_coordinate', synthetic(sc, BR, TR.RayPkg, TR.RayResult, log_m))
+        fld.aim_info = None
+        want = got = None
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            try:
+                want = RW.find_real_enp(H, stop, fld, wvl)[0]
+            except Exception as e:      # noqa: BLE001 - e.g. no successful ray at all: start_z is None
+                want = type(e).__name__
+            fld.aim_info = None
+            try:
+                got = W.find_real_enp(opm, stop, fld, wvl)[0]
+            except Exception as e:      # noqa: BLE001
+                got = type(e).__name__
+        assert log_r == log_m, (trial, sc['lo'], sc['hi'], sc['kinds'])
+        assert (want == got) or (isinstance(want, float) and np.isnan(want) and np.isnan(got)), trial
+        outcomes.add('error' if isinstance(want, str) else
+                     'crossing' if abs(sc['h'](want)) < 1e-6 else 'no crossing')
+    assert outcomes == {'error', 'crossing', 'no crossing'}
