@@ -63,18 +63,23 @@ def trace_pupil_rays(opt_model, pupils, fld, wvl, output_filter=None, rayerr_fil
     """``[trace_safe(opt_model, p, fld, wvl, output_filter, rayerr_filter, **kwargs) for p in
     pupils]`` (trace.py:159-219) with one launch.  Returns a list of ``RayResult``."""
     from . import raytrace as RT
-    if kwargs.get('pupil_type', 'rel pupil') != 'rel pupil':
-        raise NotImplementedError("pupil_type other than 'rel pupil'")
+    pupil_type = kwargs.pop('pupil_type', 'rel pupil')
     use_named_tuples = kwargs.get('use_named_tuples', False)
-    pts = np.array([np.array(p, dtype=float) for p in pupils], dtype=float).reshape(-1, 2)
-    if tracer is None:
-        table = _table_for(opt_model, table, device)
-        tracer = cuda_tracer
-    r = tracer(opt_model, table, fld, wvl, pts[:, 0].copy(), pts[:, 1].copy(), apply_vignetting,
-               kwargs)
+    if pupil_type != 'rel pupil':
+        # 'aim pt' (points on the pupil plane) / 'aim dir' (object-space directions), trace.py:291-308:
+        # the start rays are built on the host and go through one BUNDLE launch
+        r = _trace_started_rays(opt_model, pupils, fld, wvl, pupil_type, table, device,
+                                kwargs.pop('bundle_tracer', None), kwargs)
+    else:
+        pts = np.array([np.array(p, dtype=float) for p in pupils], dtype=float).reshape(-1, 2)
+        if tracer is None:
+            table = _table_for(opt_model, table, device)
+            tracer = cuda_tracer
+        r = tracer(opt_model, table, fld, wvl, pts[:, 0].copy(), pts[:, 1].copy(), apply_vignetting,
+                   kwargs)
     segs = list(opt_model.seq_model.path(wvl))
     results = []
-    for k in range(pts.shape[0]):
+    for k in range(len(r['status'])):
         pkg, err = RT.package_ray(segs, r['full'][:, :, k], float(r['op'][k]), int(r['status'][k]),
                                   int(r['fail_surf'][k]), int(r['n_seg'][k]), wvl)
         if err is not None:
@@ -102,13 +107,39 @@ def trace_pupil_rays(opt_model, pupils, fld, wvl, output_filter=None, rayerr_fil
     return results
 
 
+def _trace_started_rays(opt_model, pupils, fld, wvl, pupil_type, table, device, bundle_tracer, kwargs):
+    """start rays from ``ray_start_from_osp(pupil, fld, pupil_type)`` (no vignetting: trace.py:291-295),
+    the wide-angle / virtual-object rules of trace_base, one bundle launch.  ``bundle_tracer``: test
+    seam with the signature of ``analyses._cuda_bundle_tracer``."""
+    osp, sm = opt_model['optical_spec'], opt_model['seq_model']
+    n = len(pupils)
+    p0, d0 = np.zeros((3, n)), np.zeros((3, n))
+    kw = {k: v for k, v in kwargs.items() if k in _TRACE_RAW_KEYS}
+    kw.setdefault('first_surf', 1)
+    kw.setdefault('last_surf', sm.get_num_surfaces() - 2)
+    wide = bool(osp['fov'].is_wide_angle)
+    if wide:
+        kw['intersect_obj'] = False
+    for k, pupil in enumerate(pupils):
+        pt0, dir0 = osp.ray_start_from_osp(pupil, fld, pupil_type)
+        if not wide and dir0[2]*sm.z_dir[0] < 0:
+            dir0 = -dir0
+        p0[:, k], d0[:, k] = pt0, dir0
+    if bundle_tracer is None:
+        from .analyses import _cuda_bundle_tracer as bundle_tracer
+        table = _table_for(opt_model, table, device)
+    row = table.wvl_index(wvl) if hasattr(table, 'wvl_index') else sm.index_for_wavelength(wvl)
+    return bundle_tracer(opt_model, table, p0, d0, np.full(n, row, dtype=np.int32), kw)
+
+
 def trace_safe(opt_model, pupil, fld, wvl, output_filter, rayerr_filter, **kwargs):
     """trace.py:159-219 for one pupil point."""
     return trace_pupil_rays(opt_model, [pupil], fld, wvl, output_filter, rayerr_filter, **kwargs)[0]
 
 
 def trace_base(opt_model, pupil, fld, wvl, apply_vignetting=True, **kwargs):
-    """trace.py:253-310 for one pupil point: the ray package, or the TraceError raised."""
+    """trace.py:253-310 for one pupil point (``pupil_type``: 'rel pupil', 'aim pt', 'aim dir'): the ray
+    package, or the TraceError raised."""
     res = trace_pupil_rays(opt_model, [pupil], fld, wvl, None, 'full',
                            apply_vignetting=apply_vignetting, **kwargs)[0]
     if res.err is not None:

@@ -1101,3 +1101,44 @@ def test_real_pupil_search_decisions_equal_the_references(monkeypatch):
         outcomes.add('error' if isinstance(want, str) else
                      'crossing' if abs(sc['h'](want)) < 1e-6 else 'no crossing')
     assert outcomes == {'error', 'crossing', 'no crossing'}
+
+
+@needs_ref
+@pytest.mark.parametrize('name', ['dblgauss', 'relay_na', 'fisheye'])
+def test_aim_point_and_aim_direction_pupils(name):
+    """trace_base / trace_safe with pupil_type 'aim pt' and 'aim dir' (trace.py:253-310,
+    opticalspec.py:332-336,369-371): the reference's trace_base on the hybrid model against the
+    bundle path here, whole rays."""
+    from oracle import ref_model
+    RT, RA = ref_model.modules()
+    a, b = load_model(name), load_model(name)
+    H = ref_model.HybridModel(a)
+    wvl = a.seq_model.central_wavelength()
+    fod = a.optical_spec.fod
+    fa, fb = a.optical_spec.field_of_view.fields[1], b.optical_spec.field_of_view.fields[1]
+    angular = a.optical_spec.pupil.key[1] != 'epd'
+    if angular:
+        ptype, pupils = 'aim dir', [np.array([0.0, 0.02]), np.array([0.01, -0.015]), np.array([-0.02, 0.0])]
+    else:
+        r = fod.enp_radius
+        ptype, pupils = 'aim pt', [np.array([0.0, 0.3*r]), np.array([0.2*r, -0.4*r]), np.array([-0.5*r, 0.1*r])]
+    for pupil in pupils:
+        for check in (False, True):
+            try:
+                want = RT.trace_base(H, pupil.copy(), fa, wvl, pupil_type=ptype, check_apertures=check)
+            except Exception as e:      # noqa: BLE001 - a reference TraceError
+                want = type(e).__name__
+            try:
+                got = TR.trace_base(b, pupil.copy(), fb, wvl, pupil_type=ptype, check_apertures=check,
+                                    bundle_tracer=oracle_bundle_tracer)
+            except Exception as e:      # noqa: BLE001
+                got = type(e).__name__
+            if isinstance(want, str):
+                assert got == want
+                continue
+            assert len(want[0]) == len(got[0]) and want[1] == got[1]
+            for sw, sg in zip(want[0], got[0]):
+                assert np.array_equal(sw[0], sg[0]) and np.array_equal(sw[1], sg[1]) and sw[2] == sg[2]
+    res = TR.trace_pupil_rays(b, pupils, fb, wvl, None, 'full', pupil_type=ptype,
+                              bundle_tracer=oracle_bundle_tracer)
+    assert len(res) == 3 and all(r.pkg is not None for r in res)
