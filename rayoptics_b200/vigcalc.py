@@ -501,6 +501,18 @@ def apply_paraxial_vignetting(opt_model):
             fld.vuy = 1 - min_vuy[0]
 
 
+def set_ape(opt_model, avoid_list=None, include_list=None, bundle_fn=None):
+    """clear apertures from the existing fields and vignetting (vigcalc.py:83-99): the batched
+    ``set_clear_apertures``, then the element model -- when the model has one (an unchanged
+    ray-optics OpticalModel) -- is synchronised as the reference does"""
+    set_clear_apertures_batched(opt_model, bundle_fn, avoid_list=avoid_list, include_list=include_list)
+    try:
+        em = opt_model['em']
+    except (KeyError, TypeError, AttributeError):
+        return
+    em.sync_to_seq(opt_model['sm'])
+
+
 def set_stop_aperture(opm, trace_fn=None, **engine):
     """Set the aperture of the stop surface to satisfy the pupil specification, then recompute
     the vignetting (vigcalc.py:104-115)."""
