@@ -717,15 +717,31 @@ class SequentialModel:
     def reverse_path(self, start=None, stop=None, step=-1, wl=None):
         """Iterator of path tuples from the image surface back to the object
         (seq/sequential.py:204-253 for the whole model, ``start = len(ifcs)``): the interfaces in
-        reverse order, each with the gap that FOLLOWS it on the way back, the reverse local
-        transform, that gap's index and the negated propagation direction."""
+        reverse order, each with the gap that FOLLOWS it on the way back, the transform into the
+        next interface's frame, that gap's index and the negated propagation direction.
+
+        Transforms: the exact inverses of the forward local transforms -- forward
+        ``p' = rt (p - t)`` gives backward ``p = rt^T (p' - (-rt t))``.  Between interfaces
+        without decenters that is the reference's ``compute_local_transforms(step=-1)``
+        (``[0, 0, -thi]``, kept bit for bit); for decentered / tilted interfaces the reference's
+        ``reverse_transform`` (restated above, pinned to it) is NOT the inverse of its
+        ``forward_transform`` -- a ray turned around at the image does not come back -- so it is
+        not used here (tests/test_host.py::test_rays_retrace_themselves_on_the_reverse_path)."""
         if step != -1 or stop is not None or (start is not None and start < len(self.ifcs) - 1):
             raise NotImplementedError('reverse_path: the whole model, image to object')
         if wl is None:
             wl = self.central_wavelength()
         wi = self.index_for_wavelength(wl)
         n = len(self.ifcs)
-        tfrms = compute_local_transforms(self.ifcs, self.gaps, step=-1)
+        tfrms = []
+        for i in range(n - 1, 0, -1):                     # from interface i back to interface i-1
+            rt_f, t_f = self.lcl_tfrms[i - 1]
+            plain = (np.array_equal(rt_f, np.identity(3)) and t_f[0] == 0.0 and t_f[1] == 0.0)
+            if plain:
+                tfrms.append((np.identity(3), np.array([0., 0., -t_f[2]])))
+            else:
+                tfrms.append((np.ascontiguousarray(rt_f.T), -np.matmul(rt_f, t_f)))
+        tfrms.append((np.identity(3), np.array([0., 0., 0.])))
         path = []
         for i in range(n):
             g = n - 2 - i                     # gap between interface n-1-i and the one before it

@@ -736,3 +736,52 @@ def test_every_bundled_lens_file_loads_and_traces(oracle):
     # without the substitution policy an unknown catalog glass is an error, not a guess
     with pytest.raises(KeyError, match='glass_table'):
         seq.open_seq(f'{root}/codev/tests/ag_dblgauss.seq')
+
+
+@pytest.mark.parametrize('name', ['singlet', 'dblgauss', 'triplet', 'rc', 'cellphone', 'evenasph', 'zoom52',
+                                  'threemir', 'relay_na', 'telecentric'])
+def test_rays_retrace_themselves_on_the_reverse_path(oracle, name):
+    """Reversibility: a ray traced object -> image, turned around at the image surface and traced
+    over SequentialModel.reverse_path (reverse local transforms, negated propagation directions,
+    mirrors and tilted / decentered mirrors included) passes through the same point on every
+    interface.  Pins reverse_path / reverse_transform against the forward machinery."""
+    opm = load_model(name)
+    sm, osp = opm.seq_model, opm.optical_spec
+    sm.ifcs[0].interact_mode = 'dummy'
+    wvl = sm.central_wavelength()
+    fwd = list(sm.path(wvl))
+    rev = list(sm.reverse_path(wl=wvl, start=len(sm.ifcs)))
+    d_f, n_f = T.describe_path(fwd)
+    d_r, n_r = T.describe_path(rev)
+    n = len(fwd)
+    checked = 0
+    for fld in osp.field_of_view.fields:
+        for pupil in ([0., 0.], [0.3, -0.5], [-0.6, 0.2]):
+            pt0, dir0 = osp.ray_start_from_osp(np.array(pupil), fld, 'rel pupil')
+            if dir0[2]*sm.z_dir[0] < 0:
+                dir0 = -dir0
+            f = oracle.trace_ray(d_f, n_f, pt0, dir0, _abi.make_opts(first_surf=1, last_surf=n - 2))
+            if f['status'] != 0:
+                continue
+            last = f['ray'][-1]
+            r = oracle.trace_ray(d_r, n_r, last[0:3], -last[3:6], _abi.make_opts(first_surf=1, last_surf=n - 2))
+            assert r['status'] == 0 and r['n_seg'] == n
+            for j in range(n - 1):                 # every interface but the (possibly 1e10 away) object
+                p_f, p_r = f['ray'][n - 1 - j][0:3], r['ray'][j][0:3]
+                assert np.abs(p_f - p_r).max() < 1e-7*max(1.0, np.abs(p_f).max()), (name, j)
+            # optical path between the first and last powered surfaces is the same both ways
+            assert abs(f['op'] - r['op']) < 1e-6*max(1.0, abs(f['op']))
+            checked += 1
+    assert checked >= 3
+    if name == 'threemir':
+        # why reverse_path does not use compute_local_transforms(step=-1) -- the restatement of the
+        # reference's reverse transforms, pinned to them in test_local_transforms_equal_the_references:
+        # for decentered / tilted interfaces they are not the inverses of the forward transforms
+        ref_style = M.compute_local_transforms(sm.ifcs, sm.gaps, step=-1)
+        worst = 0.0
+        for i in range(1, n):
+            rt_f, t_f = sm.lcl_tfrms[i - 1]
+            rt_b, t_b = ref_style[n - 1 - i]
+            assert np.array_equal(rt_b, rt_f.T)
+            worst = max(worst, np.abs(t_b - (-rt_f @ t_f)).max())
+        assert worst > 10.0                        # mm
