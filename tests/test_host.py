@@ -771,6 +771,16 @@ def test_rays_retrace_themselves_on_the_reverse_path(oracle, name):
                 assert np.abs(p_f - p_r).max() < 1e-7*max(1.0, np.abs(p_f).max()), (name, j)
             # optical path between the first and last powered surfaces is the same both ways
             assert abs(f['op'] - r['op']) < 1e-6*max(1.0, abs(f['op']))
+            # the device source (general and, where the path qualifies, lean loop) on the reversed
+            # path: bit-identical to the oracle
+            from hostsim import build as HS
+            p0 = np.ascontiguousarray(last[0:3].reshape(3, 1))
+            d0 = np.ascontiguousarray(-last[3:6].reshape(3, 1))
+            for kern in [0] + ([HS.lean_kind(d_r)] if HS.lean_kind(d_r) else []):
+                h = HS.trace_bundle(d_r, np.array([n_r]), p0, d0, np.zeros(1, np.int32),
+                                    _abi.make_opts(first_surf=1, last_surf=n - 2), kernel=kern, out_kind=2)
+                assert h['status'][0] == 0 and h['op'][0] == r['op']
+                assert np.array_equal(h['full'][:, :, 0], r['ray'])
             checked += 1
     assert checked >= 3
     if name == 'threemir':
