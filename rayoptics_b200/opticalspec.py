@@ -80,6 +80,15 @@ class FieldSpec:
         for f in self.fields:
             f.fov = self
 
+    def check_is_wide_angle(self, angle_threshold=45., optical_spec=None):
+        """the importers' rule (opticalspec.py:896-905, applied by zmxread.py:288 and cmdproc.py:210):
+        object angles beyond the threshold, or real image heights with the object at infinity"""
+        if tuple(self.key) == ('image', 'real height'):
+            return bool(optical_spec is not None and optical_spec.conjugate_type('object') == 'infinite')
+        if tuple(self.key) == ('object', 'angle'):
+            return self.max_field()[0] > angle_threshold
+        return False
+
     def new_field(self, x=0.0, y=0.0, **kwargs):
         """a Field tied to this specification, not added to ``fields`` (opticalspec.py FieldSpec)"""
         return Field(x=x, y=y, fov=self, **kwargs)

@@ -326,4 +326,17 @@ def open_seq(path, glass_map=None):
                        FocusRange(surfs[-1]['thi'], 0.0))
     opm = M.OpticalModel(sm, osp, name=title or str(path).rsplit('/', 1)[-1])
     opm.dimensions = units
+    apply_wide_angle_rule(opm)
     return opm
+
+
+def apply_wide_angle_rule(opm):
+    """what both importers of the reference do last (cmdproc.py:210, zmxread.py:288):
+    ``fov.is_wide_angle = fov.check_is_wide_angle()``"""
+    osp = opm.optical_spec
+    fov = osp.field_of_view
+    wide = fov.check_is_wide_angle(optical_spec=osp)
+    if wide != bool(fov.is_wide_angle):
+        fov.is_wide_angle = wide
+        opm.update_model()
+    return wide

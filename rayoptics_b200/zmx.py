@@ -209,7 +209,10 @@ def open_zmx(path, glass_map=None):
     max_f = max((math.hypot(f.x, f.y) for f in fields), default=0.0)
     osp = OpticalSpecs(WvlSpec(wvls, ref_wl, wts if len(wts) == len(wvls) else None),
                        PupilSpec(*pupil), FieldSpec(fkey, max_f, fields), FocusRange(0.0, 0.0))
-    return M.OpticalModel(sm, osp, name=title or str(path).rsplit('/', 1)[-1])
+    opm = M.OpticalModel(sm, osp, name=title or str(path).rsplit('/', 1)[-1])
+    from .seq import apply_wide_angle_rule
+    apply_wide_angle_rule(opm)
+    return opm
 
 
 def _zmx_medium(name, glass_map):

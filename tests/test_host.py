@@ -795,3 +795,26 @@ def test_rays_retrace_themselves_on_the_reverse_path(oracle, name):
             assert np.array_equal(rt_b, rt_f.T)
             worst = max(worst, np.abs(t_b - (-rt_f @ t_f)).max())
         assert worst > 10.0                        # mm
+
+
+def test_importers_apply_the_wide_angle_rule(tmp_path):
+    """cmdproc.py:210 / zmxread.py:288: after reading, ``fov.is_wide_angle = fov.check_is_wide_angle()``
+    (opticalspec.py:896-905) -- object angles beyond 45 degrees, or real image heights with the
+    object at infinity -- which switches the start rays to the wide-angle construction."""
+    from rayoptics_b200 import seq, zmx
+    for yan, wide in ((30.0, False), (60.0, True)):
+        f = tmp_path / f'w{int(yan)}.seq'
+        f.write_text('\n'.join(['RDM', 'EPD 2', 'WL 587.6', f'YAN 0 {yan}', 'SO 0 1e11', 'S 20 2 517.642', ' STO',
+                                'S -20 30', 'SI 0 0']))
+        opm = seq.open_seq(str(f))
+        fov = opm.optical_spec.field_of_view
+        assert bool(fov.is_wide_angle) is wide and fov.check_is_wide_angle(optical_spec=opm.optical_spec) is wide
+        recs, _, _ = opm.optical_spec.grid_fields()
+        assert recs[0]['pupil_kind'] == (_abi.PUPIL_WIDE if wide else _abi.PUPIL_EPD)
+    root = '/root/reference/src/rayoptics/zemax/tests'
+    if os.path.isdir(root):
+        kw = dict(glass_map=seq.SubstituteGlasses())
+        a = zmx.open_zmx(f'{root}/US08427765-1.ZMX', **kw).optical_spec      # real heights, object at infinity
+        b = zmx.open_zmx(f'{root}/US05831776-1.zmx', **kw).optical_spec      # real heights, finite object
+        assert a.field_of_view.is_wide_angle and not b.field_of_view.is_wide_angle
+        assert a.conjugate_type('object') == 'infinite' and b.conjugate_type('object') == 'finite'
