@@ -177,6 +177,9 @@ class Circular(Aperture):
         super().__init__(**kwargs)
         self.radius = radius
 
+    def resize(self, half_size):            # set_dimension(x, y), elem/surface.py:410-411
+        self.radius = half_size
+
 
 class Rectangular(Aperture):
     def __init__(self, x_half_width=1.0, y_half_width=1.0, **kwargs):
@@ -184,12 +187,12 @@ class Rectangular(Aperture):
         self.x_half_width = x_half_width
         self.y_half_width = y_half_width
 
+    def resize(self, half_size):            # set_dimension, elem/surface.py:449-451,487-489
+        self.x_half_width = self.y_half_width = abs(half_size)
 
-class Elliptical(Aperture):
-    def __init__(self, x_half_width=1.0, y_half_width=1.0, **kwargs):
-        super().__init__(**kwargs)
-        self.x_half_width = x_half_width
-        self.y_half_width = y_half_width
+
+class Elliptical(Rectangular):
+    pass
 
 
 _APERTURE_CLASSES = {c.__name__: c for c in (Circular, Rectangular, Elliptical)}
@@ -391,7 +394,11 @@ class Surface:
         self.profile.cv = pwr/self.delta_n if self.delta_n != 0.0 else 0.0
 
     def set_max_aperture(self, max_ap):
+        """elem/surface.py:174-179: the clear apertures that are not obscurations follow"""
         self.max_aperture = max_ap
+        for ca in self.clear_apertures:
+            if not ca.is_obscuration:
+                ca.resize(max_ap)
 
     def update(self):
         self.profile.update()
@@ -645,6 +652,12 @@ class SequentialModel:
         self.z_dir = list(z_dir) if z_dir is not None else None
         self._tfrms_given = lcl_tfrms
         self._version = 0
+        # sequential.py:89: True = the interfaces carry no aperture data, clear apertures follow
+        # the boundary rays (OpticalModel.update_optical_properties).  The mirror's own files
+        # store apertures, so it is off unless a reader of a foreign format turns it on;
+        # ``input_ca_list``: interfaces whose aperture came from the file (cmdproc.py:88-94)
+        self.do_apertures = False
+        self.input_ca_list = None
         self.update_model()
 
     # -- reference API used by the hot path
@@ -1063,6 +1076,32 @@ class OpticalModel:
         self.seq_model.update_model(**kwargs)
         if self.optical_spec is not None:
             self.optical_spec.update_model(**kwargs)
+
+    def update_optical_properties(self, bundle_fn=None, do_aiming=None):
+        """The ray-traced part of the reference's ``OpticalModel.update_model`` (optical/
+        opticalmodel.py:318-354), which its importers run after reading a lens file: first-order data,
+        chief-ray aiming of every field (``OpticalSpecs.update_optical_properties``,
+        opticalspec.py:263-281) and -- when the interfaces carry no aperture data
+        (``seq_model.do_apertures``) or only some do (``input_ca_list``, cmdproc.py:88-94) --
+        clear apertures from the boundary rays of all fields (sequential.py:670-674).  All rays go
+        through bundles (``vigcalc.aim_all_fields_batched`` / ``set_clear_apertures_batched``);
+        ``bundle_fn``: test seam, default the CUDA engine.  Returns the number of interfaces whose
+        aperture was set."""
+        from . import vigcalc
+        self.update_model()
+        sm, osp = self.seq_model, self.optical_spec
+        if sm.get_num_surfaces() <= 2:
+            return 0
+        if bundle_fn is None:
+            bundle_fn = vigcalc.cuda_bundle_fn(self)
+        if osp.do_aiming if do_aiming is None else do_aiming:
+            vigcalc.aim_all_fields_batched(self, bundle_fn)
+        given = list(sm.input_ca_list or [])
+        if not (sm.do_apertures or given):
+            return 0
+        before = [ifc.max_aperture for ifc in sm.ifcs]
+        vigcalc.set_clear_apertures_batched(self, bundle_fn, avoid_list=given or None)
+        return sum(a != ifc.max_aperture for a, ifc in zip(before, sm.ifcs))
 
     def to_dict(self):
         d = {'format': 'b200rt-model-v1', 'name': self.name}

@@ -137,7 +137,7 @@ def _builtin_glass(token):
     return None
 
 
-def open_seq(path, glass_map=None):
+def open_seq(path, glass_map=None, do_update=False, bundle_fn=None):
     """Read a CODE V ``.seq`` file into an ``OpticalModel`` mirror."""
     with open(path) as f:
         text = f.read()
@@ -327,6 +327,12 @@ def open_seq(path, glass_map=None):
     opm = M.OpticalModel(sm, osp, name=title or str(path).rsplit('/', 1)[-1])
     opm.dimensions = units
     apply_wide_angle_rule(opm)
+    # cmdproc.py:196-201: any CIR input turns the automatic apertures off, the interfaces without
+    # one are then set once, around the imported ones (cmdproc.py:88-94)
+    given = [i for i, s_ in enumerate(surfs) if s_['cir'] is not None]
+    sm.do_apertures, sm.input_ca_list = (not given), (given or None)
+    if do_update:
+        opm.update_optical_properties(bundle_fn)
     return opm
 
 

@@ -43,8 +43,11 @@ def _read_text(path):
     return raw.decode('latin-1')
 
 
-def open_zmx(path, glass_map=None):
-    """Read a Zemax ``.zmx`` file into an ``OpticalModel`` mirror."""
+def open_zmx(path, glass_map=None, do_update=False, bundle_fn=None):
+    """Read a Zemax ``.zmx`` file into an ``OpticalModel`` mirror.  ``do_update``: run the ray-traced
+    part of the reference's post-import ``update_model`` (``OpticalModel.update_optical_properties``:
+    chief-ray aiming, and clear apertures from boundary rays unless the file fixes them with
+    DIAM records of type 1 / 4 / 6, zmxread.py:247-249,399-440)."""
     title = ''
     pupil = None
     wvls, wts = [], []
@@ -119,6 +122,7 @@ def open_zmx(path, glass_map=None):
             cur.setdefault('xdat', {})[int(items[0])] = float(items[1])
         elif cmd == 'DIAM':
             cur['diam'] = float(items[0])
+            cur['diam_type'] = int(float(items[1])) if len(items) > 1 else 0
     if len(surfs) < 2:
         raise ValueError(f'{path}: no surfaces')
     if wvls and len(wvls) > 1 and wvls[-1] == 550.0:       # zmxread.py:251-254
@@ -173,6 +177,8 @@ def open_zmx(path, glass_map=None):
         ifc.decenter = decenter
         if s['diam'] is not None and s['diam'] != 0.0:
             ifc.max_aperture = s['diam']
+            if s.get('diam_type', 0) == 2:          # circular obscuration (zmxread.py:416-417)
+                ifc.clear_apertures = [M.Circular(radius=s['diam'], is_obscuration=True)]
         if s['stop']:
             stop_surface = i
         ifcs.append(ifc)
@@ -212,6 +218,11 @@ def open_zmx(path, glass_map=None):
     opm = M.OpticalModel(sm, osp, name=title or str(path).rsplit('/', 1)[-1])
     from .seq import apply_wide_angle_rule
     apply_wide_angle_rule(opm)
+    # zmxread.py:247-249: DIAM records of a user-defined kind (1 circular, 4 rectangular, 6 elliptical)
+    # turn the automatic apertures off; Zemax' own semi-diameters (kind 0) are start values only
+    sm.do_apertures = not any(s_.get('diam_type', 0) in (1, 4, 6) for s_ in surfs)
+    if do_update:
+        opm.update_optical_properties(bundle_fn)
     return opm
 
 

@@ -7,6 +7,8 @@ reference's own trace_raw on start rays built by opticalspec.ray_start_from_osp
 (skipped without /root/reference) and from the golden OPD vectors.  The GPU run of the
 same calls is in tests/test_zz_gpu_additions.py.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -1142,3 +1144,81 @@ def test_aim_point_and_aim_direction_pupils(name):
     res = TR.trace_pupil_rays(b, pupils, fb, wvl, None, 'full', pupil_type=ptype,
                               bundle_tracer=oracle_bundle_tracer)
     assert len(res) == 3 and all(r.pkg is not None for r in res)
+
+
+def test_post_import_update_sets_aims_and_apertures():
+    """OpticalModel.update_optical_properties -- the ray-traced part of the reference's post-import
+    update_model (opticalmodel.py:318-354, cmdproc.py:85-94, zmxread.py:247-249): chief rays
+    aimed at the stop centre; a file without aperture data gets clear apertures from the boundary
+    rays (the stop from the axial bundle), a file with some CIR records keeps those and gets the
+    rest; DIAM kinds decide for .zmx files."""
+    from rayoptics_b200 import seq, zmx, vigcalc as V
+    sample = os.path.join(os.path.dirname(__file__), 'golden', 'samples', 'triplet_fict.seq')
+    lines = open(sample).read().splitlines()
+    tmp_dir = os.path.dirname(sample)
+    path, part_path = os.path.join(tmp_dir, '_tmp_nocir.seq'), sample
+    try:
+        open(path, 'w').write(chr(10).join(ln for ln in lines if 'CIR' not in ln))
+        raw = seq.open_seq(path)
+        sm0 = raw.seq_model
+        assert sm0.do_apertures and sm0.input_ca_list is None
+        assert all(ifc.max_aperture == 1.0 for ifc in sm0.ifcs)
+        opm = seq.open_seq(path)
+        n_set = opm.update_optical_properties(oracle_bundle_fn(opm))
+        sm, osp = opm.seq_model, opm.optical_spec
+        assert n_set >= sm.get_num_surfaces() - 2
+        wvl = sm.central_wavelength()
+        for fld in osp.field_of_view.fields:                      # aimed: the chief ray hits the stop centre
+            pkg = TR.trace_base(opm, np.array([0., 0.]), fld, wvl, tracer=oracle_tracer)
+            assert np.abs(pkg[0][sm.stop_surface][0][:2]).max() < 1e-6      # object at 1e10: start-ray rounding
+        heights = np.zeros(sm.get_num_surfaces())
+        for fld in osp.field_of_view.fields:                      # every boundary ray passes, some graze
+            for pr in osp.pupil.pupil_rays:
+                pkg = TR.trace_base(opm, np.array(pr, dtype=float), fld, wvl, tracer=oracle_tracer,
+                                    check_apertures=True)
+                for i, seg in enumerate(pkg[0]):
+                    heights[i] = max(heights[i], np.hypot(seg[0][0], seg[0][1]))
+        for i, ifc in enumerate(sm.ifcs[1:-1], start=1):
+            if i != sm.stop_surface:
+                assert abs(ifc.max_aperture - heights[i]) < 1e-9
+        # the same through the reader's do_update switch
+        again = seq.open_seq(path, do_update=True, bundle_fn=oracle_bundle_fn(seq.open_seq(path)))
+        assert [i.max_aperture for i in again.seq_model.ifcs] == [i.max_aperture for i in sm.ifcs]
+    finally:
+        os.path.exists(path) and os.remove(path)
+    # the sample itself has a CIR record on interface 2: it stays, the others are set
+    part = seq.open_seq(part_path)
+    assert not part.seq_model.do_apertures and part.seq_model.input_ca_list == [2]
+    part.update_optical_properties(oracle_bundle_fn(part))
+    assert part.seq_model.ifcs[2].max_aperture == 9.0
+    assert all(ifc.max_aperture != 1.0 for ifc in part.seq_model.ifcs[1:-1])
+    # a model that stores its apertures (the mirror's own JSON) is left alone
+    own = load_model('triplet')
+    before = [i.max_aperture for i in own.seq_model.ifcs]
+    assert own.update_optical_properties(oracle_bundle_fn(own)) == 0
+    assert [i.max_aperture for i in own.seq_model.ifcs] == before
+    # Zemax: DIAM kind 0 (automatic semi-diameters) leaves the automatic apertures on
+    root = '/root/reference/src/rayoptics/zemax/tests'
+    if os.path.isdir(root):
+        z = zmx.open_zmx(f'{root}/US05831776-1.zmx', glass_map=seq.SubstituteGlasses())
+        assert z.seq_model.do_apertures in (True, False) and z.seq_model.ifcs[1].max_aperture != 1.0
+
+
+@needs_ref
+def test_set_max_aperture_resizes_clear_apertures_like_the_reference():
+    """Surface.set_max_aperture (elem/surface.py:174-179): clear apertures follow, obscurations do not"""
+    from oracle import ref_harness as rh
+    from rayoptics_b200 import model as M
+    S = rh.ref().surface
+    own = M.Surface(clear_apertures=[M.Circular(radius=3.0), M.Rectangular(2.0, 1.0, x_offset=0.5),
+                                      M.Circular(radius=0.4, is_obscuration=True)])
+    ref = S.Surface()
+    ref.clear_apertures = [S.Circular(radius=3.0), S.Rectangular(x_half_width=2.0, y_half_width=1.0, x_offset=0.5),
+                           S.Circular(radius=0.4, is_obscuration=True)]
+    own.set_max_aperture(5.25)
+    ref.set_max_aperture(5.25)
+    assert own.max_aperture == ref.max_aperture == 5.25
+    assert (own.clear_apertures[0].radius, own.clear_apertures[2].radius) == \
+           (ref.clear_apertures[0].radius, ref.clear_apertures[2].radius) == (5.25, 0.4)
+    assert (own.clear_apertures[1].x_half_width, own.clear_apertures[1].y_half_width) == \
+           (ref.clear_apertures[1].x_half_width, ref.clear_apertures[1].y_half_width) == (5.25, 5.25)
