@@ -1077,7 +1077,7 @@ class OpticalModel:
         if self.optical_spec is not None:
             self.optical_spec.update_model(**kwargs)
 
-    def update_optical_properties(self, bundle_fn=None, do_aiming=None):
+    def update_optical_properties(self, bundle_fn=None, do_aiming=None, trace_fn=None):
         """The ray-traced part of the reference's ``OpticalModel.update_model`` (optical/
         opticalmodel.py:318-354), which its importers run after reading a lens file: first-order data,
         chief-ray aiming of every field (``OpticalSpecs.update_optical_properties``,
@@ -1085,8 +1085,8 @@ class OpticalModel:
         (``seq_model.do_apertures``) or only some do (``input_ca_list``, cmdproc.py:88-94) --
         clear apertures from the boundary rays of all fields (sequential.py:670-674).  All rays go
         through bundles (``vigcalc.aim_all_fields_batched`` / ``set_clear_apertures_batched``);
-        ``bundle_fn``: test seam, default the CUDA engine.  Returns the number of interfaces whose
-        aperture was set."""
+        ``bundle_fn`` (and ``trace_fn``, single rays of the wide-angle pupil search): test seams,
+        default the CUDA engine.  Returns the number of interfaces whose aperture was set."""
         from . import vigcalc
         self.update_model()
         sm, osp = self.seq_model, self.optical_spec
@@ -1095,7 +1095,7 @@ class OpticalModel:
         if bundle_fn is None:
             bundle_fn = vigcalc.cuda_bundle_fn(self)
         if osp.do_aiming if do_aiming is None else do_aiming:
-            vigcalc.aim_all_fields_batched(self, bundle_fn)
+            vigcalc.aim_all_fields_batched(self, bundle_fn, trace_fn=trace_fn)
         given = list(sm.input_ca_list or [])
         if not (sm.do_apertures or given):
             return 0

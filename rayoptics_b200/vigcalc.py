@@ -220,7 +220,7 @@ def _start_rays(opt_model, fields, aims, pupils):
     return p0, d0
 
 
-def aim_all_fields_batched(opt_model, bundle_fn=None, wvl=None, tol=1e-13, max_iter=30):
+def aim_all_fields_batched(opt_model, bundle_fn=None, wvl=None, tol=1e-13, max_iter=30, trace_fn=None):
     """``aim_chief_ray`` for every field at once (raytr/trace.py:313-415,627-640): each
     Newton iteration traces base + two finite-difference rays of ALL fields in one bundle,
     each backtracking round one more.  Same iteration as ``aim_chief_ray`` field by field,
@@ -235,7 +235,7 @@ def aim_all_fields_batched(opt_model, bundle_fn=None, wvl=None, tol=1e-13, max_i
         return [f.aim_info for f in fields]
     if _wide(opt_model):        # wide-angle fields: z_enp search on single rays (wideangle.py)
         from . import wideangle
-        return wideangle.aim_wide_angle_fields(opt_model, wvl)
+        return wideangle.aim_wide_angle_fields(opt_model, wvl, trace_fn)
     if bundle_fn is None:
         bundle_fn = cuda_bundle_fn(opt_model)
     wvl = osp.spectral_region.central_wvl if wvl is None else wvl
