@@ -747,6 +747,84 @@ def set_vig_batched(opm, ray_fn=None, wvl=None, max_iter_count=50):
     return launches
 
 
+# --- the bisection search as ONE launch ------------------------------------------------------
+def cuda_tile_fn(opt_model, table=None, device=0):
+    """``tile_fn(fields, wvl, px, py, **trace options) -> dict(status, fail_surf)``: the pupil points
+    ``(px[k], py[k])`` (unvignetted, shared by all fields) of every field in one grid launch"""
+    from . import engine as E
+    from .analyses import _table_for
+    from .opticalspec import grid_fields_of
+    tab = _table_for(opt_model, table, device)
+    sm = opt_model.seq_model
+
+    def fn(fields, wvl, px, py, **opts):
+        recs, eprad, z_pupil = grid_fields_of(opt_model, fields)
+        grid = E.PupilGrid(recs, [tab.wvl_index(wvl)], px, py, eprad, z_pupil, apply_vignetting=False,
+                           flip_z_dir=sm.z_dir[0], paired=True, device=tab.device)
+        res = E.trace_grid(tab, grid, outputs=('status', 'fail_surf'), summary=False, **opts)
+        out = {'status': res.status.cpu().numpy(), 'fail_surf': res.fail_surf.cpu().numpy()}
+        grid.close()
+        return out
+    return fn
+
+
+def bisection_tree(start_dir, levels):
+    """Every pupil position ``calc_vignetted_ray_by_bisection`` can visit in ``levels`` halvings,
+    in heap order (node i: blocked -> child 2i+1, passed -> child 2i+2), built with the search's own
+    update expression so the doubles are the ones it would compute; the last level (never traced)
+    holds the possible end positions.  ``[2**(levels+1) - 1, 2]``."""
+    sd = np.array(start_dir, dtype=float)
+    nodes = np.zeros((2**(levels + 1) - 1, 2))
+    nodes[0] = sd
+    step, first = 1.0, 0
+    for level in range(levels):
+        step /= 2
+        for i in range(first, first + 2**level):
+            nodes[2*i + 1] = -step*sd + nodes[i]
+            nodes[2*i + 2] = step*sd + nodes[i]
+        first += 2**level
+    return nodes
+
+
+def set_vig_by_bisection(opm, tile_fn=None, wvl=None, levels=10):
+    """Vignetting factors of all fields by the bisection search (``calc_vignetted_ray_by_bisection``,
+    vigcalc.py:347-390) in ONE launch: the search halves its step a fixed number of times, so the
+    pupil positions it can visit form a binary tree known beforehand (2**levels - 1 per pupil
+    direction); all of them, for the four directions of every field, are traced together
+    (status only, 8 B per ray) and each search becomes a walk down its tree of results.  Same
+    factors as the sequential search.  Sets ``vux, vlx, vuy, vly``; returns the limiting
+    interface of every (field, direction)."""
+    osp, sm = opm.optical_spec, opm.seq_model
+    if tile_fn is None:
+        tile_fn = cuda_tile_fn(opm)
+    wvl = osp.spectral_region.central_wvl if wvl is None else wvl
+    fields = list(osp.field_of_view.fields)
+    starts = [np.array(sd, dtype=float) for sd in osp.pupil.pupil_rays[1:]]
+    trees = [bisection_tree(sd, levels) for sd in starts]
+    n_traced = 2**levels - 1
+    px = np.concatenate([t[:n_traced, 0] for t in trees])
+    py = np.concatenate([t[:n_traced, 1] for t in trees])
+    r = tile_fn(fields, wvl, px, py, check_apertures=True, pt_inside_fuzz=1e-4)
+    status = np.asarray(r['status']).reshape(len(fields), 4, n_traced)
+    surf = np.asarray(r['fail_surf']).reshape(len(fields), 4, n_traced)
+    clips = {}
+    for fi, fld in enumerate(fields):
+        vig = [0.]*4
+        for di in range(4):
+            node, clip = 0, None
+            for _ in range(levels):
+                if status[fi, di, node] != 0:
+                    clip = int(surf[fi, di, node])
+                    node = 2*node + 1
+                else:
+                    node = 2*node + 2
+            xy = di//2
+            vig[di] = 1.0 - (trees[di][node][xy]/starts[di][xy])
+            clips[(fi, di)] = clip
+        fld.vux, fld.vlx, fld.vuy, fld.vly = vig
+    return clips
+
+
 # --- the reference's own aiming iteration (raytr/trace.py:313-415) ----------------------------
 def iterate_ray(opt_model, ifcx, xy_target, fld, wvl, trace_fn=None, full=False):
     """Iterate a ray to ``xy_target`` on interface ``ifcx``; returns the aim point on the

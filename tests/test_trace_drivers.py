@@ -1222,3 +1222,54 @@ def test_set_max_aperture_resizes_clear_apertures_like_the_reference():
            (ref.clear_apertures[0].radius, ref.clear_apertures[2].radius) == (5.25, 0.4)
     assert (own.clear_apertures[1].x_half_width, own.clear_apertures[1].y_half_width) == \
            (ref.clear_apertures[1].x_half_width, ref.clear_apertures[1].y_half_width) == (5.25, 5.25)
+
+
+def oracle_tile_fn(opm):
+    """tile_fn= seam of vigcalc.set_vig_by_bisection fed by the oracle's grid path"""
+    from oracle import rt_oracle
+    sm, osp = opm.seq_model, opm.optical_spec
+    descs, n_by_wvl, wvls = T.describe_model(sm)
+
+    def fn(fields, wvl, px, py, **opts):
+        recs, eprad, z_pupil = osp.grid_fields(fields)
+        spec = E.PupilGridSpec(recs, [sm.index_for_wavelength(wvl)], px, py, eprad, z_pupil,
+                               apply_vignetting=False, flip_z_dir=sm.z_dir[0], paired=True)
+        o = dict(first_surf=1, last_surf=len(descs) - 2)
+        o.update(opts)
+        return rt_oracle.trace_grid(spec.c_spec(), descs, n_by_wvl, 0, spec.n_rays, _abi.make_opts(**o),
+                                    n_threads=4, wvls=wvls)
+    return fn
+
+
+@pytest.mark.parametrize('name', ['dblgauss', 'triplet', 'evenasph', 'rc'])
+def test_bisection_vignetting_in_one_launch(name):
+    """vigcalc.set_vig_by_bisection (the whole bisection tree of every field and pupil direction
+    traced at once) against the sequential calc_vignetted_ray_by_bisection (equal to the
+    reference's, test_set_pupil_and_bisection_equal_the_references): same factors, same limiting
+    interfaces; the tree holds exactly the positions the search visits."""
+    from rayoptics_b200 import vigcalc as V
+    a, b = load_model(name), load_model(name)
+    for m in (a, b):
+        for ifc in m.seq_model.ifcs[1:-1]:
+            ifc.set_max_aperture(0.93*ifc.max_aperture)          # so that something limits every direction
+        for f in m.optical_spec.field_of_view.fields:
+            f.clear_vignetting()
+    wvl = a.seq_model.central_wavelength()
+    starts = a.optical_spec.pupil.pupil_rays[1:]
+    want, want_clip = [], {}
+    for fi, fld in enumerate(a.optical_spec.field_of_view.fields):
+        row = []
+        for di in range(4):
+            vig, clip, _ = V.calc_vignetted_ray_by_bisection(a, di//2, np.array(starts[di], dtype=float), fld, wvl,
+                                                             tracer=oracle_tracer)
+            row.append(vig)
+            want_clip[(fi, di)] = clip
+        want.append(row)
+    clips = V.set_vig_by_bisection(b, oracle_tile_fn(b))
+    got = [[f.vux, f.vlx, f.vuy, f.vly] for f in b.optical_spec.field_of_view.fields]
+    assert got == want and clips == want_clip
+    assert any(v > 0.01 for row in got for v in row)
+    tree = V.bisection_tree([0., -1.], 10)
+    assert tree.shape == (2047, 2) and tree[0].tolist() == [0., -1.]
+    assert tree[1].tolist() == [0., -0.5] and tree[2].tolist() == [0., -1.5]      # blocked / passed
+    assert np.all(tree[:, 0] == 0) and len(set(tree[1023:, 1])) == 1024
