@@ -215,6 +215,18 @@ def reflect(d_in, normal):
     return d_out
 
 
+def phase(ifc, inc_pt, d_in, normal, ifc_cntxt):
+    """diffracted direction and phase at an interface with a phase element (raytrace.py:41-48): the
+    interface's own ``phase`` method does the work (the reference's interfaces have one; in the
+    kernels the same arithmetic is ``hoe_phase`` / ``grating_phase`` / ``radial_doe_phase``), an
+    evanescent order -- a ``ValueError`` there -- becomes the trace error"""
+    try:
+        return ifc.phase(inc_pt, d_in, normal, ifc_cntxt)
+    except ValueError:
+        z_dir, wvl, n_in, n_out, interact_mode = ifc_cntxt
+        raise TraceEvanescentRayError(ifc, inc_pt, d_in, normal, n_in, n_out)
+
+
 def calc_optical_path(ray, path):
     """optical path between the first and last optical surfaces (raytrace.py:267-293)"""
     num_items = len(ray)

@@ -174,6 +174,16 @@ def eic_distance(r, r0):
     return e
 
 
+def ray_dist_to_perp_from_pt(r, pt):
+    """distance along the ray ``r = (p, d)`` to the foot of the perpendicular from ``pt`` (waveabr.py:135-148)"""
+    return np.dot(r[1], (pt - r[0]))
+
+
+def ray_dist_to_perp_from_origin(r):
+    """the same for the origin (waveabr.py:151-161)"""
+    return np.dot(r[1], -r[0])
+
+
 def dist_to_shortest_join(r1, r2):
     """points (and distances) of the closest join of two rays, waveabr.py:163-187"""
     p1, d1 = r1
