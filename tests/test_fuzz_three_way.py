@@ -87,7 +87,7 @@ def same(a, b):
 
 
 @pytest.mark.parametrize('lean', [0, 1, 2])
-@pytest.mark.parametrize('seed', range(40))
+@pytest.mark.parametrize('seed', range(100))
 def test_random_system_three_way(oracle, seed, lean):
     rng = np.random.default_rng(1000 + seed + 100000*lean)
     segs = random_system(rng, lean)
@@ -156,7 +156,7 @@ def add_phase_elements(rng, segs):
                 obj_virtual=bool(rng.random() < 0.5), ref_wl=float(rng.uniform(450, 650)))
 
 
-@pytest.mark.parametrize('seed', range(30))
+@pytest.mark.parametrize('seed', range(60))
 def test_random_phase_systems_three_way(oracle, seed):
     """the same with diffractive phase elements: reference == oracle bit for bit (same libm);
     device source == oracle in status / failing surface / segment counts, coordinates within
