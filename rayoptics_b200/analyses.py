@@ -17,6 +17,8 @@ chief-ray image point at the central wavelength.
 """
 from __future__ import annotations
 
+import threading
+
 import numpy as np
 import torch
 
@@ -80,8 +82,18 @@ class SpotDiagram:
 
 
 _STREAMS = {}
-_GRIDS = {}          # shape key -> PupilGrid whose device block / pinned staging is re-used
-_WORK = {}           # device -> re-used device staging buffers of spot_diagram
+# Re-used device blocks are per THREAD: two threads running analyses on one device must not share a
+# grid block (one would trace the other's description) or staging buffers.  Tables are immutable and
+# stay shared (SURVEY.md 8(b) "Threading").
+_TLS = threading.local()
+
+
+def _per_thread(name):
+    d = getattr(_TLS, name, None)
+    if d is None:
+        d = {}
+        setattr(_TLS, name, d)
+    return d
 
 
 def _side_streams(dev):
@@ -121,13 +133,14 @@ def _reusable_grid(opt_model, table, num_rays, fields, wvls, foc):
         hit = _SPECS[key] = (spec, args, kw)
     spec, args, kw = hit
     gkey = (int(table.device), spec.n_fields, spec.n_wvls, spec.nx, spec.ny, spec.paired, spec.wave is not None)
-    grid = _GRIDS.get(gkey)
+    grids = _per_thread('grids')     # shape key -> PupilGrid whose device block / pinned staging is re-used
+    grid = grids.get(gkey)
     if grid is None or grid._handle is None:
-        if len(_GRIDS) > 16:
-            for g in _GRIDS.values():
+        if len(grids) > 16:
+            for g in grids.values():
                 g.close()
-            _GRIDS.clear()
-        grid = _GRIDS[gkey] = E.PupilGrid(*args, device=table.device, **kw)
+            grids.clear()
+        grid = grids[gkey] = E.PupilGrid(*args, device=table.device, **kw)
     else:
         grid.upload(spec)
     return grid, spec
@@ -201,7 +214,7 @@ def spot_diagram(opt_model, num_rays=21, fields=None, wvls=None, foc=None, table
     with torch.cuda.device(dev):
         grid, spec = _reusable_grid(opt_model, table, num_rays, fields, wvls, foc)
         io['h2d'] += spec.host_bytes()
-        ws = _WORK.setdefault(table.device, {})
+        ws = _per_thread('work').setdefault(table.device, {})     # re-used device staging buffers
         if ws.get('ref') is None or ws['ref'].shape[0] != len(fields):
             ws['ref'] = torch.empty((len(fields), 2), dtype=torch.float64, device=dev)
         ref_dev = ws['ref']

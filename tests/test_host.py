@@ -818,3 +818,44 @@ def test_importers_apply_the_wide_angle_rule(tmp_path):
         b = zmx.open_zmx(f'{root}/US05831776-1.zmx', **kw).optical_spec      # real heights, finite object
         assert a.field_of_view.is_wide_angle and not b.field_of_view.is_wide_angle
         assert a.conjugate_type('object') == 'infinite' and b.conjugate_type('object') == 'finite'
+
+
+def test_reused_grid_blocks_are_per_thread(monkeypatch):
+    """analyses._reusable_grid: within a thread the device block of a grid shape is re-used
+    (upload, no allocation); another thread gets its own block -- two threads running analyses on
+    one device must not trace each other's grid description.  (Device grid replaced by a host
+    stand-in: only the cache policy is under test.)"""
+    import threading
+    from rayoptics_b200 import analyses as A, engine as E
+
+    class FakeGrid(E.PupilGridSpec):
+        made = 0
+
+        def __init__(self, *a, device=0, **k):
+            super().__init__(*a, **k)
+            self.device, self._handle, self.uploads = device, object(), 0
+            FakeGrid.made += 1
+
+        def upload(self, spec):
+            self.uploads += 1
+
+        def close(self):
+            self._handle = None
+    monkeypatch.setattr(E, 'PupilGrid', FakeGrid)
+    opm = load_model('dblgauss')
+    descs, n_by_wvl, wvls = T.describe_model(opm.seq_model)
+    tab = type('Tab', (), {'device': 0, 'wvl_index': lambda self, w: wvls.index(w)})()
+    fields, wv = list(opm.optical_spec.field_of_view.fields), list(opm.seq_model.wvlns)
+    seen = {}
+
+    def work(tag):
+        g1, _ = A._reusable_grid(opm, tab, 16, fields, wv, 0.0)
+        g2, _ = A._reusable_grid(opm, tab, 16, fields, wv, 0.125)      # same shape, other contents
+        seen[tag] = (g1, g2, g2.uploads)
+    work('main')
+    t = threading.Thread(target=work, args=('other',))
+    t.start()
+    t.join()
+    assert seen['main'][0] is seen['main'][1] and seen['main'][2] == 1
+    assert seen['other'][0] is seen['other'][1] and seen['other'][0] is not seen['main'][0]
+    assert FakeGrid.made == 2
