@@ -125,7 +125,8 @@ def _same_tuple(a, b):
 
 
 @pytest.mark.parametrize('name,fi,wvl', [('dblgauss', 2, 656.3), ('telecentric', 1, 587.6),
-                                         ('threemir', 1, None)])
+                                         ('threemir', 1, None), ('cellphone', 4, None), ('fisheye', 3, None),
+                                         ('rc', 2, None), ('evenasph', 5, None)])
 def test_trace_then_focus_equal_the_references(name, fi, wvl):
     """trace_fan / focus_fan, trace_pupil_coords / focus_pupil_coords, trace_wavefront /
     focus_wavefront (the two-stage forms used for rapid refocus): same traced packages, same
