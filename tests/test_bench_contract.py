@@ -93,3 +93,14 @@ def test_b200_arm_two_ranks_on_the_dry_run_engine():
         c = line['collectives']            # 3 steps, default --gather-every 8: one all-gather for all of them
         assert c == {'all_gathers_in_timed_region': 1, 'steps_per_all_gather': 3,
                      'payload_bytes_per_rank_per_gather': 3*9*16*8, 'last_combined_ok': True}
+
+
+def test_default_engine_paths_of_the_new_host_functions():
+    """tests/dry_api.py: one-launch bisection, batched set_vig, post-import update, 'aim pt' pupils, the
+    two-stage analyses, astigmatism / Coddington, real image heights (reverse path through the drop-in
+    trace_raw), wide-angle aiming, set_pupil -- each through its default (engine) code path on the
+    dry-run stand-in."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'dry_api.py')], capture_output=True, text=True,
+                       timeout=900, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-3000:]
+    assert 'ALL DEFAULT-ENGINE PATHS OK' in p.stdout
